@@ -1,0 +1,142 @@
+"""ctypes mirror of include/fountain_gpu.h (struct layouts and function prototypes).
+
+One definition serves both shared libraries that speak this ABI: the product
+(`libfountain_gpu.so`, prefix ``ftn_``) and the test oracle (prefix ``orc_``), which is
+bound from ``oracle/orc.py`` -- never from this package.
+"""
+import ctypes as C
+
+FTN_ABI_VERSION = 1
+FTN_NO_HIT = 0xFFFFFFFF
+
+FTN_OK = 0
+FTN_ERR_INVALID_ARGUMENT = -1
+FTN_ERR_CUDA = -2
+FTN_ERR_NO_DEVICE = -3
+FTN_ERR_NAN_RADIANCE = -4
+FTN_ERR_UNSUPPORTED = -5
+FTN_ERR_OUT_OF_MEMORY = -6
+
+FTN_MESH_FLIP_NORMALS = 1
+FTN_MATERIAL_MATTE, FTN_MATERIAL_METAL, FTN_MATERIAL_PLASTIC = 0, 1, 2
+FTN_LIGHT_INFINITE = 0
+FTN_SAMPLER_COUNTER, FTN_SAMPLER_REFERENCE_TILE_STREAM = 0, 1
+FTN_INTEGRATOR_PATH, FTN_INTEGRATOR_DIRECT_LIGHTING = 0, 1
+
+f32 = C.c_float
+u32 = C.c_uint32
+i32 = C.c_int32
+u64 = C.c_uint64
+
+
+class FtnRay(C.Structure):
+    _fields_ = [("o", f32 * 3), ("d", f32 * 3), ("t_max", f32), ("time", f32)]
+
+
+class FtnHit(C.Structure):
+    _fields_ = [("prim", u32), ("t", f32), ("b1", f32), ("b2", f32)]
+
+
+class FtnMeshDesc(C.Structure):
+    _fields_ = [("first_tri", u32), ("n_tris", u32), ("material_id", i32), ("flags", u32)]
+
+
+class FtnMaterial(C.Structure):
+    _fields_ = [("type", i32), ("kd", f32 * 3), ("ks", f32 * 3), ("eta", f32 * 3), ("k", f32 * 3),
+                ("u_roughness", f32), ("v_roughness", f32), ("remap_roughness", i32)]
+
+
+class FtnSphere(C.Structure):
+    _fields_ = [("object_to_world", f32 * 16), ("world_to_object", f32 * 16), ("radius", f32),
+                ("z_min", f32), ("z_max", f32), ("phi_max_deg", f32), ("reverse_orientation", i32),
+                ("material_id", i32), ("emissive", i32), ("emit", f32 * 3)]
+
+
+class FtnLight(C.Structure):
+    _fields_ = [("type", i32), ("texels", C.POINTER(f32)), ("width", i32), ("height", i32),
+                ("light_to_world", f32 * 16), ("world_to_light", f32 * 16)]
+
+
+class FtnSceneDesc(C.Structure):
+    _fields_ = [("abi_version", u32), ("positions", C.POINTER(f32)), ("normals", C.POINTER(f32)),
+                ("uvs", C.POINTER(f32)), ("n_vertices", u32), ("indices", C.POINTER(u32)),
+                ("n_triangles", u32), ("meshes", C.POINTER(FtnMeshDesc)), ("n_meshes", u32),
+                ("spheres", C.POINTER(FtnSphere)), ("n_spheres", u32),
+                ("materials", C.POINTER(FtnMaterial)), ("n_materials", u32),
+                ("lights", C.POINTER(FtnLight)), ("n_lights", u32)]
+
+
+class FtnCamera(C.Structure):
+    _fields_ = [("camera_to_world", f32 * 16), ("raster_to_camera", f32 * 16), ("lens_radius", f32),
+                ("focal_distance", f32), ("shutter_open", f32), ("shutter_close", f32)]
+
+
+class FtnFilm(C.Structure):
+    _fields_ = [("x_resolution", i32), ("y_resolution", i32), ("crop_window", f32 * 4),
+                ("filter_radius", f32 * 2)]
+
+
+class FtnSampler(C.Structure):
+    _fields_ = [("samples_per_pixel", i32), ("seed", u64), ("mode", i32), ("sample_begin", i32),
+                ("sample_stride", i32)]
+
+
+class FtnIntegrator(C.Structure):
+    _fields_ = [("type", i32), ("max_depth", i32), ("rr_threshold", f32)]
+
+
+class FtnPixel(C.Structure):
+    _fields_ = [("xyz", f32 * 3), ("filter_weight_sum", f32)]
+
+
+class FtnStats(C.Structure):
+    _fields_ = [("camera_samples", u64), ("rays_closest", u64), ("rays_any", u64), ("node_visits", u64),
+                ("tri_tests", u64), ("kernel_launches", u64), ("device_seconds", C.c_double),
+                ("bvh_build_seconds", C.c_double), ("bvh_nodes", u32), ("bvh_node_bytes", u32),
+                ("bvh_tri_bytes", u32), ("reserved", u32)]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+VOIDP = C.c_void_p
+P = C.POINTER
+
+# name (without prefix) -> (restype, argtypes).  Exactly the symbols fountain_gpu.h declares.
+PROTOTYPES = {
+    "abi_version": (u32, []),
+    "last_error": (C.c_char_p, []),
+    "device_count": (C.c_int, [P(C.c_int)]),
+    "set_device": (C.c_int, [C.c_int]),
+    "kernel_launch_count": (u64, []),
+    "scene_create": (C.c_int, [P(FtnSceneDesc), P(VOIDP)]),
+    "scene_destroy": (C.c_int, [VOIDP]),
+    "bvh_build": (C.c_int, [VOIDP]),
+    "bvh_debug_morton": (C.c_int, [VOIDP, P(u32), P(u32)]),
+    "scene_world_bound": (C.c_int, [VOIDP, P(f32)]),
+    "scene_stats": (C.c_int, [VOIDP, P(FtnStats)]),
+    "intersect": (C.c_int, [VOIDP, C.c_size_t, P(FtnRay), P(FtnHit)]),
+    "intersect_test": (C.c_int, [VOIDP, C.c_size_t, P(FtnRay), P(C.c_uint8)]),
+    "intersect_device": (C.c_int, [VOIDP, C.c_size_t, VOIDP, VOIDP, VOIDP]),
+    "intersect_test_device": (C.c_int, [VOIDP, C.c_size_t, VOIDP, VOIDP, VOIDP]),
+    "intersect_count_device": (C.c_int, [VOIDP, C.c_size_t, VOIDP, VOIDP, VOIDP, VOIDP]),
+    "render": (C.c_int, [VOIDP, P(FtnCamera), P(FtnFilm), P(FtnSampler), P(FtnIntegrator), P(FtnPixel), P(FtnStats)]),
+    "render_device": (C.c_int, [VOIDP, P(FtnCamera), P(FtnFilm), P(FtnSampler), P(FtnIntegrator), VOIDP, P(FtnStats), VOIDP]),
+    "film_to_rgb_device": (C.c_int, [C.c_size_t, VOIDP, VOIDP, VOIDP]),
+    "film_pixel_count": (C.c_int, [P(FtnFilm), P(i32), P(i32)]),
+}
+
+# Subset the CPU oracle implements (host buffers only), plus its own extras bound in oracle/orc.py.
+ORACLE_SUBSET = ("abi_version", "last_error", "scene_create", "scene_destroy", "bvh_build",
+                 "bvh_debug_morton", "scene_world_bound", "scene_stats", "intersect", "intersect_test",
+                 "render", "film_pixel_count")
+
+
+def bind(lib, prefix, names):
+    """Attach restype/argtypes for `names` and return {name: function}."""
+    out = {}
+    for name in names:
+        fn = getattr(lib, prefix + name)   # AttributeError if the symbol is missing: fail loudly
+        fn.restype, fn.argtypes = PROTOTYPES[name]
+        out[name] = fn
+    return out

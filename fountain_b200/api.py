@@ -1,0 +1,544 @@
+"""Host-side mirror of the reference's Scene / Primitive / Camera / Sampler / Film / Integrator
+API for the hot path, written above the C ABI (include/fountain_gpu.h).
+
+The reference is Rust and its toolchain is absent here, so this mirror is Python (what the
+tests and bench drive) with a C++ twin in include/fountain_host.hpp; the Rust binding a
+fountain maintainer would add is in INTEGRATION.md.  Names, argument meaning and error
+behaviour follow the reference:
+
+  TriangleMesh::new             src/shapes/triangle.rs:29      -> TriangleMesh
+  Sphere::new                   src/shapes/sphere.rs:30        -> Sphere
+  MatteMaterial / MetalMaterial src/material/{matte,metal}.rs  -> MatteMaterial, MetalMaterial
+  InfiniteAreaLight::new_*      src/light/infinite.rs:23,42    -> InfiniteAreaLight
+  Scene::new / BVH::build       src/scene/mod.rs:32, bvh.rs:27 -> Scene
+  Scene::intersect(_test)       src/scene/mod.rs:51,55         -> Scene.intersect / intersect_test (batched)
+  PerspectiveCamera::new        src/camera/mod.rs:85           -> PerspectiveCamera
+  Film::new / into_spectrum_buffer  src/film.rs:43,195         -> Film
+  RandomSampler::new_with_seed  src/sampler/random.rs:12       -> RandomSampler
+  PathIntegrator::new           src/integrator/path.rs:16      -> PathIntegrator
+  SamplerIntegrator::render_parallel  src/integrator/mod.rs:218 -> SamplerIntegrator.render_parallel
+
+Every compute call goes through a `Backend` (a bound shared library).  The default backend is
+the CUDA library; it raises if the extension or a GPU is missing -- there is no CPU path here.
+"""
+import ctypes as C
+import numpy as np
+
+from . import _abi as A
+from .transform import Transform
+
+
+class FountainError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("fountain error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Backend:
+    """A shared library speaking the fountain_gpu.h ABI under `prefix`."""
+
+    def __init__(self, lib, prefix, names, name):
+        self.lib = lib
+        self.prefix = prefix
+        self.name = name
+        self.fn = A.bind(lib, prefix, names)
+
+    def call(self, fname, *args):
+        rc = self.fn[fname](*args)
+        if rc != A.FTN_OK:
+            msg = self.fn["last_error"]()
+            raise FountainError(rc, (msg or b"").decode("utf-8", "replace"))
+        return rc
+
+    def has(self, fname):
+        return fname in self.fn
+
+
+_default_backend = None
+
+
+def default_backend():
+    """The CUDA library.  Raises (never falls back) when it cannot be used."""
+    global _default_backend
+    if _default_backend is None:
+        from .lib import load_gpu_backend
+        _default_backend = load_gpu_backend()
+    return _default_backend
+
+
+def _f32(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a if shape is None else a.reshape(shape)
+
+
+def _ptr(a, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+def _spectrum(v):
+    a = np.asarray(v, dtype=np.float32).reshape(-1)
+    return np.repeat(a, 3) if a.size == 1 else a
+
+
+# ---------------------------------------------------------------------------------------------
+# shapes / materials / lights
+# ---------------------------------------------------------------------------------------------
+
+class TriangleMesh:
+    """shapes/triangle.rs:29-74.  Vertices (and normals) are moved to world space here, on the
+    host, exactly as `TriangleMesh::new` does; the device only ever sees world space."""
+
+    def __init__(self, object_to_world, vertex_indices, vertices, normals=None, tex_coords=None,
+                 reverse_orientation=False):
+        idx = np.ascontiguousarray(vertex_indices, dtype=np.uint32).reshape(-1)
+        assert idx.size % 3 == 0                      # triangle.rs:38
+        self.vertex_indices = idx.reshape(-1, 3)
+        self.n_triangles = self.vertex_indices.shape[0]
+        v = _f32(vertices).reshape(-1, 3)
+        self.vertices = object_to_world.apply_points_f32(v)
+        self.normals = None
+        if normals is not None:
+            n = _f32(normals).reshape(-1, 3)
+            assert n.shape[0] == v.shape[0]           # triangle.rs:47
+            self.normals = object_to_world.apply_normals_f32(n)
+        self.tex_coords = None
+        if tex_coords is not None:
+            self.tex_coords = _f32(tex_coords).reshape(-1, 2)
+            assert self.tex_coords.shape[0] == v.shape[0]   # triangle.rs:61
+        self.reverse_orientation = bool(reverse_orientation)
+        self.object_to_world = object_to_world
+
+    def flip_normals(self):                           # shapes/mod.rs:27-29
+        return self.reverse_orientation ^ self.object_to_world.swaps_handedness()
+
+    @staticmethod
+    def from_ply(path, object_to_world=None, reverse_orientation=False):
+        """make_triangle_mesh_from_ply, loaders/constructors.rs:94-190."""
+        from .ply import load_ply
+        d = load_ply(path)
+        return TriangleMesh(object_to_world or Transform.identity(), d["indices"], d["vertices"],
+                            d["normals"], d["uvs"], reverse_orientation)
+
+
+class Sphere:
+    """shapes/sphere.rs:30-58."""
+
+    def __init__(self, object_to_world, reverse_orientation=False, radius=1.0, z_min=None, z_max=None,
+                 phi_max=360.0):
+        self.object_to_world = object_to_world
+        self.reverse_orientation = bool(reverse_orientation)
+        self.radius = float(radius)
+        self.z_min = -self.radius if z_min is None else float(z_min)
+        self.z_max = self.radius if z_max is None else float(z_max)
+        self.phi_max = float(phi_max)
+
+
+class MatteMaterial:
+    """material/matte.rs; constant Kd, sigma = 0 (Lambert).  Default Kd 0.5 (constructors.rs:193)."""
+    type = A.FTN_MATERIAL_MATTE
+
+    def __init__(self, kd=0.5):
+        self.kd = _spectrum(kd)
+
+    def fill(self, m):
+        m.type = self.type
+        m.kd[:] = self.kd.tolist()
+
+
+class MetalMaterial:
+    """material/metal.rs; constant eta/k; roughness default 0.01, remap default true
+    (constructors.rs:213-230)."""
+    type = A.FTN_MATERIAL_METAL
+
+    def __init__(self, eta, k, roughness=0.01, u_roughness=None, v_roughness=None, remap_roughness=True):
+        self.eta = _spectrum(eta)
+        self.k = _spectrum(k)
+        if u_roughness is not None and v_roughness is not None:
+            self.u, self.v = float(u_roughness), float(v_roughness)
+        else:
+            self.u = self.v = float(roughness)
+        self.remap = bool(remap_roughness)
+
+    def fill(self, m):
+        m.type = self.type
+        m.eta[:] = self.eta.tolist()
+        m.k[:] = self.k.tolist()
+        m.u_roughness, m.v_roughness, m.remap_roughness = self.u, self.v, int(self.remap)
+
+
+class PlasticMaterial:
+    """material/plastic.rs; defaults Kd = Ks = 0.25, roughness 0.1 (constructors.rs:232-238)."""
+    type = A.FTN_MATERIAL_PLASTIC
+
+    def __init__(self, kd=0.25, ks=0.25, roughness=0.1, remap_roughness=True):
+        self.kd, self.ks = _spectrum(kd), _spectrum(ks)
+        self.roughness, self.remap = float(roughness), bool(remap_roughness)
+
+    def fill(self, m):
+        m.type = self.type
+        m.kd[:] = self.kd.tolist()
+        m.ks[:] = self.ks.tolist()
+        m.u_roughness = m.v_roughness = self.roughness
+        m.remap_roughness = int(self.remap)
+
+
+class DiffuseAreaLight:
+    """light/diffuse.rs:24-41; attached to a shape through GeometricPrimitive.light."""
+
+    def __init__(self, emit=1.0):
+        self.emit = _spectrum(emit)
+
+
+class InfiniteAreaLight:
+    """light/infinite.rs:23-61."""
+
+    def __init__(self, texels, light_to_world):
+        t = _f32(texels)
+        assert t.ndim == 3 and t.shape[2] == 3, "texels must be (height, width, 3)"
+        self.texels = t
+        self.height, self.width = t.shape[0], t.shape[1]
+        self.light_to_world = light_to_world
+
+    @staticmethod
+    def new_uniform(radiance, light_to_world=None):
+        return InfiniteAreaLight(_spectrum(radiance).reshape(1, 1, 3), light_to_world or Transform.identity())
+
+    @staticmethod
+    def new_envmap(texels, light_to_world=None):
+        return InfiniteAreaLight(texels, light_to_world or Transform.identity())
+
+
+class GeometricPrimitive:
+    """primitive.rs:25-29: a shape (TriangleMesh expands to one primitive per triangle, as
+    PbrtSceneBuilder::shape does, loaders/pbrt.rs:275-317) with its material and area light."""
+
+    def __init__(self, shape, material=None, light=None):
+        self.shape, self.material, self.light = shape, material, light
+
+
+# ---------------------------------------------------------------------------------------------
+# Scene
+# ---------------------------------------------------------------------------------------------
+
+RAY_DTYPE = np.dtype([("o", np.float32, 3), ("d", np.float32, 3), ("t_max", np.float32), ("time", np.float32)])
+HIT_DTYPE = np.dtype([("prim", np.uint32), ("t", np.float32), ("b1", np.float32), ("b2", np.float32)])
+assert RAY_DTYPE.itemsize == 32 and HIT_DTYPE.itemsize == 16
+
+
+def make_rays(origins, dirs, t_max=np.inf, time=0.0):
+    """Ray::new (geometry/mod.rs:98-102) over arrays."""
+    o = _f32(origins).reshape(-1, 3)
+    d = _f32(dirs).reshape(-1, 3)
+    n = max(o.shape[0], d.shape[0])
+    r = np.zeros(n, dtype=RAY_DTYPE)
+    r["o"] = o
+    r["d"] = d
+    r["t_max"] = t_max
+    r["time"] = time
+    return r
+
+
+class Scene:
+    """scene/mod.rs:14-68.  `Scene(primitives, lights)` flattens everything into the SoA
+    `FtnSceneDesc`, uploads it and builds the aggregate (BVH::build, bvh.rs:27)."""
+
+    def __init__(self, primitives, lights=(), backend=None, build=True):
+        self.backend = backend or default_backend()
+        self._handle = A.VOIDP()
+        meshes = [p for p in primitives if isinstance(p.shape, TriangleMesh)]
+        spheres = [p for p in primitives if isinstance(p.shape, Sphere)]
+        materials = []
+
+        def mat_id(m):
+            if m is None:
+                return -1
+            for i, e in enumerate(materials):
+                if e is m:
+                    return i
+            materials.append(m)
+            return len(materials) - 1
+
+        # triangles first (mesh order, tri_id), then spheres: the primitive ids of the ABI
+        vbase = 0
+        pos, nrm, uvs, idx, mdescs = [], [], [], [], []
+        any_normals = any(p.shape.normals is not None for p in meshes)
+        any_uvs = any(p.shape.tex_coords is not None for p in meshes)
+        if meshes and any_normals != all(p.shape.normals is not None for p in meshes):
+            raise ValueError("either every mesh carries normals or none does")
+        if meshes and any_uvs != all(p.shape.tex_coords is not None for p in meshes):
+            raise ValueError("either every mesh carries uvs or none does")
+        first = 0
+        for p in meshes:
+            m = p.shape
+            if p.light is not None:
+                raise NotImplementedError("emissive triangle meshes are not in this path's scope (SURVEY 8a a18)")
+            pos.append(m.vertices)
+            if any_normals:
+                nrm.append(m.normals)
+            if any_uvs:
+                uvs.append(m.tex_coords)
+            idx.append(m.vertex_indices + np.uint32(vbase))
+            vbase += m.vertices.shape[0]
+            mdescs.append((first, m.n_triangles, mat_id(p.material), A.FTN_MESH_FLIP_NORMALS if m.flip_normals() else 0))
+            first += m.n_triangles
+        self.n_triangles = first
+        self.n_spheres = len(spheres)
+        self._positions = _f32(np.concatenate(pos)) if pos else np.zeros((0, 3), np.float32)
+        self._normals = _f32(np.concatenate(nrm)) if nrm else None
+        self._uvs = _f32(np.concatenate(uvs)) if uvs else None
+        self._indices = np.ascontiguousarray(np.concatenate(idx), dtype=np.uint32) if idx else np.zeros((0, 3), np.uint32)
+
+        c_meshes = (A.FtnMeshDesc * max(1, len(mdescs)))()
+        for i, (f, n, mid, fl) in enumerate(mdescs):
+            c_meshes[i].first_tri, c_meshes[i].n_tris, c_meshes[i].material_id, c_meshes[i].flags = f, n, mid, fl
+        c_spheres = (A.FtnSphere * max(1, len(spheres)))()
+        for i, p in enumerate(spheres):
+            s, cs = p.shape, c_spheres[i]
+            cs.object_to_world[:] = s.object_to_world.flat().tolist()
+            cs.world_to_object[:] = s.object_to_world.flat_inv().tolist()
+            cs.radius, cs.z_min, cs.z_max, cs.phi_max_deg = s.radius, s.z_min, s.z_max, s.phi_max
+            cs.reverse_orientation = int(s.reverse_orientation)
+            cs.material_id = mat_id(p.material)
+            cs.emissive = int(p.light is not None)
+            if p.light is not None:
+                cs.emit[:] = p.light.emit.tolist()
+        c_mats = (A.FtnMaterial * max(1, len(materials)))()
+        for i, m in enumerate(materials):
+            m.fill(c_mats[i])
+        self._light_texels = []
+        c_lights = (A.FtnLight * max(1, len(lights)))()
+        for i, l in enumerate(lights):
+            if not isinstance(l, InfiniteAreaLight):
+                raise NotImplementedError("only infinite area lights may be listed explicitly")
+            tex = _f32(l.texels)
+            self._light_texels.append(tex)
+            cl = c_lights[i]
+            cl.type = A.FTN_LIGHT_INFINITE
+            cl.texels = _ptr(tex, A.f32)
+            cl.width, cl.height = l.width, l.height
+            cl.light_to_world[:] = l.light_to_world.flat().tolist()
+            cl.world_to_light[:] = l.light_to_world.flat_inv().tolist()
+
+        d = A.FtnSceneDesc()
+        d.abi_version = A.FTN_ABI_VERSION
+        d.positions = _ptr(self._positions, A.f32)
+        d.normals = _ptr(self._normals, A.f32) if self._normals is not None else None
+        d.uvs = _ptr(self._uvs, A.f32) if self._uvs is not None else None
+        d.n_vertices = self._positions.shape[0]
+        d.indices = _ptr(self._indices, A.u32)
+        d.n_triangles = self.n_triangles
+        d.meshes, d.n_meshes = c_meshes, len(mdescs)
+        d.spheres, d.n_spheres = c_spheres, len(spheres)
+        d.materials, d.n_materials = c_mats, len(materials)
+        d.lights, d.n_lights = c_lights, len(lights)
+        self.backend.call("scene_create", C.byref(d), C.byref(self._handle))
+        self.upload_bytes = int(self._positions.nbytes + self._indices.nbytes
+                                + (self._normals.nbytes if self._normals is not None else 0)
+                                + (self._uvs.nbytes if self._uvs is not None else 0)
+                                + sum(t.nbytes for t in self._light_texels))
+        if build:
+            self.build()
+
+    def build(self):
+        """BVH::build (bvh.rs:27) + Scene::new's light preprocessing (scene/mod.rs:32-49)."""
+        self.backend.call("bvh_build", self._handle)
+
+    def close(self):
+        if self._handle:
+            self.backend.call("scene_destroy", self._handle)
+            self._handle = A.VOIDP()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._handle
+
+    def world_bound(self):
+        """Scene::world_bound (scene/mod.rs:66): (min xyz, max xyz)."""
+        out = (A.f32 * 6)()
+        self.backend.call("scene_world_bound", self._handle, out)
+        a = np.array(out[:], dtype=np.float32)
+        return a[:3], a[3:]
+
+    def stats(self):
+        st = A.FtnStats()
+        self.backend.call("scene_stats", self._handle, C.byref(st))
+        return st.as_dict()
+
+    def morton_codes_and_order(self):
+        codes = np.zeros(self.n_triangles, np.uint32)
+        order = np.zeros(self.n_triangles, np.uint32)
+        self.backend.call("bvh_debug_morton", self._handle, _ptr(codes, A.u32), _ptr(order, A.u32))
+        return codes, order
+
+    def intersect(self, rays):
+        """Scene::intersect (scene/mod.rs:51) over a batch -> HIT_DTYPE array; prim == FTN_NO_HIT on miss."""
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = np.zeros(rays.shape[0], dtype=HIT_DTYPE)
+        self.backend.call("intersect", self._handle, rays.shape[0],
+                          rays.ctypes.data_as(C.POINTER(A.FtnRay)), hits.ctypes.data_as(C.POINTER(A.FtnHit)))
+        return hits
+
+    def intersect_test(self, rays):
+        """Scene::intersect_test (scene/mod.rs:55) over a batch -> bool array."""
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        out = np.zeros(rays.shape[0], dtype=np.uint8)
+        self.backend.call("intersect_test", self._handle, rays.shape[0],
+                          rays.ctypes.data_as(C.POINTER(A.FtnRay)), out.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return out.astype(bool)
+
+
+# ---------------------------------------------------------------------------------------------
+# Sensor
+# ---------------------------------------------------------------------------------------------
+
+class PerspectiveCamera:
+    """camera/mod.rs:85-114 (CameraProjection::new :50-72 inlined)."""
+
+    def __init__(self, camera_to_world, full_resolution, screen_window=None, shutter_interval=(0.0, 1.0),
+                 lens_radius=0.0, focal_dist=1e6, fov=90.0):
+        xres, yres = int(full_resolution[0]), int(full_resolution[1])
+        if screen_window is None:       # PbrtHeader::make_camera, loaders/pbrt.rs:440-451
+            aspect = np.float32(xres) / np.float32(yres)
+            if aspect > 1.0:
+                screen_window = ((-aspect, -1.0), (aspect, 1.0))
+            else:
+                screen_window = ((-1.0, -1.0 / aspect), (1.0, 1.0 / aspect))
+        (x0, y0), (x1, y1) = screen_window
+        camera_to_screen = Transform.perspective(fov, 1.0e-2, 1000.0)
+        screen_to_raster = (Transform.scale(xres, yres, 1.0)
+                            * Transform.scale(1.0 / (x1 - x0), 1.0 / (y0 - y1), 1.0)
+                            * Transform.translate((-x0, -y1, 0.0)))
+        raster_to_screen = screen_to_raster.inverse()
+        self.raster_to_camera = camera_to_screen.inverse() * raster_to_screen
+        self.camera_to_world = camera_to_world
+        self.shutter_interval = (float(shutter_interval[0]), float(shutter_interval[1]))
+        self.lens_radius = float(lens_radius)
+        self.focal_dist = float(focal_dist)
+        self.full_resolution = (xres, yres)
+
+    def to_abi(self):
+        c = A.FtnCamera()
+        c.camera_to_world[:] = self.camera_to_world.flat().tolist()
+        c.raster_to_camera[:] = self.raster_to_camera.flat().tolist()
+        c.lens_radius, c.focal_distance = self.lens_radius, self.focal_dist
+        c.shutter_open, c.shutter_close = self.shutter_interval
+        return c
+
+
+class BoxFilter:
+    """filter/mod.rs:10-32."""
+
+    def __init__(self, radius=(0.5, 0.5)):
+        self.radius = (float(radius[0]), float(radius[1]))
+
+
+class Film:
+    """film.rs:18-81.  After a render `pixels` is an (h, w, 4) float32 array of XYZ sums and
+    filter-weight sums -- `Film.pixels` (film.rs:24)."""
+
+    def __init__(self, resolution, crop_window=((0.0, 0.0), (1.0, 1.0)), filter=None, diagonal=35.0,
+                 backend=None):
+        self.full_resolution = (int(resolution[0]), int(resolution[1]))
+        (cx0, cy0), (cx1, cy1) = crop_window
+        self.crop_window = (float(cx0), float(cx1), float(cy0), float(cy1))   # pbrt `cropwindow` order
+        self.filter = filter or BoxFilter()
+        self.diagonal = diagonal
+        self.backend = backend or default_backend()
+        w, h = A.i32(), A.i32()
+        self.backend.call("film_pixel_count", C.byref(self.to_abi()), C.byref(w), C.byref(h))
+        self.width, self.height = w.value, h.value
+        self.pixels = np.zeros((self.height, self.width, 4), dtype=np.float32)
+
+    def to_abi(self):
+        f = A.FtnFilm()
+        f.x_resolution, f.y_resolution = self.full_resolution
+        f.crop_window[:] = list(self.crop_window)
+        f.filter_radius[:] = list(self.filter.radius)
+        return f
+
+    def into_spectrum_buffer(self):
+        """film.rs:195-210: (rgb (h*w, 3), (w, h)); XYZ -> RGB, times 1/weight, clamped at 0."""
+        xyz = self.pixels[..., :3].reshape(-1, 3)
+        wsum = self.pixels[..., 3].reshape(-1)
+        m = np.array([[3.240479, -1.537150, -0.498535], [-0.969256, 1.875991, 0.041556],
+                      [0.055648, -0.204043, 1.057311]], dtype=np.float32)
+        rgb = np.empty_like(xyz)
+        for i in range(3):
+            rgb[:, i] = (m[i, 0] * xyz[:, 0] + m[i, 1] * xyz[:, 1]) + m[i, 2] * xyz[:, 2]
+        nz = wsum != 0
+        inv = np.float32(1.0) / wsum[nz]
+        rgb[nz] = np.maximum(np.float32(0.0), rgb[nz] * inv[:, None])
+        return rgb, (self.width, self.height)
+
+
+class RandomSampler:
+    """sampler/random.rs:6-21.  `mode` selects the stream: the GPU's counter stream (default) or
+    the reference's sequential per-tile xoshiro256+ stream (CPU oracle only)."""
+
+    def __init__(self, samples_per_pixel, seed=0, mode=A.FTN_SAMPLER_COUNTER):
+        self.samples_per_pixel, self.seed, self.mode = int(samples_per_pixel), int(seed), int(mode)
+
+    @staticmethod
+    def new_with_seed(samples_per_pixel, seed, mode=A.FTN_SAMPLER_COUNTER):
+        return RandomSampler(samples_per_pixel, seed, mode)
+
+    def to_abi(self, sample_begin=0, sample_stride=1):
+        s = A.FtnSampler()
+        s.samples_per_pixel, s.seed, s.mode = self.samples_per_pixel, self.seed, self.mode
+        s.sample_begin, s.sample_stride = sample_begin, sample_stride
+        return s
+
+
+class PathIntegrator:
+    """integrator/path.rs:10-20."""
+
+    def __init__(self, max_depth, rr_threshold):
+        self.max_depth, self.rr_threshold = int(max_depth), float(rr_threshold)
+
+    def to_abi(self):
+        i = A.FtnIntegrator()
+        i.type, i.max_depth, i.rr_threshold = A.FTN_INTEGRATOR_PATH, self.max_depth, self.rr_threshold
+        return i
+
+
+class DirectLightingIntegrator:
+    """integrator/direct_lighting.rs:20-25, LightStrategy::UniformSampleOne only
+    (UniformSampleAll is unimplemented!() in the reference, :108-116)."""
+
+    def __init__(self, max_depth, strategy="one"):
+        if strategy != "one":
+            raise NotImplementedError("uniform_sample_all_lights is unimplemented!() in the reference")
+        self.max_depth = int(max_depth)
+
+    def to_abi(self):
+        i = A.FtnIntegrator()
+        i.type, i.max_depth, i.rr_threshold = A.FTN_INTEGRATOR_DIRECT_LIGHTING, self.max_depth, 0.0
+        return i
+
+
+class SamplerIntegrator:
+    """integrator/mod.rs:22-25, 218-227."""
+
+    def __init__(self, camera, radiance):
+        self.camera, self.radiance = camera, radiance
+        self.last_stats = None
+
+    def render_parallel(self, scene, film, sampler, sample_begin=0, sample_stride=1):
+        """Renders into film.pixels.  Raises FountainError(FTN_ERR_NAN_RADIANCE) where the
+        reference panics in check_radiance (integrator/mod.rs:285)."""
+        st = A.FtnStats()
+        out = np.zeros((film.height, film.width, 4), dtype=np.float32)
+        cam, f, s, it = self.camera.to_abi(), film.to_abi(), sampler.to_abi(sample_begin, sample_stride), self.radiance.to_abi()
+        scene.backend.call("render", scene.handle, C.byref(cam), C.byref(f), C.byref(s), C.byref(it),
+                           out.ctypes.data_as(C.POINTER(A.FtnPixel)), C.byref(st))
+        film.pixels = out
+        self.last_stats = st.as_dict()
+        return self.last_stats
+
+    render = render_parallel   # integrator/mod.rs:206 (sequential variant: same result here)

@@ -1,0 +1,231 @@
+"""Builders for the workloads BASELINE.json names.  Pure host-side
+scene description (numpy) -- the same arrays feed the CUDA library and, in tests, the oracle.
+"""
+import math
+import os
+
+import numpy as np
+
+from . import api
+from .transform import Transform
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROUNDED_CUBE_PLY = os.path.join(_ROOT, "tests", "golden", "rounded_cube.ply")
+
+
+# ---- C1: testscenes/furnace_empty.pbrt --------------------------------------------------------
+def furnace_scene(backend=None):
+    """Radius-100 sphere, matte Kd .5, diffuse area light L 1, ReverseOrientation; camera at
+    (0,-2,0) looking at the origin, up +z, fov 60, 16x16, box filter (furnace_empty.pbrt:2-19)."""
+    sphere = api.Sphere(Transform.identity(), reverse_orientation=True, radius=100.0)
+    prim = api.GeometricPrimitive(sphere, api.MatteMaterial(0.5), api.DiffuseAreaLight(1.0))
+    scene = api.Scene([prim], [], backend=backend)
+    cam_to_world = Transform.look_at((0, -2, 0), (0, 0, 0), (0, 0, 1)).inverse()   # pbrt.rs:430
+    camera = api.PerspectiveCamera(cam_to_world, (16, 16), fov=60.0)
+    film = api.Film((16, 16), backend=backend)
+    return scene, camera, film
+
+
+# ---- C2: data/rounded_cube.ply, Lambert, uniform env ---------------------------------------------
+def rounded_cube_scene(backend=None, resolution=(512, 512), material=None, light=None, ply=None):
+    """rounded_cube.ply at the identity, `matte` default Kd .5, `LightSource "infinite" L 1`;
+    camera LookAt 0 -40 0 -> 0 0 0 up 0 0 1, fov 40, no lens."""
+    mesh = api.TriangleMesh.from_ply(ply or ROUNDED_CUBE_PLY)
+    prim = api.GeometricPrimitive(mesh, material or api.MatteMaterial(0.5))
+    lights = [light or api.InfiniteAreaLight.new_uniform(1.0)]
+    scene = api.Scene([prim], lights, backend=backend)
+    cam_to_world = Transform.look_at((0, -40, 0), (0, 0, 0), (0, 0, 1)).inverse()
+    camera = api.PerspectiveCamera(cam_to_world, resolution, fov=40.0)
+    film = api.Film(resolution, backend=backend)
+    return scene, camera, film
+
+
+# ---- C3 / C5: synthetic tessellated sphere with seeded radial displacement ----------------------
+def _hash01(ix, iy, seed):
+    """Stateless integer hash -> [0,1) float64 (lowbias32 finaliser)."""
+    x = (ix.astype(np.uint64) * np.uint64(0x9E3779B1) + iy.astype(np.uint64) * np.uint64(0x85EBCA77)
+         + np.uint64(seed) * np.uint64(0xC2B2AE3D)) & np.uint64(0xFFFFFFFF)
+    x = x.astype(np.uint32)
+    x ^= x >> np.uint32(16)
+    x = (x.astype(np.uint64) * np.uint64(0x7FEB352D) & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    x ^= x >> np.uint32(15)
+    x = (x.astype(np.uint64) * np.uint64(0x846CA68B) & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    x ^= x >> np.uint32(16)
+    return x.astype(np.float64) / 4294967296.0
+
+
+def displaced_sphere_mesh(n_lon, n_lat, radius=10.0, amplitude=0.05, seed=1, with_normals=True):
+    """Lat-long grid of n_lon x n_lat quads x 2 triangles (1000 x 500 -> 1M tris).
+    Radius is scaled by 1 + amplitude * smooth value noise so the BVH is not trivial.  Poles are
+    pinched (degenerate quads collapse to triangles that the watertight test rejects cleanly)."""
+    lon = np.arange(n_lon + 1)
+    lat = np.arange(n_lat + 1)
+    LON, LAT = np.meshgrid(lon % n_lon, lat, indexing="xy")           # wrap the seam
+    phi = 2.0 * math.pi * (LON / n_lon)
+    theta = math.pi * (LAT / n_lat)
+    # value noise on a coarse 64 x 32 lattice, bilinear, periodic in longitude
+    gx, gy = 64, 32
+    fx = LON / n_lon * gx
+    fy = LAT / n_lat * gy
+    x0 = np.floor(fx).astype(np.int64); y0 = np.floor(fy).astype(np.int64)
+    tx = fx - x0; ty = fy - y0
+    tx = tx * tx * (3 - 2 * tx); ty = ty * ty * (3 - 2 * ty)
+
+    def g(ix, iy):
+        return _hash01(np.mod(ix, gx), np.clip(iy, 0, gy), seed)
+
+    noise = ((g(x0, y0) * (1 - tx) + g(x0 + 1, y0) * tx) * (1 - ty)
+             + (g(x0, y0 + 1) * (1 - tx) + g(x0 + 1, y0 + 1) * tx) * ty)
+    fine = _hash01(LON.astype(np.int64), LAT.astype(np.int64), seed + 17)
+    pole_fade = np.sin(theta) ** 2                                     # single point at each pole
+    r = radius * (1.0 + amplitude * pole_fade * (noise - 0.5) * 2.0 + 0.002 * pole_fade * (fine - 0.5))
+    st = np.sin(theta)
+    P = np.stack([r * st * np.cos(phi), r * st * np.sin(phi), r * np.cos(theta)], axis=-1)
+    verts = P.reshape(-1, 3).astype(np.float32)
+    W = n_lon + 1
+    i, j = np.meshgrid(np.arange(n_lon), np.arange(n_lat), indexing="xy")
+    a = (j * W + i).reshape(-1); b = a + 1; c = a + W; d = c + 1
+    tris = np.empty((a.size * 2, 3), dtype=np.uint32)
+    tris[0::2] = np.stack([a, c, b], axis=1)       # outward-facing (counter-clockwise from outside)
+    tris[1::2] = np.stack([b, c, d], axis=1)
+    normals = None
+    if with_normals:
+        n = verts / np.maximum(np.linalg.norm(verts, axis=1, keepdims=True), 1e-20)
+        normals = n.astype(np.float32)
+    return verts, tris, normals
+
+
+def synthetic_mesh_scene(n_lon=1000, n_lat=500, backend=None, material=None, light=None, resolution=(2048, 2048),
+                         seed=1, build=True):
+    """C3 (1000 x 500 -> 1M triangles) / C5 (5000 x 5000 -> 50M): Lambert + uniform env."""
+    v, t, n = displaced_sphere_mesh(n_lon, n_lat, seed=seed)
+    mesh = api.TriangleMesh(Transform.identity(), t, v, n)
+    prim = api.GeometricPrimitive(mesh, material or api.MatteMaterial(0.5))
+    scene = api.Scene([prim], [light or api.InfiniteAreaLight.new_uniform(1.0)], backend=backend, build=build)
+    cam_to_world = Transform.look_at((0, -40, 0), (0, 0, 0), (0, 0, 1)).inverse()
+    camera = api.PerspectiveCamera(cam_to_world, resolution, fov=40.0)
+    return scene, camera
+
+
+def primary_ray_batch(camera, resolution, oracle_lib=None):
+    """Batch A of C3: one pinhole ray through every pixel centre (numpy restatement of
+    camera/mod.rs:117-143 for lens_radius == 0; tests check it against the oracle's camera)."""
+    w, h = resolution
+    xs, ys = np.meshgrid(np.arange(w, dtype=np.float32) + np.float32(0.5),
+                         np.arange(h, dtype=np.float32) + np.float32(0.5), indexing="xy")
+    r2c = camera.raster_to_camera.m
+    px = np.stack([xs.reshape(-1), ys.reshape(-1), np.zeros(w * h), np.ones(w * h)], axis=0).astype(np.float64)
+    pc = r2c @ px
+    pc = pc[:3] / pc[3]
+    d = pc / np.linalg.norm(pc, axis=0, keepdims=True)
+    c2w = camera.camera_to_world.m
+    dw = (c2w[:3, :3] @ d).T
+    o = np.broadcast_to(c2w[:3, 3], dw.shape)
+    return api.make_rays(o.astype(np.float32), dw.astype(np.float32))
+
+
+def diffuse_bounce_batch(rays, hits, positions, indices, seed=2):
+    """Batch B of C3: for every batch-A hit, one cosine-hemisphere direction about the geometric
+    normal (facing the incoming ray) from a seeded generator; origin nudged off the surface."""
+    m = hits["prim"] != 0xFFFFFFFF
+    hr, hh = rays[m], hits[m]
+    tri = indices[hh["prim"]]
+    p0, p1, p2 = positions[tri[:, 0]].astype(np.float64), positions[tri[:, 1]].astype(np.float64), positions[tri[:, 2]].astype(np.float64)
+    n = np.cross(p1 - p0, p2 - p0)
+    n /= np.maximum(np.linalg.norm(n, axis=1, keepdims=True), 1e-30)
+    d_in = hr["d"].astype(np.float64)
+    n = np.where((np.sum(n * d_in, axis=1) > 0)[:, None], -n, n)
+    p = hr["o"].astype(np.float64) + d_in * hh["t"][:, None].astype(np.float64)
+    rng = np.random.default_rng(seed)
+    u = rng.random((p.shape[0], 2))
+    r = np.sqrt(u[:, 0]); ph = 2 * math.pi * u[:, 1]
+    lx, ly, lz = r * np.cos(ph), r * np.sin(ph), np.sqrt(np.maximum(0.0, 1 - u[:, 0]))
+    a = np.where((np.abs(n[:, 0]) > 0.9)[:, None], np.array([0.0, 1.0, 0.0]), np.array([1.0, 0.0, 0.0]))
+    t = np.cross(n, a); t /= np.linalg.norm(t, axis=1, keepdims=True)
+    b = np.cross(n, t)
+    d = t * lx[:, None] + b * ly[:, None] + n * lz[:, None]
+    o = p + n * 1e-3
+    return api.make_rays(o.astype(np.float32), d.astype(np.float32))
+
+
+# ---- C4: "Rust-logo-style": gear-ring mesh, TR metal, thin lens, image env -----------------------
+def gear_ring_mesh(n_teeth=48, seg_per_tooth=16, n_height=24, n_radial=24, r_in=4.0, r_out=7.0, tooth=0.8,
+                   height=1.5):
+    """Extruded gear ring (outer wall with teeth, inner wall, top and bottom annuli), uniformly
+    tessellated; default ~ 200 k triangles with the default arguments scaled by `detail`."""
+    n_ang = n_teeth * seg_per_tooth
+    ang = np.linspace(0.0, 2.0 * math.pi, n_ang, endpoint=False)
+    prof = r_out + tooth * np.clip(np.sin(ang * n_teeth) * 3.0, -1.0, 1.0) * 0.5
+
+    verts, tris = [], []
+
+    def add_grid(P, flip):
+        # P: (rows, n_ang, 3) closed in the angular direction
+        rows = P.shape[0]
+        base = sum(v.shape[0] for v in verts)
+        verts.append(P.reshape(-1, 3))
+        i, j = np.meshgrid(np.arange(n_ang), np.arange(rows - 1), indexing="xy")
+        a = (j * n_ang + i).reshape(-1); b = (j * n_ang + (i + 1) % n_ang).reshape(-1)
+        c = a + n_ang; d = b + n_ang
+        t = np.empty((a.size * 2, 3), dtype=np.int64)
+        if flip:
+            t[0::2] = np.stack([a, c, b], axis=1); t[1::2] = np.stack([b, c, d], axis=1)
+        else:
+            t[0::2] = np.stack([a, b, c], axis=1); t[1::2] = np.stack([b, d, c], axis=1)
+        tris.append(t + base)
+
+    z = np.linspace(0.0, height, n_height + 1)
+    ca, sa = np.cos(ang), np.sin(ang)
+    outer = np.stack([np.broadcast_to(prof * ca, (z.size, n_ang)), np.broadcast_to(prof * sa, (z.size, n_ang)),
+                      np.broadcast_to(z[:, None], (z.size, n_ang))], axis=-1)
+    add_grid(outer, flip=False)
+    inner = np.stack([np.broadcast_to(r_in * ca, (z.size, n_ang)), np.broadcast_to(r_in * sa, (z.size, n_ang)),
+                      np.broadcast_to(z[:, None], (z.size, n_ang))], axis=-1)
+    add_grid(inner, flip=True)
+    s = np.linspace(0.0, 1.0, n_radial + 1)[:, None]
+    rad = r_in + (prof[None, :] - r_in) * s
+    top = np.stack([rad * ca, rad * sa, np.full_like(rad, height)], axis=-1)
+    add_grid(top, flip=False)
+    bot = np.stack([rad * ca, rad * sa, np.zeros_like(rad)], axis=-1)
+    add_grid(bot, flip=True)
+    return np.concatenate(verts).astype(np.float32), np.concatenate(tris).astype(np.uint32)
+
+
+def sky_sun_envmap(width=2048, height=1024, seed=3, peak=1.0e4):
+    """Procedural lat-long sky + sun map (the reference's HDR is not in the repository)."""
+    rng = np.random.default_rng(seed)
+    t = (np.arange(height) + 0.5) / height * math.pi
+    p = (np.arange(width) + 0.5) / width * 2 * math.pi
+    T, P = np.meshgrid(t, p, indexing="ij")
+    d = np.stack([np.sin(T) * np.cos(P), np.sin(T) * np.sin(P), np.cos(T)], axis=-1)
+    up = np.clip(d[..., 2], 0, 1)
+    sky = np.stack([0.25 + 0.35 * (1 - up), 0.35 + 0.35 * (1 - up), 0.6 + 0.3 * (1 - up)], axis=-1)
+    ground = np.array([0.18, 0.16, 0.14])
+    img = np.where((d[..., 2] > 0)[..., None], sky, ground)
+    sun_dir = np.array([math.cos(1.0) * math.cos(0.7), math.cos(1.0) * math.sin(0.7), math.sin(1.0)])
+    cosang = np.clip(d @ sun_dir, -1, 1)
+    img = img + peak * np.exp(-((np.arccos(cosang) / 0.02) ** 2))[..., None] * np.array([1.0, 0.9, 0.75])
+    img = img * (1.0 + 0.05 * rng.random(img.shape[:2])[..., None])
+    return img.astype(np.float32)
+
+
+def logo_style_scene(backend=None, resolution=(1920, 1080), detail=1.0, env_size=(2048, 1024)):
+    """C4: gear ring on a ground quad, Cu metal roughness 0.01 (remapped), thin lens focused on
+    the ring, sky+sun environment."""
+    k = max(1, int(round(detail * 4)))
+    v, t = gear_ring_mesh(seg_per_tooth=4 * k, n_height=6 * k, n_radial=6 * k)
+    ring = api.TriangleMesh(Transform.translate((0, 0, 0.01)), t, v)
+    g = 40.0
+    gv = np.array([[-g, -g, 0], [g, -g, 0], [g, g, 0], [-g, g, 0]], dtype=np.float32)
+    gt = np.array([[0, 1, 2], [0, 2, 3]], dtype=np.uint32)
+    ground = api.TriangleMesh(Transform.identity(), gt, gv)
+    copper = api.MetalMaterial(eta=(0.2, 0.92, 1.1), k=(3.9, 2.45, 2.14), roughness=0.01, remap_roughness=True)
+    prims = [api.GeometricPrimitive(ring, copper), api.GeometricPrimitive(ground, api.MatteMaterial(0.5))]
+    env = api.InfiniteAreaLight.new_envmap(sky_sun_envmap(env_size[0], env_size[1]))
+    scene = api.Scene(prims, [env], backend=backend)
+    eye = np.array([0.0, -18.0, 9.0]); look = np.array([0.0, 0.0, 0.75])
+    cam_to_world = Transform.look_at(eye, look, (0, 0, 1)).inverse()
+    camera = api.PerspectiveCamera(cam_to_world, resolution, fov=40.0, lens_radius=0.1,
+                                   focal_dist=float(np.linalg.norm(look - eye)))
+    film = api.Film(resolution, backend=backend)
+    return scene, camera, film

@@ -1,0 +1,291 @@
+/*
+ * fountain_gpu.h -- C ABI of the B200-native wavefront path tracer that replaces
+ * fountain's data-parallel hot path (camera ray -> BVH closest/any hit -> shade ->
+ * light MIS -> film).  Plain C: pointers and sizes only, no C++/torch types.
+ *
+ * Every entry point names the reference interface it replaces (file:line relative
+ * to akofke/fountain).  The reference is pure Rust; a Rust host crate binds these
+ * with `extern "C"` (see INTEGRATION.md for the stub).
+ *
+ * Conventions
+ *   - All functions return 0 on success, a negative FtnStatus on failure; the
+ *     message is available from ftn_last_error() (thread-local).  Nothing throws
+ *     or aborts across the ABI.
+ *   - The caller owns every input array and every output buffer.  The library
+ *     copies inputs during ftn_scene_create and keeps nothing after return.
+ *   - `*_device` variants take pointers into the CURRENT CUDA device's memory
+ *     (e.g. a torch tensor's data_ptr) and enqueue work on `stream` (a
+ *     cudaStream_t passed as void*; NULL = legacy default stream).  They do not
+ *     synchronise.
+ *   - Primitive ids crossing the ABI are insertion indices: triangles first, in
+ *     index-buffer order (mesh order, tri_id), then spheres.  The reference's own
+ *     post-build permutation (bvh.rs:52) is not stable and is not exposed.
+ *   - Matrices are 16 floats, COLUMN-major (cgmath Matrix4 layout: m[4*c + r]),
+ *     as Transform::from_flat (geometry/transform.rs:34-42).
+ */
+#ifndef FOUNTAIN_GPU_H
+#define FOUNTAIN_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define FTN_API __declspec(dllexport)
+#else
+#define FTN_API __attribute__((visibility("default")))
+#endif
+
+#define FTN_ABI_VERSION 1u
+#define FTN_NO_HIT 0xFFFFFFFFu
+
+typedef enum FtnStatus {
+    FTN_OK = 0,
+    FTN_ERR_INVALID_ARGUMENT = -1,
+    FTN_ERR_CUDA = -2,             /* a CUDA call failed; message carries cudaGetErrorString */
+    FTN_ERR_NO_DEVICE = -3,        /* no CUDA device: there is NO CPU fallback */
+    FTN_ERR_NAN_RADIANCE = -4,     /* mirrors check_radiance panic, integrator/mod.rs:285 */
+    FTN_ERR_UNSUPPORTED = -5,      /* e.g. env-map sample with map_pdf == 0 (infinite.rs:101 unimplemented!()) */
+    FTN_ERR_OUT_OF_MEMORY = -6
+} FtnStatus;
+
+/* ---- rays and hits --------------------------------------------------------------- */
+
+/* geometry/mod.rs:88-93 `Ray { origin, dir, t_max, time }` -- 32 bytes, same field order. */
+typedef struct FtnRay {
+    float o[3];
+    float d[3];
+    float t_max;
+    float time;
+} FtnRay;
+
+/* Compact hit record (replaces the fat SurfaceInteraction of interaction.rs:61-84 at the
+ * aggregate seam; everything else is re-derivable from prim + barycentrics, triangle.rs:246-250).
+ * prim == FTN_NO_HIT on a miss.  For triangles b1,b2 are the barycentrics of vertices 1,2
+ * (b0 = e0*inv_det is returned implicitly as the reference computes it, NOT as 1-b1-b2: use
+ * ftn_intersect_full if b0 is needed bit-exactly).  For spheres b1,b2 hold (phi, unused). */
+typedef struct FtnHit {
+    uint32_t prim;
+    float t;
+    float b1;
+    float b2;
+} FtnHit;
+
+/* ---- scene description ------------------------------------------------------------ */
+
+enum { FTN_MESH_FLIP_NORMALS = 1u };   /* reverse_orientation ^ transform_swaps_handedness, shapes/mod.rs:27-29 */
+
+/* One TriangleMesh (shapes/triangle.rs:10-26).  Vertices are ALREADY in world space, as
+ * TriangleMesh::new leaves them (triangle.rs:42-58). */
+typedef struct FtnMeshDesc {
+    uint32_t first_tri;      /* first triangle in the scene-wide index buffer */
+    uint32_t n_tris;
+    int32_t  material_id;    /* index into materials[], -1 = no material (null BSDF, path.rs:76-80) */
+    uint32_t flags;          /* FTN_MESH_* */
+} FtnMeshDesc;
+
+typedef enum FtnMaterialType {
+    FTN_MATERIAL_MATTE = 0,   /* material/matte.rs:36-52 (sigma must be 0: Lambert only) */
+    FTN_MATERIAL_METAL = 1,   /* material/metal.rs:38-65 */
+    FTN_MATERIAL_PLASTIC = 2  /* material/plastic.rs:24-48 */
+} FtnMaterialType;
+
+/* Constant-texture materials only (texture/mod.rs:34-42). */
+typedef struct FtnMaterial {
+    int32_t type;            /* FtnMaterialType */
+    float kd[3];             /* matte Kd / plastic Kd */
+    float ks[3];             /* plastic Ks */
+    float eta[3];            /* metal eta */
+    float k[3];              /* metal k */
+    float u_roughness;       /* metal uroughness / plastic+metal isotropic roughness */
+    float v_roughness;
+    int32_t remap_roughness; /* constructors.rs:227 default true */
+} FtnMaterial;
+
+/* shapes/sphere.rs:16-27 (+ the DiffuseAreaLight it may carry, light/diffuse.rs:24-41). */
+typedef struct FtnSphere {
+    float object_to_world[16];
+    float world_to_object[16];
+    float radius;
+    float z_min, z_max;      /* as given to Sphere::new (sphere.rs:30-49), before clamping */
+    float phi_max_deg;
+    int32_t reverse_orientation;
+    int32_t material_id;     /* -1 = none */
+    int32_t emissive;        /* 1 = has a diffuse area light */
+    float emit[3];           /* L of the area light */
+} FtnSphere;
+
+typedef enum FtnLightType {
+    FTN_LIGHT_INFINITE = 0   /* light/infinite.rs:13-165 */
+} FtnLightType;
+
+/* Explicit `LightSource`s in file order (scene/mod.rs:32-49).  Area lights are implied by
+ * emissive spheres and are appended after these, in primitive order. */
+typedef struct FtnLight {
+    int32_t type;            /* FtnLightType */
+    const float* texels;     /* RGB f32, w*h*3, row-major (s fastest); level-0 of the MIPMap */
+    int32_t width, height;   /* 1x1 for new_uniform (infinite.rs:42-61) */
+    float light_to_world[16];
+    float world_to_light[16];
+} FtnLight;
+
+typedef struct FtnSceneDesc {
+    uint32_t abi_version;    /* FTN_ABI_VERSION */
+    const float* positions;  /* 3*n_vertices, world space */
+    const float* normals;    /* 3*n_vertices or NULL (un-normalised is fine, triangle.rs:335) */
+    const float* uvs;        /* 2*n_vertices or NULL (default uv (0,0),(1,0),(1,1), triangle.rs:131-143) */
+    uint32_t n_vertices;
+    const uint32_t* indices; /* 3*n_triangles */
+    uint32_t n_triangles;
+    const FtnMeshDesc* meshes;
+    uint32_t n_meshes;
+    const FtnSphere* spheres;
+    uint32_t n_spheres;
+    const FtnMaterial* materials;
+    uint32_t n_materials;
+    const FtnLight* lights;
+    uint32_t n_lights;
+} FtnSceneDesc;
+
+/* ---- sensor ----------------------------------------------------------------------- */
+
+/* camera/mod.rs:74-114 PerspectiveCamera after construction. */
+typedef struct FtnCamera {
+    float camera_to_world[16];
+    float raster_to_camera[16];
+    float lens_radius;
+    float focal_distance;
+    float shutter_open, shutter_close;
+} FtnCamera;
+
+/* film.rs:43-81 Film::new + filter/mod.rs:10-32 BoxFilter. */
+typedef struct FtnFilm {
+    int32_t x_resolution, y_resolution;
+    float crop_window[4];    /* x0,x1,y0,y1 as the pbrt `cropwindow` (pbrt.rs:491-495) */
+    float filter_radius[2];  /* box filter radius (0.5,0.5 default) */
+} FtnFilm;
+
+typedef enum FtnSamplerMode {
+    /* Counter-based stream: u(pixel, sample, dimension) -- the GPU's native mode. */
+    FTN_SAMPLER_COUNTER = 0,
+    /* The reference's sequential per-tile xoshiro256+ stream (sampler/random.rs:6-76,
+     * integrator/mod.rs:182-204).  Oracle only; the GPU library rejects it. */
+    FTN_SAMPLER_REFERENCE_TILE_STREAM = 1
+} FtnSamplerMode;
+
+typedef struct FtnSampler {
+    int32_t samples_per_pixel;
+    uint64_t seed;
+    int32_t mode;            /* FtnSamplerMode */
+    /* sample-index sharding for multi-GPU: this call renders samples
+     * s = sample_begin + i*sample_stride < samples_per_pixel.  (0,1) renders all. */
+    int32_t sample_begin;
+    int32_t sample_stride;
+} FtnSampler;
+
+typedef enum FtnIntegratorType {
+    FTN_INTEGRATOR_PATH = 0,            /* integrator/path.rs:10-96 */
+    FTN_INTEGRATOR_DIRECT_LIGHTING = 1  /* integrator/direct_lighting.rs (UniformSampleOne) */
+} FtnIntegratorType;
+
+typedef struct FtnIntegrator {
+    int32_t type;
+    int32_t max_depth;       /* PathIntegrator::new(max_depth, rr_threshold), render.rs:76 uses (5, 1.0) */
+    float rr_threshold;
+} FtnIntegrator;
+
+/* film.rs:12-16 `Pixel { xyz, filter_weight_sum }` -- 16 bytes. */
+typedef struct FtnPixel {
+    float xyz[3];
+    float filter_weight_sum;
+} FtnPixel;
+
+typedef struct FtnStats {
+    uint64_t camera_samples;
+    uint64_t rays_closest;   /* Scene::intersect calls (primary + continuation + MIS) */
+    uint64_t rays_any;       /* Scene::intersect_test calls (shadow) */
+    uint64_t node_visits;    /* 0 unless built with FTN_COUNT_TRAVERSAL / requested via env */
+    uint64_t tri_tests;
+    uint64_t kernel_launches;
+    double   device_seconds; /* CUDA-event time of the whole call on its stream */
+    double   bvh_build_seconds;
+    uint32_t bvh_nodes;
+    uint32_t bvh_node_bytes;
+    uint32_t bvh_tri_bytes;
+    uint32_t reserved;
+} FtnStats;
+
+typedef struct FtnScene FtnScene;
+
+/* ---- library ---------------------------------------------------------------------- */
+
+FTN_API uint32_t    ftn_abi_version(void);
+FTN_API const char* ftn_last_error(void);
+FTN_API int         ftn_device_count(int* out_count);
+FTN_API int         ftn_set_device(int device);
+/* Total kernels launched by this library in this process (the bench's gpu_launches). */
+FTN_API uint64_t    ftn_kernel_launch_count(void);
+
+/* ---- scene / aggregate (replaces Scene::new scene/mod.rs:32, BVH::build bvh.rs:27) ------ */
+
+/* Uploads the scene into flat SoA device buffers.  Does not build the BVH. */
+FTN_API int ftn_scene_create(const FtnSceneDesc* desc, FtnScene** out_scene);
+FTN_API int ftn_scene_destroy(FtnScene* scene);
+
+/* Morton-code LBVH build on the device: morton3 (morton.rs:3-36) of the primitive-bound
+ * centroids normalised by Bounds3f::offset (bounds.rs:200-206) in the centroid bounds,
+ * stable radix sort, Karras hierarchy, refit, wide-node collapse.  Idempotent. */
+FTN_API int ftn_bvh_build(FtnScene* scene);
+
+/* Bit-exact check hooks: the 30-bit Morton code of every triangle in INPUT order and the
+ * sorted primitive order (ties by index).  Either pointer may be NULL. */
+FTN_API int ftn_bvh_debug_morton(const FtnScene* scene, uint32_t* codes, uint32_t* order);
+
+/* Scene::world_bound (scene/mod.rs:66): min xyz, max xyz. */
+FTN_API int ftn_scene_world_bound(const FtnScene* scene, float out_min_max[6]);
+
+FTN_API int ftn_scene_stats(const FtnScene* scene, FtnStats* out);
+
+/* Scene::intersect (scene/mod.rs:51) over a batch: closest hit, HOST buffers. */
+FTN_API int ftn_intersect(const FtnScene* scene, size_t n, const FtnRay* rays, FtnHit* hits);
+/* Scene::intersect_test (scene/mod.rs:55) over a batch: out[i] = 1 if any hit. */
+FTN_API int ftn_intersect_test(const FtnScene* scene, size_t n, const FtnRay* rays, uint8_t* out);
+
+FTN_API int ftn_intersect_device(const FtnScene* scene, size_t n, const FtnRay* d_rays,
+                                 FtnHit* d_hits, void* stream);
+FTN_API int ftn_intersect_test_device(const FtnScene* scene, size_t n, const FtnRay* d_rays,
+                                      uint8_t* d_out, void* stream);
+/* Same as ftn_intersect_device but also accumulates node-visit / triangle-test counts
+ * (two uint64 on the device: [0]=nodes, [1]=tris).  Used for the bytes-per-ray roofline. */
+FTN_API int ftn_intersect_count_device(const FtnScene* scene, size_t n, const FtnRay* d_rays,
+                                       FtnHit* d_hits, uint64_t* d_counters, void* stream);
+
+/* ---- integrator (replaces SamplerIntegrator::render_parallel, integrator/mod.rs:218) ---- */
+
+/* Renders and writes film.pixels (film.rs:24) for the cropped pixel bounds, row-major:
+ * XYZ sums and filter-weight sums, exactly what merge_film_tile (film.rs:121) leaves. */
+FTN_API int ftn_render(const FtnScene* scene, const FtnCamera* camera, const FtnFilm* film,
+                       const FtnSampler* sampler, const FtnIntegrator* integrator,
+                       FtnPixel* out_pixels, FtnStats* out_stats);
+
+/* Device variant for multi-GPU sharding: ACCUMULATES this call's samples into d_pixels
+ * (4 floats per pixel: xyz + weight; caller zero-fills).  The caller then sum-reduces
+ * d_pixels across ranks (NCCL) -- the analogue of merge_film_tile's Mutex merge. */
+FTN_API int ftn_render_device(const FtnScene* scene, const FtnCamera* camera, const FtnFilm* film,
+                              const FtnSampler* sampler, const FtnIntegrator* integrator,
+                              FtnPixel* d_pixels, FtnStats* out_stats, void* stream);
+
+/* Film::into_spectrum_buffer (film.rs:195-210): XYZ -> RGB, divide by weight, clamp >= 0.
+ * n pixels; out_rgb is 3 floats per pixel.  Device buffers. */
+FTN_API int ftn_film_to_rgb_device(size_t n, const FtnPixel* d_pixels, float* d_rgb, void* stream);
+
+/* Number of pixels ftn_render writes for this film (cropped_pixel_bounds area, film.rs:49-58). */
+FTN_API int ftn_film_pixel_count(const FtnFilm* film, int32_t* out_w, int32_t* out_h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOUNTAIN_GPU_H */
