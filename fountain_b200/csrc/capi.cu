@@ -1,0 +1,143 @@
+// extern "C" surface of libfountain_gpu.so (include/fountain_gpu.h).  No CPU fallback: every
+// compute entry point needs a CUDA device and says so when there is none.
+#include "ftn_scene.h"
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+namespace ftn {
+static thread_local std::string g_last_error;
+static std::atomic<uint64_t> g_launches{0};
+
+int set_error(int code, const std::string& msg) { g_last_error = msg; return code; }
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s failed: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+    cudaGetLastError();   // clear the sticky flag of non-fatal errors
+    const int code = (e == cudaErrorMemoryAllocation) ? FTN_ERR_OUT_OF_MEMORY
+                   : (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? FTN_ERR_NO_DEVICE : FTN_ERR_CUDA;
+    return set_error(code, buf);
+}
+void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int intersect_device(const FtnScene* s, size_t n, const FtnRay* d_rays, FtnHit* d_hits, uint8_t* d_any,
+                     bool any, unsigned long long* d_counters, cudaStream_t st);
+int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, const FtnSampler* smp,
+                  const FtnIntegrator* integ, FtnPixel* d_pixels, FtnStats* stats, cudaStream_t st);
+int film_to_rgb_device(size_t n, const FtnPixel* d_pixels, float* d_rgb, cudaStream_t st);
+int film_pixel_count(const FtnFilm* f, int32_t* w, int32_t* h);
+}  // namespace ftn
+
+using namespace ftn;
+
+extern "C" {
+
+FTN_API uint32_t ftn_abi_version(void) { return FTN_ABI_VERSION; }
+FTN_API const char* ftn_last_error(void) { return g_last_error.c_str(); }
+FTN_API uint64_t ftn_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+FTN_API int ftn_device_count(int* out_count) {
+    if (!out_count) return set_error(FTN_ERR_INVALID_ARGUMENT, "null argument");
+    *out_count = 0;
+    cudaError_t e = cudaGetDeviceCount(out_count);
+    if (e != cudaSuccess) { *out_count = 0; return cuda_fail(e, "cudaGetDeviceCount", __FILE__, __LINE__); }
+    return FTN_OK;
+}
+FTN_API int ftn_set_device(int device) { FTN_CUDA(cudaSetDevice(device)); return FTN_OK; }
+
+FTN_API int ftn_scene_create(const FtnSceneDesc* desc, FtnScene** out_scene) {
+    int n = 0;
+    FTN_TRY(ftn_device_count(&n));
+    if (n < 1) return set_error(FTN_ERR_NO_DEVICE, "no CUDA device; this library has no CPU path");
+    return scene_create(desc, out_scene);
+}
+FTN_API int ftn_scene_destroy(FtnScene* scene) { return scene_destroy(scene); }
+FTN_API int ftn_bvh_build(FtnScene* scene) { return bvh_build(scene); }
+
+FTN_API int ftn_bvh_debug_morton(const FtnScene* s, uint32_t* codes, uint32_t* order) {
+    if (!s || !s->built) return set_error(FTN_ERR_INVALID_ARGUMENT, "scene not built");
+    if (s->n_tris == 0) return FTN_OK;
+    if (codes) FTN_CUDA(cudaMemcpy(codes, s->d_codes, (size_t)s->n_tris * 4, cudaMemcpyDeviceToHost));
+    if (order) FTN_CUDA(cudaMemcpy(order, s->d_order, (size_t)s->n_tris * 4, cudaMemcpyDeviceToHost));
+    return FTN_OK;
+}
+FTN_API int ftn_scene_world_bound(const FtnScene* s, float out[6]) {
+    if (!s || !s->built || !out) return set_error(FTN_ERR_INVALID_ARGUMENT, "scene not built");
+    std::memcpy(out, s->bounds, sizeof(float) * 6);
+    return FTN_OK;
+}
+FTN_API int ftn_scene_stats(const FtnScene* s, FtnStats* st) {
+    if (!s || !st) return set_error(FTN_ERR_INVALID_ARGUMENT, "null argument");
+    std::memset(st, 0, sizeof(*st));
+    st->bvh_build_seconds = s->build_seconds; st->bvh_nodes = s->n_nodes; st->bvh_node_bytes = 64; st->bvh_tri_bytes = 48;
+    st->kernel_launches = ftn_kernel_launch_count();
+    return FTN_OK;
+}
+
+FTN_API int ftn_intersect_device(const FtnScene* s, size_t n, const FtnRay* d_rays, FtnHit* d_hits, void* stream) {
+    return intersect_device(s, n, d_rays, d_hits, nullptr, false, nullptr, (cudaStream_t)stream);
+}
+FTN_API int ftn_intersect_test_device(const FtnScene* s, size_t n, const FtnRay* d_rays, uint8_t* d_out, void* stream) {
+    return intersect_device(s, n, d_rays, nullptr, d_out, true, nullptr, (cudaStream_t)stream);
+}
+FTN_API int ftn_intersect_count_device(const FtnScene* s, size_t n, const FtnRay* d_rays, FtnHit* d_hits, uint64_t* d_counters, void* stream) {
+    if (!d_counters) return set_error(FTN_ERR_INVALID_ARGUMENT, "null counters");
+    return intersect_device(s, n, d_rays, d_hits, nullptr, false, (unsigned long long*)d_counters, (cudaStream_t)stream);
+}
+
+static int intersect_host(const FtnScene* s, size_t n, const FtnRay* rays, FtnHit* hits, uint8_t* any_out, bool any) {
+    if (!s) return set_error(FTN_ERR_INVALID_ARGUMENT, "null scene");
+    if (n == 0) return FTN_OK;
+    if (!rays || (!any && !hits) || (any && !any_out)) return set_error(FTN_ERR_INVALID_ARGUMENT, "null buffer");
+    FTN_CUDA(cudaSetDevice(s->device));
+    FtnRay* d_rays = nullptr; void* d_out = nullptr;
+    const size_t out_bytes = any ? n : n * sizeof(FtnHit);
+    cudaError_t e = cudaMalloc(&d_rays, n * sizeof(FtnRay));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc rays", __FILE__, __LINE__);
+    e = cudaMalloc(&d_out, out_bytes);
+    if (e != cudaSuccess) { cudaFree(d_rays); return cuda_fail(e, "cudaMalloc hits", __FILE__, __LINE__); }
+    int rc = FTN_OK;
+    if ((e = cudaMemcpy(d_rays, rays, n * sizeof(FtnRay), cudaMemcpyHostToDevice)) != cudaSuccess) rc = cuda_fail(e, "H2D rays", __FILE__, __LINE__);
+    if (rc == FTN_OK) rc = intersect_device(s, n, d_rays, any ? nullptr : (FtnHit*)d_out, any ? (uint8_t*)d_out : nullptr, any, nullptr, 0);
+    if (rc == FTN_OK && (e = cudaMemcpy(any ? (void*)any_out : (void*)hits, d_out, out_bytes, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "D2H hits", __FILE__, __LINE__);
+    cudaFree(d_rays); cudaFree(d_out);
+    return rc;
+}
+FTN_API int ftn_intersect(const FtnScene* s, size_t n, const FtnRay* rays, FtnHit* hits) { return intersect_host(s, n, rays, hits, nullptr, false); }
+FTN_API int ftn_intersect_test(const FtnScene* s, size_t n, const FtnRay* rays, uint8_t* out) { return intersect_host(s, n, rays, nullptr, out, true); }
+
+FTN_API int ftn_render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, const FtnSampler* smp,
+                              const FtnIntegrator* integ, FtnPixel* d_pixels, FtnStats* stats, void* stream) {
+    const uint64_t l0 = ftn_kernel_launch_count();
+    const int rc = render_device(s, cam, film, smp, integ, d_pixels, stats, (cudaStream_t)stream);
+    if (stats) stats->kernel_launches = ftn_kernel_launch_count() - l0;
+    return rc;
+}
+FTN_API int ftn_render(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, const FtnSampler* smp,
+                       const FtnIntegrator* integ, FtnPixel* out_pixels, FtnStats* stats) {
+    if (!s || !film || !out_pixels) return set_error(FTN_ERR_INVALID_ARGUMENT, "null argument");
+    int32_t w = 0, h = 0;
+    FTN_TRY(film_pixel_count(film, &w, &h));
+    FTN_CUDA(cudaSetDevice(s->device));
+    const size_t bytes = (size_t)w * h * sizeof(FtnPixel);
+    FtnPixel* d_px = nullptr;
+    FTN_CUDA(cudaMalloc(&d_px, bytes));
+    cudaError_t e = cudaMemset(d_px, 0, bytes);
+    int rc = (e == cudaSuccess) ? FTN_OK : cuda_fail(e, "memset film", __FILE__, __LINE__);
+    int render_rc = FTN_OK;
+    if (rc == FTN_OK) render_rc = ftn_render_device(s, cam, film, smp, integ, d_px, stats, nullptr);
+    // like the reference's panic, a NaN / unsupported render still leaves the film readable
+    if (rc == FTN_OK && (render_rc == FTN_OK || render_rc == FTN_ERR_NAN_RADIANCE || render_rc == FTN_ERR_UNSUPPORTED)) {
+        std::string keep = g_last_error;
+        if ((e = cudaMemcpy(out_pixels, d_px, bytes, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "D2H film", __FILE__, __LINE__);
+        else g_last_error = keep;
+    }
+    cudaFree(d_px);
+    return rc != FTN_OK ? rc : render_rc;
+}
+FTN_API int ftn_film_to_rgb_device(size_t n, const FtnPixel* d_pixels, float* d_rgb, void* stream) {
+    return film_to_rgb_device(n, d_pixels, d_rgb, (cudaStream_t)stream);
+}
+FTN_API int ftn_film_pixel_count(const FtnFilm* film, int32_t* w, int32_t* h) { return film_pixel_count(film, w, h); }
+
+}  // extern "C"

@@ -1,0 +1,302 @@
+// Per-path logic of the wavefront path tracer as FTN_HD functions; the kernels in render.cu are
+// thin wrappers (load state, call, store state, push queues).  Restates
+// PathIntegrator::incident_radiance (integrator/path.rs:25-95), uniform_sample_one_light /
+// estimate_direct (integrator/mod.rs:289-395), DirectLightingIntegrator (direct_lighting.rs:50-106)
+// and Film::add_sample_to_tile / merge_film_tile (film.rs:121-172).
+#pragma once
+#include "ftn_shade.cuh"
+#include "ftn_trace.cuh"
+
+namespace ftn {
+
+enum { ERR_NAN = 1u, ERR_UNSUPPORTED = 2u };
+
+FTN_HD void flag_error(uint32_t* err, uint32_t bit) {
+#if defined(__CUDA_ARCH__)
+    atomicOr(err, bit);
+#else
+    *err |= bit;
+#endif
+}
+
+struct FilmGeom {
+    int xres, yres;
+    int crop_min[2], crop_max[2];      // cropped_pixel_bounds, film.rs:49-58
+    int sb_min[2], sb_max[2];          // sample_bounds, film.rs:86-93
+    float radius[2], inv_radius[2];
+};
+
+struct PassParams {
+    FilmGeom film;
+    FtnCamera cam;
+    uint64_t seed_key;
+    int spp;                // samples_per_pixel of the whole render
+    int s_first;            // first global sample index of this pass
+    int s_stride;           // stride between consecutive samples of this pass
+    int s_count;            // samples per pixel in this pass
+    uint32_t n_paths;       // sample pixels * s_count
+    int integrator;         // FtnIntegratorType
+    int max_depth;
+    float rr_threshold;
+};
+
+#define FTN_STATE_BOUNCES 0xFFFFu
+#define FTN_STATE_SPECULAR 0x10000u
+
+// path id -> counter-sampler key.  path = sample_pixel * s_count + local sample; the global
+// pixel-sample index is ((y * xres) + x) * spp + s in RASTER coordinates (same in the oracle).
+FTN_HD uint64_t path_sample_key(const PassParams& pp, uint32_t path, int* x_out, int* y_out) {
+    const int sbw = pp.film.sb_max[0] - pp.film.sb_min[0];
+    const uint32_t pix = path / (uint32_t)pp.s_count, sl = path % (uint32_t)pp.s_count;
+    const int x = pp.film.sb_min[0] + (int)(pix % (uint32_t)sbw), y = pp.film.sb_min[1] + (int)(pix / (uint32_t)sbw);
+    const int s = pp.s_first + (int)sl * pp.s_stride;
+    const uint64_t sample_index = ((uint64_t)((int64_t)y * pp.film.xres + x)) * (uint64_t)pp.spp + (uint64_t)s;
+    if (x_out) *x_out = x;
+    if (y_out) *y_out = y;
+    return sampler_sample_key(pp.seed_key, sample_index);
+}
+
+// Sampler::get_camera_sample (sampler/mod.rs:43-51) + Camera::generate_ray
+FTN_HD RayF raygen_path(const PassParams& pp, uint32_t path, float* fx, float* fy) {
+    int x, y;
+    const uint64_t key = path_sample_key(pp, path, &x, &y);
+    const float jx = sampler_uniform(key, 0), jy = sampler_uniform(key, 1);
+    const float lx = sampler_uniform(key, 2), ly = sampler_uniform(key, 3), tu = sampler_uniform(key, 4);
+    *fx = rn_add((float)x, jx); *fy = rn_add((float)y, jy);
+    return camera_ray(pp.cam, *fx, *fy, lx, ly, tu);
+}
+
+// Re-derive the surface at the hit the extend stage found: the same deterministic test on the
+// same (ray, primitive) pair reproduces t and the barycentrics bit for bit, so the queues carry a
+// 4-byte slot instead of a fat hit record (the reference builds a full SurfaceInteraction per
+// accepted candidate, triangle.rs:270-392).
+FTN_HD bool surface_at_hit(const SceneView& sc, uint32_t slot, const RayF& ray, Surface* s) {
+    if (slot & FTN_SPHERE_SLOT_FLAG) {
+        const SphereData& sd = sc.spheres[slot & ~FTN_SPHERE_SLOT_FLAG];
+        SphereHit sh;
+        if (!sphere_intersect(sd, ray, &sh)) return false;
+        sphere_surface(sd, sh, s);
+        return true;
+    }
+    const F4 a = ld4(sc.bvh.tris + 3 * (size_t)slot), b = ld4(sc.bvh.tris + 3 * (size_t)slot + 1), c = ld4(sc.bvh.tris + 3 * (size_t)slot + 2);
+    TriHit th;
+    const RayShear sh = make_ray_shear(ray.d);
+    if (!triangle_intersect(V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), V3(c.x, c.y, c.z), ray.o, sh, ray.t_max, &th)) return false;
+    triangle_surface(sc, slot, th, ray.d, s);
+    return true;
+}
+
+FTN_HD int hit_material(const SceneView& sc, uint32_t slot) {
+    if (slot & FTN_SPHERE_SLOT_FLAG) return sc.spheres[slot & ~FTN_SPHERE_SLOT_FLAG].material;
+    return sc.meshes[f2u(ld4(sc.bvh.tris + 3 * (size_t)slot + 1).w)].material;
+}
+
+FTN_HD V3 area_emitted(const LightData& l, V3 n, V3 w) {   // DiffuseAreaLight::emitted_radiance, diffuse.rs:45-51
+    return (x_dot(n, w) > 0.0f) ? V3(l.emit[0], l.emit[1], l.emit[2]) : v3s(0.0f);
+}
+
+// Scene::environment_emitted_radiance, scene/mod.rs:58-64
+FTN_HD V3 scene_env_radiance(const SceneView& sc, V3 dir) {
+    V3 le = v3s(0.0f);
+    for (uint32_t l = 0; l < sc.n_lights; ++l) if (sc.lights[l].type == 0) le = le + env_emitted(sc.lights[l].env, dir);
+    return le;
+}
+
+// ---- uniform_sample_one_light + estimate_direct (integrator/mod.rs:289-395) ------------------------------
+struct DirectOut {
+    bool has_shadow; V3 sh_o, sh_d, sh_L;
+    bool has_mis; V3 mis_o, mis_d, mis_w; int mis_light;
+};
+
+FTN_HD void sample_direct(const SceneView& sc, const Surface& s, const Bsdf& bsdf, V3 scale,
+                          uint64_t key, uint32_t dim0, DirectOut* out, uint32_t* err) {
+    out->has_shadow = false; out->has_mis = false;
+    const uint32_t n_lights = sc.n_lights;
+    if (n_lights == 0u) return;
+    const float pick = sampler_uniform(key, dim0) * (float)n_lights;
+    const float capped = fminf(pick, (float)(n_lights - 1u));
+    const uint32_t li = (capped > 0.0f) ? (uint32_t)capped : 0u;
+    const float ul0 = sampler_uniform(key, dim0 + 1), ul1 = sampler_uniform(key, dim0 + 2);
+    const float us0 = sampler_uniform(key, dim0 + 3), us1 = sampler_uniform(key, dim0 + 4);
+    const LightData& light = sc.lights[li];
+    const float nl = (float)n_lights;
+    const int flags = BXDF_ALL & ~BXDF_SPECULAR;
+    // --- light sample ---
+    V3 wi = v3s(0.0f), Li = v3s(0.0f); float pdf = 0.0f; V3 p1 = v3s(0.0f), p1_err = v3s(0.0f), p1_n = v3s(0.0f);
+    bool ok = true;
+    if (light.type == 0) {
+        if (!env_sample(light.env, ul0, ul1, &wi, &pdf, &Li)) { flag_error(err, ERR_UNSUPPORTED); ok = false; }
+        else {
+            const float two_r = rn_mul(2.0f, light.env.world_radius);
+            p1 = x_add(s.p, x_scale(wi, two_r));   // infinite.rs:121-129: far endpoint, n = 0, p_err = 0
+        }
+    } else {   // diffuse.rs:74-89
+        const SphereData& sd = sc.spheres[light.sphere];
+        const ShapeSample ps = sphere_sample(sd, ul0, ul1);
+        wi = x_normalize(x_sub(ps.p, s.p));
+        pdf = sphere_pdf_from_ref(sd, s, wi);
+        Li = area_emitted(light, ps.n, x_neg(wi));
+        p1 = ps.p; p1_err = ps.p_err; p1_n = ps.n;
+    }
+    if (ok && pdf > 0.0f && !is_black(Li)) {
+        const V3 f = bsdf_f(bsdf, s.wo, wi, flags) * abs_dot(wi, s.ns);
+        const float spdf = bsdf_pdf(bsdf, s.wo, wi, flags);
+        if (!is_black(f)) {
+            // VisibilityTester -> SurfaceHit::spawn_ray_to_hit, interaction.rs:48-58
+            const V3 origin = offset_ray_origin(s.p, s.p_err, s.n, x_sub(p1, s.p));
+            const V3 target = offset_ray_origin(p1, p1_err, p1_n, x_sub(origin, p1));
+            const float w = power_heuristic1(pdf, spdf);
+            out->has_shadow = true; out->sh_o = origin; out->sh_d = x_sub(target, origin);
+            out->sh_L = scale * (nl * (f * Li * w / pdf));
+        }
+    }
+    // --- BSDF sample ---
+    ScatterSample bs;
+    if (bsdf_sample_f(bsdf, s.wo, us0, us1, flags, &bs)) {
+        const V3 f = bs.f * abs_dot(bs.wi, s.ns);
+        if (is_black(f)) return;
+        float lpdf;
+        if (light.type == 0) lpdf = env_pdf(light.env, bs.wi);
+        else lpdf = sphere_pdf_from_ref(sc.spheres[light.sphere], s, bs.wi);
+        if (lpdf == 0.0f) return;
+        const float w = power_heuristic1(bs.pdf, lpdf);
+        out->has_mis = true; out->mis_o = spawn_origin(s, bs.wi); out->mis_d = bs.wi;
+        out->mis_w = scale * (nl * (f * w / bs.pdf)); out->mis_light = (int)li;
+    }
+}
+
+// ---- one shaded bounce ---------------------------------------------------------------------------------------
+struct ShadeOut {
+    V3 L, beta;
+    uint32_t state;
+    bool alive; V3 next_o, next_d;
+    DirectOut direct;
+};
+
+// `ray` is the ray that produced `slot`; state/beta/L are the path's values on entry.
+FTN_HD void shade_surface(const SceneView& sc, const PassParams& pp, uint32_t path, const RayF& ray, uint32_t slot,
+                          uint32_t state, V3 beta, V3 L, ShadeOut* out, uint32_t* err) {
+    out->L = L; out->beta = beta; out->state = state; out->alive = false;
+    out->direct.has_shadow = false; out->direct.has_mis = false;
+    Surface s;
+    if (!surface_at_hit(sc, slot, ray, &s)) return;
+    const int bounces = (int)(state & FTN_STATE_BOUNCES);
+    const bool direct_only = pp.integrator == FTN_INTEGRATOR_DIRECT_LIGHTING;
+    // emitted light at the intersection: path.rs:45-51 / direct_lighting.rs:71
+    if (s.light >= 0 && (direct_only || bounces == 0 || (state & FTN_STATE_SPECULAR)))
+        L = L + beta * area_emitted(sc.lights[s.light], s.n, direct_only ? s.wo : x_neg(ray.d));
+    out->L = L;
+    if (!direct_only && bounces >= pp.max_depth) return;   // path.rs:54
+    if (s.material < 0) {
+        // null BSDF: respawn in the same direction without counting a bounce (path.rs:76-80);
+        // unimplemented!() under the direct-lighting integrator (direct_lighting.rs:98)
+        if (direct_only) { flag_error(err, ERR_UNSUPPORTED); return; }
+        out->alive = true; out->next_o = spawn_origin(s, ray.d); out->next_d = ray.d;
+        return;
+    }
+    Bsdf bsdf;
+    bsdf_init(&bsdf, s.ns, s.n, s.sdpdu);
+    material_bsdf(sc.materials[s.material], &bsdf);
+    const uint64_t key = path_sample_key(pp, path, nullptr, nullptr);
+    const uint32_t dim0 = DIM_CAMERA + (direct_only ? 0u : (uint32_t)DIM_PER_BOUNCE * (uint32_t)bounces);
+    if (bsdf_num_components(bsdf, BXDF_ALL & ~BXDF_SPECULAR) > 0)
+        sample_direct(sc, s, bsdf, direct_only ? v3s(1.0f) : beta, key, dim0, &out->direct, err);
+    if (direct_only) return;
+    // continuation: Bsdf::sample_f(wo, get_2d(), ALL), path.rs:68-76
+    const float u0 = sampler_uniform(key, dim0 + 5), u1 = sampler_uniform(key, dim0 + 6);
+    ScatterSample cs;
+    if (!bsdf_sample_f(bsdf, x_neg(ray.d), u0, u1, BXDF_ALL, &cs) || is_black(cs.f)) return;
+    beta = beta * (cs.f * abs_dot(cs.wi, s.ns) / cs.pdf);
+    const uint32_t spec = (cs.type & BXDF_SPECULAR) ? FTN_STATE_SPECULAR : 0u;
+    const float mb = max_component(beta);
+    if (mb < pp.rr_threshold && bounces > 3) {   // path.rs:84-91
+        const float q = fmaxf(0.05f, 1.0f - mb);
+        if (sampler_uniform(key, dim0 + 7) < q) return;
+        beta = beta / (1.0f - q);
+    }
+    out->alive = true; out->next_o = spawn_origin(s, cs.wi); out->next_d = cs.wi;
+    out->beta = beta; out->state = spec | (uint32_t)(bounces + 1);
+}
+
+// Radiance arriving along an MIS (BSDF-sampled) ray, integrator/mod.rs:364-389.
+FTN_HD V3 mis_incident(const SceneView& sc, const LightData& light, const RayF& ray, uint32_t slot) {
+    if (slot == FTN_NO_HIT_SLOT) return (light.type == 0) ? env_emitted(light.env, ray.d) : v3s(0.0f);
+    if (slot & FTN_SPHERE_SLOT_FLAG) {
+        const uint32_t si = slot & ~FTN_SPHERE_SLOT_FLAG;
+        if (light.type == 1 && (uint32_t)light.sphere == si) {   // the SAME light only (:370-381)
+            SphereHit sh;
+            if (sphere_intersect(sc.spheres[si], ray, &sh)) return area_emitted(light, sh.n, x_neg(ray.d));
+        }
+    }
+    return v3s(0.0f);
+}
+
+// ---- film ---------------------------------------------------------------------------------------------------------
+FTN_HD int iceil(float v) { return (int)ceilf(v); }
+FTN_HD int ifloor(float v) { return (int)floorf(v); }
+FTN_HD int imin(int a, int b) { return a < b ? a : b; }
+FTN_HD int imax(int a, int b) { return a > b ? a : b; }
+
+// Everything that Film::add_sample_to_tile (film.rs:136-172) would add to film pixel `i` from the
+// samples of this pass, gathered in a fixed order (sample rows, sample columns, samples).  The
+// footprint is p0 = ceil(pd - r), p1 = floor(pd + r) + 1 clipped to the pixel bounds of the
+// sample's 16x16 tile (get_film_tile, film.rs:95-113, including its `- radius` in p1y).
+FTN_HD void film_gather_pixel(const PassParams& pp, const float2* p_film, const float4* Lbuf, int i, int reach,
+                              float4* acc_io, uint32_t* err) {
+    const FilmGeom& f = pp.film;
+    const int fw = f.crop_max[0] - f.crop_min[0];
+    const int px = f.crop_min[0] + i % fw, py = f.crop_min[1] + i / fw;
+    const int sbw = f.sb_max[0] - f.sb_min[0];
+    float4 acc = *acc_io;
+    for (int sy = imax(py - reach, f.sb_min[1]); sy <= imin(py + reach, f.sb_max[1] - 1); ++sy) {
+        const int ty0 = f.sb_min[1] + ((sy - f.sb_min[1]) / 16) * 16, ty1 = imin(ty0 + 16, f.sb_max[1]);
+        const int tp0y = imax(iceil(rn_sub(rn_sub((float)ty0, 0.5f), f.radius[1])), f.crop_min[1]);
+        const int tp1y = imin(iceil(rn_add(rn_sub(rn_sub((float)ty1, 0.5f), f.radius[1]), 1.0f)), f.crop_max[1]);
+        if (py < tp0y || py >= tp1y) continue;
+        for (int sx = imax(px - reach, f.sb_min[0]); sx <= imin(px + reach, f.sb_max[0] - 1); ++sx) {
+            const int tx0 = f.sb_min[0] + ((sx - f.sb_min[0]) / 16) * 16, tx1 = imin(tx0 + 16, f.sb_max[0]);
+            const int tp0x = imax(iceil(rn_sub(rn_sub((float)tx0, 0.5f), f.radius[0])), f.crop_min[0]);
+            const int tp1x = imin(iceil(rn_add(rn_add(rn_sub((float)tx1, 0.5f), f.radius[0]), 1.0f)), f.crop_max[0]);
+            if (px < tp0x || px >= tp1x) continue;
+            const uint32_t base = ((uint32_t)(sy - f.sb_min[1]) * (uint32_t)sbw + (uint32_t)(sx - f.sb_min[0])) * (uint32_t)pp.s_count;
+            for (int s = 0; s < pp.s_count; ++s) {
+                const float2 pf = p_film[base + s];
+                const float dx = rn_sub(pf.x, 0.5f), dy = rn_sub(pf.y, 0.5f);
+                const int p0x = iceil(rn_sub(dx, f.radius[0])), p1x = ifloor(rn_add(dx, f.radius[0])) + 1;
+                const int p0y = iceil(rn_sub(dy, f.radius[1])), p1y = ifloor(rn_add(dy, f.radius[1])) + 1;
+                if (px < p0x || px >= p1x || py < p0y || py >= p1y) continue;
+                const float4 L = Lbuf[base + s];
+                if (L.x != L.x || L.y != L.y || L.z != L.z) flag_error(err, ERR_NAN);   // check_radiance, integrator/mod.rs:285
+                // BoxFilter::evaluate == 1 for every table entry (filter/mod.rs:17-19); ray weight 1
+                acc.x = rn_add(acc.x, L.x); acc.y = rn_add(acc.y, L.y); acc.z = rn_add(acc.z, L.z); acc.w = rn_add(acc.w, 1.0f);
+            }
+        }
+    }
+    *acc_io = acc;
+}
+
+// rgb_to_xyz of the accumulated sums (spectrum/mod.rs:37-43) added into Film.pixels (merge_film_tile)
+FTN_HD void film_resolve_pixel(float4 a, float4* px) {
+    const float X = rn_add(rn_add(rn_mul(0.412453f, a.x), rn_mul(0.357580f, a.y)), rn_mul(0.180423f, a.z));
+    const float Y = rn_add(rn_add(rn_mul(0.212671f, a.x), rn_mul(0.715160f, a.y)), rn_mul(0.072169f, a.z));
+    const float Z = rn_add(rn_add(rn_mul(0.019334f, a.x), rn_mul(0.119193f, a.y)), rn_mul(0.950227f, a.z));
+    px->x = rn_add(px->x, X); px->y = rn_add(px->y, Y); px->z = rn_add(px->z, Z); px->w = rn_add(px->w, a.w);
+}
+
+// Film::new / sample_bounds (film.rs:49-58, 86-93); host side
+inline int film_geometry(const FtnFilm* f, FilmGeom* g) {
+    if (f->x_resolution < 1 || f->y_resolution < 1) return FTN_ERR_INVALID_ARGUMENT;
+    if (!(f->filter_radius[0] > 0.0f) || !(f->filter_radius[1] > 0.0f)) return FTN_ERR_INVALID_ARGUMENT;
+    g->xres = f->x_resolution; g->yres = f->y_resolution;
+    g->crop_min[0] = (int)ceilf((float)g->xres * f->crop_window[0]); g->crop_min[1] = (int)ceilf((float)g->yres * f->crop_window[2]);
+    g->crop_max[0] = (int)ceilf((float)g->xres * f->crop_window[1]); g->crop_max[1] = (int)ceilf((float)g->yres * f->crop_window[3]);
+    for (int a = 0; a < 2; ++a) { g->radius[a] = f->filter_radius[a]; g->inv_radius[a] = 1.0f / f->filter_radius[a]; }
+    for (int a = 0; a < 2; ++a) {
+        g->sb_min[a] = (int)floorf((float)g->crop_min[a] + 0.5f - g->radius[a]);
+        g->sb_max[a] = (int)ceilf((float)g->crop_max[a] - 0.5f + g->radius[a]);
+    }
+    if (g->crop_max[0] <= g->crop_min[0] || g->crop_max[1] <= g->crop_min[1]) return FTN_ERR_INVALID_ARGUMENT;
+    return FTN_OK;
+}
+
+}  // namespace ftn

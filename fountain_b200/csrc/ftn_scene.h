@@ -1,0 +1,114 @@
+// Internal (non-ABI) declarations shared by the .cu translation units of libfountain_gpu.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/fountain_gpu.h"
+#include "ftn_bvh.cuh"
+
+namespace ftn {
+
+// ---- error plumbing ------------------------------------------------------------------------------
+int set_error(int code, const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+void count_launch(uint64_t n = 1);
+
+#define FTN_CUDA(call)                                                              \
+    do {                                                                            \
+        cudaError_t e__ = (call);                                                   \
+        if (e__ != cudaSuccess) return ftn::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+#define FTN_TRY(call)                 \
+    do {                              \
+        int rc__ = (call);            \
+        if (rc__ != FTN_OK) return rc__; \
+    } while (0)
+// after every kernel launch
+#define FTN_LAUNCHED()                                   \
+    do {                                                 \
+        ftn::count_launch();                             \
+        FTN_CUDA(cudaGetLastError());                    \
+    } while (0)
+
+// ---- device-side scene tables ----------------------------------------------------------------------
+struct MeshData {
+    uint32_t first_tri, n_tris;
+    int32_t material;
+    uint32_t flags;          // FTN_MESH_*
+};
+
+struct MaterialData {
+    int32_t type;            // FtnMaterialType
+    float kd[3], ks[3], eta[3], k[3];
+    float alpha_x, alpha_y;  // after the roughness remap (microfacet.rs:40-45)
+};
+
+// light/infinite.rs: level-0 texels + the Distribution2D tables (sampling.rs:137-180)
+struct EnvLightData {
+    const F4* texels;        // w*h RGBA (A unused)
+    int32_t w, h;
+    int32_t nu, nv;          // distribution grid: nu = h, nv = w (infinite.rs:64 swaps them)
+    const float* cond_func;  // nv * nu
+    const float* cond_cdf;   // nv * (nu+1)
+    const float* cond_integral;  // nv  (== marginal func)
+    const float* marg_cdf;   // nv + 1
+    float marg_integral;
+    int32_t levels;          // 1 + floor(log2(max(w,h)))  (mipmap.rs:103)
+    M4 l2w, w2l;
+    float world_radius;      // Scene::new -> preprocess (infinite.rs:93-97)
+    float world_center[3];
+};
+
+struct LightData {
+    int32_t type;            // 0 infinite, 1 diffuse area on a sphere
+    int32_t sphere;          // area: sphere index
+    float emit[3];
+    EnvLightData env;
+};
+
+struct SceneView {
+    BvhView bvh;
+    const float* pos; const float* nrm; const float* uv;   // nrm / uv may be null
+    const uint32_t* idx;
+    const MeshData* meshes;
+    const MaterialData* materials;
+    const SphereData* spheres; uint32_t n_spheres;
+    const LightData* lights; uint32_t n_lights;
+    uint32_t n_tris;
+};
+
+}  // namespace ftn
+
+struct FtnScene {
+    int device = 0;
+    uint32_t n_verts = 0, n_tris = 0, n_meshes = 0, n_spheres = 0, n_materials = 0, n_lights = 0;
+    float* d_pos = nullptr; float* d_nrm = nullptr; float* d_uv = nullptr; uint32_t* d_idx = nullptr;
+    ftn::MeshData* d_meshes = nullptr;
+    ftn::MaterialData* d_materials = nullptr;
+    ftn::SphereData* d_spheres = nullptr;
+    ftn::LightData* d_lights = nullptr;
+    std::vector<ftn::SphereData> h_spheres;
+    std::vector<ftn::LightData> h_lights;
+    std::vector<void*> owned;        // every other device allocation (env tables, ...)
+    // aggregate
+    bool built = false;
+    ftn::F4* d_nodes = nullptr; ftn::F4* d_tris = nullptr;
+    uint32_t n_nodes = 0;
+    uint32_t* d_codes = nullptr;     // Morton code per triangle, INPUT order
+    uint32_t* d_order = nullptr;     // sorted primitive order
+    float bounds[6] = {0, 0, 0, 0, 0, 0};
+    double build_seconds = 0.0;
+    unsigned long long* d_work = nullptr;   // dynamic work-fetch counter of the batch queries
+    ftn::SceneView view() const;
+};
+
+namespace ftn {
+int scene_create(const FtnSceneDesc* d, FtnScene** out);
+int scene_destroy(FtnScene* s);
+int bvh_build(FtnScene* s);
+// device-wide exclusive scan of n uint32 (in place allowed: out may equal in)
+int exclusive_scan_u32(const uint32_t* d_in, uint32_t* d_out, size_t n, cudaStream_t st);
+// stable LSD radix sort of (key,value) pairs on `bits` low bits; result in d_keys/d_vals
+int radix_sort_pairs(uint32_t* d_keys, uint32_t* d_vals, size_t n, int bits, cudaStream_t st);
+}  // namespace ftn

@@ -1,0 +1,503 @@
+// Shading-side device functions: sampling routines, Lambert / Trowbridge-Reitz lobes, Fresnel,
+// the Bsdf frame, the infinite (env-map) and sphere area lights, the thin-lens camera.
+// Reference rows: SURVEY.md 8a a10-a18.  Geometry that feeds ray origins uses the exact ops of
+// ftn_common.cuh; BSDF / Fresnel / pdf arithmetic uses plain operators (FMA contraction allowed,
+// tolerance stated in tests/test_gpu_render.py).
+#pragma once
+#include "ftn_scene.h"
+#include "ftn_geom.cuh"
+
+namespace ftn {
+
+// ---- tiny RGB helper -------------------------------------------------------------------------------
+FTN_HD V3 operator+(V3 a, V3 b) { return V3(a.x + b.x, a.y + b.y, a.z + b.z); }
+FTN_HD V3 operator-(V3 a, V3 b) { return V3(a.x - b.x, a.y - b.y, a.z - b.z); }
+FTN_HD V3 operator*(V3 a, V3 b) { return V3(a.x * b.x, a.y * b.y, a.z * b.z); }
+FTN_HD V3 operator/(V3 a, V3 b) { return V3(a.x / b.x, a.y / b.y, a.z / b.z); }
+FTN_HD V3 operator*(V3 a, float s) { return V3(a.x * s, a.y * s, a.z * s); }
+FTN_HD V3 operator*(float s, V3 a) { return V3(s * a.x, s * a.y, s * a.z); }
+FTN_HD V3 operator/(V3 a, float s) { return V3(a.x / s, a.y / s, a.z / s); }
+FTN_HD V3 operator+(V3 a, float s) { return V3(a.x + s, a.y + s, a.z + s); }
+FTN_HD V3 operator-(V3 a, float s) { return V3(a.x - s, a.y - s, a.z - s); }
+FTN_HD V3 operator-(V3 a) { return V3(-a.x, -a.y, -a.z); }
+FTN_HD V3 vsqrt(V3 a) { return V3(sqrtf(a.x), sqrtf(a.y), sqrtf(a.z)); }
+FTN_HD bool is_black(V3 a) { return a.x == 0.0f && a.y == 0.0f && a.z == 0.0f; }          // spectrum/mod.rs:78-80
+FTN_HD bool has_nans(V3 a) { return a.x != a.x || a.y != a.y || a.z != a.z; }
+FTN_HD float max_component(V3 a) { return fmaxf(fmaxf(a.x, a.y), a.z); }                     // :100-102 (finite inputs)
+FTN_HD float dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+FTN_HD V3 cross(V3 a, V3 b) { return V3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+FTN_HD V3 normalize(V3 a) { return a * (1.0f / sqrtf(dot(a, a))); }
+FTN_HD float abs_dot(V3 a, V3 b) { return fabsf(dot(a, b)); }
+
+// ---- sampling.rs -------------------------------------------------------------------------------------
+FTN_HD void concentric_sample_disk(float u0, float u1, float* dx, float* dy) {   // :5-19
+    const float ox = 2.0f * u0 - 1.0f, oy = 2.0f * u1 - 1.0f;
+    if (ox == 0.0f && oy == 0.0f) { *dx = 0.0f; *dy = 0.0f; return; }
+    float theta, r;
+    if (fabsf(ox) > fabsf(oy)) { theta = FTN_PI_4 * (oy / ox); r = ox; }
+    else { theta = FTN_PI_2 - FTN_PI_4 * (ox / oy); r = oy; }
+    *dx = r * cosf(theta); *dy = r * sinf(theta);
+}
+FTN_HD V3 cosine_sample_hemisphere(float u0, float u1) {   // :21-25
+    float dx, dy; concentric_sample_disk(u0, u1, &dx, &dy);
+    return V3(dx, dy, sqrtf(fmaxf(0.0f, 1.0f - dx * dx - dy * dy)));
+}
+FTN_HD float power_heuristic1(float f, float g) { return (f * f) / (f * f + g * g); }   // :53-57 with nf = ng = 1
+
+// ---- level-0 MIPMap lookup, mipmap.rs:245-312, ImageWrap::Repeat -------------------------------------
+FTN_HD V3 env_texel(const EnvLightData& e, int s, int t) {
+    int ss = s % e.w; if (ss < 0) ss += e.w;
+    int tt = t % e.h; if (tt < 0) tt += e.h;
+    const F4 v = ld4(e.texels + (size_t)tt * e.w + ss);
+    return V3(v.x, v.y, v.z);
+}
+FTN_HD V3 env_triangle0(const EnvLightData& e, float sx, float ty) {   // :265-279
+    const float s = sx * (float)e.w - 0.5f, t = ty * (float)e.h - 0.5f;
+    const float fs = floorf(s), ft = floorf(t);
+    const int s0 = (int)fs, t0 = (int)ft;
+    const float ds = s - fs, dt = t - ft;
+    return env_texel(e, s0, t0) * (1.0f - ds) * (1.0f - dt) + env_texel(e, s0, t0 + 1) * (1.0f - ds) * dt
+         + env_texel(e, s0 + 1, t0) * ds * (1.0f - dt) + env_texel(e, s0 + 1, t0 + 1) * ds * dt;
+}
+// lookup_trilinear_width for the widths the env light uses (0 and 1/max(w,h)): level 0 only
+// (SURVEY section 5 note 1); a 1x1 map with width = 1 returns the texel itself.
+FTN_HD V3 env_lookup_width(const EnvLightData& e, float sx, float ty, float width) {
+    const float level = (float)e.levels - 1.0f + log2f(fmaxf(width, 1.0e-8f));
+    if (level < 0.0f) return env_triangle0(e, sx, ty);
+    if (level >= (float)(e.levels - 1)) return env_texel(e, 0, 0);
+    return env_triangle0(e, sx, ty);
+}
+
+// InfiniteAreaLight::compute_distribution, infinite.rs:63-77:
+//   func[j * width + i] = luminance(lookup(u = i/width, v = j/height, 1/max)) * sin(pi (j+.5)/height)
+// with (height, width) = (map.w, map.h) exactly as the reference destructures them (nu = width).
+FTN_HD float env_func_value(const EnvLightData& env, int k) {
+    const int width = env.nu, height = env.nv;
+    const int i = k % width, j = k / width;
+    const float v = (float)j / (float)height;
+    const float sin_theta = sinf(FTN_PI * ((float)j + 0.5f) / (float)height);
+    const float u = (float)i / (float)width;
+    const float filter = 1.0f / (float)(width > height ? width : height);
+    const V3 c = env_lookup_width(env, u, v, filter);
+    return (c.x * 0.212671f + c.y * 0.715160f + c.z * 0.072169f) * sin_theta;   // Spectrum::luminance, spectrum/mod.rs:104-107
+}
+// Distribution1D::new for one row (sampling.rs:84-107): the running f32 sum is sequential by
+// definition, so one thread owns one row.
+FTN_HD void dist_row_build(const float* f, int nu, float* c, float* integral) {
+    float run = 0.0f;
+    c[0] = 0.0f;
+    const float nf = (float)nu;
+    for (int i = 1; i <= nu; ++i) { run = rn_add(run, rn_div(f[i - 1], nf)); c[i] = run; }
+    const float total = run;
+    *integral = total;
+    if (total == 0.0f) { for (int i = 1; i <= nu; ++i) c[i] = rn_div((float)i, nf); }
+    else { for (int i = 1; i <= nu; ++i) c[i] = rn_div(c[i], total); }
+}
+
+// sampling.rs:66-81 over a device array: index of the last cdf entry <= u, clamped to [0, size-2]
+FTN_HD int search_sorted_le(const float* cdf, int size, float u) {
+    int first = 0, len = size;
+    while (len > 0) {
+        const int half = len >> 1, middle = first + half;
+        if (cdf[middle] <= u) { first = middle + 1; len -= half + 1; }
+        else len = half;
+    }
+    int r = first - 1;
+    if (r < 0) r = 0;
+    if (r > size - 2) r = size - 2;
+    return r;
+}
+// Distribution1D::sample_continuous, sampling.rs:121-134
+FTN_HD void dist1d_sample(const float* func, const float* cdf, int n, float integral, float u, float* x, float* pdf, int* idx) {
+    const int i = search_sorted_le(cdf, n + 1, u);
+    float du = u - cdf[i];
+    const float w = cdf[i + 1] - cdf[i];
+    if (w > 0.0f) du /= w;
+    *pdf = func[i] / integral;
+    *x = ((float)i + du) / (float)n;
+    *idx = i;
+}
+// Distribution2D::sample_continuous / pdf, sampling.rs:163-179
+FTN_HD void env_dist_sample(const EnvLightData& e, float u0, float u1, float* d0, float* d1, float* pdf) {
+    float pdf1, pdf0; int v, dummy;
+    dist1d_sample(e.cond_integral, e.marg_cdf, e.nv, e.marg_integral, u1, d1, &pdf1, &v);
+    dist1d_sample(e.cond_func + (size_t)v * e.nu, e.cond_cdf + (size_t)v * (e.nu + 1), e.nu, e.cond_integral[v], u0, d0, &pdf0, &dummy);
+    *pdf = pdf0 * pdf1;
+}
+FTN_HD float env_dist_pdf(const EnvLightData& e, float px, float py) {
+    const float fu = px * (float)e.nu, fv = py * (float)e.nv;
+    int iu = (fu > 0.0f) ? (int)fminf(fu, 2.0e9f) : 0; if (iu > e.nu - 1) iu = e.nu - 1;
+    int iv = (fv > 0.0f) ? (int)fminf(fv, 2.0e9f) : 0; if (iv > e.nv - 1) iv = e.nv - 1;
+    return e.cond_func[(size_t)iv * e.nu + iu] / e.marg_integral;
+}
+
+FTN_HD float spherical_theta(V3 v) { return acosf(clampf(v.z, -1.0f, 1.0f)); }   // geometry/mod.rs:23-25
+FTN_HD float spherical_phi(V3 v) { const float p = atan2f(v.y, v.x); return (p < 0.0f) ? p + (2.0f * FTN_PI) : p; }   // :27-34
+
+// InfiniteAreaLight::environment_emitted_radiance, infinite.rs:156-164
+FTN_HD V3 env_emitted(const EnvLightData& e, V3 dir) {
+    const V3 w = normalize(transform_vector(e.w2l, dir));
+    return env_lookup_width(e, spherical_phi(w) * (1.0f / (2.0f * FTN_PI)), spherical_theta(w) * FTN_INV_PI, 0.0f);
+}
+// InfiniteAreaLight::pdf_incident_radiance, infinite.rs:142-154
+FTN_HD float env_pdf(const EnvLightData& e, V3 wi_w) {
+    const V3 wi = transform_vector(e.w2l, wi_w);
+    const float theta = spherical_theta(wi), phi = spherical_phi(wi);
+    const float st = sinf(theta);
+    if (st == 0.0f) return 0.0f;
+    return env_dist_pdf(e, phi * (1.0f / (2.0f * FTN_PI)), theta * FTN_INV_PI) / (2.0f * FTN_PI * FTN_PI * st);
+}
+// InfiniteAreaLight::sample_incident_radiance, infinite.rs:99-140.  Returns false where the
+// reference hits unimplemented!() (map_pdf == 0).
+FTN_HD bool env_sample(const EnvLightData& e, float u0, float u1, V3* wi, float* pdf, V3* radiance) {
+    float uvx, uvy, map_pdf;
+    env_dist_sample(e, u0, u1, &uvx, &uvy, &map_pdf);
+    if (map_pdf == 0.0f) return false;
+    const float theta = uvy * FTN_PI, phi = uvx * 2.0f * FTN_PI;
+    const float st = sinf(theta), ct = cosf(theta);
+    *wi = transform_vector(e.l2w, V3(st * cosf(phi), st * sinf(phi), ct));
+    *pdf = (st == 0.0f) ? 0.0f : map_pdf / (2.0f * FTN_PI * FTN_PI * st);
+    *radiance = env_lookup_width(e, uvx, uvy, 0.0f);
+    return true;
+}
+
+// ---- fresnel.rs ------------------------------------------------------------------------------------------
+FTN_HD float fresnel_dielectric(float cos_i, float eta_i, float eta_t) {   // :4-22
+    cos_i = clampf(cos_i, -1.0f, 1.0f);
+    if (!(cos_i > 0.0f)) { const float t = eta_i; eta_i = eta_t; eta_t = t; cos_i = fabsf(cos_i); }
+    const float sin_i = sqrtf(fmaxf(1.0f - cos_i * cos_i, 0.0f));
+    const float sin_t = eta_i / eta_t * sin_i;
+    if (sin_t >= 1.0f) return 1.0f;
+    const float cos_t = sqrtf(fmaxf(1.0f - sin_t * sin_t, 0.0f));
+    const float rpar = ((eta_t * cos_i) - (eta_i * cos_t)) / ((eta_t * cos_i) + (eta_i * cos_t));
+    const float rper = ((eta_i * cos_i) - (eta_t * cos_t)) / ((eta_i * cos_i) + (eta_t * cos_t));
+    return (rpar * rpar + rper * rper) / 2.0f;
+}
+FTN_HD V3 fresnel_conductor(float cos_i, V3 eta_t, V3 k) {   // :25-48 with eta_i = 1 (metal.rs:54)
+    cos_i = clampf(cos_i, -1.0f, 1.0f);
+    const V3 one = v3s(1.0f);
+    const V3 eta = eta_t / one, eta_k = k / one;
+    const float cos2 = cos_i * cos_i, sin2 = 1.0f - cos2;
+    const V3 eta2 = eta * eta, eta_k2 = eta_k * eta_k;
+    const V3 t0 = eta2 - eta_k2 - sin2;
+    const V3 a2plusb2 = vsqrt(t0 * t0 + 4.0f * eta2 * eta_k2);
+    const V3 t1 = a2plusb2 + cos2;
+    const V3 a = vsqrt(0.5f * (a2plusb2 + t0));
+    const V3 t2 = (2.0f * cos_i) * a;
+    const V3 Rs = (t1 - t2) / (t1 + t2);
+    const V3 t3 = cos2 * a2plusb2 + sin2 * sin2;
+    const V3 t4 = t2 * sin2;
+    const V3 Rp = Rs * (t3 - t4) / (t3 + t4);
+    return 0.5f * (Rp + Rs);
+}
+
+// ---- reflection/mod.rs trig helpers :24-86 -------------------------------------------------------------------
+FTN_HD float cos2_theta(V3 w) { return w.z * w.z; }
+FTN_HD float abs_cos_theta(V3 w) { return fabsf(w.z); }
+FTN_HD float sin2_theta(V3 w) { return fmaxf(0.0f, 1.0f - cos2_theta(w)); }
+FTN_HD float sin_theta(V3 w) { return sqrtf(sin2_theta(w)); }
+FTN_HD float tan_theta(V3 w) { return sin_theta(w) / w.z; }
+FTN_HD float tan2_theta(V3 w) { return sin2_theta(w) / cos2_theta(w); }
+FTN_HD float cos_phi(V3 w) { const float s = sin_theta(w); return (s == 0.0f) ? 1.0f : clampf(w.x / s, -1.0f, 1.0f); }
+FTN_HD float sin_phi(V3 w) { const float s = sin_theta(w); return (s == 0.0f) ? 0.0f : clampf(w.y / s, -1.0f, 1.0f); }
+FTN_HD bool same_hemisphere(V3 a, V3 b) { return sign_positive(a.z) == sign_positive(b.z); }
+FTN_HD V3 reflect(V3 wo, V3 n) { return -wo + 2.0f * dot(wo, n) * n; }
+FTN_HD bool is_inf(float f) { return fabsf(f) == FTN_INF; }
+
+enum { BXDF_REFLECTION = 1, BXDF_TRANSMISSION = 2, BXDF_DIFFUSE = 4, BXDF_GLOSSY = 8, BXDF_SPECULAR = 16, BXDF_ALL = 31 };
+
+// One lobe of a Bsdf (bsdf.rs holds up to 8 `dyn BxDF`; the in-scope materials produce at most 2).
+struct Lobe {
+    int kind;          // 0 LambertianReflection, 1 MicrofacetReflection<TrowbridgeReitz, F>
+    V3 r;
+    float ax, ay;
+    int fresnel;       // 0 FresnelConductor{1, eta, k}, 1 FresnelDielectric{1.5, 1.0}
+    V3 eta, k;
+};
+FTN_HD int lobe_type(const Lobe& l) { return l.kind == 0 ? (BXDF_REFLECTION | BXDF_DIFFUSE) : (BXDF_REFLECTION | BXDF_GLOSSY); }
+FTN_HD bool lobe_matches(const Lobe& l, int flags) { const int t = lobe_type(l); return (flags & t) == t; }
+
+// microfacet.rs:135-160
+FTN_HD float tr_d(const Lobe& l, V3 wh) {
+    const float t2 = tan2_theta(wh);
+    if (is_inf(t2)) return 0.0f;
+    const float cos4 = cos2_theta(wh) * cos2_theta(wh);
+    const float cp = cos_phi(wh), sp = sin_phi(wh);
+    const float e = ((cp * cp) / (l.ax * l.ax) + (sp * sp) / (l.ay * l.ay)) * t2;
+    return 1.0f / (FTN_PI * l.ax * l.ay * cos4 * (1.0f + e) * (1.0f + e));
+}
+FTN_HD float tr_lambda(const Lobe& l, V3 w) {
+    const float att = fabsf(tan_theta(w));
+    if (is_inf(att)) return 0.0f;
+    const float cp = cos_phi(w), sp = sin_phi(w);
+    const float alpha = sqrtf((cp * cp) * l.ax * l.ax + (sp * sp) * l.ay * l.ay);
+    const float a2t2 = (alpha * att) * (alpha * att);
+    return (-1.0f + sqrtf(1.0f + a2t2)) / 2.0f;
+}
+FTN_HD float tr_pdf(const Lobe& l, V3 wh) { return tr_d(l, wh) * abs_cos_theta(wh); }   // microfacet.rs:28-31
+// microfacet.rs:162-186 (full-NDF sampling)
+FTN_HD V3 tr_sample_wh(const Lobe& l, V3 wo, float u0, float u1) {
+    float cos_t, phi;
+    if (l.ax == l.ay) {
+        const float tan2 = (l.ax * l.ax) * u0 / (1.0f - u0);
+        cos_t = 1.0f / sqrtf(1.0f + tan2);
+        phi = 2.0f * FTN_PI * u1;
+    } else {
+        phi = atanf(l.ay / l.ax * tanf(2.0f * FTN_PI * u1 + 0.5f * FTN_PI));
+        if (u1 > 0.5f) phi += FTN_PI;
+        const float sp = sinf(phi), cp = cosf(phi);
+        const float alpha2 = 1.0f / ((cp * cp) / (l.ax * l.ax) + (sp * sp) / (l.ay * l.ay));
+        const float tan2 = alpha2 * u0 / (1.0f - u0);
+        cos_t = 1.0f / sqrtf(1.0f + tan2);
+    }
+    const float sin_t = sqrtf(fmaxf(0.0f, 1.0f - cos_t * cos_t));
+    const V3 wh = V3(sin_t * cosf(phi), sin_t * sinf(phi), cos_t);   // spherical_direction, math.rs:74-80
+    return same_hemisphere(wo, wh) ? wh : -wh;
+}
+FTN_HD V3 lobe_fresnel(const Lobe& l, float cos_i) {
+    if (l.fresnel == 0) return fresnel_conductor(fabsf(cos_i), l.eta, l.k);   // fresnel.rs:70-73
+    return v3s(fresnel_dielectric(cos_i, 1.5f, 1.0f));                         // plastic.rs:34
+}
+FTN_HD V3 lobe_f(const Lobe& l, V3 wo, V3 wi) {
+    if (l.kind == 0) return l.r * FTN_INV_PI;   // reflection/mod.rs:159-161
+    const float cos_o = abs_cos_theta(wo), cos_i = abs_cos_theta(wi);   // :318-336
+    V3 wh = wi + wo;
+    if (cos_i == 0.0f || cos_o == 0.0f || (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f)) return v3s(0.0f);
+    wh = normalize(wh);
+    const V3 whf = (wh.z < 0.0f) ? -wh : wh;   // faceforward(wh, (0,0,1)): dot = wh.z
+    const V3 F = lobe_fresnel(l, dot(wi, whf));
+    const float G = 1.0f / (1.0f + tr_lambda(l, wo) + tr_lambda(l, wi));   // microfacet.rs:21-23
+    return l.r * tr_d(l, wh) * G * F / (4.0f * cos_i * cos_o);
+}
+FTN_HD float lobe_pdf(const Lobe& l, V3 wo, V3 wi) {
+    if (l.kind == 0) return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * FTN_INV_PI : 0.0f;   // :140-146
+    if (!same_hemisphere(wo, wi)) return 0.0f;   // :354-360
+    const V3 wh = normalize(wo + wi);
+    return tr_pdf(l, wh) / (4.0f * dot(wo, wh));
+}
+struct ScatterSample { V3 f, wi; float pdf; int type; };
+FTN_HD bool lobe_sample_f(const Lobe& l, V3 wo, float u0, float u1, ScatterSample* s) {
+    if (l.kind == 0) {   // :131-138
+        V3 wi = cosine_sample_hemisphere(u0, u1);
+        if (wo.z < 0.0f) wi.z *= -1.0f;
+        s->pdf = lobe_pdf(l, wo, wi); s->f = lobe_f(l, wo, wi); s->wi = wi; s->type = lobe_type(l);
+        return true;
+    }
+    const V3 wh = tr_sample_wh(l, wo, u0, u1);   // :338-352
+    const V3 wi = reflect(wo, wh);
+    if (!same_hemisphere(wo, wi)) return false;
+    s->pdf = tr_pdf(l, wh) / (4.0f * dot(wo, wh));
+    s->f = lobe_f(l, wo, wi); s->wi = wi; s->type = lobe_type(l);
+    return true;
+}
+
+// reflection/bsdf.rs:8-148
+struct Bsdf {
+    V3 ns, ng, ss, ts;
+    Lobe lobes[2];
+    int n;
+};
+FTN_HD void bsdf_init(Bsdf* b, V3 ns, V3 ng, V3 shading_dpdu) {   // :31-46
+    b->ns = ns; b->ng = ng;
+    b->ss = x_normalize(shading_dpdu);
+    b->ts = x_normalize(x_cross(ns, b->ss));
+    b->n = 0;
+}
+FTN_HD int bsdf_num_components(const Bsdf& b, int flags) { int c = 0; for (int i = 0; i < b.n; ++i) if (lobe_matches(b.lobes[i], flags)) ++c; return c; }
+FTN_HD V3 bsdf_to_local(const Bsdf& b, V3 v) { return V3(dot(v, b.ss), dot(v, b.ts), dot(v, b.ns)); }
+FTN_HD V3 bsdf_to_world(const Bsdf& b, V3 v) {
+    return V3(b.ss.x * v.x + b.ts.x * v.y + b.ns.x * v.z, b.ss.y * v.x + b.ts.y * v.y + b.ns.y * v.z, b.ss.z * v.x + b.ts.z * v.y + b.ns.z * v.z);
+}
+FTN_HD V3 bsdf_sum_f(const Bsdf& b, V3 wo, V3 wi, bool refl, int flags) {
+    V3 sum = v3s(0.0f);
+    for (int i = 0; i < b.n; ++i) {
+        if (!lobe_matches(b.lobes[i], flags)) continue;
+        const int ty = lobe_type(b.lobes[i]);
+        if ((refl && (ty & BXDF_REFLECTION)) || (!refl && (ty & BXDF_TRANSMISSION))) sum = sum + lobe_f(b.lobes[i], wo, wi);
+    }
+    return sum;
+}
+FTN_HD V3 bsdf_f(const Bsdf& b, V3 wo_w, V3 wi_w, int flags) {   // :67-82
+    const V3 wi = bsdf_to_local(b, wi_w), wo = bsdf_to_local(b, wo_w);
+    if (wo.z == 0.0f) return v3s(0.0f);
+    const bool refl = dot(wi_w, b.ng) * dot(wo_w, b.ng) > 0.0f;
+    return bsdf_sum_f(b, wo, wi, refl, flags);
+}
+FTN_HD float bsdf_pdf(const Bsdf& b, V3 wo_w, V3 wi_w, int flags) {   // :131-144
+    const V3 wo = bsdf_to_local(b, wo_w), wi = bsdf_to_local(b, wi_w);
+    if (wo.z == 0.0f) return 0.0f;
+    float p = 0.0f; int nm = 0;
+    for (int i = 0; i < b.n; ++i) if (lobe_matches(b.lobes[i], flags)) { p += lobe_pdf(b.lobes[i], wo, wi); ++nm; }
+    return nm > 0 ? p / (float)nm : 0.0f;
+}
+FTN_HD bool bsdf_sample_f(const Bsdf& b, V3 wo_w, float u0, float u1, int flags, ScatterSample* out) {   // :85-129
+    const int nm = bsdf_num_components(b, flags);
+    if (nm == 0) return false;
+    const float matching = (float)nm;
+    const int comp = (int)fminf(floorf(u0 * matching), matching - 1.0f);
+    int which = -1, cnt = comp;
+    for (int i = 0; i < b.n; ++i) if (lobe_matches(b.lobes[i], flags)) { if (cnt-- == 0) { which = i; break; } }
+    const float ur0 = u0 * matching - (float)comp;
+    const V3 wo = bsdf_to_local(b, wo_w);
+    ScatterSample s;
+    if (!lobe_sample_f(b.lobes[which], wo, ur0, u1, &s)) return false;
+    if (s.pdf == 0.0f) return false;
+    const V3 wi = s.wi;
+    const V3 wi_w = bsdf_to_world(b, wi);
+    float pdf = s.pdf;
+    if (nm > 1) {
+        for (int i = 0; i < b.n; ++i) if (i != which && lobe_matches(b.lobes[i], flags)) pdf += lobe_pdf(b.lobes[i], wo, wi);
+        pdf /= matching;
+    }
+    const bool refl = dot(wi_w, b.ng) * dot(wo_w, b.ng) > 0.0f;
+    out->f = bsdf_sum_f(b, wo, wi, refl, flags);
+    out->wi = wi_w; out->pdf = pdf; out->type = s.type;
+    return true;
+}
+
+// Material::compute_scattering_functions: matte.rs:36-52, metal.rs:38-65, plastic.rs:24-48
+FTN_HD void material_bsdf(const MaterialData& m, Bsdf* b) {
+    if (m.type == FTN_MATERIAL_MATTE) {
+        const V3 r = V3(clampf(m.kd[0], 0.0f, FTN_INF), clampf(m.kd[1], 0.0f, FTN_INF), clampf(m.kd[2], 0.0f, FTN_INF));
+        if (!is_black(r)) { Lobe& l = b->lobes[b->n++]; l.kind = 0; l.r = r; }
+    } else if (m.type == FTN_MATERIAL_METAL) {
+        Lobe& l = b->lobes[b->n++];
+        l.kind = 1; l.r = v3s(1.0f); l.ax = m.alpha_x; l.ay = m.alpha_y; l.fresnel = 0;
+        l.eta = V3(m.eta[0], m.eta[1], m.eta[2]); l.k = V3(m.k[0], m.k[1], m.k[2]);
+    } else {
+        const V3 kd = V3(m.kd[0], m.kd[1], m.kd[2]), ks = V3(m.ks[0], m.ks[1], m.ks[2]);
+        if (!is_black(kd)) { Lobe& l = b->lobes[b->n++]; l.kind = 0; l.r = kd; }
+        if (!is_black(ks)) { Lobe& l = b->lobes[b->n++]; l.kind = 1; l.r = ks; l.ax = m.alpha_x; l.ay = m.alpha_x; l.fresnel = 1; l.eta = v3s(0.0f); l.k = v3s(0.0f); }
+    }
+}
+
+// ---- surface reconstruction -------------------------------------------------------------------------------------
+// SurfaceHit (interaction.rs:12-18) + what Bsdf::new needs (shading normal, shading dpdu).
+struct Surface {
+    V3 p, p_err, n;      // hit.p, hit.p_err, hit.n
+    V3 ns, sdpdu;        // shading_n, shading_geom.dpdu
+    V3 wo;               // SurfaceInteraction.wo
+    int material;        // -1 none
+    int light;           // area light index, -1 none
+};
+
+// Triangle::intersect tail, triangle.rs:270-392, from the slot's vertices and the barycentrics
+// the traversal found (exact ops: p, p_err and n feed spawned ray origins).
+FTN_HD void triangle_surface(const SceneView& sc, uint32_t slot, const TriHit& h, V3 ray_d, Surface* s) {
+    const F4 a = ld4(sc.bvh.tris + 3 * (size_t)slot), b = ld4(sc.bvh.tris + 3 * (size_t)slot + 1), c = ld4(sc.bvh.tris + 3 * (size_t)slot + 2);
+    const V3 p0 = V3(a.x, a.y, a.z), p1 = V3(b.x, b.y, b.z), p2 = V3(c.x, c.y, c.z);
+    const uint32_t prim = f2u(a.w), mesh_id = f2u(b.w);
+    const MeshData mesh = sc.meshes[mesh_id];
+    const uint32_t v0 = sc.idx[3 * (size_t)prim], v1 = sc.idx[3 * (size_t)prim + 1], v2 = sc.idx[3 * (size_t)prim + 2];
+    float uv[3][2] = {{0.0f, 0.0f}, {1.0f, 0.0f}, {1.0f, 1.0f}};   // triangle.rs:131-143
+    if (sc.uv) {
+        uv[0][0] = sc.uv[2 * v0]; uv[0][1] = sc.uv[2 * v0 + 1]; uv[1][0] = sc.uv[2 * v1]; uv[1][1] = sc.uv[2 * v1 + 1];
+        uv[2][0] = sc.uv[2 * v2]; uv[2][1] = sc.uv[2 * v2 + 1];
+    }
+    const float duv02x = rn_sub(uv[0][0], uv[2][0]), duv02y = rn_sub(uv[0][1], uv[2][1]);
+    const float duv12x = rn_sub(uv[1][0], uv[2][0]), duv12y = rn_sub(uv[1][1], uv[2][1]);
+    const V3 dp02 = x_sub(p0, p2), dp12 = x_sub(p1, p2);
+    const float determinant = rn_sub(rn_mul(duv02x, duv12y), rn_mul(duv02y, duv12x));
+    V3 dpdu, dpdv;
+    if (fabsf(determinant) < 1.0e-8f) {
+        // degenerate uv; a zero-area triangle cannot reach here (det == 0 rejects it in the hit test)
+        const V3 ng = x_cross(x_sub(p2, p0), x_sub(p1, p0));
+        coordinate_system(x_normalize(ng), &dpdu, &dpdv);
+    } else {
+        const float inv = rn_div(1.0f, determinant);
+        dpdu = x_scale(x_sub(x_scale(dp02, duv12y), x_scale(dp12, duv02y)), inv);
+    }
+    const float xs = rn_add(rn_add(fabsf(rn_mul(h.b0, p0.x)), fabsf(rn_mul(h.b1, p1.x))), fabsf(rn_mul(h.b2, p2.x)));
+    const float ys = rn_add(rn_add(fabsf(rn_mul(h.b0, p0.y)), fabsf(rn_mul(h.b1, p1.y))), fabsf(rn_mul(h.b2, p2.y)));
+    const float zs = rn_add(rn_add(fabsf(rn_mul(h.b0, p0.z)), fabsf(rn_mul(h.b1, p1.z))), fabsf(rn_mul(h.b2, p2.z)));
+    const float g7 = gamma_n(7);
+    s->p_err = V3(rn_mul(g7, xs), rn_mul(g7, ys), rn_mul(g7, zs));
+    s->p = x_add(x_add(x_scale(p0, h.b0), x_scale(p1, h.b1)), x_scale(p2, h.b2));
+    V3 n = x_normalize(x_cross(dp02, dp12));
+    V3 ns = n;
+    if (mesh.flags & FTN_MESH_FLIP_NORMALS) { n = x_scale(n, -1.0f); ns = x_scale(ns, -1.0f); }
+    V3 sdpdu = dpdu;
+    if (sc.nrm) {
+        const V3 n0 = V3(sc.nrm[3 * v0], sc.nrm[3 * v0 + 1], sc.nrm[3 * v0 + 2]);
+        const V3 n1 = V3(sc.nrm[3 * v1], sc.nrm[3 * v1 + 1], sc.nrm[3 * v1 + 2]);
+        const V3 n2 = V3(sc.nrm[3 * v2], sc.nrm[3 * v2 + 1], sc.nrm[3 * v2 + 2]);
+        ns = x_normalize(x_add(x_add(x_scale(n0, h.b0), x_scale(n1, h.b1)), x_scale(n2, h.b2)));
+        V3 ss = x_normalize(dpdu);
+        V3 ts = x_cross(ns, ss);
+        if (x_len2(ts) > 0.0f) { ts = x_normalize(ts); ss = x_cross(ts, ns); }
+        else { coordinate_system(ns, &ts, &ss); }
+        sdpdu = ss;
+        n = faceforward(n, ns);
+    }
+    s->n = n; s->ns = ns; s->sdpdu = sdpdu;
+    s->wo = x_neg(ray_d);
+    s->material = mesh.material;
+    s->light = -1;
+}
+
+FTN_HD void sphere_surface(const SphereData& sd, const SphereHit& h, Surface* s) {
+    s->p = h.p; s->p_err = h.p_err; s->n = h.n; s->ns = h.ns; s->sdpdu = h.dpdu; s->wo = h.wo;
+    s->material = sd.material; s->light = sd.light;
+}
+
+// SurfaceHit::spawn_ray, interaction.rs:22-30
+FTN_HD V3 spawn_origin(const Surface& s, V3 dir) { return offset_ray_origin(s.p, s.p_err, s.n, dir); }
+
+// ---- sphere area light (light/diffuse.rs, shapes/mod.rs:43-66, sphere.rs:202-218) ---------------------
+struct ShapeSample { V3 p, p_err, n; };
+FTN_HD ShapeSample sphere_sample(const SphereData& sd, float u0, float u1) {
+    const float z = rn_sub(1.0f, rn_mul(2.0f, u0));   // uniform_sample_sphere, sampling.rs:37-42
+    const float r = rn_sqrt(fmaxf(rn_sub(1.0f, rn_mul(z, z)), 0.0f));
+    const float phi = rn_mul(rn_mul(2.0f, FTN_PI), u1);
+    V3 p_obj = x_scale(V3(rn_mul(r, cosf(phi)), rn_mul(r, sinf(phi)), z), sd.radius);
+    V3 n = x_normalize(transform_normal_inv(sd.w2o, p_obj));
+    if (sd.reverse_orientation) n = x_scale(n, -1.0f);
+    p_obj = x_scale(p_obj, rn_div(sd.radius, x_len(p_obj)));
+    const V3 pe = x_scale(x_abs(p_obj), gamma_n(5));
+    ShapeSample s;
+    s.p = point_tf_err_to_err(sd.o2w, p_obj, pe, &s.p_err);
+    s.n = n;
+    return s;
+}
+// Shape::pdf_from_ref, shapes/mod.rs:55-66
+FTN_HD float sphere_pdf_from_ref(const SphereData& sd, const Surface& ref, V3 wi) {
+    RayF ray; ray.o = spawn_origin(ref, wi); ray.d = wi; ray.t_max = FTN_INF; ray.time = 0.0f;
+    SphereHit h;
+    if (!sphere_intersect(sd, ray, &h)) return 0.0f;
+    const V3 d = x_sub(ref.p, h.p);
+    return rn_div(x_len2(d), rn_mul(x_abs_dot(h.n, x_neg(wi)), sd.area));
+}
+
+// ---- thin-lens perspective camera, camera/mod.rs:117-143 (exact ops: primary rays match the oracle) -----
+FTN_HD RayF camera_ray(const FtnCamera& cam, float fx, float fy, float lx, float ly, float tu) {
+    M4 r2c, c2w;
+    for (int i = 0; i < 16; ++i) { r2c.m[i] = cam.raster_to_camera[i]; c2w.m[i] = cam.camera_to_world[i]; }
+    const V3 pc = transform_point(r2c, V3(fx, fy, 0.0f));
+    RayF ray;
+    ray.o = V3(0.0f, 0.0f, 0.0f);
+    ray.d = x_normalize(pc);
+    ray.time = rn_add(rn_mul(rn_sub(1.0f, tu), cam.shutter_open), rn_mul(tu, cam.shutter_close));   // lerp, math.rs:21-23
+    ray.t_max = FTN_INF;
+    if (cam.lens_radius > 0.0f) {
+        float dx, dy;
+        {   // concentric_sample_disk with exact ops
+            const float ox = rn_sub(rn_mul(2.0f, lx), 1.0f), oy = rn_sub(rn_mul(2.0f, ly), 1.0f);
+            if (ox == 0.0f && oy == 0.0f) { dx = 0.0f; dy = 0.0f; }
+            else {
+                float theta, r;
+                if (fabsf(ox) > fabsf(oy)) { theta = rn_mul(FTN_PI_4, rn_div(oy, ox)); r = ox; }
+                else { theta = rn_sub(FTN_PI_2, rn_mul(FTN_PI_4, rn_div(ox, oy))); r = oy; }
+                dx = rn_mul(r, cosf(theta)); dy = rn_mul(r, sinf(theta));
+            }
+        }
+        const float plx = rn_mul(cam.lens_radius, dx), ply = rn_mul(cam.lens_radius, dy);
+        const float ft = rn_div(cam.focal_distance, ray.d.z);
+        const V3 pf = x_add(ray.o, x_scale(ray.d, ft));
+        ray.o = V3(plx, ply, 0.0f);
+        ray.d = x_normalize(x_sub(pf, ray.o));
+    }
+    V3 oe, de;
+    return ray_transform_err(c2w, ray, &oe, &de);
+}
+
+}  // namespace ftn

@@ -1,0 +1,452 @@
+// Scene upload into flat SoA device buffers and the Morton-code LBVH build
+// (replaces Scene::new scene/mod.rs:32-49 and BVH::build bvh.rs:27-158).
+//
+// Build pipeline, all on the device:
+//   k_tri_bounds      per-triangle AABB + centroid (Triangle::world_bound triangle.rs:151-157,
+//                     Bounds3::centroid bounds.rs:161-163) and the scene / centroid bounds
+//   k_morton          morton3 (morton.rs:3-36) of Bounds3f::offset (bounds.rs:200-206)
+//   radix_sort_pairs  stable sort of (code, primitive) -- sort_scan.cu
+//   k_lbvh_topology   Karras hierarchy over the sorted keys
+//   k_lbvh_refit      bottom-up boxes with per-node arrival counters
+//   k_lbvh_emit       leaf collapse (<= FTN_LEAF_MAX triangles) + BVH2x64 node records
+//   k_gather_tris     48-byte pre-gathered triangle records in leaf order
+#include "ftn_scene.h"
+#include "ftn_lbvh.cuh"
+#include <chrono>
+#include <cmath>
+#include <cstring>
+
+namespace ftn {
+
+// ---- ordered-float atomics: exact (min/max do not round), order independent --------------------
+__device__ __forceinline__ uint32_t float_flip(float f) { uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float float_unflip(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u); }
+
+struct BuildBounds { uint32_t scene_lo[3], scene_hi[3], cen_lo[3], cen_hi[3]; };
+
+__global__ void k_init_bounds(BuildBounds* b) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        for (int i = 0; i < 3; ++i) {
+            b->scene_lo[i] = float_flip(FLT_MAX); b->scene_hi[i] = float_flip(-FLT_MAX);   // Bounds3::empty, bounds.rs:125-127
+            b->cen_lo[i] = float_flip(FLT_MAX); b->cen_hi[i] = float_flip(-FLT_MAX);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_tri_bounds(const float* __restrict__ pos, const uint32_t* __restrict__ idx, uint32_t n_tris,
+             F4* __restrict__ tri_lo, F4* __restrict__ tri_hi, BuildBounds* __restrict__ gb) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    float clo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, chi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    if (i < n_tris) {
+        F4 l, h; float c[3];
+        tri_bounds_centroid(pos, idx, i, &l, &h, c);
+        lo[0] = l.x; lo[1] = l.y; lo[2] = l.z; hi[0] = h.x; hi[1] = h.y; hi[2] = h.z;
+        for (int a = 0; a < 3; ++a) { clo[a] = c[a]; chi[a] = c[a]; }
+        tri_lo[i] = l; tri_hi[i] = h;   // centroid.x / .y ride in the w lanes; centroid.z is recomputed
+    }
+    // warp reduce, then one atomic per warp per component
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+            clo[a] = fminf(clo[a], __shfl_xor_sync(0xffffffffu, clo[a], o));
+            chi[a] = fmaxf(chi[a], __shfl_xor_sync(0xffffffffu, chi[a], o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&gb->scene_lo[a], float_flip(lo[a])); atomicMax(&gb->scene_hi[a], float_flip(hi[a]));
+            atomicMin(&gb->cen_lo[a], float_flip(clo[a])); atomicMax(&gb->cen_hi[a], float_flip(chi[a]));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_morton(const F4* __restrict__ tri_lo, const F4* __restrict__ tri_hi, uint32_t n_tris, const BuildBounds* __restrict__ gb,
+         uint32_t* __restrict__ codes_in_order, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_tris) return;
+    float cmin[3], cmax[3];
+    for (int a = 0; a < 3; ++a) { cmin[a] = float_unflip(gb->cen_lo[a]); cmax[a] = float_unflip(gb->cen_hi[a]); }
+    const uint32_t code = tri_morton(tri_lo[i], tri_hi[i], cmin, cmax);
+    codes_in_order[i] = code;
+    keys[i] = code;
+    vals[i] = i;
+}
+
+// ---- Karras topology, refit, emission (bodies in ftn_lbvh.cuh) ----------------------------------------------
+__global__ void __launch_bounds__(256)
+k_lbvh_topology(const uint32_t* __restrict__ codes, int n, LbvhArrays a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n - 1) lbvh_topology_node(codes, n, i, a);
+}
+
+// one thread per leaf climbs; the second arrival at a node owns it (both children are complete)
+__global__ void __launch_bounds__(256)
+k_lbvh_refit(int n, LbvhArrays a, const F4* __restrict__ leaf_lo, const F4* __restrict__ leaf_hi) {
+    const int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+    if (leaf >= n) return;
+    uint32_t node = a.parent[n - 1 + leaf];
+    while (node != 0xFFFFFFFFu) {
+        __threadfence();
+        if (atomicAdd(&a.arrive[node], 1u) == 0u) return;
+        __threadfence();
+        lbvh_join_children(a, leaf_lo, leaf_hi, node);
+        node = a.parent[node];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_gather_leaf_boxes(const F4* __restrict__ tri_lo, const F4* __restrict__ tri_hi, const uint32_t* __restrict__ order, uint32_t n,
+                    F4* __restrict__ leaf_lo, F4* __restrict__ leaf_hi) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    leaf_lo[i] = tri_lo[order[i]]; leaf_hi[i] = tri_hi[order[i]];
+}
+
+__global__ void __launch_bounds__(256)
+k_lbvh_survive(int n, LbvhArrays a, uint32_t* __restrict__ survive) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n - 1) survive[i] = lbvh_survives(a, i);
+}
+
+__global__ void __launch_bounds__(256)
+k_lbvh_emit(int n, LbvhArrays a, const F4* __restrict__ leaf_lo, const F4* __restrict__ leaf_hi,
+            const uint32_t* __restrict__ survive, const uint32_t* __restrict__ new_index, F4* __restrict__ nodes) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n - 1 && survive[i]) lbvh_emit_node(a, leaf_lo, leaf_hi, survive, new_index, i, nodes);
+}
+
+__global__ void k_lbvh_emit_single(uint32_t n, const BuildBounds* gb, F4* nodes) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) { lo[a] = float_unflip(gb->scene_lo[a]); hi[a] = float_unflip(gb->scene_hi[a]); }
+    lbvh_emit_single(n, lo, hi, nodes);
+}
+
+__global__ void __launch_bounds__(256)
+k_gather_tris(const float* __restrict__ pos, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ order, uint32_t n,
+              const MeshData* __restrict__ meshes, uint32_t n_meshes, F4* __restrict__ tris) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) lbvh_gather_tri(pos, idx, order, i, meshes, n_meshes, tris);
+}
+
+// ---- env-map tables on the device -------------------------------------------------------------------------
+// MIPMap level-0 lookups (mipmap.rs:245-312); shared with the shading kernels via ftn_shade.cuh.
+}  // namespace ftn
+#include "ftn_shade.cuh"
+namespace ftn {
+
+__global__ void __launch_bounds__(256)
+k_env_func(EnvLightData env, float* __restrict__ func) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < env.nu * env.nv) func[k] = env_func_value(env, k);
+}
+__global__ void __launch_bounds__(128)
+k_env_row_cdf(const float* __restrict__ func, int nu, int nv, float* __restrict__ cdf, float* __restrict__ integral) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < nv) dist_row_build(func + (size_t)v * nu, nu, cdf + (size_t)v * (nu + 1), integral + v);
+}
+
+SceneView make_view(const FtnScene& s) {
+    SceneView v;
+    v.bvh.nodes = s.d_nodes; v.bvh.tris = s.d_tris; v.bvh.n_nodes = s.n_nodes; v.bvh.n_tris = s.n_tris;
+    v.pos = s.d_pos; v.nrm = s.d_nrm; v.uv = s.d_uv; v.idx = s.d_idx;
+    v.meshes = s.d_meshes; v.materials = s.d_materials;
+    v.spheres = s.d_spheres; v.n_spheres = s.n_spheres;
+    v.lights = s.d_lights; v.n_lights = (uint32_t)s.h_lights.size();
+    v.n_tris = s.n_tris;
+    return v;
+}
+
+template <class T> static int upload(T** dst, const T* src, size_t count) {
+    *dst = nullptr;
+    if (count == 0) return FTN_OK;
+    FTN_CUDA(cudaMalloc((void**)dst, count * sizeof(T)));
+    FTN_CUDA(cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice));
+    return FTN_OK;
+}
+
+static M4 to_m4(const float* f) { M4 m; std::memcpy(m.m, f, 64); return m; }
+
+// microfacet.rs:40-45 (host, once per material: the table is scene data, not per-hit work)
+static float roughness_to_alpha_host(float roughness) {
+    float rough = std::fmax(roughness, 1.0e-3f);
+    float x = std::log(rough);
+    return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
+}
+
+static int build_env_light(FtnScene* s, const FtnLight& fl, LightData* out) {
+    EnvLightData& e = out->env;
+    e.w = fl.width; e.h = fl.height;
+    e.nu = fl.height; e.nv = fl.width;   // infinite.rs:64: `let (height, width) = mipmap.resolution()`
+    int mx = fl.width > fl.height ? fl.width : fl.height;
+    int lv = 0; while ((1 << (lv + 1)) <= mx) ++lv;
+    e.levels = 1 + lv;
+    e.l2w = to_m4(fl.light_to_world); e.w2l = to_m4(fl.world_to_light);
+    e.world_radius = 0.0f; e.world_center[0] = e.world_center[1] = e.world_center[2] = 0.0f;
+    const size_t n = (size_t)fl.width * fl.height;
+    std::vector<F4> tex(n);
+    for (size_t i = 0; i < n; ++i) { tex[i].x = fl.texels[3 * i]; tex[i].y = fl.texels[3 * i + 1]; tex[i].z = fl.texels[3 * i + 2]; tex[i].w = 0.0f; }
+    F4* d_tex; float *d_func, *d_cdf, *d_int, *d_mcdf;
+    FTN_TRY(upload(&d_tex, tex.data(), n));
+    s->owned.push_back(d_tex);
+    e.texels = d_tex;
+    FTN_CUDA(cudaMalloc(&d_func, n * sizeof(float))); s->owned.push_back(d_func);
+    FTN_CUDA(cudaMalloc(&d_cdf, (size_t)e.nv * (e.nu + 1) * sizeof(float))); s->owned.push_back(d_cdf);
+    FTN_CUDA(cudaMalloc(&d_int, (size_t)e.nv * sizeof(float))); s->owned.push_back(d_int);
+    FTN_CUDA(cudaMalloc(&d_mcdf, (size_t)(e.nv + 1) * sizeof(float))); s->owned.push_back(d_mcdf);
+    e.cond_func = d_func; e.cond_cdf = d_cdf; e.cond_integral = d_int; e.marg_cdf = d_mcdf;
+    k_env_func<<<(unsigned)((n + 255) / 256), 256>>>(e, d_func);
+    FTN_LAUNCHED();
+    k_env_row_cdf<<<(e.nv + 127) / 128, 128>>>(d_func, e.nu, e.nv, d_cdf, d_int);
+    FTN_LAUNCHED();
+    // marginal = Distribution1D::new(row integrals): one more "row" of length nv
+    float* d_mint;
+    FTN_CUDA(cudaMalloc(&d_mint, sizeof(float))); s->owned.push_back(d_mint);
+    k_env_row_cdf<<<1, 128>>>(d_int, e.nv, 1, d_mcdf, d_mint);
+    FTN_LAUNCHED();
+    FTN_CUDA(cudaMemcpy(&e.marg_integral, d_mint, sizeof(float), cudaMemcpyDeviceToHost));
+    return FTN_OK;
+}
+
+int scene_create(const FtnSceneDesc* d, FtnScene** out) {
+    if (!d || !out) return set_error(FTN_ERR_INVALID_ARGUMENT, "null argument");
+    if (d->abi_version != FTN_ABI_VERSION) return set_error(FTN_ERR_INVALID_ARGUMENT, "abi version mismatch");
+    if (d->n_triangles && (!d->positions || !d->indices || !d->meshes)) return set_error(FTN_ERR_INVALID_ARGUMENT, "triangles without positions/indices/meshes");
+    if (d->n_triangles >= (1u << 30)) return set_error(FTN_ERR_INVALID_ARGUMENT, "too many triangles (leaf refs hold 30 bits)");
+    uint32_t covered = 0;
+    for (uint32_t m = 0; m < d->n_meshes; ++m) {
+        if (d->meshes[m].first_tri != covered) return set_error(FTN_ERR_INVALID_ARGUMENT, "meshes must tile the index buffer in order");
+        if (d->meshes[m].material_id >= (int32_t)d->n_materials) return set_error(FTN_ERR_INVALID_ARGUMENT, "material id out of range");
+        covered += d->meshes[m].n_tris;
+        if (covered > d->n_triangles) return set_error(FTN_ERR_INVALID_ARGUMENT, "mesh range exceeds the index buffer");
+    }
+    if (covered != d->n_triangles) return set_error(FTN_ERR_INVALID_ARGUMENT, "meshes do not cover all triangles");
+    for (size_t k = 0; k < 3 * (size_t)d->n_triangles; ++k)
+        if (d->indices[k] >= d->n_vertices) return set_error(FTN_ERR_INVALID_ARGUMENT, "vertex index out of range");
+    int dev = 0;
+    FTN_CUDA(cudaGetDevice(&dev));
+    FtnScene* s = new FtnScene();
+    s->device = dev;
+    s->n_verts = d->n_vertices; s->n_tris = d->n_triangles; s->n_meshes = d->n_meshes;
+    s->n_spheres = d->n_spheres; s->n_materials = d->n_materials; s->n_lights = d->n_lights;
+    int rc = FTN_OK;
+    auto bail = [&](int code) { scene_destroy(s); return code; };
+    if ((rc = upload(&s->d_pos, d->positions, 3 * (size_t)d->n_vertices)) != FTN_OK) return bail(rc);
+    if (d->normals && (rc = upload(&s->d_nrm, d->normals, 3 * (size_t)d->n_vertices)) != FTN_OK) return bail(rc);
+    if (d->uvs && (rc = upload(&s->d_uv, d->uvs, 2 * (size_t)d->n_vertices)) != FTN_OK) return bail(rc);
+    if ((rc = upload(&s->d_idx, d->indices, 3 * (size_t)d->n_triangles)) != FTN_OK) return bail(rc);
+    std::vector<MeshData> meshes(d->n_meshes);
+    for (uint32_t m = 0; m < d->n_meshes; ++m) {
+        meshes[m].first_tri = d->meshes[m].first_tri; meshes[m].n_tris = d->meshes[m].n_tris;
+        meshes[m].material = d->meshes[m].material_id; meshes[m].flags = d->meshes[m].flags;
+    }
+    if ((rc = upload(&s->d_meshes, meshes.data(), meshes.size())) != FTN_OK) return bail(rc);
+    std::vector<MaterialData> mats(d->n_materials);
+    for (uint32_t m = 0; m < d->n_materials; ++m) {
+        const FtnMaterial& fm = d->materials[m];
+        MaterialData& md = mats[m];
+        md.type = fm.type;
+        if (fm.type < FTN_MATERIAL_MATTE || fm.type > FTN_MATERIAL_PLASTIC) return bail(set_error(FTN_ERR_INVALID_ARGUMENT, "unknown material type"));
+        for (int c = 0; c < 3; ++c) { md.kd[c] = fm.kd[c]; md.ks[c] = fm.ks[c]; md.eta[c] = fm.eta[c]; md.k[c] = fm.k[c]; }
+        float ur = fm.u_roughness, vr = fm.v_roughness;
+        if (fm.type == FTN_MATERIAL_PLASTIC) vr = ur;
+        if (fm.remap_roughness) { ur = roughness_to_alpha_host(ur); vr = roughness_to_alpha_host(vr); }
+        md.alpha_x = ur; md.alpha_y = vr;
+    }
+    if ((rc = upload(&s->d_materials, mats.data(), mats.size())) != FTN_OK) return bail(rc);
+    // explicit lights first, then area lights of emissive spheres in primitive order (scene/mod.rs:32-49)
+    for (uint32_t l = 0; l < d->n_lights; ++l) {
+        const FtnLight& fl = d->lights[l];
+        if (fl.type != FTN_LIGHT_INFINITE || fl.width < 1 || fl.height < 1 || !fl.texels) return bail(set_error(FTN_ERR_INVALID_ARGUMENT, "bad light"));
+        LightData ld; std::memset(&ld, 0, sizeof(ld));
+        ld.type = 0; ld.sphere = -1;
+        if ((rc = build_env_light(s, fl, &ld)) != FTN_OK) return bail(rc);
+        s->h_lights.push_back(ld);
+    }
+    s->h_spheres.resize(d->n_spheres);
+    for (uint32_t i = 0; i < d->n_spheres; ++i) {
+        const FtnSphere& fs = d->spheres[i];
+        SphereData& sd = s->h_spheres[i];
+        if (fs.material_id >= (int32_t)d->n_materials) return bail(set_error(FTN_ERR_INVALID_ARGUMENT, "material id out of range"));
+        sd.o2w = to_m4(fs.object_to_world); sd.w2o = to_m4(fs.world_to_object);
+        // Sphere::new, sphere.rs:30-49
+        const float r = fs.radius;
+        sd.radius = r;
+        sd.z_min = std::fmin(std::fmax(std::fmin(fs.z_min, fs.z_max), -r), r);
+        sd.z_max = std::fmin(std::fmax(std::fmax(fs.z_min, fs.z_max), -r), r);
+        sd.theta_min = std::acos(std::fmin(std::fmax(fs.z_min / r, -1.0f), 1.0f));
+        sd.theta_max = std::acos(std::fmin(std::fmax(fs.z_max / r, -1.0f), 1.0f));
+        sd.phi_max = std::fmin(std::fmax(fs.phi_max_deg, 0.0f), 360.0f) * (3.14159265358979323846f / 180.0f);
+        sd.reverse_orientation = fs.reverse_orientation;
+        sd.material = fs.material_id;
+        sd.light = -1;
+        sd.emit[0] = fs.emit[0]; sd.emit[1] = fs.emit[1]; sd.emit[2] = fs.emit[2];
+        sd.area = sd.phi_max * sd.radius * (sd.z_max - sd.z_min);   // sphere.rs:77-79
+        if (fs.emissive) {
+            LightData ld; std::memset(&ld, 0, sizeof(ld));
+            ld.type = 1; ld.sphere = (int32_t)i;
+            ld.emit[0] = fs.emit[0]; ld.emit[1] = fs.emit[1]; ld.emit[2] = fs.emit[2];
+            sd.light = (int)s->h_lights.size();
+            s->h_lights.push_back(ld);
+        }
+    }
+    if ((rc = upload(&s->d_spheres, s->h_spheres.data(), s->h_spheres.size())) != FTN_OK) return bail(rc);
+    if ((rc = upload(&s->d_lights, s->h_lights.data(), s->h_lights.size())) != FTN_OK) return bail(rc);
+    cudaError_t e = cudaMalloc(&s->d_work, sizeof(unsigned long long));
+    if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc work counter", __FILE__, __LINE__));
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return bail(cuda_fail(e, "scene_create sync", __FILE__, __LINE__));
+    *out = s;
+    return FTN_OK;
+}
+
+int scene_destroy(FtnScene* s) {
+    if (!s) return FTN_OK;
+    cudaFree(s->d_pos); cudaFree(s->d_nrm); cudaFree(s->d_uv); cudaFree(s->d_idx);
+    cudaFree(s->d_meshes); cudaFree(s->d_materials); cudaFree(s->d_spheres); cudaFree(s->d_lights);
+    cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_codes); cudaFree(s->d_order); cudaFree(s->d_work);
+    for (void* p : s->owned) cudaFree(p);
+    delete s;
+    return FTN_OK;
+}
+
+// Bounds3::join of the sphere bounds on the host: Shape::world_bound = o2w(object_bound),
+// shapes/mod.rs:17-19, transform.rs:276-283, corner order bounds.rs:184-196 (8 points, min/max only).
+static void sphere_world_bound(const SphereData& sd, float lo[3], float hi[3]) {
+    const float omin[3] = {-sd.radius, -sd.radius, sd.z_min}, omax[3] = {sd.radius, sd.radius, sd.z_max};
+    for (int a = 0; a < 3; ++a) { lo[a] = FLT_MAX; hi[a] = -FLT_MAX; }
+    for (int c = 0; c < 8; ++c) {
+        const float p[3] = {(c & 4) ? omax[0] : omin[0], (c & 2) ? omax[1] : omin[1], (c & 1) ? omax[2] : omin[2]};
+        const float* m = sd.o2w.m;
+        float q[4];
+        for (int r = 0; r < 4; ++r) q[r] = ((m[r] * p[0] + m[4 + r] * p[1]) + m[8 + r] * p[2]) + m[12 + r] * 1.0f;
+        const float iw = 1.0f / q[3];
+        for (int a = 0; a < 3; ++a) { const float v = q[a] * iw; lo[a] = std::fmin(lo[a], v); hi[a] = std::fmax(hi[a], v); }
+    }
+}
+
+int bvh_build(FtnScene* s) {
+    if (!s) return set_error(FTN_ERR_INVALID_ARGUMENT, "null scene");
+    if (s->built) return FTN_OK;
+    FTN_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = 0;
+    cudaEvent_t ev0, ev1;
+    FTN_CUDA(cudaEventCreate(&ev0)); FTN_CUDA(cudaEventCreate(&ev1));
+    FTN_CUDA(cudaEventRecord(ev0, st));
+    const uint32_t n = s->n_tris;
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    int rc = FTN_OK;
+    if (n > 0) {
+        BuildBounds* d_gb = nullptr;
+        F4 *tri_lo = nullptr, *tri_hi = nullptr, *leaf_lo = nullptr, *leaf_hi = nullptr;
+        uint32_t *keys = nullptr, *survive = nullptr;
+        LbvhArrays a; std::memset(&a, 0, sizeof(a));
+        std::vector<void*> tmp;
+        auto dalloc = [&](void** p, size_t bytes) -> int {
+            cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc (bvh build)", __FILE__, __LINE__);
+            tmp.push_back(*p);
+            return FTN_OK;
+        };
+        auto cleanup = [&]() { for (void* p : tmp) cudaFree(p); };
+        const unsigned gb256 = (n + 255) / 256;
+        do {
+            if ((rc = dalloc((void**)&d_gb, sizeof(BuildBounds))) != FTN_OK) break;
+            if ((rc = dalloc((void**)&tri_lo, (size_t)n * sizeof(F4))) != FTN_OK) break;
+            if ((rc = dalloc((void**)&tri_hi, (size_t)n * sizeof(F4))) != FTN_OK) break;
+            if ((rc = dalloc((void**)&keys, (size_t)n * 4)) != FTN_OK) break;
+            cudaError_t e;
+            if (!s->d_codes && (e = cudaMalloc(&s->d_codes, (size_t)n * 4)) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc codes", __FILE__, __LINE__); break; }
+            if (!s->d_order && (e = cudaMalloc(&s->d_order, (size_t)n * 4)) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc order", __FILE__, __LINE__); break; }
+            k_init_bounds<<<1, 32, 0, st>>>(d_gb); count_launch();
+            k_tri_bounds<<<gb256, 256, 0, st>>>(s->d_pos, s->d_idx, n, tri_lo, tri_hi, d_gb); count_launch();
+            k_morton<<<gb256, 256, 0, st>>>(tri_lo, tri_hi, n, d_gb, s->d_codes, keys, s->d_order); count_launch();
+            if ((e = cudaGetLastError()) != cudaSuccess) { rc = cuda_fail(e, "bounds/morton kernels", __FILE__, __LINE__); break; }
+            if ((rc = radix_sort_pairs(keys, s->d_order, n, 30, st)) != FTN_OK) break;
+            if ((rc = dalloc((void**)&leaf_lo, (size_t)n * sizeof(F4))) != FTN_OK) break;
+            if ((rc = dalloc((void**)&leaf_hi, (size_t)n * sizeof(F4))) != FTN_OK) break;
+            k_gather_leaf_boxes<<<gb256, 256, 0, st>>>(tri_lo, tri_hi, s->d_order, n, leaf_lo, leaf_hi); count_launch();
+            if (!s->d_tris && (e = cudaMalloc(&s->d_tris, (size_t)n * 3 * sizeof(F4))) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc tris", __FILE__, __LINE__); break; }
+            k_gather_tris<<<gb256, 256, 0, st>>>(s->d_pos, s->d_idx, s->d_order, n, s->d_meshes, s->n_meshes, s->d_tris); count_launch();
+            if ((e = cudaGetLastError()) != cudaSuccess) { rc = cuda_fail(e, "gather kernels", __FILE__, __LINE__); break; }
+            if (n <= (uint32_t)FTN_LEAF_MAX) {
+                if (!s->d_nodes && (e = cudaMalloc(&s->d_nodes, 4 * sizeof(F4))) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc nodes", __FILE__, __LINE__); break; }
+                k_lbvh_emit_single<<<1, 32, 0, st>>>(n, d_gb, s->d_nodes); count_launch();
+                s->n_nodes = 1;
+            } else {
+                const size_t ni = n - 1;
+                if ((rc = dalloc((void**)&a.left, ni * 4)) != FTN_OK) break;
+                if ((rc = dalloc((void**)&a.right, ni * 4)) != FTN_OK) break;
+                if ((rc = dalloc((void**)&a.first, ni * 4)) != FTN_OK) break;
+                if ((rc = dalloc((void**)&a.last, ni * 4)) != FTN_OK) break;
+                if ((rc = dalloc((void**)&a.parent, (2 * (size_t)n - 1) * 4)) != FTN_OK) break;
+                if ((rc = dalloc((void**)&a.arrive, ni * 4)) != FTN_OK) break;
+                if ((rc = dalloc((void**)&a.node_lo, ni * sizeof(F4))) != FTN_OK) break;
+                if ((rc = dalloc((void**)&a.node_hi, ni * sizeof(F4))) != FTN_OK) break;
+                if ((rc = dalloc((void**)&survive, ni * 4)) != FTN_OK) break;
+                if ((e = cudaMemsetAsync(a.arrive, 0, ni * 4, st)) != cudaSuccess) { rc = cuda_fail(e, "memset arrive", __FILE__, __LINE__); break; }
+                const unsigned gi = (unsigned)((ni + 255) / 256);
+                k_lbvh_topology<<<gi, 256, 0, st>>>(keys, (int)n, a); count_launch();
+                k_lbvh_refit<<<gb256, 256, 0, st>>>((int)n, a, leaf_lo, leaf_hi); count_launch();
+                k_lbvh_survive<<<gi, 256, 0, st>>>((int)n, a, survive); count_launch();
+                if ((e = cudaGetLastError()) != cudaSuccess) { rc = cuda_fail(e, "lbvh kernels", __FILE__, __LINE__); break; }
+                uint32_t last_flag = 0, last_idx = 0;
+                if ((e = cudaMemcpyAsync(&last_flag, survive + ni - 1, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { rc = cuda_fail(e, "read survive", __FILE__, __LINE__); break; }
+                uint32_t* new_index = a.arrive;   // reuse: arrival counters are dead after the refit
+                if ((rc = exclusive_scan_u32(survive, new_index, ni, st)) != FTN_OK) break;
+                if ((e = cudaMemcpyAsync(&last_idx, new_index + ni - 1, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { rc = cuda_fail(e, "read scan", __FILE__, __LINE__); break; }
+                if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { rc = cuda_fail(e, "lbvh sync", __FILE__, __LINE__); break; }
+                s->n_nodes = last_idx + last_flag;
+                if (s->d_nodes) { cudaFree(s->d_nodes); s->d_nodes = nullptr; }
+                if ((e = cudaMalloc(&s->d_nodes, (size_t)s->n_nodes * 4 * sizeof(F4))) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc nodes", __FILE__, __LINE__); break; }
+                k_lbvh_emit<<<gi, 256, 0, st>>>((int)n, a, leaf_lo, leaf_hi, survive, new_index, s->d_nodes); count_launch();
+            }
+            if ((e = cudaGetLastError()) != cudaSuccess) { rc = cuda_fail(e, "emit kernels", __FILE__, __LINE__); break; }
+            BuildBounds hb;
+            if ((e = cudaMemcpyAsync(&hb, d_gb, sizeof(hb), cudaMemcpyDeviceToHost, st)) != cudaSuccess) { rc = cuda_fail(e, "read bounds", __FILE__, __LINE__); break; }
+            if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { rc = cuda_fail(e, "bvh build sync", __FILE__, __LINE__); break; }
+            for (int c = 0; c < 3; ++c) {
+                uint32_t ul = hb.scene_lo[c], uh = hb.scene_hi[c];
+                uint32_t bl = (ul & 0x80000000u) ? (ul & 0x7FFFFFFFu) : ~ul, bh = (uh & 0x80000000u) ? (uh & 0x7FFFFFFFu) : ~uh;
+                std::memcpy(&lo[c], &bl, 4); std::memcpy(&hi[c], &bh, 4);
+            }
+        } while (0);
+        cleanup();
+        if (rc != FTN_OK) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); return rc; }
+    }
+    for (const SphereData& sd : s->h_spheres) {
+        float slo[3], shi[3];
+        sphere_world_bound(sd, slo, shi);
+        for (int c = 0; c < 3; ++c) { lo[c] = std::fmin(lo[c], slo[c]); hi[c] = std::fmax(hi[c], shi[c]); }
+    }
+    for (int c = 0; c < 3; ++c) { s->bounds[c] = lo[c]; s->bounds[3 + c] = hi[c]; }
+    // Scene::new -> Light::preprocess (infinite.rs:93-97): bounding sphere of the world bound (bounds.rs:208-212)
+    bool lights_changed = false;
+    for (LightData& ld : s->h_lights) {
+        if (ld.type != 0) continue;
+        float c[3], r2 = 0.0f;
+        for (int a = 0; a < 3; ++a) c[a] = (lo[a] + hi[a]) / 2.0f;
+        const float dx = hi[0] - c[0], dy = hi[1] - c[1], dz = hi[2] - c[2];
+        r2 = (dx * dx + dy * dy) + dz * dz;
+        ld.env.world_radius = std::sqrt(r2);
+        ld.env.world_center[0] = c[0]; ld.env.world_center[1] = c[1]; ld.env.world_center[2] = c[2];
+        lights_changed = true;
+    }
+    if (lights_changed) FTN_CUDA(cudaMemcpy(s->d_lights, s->h_lights.data(), s->h_lights.size() * sizeof(LightData), cudaMemcpyHostToDevice));
+    FTN_CUDA(cudaEventRecord(ev1, st));
+    FTN_CUDA(cudaEventSynchronize(ev1));
+    float ms = 0.0f;
+    FTN_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    s->build_seconds = ms * 1e-3;
+    s->built = true;
+    return FTN_OK;
+}
+
+}  // namespace ftn
+
+ftn::SceneView FtnScene::view() const { return ftn::make_view(*this); }

@@ -1,0 +1,367 @@
+// TEST HARNESS ONLY -- not part of the product.
+//
+// Compiles the FTN_HD device functions of fountain_b200/csrc/*.cuh with g++ and drives them
+// sequentially on the CPU behind the same C ABI (prefix `sim_`), so that the CPU-only test tier
+// (`pytest -m "not gpu"`, no GPU in the build container) can check the kernels' per-thread logic
+// -- LBVH topology + BVH2x64 emission + traversal, watertight triangle, EFloat sphere, BSDFs,
+// env-map tables / sampling, path logic, film gather -- against the oracle before any GPU
+// minute is spent.  What it cannot cover (radix sort, scans, atomics, queue compaction, launch
+// glue) is covered by the `-m gpu` tests.  libfountain_gpu.so never links this file and has no
+// CPU execution path.
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+#include "../../fountain_b200/csrc/ftn_path.cuh"
+#include "../../fountain_b200/csrc/ftn_lbvh.cuh"
+
+using namespace ftn;
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const char* m) { g_err = m; return code; }
+
+struct SimScene {
+    std::vector<float> pos, nrm, uv; std::vector<uint32_t> idx;
+    std::vector<MeshData> meshes; std::vector<MaterialData> mats;
+    std::vector<SphereData> spheres; std::vector<LightData> lights;
+    std::vector<std::vector<F4>> env_tex; std::vector<std::vector<float>> env_f;   // storage behind EnvLightData pointers
+    std::vector<F4> nodes, tris; uint32_t n_nodes = 0;
+    std::vector<uint32_t> codes, order;
+    float bounds[6]; bool built = false; uint32_t n_tris = 0;
+    SceneView view() const {
+        SceneView v;
+        v.bvh.nodes = nodes.data(); v.bvh.tris = tris.data(); v.bvh.n_nodes = n_nodes; v.bvh.n_tris = n_tris;
+        v.pos = pos.data(); v.nrm = nrm.empty() ? nullptr : nrm.data(); v.uv = uv.empty() ? nullptr : uv.data(); v.idx = idx.data();
+        v.meshes = meshes.data(); v.materials = mats.data(); v.spheres = spheres.data(); v.n_spheres = (uint32_t)spheres.size();
+        v.lights = lights.data(); v.n_lights = (uint32_t)lights.size(); v.n_tris = n_tris;
+        return v;
+    }
+};
+M4 to_m4(const float* f) { M4 m; std::memcpy(m.m, f, 64); return m; }
+float roughness_to_alpha_host(float roughness) {   // same as scene.cu
+    float rough = std::fmax(roughness, 1.0e-3f);
+    float x = std::log(rough);
+    return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
+}
+}  // namespace
+
+#define SIM_API extern "C" __attribute__((visibility("default")))
+
+SIM_API uint32_t sim_abi_version(void) { return FTN_ABI_VERSION; }
+SIM_API const char* sim_last_error(void) { return g_err.c_str(); }
+
+SIM_API int sim_scene_create(const FtnSceneDesc* d, SimScene** out) {
+    SimScene* s = new SimScene();
+    s->n_tris = d->n_triangles;
+    s->pos.assign(d->positions, d->positions + 3 * (size_t)d->n_vertices);
+    if (d->normals) s->nrm.assign(d->normals, d->normals + 3 * (size_t)d->n_vertices);
+    if (d->uvs) s->uv.assign(d->uvs, d->uvs + 2 * (size_t)d->n_vertices);
+    s->idx.assign(d->indices, d->indices + 3 * (size_t)d->n_triangles);
+    for (uint32_t m = 0; m < d->n_meshes; ++m) { MeshData md; md.first_tri = d->meshes[m].first_tri; md.n_tris = d->meshes[m].n_tris; md.material = d->meshes[m].material_id; md.flags = d->meshes[m].flags; s->meshes.push_back(md); }
+    for (uint32_t m = 0; m < d->n_materials; ++m) {
+        const FtnMaterial& fm = d->materials[m]; MaterialData md; md.type = fm.type;
+        for (int c = 0; c < 3; ++c) { md.kd[c] = fm.kd[c]; md.ks[c] = fm.ks[c]; md.eta[c] = fm.eta[c]; md.k[c] = fm.k[c]; }
+        float ur = fm.u_roughness, vr = fm.v_roughness;
+        if (fm.type == FTN_MATERIAL_PLASTIC) vr = ur;
+        if (fm.remap_roughness) { ur = roughness_to_alpha_host(ur); vr = roughness_to_alpha_host(vr); }
+        md.alpha_x = ur; md.alpha_y = vr; s->mats.push_back(md);
+    }
+    s->env_tex.reserve(d->n_lights); s->env_f.reserve(5 * d->n_lights);
+    for (uint32_t l = 0; l < d->n_lights; ++l) {
+        const FtnLight& fl = d->lights[l];
+        LightData ld; std::memset(&ld, 0, sizeof(ld)); ld.type = 0; ld.sphere = -1;
+        EnvLightData& e = ld.env;
+        e.w = fl.width; e.h = fl.height; e.nu = fl.height; e.nv = fl.width;
+        int mx = std::max(fl.width, fl.height), lv = 0; while ((1 << (lv + 1)) <= mx) ++lv;
+        e.levels = 1 + lv; e.l2w = to_m4(fl.light_to_world); e.w2l = to_m4(fl.world_to_light);
+        const size_t n = (size_t)fl.width * fl.height;
+        s->env_tex.emplace_back(n);
+        for (size_t i = 0; i < n; ++i) { F4 t; t.x = fl.texels[3 * i]; t.y = fl.texels[3 * i + 1]; t.z = fl.texels[3 * i + 2]; t.w = 0; s->env_tex.back()[i] = t; }
+        e.texels = s->env_tex.back().data();
+        s->env_f.emplace_back(n); std::vector<float>& func = s->env_f.back();
+        for (size_t k = 0; k < n; ++k) func[k] = env_func_value(e, (int)k);                       // k_env_func
+        s->env_f.emplace_back((size_t)e.nv * (e.nu + 1)); std::vector<float>& cdf = s->env_f.back();
+        s->env_f.emplace_back(e.nv); std::vector<float>& integ = s->env_f.back();
+        for (int v = 0; v < e.nv; ++v) dist_row_build(&func[(size_t)v * e.nu], e.nu, &cdf[(size_t)v * (e.nu + 1)], &integ[v]);   // k_env_row_cdf
+        s->env_f.emplace_back(e.nv + 1); std::vector<float>& mcdf = s->env_f.back();
+        dist_row_build(integ.data(), e.nv, mcdf.data(), &e.marg_integral);
+        e.cond_func = func.data(); e.cond_cdf = cdf.data(); e.cond_integral = integ.data(); e.marg_cdf = mcdf.data();
+        s->lights.push_back(ld);
+    }
+    for (uint32_t i = 0; i < d->n_spheres; ++i) {
+        const FtnSphere& fs = d->spheres[i]; SphereData sd;
+        sd.o2w = to_m4(fs.object_to_world); sd.w2o = to_m4(fs.world_to_object);
+        const float r = fs.radius; sd.radius = r;
+        sd.z_min = std::fmin(std::fmax(std::fmin(fs.z_min, fs.z_max), -r), r);
+        sd.z_max = std::fmin(std::fmax(std::fmax(fs.z_min, fs.z_max), -r), r);
+        sd.theta_min = std::acos(std::fmin(std::fmax(fs.z_min / r, -1.0f), 1.0f));
+        sd.theta_max = std::acos(std::fmin(std::fmax(fs.z_max / r, -1.0f), 1.0f));
+        sd.phi_max = std::fmin(std::fmax(fs.phi_max_deg, 0.0f), 360.0f) * (3.14159265358979323846f / 180.0f);
+        sd.reverse_orientation = fs.reverse_orientation; sd.material = fs.material_id; sd.light = -1;
+        sd.emit[0] = fs.emit[0]; sd.emit[1] = fs.emit[1]; sd.emit[2] = fs.emit[2];
+        sd.area = sd.phi_max * sd.radius * (sd.z_max - sd.z_min);
+        if (fs.emissive) {
+            LightData ld; std::memset(&ld, 0, sizeof(ld)); ld.type = 1; ld.sphere = (int)i;
+            ld.emit[0] = fs.emit[0]; ld.emit[1] = fs.emit[1]; ld.emit[2] = fs.emit[2];
+            sd.light = (int)s->lights.size(); s->lights.push_back(ld);
+        }
+        s->spheres.push_back(sd);
+    }
+    *out = s;
+    return FTN_OK;
+}
+SIM_API int sim_scene_destroy(SimScene* s) { delete s; return FTN_OK; }
+
+// the device build pipeline of scene.cu as sequential loops over the same per-element bodies
+SIM_API int sim_bvh_build(SimScene* s) {
+    if (s->built) return FTN_OK;
+    const uint32_t n = s->n_tris;
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    if (n > 0) {
+        std::vector<F4> tri_lo(n), tri_hi(n);
+        float cmin[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, cmax[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        for (uint32_t i = 0; i < n; ++i) {   // k_tri_bounds
+            float c[3]; tri_bounds_centroid(s->pos.data(), s->idx.data(), i, &tri_lo[i], &tri_hi[i], c);
+            const float l[3] = {tri_lo[i].x, tri_lo[i].y, tri_lo[i].z}, h[3] = {tri_hi[i].x, tri_hi[i].y, tri_hi[i].z};
+            for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], l[a]); hi[a] = fmaxf(hi[a], h[a]); cmin[a] = fminf(cmin[a], c[a]); cmax[a] = fmaxf(cmax[a], c[a]); }
+        }
+        s->codes.resize(n); s->order.resize(n);
+        for (uint32_t i = 0; i < n; ++i) s->codes[i] = tri_morton(tri_lo[i], tri_hi[i], cmin, cmax);   // k_morton
+        std::iota(s->order.begin(), s->order.end(), 0u);
+        std::stable_sort(s->order.begin(), s->order.end(), [&](uint32_t a, uint32_t b) { return s->codes[a] < s->codes[b]; });   // radix_sort_pairs
+        std::vector<uint32_t> keys(n);
+        for (uint32_t i = 0; i < n; ++i) keys[i] = s->codes[s->order[i]];
+        std::vector<F4> leaf_lo(n), leaf_hi(n);
+        for (uint32_t i = 0; i < n; ++i) { leaf_lo[i] = tri_lo[s->order[i]]; leaf_hi[i] = tri_hi[s->order[i]]; }
+        s->tris.resize(3 * (size_t)n);
+        for (uint32_t i = 0; i < n; ++i) lbvh_gather_tri(s->pos.data(), s->idx.data(), s->order.data(), i, s->meshes.data(), (uint32_t)s->meshes.size(), s->tris.data());
+        if (n <= (uint32_t)FTN_LEAF_MAX) {
+            s->nodes.resize(4); lbvh_emit_single(n, lo, hi, s->nodes.data()); s->n_nodes = 1;
+        } else {
+            const size_t ni = n - 1;
+            std::vector<uint32_t> left(ni), right(ni), first(ni), last(ni), parent(2 * (size_t)n - 1), arrive(ni, 0), survive(ni), new_index(ni);
+            std::vector<F4> node_lo(ni), node_hi(ni);
+            LbvhArrays a; a.left = left.data(); a.right = right.data(); a.first = first.data(); a.last = last.data();
+            a.parent = parent.data(); a.arrive = arrive.data(); a.node_lo = node_lo.data(); a.node_hi = node_hi.data();
+            for (size_t i = 0; i < ni; ++i) lbvh_topology_node(keys.data(), (int)n, (int)i, a);   // k_lbvh_topology
+            for (uint32_t leaf = 0; leaf < n; ++leaf) {   // k_lbvh_refit: second arrival joins
+                uint32_t node = parent[n - 1 + leaf];
+                while (node != 0xFFFFFFFFu) {
+                    if (arrive[node]++ == 0u) break;
+                    lbvh_join_children(a, leaf_lo.data(), leaf_hi.data(), node);
+                    node = parent[node];
+                }
+            }
+            for (size_t i = 0; i < ni; ++i) { if (arrive[i] != 2u) return fail(FTN_ERR_CUDA, "refit did not reach every node twice"); }
+            uint32_t run = 0;
+            for (size_t i = 0; i < ni; ++i) { survive[i] = lbvh_survives(a, (int)i); new_index[i] = run; run += survive[i]; }   // survive + scan
+            s->n_nodes = run; s->nodes.resize(4 * (size_t)run);
+            for (size_t i = 0; i < ni; ++i) if (survive[i]) lbvh_emit_node(a, leaf_lo.data(), leaf_hi.data(), survive.data(), new_index.data(), (int)i, s->nodes.data());
+        }
+    }
+    // sphere bounds + light preprocessing exactly as bvh_build() in scene.cu
+    for (const SphereData& sd : s->spheres) {
+        const float omin[3] = {-sd.radius, -sd.radius, sd.z_min}, omax[3] = {sd.radius, sd.radius, sd.z_max};
+        for (int c = 0; c < 8; ++c) {
+            const float p[3] = {(c & 4) ? omax[0] : omin[0], (c & 2) ? omax[1] : omin[1], (c & 1) ? omax[2] : omin[2]};
+            const float* m = sd.o2w.m; float q[4];
+            for (int r = 0; r < 4; ++r) q[r] = ((m[r] * p[0] + m[4 + r] * p[1]) + m[8 + r] * p[2]) + m[12 + r] * 1.0f;
+            const float iw = 1.0f / q[3];
+            for (int a = 0; a < 3; ++a) { const float v = q[a] * iw; lo[a] = std::fmin(lo[a], v); hi[a] = std::fmax(hi[a], v); }
+        }
+    }
+    for (int c = 0; c < 3; ++c) { s->bounds[c] = lo[c]; s->bounds[3 + c] = hi[c]; }
+    for (LightData& ld : s->lights) {
+        if (ld.type != 0) continue;
+        float c[3]; for (int a = 0; a < 3; ++a) c[a] = (lo[a] + hi[a]) / 2.0f;
+        const float dx = hi[0] - c[0], dy = hi[1] - c[1], dz = hi[2] - c[2];
+        ld.env.world_radius = std::sqrt((dx * dx + dy * dy) + dz * dz);
+        ld.env.world_center[0] = c[0]; ld.env.world_center[1] = c[1]; ld.env.world_center[2] = c[2];
+    }
+    s->built = true;
+    return FTN_OK;
+}
+
+SIM_API int sim_bvh_debug_morton(const SimScene* s, uint32_t* codes, uint32_t* order) {
+    if (codes) std::copy(s->codes.begin(), s->codes.end(), codes);
+    if (order) std::copy(s->order.begin(), s->order.end(), order);
+    return FTN_OK;
+}
+SIM_API int sim_scene_world_bound(const SimScene* s, float out[6]) { std::memcpy(out, s->bounds, 24); return FTN_OK; }
+SIM_API int sim_scene_stats(const SimScene* s, FtnStats* st) {
+    std::memset(st, 0, sizeof(*st)); st->bvh_nodes = s->n_nodes; st->bvh_node_bytes = 64; st->bvh_tri_bytes = 48; return FTN_OK;
+}
+
+static RayF to_rayf(const FtnRay& r) { RayF q; q.o = V3(r.o[0], r.o[1], r.o[2]); q.d = V3(r.d[0], r.d[1], r.d[2]); q.t_max = r.t_max; q.time = r.time; return q; }
+
+// k_intersect_batch, one "thread" at a time
+SIM_API int sim_intersect(const SimScene* s, size_t n, const FtnRay* rays, FtnHit* hits) {
+    const SceneView sc = s->view();
+    for (size_t i = 0; i < n; ++i) {
+        const RayF ray = to_rayf(rays[i]);
+        SceneHit h; TraceCounters tc; tc.nodes = tc.tris = 0;
+        scene_intersect<false, false>(sc, ray, &h, &tc);
+        FtnHit out;
+        if (h.slot == FTN_NO_HIT_SLOT) { out.prim = FTN_NO_HIT; out.t = ray.t_max; out.b1 = 0; out.b2 = 0; }
+        else if (h.slot & FTN_SPHERE_SLOT_FLAG) { out.prim = sc.n_tris + (h.slot & ~FTN_SPHERE_SLOT_FLAG); out.t = h.t; out.b1 = 0; out.b2 = 0; }
+        else { out.prim = f2u(sc.bvh.tris[3 * (size_t)h.slot].w); out.t = h.t; out.b1 = h.tri.b1; out.b2 = h.tri.b2; }
+        hits[i] = out;
+    }
+    return FTN_OK;
+}
+SIM_API int sim_intersect_test(const SimScene* s, size_t n, const FtnRay* rays, uint8_t* out) {
+    const SceneView sc = s->view();
+    for (size_t i = 0; i < n; ++i) {
+        SceneHit h; TraceCounters tc; tc.nodes = tc.tris = 0;
+        scene_intersect<true, false>(sc, to_rayf(rays[i]), &h, &tc);
+        out[i] = h.slot != FTN_NO_HIT_SLOT;
+    }
+    return FTN_OK;
+}
+SIM_API int sim_intersect_count(const SimScene* s, size_t n, const FtnRay* rays, FtnHit* hits, uint64_t* counters) {
+    const SceneView sc = s->view();
+    for (size_t i = 0; i < n; ++i) {
+        SceneHit h; TraceCounters tc; tc.nodes = tc.tris = 0;
+        scene_intersect<false, true>(sc, to_rayf(rays[i]), &h, &tc);
+        counters[0] += tc.nodes; counters[1] += tc.tris;
+        (void)hits;
+    }
+    return FTN_OK;
+}
+
+SIM_API int sim_film_pixel_count(const FtnFilm* f, int32_t* w, int32_t* h) {
+    FilmGeom g; if (film_geometry(f, &g) != FTN_OK) return fail(FTN_ERR_INVALID_ARGUMENT, "bad film");
+    if (w) *w = g.crop_max[0] - g.crop_min[0];
+    if (h) *h = g.crop_max[1] - g.crop_min[1];
+    return FTN_OK;
+}
+
+// render_device() of render.cu with every kernel replaced by a loop over its per-path body.
+SIM_API int sim_render(const SimScene* s, const FtnCamera* cam, const FtnFilm* film, const FtnSampler* smp,
+                       const FtnIntegrator* integ, FtnPixel* out_pixels, FtnStats* stats) {
+    if (smp->mode != FTN_SAMPLER_COUNTER) return fail(FTN_ERR_UNSUPPORTED, "counter sampler only");
+    FilmGeom fg; if (film_geometry(film, &fg) != FTN_OK) return fail(FTN_ERR_INVALID_ARGUMENT, "bad film");
+    const int fw = fg.crop_max[0] - fg.crop_min[0], fh = fg.crop_max[1] - fg.crop_min[1];
+    const int sbw = fg.sb_max[0] - fg.sb_min[0], sbh = fg.sb_max[1] - fg.sb_min[1];
+    const size_t n_spix = (size_t)sbw * sbh;
+    const int n_samples = (smp->sample_begin < smp->samples_per_pixel) ? (smp->samples_per_pixel - smp->sample_begin + smp->sample_stride - 1) / smp->sample_stride : 0;
+    int s_per_pass = (int)std::max<size_t>(1, ((size_t)1 << 16) / std::max<size_t>(1, n_spix));   // small passes: exercises multi-pass accumulation
+    s_per_pass = std::min(s_per_pass, std::max(1, n_samples));
+    const size_t P = n_spix * (size_t)s_per_pass;
+    std::vector<float4> L(P); std::vector<float2> pfilm(P);
+    std::vector<float4> accum((size_t)fw * fh, make_float4(0, 0, 0, 0));
+    const SceneView sc = s->view();
+    uint32_t err = 0;
+    uint64_t rays_closest = 0, rays_any = 0, camera_samples = 0;
+    bool has_area = false; for (const LightData& l : s->lights) if (l.type == 1) has_area = true;
+    PassParams pp; std::memset(&pp, 0, sizeof(pp));
+    pp.film = fg; pp.cam = *cam; pp.seed_key = sampler_seed_key(smp->seed);
+    pp.spp = smp->samples_per_pixel; pp.s_stride = smp->sample_stride;
+    pp.integrator = integ->type; pp.max_depth = integ->max_depth; pp.rr_threshold = integ->rr_threshold;
+    const int reach = (int)std::ceil(std::max(fg.radius[0], fg.radius[1]) + 0.5f);
+    for (int done = 0; done < n_samples; done += s_per_pass) {
+        const int sc_n = std::min(s_per_pass, n_samples - done);
+        pp.s_first = smp->sample_begin + done * smp->sample_stride; pp.s_count = sc_n; pp.n_paths = (uint32_t)(n_spix * (size_t)sc_n);
+        for (uint32_t path = 0; path < pp.n_paths; ++path) {
+            float fx, fy;
+            RayF ray = raygen_path(pp, path, &fx, &fy);   // k_raygen
+            pfilm[path] = make_float2(fx, fy);
+            V3 Lp = v3s(0.0f), beta = v3s(1.0f); uint32_t state = 0;
+            ++camera_samples;
+            for (int it = 0; it < integ->max_depth + 2 + 4096; ++it) {
+                SceneHit h; TraceCounters tc; tc.nodes = tc.tris = 0;
+                scene_intersect<false, false>(sc, ray, &h, &tc);   // k_extend
+                ++rays_closest;
+                if (h.slot == FTN_NO_HIT_SLOT) {   // k_shade_miss
+                    const bool add = (pp.integrator == FTN_INTEGRATOR_DIRECT_LIGHTING) || ((state & FTN_STATE_BOUNCES) == 0u) || (state & FTN_STATE_SPECULAR);
+                    if (add) Lp = Lp + beta * scene_env_radiance(sc, ray.d);
+                    break;
+                }
+                ShadeOut o;
+                shade_surface(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err);   // k_shade<...>
+                Lp = o.L;
+                if (o.direct.has_shadow) {   // k_shadow
+                    RayF sr; sr.o = o.direct.sh_o; sr.d = o.direct.sh_d; sr.t_max = rn_sub(1.0f, 0.0001f); sr.time = ray.time;
+                    SceneHit sh; scene_intersect<true, false>(sc, sr, &sh, &tc); ++rays_any;
+                    if (sh.slot == FTN_NO_HIT_SLOT) Lp = Lp + o.direct.sh_L;
+                }
+                if (o.direct.has_mis) {   // k_mis
+                    RayF mr; mr.o = o.direct.mis_o; mr.d = o.direct.mis_d; mr.t_max = FTN_INF; mr.time = ray.time;
+                    SceneHit mh;
+                    if (has_area) scene_intersect<false, false>(sc, mr, &mh, &tc); else scene_intersect<true, false>(sc, mr, &mh, &tc);
+                    ++rays_closest;
+                    const V3 inc = mis_incident(sc, sc.lights[o.direct.mis_light], mr, mh.slot);
+                    if (!is_black(inc)) Lp = Lp + o.direct.mis_w * inc;
+                }
+                if (!o.alive) break;
+                ray.o = o.next_o; ray.d = o.next_d; ray.t_max = FTN_INF; beta = o.beta; state = o.state;
+            }
+            L[path] = make_float4(Lp.x, Lp.y, Lp.z, 0.0f);
+        }
+        for (int i = 0; i < fw * fh; ++i) film_gather_pixel(pp, pfilm.data(), L.data(), i, reach, &accum[i], &err);   // k_film_accumulate
+    }
+    for (int i = 0; i < fw * fh; ++i) {   // k_film_resolve into a zeroed film
+        float4 p = make_float4(0, 0, 0, 0);
+        film_resolve_pixel(accum[i], &p);
+        out_pixels[i].xyz[0] = p.x; out_pixels[i].xyz[1] = p.y; out_pixels[i].xyz[2] = p.z; out_pixels[i].filter_weight_sum = p.w;
+    }
+    if (stats) { std::memset(stats, 0, sizeof(*stats)); stats->camera_samples = camera_samples; stats->rays_closest = rays_closest; stats->rays_any = rays_any; stats->bvh_nodes = s->n_nodes; stats->bvh_node_bytes = 64; stats->bvh_tri_bytes = 48; }
+    if (err & ERR_NAN) return fail(FTN_ERR_NAN_RADIANCE, "NaN radiance");
+    if (err & ERR_UNSUPPORTED) return fail(FTN_ERR_UNSUPPORTED, "unsupported");
+    return FTN_OK;
+}
+
+// ---- per-function hooks mirroring the oracle's orc_kat_* ------------------------------------------------------
+SIM_API int sim_kat_triangle_intersect(const float p0[3], const float p1[3], const float p2[3], const FtnRay* r, float out[4]) {
+    TriHit h; const RayF ray = to_rayf(*r);
+    if (!triangle_intersect(V3(p0[0], p0[1], p0[2]), V3(p1[0], p1[1], p1[2]), V3(p2[0], p2[1], p2[2]), ray.o, make_ray_shear(ray.d), ray.t_max, &h)) return 0;
+    out[0] = h.t; out[1] = h.b0; out[2] = h.b1; out[3] = h.b2; return 1;
+}
+SIM_API int sim_kat_sphere_intersect(const FtnSphere* fs, const FtnRay* r, float out[13]) {
+    FtnSceneDesc d; std::memset(&d, 0, sizeof(d)); d.abi_version = FTN_ABI_VERSION; d.spheres = fs; d.n_spheres = 1;
+    SimScene* s; sim_scene_create(&d, &s);
+    SphereHit h; const bool hit = sphere_intersect(s->spheres[0], to_rayf(*r), &h);
+    if (hit) {
+        out[0] = h.t; out[1] = h.p.x; out[2] = h.p.y; out[3] = h.p.z; out[4] = h.p_err.x; out[5] = h.p_err.y; out[6] = h.p_err.z;
+        out[7] = h.n.x; out[8] = h.n.y; out[9] = h.n.z; out[10] = h.wo.x; out[11] = h.wo.y; out[12] = h.wo.z;
+    }
+    delete s;
+    return hit ? 1 : 0;
+}
+SIM_API void sim_kat_camera_ray(const FtnCamera* cam, float fx, float fy, float lx, float ly, float tu, FtnRay* out) {
+    const RayF r = camera_ray(*cam, fx, fy, lx, ly, tu);
+    out->o[0] = r.o.x; out->o[1] = r.o.y; out->o[2] = r.o.z; out->d[0] = r.d.x; out->d[1] = r.d.y; out->d[2] = r.d.z; out->t_max = r.t_max; out->time = r.time;
+}
+SIM_API void sim_kat_offset_ray_origin(const float p[3], const float e[3], const float n[3], const float d[3], float out[3]) {
+    const V3 r = offset_ray_origin(V3(p[0], p[1], p[2]), V3(e[0], e[1], e[2]), V3(n[0], n[1], n[2]), V3(d[0], d[1], d[2]));
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+SIM_API void sim_kat_bsdf(const FtnMaterial* m, const float wo[3], const float wi[3], const float u[2], float out[12]) {
+    FtnSceneDesc d; std::memset(&d, 0, sizeof(d)); d.abi_version = FTN_ABI_VERSION; d.materials = m; d.n_materials = 1;
+    SimScene* s; sim_scene_create(&d, &s);
+    Bsdf b; bsdf_init(&b, V3(0, 0, 1), V3(0, 0, 1), V3(1, 0, 0));
+    material_bsdf(s->mats[0], &b);
+    const V3 o(wo[0], wo[1], wo[2]), i(wi[0], wi[1], wi[2]);
+    const V3 f = bsdf_f(b, o, i, BXDF_ALL);
+    out[0] = f.x; out[1] = f.y; out[2] = f.z; out[3] = bsdf_pdf(b, o, i, BXDF_ALL);
+    ScatterSample sm; const bool ok = bsdf_sample_f(b, o, u[0], u[1], BXDF_ALL, &sm);
+    out[4] = ok ? 1.0f : 0.0f;
+    if (ok) { out[5] = sm.f.x; out[6] = sm.f.y; out[7] = sm.f.z; out[8] = sm.wi.x; out[9] = sm.wi.y; out[10] = sm.wi.z; out[11] = sm.pdf; }
+    else for (int k = 5; k < 12; ++k) out[k] = 0.0f;
+    delete s;
+}
+SIM_API int sim_kat_env(const SimScene* s, const float u[2], float out[11]) {
+    const EnvLightData& e = s->lights[0].env;
+    V3 wi, L; float pdf;
+    if (!env_sample(e, u[0], u[1], &wi, &pdf, &L)) return FTN_ERR_UNSUPPORTED;
+    out[0] = wi.x; out[1] = wi.y; out[2] = wi.z; out[3] = pdf; out[4] = L.x; out[5] = L.y; out[6] = L.z;
+    out[7] = env_pdf(e, wi);
+    const V3 le = env_emitted(e, wi); out[8] = le.x; out[9] = le.y; out[10] = le.z;
+    return FTN_OK;
+}
+SIM_API float sim_kat_counter_uniform(uint64_t seed, uint64_t sample_index, uint32_t dim) {
+    return sampler_uniform(sampler_sample_key(sampler_seed_key(seed), sample_index), dim);
+}
+SIM_API float sim_kat_gamma(int n) { return gamma_n(n); }

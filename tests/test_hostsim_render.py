@@ -1,0 +1,115 @@
+"""CPU tier: the wavefront path logic (ftn_path.cuh, host-compiled) against the oracle --
+tests/furnace.rs thresholds, counter-sampler image A/B, sample sharding, film footprint."""
+import numpy as np
+import pytest
+
+from fountain_b200 import _abi as A
+from fountain_b200 import api, scenes
+from fountain_b200.transform import Transform
+from tests import parity
+
+
+@pytest.fixture(scope="module")
+def sim_backend():
+    from tests.hostsim import sim
+    return sim.backend()
+
+
+# ---- tests/furnace.rs on the device path logic ------------------------------------------------
+def test_furnace_path(sim_backend):
+    rgb, _, _ = parity.render(sim_backend, scenes.furnace_scene, api.PathIntegrator(10, 1.0), 128)
+    assert np.all(np.abs(rgb - 2.0) <= 0.1)                      # furnace.rs:20
+
+
+def test_furnace_path_no_rr(sim_backend, orc_backend):
+    rgb, px, st = parity.render(sim_backend, scenes.furnace_scene, api.PathIntegrator(10, 0.0), 128)
+    assert np.all(np.abs(rgb - 2.0) <= 0.001)                    # furnace.rs:36
+    assert st["rays_closest"] == 16 * 16 * 128 * 21 and st["rays_any"] == 16 * 16 * 128 * 10
+    ref, rpx, rst = parity.render(orc_backend, scenes.furnace_scene, api.PathIntegrator(10, 0.0), 128)
+    assert np.allclose(rgb, ref, rtol=2e-5, atol=0)
+    assert np.array_equal(px[..., 3], rpx[..., 3])
+
+
+def test_furnace_directlighting(sim_backend):
+    rgb, _, _ = parity.render(sim_backend, scenes.furnace_scene, api.DirectLightingIntegrator(3), 128)
+    assert np.all(np.abs(rgb - 1.5) <= 0.00001)                  # furnace.rs:55
+
+
+# ---- image A/B at equal counter streams ----------------------------------------------------------
+@pytest.mark.parametrize("material", ["matte", "metal", "plastic"])
+def test_cube_image_matches_oracle(sim_backend, orc_backend, material):
+    mat = {"matte": lambda: api.MatteMaterial((0.5, 0.4, 0.6)),
+           "metal": lambda: api.MetalMaterial((0.2, 0.92, 1.1), (3.9, 2.45, 2.14), roughness=0.1),
+           "plastic": lambda: api.PlasticMaterial(0.3, 0.4, 0.15)}[material]
+    kw = dict(resolution=(40, 40))
+    a, apx, ast = parity.render(sim_backend, lambda backend, **k: scenes.rounded_cube_scene(backend=backend, material=mat(), **k), api.PathIntegrator(5, 1.0), 4, seed=3, **kw)
+    b, bpx, bst = parity.render(orc_backend, lambda backend, **k: scenes.rounded_cube_scene(backend=backend, material=mat(), **k), api.PathIntegrator(5, 1.0), 4, seed=3, **kw)
+    mean_rel, frac_off = parity.image_diff(a, b)
+    assert mean_rel < 2e-3 and frac_off < 0.02, (mean_rel, frac_off)
+    assert np.array_equal(apx[..., 3], bpx[..., 3])
+    # identical control flow almost everywhere => nearly identical ray counts
+    assert abs(ast["rays_closest"] - bst["rays_closest"]) <= 0.002 * bst["rays_closest"]
+    assert abs(ast["rays_any"] - bst["rays_any"]) <= 0.002 * bst["rays_any"]
+
+
+def test_envmap_thin_lens_image_matches_oracle(sim_backend, orc_backend):
+    def build(backend):
+        env = api.InfiniteAreaLight.new_envmap(scenes.sky_sun_envmap(64, 32, peak=50.0), Transform.rotate(20, (0, 0, 1)))
+        scene, camera, film = scenes.rounded_cube_scene(backend=backend, resolution=(36, 24), light=env,
+                                                        material=api.MetalMaterial((0.2, 0.92, 1.1), (3.9, 2.45, 2.14), roughness=0.3))
+        camera = api.PerspectiveCamera(camera.camera_to_world, (36, 24), fov=40.0, lens_radius=0.5, focal_dist=32.0)
+        return scene, camera, film
+    a, _, _ = parity.render(sim_backend, lambda backend: build(backend), api.PathIntegrator(4, 1.0), 4, seed=9)
+    b, _, _ = parity.render(orc_backend, lambda backend: build(backend), api.PathIntegrator(4, 1.0), 4, seed=9)
+    mean_rel, frac_off = parity.image_diff(a, b)
+    assert mean_rel < 5e-3 and frac_off < 0.03, (mean_rel, frac_off)
+
+
+def test_null_material_is_skipped(sim_backend, orc_backend):
+    """A mesh without a material has a null BSDF: paths pass through (path.rs:76-80)."""
+    def build_null(backend):
+        mesh = api.TriangleMesh.from_ply(scenes.ROUNDED_CUBE_PLY)
+        scene = api.Scene([api.GeometricPrimitive(mesh, None)], [api.InfiniteAreaLight.new_uniform(1.0)], backend=backend)
+        _, camera, film = scenes.rounded_cube_scene(backend=backend, resolution=(24, 24))
+        return scene, camera, film
+    a, _, _ = parity.render(sim_backend, build_null, api.PathIntegrator(5, 1.0), 2)
+    b, _, _ = parity.render(orc_backend, build_null, api.PathIntegrator(5, 1.0), 2)
+    assert np.allclose(a, 1.0, atol=1e-5) and np.allclose(b, 1.0, atol=1e-5)    # sees the environment through the cube
+
+
+def test_sample_sharding_partitions_the_render(sim_backend):
+    scene, camera, film = scenes.rounded_cube_scene(backend=sim_backend, resolution=(24, 24))
+    integ = api.SamplerIntegrator(camera, api.PathIntegrator(5, 1.0))
+    sampler = api.RandomSampler.new_with_seed(8, 5)
+    integ.render_parallel(scene, film, sampler)
+    full = film.pixels.copy()
+    acc = np.zeros_like(full)
+    for rank in range(4):
+        integ.render_parallel(scene, film, sampler, sample_begin=rank, sample_stride=4)
+        assert np.all(film.pixels[..., 3] == 2.0)
+        acc += film.pixels
+    assert np.allclose(acc, full, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("radius,crop", [((0.5, 0.5), ((0.0, 0.0), (1.0, 1.0))), ((1.5, 1.0), ((0.0, 0.0), (1.0, 1.0))),
+                                         ((0.5, 0.5), ((0.25, 0.1), (0.8, 0.75))), ((0.3, 0.3), ((0.0, 0.0), (1.0, 1.0)))])
+def test_film_footprint_matches_oracle(sim_backend, orc_backend, radius, crop):
+    """Filter radius / crop window variants of Film::add_sample_to_tile + get_film_tile (incl. the
+    tile clipping and the `- radius` quirk of film.rs:100): weights are small integers -> exact."""
+    def build(backend):
+        scene, camera, _ = scenes.rounded_cube_scene(backend=backend, resolution=(40, 36))
+        film = api.Film((40, 36), crop_window=crop, filter=api.BoxFilter(radius), backend=backend)
+        return scene, camera, film
+    a, apx, _ = parity.render(sim_backend, build, api.PathIntegrator(1, 1.0), 3, seed=2)
+    b, bpx, _ = parity.render(orc_backend, build, api.PathIntegrator(1, 1.0), 3, seed=2)
+    assert apx.shape == bpx.shape
+    assert np.array_equal(apx[..., 3], bpx[..., 3])                   # filter-weight sums: exact
+    assert np.allclose(apx[..., :3], bpx[..., :3], rtol=2e-4, atol=1e-5)
+
+
+def test_reference_stream_is_rejected(sim_backend):
+    scene, camera, film = scenes.furnace_scene(backend=sim_backend)
+    with pytest.raises(api.FountainError) as e:
+        api.SamplerIntegrator(camera, api.PathIntegrator(2, 1.0)).render_parallel(
+            scene, film, api.RandomSampler.new_with_seed(1, 0, mode=A.FTN_SAMPLER_REFERENCE_TILE_STREAM))
+    assert e.value.code == A.FTN_ERR_UNSUPPORTED
