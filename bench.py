@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native path (BASELINE.json metric: Mrays/s incl.
+secondary rays, and camera samples/s, per scene, next to the host-CPU figure).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4|c5]
+
+A "step" is one pass of the hot path over one batch of synthetic input:
+  c2 (default, BASELINE configs[1]): one full render of data/rounded_cube.ply, Lambert, uniform
+      env light, 512x512, 64 spp, path depth 5 (16.8 M camera samples per step).
+  c3: one closest-hit query of a 4 Mi incoherent diffuse-bounce ray batch on the 1M-triangle mesh.
+  c4: logo-style scene (thin lens, TR metal, image env), 1920x1080 at --spp.
+  c5: large synthetic mesh (--tris) at 3840x2160 at --spp.
+Prints ONE JSON line (rank 0).  `value` = whole-job Mrays/s with the scene resident in HBM;
+`e2e` = the same metric through the host-buffer API (scene upload + BVH build + render + film
+read-back inside the timed region).  N > 1: one process per GPU (torchrun), replicated scene,
+sample-index sharding, one NCCL reduction of the film; per-GPU work is fixed (weak scaling).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from fountain_b200 import _abi as A          # noqa: E402
+from fountain_b200 import api, scenes        # noqa: E402
+
+METRIC = "Mrays/s (closest-hit + any-hit + MIS rays)"
+UNIT = "Mrays/s"
+
+
+# ---------------------------------------------------------------------------------------------------
+def workload_scene(name, backend, args):
+    """-> (scene, camera, film, integrator, spp, description)"""
+    if name == "c2":
+        scene, camera, film = scenes.rounded_cube_scene(backend=backend, resolution=(512, 512))
+        return scene, camera, film, api.PathIntegrator(5, 1.0), args.spp or 64, \
+            "C2 rounded_cube.ply (4332 tris) Lambert Kd .5, uniform env L=1, 512x512, %d spp, path depth 5, rr 1.0" % (args.spp or 64)
+    if name == "c4":
+        scene, camera, film = scenes.logo_style_scene(backend=backend, resolution=(1920, 1080), detail=args.detail)
+        return scene, camera, film, api.PathIntegrator(5, 1.0), args.spp or 16, \
+            "C4 logo-style gear ring (%d tris) TR copper r=.01, thin lens, 2048x1024 sky+sun env, 1920x1080, %d spp, depth 5" % (scene.n_triangles, args.spp or 16)
+    if name == "c5":
+        n_lon = int(round(args.tris ** 0.5))
+        scene, camera = scenes.synthetic_mesh_scene(n_lon, n_lon // 2, backend=backend, resolution=(3840, 2160))
+        film = api.Film((3840, 2160), backend=backend)
+        return scene, camera, film, api.PathIntegrator(5, 1.0), args.spp or 4, \
+            "C5 displaced sphere (%d tris) Lambert, uniform env, 3840x2160, %d spp, depth 5" % (scene.n_triangles, args.spp or 4)
+    raise SystemExit("unknown render workload %r" % name)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for t, line in self.rows:
+            if t0 is not None and not (t0 - 0.05 <= t <= t1 + 0.15):
+                continue
+            p = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_from_profiles(kernel):
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(kernel)
+    return None
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_baseline(name, args, budget_s=15.0):
+    """The oracle (CPU restatement of the reference algorithm) on the host cores, on a bounded
+    sample of the same workload: the same scene / camera / resolution at reduced spp."""
+    from oracle import orc
+    be = orc.backend()
+    cores = orc.hardware_threads()
+    orc.set_threads(cores)
+    scene, camera, film, integ, spp, desc = workload_scene(name, be, args)
+    runner = api.SamplerIntegrator(camera, integ)
+    t = time.perf_counter()
+    st = runner.render_parallel(scene, film, api.RandomSampler.new_with_seed(1, 0, mode=A.FTN_SAMPLER_REFERENCE_TILE_STREAM))
+    t1 = time.perf_counter() - t
+    n = max(1, min(spp, int(budget_s / max(t1, 1e-3))))
+    t = time.perf_counter()
+    st = runner.render_parallel(scene, film, api.RandomSampler.new_with_seed(n, 0, mode=A.FTN_SAMPLER_REFERENCE_TILE_STREAM))
+    dt = time.perf_counter() - t
+    rays = st["rays_closest"] + st["rays_any"]
+    return {"value": rays / dt / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+            "samples_per_s": st["camera_samples"] / dt, "seconds": dt, "bvh_build_seconds": scene.stats()["bvh_build_seconds"],
+            "sample": "%s at %d of %d spp, reference tile-stream sampler, %d threads (C++ restatement of the reference; Rust toolchain absent)"
+                      % (desc.split(",")[0], n, spp, cores)}
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm's CPU implementation (oracle port) on the host
+    cores; each step = BVH build + render of a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import orc
+    be = orc.backend()
+    cores = orc.hardware_threads()
+    orc.set_threads(cores)
+    name = args.workload
+    scene, camera, film, integ, spp, desc = workload_scene(name, be, args)
+    runner = api.SamplerIntegrator(camera, integ)
+    t = time.perf_counter()
+    runner.render_parallel(scene, film, api.RandomSampler.new_with_seed(1, 0, mode=A.FTN_SAMPLER_REFERENCE_TILE_STREAM))
+    t1 = time.perf_counter() - t
+    total = args.steps + args.warmup
+    n = max(1, min(spp, int(120.0 / total / max(t1, 1e-3))))   # whole run within ~2 minutes
+    rays = samples = 0
+    secs = 0.0
+    for i in range(total):
+        t = time.perf_counter()
+        scene, camera, film, integ, _, _ = workload_scene(name, be, args)      # scene build + BVH::build
+        st = api.SamplerIntegrator(camera, integ).render_parallel(scene, film, api.RandomSampler.new_with_seed(n, i, mode=A.FTN_SAMPLER_REFERENCE_TILE_STREAM))
+        dt = time.perf_counter() - t
+        if i >= args.warmup:
+            secs += dt; rays += st["rays_closest"] + st["rays_any"]; samples += st["camera_samples"]
+    v = rays / secs / 1e6
+    sample = "%s at %d of %d spp per step (BVH build + render), %d host threads" % (desc.split(",")[0], n, spp, cores)
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "config": {"workload": desc, "sample": sample},
+           "samples_per_s": samples / secs,
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_ours_render(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    gpu = api.default_backend()
+    gpu.call("set_device", local_rank)
+
+    name = args.workload
+    scene, camera, film, integ, spp, desc = workload_scene(name, gpu, args)
+    # weak scaling: every rank renders `spp` samples per pixel of a (spp * world)-spp image,
+    # sample indices interleaved across ranks (rank r owns s = r, r + world, ...)
+    spp_total = spp * world
+    sampler = api.RandomSampler.new_with_seed(spp_total, 0)
+    cam_abi, film_abi, integ_abi = camera.to_abi(), film.to_abi(), integ.to_abi()
+    smp_abi = sampler.to_abi(sample_begin=rank, sample_stride=world)
+    n_px = film.width * film.height
+    d_film = torch.zeros((n_px, 4), dtype=torch.float32, device=dev)
+    d_rgb = torch.empty((n_px, 3), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def one_step(stats):
+        d_film.zero_()
+        gpu.call("render_device", scene.handle, C.byref(cam_abi), C.byref(film_abi), C.byref(smp_abi), C.byref(integ_abi),
+                 C.c_void_p(d_film.data_ptr()), C.byref(stats), C.c_void_p(stream.cuda_stream))
+        if world > 1:
+            dist.reduce(d_film, dst=0, op=dist.ReduceOp.SUM)            # merge_film_tile across GPUs
+        if rank == 0:
+            gpu.call("film_to_rgb_device", n_px, C.c_void_p(d_film.data_ptr()), C.c_void_p(d_rgb.data_ptr()), C.c_void_p(stream.cuda_stream))
+
+    st = A.FtnStats()
+    for _ in range(args.warmup):
+        one_step(st)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = int(gpu.fn["kernel_launch_count"]())
+    ms_total = 0.0
+    rays = samples = 0
+    tsec = [0.0, 0.0, 0.0]; tl = [0, 0, 0]; trays = [0, 0, 0]
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()                                                  # L2 flush between timed iterations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        one_step(st)
+        e1.record(stream)
+        e1.synchronize()
+        ms_total += e0.elapsed_time(e1)
+        rays += st.rays_closest + st.rays_any
+        samples += st.camera_samples
+        for c in range(3):
+            tsec[c] += st.trace_seconds[c]; tl[c] += st.trace_launches[c]; trays[c] += st.trace_rays[c]
+    torch.cuda.synchronize()
+    t_wall1 = time.perf_counter()
+    launches = int(gpu.fn["kernel_launch_count"]()) - launches0
+    clock_info = clocks.stop(t_wall0, t_wall1) if clocks else None
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        tot = torch.tensor([rays, samples, launches], dtype=torch.float64, device=dev)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        rays, samples, launches = (int(x) for x in tot.tolist())
+    value = rays / (ms_total * 1e-3) / 1e6
+
+    # ---- traversal counts for the algorithmic-bytes roofline (untimed counting render, same rays) ----
+    cst = A.FtnStats(); cst.reserved = 1
+    d_film.zero_()
+    gpu.call("render_device", scene.handle, C.byref(cam_abi), C.byref(film_abi), C.byref(smp_abi), C.byref(integ_abi),
+             C.c_void_p(d_film.data_ptr()), C.byref(cst), C.c_void_p(stream.cuda_stream))
+    torch.cuda.synchronize()
+    node_b, tri_b = cst.bvh_node_bytes, cst.bvh_tri_bytes
+    k = 0                                                             # dominant kernel: k_extend (closest hit)
+    bytes_per_step = node_b * cst.trace_nodes[k] + tri_b * cst.trace_tris[k] + 48 * cst.trace_rays[k]
+    launches_per_step = max(1, tl[k] // args.steps)
+    peak, peak_src = measured_peak()
+    achieved = bytes_per_step * args.steps / max(tsec[k], 1e-12) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic_from_profiles("k_extend"), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_per_step / launches_per_step,
+                "avg_launch_ms": tsec[k] / max(1, tl[k]) * 1e3, "launches_per_step": launches_per_step,
+                "bytes_per_ray": bytes_per_step / max(1, cst.trace_rays[k]),
+                "nodes_per_ray": cst.trace_nodes[k] / max(1, cst.trace_rays[k]), "tris_per_ray": cst.trace_tris[k] / max(1, cst.trace_rays[k]),
+                "node_bytes": node_b, "tri_bytes": tri_b, "kernel_share_of_step": tsec[k] / (ms_total * 1e-3),
+                "all_traversal_share_of_step": sum(tsec) / (ms_total * 1e-3),
+                "kernel_mrays_per_s": trays[k] / max(tsec[k], 1e-12) / 1e6,
+                "note": "working set (%.1f MB nodes+tris) is L2-resident for this scene; HBM peak is the stated denominator"
+                        % ((cst.bvh_nodes * node_b + scene.n_triangles * tri_b) / 1e6)}
+
+    # ---- e2e: host buffers in, host film out; scene upload + BVH build + render + read-back per step ----
+    e2e_rays = 0
+    e2e_secs = 0.0
+    h2d = d2h = 0
+    for i in range(max(1, min(args.steps, 3))):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        sc2, cam2, film2, integ2, _, _ = workload_scene(name, gpu, args)          # PLY arrays -> ftn_scene_create (H2D) + ftn_bvh_build
+        if world == 1:
+            st2 = api.SamplerIntegrator(cam2, integ2).render_parallel(sc2, film2, sampler)   # ftn_render: film D2H inside
+            r = st2["rays_closest"] + st2["rays_any"]
+            d2h = film2.pixels.nbytes
+        else:
+            s2 = A.FtnStats()
+            d_film.zero_()
+            gpu.call("render_device", sc2.handle, C.byref(cam2.to_abi()), C.byref(film2.to_abi()), C.byref(smp_abi), C.byref(integ2.to_abi()),
+                     C.c_void_p(d_film.data_ptr()), C.byref(s2), C.c_void_p(stream.cuda_stream))
+            dist.reduce(d_film, dst=0, op=dist.ReduceOp.SUM)
+            host_film = d_film.cpu() if rank == 0 else None
+            r = s2.rays_closest + s2.rays_any
+            d2h = (host_film.numel() * 4) if rank == 0 else 0
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        h2d = sc2.upload_bytes
+        sc2.close()
+        if world > 1:
+            tt = torch.tensor([dt, float(r)], dtype=torch.float64, device=dev)
+            mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            dt, r = float(mx[0].item()), int(sm[1].item())
+        e2e_secs += dt; e2e_rays += r
+    e2e = {"value": e2e_rays / e2e_secs / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "ms_per_step": e2e_secs / max(1, min(args.steps, 3)) * 1e3,
+           "includes": "ftn_scene_create (mesh H2D) + ftn_bvh_build + ftn_render + film D2H"}
+
+    if rank == 0:
+        base = cpu_baseline(name, args) if (world == 1 and not args.no_cpu_baseline) else None
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic",
+               "config": {"workload": desc, "spp_per_gpu": spp, "spp_total": spp_total,
+                          "parallelism": "replicated scene, sample-index sharding, NCCL film reduce" if world > 1 else "single GPU",
+                          "l2": "flushed between timed steps (256 MiB write)", "bvh": "LBVH (30-bit Morton, radix sort) -> BVH2x64, leaves <= 4 tris"},
+               "samples_per_s": samples / (ms_total * 1e-3), "rays_per_step": rays // args.steps,
+               "clocks": clock_info, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": base,
+               "bvh_build_ms": scene.stats()["bvh_build_seconds"] * 1e3}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_ours_raybatch(args):
+    """c3: closest-hit ray batches on the 1M-triangle mesh: coherent primary rays and incoherent
+    diffuse-bounce rays.  value = incoherent batch."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    gpu = api.default_backend()
+    gpu.call("set_device", local_rank)
+    n_lon = int(round(args.tris ** 0.5)); side = (n_lon, n_lon // 2)          # n_lon * n_lat * 2 triangles
+    t0 = time.perf_counter()
+    scene, camera = scenes.synthetic_mesh_scene(side[0], side[1], backend=gpu, resolution=(2048, 2048))
+    build_wall = time.perf_counter() - t0
+    prim = scenes.primary_ray_batch(camera, (2048, 2048))
+    hits = scene.intersect(prim)
+    inc = scenes.diffuse_bounce_batch(prim, hits, scene._positions, scene._indices, seed=2)
+    reps = int(np.ceil((4 << 20) / max(1, len(inc))))
+    inc = np.concatenate([inc] * reps)[: 4 << 20] if len(inc) < (4 << 20) else inc
+    stream = torch.cuda.current_stream()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    results = {}
+    peak, peak_src = measured_peak()
+    for label, batch in (("coherent_primary", prim), ("incoherent_diffuse", inc)):
+        n = len(batch)
+        d_rays = torch.from_numpy(batch.view(np.float32).reshape(n, 8)).to(dev)
+        d_hits = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        d_cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+        gpu.call("intersect_count_device", scene.handle, n, C.c_void_p(d_rays.data_ptr()), C.c_void_p(d_hits.data_ptr()),
+                 C.c_void_p(d_cnt.data_ptr()), C.c_void_p(stream.cuda_stream))
+        torch.cuda.synchronize()
+        nodes, tris = (int(x) for x in d_cnt.tolist())
+        for _ in range(args.warmup):
+            gpu.call("intersect_device", scene.handle, n, C.c_void_p(d_rays.data_ptr()), C.c_void_p(d_hits.data_ptr()), C.c_void_p(stream.cuda_stream))
+        times = []
+        l0 = int(gpu.fn["kernel_launch_count"]())
+        for _ in range(args.steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            gpu.call("intersect_device", scene.handle, n, C.c_void_p(d_rays.data_ptr()), C.c_void_p(d_hits.data_ptr()), C.c_void_p(stream.cuda_stream))
+            e1.record(stream); e1.synchronize()
+            times.append(e0.elapsed_time(e1))
+        launches = int(gpu.fn["kernel_launch_count"]()) - l0
+        med = float(np.median(times))
+        st = scene.stats()
+        bytes_ = st["bvh_node_bytes"] * nodes + st["bvh_tri_bytes"] * tris + 48 * n
+        results[label] = {"rays": n, "ms_median": med, "mrays_per_s": n / (med * 1e-3) / 1e6, "nodes_per_ray": nodes / n, "tris_per_ray": tris / n,
+                          "bytes_per_ray": bytes_ / n, "achieved_gbs": bytes_ / (med * 1e-3) / 1e9, "frac_of_peak": bytes_ / (med * 1e-3) / 1e9 / peak,
+                          "launches": launches, "hit_fraction": float((d_hits[:, 0].view(torch.int32) != -1).float().mean().item())}
+    # e2e: host rays in, host hits out
+    t0 = time.perf_counter()
+    for _ in range(3):
+        scene.intersect(inc)
+    e2e_dt = (time.perf_counter() - t0) / 3
+    inc_r = results["incoherent_diffuse"]
+    if rank == 0:
+        st = scene.stats()
+        print(json.dumps({"metric": METRIC, "value": inc_r["mrays_per_s"], "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": inc_r["ms_median"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic",
+                          "config": {"workload": "C3 displaced sphere %d tris: closest-hit batches, 2048x2048 primary + %d incoherent diffuse-bounce rays"
+                                                 % (scene.n_triangles, len(inc)), "l2": "flushed between timed steps (256 MiB write)"},
+                          "batches": results, "gpu_launches": results["incoherent_diffuse"]["launches"],
+                          "e2e": {"value": len(inc) / e2e_dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(inc.nbytes), "d2h_bytes_per_step": int(len(inc) * 16)},
+                          "roofline": {"bound": "hbm", "kernel": "k_intersect_batch<closest>", "achieved": inc_r["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                                       "frac": inc_r["frac_of_peak"], "traffic": traffic_from_profiles("k_intersect_batch"), "peak_source": peak_src},
+                          "bvh_build_ms": st["bvh_build_seconds"] * 1e3, "scene_create_and_build_wall_s": build_wall, "bvh_nodes": st["bvh_nodes"]}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--spp", type=int, default=0)
+    ap.add_argument("--tris", type=int, default=1_000_000)
+    ap.add_argument("--detail", type=float, default=1.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    elif args.workload == "c3":
+        run_ours_raybatch(args)
+    else:
+        run_ours_render(args)
+
+
+if __name__ == "__main__":
+    main()

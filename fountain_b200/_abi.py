@@ -93,10 +93,12 @@ class FtnStats(C.Structure):
     _fields_ = [("camera_samples", u64), ("rays_closest", u64), ("rays_any", u64), ("node_visits", u64),
                 ("tri_tests", u64), ("kernel_launches", u64), ("device_seconds", C.c_double),
                 ("bvh_build_seconds", C.c_double), ("bvh_nodes", u32), ("bvh_node_bytes", u32),
-                ("bvh_tri_bytes", u32), ("reserved", u32)]
+                ("bvh_tri_bytes", u32), ("reserved", u32), ("trace_seconds", C.c_double * 3),
+                ("trace_launches", u64 * 3), ("trace_rays", u64 * 3), ("trace_nodes", u64 * 3), ("trace_tris", u64 * 3)]
 
     def as_dict(self):
-        return {name: getattr(self, name) for name, _ in self._fields_}
+        return {name: (list(getattr(self, name)) if hasattr(getattr(self, name), "__len__") else getattr(self, name))
+                for name, _ in self._fields_}
 
 
 VOIDP = C.c_void_p

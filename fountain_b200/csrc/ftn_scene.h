@@ -100,6 +100,10 @@ struct FtnScene {
     float bounds[6] = {0, 0, 0, 0, 0, 0};
     double build_seconds = 0.0;
     unsigned long long* d_work = nullptr;   // dynamic work-fetch counter of the batch queries
+    bool material_present[3] = {false, false, false};   // which shade kernels a render launches
+    bool has_null_material = false;         // any primitive with a null BSDF (path.rs:76-80)
+    mutable void* ws = nullptr;             // cached render workspace (one render at a time per scene)
+    mutable size_t ws_bytes = 0;
     ftn::SceneView view() const;
 };
 

@@ -71,6 +71,14 @@ __device__ __forceinline__ void queue_push(uint32_t* const* queues, uint32_t* co
 
 struct Queues { uint32_t* q[Q_COUNT]; };
 
+// node-visit / triangle-test totals of the counting variants (the bytes-per-ray roofline input)
+__device__ __forceinline__ void flush_trace_counters(const TraceCounters& tc, unsigned long long* trav) {
+    unsigned long long n = tc.nodes, t = tc.tris;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { n += __shfl_xor_sync(0xffffffffu, n, o); t += __shfl_xor_sync(0xffffffffu, t, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&trav[0], n); atomicAdd(&trav[1], t); }
+}
+
 // ---- raygen ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_raygen(PassParams pp, PathArrays pa) {
@@ -88,9 +96,12 @@ k_raygen(PassParams pp, PathArrays pa) {
 
 // ---- extend: closest hit + binning by material class ----------------------------------------------------------
 // queue_in == nullptr: the identity queue (first bounce of a pass)
+template <bool COUNT>
 __global__ void __launch_bounds__(FTN_TRACE_THREADS)
-k_extend(SceneView sc, PathArrays pa, const uint32_t* __restrict__ queue_in, uint32_t n_in, Queues qs, uint32_t* __restrict__ counts) {
+k_extend(SceneView sc, PathArrays pa, const uint32_t* __restrict__ queue_in, uint32_t n_in, Queues qs, uint32_t* __restrict__ counts,
+         unsigned long long* __restrict__ trav) {
     const int lane = threadIdx.x & 31;
+    TraceCounters tc; tc.nodes = 0; tc.tris = 0;
     for (;;) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(&counts[W_EXTEND], 32u);
@@ -102,8 +113,8 @@ k_extend(SceneView sc, PathArrays pa, const uint32_t* __restrict__ queue_in, uin
         if (k < n_in) {
             path = queue_in ? queue_in[k] : k;
             const RayF ray = load_ray(pa, path);
-            SceneHit h; TraceCounters tc;
-            scene_intersect<false, false>(sc, ray, &h, &tc);
+            SceneHit h;
+            scene_intersect<false, COUNT>(sc, ray, &h, &tc);
             pa.hit[path] = h.slot;
             if (h.slot == FTN_NO_HIT_SLOT) target = Q_MISS;
             else {
@@ -113,6 +124,7 @@ k_extend(SceneView sc, PathArrays pa, const uint32_t* __restrict__ queue_in, uin
         }
         queue_push(qs.q, counts, target, path);
     }
+    if (COUNT) flush_trace_counters(tc, trav);
 }
 
 // ---- miss: Scene::environment_emitted_radiance (path.rs:45-51, scene/mod.rs:58-64) -----------------------------
@@ -164,10 +176,12 @@ k_shade(SceneView sc, PassParams pp, PathArrays pa, const uint32_t* __restrict__
 }
 
 // ---- shadow rays: VisibilityTester::unoccluded (light/mod.rs:82-84) ---------------------------------------------
+template <bool COUNT>
 __global__ void __launch_bounds__(FTN_TRACE_THREADS)
-k_shadow(SceneView sc, PathArrays pa, const uint32_t* __restrict__ queue, uint32_t* __restrict__ counts) {
+k_shadow(SceneView sc, PathArrays pa, const uint32_t* __restrict__ queue, uint32_t* __restrict__ counts, unsigned long long* __restrict__ trav) {
     const uint32_t n = counts[Q_SHADOW];
     const int lane = threadIdx.x & 31;
+    TraceCounters tc; tc.nodes = 0; tc.tris = 0;
     for (;;) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(&counts[W_SHADOW], 32u);
@@ -179,19 +193,21 @@ k_shadow(SceneView sc, PathArrays pa, const uint32_t* __restrict__ queue, uint32
             RayF ray; ray.o = ld3(pa.sh_o, path); ray.d = ld3(pa.sh_d, path);
             ray.t_max = rn_sub(1.0f, 0.0001f);   // 1 - SHADOW_EPSILON, interaction.rs:10,55
             ray.time = pa.ray_o[path].w;
-            SceneHit h; TraceCounters tc;
-            scene_intersect<true, false>(sc, ray, &h, &tc);
+            SceneHit h;
+            scene_intersect<true, COUNT>(sc, ray, &h, &tc);
             if (h.slot == FTN_NO_HIT_SLOT) st3(pa.L, path, ld3(pa.L, path) + ld3(pa.sh_L, path));
         }
     }
+    if (COUNT) flush_trace_counters(tc, trav);
 }
 
 // ---- MIS (BSDF-sampled) rays: integrator/mod.rs:364-389 ---------------------------------------------------------------
-template <bool ENV_ONLY>
+template <bool ENV_ONLY, bool COUNT>
 __global__ void __launch_bounds__(FTN_TRACE_THREADS)
-k_mis(SceneView sc, PathArrays pa, const uint32_t* __restrict__ queue, uint32_t* __restrict__ counts) {
+k_mis(SceneView sc, PathArrays pa, const uint32_t* __restrict__ queue, uint32_t* __restrict__ counts, unsigned long long* __restrict__ trav) {
     const uint32_t n = counts[Q_MIS];
     const int lane = threadIdx.x & 31;
+    TraceCounters tc; tc.nodes = 0; tc.tris = 0;
     for (;;) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(&counts[W_MIS], 32u);
@@ -203,14 +219,15 @@ k_mis(SceneView sc, PathArrays pa, const uint32_t* __restrict__ queue, uint32_t*
             const float4 w4 = pa.mis_w[path];
             const LightData& light = sc.lights[f2u(w4.w)];
             RayF ray; ray.o = ld3(pa.mis_o, path); ray.d = ld3(pa.mis_d, path); ray.t_max = FTN_INF; ray.time = pa.ray_o[path].w;
-            SceneHit h; TraceCounters tc;
+            SceneHit h;
             // with only infinite lights a hit contributes nothing whatever it is, so any-hit suffices
-            if (ENV_ONLY) scene_intersect<true, false>(sc, ray, &h, &tc);
-            else scene_intersect<false, false>(sc, ray, &h, &tc);
+            if (ENV_ONLY) scene_intersect<true, COUNT>(sc, ray, &h, &tc);
+            else scene_intersect<false, COUNT>(sc, ray, &h, &tc);
             const V3 incident = mis_incident(sc, light, ray, h.slot);
             if (!is_black(incident)) st3(pa.L, path, ld3(pa.L, path) + V3(w4.x, w4.y, w4.z) * incident);
         }
     }
+    if (COUNT) flush_trace_counters(tc, trav);
 }
 
 // ---- film ---------------------------------------------------------------------------------------------------------------
@@ -260,18 +277,40 @@ int film_pixel_count(const FtnFilm* f, int32_t* w, int32_t* h) {
     return FTN_OK;
 }
 
-struct DeviceBuf {
-    void* p = nullptr;
-    ~DeviceBuf() { if (p) cudaFree(p); }
-    int alloc(size_t bytes) {
-        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
-        if (e != cudaSuccess) { p = nullptr; return cuda_fail(e, "cudaMalloc (render)", __FILE__, __LINE__); }
-        return FTN_OK;
+// Device workspace of the wavefront state, cached on the scene between renders (a render of the
+// same size allocates nothing).
+static int workspace_reserve(const FtnScene* s, size_t bytes, char** base) {
+    if (s->ws_bytes < bytes) {
+        if (s->ws) { cudaFree(s->ws); s->ws = nullptr; s->ws_bytes = 0; }
+        cudaError_t e = cudaMalloc(&s->ws, bytes);
+        if (e != cudaSuccess) { s->ws = nullptr; return cuda_fail(e, "cudaMalloc (render workspace)", __FILE__, __LINE__); }
+        s->ws_bytes = bytes;
     }
-    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+    *base = (char*)s->ws;
+    return FTN_OK;
+}
+struct Carver {
+    char* p; size_t off = 0;
+    template <class T> T* take(size_t count) { off = (off + 255) & ~(size_t)255; T* r = reinterpret_cast<T*>(p + off); off += count * sizeof(T); return r; }
 };
 
 static size_t g_max_paths_per_pass = 4u << 20;
+
+// CUDA-event pairs around every traversal launch, per kernel class (extend / shadow / mis): the
+// live per-kernel durations bench.py's roofline uses.
+struct TraceTimer {
+    std::vector<cudaEvent_t> ev; std::vector<int> cls;
+    cudaStream_t st;
+    int begin(int c) { cudaEvent_t a, b; if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return -1; ev.push_back(a); ev.push_back(b); cls.push_back(c); cudaEventRecord(a, st); return 0; }
+    void end() { cudaEventRecord(ev.back(), st); }
+    void collect(double secs[3], uint64_t launches[3]) {
+        for (size_t i = 0; i < cls.size(); ++i) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]) == cudaSuccess) { secs[cls[i]] += ms * 1e-3; launches[cls[i]]++; }
+        }
+    }
+    ~TraceTimer() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+};
 
 int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, const FtnSampler* smp,
                   const FtnIntegrator* integ, FtnPixel* d_pixels, FtnStats* stats, cudaStream_t st) {
@@ -281,6 +320,7 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
     if (smp->samples_per_pixel < 1 || smp->sample_stride < 1 || smp->sample_begin < 0) return set_error(FTN_ERR_INVALID_ARGUMENT, "bad sampler");
     if (integ->type != FTN_INTEGRATOR_PATH && integ->type != FTN_INTEGRATOR_DIRECT_LIGHTING) return set_error(FTN_ERR_INVALID_ARGUMENT, "bad integrator");
     if (integ->max_depth < 0 || integ->max_depth > 60000) return set_error(FTN_ERR_INVALID_ARGUMENT, "bad max_depth");
+    const bool count_traversal = stats && stats->reserved == 1u;   // input flag: also count node visits / triangle tests
     FTN_CUDA(cudaSetDevice(s->device));
     FilmGeom fg;
     if (film_geometry(film, &fg) != FTN_OK) return set_error(FTN_ERR_INVALID_ARGUMENT, "bad film (resolution, filter radius or crop window)");
@@ -300,45 +340,34 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
     FTN_CUDA(cudaEventCreate(&ev0)); FTN_CUDA(cudaEventCreate(&ev1));
     FTN_CUDA(cudaEventRecord(ev0, st));
 
-    DeviceBuf b_f4[10], b_hit, b_state, b_pfilm, b_accum, b_queues, b_counts, b_err;
-    for (int i = 0; i < 10; ++i) FTN_TRY(b_f4[i].alloc(P * sizeof(float4)));
-    FTN_TRY(b_hit.alloc(P * 4)); FTN_TRY(b_state.alloc(P * 4)); FTN_TRY(b_pfilm.alloc(P * sizeof(float2)));
-    FTN_TRY(b_accum.alloc((size_t)fw * fh * sizeof(float4)));
-    FTN_TRY(b_queues.alloc((size_t)(Q_COUNT + 1) * P * 4));
-    FTN_TRY(b_counts.alloc(CTR_COUNT * 4)); FTN_TRY(b_err.alloc(4));
+    const size_t ws_bytes = 10 * (P * sizeof(float4) + 256) + 2 * (P * 4 + 256) + P * sizeof(float2) + 256 +
+                            (size_t)fw * fh * sizeof(float4) + 256 + (size_t)(Q_COUNT + 1) * (P * 4 + 256) + 4096;
+    Carver cv; 
+    FTN_TRY(workspace_reserve(s, ws_bytes, &cv.p));
     PathArrays pa;
-    pa.ray_o = b_f4[0].as<float4>(); pa.ray_d = b_f4[1].as<float4>(); pa.beta = b_f4[2].as<float4>(); pa.L = b_f4[3].as<float4>();
-    pa.sh_o = b_f4[4].as<float4>(); pa.sh_d = b_f4[5].as<float4>(); pa.sh_L = b_f4[6].as<float4>();
-    pa.mis_o = b_f4[7].as<float4>(); pa.mis_d = b_f4[8].as<float4>(); pa.mis_w = b_f4[9].as<float4>();
-    pa.hit = b_hit.as<uint32_t>(); pa.state = b_state.as<uint32_t>(); pa.p_film = b_pfilm.as<float2>();
-    float4* accum = b_accum.as<float4>();
-    uint32_t* counts = b_counts.as<uint32_t>();
-    uint32_t* d_err = b_err.as<uint32_t>();
-    uint32_t* qmem = b_queues.as<uint32_t>();
-    uint32_t* active_in = qmem + (size_t)Q_COUNT * P;   // ping-pong partner of Q_ACTIVE_OUT
+    pa.ray_o = cv.take<float4>(P); pa.ray_d = cv.take<float4>(P); pa.beta = cv.take<float4>(P); pa.L = cv.take<float4>(P);
+    pa.sh_o = cv.take<float4>(P); pa.sh_d = cv.take<float4>(P); pa.sh_L = cv.take<float4>(P);
+    pa.mis_o = cv.take<float4>(P); pa.mis_d = cv.take<float4>(P); pa.mis_w = cv.take<float4>(P);
+    pa.hit = cv.take<uint32_t>(P); pa.state = cv.take<uint32_t>(P); pa.p_film = cv.take<float2>(P);
+    float4* accum = cv.take<float4>((size_t)fw * fh);
     Queues qs;
-    for (int q = 0; q < Q_COUNT; ++q) qs.q[q] = qmem + (size_t)q * P;
+    for (int q = 0; q < Q_COUNT; ++q) qs.q[q] = cv.take<uint32_t>(P);
+    uint32_t* active_in = cv.take<uint32_t>(P);   // ping-pong partner of Q_ACTIVE_OUT
+    uint32_t* counts = cv.take<uint32_t>(CTR_COUNT);
+    uint32_t* d_err = cv.take<uint32_t>(1);
+    unsigned long long* d_trav = cv.take<unsigned long long>(6);   // [class][nodes, tris]
     FTN_CUDA(cudaMemsetAsync(accum, 0, (size_t)fw * fh * sizeof(float4), st));
     FTN_CUDA(cudaMemsetAsync(d_err, 0, 4, st));
+    FTN_CUDA(cudaMemsetAsync(d_trav, 0, 6 * sizeof(unsigned long long), st));
 
     const SceneView sc = s->view();
-    bool has_area = false, mat_present[3] = {false, false, false};
+    bool has_area = false;
     for (const LightData& l : s->h_lights) if (l.type == 1) has_area = true;
-    {   // which material classes exist decides which shade kernels are launched at all
-        std::vector<MaterialData> mats(s->n_materials);
-        if (s->n_materials) FTN_CUDA(cudaMemcpy(mats.data(), s->d_materials, mats.size() * sizeof(MaterialData), cudaMemcpyDeviceToHost));
-        for (const MaterialData& m : mats) mat_present[m.type] = true;
-    }
-    bool has_null = false;   // any primitive without a material (null BSDF, path.rs:76-80)
-    {
-        std::vector<MeshData> meshes(s->n_meshes);
-        if (s->n_meshes) FTN_CUDA(cudaMemcpy(meshes.data(), s->d_meshes, meshes.size() * sizeof(MeshData), cudaMemcpyDeviceToHost));
-        for (const MeshData& m : meshes) if (m.material < 0) has_null = true;
-        for (const SphereData& sd : s->h_spheres) if (sd.material < 0) has_null = true;
-    }
-    uint64_t rays_closest = 0, rays_any = 0, camera_samples = 0;
+    uint64_t camera_samples = 0;
+    uint64_t class_rays[3] = {0, 0, 0};
     const unsigned shade_grid = (unsigned)(sm_count() * 8);
     const int reach = (int)std::ceil(std::max(fg.radius[0], fg.radius[1]) + 0.5f);
+    TraceTimer timer; timer.st = st;
 
     PassParams pp; std::memset(&pp, 0, sizeof(pp));
     pp.film = fg; pp.cam = *cam; pp.seed_key = sampler_seed_key(smp->seed);
@@ -361,29 +390,44 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
         for (int it = 0; it < iter_cap && n_active > 0; ++it) {
             FTN_CUDA(cudaMemsetAsync(counts, 0, CTR_COUNT * 4, st));
             Queues q = qs; q.q[Q_ACTIVE_OUT] = q_out;
-            k_extend<<<trace_grid(n_active, FTN_TRACE_BLOCKS_PER_SM), FTN_TRACE_THREADS, 0, st>>>(sc, pa, q_in, n_active, q, counts);
+            const unsigned ge = trace_grid(n_active, FTN_TRACE_BLOCKS_PER_SM);
+            timer.begin(0);
+            if (count_traversal) k_extend<true><<<ge, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q_in, n_active, q, counts, d_trav);
+            else k_extend<false><<<ge, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q_in, n_active, q, counts, d_trav);
+            timer.end();
             FTN_LAUNCHED();
-            rays_closest += n_active;
+            class_rays[0] += n_active;
             k_shade_miss<<<shade_grid, 256, 0, st>>>(sc, pp, pa, q.q[Q_MISS], counts);
             FTN_LAUNCHED();
-            if (has_null) { k_shade<Q_NULL><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_NULL], q, counts, d_err); FTN_LAUNCHED(); }
-            if (mat_present[0]) { k_shade<Q_MAT0><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT0], q, counts, d_err); FTN_LAUNCHED(); }
-            if (mat_present[1]) { k_shade<Q_MAT1><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT1], q, counts, d_err); FTN_LAUNCHED(); }
-            if (mat_present[2]) { k_shade<Q_MAT2><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT2], q, counts, d_err); FTN_LAUNCHED(); }
+            if (s->has_null_material) { k_shade<Q_NULL><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_NULL], q, counts, d_err); FTN_LAUNCHED(); }
+            if (s->material_present[0]) { k_shade<Q_MAT0><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT0], q, counts, d_err); FTN_LAUNCHED(); }
+            if (s->material_present[1]) { k_shade<Q_MAT1><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT1], q, counts, d_err); FTN_LAUNCHED(); }
+            if (s->material_present[2]) { k_shade<Q_MAT2><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT2], q, counts, d_err); FTN_LAUNCHED(); }
             uint32_t hc[CTR_COUNT];
             FTN_CUDA(cudaMemcpyAsync(hc, counts, sizeof(hc), cudaMemcpyDeviceToHost, st));
             FTN_CUDA(cudaStreamSynchronize(st));
             if (hc[Q_SHADOW]) {
-                k_shadow<<<trace_grid(hc[Q_SHADOW], FTN_TRACE_BLOCKS_PER_SM), FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_SHADOW], counts);
+                const unsigned g = trace_grid(hc[Q_SHADOW], FTN_TRACE_BLOCKS_PER_SM);
+                timer.begin(1);
+                if (count_traversal) k_shadow<true><<<g, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_SHADOW], counts, d_trav + 2);
+                else k_shadow<false><<<g, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_SHADOW], counts, d_trav + 2);
+                timer.end();
                 FTN_LAUNCHED();
-                rays_any += hc[Q_SHADOW];
+                class_rays[1] += hc[Q_SHADOW];
             }
             if (hc[Q_MIS]) {
                 const unsigned g = trace_grid(hc[Q_MIS], FTN_TRACE_BLOCKS_PER_SM);
-                if (has_area) k_mis<false><<<g, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts);
-                else k_mis<true><<<g, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts);
+                timer.begin(2);
+                if (has_area) {
+                    if (count_traversal) k_mis<false, true><<<g, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts, d_trav + 4);
+                    else k_mis<false, false><<<g, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts, d_trav + 4);
+                } else {
+                    if (count_traversal) k_mis<true, true><<<g, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts, d_trav + 4);
+                    else k_mis<true, false><<<g, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts, d_trav + 4);
+                }
+                timer.end();
                 FTN_LAUNCHED();
-                rays_closest += hc[Q_MIS];
+                class_rays[2] += hc[Q_MIS];
             }
             n_active = hc[Q_ACTIVE_OUT];
             q_in = q_out;
@@ -395,7 +439,9 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
     k_film_resolve<<<(fw * fh + 255) / 256, 256, 0, st>>>(accum, d_pixels, fw * fh);
     FTN_LAUNCHED();
     uint32_t h_err = 0;
+    unsigned long long h_trav[6] = {0, 0, 0, 0, 0, 0};
     FTN_CUDA(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, st));
+    FTN_CUDA(cudaMemcpyAsync(h_trav, d_trav, sizeof(h_trav), cudaMemcpyDeviceToHost, st));
     FTN_CUDA(cudaEventRecord(ev1, st));
     FTN_CUDA(cudaEventSynchronize(ev1));
     float ms = 0.0f;
@@ -403,9 +449,13 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
     cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));
-        stats->camera_samples = camera_samples; stats->rays_closest = rays_closest; stats->rays_any = rays_any;
+        stats->camera_samples = camera_samples;
+        stats->rays_closest = class_rays[0] + class_rays[2]; stats->rays_any = class_rays[1];   // Scene::intersect / intersect_test calls
         stats->device_seconds = ms * 1e-3; stats->bvh_build_seconds = s->build_seconds;
         stats->bvh_nodes = s->n_nodes; stats->bvh_node_bytes = 64; stats->bvh_tri_bytes = 48;
+        timer.collect(stats->trace_seconds, stats->trace_launches);
+        for (int c = 0; c < 3; ++c) { stats->trace_rays[c] = class_rays[c]; stats->trace_nodes[c] = h_trav[2 * c]; stats->trace_tris[c] = h_trav[2 * c + 1]; }
+        stats->node_visits = h_trav[0] + h_trav[2] + h_trav[4]; stats->tri_tests = h_trav[1] + h_trav[3] + h_trav[5];
     }
     if (h_err & ERR_NAN) return set_error(FTN_ERR_NAN_RADIANCE, "NaN radiance value (check_radiance, integrator/mod.rs:285)");
     if (h_err & ERR_UNSUPPORTED) return set_error(FTN_ERR_UNSUPPORTED, "the reference hits unimplemented!() on this input (env map_pdf == 0 or a null BSDF under the direct-lighting integrator)");

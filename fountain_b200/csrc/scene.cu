@@ -256,7 +256,10 @@ int scene_create(const FtnSceneDesc* d, FtnScene** out) {
         if (fm.type == FTN_MATERIAL_PLASTIC) vr = ur;
         if (fm.remap_roughness) { ur = roughness_to_alpha_host(ur); vr = roughness_to_alpha_host(vr); }
         md.alpha_x = ur; md.alpha_y = vr;
+        s->material_present[fm.type] = true;
     }
+    for (uint32_t m = 0; m < d->n_meshes; ++m) if (d->meshes[m].material_id < 0 && d->meshes[m].n_tris) s->has_null_material = true;
+    for (uint32_t i = 0; i < d->n_spheres; ++i) if (d->spheres[i].material_id < 0) s->has_null_material = true;
     if ((rc = upload(&s->d_materials, mats.data(), mats.size())) != FTN_OK) return bail(rc);
     // explicit lights first, then area lights of emissive spheres in primitive order (scene/mod.rs:32-49)
     for (uint32_t l = 0; l < d->n_lights; ++l) {
@@ -308,7 +311,7 @@ int scene_destroy(FtnScene* s) {
     if (!s) return FTN_OK;
     cudaFree(s->d_pos); cudaFree(s->d_nrm); cudaFree(s->d_uv); cudaFree(s->d_idx);
     cudaFree(s->d_meshes); cudaFree(s->d_materials); cudaFree(s->d_spheres); cudaFree(s->d_lights);
-    cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_codes); cudaFree(s->d_order); cudaFree(s->d_work);
+    cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_codes); cudaFree(s->d_order); cudaFree(s->d_work); cudaFree(s->ws);
     for (void* p : s->owned) cudaFree(p);
     delete s;
     return FTN_OK;

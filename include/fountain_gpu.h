@@ -215,7 +215,13 @@ typedef struct FtnStats {
     uint32_t bvh_nodes;
     uint32_t bvh_node_bytes;
     uint32_t bvh_tri_bytes;
-    uint32_t reserved;
+    uint32_t reserved;       /* INPUT to ftn_render*: 1 = also count node visits / triangle tests (slower) */
+    /* per traversal-kernel class: 0 = extend (closest hit), 1 = shadow (any hit), 2 = MIS */
+    double   trace_seconds[3];   /* sum of CUDA-event durations of that class's launches */
+    uint64_t trace_launches[3];
+    uint64_t trace_rays[3];
+    uint64_t trace_nodes[3];     /* only with reserved == 1 */
+    uint64_t trace_tris[3];
 } FtnStats;
 
 typedef struct FtnScene FtnScene;

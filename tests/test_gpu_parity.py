@@ -1,0 +1,138 @@
+"""`-m gpu` tier: the CUDA library on a real B200, through the C ABI, against the CPU oracle on
+the same seeded inputs (SURVEY 8c tolerances).  Integer work (Morton codes, sorted order) is
+bit-exact; ray batches are bit-identical wherever the same primitive is found."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from fountain_b200 import _abi as A
+from fountain_b200 import api, scenes
+from fountain_b200.transform import Transform
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cubes(gpu_backend, orc_backend, rounded_cube_path):
+    return parity.cube_scenes(gpu_backend, orc_backend, rounded_cube_path)
+
+
+def test_library_exports_and_device(gpu_backend):
+    n = C.c_int(0)
+    assert gpu_backend.fn["device_count"](C.byref(n)) == 0 and n.value >= 1
+    assert gpu_backend.fn["abi_version"]() == A.FTN_ABI_VERSION
+
+
+def test_morton_and_order_bit_exact(cubes):
+    assert parity.check_morton(*cubes) == 4332
+
+
+def test_world_bound_matches(cubes):
+    (lo_a, hi_a), (lo_b, hi_b) = cubes[0].world_bound(), cubes[1].world_bound()
+    assert np.array_equal(lo_a, lo_b) and np.array_equal(hi_a, hi_b)
+
+
+def test_ray_batch_parity_cube(cubes):
+    st = parity.check_ray_batch(cubes[0], cubes[1], parity.random_ray_batch(200_000, 5), "cube")
+    assert st["hits"] > 50_000
+
+
+def test_watertight_cube(cubes):
+    """tests/tri_watertight.rs on the GPU aggregate: 0 misses in 100k directions, both queries."""
+    hits = parity.check_watertight(cubes[0], n=100_000)
+    ref = cubes[1].intersect(api.make_rays(np.zeros((100_000, 3)), parity.unit_sphere_dirs(100_000, 7)))
+    parity.compare_hits(hits, ref, "watertight")
+
+
+@pytest.mark.parametrize("n_lon,n_lat", [(96, 48), (400, 200)])
+def test_morton_sort_and_rays_displaced_sphere(gpu_backend, orc_backend, n_lon, n_lat):
+    """Exercises the multi-tile radix sort / scan (160k triangles) and deeper trees."""
+    v, t, n = scenes.displaced_sphere_mesh(n_lon, n_lat)
+    mesh = api.TriangleMesh(Transform.identity(), t, v, n)
+    a = api.Scene([api.GeometricPrimitive(mesh)], [], backend=gpu_backend)
+    b = api.Scene([api.GeometricPrimitive(mesh)], [], backend=orc_backend)
+    parity.check_morton(a, b)
+    parity.check_ray_batch(a, b, parity.random_ray_batch(100_000, 9, extent=10.0, far=40.0), "displaced sphere")
+
+
+@pytest.mark.parametrize("n_tris", [1, 2, 3, 4, 5, 7, 9, 33, 2049])
+def test_small_scenes(gpu_backend, orc_backend, n_tris):
+    rng = np.random.default_rng(n_tris)
+    v = rng.uniform(-1, 1, (3 * n_tris, 3)).astype(np.float32)
+    t = np.arange(3 * n_tris, dtype=np.uint32).reshape(-1, 3)
+    mesh = api.TriangleMesh(Transform.identity(), t, v)
+    a = api.Scene([api.GeometricPrimitive(mesh)], [], backend=gpu_backend)
+    b = api.Scene([api.GeometricPrimitive(mesh)], [], backend=orc_backend)
+    parity.check_morton(a, b)
+    rays = parity.random_ray_batch(5000, 100 + n_tris, extent=1.0, far=4.0)
+    parity.compare_hits(a.intersect(rays), b.intersect(rays), "small")
+    assert np.array_equal(a.intersect_test(rays), b.intersect_test(rays))
+
+
+def test_coincident_centroids(gpu_backend, orc_backend):
+    base = np.array([[-1, -1, 0], [1, -1, 0], [0, 2, 0]], dtype=np.float32)
+    v = np.concatenate([base] * 6).astype(np.float32)
+    t = np.arange(18, dtype=np.uint32).reshape(-1, 3)
+    mesh = api.TriangleMesh(Transform.identity(), t, v)
+    a = api.Scene([api.GeometricPrimitive(mesh)], [], backend=gpu_backend)
+    b = api.Scene([api.GeometricPrimitive(mesh)], [], backend=orc_backend)
+    parity.check_morton(a, b)
+    rays = api.make_rays([[0, 0, 5]] * 4, [[0, 0, -1], [0.1, 0.2, -1], [3, 0, -1], [0, 0, 1]])
+    ha, hb = a.intersect(rays), b.intersect(rays)
+    assert np.array_equal(ha["prim"] == A.FTN_NO_HIT, hb["prim"] == A.FTN_NO_HIT) and np.array_equal(ha["t"], hb["t"])
+
+
+def test_empty_scene_and_empty_batch(gpu_backend):
+    s = api.Scene([], [], backend=gpu_backend)
+    rays = parity.random_ray_batch(64, 1)
+    assert (s.intersect(rays)["prim"] == A.FTN_NO_HIT).all() and not s.intersect_test(rays).any()
+    assert len(s.intersect(rays[:0])) == 0
+
+
+def test_spheres_bvh_test_of_the_reference(gpu_backend, orc_backend):
+    """src/bvh.rs:401-444 (100 random spheres, rays from the origin) on the GPU aggregate."""
+    def build(backend):
+        rng = np.random.default_rng(3)
+        prims = [api.GeometricPrimitive(api.Sphere(Transform.translate(rng.uniform(-10, 10, 3).astype(np.float32)),
+                                                   radius=float(rng.uniform(0.5, 3.0)))) for _ in range(100)]
+        return api.Scene(prims, [], backend=backend)
+    a, b = build(gpu_backend), build(orc_backend)
+    rays = api.make_rays(np.zeros((500, 3)), parity.unit_sphere_dirs(500, 33))
+    ha, hb = a.intersect(rays), b.intersect(rays)
+    assert np.array_equal(ha["prim"], hb["prim"]) and np.array_equal(ha["t"], hb["t"])
+    assert np.array_equal(a.intersect_test(rays), ha["prim"] != A.FTN_NO_HIT)
+
+
+def test_error_paths(gpu_backend):
+    s = api.Scene([], [], backend=gpu_backend, build=False)
+    with pytest.raises(api.FountainError) as e:
+        s.intersect(parity.random_ray_batch(4, 1))
+    assert e.value.code == A.FTN_ERR_INVALID_ARGUMENT
+    with pytest.raises(api.FountainError):
+        api.Film((0, 10), backend=gpu_backend)
+
+
+def test_million_triangle_properties(gpu_backend):
+    """BASELINE config C3 at full size (1M triangles): size-independent properties -- the sorted
+    order is a permutation with non-decreasing codes, a closed surface is hit from inside by every
+    ray, any-hit == (closest hit exists), and t equals the analytic sphere distance within the
+    displacement amplitude."""
+    scene, camera = scenes.synthetic_mesh_scene(1000, 500, backend=gpu_backend)
+    assert scene.n_triangles == 1_000_000
+    codes, order = scene.morton_codes_and_order()
+    assert np.array_equal(np.sort(order), np.arange(scene.n_triangles, dtype=np.uint32))
+    sc = codes[order]
+    assert np.all(sc[1:] >= sc[:-1])
+    same = sc[1:] == sc[:-1]
+    assert np.all(order[1:][same] > order[:-1][same])            # stable: ties by index
+    dirs = parity.unit_sphere_dirs(400_000, 11)
+    rays = api.make_rays(np.zeros((400_000, 3)), dirs)
+    hits = scene.intersect(rays)
+    assert (hits["prim"] != A.FTN_NO_HIT).all()
+    assert scene.intersect_test(rays).all()
+    assert np.all(np.abs(hits["t"] - 10.0) < 0.6)
+    outside = api.make_rays(dirs * 40.0, -dirs)
+    h2 = scene.intersect(outside)
+    assert (h2["prim"] != A.FTN_NO_HIT).all() and np.all(np.abs(h2["t"] - 30.0) < 0.6)
