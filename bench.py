@@ -273,15 +273,16 @@ def run_ours_render(args):
                         % ((cst.bvh_nodes * node_b + scene.n_triangles * tri_b) / 1e6)}
 
     # ---- e2e: host buffers in, host film out; scene upload + BVH build + render + read-back per step ----
-    e2e_rays = 0
-    e2e_secs = 0.0
+    e2e_samples = []          # (seconds, rays) per e2e step; the median step is reported
     h2d = d2h = 0
-    for i in range(max(1, min(args.steps, 3))):
+    n_e2e = 0 if args.no_e2e else max(3, min(args.steps, 5))
+    for i in range(n_e2e):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         sc2, cam2, film2, integ2, _, _ = workload_scene(name, gpu, args)          # PLY arrays -> ftn_scene_create (H2D) + ftn_bvh_build
+        t_build = time.perf_counter() - t0
         if world == 1:
             st2 = api.SamplerIntegrator(cam2, integ2).render_parallel(sc2, film2, sampler)   # ftn_render: film D2H inside
             r = st2["rays_closest"] + st2["rays_any"]
@@ -297,6 +298,8 @@ def run_ours_render(args):
             d2h = (host_film.numel() * 4) if rank == 0 else 0
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        if rank == 0:
+            print("e2e step %d: scene+build %.2f ms, total %.2f ms" % (i, t_build * 1e3, dt * 1e3), file=sys.stderr)
         h2d = sc2.upload_bytes
         sc2.close()
         if world > 1:
@@ -304,10 +307,12 @@ def run_ours_render(args):
             mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
             sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
             dt, r = float(mx[0].item()), int(sm[1].item())
-        e2e_secs += dt; e2e_rays += r
-    e2e = {"value": e2e_rays / e2e_secs / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "ms_per_step": e2e_secs / max(1, min(args.steps, 3)) * 1e3,
-           "includes": "ftn_scene_create (mesh H2D) + ftn_bvh_build + ftn_render + film D2H"}
+        e2e_samples.append((dt, r))
+    e2e_med = sorted(e2e_samples)[len(e2e_samples) // 2] if e2e_samples else None
+    e2e = None if n_e2e == 0 else {
+        "value": e2e_med[1] / e2e_med[0] / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+        "ms_per_step": e2e_med[0] * 1e3, "ms_all_steps": [round(x[0] * 1e3, 3) for x in e2e_samples],
+        "includes": "ftn_scene_create (host mesh arrays -> H2D) + ftn_bvh_build + ftn_render + film D2H; PLY text parsing excluded (stays on the host side of the ABI)"}
 
     if rank == 0:
         base = cpu_baseline(name, args) if (world == 1 and not args.no_cpu_baseline) else None
@@ -344,11 +349,18 @@ def run_ours_raybatch(args):
     inc = scenes.diffuse_bounce_batch(prim, hits, scene._positions, scene._indices, seed=2)
     reps = int(np.ceil((4 << 20) / max(1, len(inc))))
     inc = np.concatenate([inc] * reps)[: 4 << 20] if len(inc) < (4 << 20) else inc
+    # batch C (harder than the spec's batch B, whose rays mostly leave the convex mesh): uniformly random
+    # origins INSIDE the closed mesh with uniformly random directions -- every ray hits, none is coherent
+    rng = np.random.default_rng(4)
+    n_int = 4 << 20
+    o = rng.normal(size=(n_int, 3)); o *= (rng.random((n_int, 1)) ** (1 / 3) * 9.0) / np.linalg.norm(o, axis=1, keepdims=True)
+    d = rng.normal(size=(n_int, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    interior = api.make_rays(o.astype(np.float32), d.astype(np.float32))
     stream = torch.cuda.current_stream()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     results = {}
     peak, peak_src = measured_peak()
-    for label, batch in (("coherent_primary", prim), ("incoherent_diffuse", inc)):
+    for label, batch in (("coherent_primary", prim), ("incoherent_diffuse", inc), ("incoherent_interior", interior)):
         n = len(batch)
         d_rays = torch.from_numpy(batch.view(np.float32).reshape(n, 8)).to(dev)
         d_hits = torch.empty((n, 4), dtype=torch.float32, device=dev)
@@ -406,6 +418,7 @@ def main():
     ap.add_argument("--tris", type=int, default=1_000_000)
     ap.add_argument("--detail", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -114,8 +114,8 @@ class TriangleMesh:
     @staticmethod
     def from_ply(path, object_to_world=None, reverse_orientation=False):
         """make_triangle_mesh_from_ply, loaders/constructors.rs:94-190."""
-        from .ply import load_ply
-        d = load_ply(path)
+        from .ply import load_ply_cached
+        d = load_ply_cached(path)
         return TriangleMesh(object_to_world or Transform.identity(), d["indices"], d["vertices"],
                             d["normals"], d["uvs"], reverse_orientation)
 

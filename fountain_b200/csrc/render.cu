@@ -17,6 +17,7 @@
 // the lanes by destination queue, one atomicAdd per group, __shfl_sync broadcasts the base).
 #include "ftn_scene.h"
 #include "ftn_path.cuh"
+#include "ftn_trace_persistent.cuh"
 #include <algorithm>
 #include <cstring>
 #include <cmath>
@@ -96,25 +97,20 @@ k_raygen(PassParams pp, PathArrays pa) {
 
 // ---- extend: closest hit + binning by material class ----------------------------------------------------------
 // queue_in == nullptr: the identity queue (first bounce of a pass)
-template <bool COUNT>
-__global__ void __launch_bounds__(FTN_TRACE_THREADS)
-k_extend(SceneView sc, PathArrays pa, const uint32_t* __restrict__ queue_in, uint32_t n_in, Queues qs, uint32_t* __restrict__ counts,
-         unsigned long long* __restrict__ trav) {
-    const int lane = threadIdx.x & 31;
-    TraceCounters tc; tc.nodes = 0; tc.tris = 0;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&counts[W_EXTEND], 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n_in) break;
-        const uint32_t k = base + lane;
-        int target = -1;
-        uint32_t path = 0;
-        if (k < n_in) {
-            path = queue_in ? queue_in[k] : k;
-            const RayF ray = load_ray(pa, path);
-            SceneHit h;
-            scene_intersect<false, COUNT>(sc, ray, &h, &tc);
+struct PathRaySource {
+    PathArrays pa; const uint32_t* queue;
+    __device__ __forceinline__ bool load(uint32_t k, RayF* ray) const {
+        const uint32_t path = queue ? queue[k] : k;
+        *ray = load_ray(pa, path);
+        return true;
+    }
+};
+struct ExtendSink {
+    SceneView sc; PathArrays pa; const uint32_t* queue; Queues qs; uint32_t* counts;
+    __device__ __forceinline__ void store(bool valid, uint32_t k, const RayF&, const SceneHit& h) const {
+        int target = -1; uint32_t path = 0;
+        if (valid) {
+            path = queue ? queue[k] : k;
             pa.hit[path] = h.slot;
             if (h.slot == FTN_NO_HIT_SLOT) target = Q_MISS;
             else {
@@ -122,8 +118,17 @@ k_extend(SceneView sc, PathArrays pa, const uint32_t* __restrict__ queue_in, uin
                 target = (material < 0) ? Q_NULL : (Q_MAT0 + sc.materials[material].type);
             }
         }
-        queue_push(qs.q, counts, target, path);
+        queue_push(qs.q, counts, target, path);   // all 32 lanes arrive here together
     }
+};
+template <bool COUNT>
+__global__ void __launch_bounds__(FTN_TRACE_THREADS)
+k_extend(SceneView sc, PathArrays pa, const uint32_t* __restrict__ queue_in, uint32_t n_in, Queues qs, uint32_t* __restrict__ counts,
+         unsigned long long* __restrict__ trav) {
+    PathRaySource src; src.pa = pa; src.queue = queue_in;
+    ExtendSink sink; sink.sc = sc; sink.pa = pa; sink.queue = queue_in; sink.qs = qs; sink.counts = counts;
+    TraceCounters tc; tc.nodes = 0; tc.tris = 0;
+    trace_persistent<false, COUNT>(sc, n_in, &counts[W_EXTEND], src, sink, tc);
     if (COUNT) flush_trace_counters(tc, trav);
 }
 
@@ -176,57 +181,61 @@ k_shade(SceneView sc, PassParams pp, PathArrays pa, const uint32_t* __restrict__
 }
 
 // ---- shadow rays: VisibilityTester::unoccluded (light/mod.rs:82-84) ---------------------------------------------
+struct ShadowSource {
+    PathArrays pa; const uint32_t* queue;
+    __device__ __forceinline__ bool load(uint32_t k, RayF* ray) const {
+        const uint32_t path = queue[k];
+        ray->o = ld3(pa.sh_o, path); ray->d = ld3(pa.sh_d, path);
+        ray->t_max = rn_sub(1.0f, 0.0001f);   // 1 - SHADOW_EPSILON, interaction.rs:10,55
+        ray->time = pa.ray_o[path].w;
+        return true;
+    }
+};
+struct ShadowSink {
+    PathArrays pa; const uint32_t* queue;
+    __device__ __forceinline__ void store(bool valid, uint32_t k, const RayF&, const SceneHit& h) const {
+        if (!valid || h.slot != FTN_NO_HIT_SLOT) return;
+        const uint32_t path = queue[k];
+        st3(pa.L, path, ld3(pa.L, path) + ld3(pa.sh_L, path));
+    }
+};
 template <bool COUNT>
 __global__ void __launch_bounds__(FTN_TRACE_THREADS)
 k_shadow(SceneView sc, PathArrays pa, const uint32_t* __restrict__ queue, uint32_t* __restrict__ counts, unsigned long long* __restrict__ trav) {
-    const uint32_t n = counts[Q_SHADOW];
-    const int lane = threadIdx.x & 31;
+    ShadowSource src; src.pa = pa; src.queue = queue;
+    ShadowSink sink; sink.pa = pa; sink.queue = queue;
     TraceCounters tc; tc.nodes = 0; tc.tris = 0;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&counts[W_SHADOW], 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const uint32_t k = base + lane;
-        if (k < n) {
-            const uint32_t path = queue[k];
-            RayF ray; ray.o = ld3(pa.sh_o, path); ray.d = ld3(pa.sh_d, path);
-            ray.t_max = rn_sub(1.0f, 0.0001f);   // 1 - SHADOW_EPSILON, interaction.rs:10,55
-            ray.time = pa.ray_o[path].w;
-            SceneHit h;
-            scene_intersect<true, COUNT>(sc, ray, &h, &tc);
-            if (h.slot == FTN_NO_HIT_SLOT) st3(pa.L, path, ld3(pa.L, path) + ld3(pa.sh_L, path));
-        }
-    }
+    trace_persistent<true, COUNT>(sc, counts[Q_SHADOW], &counts[W_SHADOW], src, sink, tc);
     if (COUNT) flush_trace_counters(tc, trav);
 }
 
 // ---- MIS (BSDF-sampled) rays: integrator/mod.rs:364-389 ---------------------------------------------------------------
+struct MisSource {
+    PathArrays pa; const uint32_t* queue;
+    __device__ __forceinline__ bool load(uint32_t k, RayF* ray) const {
+        const uint32_t path = queue[k];
+        ray->o = ld3(pa.mis_o, path); ray->d = ld3(pa.mis_d, path); ray->t_max = FTN_INF; ray->time = pa.ray_o[path].w;
+        return true;
+    }
+};
+struct MisSink {
+    SceneView sc; PathArrays pa; const uint32_t* queue;
+    __device__ __forceinline__ void store(bool valid, uint32_t k, const RayF& ray, const SceneHit& h) const {
+        if (!valid) return;
+        const uint32_t path = queue[k];
+        const float4 w4 = pa.mis_w[path];
+        const V3 incident = mis_incident(sc, sc.lights[f2u(w4.w)], ray, h.slot);
+        if (!is_black(incident)) st3(pa.L, path, ld3(pa.L, path) + V3(w4.x, w4.y, w4.z) * incident);
+    }
+};
+// ENV_ONLY: with only infinite lights a hit contributes nothing whatever it is, so any-hit suffices
 template <bool ENV_ONLY, bool COUNT>
 __global__ void __launch_bounds__(FTN_TRACE_THREADS)
 k_mis(SceneView sc, PathArrays pa, const uint32_t* __restrict__ queue, uint32_t* __restrict__ counts, unsigned long long* __restrict__ trav) {
-    const uint32_t n = counts[Q_MIS];
-    const int lane = threadIdx.x & 31;
+    MisSource src; src.pa = pa; src.queue = queue;
+    MisSink sink; sink.sc = sc; sink.pa = pa; sink.queue = queue;
     TraceCounters tc; tc.nodes = 0; tc.tris = 0;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&counts[W_MIS], 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const uint32_t k = base + lane;
-        if (k < n) {
-            const uint32_t path = queue[k];
-            const float4 w4 = pa.mis_w[path];
-            const LightData& light = sc.lights[f2u(w4.w)];
-            RayF ray; ray.o = ld3(pa.mis_o, path); ray.d = ld3(pa.mis_d, path); ray.t_max = FTN_INF; ray.time = pa.ray_o[path].w;
-            SceneHit h;
-            // with only infinite lights a hit contributes nothing whatever it is, so any-hit suffices
-            if (ENV_ONLY) scene_intersect<true, COUNT>(sc, ray, &h, &tc);
-            else scene_intersect<false, COUNT>(sc, ray, &h, &tc);
-            const V3 incident = mis_incident(sc, light, ray, h.slot);
-            if (!is_black(incident)) st3(pa.L, path, ld3(pa.L, path) + V3(w4.x, w4.y, w4.z) * incident);
-        }
-    }
+    trace_persistent<ENV_ONLY, COUNT>(sc, counts[Q_MIS], &counts[W_MIS], src, sink, tc);
     if (COUNT) flush_trace_counters(tc, trav);
 }
 

@@ -216,7 +216,7 @@ int scene_create(const FtnSceneDesc* d, FtnScene** out) {
     if (!d || !out) return set_error(FTN_ERR_INVALID_ARGUMENT, "null argument");
     if (d->abi_version != FTN_ABI_VERSION) return set_error(FTN_ERR_INVALID_ARGUMENT, "abi version mismatch");
     if (d->n_triangles && (!d->positions || !d->indices || !d->meshes)) return set_error(FTN_ERR_INVALID_ARGUMENT, "triangles without positions/indices/meshes");
-    if (d->n_triangles >= (1u << 30)) return set_error(FTN_ERR_INVALID_ARGUMENT, "too many triangles (leaf refs hold 30 bits)");
+    if (d->n_triangles >= (1u << 29)) return set_error(FTN_ERR_INVALID_ARGUMENT, "too many triangles (leaf refs hold 29 bits)");
     uint32_t covered = 0;
     for (uint32_t m = 0; m < d->n_meshes; ++m) {
         if (d->meshes[m].first_tri != covered) return set_error(FTN_ERR_INVALID_ARGUMENT, "meshes must tile the index buffer in order");

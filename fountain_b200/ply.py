@@ -2,6 +2,8 @@
 crate the reference's loader uses (src/loaders/constructors.rs:94-190): x,y,z [,nx,ny,nz]
 [,u,v] per vertex and `vertex_indices` faces with exactly three indices.  Host-side only.
 """
+import os
+
 import numpy as np
 
 _PLY_TYPES = {"char": "i1", "uchar": "u1", "short": "i2", "ushort": "u2", "int": "i4", "uint": "u4",
@@ -74,3 +76,14 @@ def load_ply(path):
     if all(k in v for k in ("u", "v")):
         res["uvs"] = np.stack([v["u"], v["v"]], axis=1).astype(np.float32)
     return res
+
+
+_CACHE = {}
+
+
+def load_ply_cached(path):
+    """Parse once per process (the arrays are treated as read-only by the callers)."""
+    key = (os.path.abspath(path), os.path.getmtime(path))
+    if key not in _CACHE:
+        _CACHE[key] = load_ply(path)
+    return _CACHE[key]
