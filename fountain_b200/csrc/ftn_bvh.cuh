@@ -51,26 +51,23 @@ FTN_HD RaySlab make_ray_slab(V3 o, V3 d) {
     return s;
 }
 // bounds.rs:214-233 for one box given as (lo,hi) per axis; returns hit and the entry distance.
+// Branch-free: the reference returns early as soon as t0 > t1; t0 only grows and t1 only shrinks
+// (f32::max/min ignore NaNs, like fmaxf/fminf), so testing once at the end accepts exactly the
+// same boxes without divergent branches inside the warp.
 FTN_HD bool slab_test(const RaySlab& r, float lox, float hix, float loy, float hiy, float loz, float hiz,
                       float t_max, float* t_entry) {
-    float t0 = 0.0f, t1 = t_max;
-    float tn = rn_mul(rn_sub(lox, r.o.x), r.inv_d.x), tf = rn_mul(rn_sub(hix, r.o.x), r.inv_d.x);
-    if (tn > tf) { float s = tn; tn = tf; tf = s; }
-    tf = rn_mul(tf, r.widen);
-    t0 = fmaxf(t0, tn); t1 = fminf(t1, tf);
-    if (t0 > t1) return false;
-    tn = rn_mul(rn_sub(loy, r.o.y), r.inv_d.y); tf = rn_mul(rn_sub(hiy, r.o.y), r.inv_d.y);
-    if (tn > tf) { float s = tn; tn = tf; tf = s; }
-    tf = rn_mul(tf, r.widen);
-    t0 = fmaxf(t0, tn); t1 = fminf(t1, tf);
-    if (t0 > t1) return false;
-    tn = rn_mul(rn_sub(loz, r.o.z), r.inv_d.z); tf = rn_mul(rn_sub(hiz, r.o.z), r.inv_d.z);
-    if (tn > tf) { float s = tn; tn = tf; tf = s; }
-    tf = rn_mul(tf, r.widen);
-    t0 = fmaxf(t0, tn); t1 = fminf(t1, tf);
-    if (t0 > t1) return false;
+    const float ax = rn_mul(rn_sub(lox, r.o.x), r.inv_d.x), bx = rn_mul(rn_sub(hix, r.o.x), r.inv_d.x);
+    const float ay = rn_mul(rn_sub(loy, r.o.y), r.inv_d.y), by = rn_mul(rn_sub(hiy, r.o.y), r.inv_d.y);
+    const float az = rn_mul(rn_sub(loz, r.o.z), r.inv_d.z), bz = rn_mul(rn_sub(hiz, r.o.z), r.inv_d.z);
+    // `if t_near > t_far { swap }`: near = (a > b) ? b : a, far = (a > b) ? a : b  (NaN: no swap)
+    const bool sx = ax > bx, sy = ay > by, sz = az > bz;
+    const float nx = sx ? bx : ax, fx = rn_mul(sx ? ax : bx, r.widen);
+    const float ny = sy ? by : ay, fy = rn_mul(sy ? ay : by, r.widen);
+    const float nz = sz ? bz : az, fz = rn_mul(sz ? az : bz, r.widen);
+    const float t0 = fmaxf(fmaxf(fmaxf(0.0f, nx), ny), nz);
+    const float t1 = fminf(fminf(fminf(t_max, fx), fy), fz);
     *t_entry = t0;
-    return true;
+    return !(t0 > t1);
 }
 
 struct TraceCounters { uint32_t nodes, tris; };

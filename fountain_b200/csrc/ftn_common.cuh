@@ -57,10 +57,11 @@ FTN_HD float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
 // err_float.rs:5-10 gamma(n) evaluated in f32; constants checked in tests against the oracle.
 #define FTN_MACHINE_EPS 5.9604644775390625e-08f   /* f32::EPSILON * 0.5 = 2^-24 */
-FTN_HD float gamma_n(int n) {
-    float nf = (float)n;
-    return rn_div(rn_mul(nf, FTN_MACHINE_EPS), rn_sub(1.0f, rn_mul(nf, FTN_MACHINE_EPS)));
-}
+// constexpr: folded at compile time in IEEE f32 (each op rounds once; no a*b+c shape to contract),
+// so no division is executed per ray / per triangle.
+constexpr float gamma_c(int n) { return ((float)n * FTN_MACHINE_EPS) / (1.0f - (float)n * FTN_MACHINE_EPS); }
+template <int N> struct GammaK { static constexpr float value = gamma_c(N); };
+#define gamma_n(n) (ftn::GammaK<(n)>::value)
 
 FTN_HD bool sign_positive(float f) { return (f2u(f) >> 31) == 0u; }   // f32::is_sign_positive
 

@@ -11,6 +11,14 @@ FTN_HD bool sign_differs(float a, float b, float c) {
     return sign_positive(a) != sign_positive(b) || sign_positive(b) != sign_positive(c);
 }
 
+// (kx,ky,kz) is always a cyclic rotation of (0,1,2) (kx = kz+1, ky = kx+1 mod 3), so the
+// permutation is two selects per component instead of indexed (branchy) component access.
+FTN_HD V3 permute(V3 p, int kx, int ky, int kz) {
+    (void)kx; (void)ky;
+    const bool r0 = kz == 2, r1 = kz == 0;   // kz==2: (x,y,z); kz==0: (y,z,x); kz==1: (z,x,y)
+    return V3(r0 ? p.x : (r1 ? p.y : p.z), r0 ? p.y : (r1 ? p.z : p.x), r0 ? p.z : (r1 ? p.x : p.y));
+}
+
 // Per-ray constants of the watertight test (triangle.rs:191-205: the "TODO: cache shear
 // coefficients in ray" the reference leaves open).  Same values, computed once per ray.
 struct RayShear {
@@ -22,7 +30,8 @@ FTN_HD RayShear make_ray_shear(V3 d) {
     s.kz = max_dimension(x_abs(d));
     s.kx = (s.kz + 1) % 3;
     s.ky = (s.kx + 1) % 3;
-    float dx = d[s.kx], dy = d[s.ky], dz = d[s.kz];
+    const V3 dp = permute(d, s.kx, s.ky, s.kz);
+    float dx = dp.x, dy = dp.y, dz = dp.z;
     s.sx = rn_div(-dx, dz);
     s.sy = rn_div(-dy, dz);
     s.sz = rn_div(1.0f, dz);
@@ -30,8 +39,6 @@ FTN_HD RayShear make_ray_shear(V3 d) {
 }
 
 struct TriHit { float t, b0, b1, b2; };
-
-FTN_HD V3 permute(V3 p, int kx, int ky, int kz) { return V3(p[kx], p[ky], p[kz]); }
 
 // triangle.rs:176-268.  `t_max` is the ray's current t_max (shrinks during closest-hit search).
 FTN_HD bool triangle_intersect(V3 p0, V3 p1, V3 p2, V3 ro, const RayShear& rs, float t_max, TriHit* out) {

@@ -76,6 +76,7 @@ struct SceneView {
     const SphereData* spheres; uint32_t n_spheres;
     const LightData* lights; uint32_t n_lights;
     uint32_t n_tris;
+    int refill_threshold;    // persistent traversal: leave the traverse loop when fewer lanes are active
 };
 
 }  // namespace ftn

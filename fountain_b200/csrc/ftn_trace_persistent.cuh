@@ -29,7 +29,8 @@ namespace ftn {
 // Sink:    __device__ void store(bool valid, uint32_t item, const RayF& ray, const SceneHit& hit)
 //          called by ALL 32 lanes together (valid = this lane has a finished ray), so it may use
 //          warp collectives (queue_push).
-template <bool ANY, bool COUNT, class Source, class Sink>
+// SPHERES = false compiles the EFloat sphere side list out of the kernel (scenes without spheres).
+template <bool ANY, bool COUNT, bool SPHERES, class Source, class Sink>
 __device__ __forceinline__ void trace_persistent(const SceneView& sc, uint32_t n_items, uint32_t* work_counter,
                                                  Source& src, Sink& sink, TraceCounters& tc) {
     const int lane = threadIdx.x & 31;
@@ -43,7 +44,7 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sc, uint32_t n
     SceneHit hit; hit.slot = FTN_NO_HIT_SLOT; hit.t = 0.0f; hit.tri.t = hit.tri.b0 = hit.tri.b1 = hit.tri.b2 = 0.0f;
     float t_max = 0.0f;
     int stack[FTN_STACK_SIZE];
-    int sp = 0, cur = FTN_TRAVERSAL_DONE;
+    int sp = 0, cur = FTN_TRAVERSAL_DONE, leaf = 0;   // leaf < 0: a postponed leaf reference
 
     for (;;) {
         // ---- flush ----
@@ -67,14 +68,16 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sc, uint32_t n
                     else {
                         t_max = ray.t_max;
                         // analytic spheres first, with the ray's own t_max (see ftn_trace.cuh)
-                        for (uint32_t i = 0; i < sc.n_spheres; ++i) {
-                            RayF r = ray; r.t_max = t_max;
-                            SphereHit sh;
-                            if (COUNT) tc.tris++;
-                            if (sphere_intersect(sc.spheres[i], r, &sh)) { t_max = sh.t; hit.slot = FTN_SPHERE_SLOT_FLAG | i; if (ANY) break; }
+                        if (SPHERES) {
+                            for (uint32_t i = 0; i < sc.n_spheres; ++i) {
+                                RayF r = ray; r.t_max = t_max;
+                                SphereHit sh;
+                                if (COUNT) tc.tris++;
+                                if (sphere_intersect(sc.spheres[i], r, &sh)) { t_max = sh.t; hit.slot = FTN_SPHERE_SLOT_FLAG | i; if (ANY) break; }
+                            }
                         }
                         if ((ANY && hit.slot != FTN_NO_HIT_SLOT) || bvh.n_nodes == 0u) { finished = true; cur = FTN_TRAVERSAL_DONE; }
-                        else { slab = make_ray_slab(ray.o, ray.d); shear = make_ray_shear(ray.d); sp = 0; cur = 0; }
+                        else { slab = make_ray_slab(ray.o, ray.d); shear = make_ray_shear(ray.d); sp = 0; cur = 0; leaf = 0; }
                     }
                 }
             }
@@ -82,10 +85,12 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sc, uint32_t n
         }
         if (__ballot_sync(0xffffffffu, has_ray) == 0u) break;
         // ---- traverse ----
-        const int thresh = exhausted ? 1 : FTN_REFILL_THRESHOLD;
+        const int thresh = exhausted ? 1 : sc.refill_threshold;
         for (;;) {
             const bool act = has_ray && !finished;
-            // phase 1: interior nodes until this lane holds a leaf (or is done)
+            // phase 1: interior nodes.  The first leaf a lane meets is POSTPONED (speculative
+            // traversal): the lane keeps walking until it meets a second leaf or runs out of nodes, so
+            // lanes wait for each other only every other leaf.
             while (act && cur >= 0) {
                 const F4* nd = bvh.nodes + 4 * (size_t)cur;
                 const F4 n0 = ld4(nd), n1 = ld4(nd + 1), nz = ld4(nd + 2), ci = ld4(nd + 3);
@@ -101,10 +106,14 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sc, uint32_t n
                 } else if (h0) cur = c0;
                 else if (h1) cur = c1;
                 else cur = (sp > 0) ? stack[--sp] : FTN_TRAVERSAL_DONE;
+                if (cur < 0 && cur != FTN_TRAVERSAL_DONE && leaf >= 0) {
+                    leaf = cur;
+                    cur = (sp > 0) ? stack[--sp] : FTN_TRAVERSAL_DONE;
+                }
             }
-            // phase 2: one leaf
-            if (act && cur < 0 && cur != FTN_TRAVERSAL_DONE) {
-                const uint32_t ref = ~(uint32_t)cur;
+            // phase 2: the postponed leaf, then the second one if the lane stopped on it
+            while (act && leaf < 0) {
+                const uint32_t ref = ~(uint32_t)leaf;
                 const uint32_t first = ref >> 2, count = (ref & 3u) + 1u;
                 bool stop = false;
                 for (uint32_t i = 0; i < count; ++i) {
@@ -117,7 +126,9 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sc, uint32_t n
                         if (ANY) { stop = true; break; }
                     }
                 }
-                cur = (stop || sp == 0) ? FTN_TRAVERSAL_DONE : stack[--sp];
+                leaf = 0;
+                if (stop) cur = FTN_TRAVERSAL_DONE;
+                else if (cur < 0 && cur != FTN_TRAVERSAL_DONE) { leaf = cur; cur = (sp > 0) ? stack[--sp] : FTN_TRAVERSAL_DONE; }
             }
             if (act && cur == FTN_TRAVERSAL_DONE) finished = true;
             // phase 3: leave when the warp is too empty (idle lanes then flush + refill)

@@ -121,14 +121,14 @@ struct ExtendSink {
         queue_push(qs.q, counts, target, path);   // all 32 lanes arrive here together
     }
 };
-template <bool COUNT>
+template <bool COUNT, bool SPH>
 __global__ void __launch_bounds__(FTN_TRACE_THREADS)
 k_extend(SceneView sc, PathArrays pa, const uint32_t* __restrict__ queue_in, uint32_t n_in, Queues qs, uint32_t* __restrict__ counts,
          unsigned long long* __restrict__ trav) {
     PathRaySource src; src.pa = pa; src.queue = queue_in;
     ExtendSink sink; sink.sc = sc; sink.pa = pa; sink.queue = queue_in; sink.qs = qs; sink.counts = counts;
     TraceCounters tc; tc.nodes = 0; tc.tris = 0;
-    trace_persistent<false, COUNT>(sc, n_in, &counts[W_EXTEND], src, sink, tc);
+    trace_persistent<false, COUNT, SPH>(sc, n_in, &counts[W_EXTEND], src, sink, tc);
     if (COUNT) flush_trace_counters(tc, trav);
 }
 
@@ -199,13 +199,13 @@ struct ShadowSink {
         st3(pa.L, path, ld3(pa.L, path) + ld3(pa.sh_L, path));
     }
 };
-template <bool COUNT>
+template <bool COUNT, bool SPH>
 __global__ void __launch_bounds__(FTN_TRACE_THREADS)
 k_shadow(SceneView sc, PathArrays pa, const uint32_t* __restrict__ queue, uint32_t* __restrict__ counts, unsigned long long* __restrict__ trav) {
     ShadowSource src; src.pa = pa; src.queue = queue;
     ShadowSink sink; sink.pa = pa; sink.queue = queue;
     TraceCounters tc; tc.nodes = 0; tc.tris = 0;
-    trace_persistent<true, COUNT>(sc, counts[Q_SHADOW], &counts[W_SHADOW], src, sink, tc);
+    trace_persistent<true, COUNT, SPH>(sc, counts[Q_SHADOW], &counts[W_SHADOW], src, sink, tc);
     if (COUNT) flush_trace_counters(tc, trav);
 }
 
@@ -229,13 +229,13 @@ struct MisSink {
     }
 };
 // ENV_ONLY: with only infinite lights a hit contributes nothing whatever it is, so any-hit suffices
-template <bool ENV_ONLY, bool COUNT>
+template <bool ENV_ONLY, bool COUNT, bool SPH>
 __global__ void __launch_bounds__(FTN_TRACE_THREADS)
 k_mis(SceneView sc, PathArrays pa, const uint32_t* __restrict__ queue, uint32_t* __restrict__ counts, unsigned long long* __restrict__ trav) {
     MisSource src; src.pa = pa; src.queue = queue;
     MisSink sink; sink.sc = sc; sink.pa = pa; sink.queue = queue;
     TraceCounters tc; tc.nodes = 0; tc.tris = 0;
-    trace_persistent<ENV_ONLY, COUNT>(sc, counts[Q_MIS], &counts[W_MIS], src, sink, tc);
+    trace_persistent<ENV_ONLY, COUNT, SPH>(sc, counts[Q_MIS], &counts[W_MIS], src, sink, tc);
     if (COUNT) flush_trace_counters(tc, trav);
 }
 
@@ -307,6 +307,13 @@ static size_t g_max_paths_per_pass = 4u << 20;
 
 // CUDA-event pairs around every traversal launch, per kernel class (extend / shadow / mis): the
 // live per-kernel durations bench.py's roofline uses.
+// runtime bools -> template arguments B0, B1
+#define FTN_BOOL2(f0, f1, CALL)                                                      \
+    do {                                                                             \
+        if (f0) { constexpr bool B0 = true;  if (f1) { constexpr bool B1 = true; CALL; } else { constexpr bool B1 = false; CALL; } } \
+        else    { constexpr bool B0 = false; if (f1) { constexpr bool B1 = true; CALL; } else { constexpr bool B1 = false; CALL; } } \
+    } while (0)
+
 struct TraceTimer {
     std::vector<cudaEvent_t> ev; std::vector<int> cls;
     cudaStream_t st;
@@ -370,6 +377,7 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
     FTN_CUDA(cudaMemsetAsync(d_trav, 0, 6 * sizeof(unsigned long long), st));
 
     const SceneView sc = s->view();
+    const bool sph = s->n_spheres > 0;
     bool has_area = false;
     for (const LightData& l : s->h_lights) if (l.type == 1) has_area = true;
     uint64_t camera_samples = 0;
@@ -401,8 +409,7 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
             Queues q = qs; q.q[Q_ACTIVE_OUT] = q_out;
             const unsigned ge = trace_grid(n_active, FTN_TRACE_BLOCKS_PER_SM);
             timer.begin(0);
-            if (count_traversal) k_extend<true><<<ge, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q_in, n_active, q, counts, d_trav);
-            else k_extend<false><<<ge, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q_in, n_active, q, counts, d_trav);
+            FTN_BOOL2(count_traversal, sph, (k_extend<B0, B1><<<ge, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q_in, n_active, q, counts, d_trav)));
             timer.end();
             FTN_LAUNCHED();
             class_rays[0] += n_active;
@@ -418,8 +425,7 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
             if (hc[Q_SHADOW]) {
                 const unsigned g = trace_grid(hc[Q_SHADOW], FTN_TRACE_BLOCKS_PER_SM);
                 timer.begin(1);
-                if (count_traversal) k_shadow<true><<<g, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_SHADOW], counts, d_trav + 2);
-                else k_shadow<false><<<g, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_SHADOW], counts, d_trav + 2);
+                FTN_BOOL2(count_traversal, sph, (k_shadow<B0, B1><<<g, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_SHADOW], counts, d_trav + 2)));
                 timer.end();
                 FTN_LAUNCHED();
                 class_rays[1] += hc[Q_SHADOW];
@@ -427,13 +433,8 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
             if (hc[Q_MIS]) {
                 const unsigned g = trace_grid(hc[Q_MIS], FTN_TRACE_BLOCKS_PER_SM);
                 timer.begin(2);
-                if (has_area) {
-                    if (count_traversal) k_mis<false, true><<<g, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts, d_trav + 4);
-                    else k_mis<false, false><<<g, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts, d_trav + 4);
-                } else {
-                    if (count_traversal) k_mis<true, true><<<g, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts, d_trav + 4);
-                    else k_mis<true, false><<<g, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts, d_trav + 4);
-                }
+                if (has_area) { FTN_BOOL2(count_traversal, sph, (k_mis<false, B0, B1><<<g, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts, d_trav + 4))); }
+                else { FTN_BOOL2(count_traversal, sph, (k_mis<true, B0, B1><<<g, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts, d_trav + 4))); }
                 timer.end();
                 FTN_LAUNCHED();
                 class_rays[2] += hc[Q_MIS];

@@ -12,6 +12,8 @@
 //   k_gather_tris     48-byte pre-gathered triangle records in leaf order
 #include "ftn_scene.h"
 #include "ftn_lbvh.cuh"
+#include <cstdlib>
+#define FTN_REFILL_THRESHOLD_DEFAULT 16
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -158,6 +160,8 @@ SceneView make_view(const FtnScene& s) {
     v.spheres = s.d_spheres; v.n_spheres = s.n_spheres;
     v.lights = s.d_lights; v.n_lights = (uint32_t)s.h_lights.size();
     v.n_tris = s.n_tris;
+    static const int thr = [] { const char* e = getenv("FTN_REFILL_THRESHOLD"); int t = e ? atoi(e) : FTN_REFILL_THRESHOLD_DEFAULT; return t < 1 ? 1 : (t > 32 ? 32 : t); }();
+    v.refill_threshold = thr;
     return v;
 }
 

@@ -12,7 +12,7 @@ GPU_LIB_PATH = os.path.join(_HERE, "csrc", "libfountain_gpu.so")
 
 
 def load_gpu_library(path=None):
-    path = path or GPU_LIB_PATH
+    path = path or os.environ.get("FTN_GPU_LIB") or GPU_LIB_PATH   # FTN_GPU_LIB: A/B experiments with variant builds
     if not os.path.exists(path):
         raise ImportError("CUDA extension not built: %s is missing. Run `python -c 'import __graft_entry__ as g; "
                           "g.build()'` (nvcc, sm_100a). There is no CPU fallback." % path)

@@ -35,7 +35,7 @@ struct SimScene {
         v.bvh.nodes = nodes.data(); v.bvh.tris = tris.data(); v.bvh.n_nodes = n_nodes; v.bvh.n_tris = n_tris;
         v.pos = pos.data(); v.nrm = nrm.empty() ? nullptr : nrm.data(); v.uv = uv.empty() ? nullptr : uv.data(); v.idx = idx.data();
         v.meshes = meshes.data(); v.materials = mats.data(); v.spheres = spheres.data(); v.n_spheres = (uint32_t)spheres.size();
-        v.lights = lights.data(); v.n_lights = (uint32_t)lights.size(); v.n_tris = n_tris;
+        v.lights = lights.data(); v.n_lights = (uint32_t)lights.size(); v.n_tris = n_tris; v.refill_threshold = 20;
         return v;
     }
 };
@@ -364,4 +364,7 @@ SIM_API int sim_kat_env(const SimScene* s, const float u[2], float out[11]) {
 SIM_API float sim_kat_counter_uniform(uint64_t seed, uint64_t sample_index, uint32_t dim) {
     return sampler_uniform(sampler_sample_key(sampler_seed_key(seed), sample_index), dim);
 }
-SIM_API float sim_kat_gamma(int n) { return gamma_n(n); }
+SIM_API float sim_kat_gamma(int n) {
+    switch (n) { case 1: return gamma_n(1); case 2: return gamma_n(2); case 3: return gamma_n(3); case 4: return gamma_n(4);
+                 case 5: return gamma_n(5); case 6: return gamma_n(6); case 7: return gamma_n(7); default: return gamma_n(8); }
+}
