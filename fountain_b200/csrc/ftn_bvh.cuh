@@ -1,17 +1,22 @@
-// Flattened BVH layouts and the traversal loops.
+// Flattened BVH layouts and the single-ray traversal loop.
 //
-// Layout "BVH2x64": one 64-byte, 64-byte-aligned record per interior node holding BOTH
-// children's boxes (so one node fetch = 4 x 128-bit loads decides two subtrees) and
-// triangles re-laid as 48-byte pre-gathered records in leaf order (3 x 128-bit loads, no
+// Triangles are re-laid as 48-byte pre-gathered records in leaf order (3 x 128-bit loads, no
 // index indirection; replaces the reference's Box<dyn Primitive> -> Arc<TriangleMesh> ->
-// indices -> vertices chain, bvh.rs:181 / triangle.rs:96-111).
-//
-//   node:  n0 = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)
-//          n1 = (c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y)
-//          nz = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)
-//          ci = (child0, child1, unused, unused)   child >= 0: interior node index
-//                                                  child <  0: leaf, ~child = first*4 + (count-1)
+// indices -> vertices chain, bvh.rs:181 / triangle.rs:96-111):
 //   tri:   (p0.xyz, prim id), (p1.xyz, mesh id), (p2.xyz, unused)
+//
+// Interior nodes, FTN_BVH_WIDTH = 2 (default) -- "BVH2x64": 64-byte record with both children's boxes:
+//   n0 = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)  n1 = (c1...)  nz = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)
+//   ci = (child0, child1, -, -)
+// FTN_BVH_WIDTH = 4 -- "BVH4x128" (built with -DFTN_BVH_WIDTH=4; measured SLOWER on B200, kept for
+// A/B): one 128-byte record holding the boxes of up to four children in SoA form.  It halves the
+// node visits (C3 interior rays: 35.3 -> 18.3 per ray) but the four exact slab tests + the sorting
+// network cost more issue slots than the saved round trips buy back: 1866 vs 2049 Mrays/s
+// (profiles/r01_ab_bvh4_vs_bvh2.txt).  The traversal is issue-bound, not latency-bound.
+//   q0 = lo.x[0..3]  q1 = hi.x[0..3]  q2 = lo.y[..]  q3 = hi.y[..]  q4 = lo.z[..]  q5 = hi.z[..]
+//   q6 = child[0..3] (int bits)       q7 = unused
+//   unused child slots carry child = FTN_TRAVERSAL_DONE and are masked out of the box test.
+// child >= 0: interior node index;  child < 0: leaf, ~child = first*4 + (count-1), count <= 4.
 //
 // The box test is the reference's slab test with 1/d hoisted (bounds.rs:214-233): same
 // roundings, same 1+2*gamma(3) widening, same NaN-ignoring min/max.
@@ -20,15 +25,26 @@
 
 namespace ftn {
 
+#ifndef FTN_BVH_WIDTH
+#define FTN_BVH_WIDTH 2
+#endif
+#if FTN_BVH_WIDTH == 4
+#define FTN_NODE_F4 8
+#else
+#define FTN_NODE_F4 4
+#endif
+#define FTN_NODE_BYTES (16 * FTN_NODE_F4)
+
 #define FTN_LEAF_MAX 4
-#define FTN_STACK_SIZE 64
+#define FTN_STACK_SIZE 96   /* binary depth <= 62 (30 code bits + index bits); BVH4 pushes <= 3 per level of <= 31 */
 #define FTN_NO_HIT_SLOT 0xFFFFFFFFu
 #define FTN_SPHERE_SLOT_FLAG 0x80000000u
+#define FTN_TRAVERSAL_DONE ((int)0x80000000)
 
 struct F4 { float x, y, z, w; };
 
 struct BvhView {
-    const F4* nodes;      // 4 x F4 per node
+    const F4* nodes;      // FTN_NODE_F4 x F4 per node
     const F4* tris;       // 3 x F4 per triangle, leaf order
     uint32_t n_nodes;     // 0 => no triangles
     uint32_t n_tris;
@@ -72,11 +88,82 @@ FTN_HD bool slab_test(const RaySlab& r, float lox, float hix, float loy, float h
 
 struct TraceCounters { uint32_t nodes, tris; };
 
-// Closest hit (ANY = false: Scene::intersect, bvh.rs:160-215) or any hit (ANY = true:
-// Scene::intersect_test, bvh.rs:217-266) against the triangle BVH.  `t_max` in/out.
-// Returns the leaf-order slot of the accepted triangle or FTN_NO_HIT_SLOT.
+FTN_HD void cswap(float& ka, int& va, float& kb, int& vb) {   // compare-exchange on (key, value)
+    const bool s = kb < ka;
+    const float k0 = s ? kb : ka, k1 = s ? ka : kb;
+    const int v0 = s ? vb : va, v1 = s ? va : vb;
+    ka = k0; va = v0; kb = k1; vb = v1;
+}
+
+// Tests the children of interior node `cur` and returns the next reference to visit: the nearest
+// entered child (the others are pushed far-to-near), or a popped entry, or FTN_TRAVERSAL_DONE.
+// Front-to-back by entry distance (the reference orders by split-axis sign, bvh.rs:194-201; the
+// order only decides which of two exactly tied hits is kept).
+FTN_HD int node_step(const BvhView& bvh, int cur, const RaySlab& slab, float t_max, int* stack, int& sp) {
+    const F4* nd = bvh.nodes + (size_t)FTN_NODE_F4 * (size_t)cur;
+#if FTN_BVH_WIDTH == 4
+    const F4 lx = ld4(nd), hx = ld4(nd + 1), ly = ld4(nd + 2), hy = ld4(nd + 3), lz = ld4(nd + 4), hz = ld4(nd + 5), cr = ld4(nd + 6);
+    const float inf = FTN_INF;
+    float e0, e1, e2, e3;
+    int c0 = (int)f2u(cr.x), c1 = (int)f2u(cr.y), c2 = (int)f2u(cr.z), c3 = (int)f2u(cr.w);
+    // an unused slot is marked by its child reference (the swap-on-inverted rule of the slab test
+    // would otherwise read an inverted or NaN box as an infinite one)
+    const bool h0 = slab_test(slab, lx.x, hx.x, ly.x, hy.x, lz.x, hz.x, t_max, &e0) && c0 != FTN_TRAVERSAL_DONE;
+    const bool h1 = slab_test(slab, lx.y, hx.y, ly.y, hy.y, lz.y, hz.y, t_max, &e1) && c1 != FTN_TRAVERSAL_DONE;
+    const bool h2 = slab_test(slab, lx.z, hx.z, ly.z, hy.z, lz.z, hz.z, t_max, &e2) && c2 != FTN_TRAVERSAL_DONE;
+    const bool h3 = slab_test(slab, lx.w, hx.w, ly.w, hy.w, lz.w, hz.w, t_max, &e3) && c3 != FTN_TRAVERSAL_DONE;
+    e0 = h0 ? e0 : inf; e1 = h1 ? e1 : inf; e2 = h2 ? e2 : inf; e3 = h3 ? e3 : inf;
+    // 5-comparator sorting network on (entry distance, child); misses sort to the back with +inf.
+    // Entry distances are >= 0 and finite for entered boxes, so +inf marks exactly the misses.
+    cswap(e0, c0, e1, c1); cswap(e2, c2, e3, c3); cswap(e0, c0, e2, c2); cswap(e1, c1, e3, c3); cswap(e1, c1, e2, c2);
+    const int nh = (int)h0 + (int)h1 + (int)h2 + (int)h3;
+    if (nh == 0) return (sp > 0) ? stack[--sp] : FTN_TRAVERSAL_DONE;
+    if (nh > 3) stack[sp++] = c3;
+    if (nh > 2) stack[sp++] = c2;
+    if (nh > 1) stack[sp++] = c1;
+    return c0;
+#else
+    const F4 n0 = ld4(nd), n1 = ld4(nd + 1), nz = ld4(nd + 2), ci = ld4(nd + 3);
+    float e0, e1;
+    const int c0 = (int)f2u(ci.x), c1 = (int)f2u(ci.y);
+    const bool h0 = slab_test(slab, n0.x, n0.y, n0.z, n0.w, nz.x, nz.y, t_max, &e0);
+    const bool h1 = slab_test(slab, n1.x, n1.y, n1.z, n1.w, nz.z, nz.w, t_max, &e1) && c1 != FTN_TRAVERSAL_DONE;
+    if (h0 && h1) {
+        const bool swap = e1 < e0;
+        stack[sp++] = swap ? c0 : c1;
+        return swap ? c1 : c0;
+    }
+    if (h0) return c0;
+    if (h1) return c1;
+    return (sp > 0) ? stack[--sp] : FTN_TRAVERSAL_DONE;
+#endif
+}
+
+// Tests the triangles of leaf reference `leaf` (< 0); returns true if ANY and a hit was accepted.
 template <bool ANY, bool COUNT>
-FTN_HD uint32_t bvh2_traverse(const BvhView& bvh, V3 ro, V3 rd, float* t_max_io, TriHit* hit_out, TraceCounters* ctr) {
+FTN_HD bool leaf_step(const BvhView& bvh, int leaf, V3 ro, const RayShear& shear, float* t_max, uint32_t* best, TriHit* hit, TraceCounters* ctr) {
+    const uint32_t ref = ~(uint32_t)leaf;
+    const uint32_t first = ref >> 2, count = (ref & 3u) + 1u;
+    for (uint32_t i = 0; i < count; ++i) {
+        const F4* t = bvh.tris + 3 * (size_t)(first + i);
+        const F4 a = ld4(t), b = ld4(t + 1), c = ld4(t + 2);
+        if (COUNT) ctr->tris++;
+        TriHit h;
+        if (triangle_intersect(V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), V3(c.x, c.y, c.z), ro, shear, *t_max, &h)) {
+            *t_max = h.t; *best = first + i; *hit = h;
+            if (ANY) return true;
+        }
+    }
+    return false;
+}
+
+// Closest hit (ANY = false: Scene::intersect, bvh.rs:160-215) or any hit (ANY = true:
+// Scene::intersect_test, bvh.rs:217-266) against the triangle BVH, one ray.  `t_max` in/out.
+// Returns the leaf-order slot of the accepted triangle or FTN_NO_HIT_SLOT.  This is the plain
+// statement of the traversal (and what the host test harness runs); the kernels use the
+// warp-persistent form of the same steps in ftn_trace_persistent.cuh.
+template <bool ANY, bool COUNT>
+FTN_HD uint32_t bvh_traverse(const BvhView& bvh, V3 ro, V3 rd, float* t_max_io, TriHit* hit_out, TraceCounters* ctr) {
     uint32_t best = FTN_NO_HIT_SLOT;
     if (bvh.n_nodes == 0u) return best;
     float t_max = *t_max_io;
@@ -85,39 +172,14 @@ FTN_HD uint32_t bvh2_traverse(const BvhView& bvh, V3 ro, V3 rd, float* t_max_io,
     int stack[FTN_STACK_SIZE];
     int sp = 0;
     int cur = 0;
-    for (;;) {
+    while (cur != FTN_TRAVERSAL_DONE) {
         if (cur >= 0) {
-            const F4* n = bvh.nodes + 4 * (size_t)cur;
-            const F4 n0 = ld4(n), n1 = ld4(n + 1), nz = ld4(n + 2), ci = ld4(n + 3);
             if (COUNT) ctr->nodes++;
-            float e0, e1;
-            const bool h0 = slab_test(slab, n0.x, n0.y, n0.z, n0.w, nz.x, nz.y, t_max, &e0);
-            const bool h1 = slab_test(slab, n1.x, n1.y, n1.z, n1.w, nz.z, nz.w, t_max, &e1);
-            const int c0 = (int)f2u(ci.x), c1 = (int)f2u(ci.y);
-            if (h0 && h1) {
-                // front-to-back by entry distance (the reference orders by split-axis sign, bvh.rs:194-201;
-                // order only affects which of two exactly-tied hits is kept)
-                if (e1 < e0) { if (sp < FTN_STACK_SIZE) stack[sp++] = c0; cur = c1; }
-                else { if (sp < FTN_STACK_SIZE) stack[sp++] = c1; cur = c0; }
-                continue;
-            } else if (h0) { cur = c0; continue; }
-            else if (h1) { cur = c1; continue; }
+            cur = node_step(bvh, cur, slab, t_max, stack, sp);
         } else {
-            const uint32_t ref = ~(uint32_t)cur;
-            const uint32_t first = ref >> 2, count = (ref & 3u) + 1u;
-            for (uint32_t i = 0; i < count; ++i) {
-                const F4* t = bvh.tris + 3 * (size_t)(first + i);
-                const F4 a = ld4(t), b = ld4(t + 1), c = ld4(t + 2);
-                if (COUNT) ctr->tris++;
-                TriHit h;
-                if (triangle_intersect(V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), V3(c.x, c.y, c.z), ro, shear, t_max, &h)) {
-                    t_max = h.t; best = first + i; *hit_out = h;
-                    if (ANY) { *t_max_io = t_max; return best; }
-                }
-            }
+            if (leaf_step<ANY, COUNT>(bvh, cur, ro, shear, &t_max, &best, hit_out, ctr)) break;
+            cur = (sp > 0) ? stack[--sp] : FTN_TRAVERSAL_DONE;
         }
-        if (sp == 0) break;
-        cur = stack[--sp];
     }
     *t_max_io = t_max;
     return best;

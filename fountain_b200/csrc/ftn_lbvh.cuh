@@ -128,9 +128,80 @@ FTN_HD int lbvh_emit_child(const LbvhArrays& a, const uint32_t* survive, const u
     if (survive[ref]) return (int)new_index[ref];
     return lbvh_encode_leaf_ref(a.first[ref], a.last[ref] - a.first[ref] + 1u);
 }
-// one BVH2x64 record for the surviving interior node i
+// ---- emission of the traversal layout (ftn_bvh.cuh) ---------------------------------------------------
+// depth of interior node i in the binary tree (root = 0), by walking the parent links
+FTN_HD uint32_t lbvh_depth(const LbvhArrays& a, int i) {
+    uint32_t d = 0;
+    uint32_t p = a.parent[i];
+    while (p != 0xFFFFFFFFu) { ++d; p = a.parent[p]; }
+    return d;
+}
+// Which surviving binary nodes become records of the emitted layout.  Width 2: all of them.
+// Width 4: those at even depth; a surviving node at odd depth is absorbed into its parent's
+// record, which then lists its two children directly (2-level collapse, 2..4 children per record).
+FTN_HD uint32_t lbvh_is_record(const LbvhArrays& a, const uint32_t* survive, int i) {
+#if FTN_BVH_WIDTH == 4
+    return (survive[i] && (lbvh_depth(a, i) & 1u) == 0u) ? 1u : 0u;
+#else
+    return survive[i];
+#endif
+}
+
+#if FTN_BVH_WIDTH == 4
+struct Node4Builder {
+    float lx[4], hx[4], ly[4], hy[4], lz[4], hz[4]; int child[4]; int n;
+};
+FTN_HD void node4_add(Node4Builder* b, F4 lo, F4 hi, int ref) {
+    const int k = b->n++;
+    b->lx[k] = lo.x; b->hx[k] = hi.x; b->ly[k] = lo.y; b->hy[k] = hi.y; b->lz[k] = lo.z; b->hz[k] = hi.z; b->child[k] = ref;
+}
+FTN_HD void node4_store(const Node4Builder& b, F4* out) {
+    float lx[4], hx[4], ly[4], hy[4], lz[4], hz[4]; int ch[4];
+    const float inf = FTN_INF;
+    for (int k = 0; k < 4; ++k) {
+        const bool used = k < b.n;
+        lx[k] = used ? b.lx[k] : inf; hx[k] = used ? b.hx[k] : -inf;
+        ly[k] = used ? b.ly[k] : inf; hy[k] = used ? b.hy[k] : -inf;
+        lz[k] = used ? b.lz[k] : inf; hz[k] = used ? b.hz[k] : -inf;
+        ch[k] = used ? b.child[k] : FTN_TRAVERSAL_DONE;
+    }
+    F4 q;
+    q.x = lx[0]; q.y = lx[1]; q.z = lx[2]; q.w = lx[3]; out[0] = q;
+    q.x = hx[0]; q.y = hx[1]; q.z = hx[2]; q.w = hx[3]; out[1] = q;
+    q.x = ly[0]; q.y = ly[1]; q.z = ly[2]; q.w = ly[3]; out[2] = q;
+    q.x = hy[0]; q.y = hy[1]; q.z = hy[2]; q.w = hy[3]; out[3] = q;
+    q.x = lz[0]; q.y = lz[1]; q.z = lz[2]; q.w = lz[3]; out[4] = q;
+    q.x = hz[0]; q.y = hz[1]; q.z = hz[2]; q.w = hz[3]; out[5] = q;
+    q.x = u2f((uint32_t)ch[0]); q.y = u2f((uint32_t)ch[1]); q.z = u2f((uint32_t)ch[2]); q.w = u2f((uint32_t)ch[3]); out[6] = q;
+    q.x = q.y = q.z = q.w = 0.0f; out[7] = q;
+}
+// child `ref` of an even-depth record: a leaf-ish subtree becomes a leaf reference; a surviving
+// (odd-depth) interior node is replaced by its own two children.
+FTN_HD void node4_add_subtree(Node4Builder* b, const LbvhArrays& a, const F4* leaf_lo, const F4* leaf_hi,
+                              const uint32_t* survive, const uint32_t* new_index, uint32_t ref, bool expand) {
+    F4 lo, hi;
+    if ((ref & LBVH_LEAF_FLAG) || !survive[ref]) {
+        lbvh_load_child_box(a, leaf_lo, leaf_hi, ref, &lo, &hi);
+        node4_add(b, lo, hi, lbvh_emit_child(a, survive, new_index, ref));   // leaf reference
+    } else if (expand) {
+        node4_add_subtree(b, a, leaf_lo, leaf_hi, survive, new_index, a.left[ref], false);
+        node4_add_subtree(b, a, leaf_lo, leaf_hi, survive, new_index, a.right[ref], false);
+    } else {
+        lbvh_load_child_box(a, leaf_lo, leaf_hi, ref, &lo, &hi);
+        node4_add(b, lo, hi, (int)new_index[ref]);                          // an even-depth record
+    }
+}
+#endif
+
+// one record of the traversal layout for binary node i (for which lbvh_is_record is 1)
 FTN_HD void lbvh_emit_node(const LbvhArrays& a, const F4* leaf_lo, const F4* leaf_hi, const uint32_t* survive,
                            const uint32_t* new_index, int i, F4* nodes) {
+#if FTN_BVH_WIDTH == 4
+    Node4Builder b; b.n = 0;
+    node4_add_subtree(&b, a, leaf_lo, leaf_hi, survive, new_index, a.left[i], true);
+    node4_add_subtree(&b, a, leaf_lo, leaf_hi, survive, new_index, a.right[i], true);
+    node4_store(b, nodes + (size_t)FTN_NODE_F4 * (size_t)new_index[i]);
+#else
     F4 l0, h0, l1, h1;
     const uint32_t lr = a.left[i], rr = a.right[i];
     lbvh_load_child_box(a, leaf_lo, leaf_hi, lr, &l0, &h0);
@@ -143,17 +214,25 @@ FTN_HD void lbvh_emit_node(const LbvhArrays& a, const F4* leaf_lo, const F4* lea
     nz.x = l0.z; nz.y = h0.z; nz.z = l1.z; nz.w = h1.z;
     ci.x = u2f((uint32_t)c0); ci.y = u2f((uint32_t)c1); ci.z = 0.0f; ci.w = 0.0f;
     out[0] = n0; out[1] = n1; out[2] = nz; out[3] = ci;
+#endif
 }
-// root when the whole scene fits one leaf (n <= FTN_LEAF_MAX): child 0 = the leaf, child 1 = never hit
+// root when the whole scene fits one leaf (n <= FTN_LEAF_MAX): one child = the leaf
 FTN_HD void lbvh_emit_single(uint32_t n, const float lo[3], const float hi[3], F4* nodes) {
+    const int leaf = lbvh_encode_leaf_ref(0u, n);
+#if FTN_BVH_WIDTH == 4
+    Node4Builder b; b.n = 0;
+    F4 l, h; l.x = lo[0]; l.y = lo[1]; l.z = lo[2]; l.w = 0.0f; h.x = hi[0]; h.y = hi[1]; h.z = hi[2]; h.w = 0.0f;
+    node4_add(&b, l, h, leaf);
+    node4_store(b, nodes);
+#else
     F4 n0, n1, nz, ci;
     const float inf = FTN_INF;
     n0.x = lo[0]; n0.y = hi[0]; n0.z = lo[1]; n0.w = hi[1];
     n1.x = inf; n1.y = -inf; n1.z = inf; n1.w = -inf;
     nz.x = lo[2]; nz.y = hi[2]; nz.z = inf; nz.w = -inf;
-    const int leaf = lbvh_encode_leaf_ref(0u, n);
-    ci.x = u2f((uint32_t)leaf); ci.y = u2f((uint32_t)leaf); ci.z = 0.0f; ci.w = 0.0f;
+    ci.x = u2f((uint32_t)leaf); ci.y = u2f((uint32_t)FTN_TRAVERSAL_DONE); ci.z = 0.0f; ci.w = 0.0f;
     nodes[0] = n0; nodes[1] = n1; nodes[2] = nz; nodes[3] = ci;
+#endif
 }
 // 48-byte pre-gathered triangle record for leaf-order slot i
 FTN_HD void lbvh_gather_tri(const float* pos, const uint32_t* idx, const uint32_t* order, uint32_t i,

@@ -33,7 +33,7 @@ FTN_HD void scene_intersect(const SceneView& sc, const RayF& ray, SceneHit* out,
         }
     }
     TriHit th;
-    const uint32_t slot = bvh2_traverse<ANY, COUNT>(sc.bvh, ray.o, ray.d, &t_max, &th, ctr);
+    const uint32_t slot = bvh_traverse<ANY, COUNT>(sc.bvh, ray.o, ray.d, &t_max, &th, ctr);
     if (slot != FTN_NO_HIT_SLOT) { out->slot = slot; out->tri = th; }
     out->t = t_max;
 }

@@ -23,7 +23,6 @@ namespace ftn {
 #ifndef FTN_REFILL_THRESHOLD
 #define FTN_REFILL_THRESHOLD 20
 #endif
-#define FTN_TRAVERSAL_DONE ((int)0x80000000)
 
 // Source:  __device__ bool load(uint32_t item, RayF* ray)       -- false: nothing to trace for this item
 // Sink:    __device__ void store(bool valid, uint32_t item, const RayF& ray, const SceneHit& hit)
@@ -92,20 +91,8 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sc, uint32_t n
             // traversal): the lane keeps walking until it meets a second leaf or runs out of nodes, so
             // lanes wait for each other only every other leaf.
             while (act && cur >= 0) {
-                const F4* nd = bvh.nodes + 4 * (size_t)cur;
-                const F4 n0 = ld4(nd), n1 = ld4(nd + 1), nz = ld4(nd + 2), ci = ld4(nd + 3);
                 if (COUNT) tc.nodes++;
-                float e0, e1;
-                const bool h0 = slab_test(slab, n0.x, n0.y, n0.z, n0.w, nz.x, nz.y, t_max, &e0);
-                const bool h1 = slab_test(slab, n1.x, n1.y, n1.z, n1.w, nz.z, nz.w, t_max, &e1);
-                const int c0 = (int)f2u(ci.x), c1 = (int)f2u(ci.y);
-                if (h0 && h1) {
-                    const bool swap = e1 < e0;
-                    stack[sp++] = swap ? c0 : c1;
-                    cur = swap ? c1 : c0;
-                } else if (h0) cur = c0;
-                else if (h1) cur = c1;
-                else cur = (sp > 0) ? stack[--sp] : FTN_TRAVERSAL_DONE;
+                cur = node_step(bvh, cur, slab, t_max, stack, sp);
                 if (cur < 0 && cur != FTN_TRAVERSAL_DONE && leaf >= 0) {
                     leaf = cur;
                     cur = (sp > 0) ? stack[--sp] : FTN_TRAVERSAL_DONE;
@@ -113,19 +100,7 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sc, uint32_t n
             }
             // phase 2: the postponed leaf, then the second one if the lane stopped on it
             while (act && leaf < 0) {
-                const uint32_t ref = ~(uint32_t)leaf;
-                const uint32_t first = ref >> 2, count = (ref & 3u) + 1u;
-                bool stop = false;
-                for (uint32_t i = 0; i < count; ++i) {
-                    const F4* t = bvh.tris + 3 * (size_t)(first + i);
-                    const F4 a = ld4(t), b = ld4(t + 1), c = ld4(t + 2);
-                    if (COUNT) tc.tris++;
-                    TriHit h;
-                    if (triangle_intersect(V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), V3(c.x, c.y, c.z), ray.o, shear, t_max, &h)) {
-                        t_max = h.t; hit.slot = first + i; hit.tri = h;
-                        if (ANY) { stop = true; break; }
-                    }
-                }
+                const bool stop = leaf_step<ANY, COUNT>(bvh, leaf, ray.o, shear, &t_max, &hit.slot, &hit.tri, &tc);
                 leaf = 0;
                 if (stop) cur = FTN_TRAVERSAL_DONE;
                 else if (cur < 0 && cur != FTN_TRAVERSAL_DONE) { leaf = cur; cur = (sp > 0) ? stack[--sp] : FTN_TRAVERSAL_DONE; }

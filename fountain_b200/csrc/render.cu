@@ -462,7 +462,7 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
         stats->camera_samples = camera_samples;
         stats->rays_closest = class_rays[0] + class_rays[2]; stats->rays_any = class_rays[1];   // Scene::intersect / intersect_test calls
         stats->device_seconds = ms * 1e-3; stats->bvh_build_seconds = s->build_seconds;
-        stats->bvh_nodes = s->n_nodes; stats->bvh_node_bytes = 64; stats->bvh_tri_bytes = 48;
+        stats->bvh_nodes = s->n_nodes; stats->bvh_node_bytes = FTN_NODE_BYTES; stats->bvh_tri_bytes = 48;
         timer.collect(stats->trace_seconds, stats->trace_launches);
         for (int c = 0; c < 3; ++c) { stats->trace_rays[c] = class_rays[c]; stats->trace_nodes[c] = h_trav[2 * c]; stats->trace_tris[c] = h_trav[2 * c + 1]; }
         stats->node_visits = h_trav[0] + h_trav[2] + h_trav[4]; stats->tri_tests = h_trav[1] + h_trav[3] + h_trav[5];

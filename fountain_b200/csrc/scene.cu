@@ -115,10 +115,17 @@ k_lbvh_survive(int n, LbvhArrays a, uint32_t* __restrict__ survive) {
 }
 
 __global__ void __launch_bounds__(256)
-k_lbvh_emit(int n, LbvhArrays a, const F4* __restrict__ leaf_lo, const F4* __restrict__ leaf_hi,
-            const uint32_t* __restrict__ survive, const uint32_t* __restrict__ new_index, F4* __restrict__ nodes) {
+k_lbvh_mark_records(int n, LbvhArrays a, const uint32_t* __restrict__ survive, uint32_t* __restrict__ is_record) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n - 1 && survive[i]) lbvh_emit_node(a, leaf_lo, leaf_hi, survive, new_index, i, nodes);
+    if (i < n - 1) is_record[i] = lbvh_is_record(a, survive, i);
+}
+
+__global__ void __launch_bounds__(256)
+k_lbvh_emit(int n, LbvhArrays a, const F4* __restrict__ leaf_lo, const F4* __restrict__ leaf_hi,
+            const uint32_t* __restrict__ survive, const uint32_t* __restrict__ is_record, const uint32_t* __restrict__ new_index,
+            F4* __restrict__ nodes) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n - 1 && is_record[i]) lbvh_emit_node(a, leaf_lo, leaf_hi, survive, new_index, i, nodes);
 }
 
 __global__ void k_lbvh_emit_single(uint32_t n, const BuildBounds* gb, F4* nodes) {
@@ -350,7 +357,7 @@ int bvh_build(FtnScene* s) {
     if (n > 0) {
         BuildBounds* d_gb = nullptr;
         F4 *tri_lo = nullptr, *tri_hi = nullptr, *leaf_lo = nullptr, *leaf_hi = nullptr;
-        uint32_t *keys = nullptr, *survive = nullptr;
+        uint32_t *keys = nullptr, *survive = nullptr, *is_record = nullptr;
         LbvhArrays a; std::memset(&a, 0, sizeof(a));
         std::vector<void*> tmp;
         auto dalloc = [&](void** p, size_t bytes) -> int {
@@ -381,7 +388,7 @@ int bvh_build(FtnScene* s) {
             k_gather_tris<<<gb256, 256, 0, st>>>(s->d_pos, s->d_idx, s->d_order, n, s->d_meshes, s->n_meshes, s->d_tris); count_launch();
             if ((e = cudaGetLastError()) != cudaSuccess) { rc = cuda_fail(e, "gather kernels", __FILE__, __LINE__); break; }
             if (n <= (uint32_t)FTN_LEAF_MAX) {
-                if (!s->d_nodes && (e = cudaMalloc(&s->d_nodes, 4 * sizeof(F4))) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc nodes", __FILE__, __LINE__); break; }
+                if (!s->d_nodes && (e = cudaMalloc(&s->d_nodes, FTN_NODE_F4 * sizeof(F4))) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc nodes", __FILE__, __LINE__); break; }
                 k_lbvh_emit_single<<<1, 32, 0, st>>>(n, d_gb, s->d_nodes); count_launch();
                 s->n_nodes = 1;
             } else {
@@ -395,6 +402,7 @@ int bvh_build(FtnScene* s) {
                 if ((rc = dalloc((void**)&a.node_lo, ni * sizeof(F4))) != FTN_OK) break;
                 if ((rc = dalloc((void**)&a.node_hi, ni * sizeof(F4))) != FTN_OK) break;
                 if ((rc = dalloc((void**)&survive, ni * 4)) != FTN_OK) break;
+                if ((rc = dalloc((void**)&is_record, ni * 4)) != FTN_OK) break;
                 if ((e = cudaMemsetAsync(a.arrive, 0, ni * 4, st)) != cudaSuccess) { rc = cuda_fail(e, "memset arrive", __FILE__, __LINE__); break; }
                 const unsigned gi = (unsigned)((ni + 255) / 256);
                 k_lbvh_topology<<<gi, 256, 0, st>>>(keys, (int)n, a); count_launch();
@@ -402,15 +410,16 @@ int bvh_build(FtnScene* s) {
                 k_lbvh_survive<<<gi, 256, 0, st>>>((int)n, a, survive); count_launch();
                 if ((e = cudaGetLastError()) != cudaSuccess) { rc = cuda_fail(e, "lbvh kernels", __FILE__, __LINE__); break; }
                 uint32_t last_flag = 0, last_idx = 0;
-                if ((e = cudaMemcpyAsync(&last_flag, survive + ni - 1, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { rc = cuda_fail(e, "read survive", __FILE__, __LINE__); break; }
+                k_lbvh_mark_records<<<gi, 256, 0, st>>>((int)n, a, survive, is_record); count_launch();
+                if ((e = cudaMemcpyAsync(&last_flag, is_record + ni - 1, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { rc = cuda_fail(e, "read record flags", __FILE__, __LINE__); break; }
                 uint32_t* new_index = a.arrive;   // reuse: arrival counters are dead after the refit
-                if ((rc = exclusive_scan_u32(survive, new_index, ni, st)) != FTN_OK) break;
+                if ((rc = exclusive_scan_u32(is_record, new_index, ni, st)) != FTN_OK) break;
                 if ((e = cudaMemcpyAsync(&last_idx, new_index + ni - 1, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { rc = cuda_fail(e, "read scan", __FILE__, __LINE__); break; }
                 if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { rc = cuda_fail(e, "lbvh sync", __FILE__, __LINE__); break; }
                 s->n_nodes = last_idx + last_flag;
                 if (s->d_nodes) { cudaFree(s->d_nodes); s->d_nodes = nullptr; }
-                if ((e = cudaMalloc(&s->d_nodes, (size_t)s->n_nodes * 4 * sizeof(F4))) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc nodes", __FILE__, __LINE__); break; }
-                k_lbvh_emit<<<gi, 256, 0, st>>>((int)n, a, leaf_lo, leaf_hi, survive, new_index, s->d_nodes); count_launch();
+                if ((e = cudaMalloc(&s->d_nodes, (size_t)s->n_nodes * FTN_NODE_F4 * sizeof(F4))) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc nodes", __FILE__, __LINE__); break; }
+                k_lbvh_emit<<<gi, 256, 0, st>>>((int)n, a, leaf_lo, leaf_hi, survive, is_record, new_index, s->d_nodes); count_launch();
             }
             if ((e = cudaGetLastError()) != cudaSuccess) { rc = cuda_fail(e, "emit kernels", __FILE__, __LINE__); break; }
             BuildBounds hb;

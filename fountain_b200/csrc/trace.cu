@@ -12,8 +12,10 @@ namespace ftn {
 struct BatchSource {
     const FtnRay* rays;
     __device__ __forceinline__ bool load(uint32_t i, RayF* ray) const {
-        const float4 r0 = __ldg(reinterpret_cast<const float4*>(rays + i));
-        const float4 r1 = __ldg(reinterpret_cast<const float4*>(rays + i) + 1);
+        // rays and hits stream through once: evict-first (ld.global.cs / st.global.cs) so that they
+        // do not push BVH nodes and triangles out of the L2
+        const float4 r0 = __ldcs(reinterpret_cast<const float4*>(rays + i));
+        const float4 r1 = __ldcs(reinterpret_cast<const float4*>(rays + i) + 1);
         ray->o = V3(r0.x, r0.y, r0.z); ray->d = V3(r0.w, r1.x, r1.y); ray->t_max = r1.z; ray->time = r1.w;
         return true;
     }
@@ -28,7 +30,7 @@ struct BatchSink {
         if (h.slot == FTN_NO_HIT_SLOT) { prim = FTN_NO_HIT; t = ray.t_max; }
         else if (h.slot & FTN_SPHERE_SLOT_FLAG) prim = sc.n_tris + (h.slot & ~FTN_SPHERE_SLOT_FLAG);
         else { prim = f2u(ld4(sc.bvh.tris + 3 * (size_t)h.slot).w); b1 = h.tri.b1; b2 = h.tri.b2; }
-        reinterpret_cast<float4*>(hits)[i] = make_float4(__uint_as_float(prim), t, b1, b2);
+        __stcs(reinterpret_cast<float4*>(hits) + i, make_float4(__uint_as_float(prim), t, b1, b2));
     }
 };
 

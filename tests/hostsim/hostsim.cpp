@@ -138,7 +138,7 @@ SIM_API int sim_bvh_build(SimScene* s) {
         s->tris.resize(3 * (size_t)n);
         for (uint32_t i = 0; i < n; ++i) lbvh_gather_tri(s->pos.data(), s->idx.data(), s->order.data(), i, s->meshes.data(), (uint32_t)s->meshes.size(), s->tris.data());
         if (n <= (uint32_t)FTN_LEAF_MAX) {
-            s->nodes.resize(4); lbvh_emit_single(n, lo, hi, s->nodes.data()); s->n_nodes = 1;
+            s->nodes.resize(FTN_NODE_F4); lbvh_emit_single(n, lo, hi, s->nodes.data()); s->n_nodes = 1;
         } else {
             const size_t ni = n - 1;
             std::vector<uint32_t> left(ni), right(ni), first(ni), last(ni), parent(2 * (size_t)n - 1), arrive(ni, 0), survive(ni), new_index(ni);
@@ -156,9 +156,11 @@ SIM_API int sim_bvh_build(SimScene* s) {
             }
             for (size_t i = 0; i < ni; ++i) { if (arrive[i] != 2u) return fail(FTN_ERR_CUDA, "refit did not reach every node twice"); }
             uint32_t run = 0;
-            for (size_t i = 0; i < ni; ++i) { survive[i] = lbvh_survives(a, (int)i); new_index[i] = run; run += survive[i]; }   // survive + scan
-            s->n_nodes = run; s->nodes.resize(4 * (size_t)run);
-            for (size_t i = 0; i < ni; ++i) if (survive[i]) lbvh_emit_node(a, leaf_lo.data(), leaf_hi.data(), survive.data(), new_index.data(), (int)i, s->nodes.data());
+            for (size_t i = 0; i < ni; ++i) survive[i] = lbvh_survives(a, (int)i);                         // k_lbvh_survive
+            std::vector<uint32_t> is_record(ni);
+            for (size_t i = 0; i < ni; ++i) { is_record[i] = lbvh_is_record(a, survive.data(), (int)i); new_index[i] = run; run += is_record[i]; }   // mark + scan
+            s->n_nodes = run; s->nodes.resize((size_t)FTN_NODE_F4 * (size_t)run);
+            for (size_t i = 0; i < ni; ++i) if (is_record[i]) lbvh_emit_node(a, leaf_lo.data(), leaf_hi.data(), survive.data(), new_index.data(), (int)i, s->nodes.data());
         }
     }
     // sphere bounds + light preprocessing exactly as bvh_build() in scene.cu
@@ -191,7 +193,7 @@ SIM_API int sim_bvh_debug_morton(const SimScene* s, uint32_t* codes, uint32_t* o
 }
 SIM_API int sim_scene_world_bound(const SimScene* s, float out[6]) { std::memcpy(out, s->bounds, 24); return FTN_OK; }
 SIM_API int sim_scene_stats(const SimScene* s, FtnStats* st) {
-    std::memset(st, 0, sizeof(*st)); st->bvh_nodes = s->n_nodes; st->bvh_node_bytes = 64; st->bvh_tri_bytes = 48; return FTN_OK;
+    std::memset(st, 0, sizeof(*st)); st->bvh_nodes = s->n_nodes; st->bvh_node_bytes = FTN_NODE_BYTES; st->bvh_tri_bytes = 48; return FTN_OK;
 }
 
 static RayF to_rayf(const FtnRay& r) { RayF q; q.o = V3(r.o[0], r.o[1], r.o[2]); q.d = V3(r.d[0], r.d[1], r.d[2]); q.t_max = r.t_max; q.time = r.time; return q; }
@@ -307,7 +309,7 @@ SIM_API int sim_render(const SimScene* s, const FtnCamera* cam, const FtnFilm* f
         film_resolve_pixel(accum[i], &p);
         out_pixels[i].xyz[0] = p.x; out_pixels[i].xyz[1] = p.y; out_pixels[i].xyz[2] = p.z; out_pixels[i].filter_weight_sum = p.w;
     }
-    if (stats) { std::memset(stats, 0, sizeof(*stats)); stats->camera_samples = camera_samples; stats->rays_closest = rays_closest; stats->rays_any = rays_any; stats->bvh_nodes = s->n_nodes; stats->bvh_node_bytes = 64; stats->bvh_tri_bytes = 48; }
+    if (stats) { std::memset(stats, 0, sizeof(*stats)); stats->camera_samples = camera_samples; stats->rays_closest = rays_closest; stats->rays_any = rays_any; stats->bvh_nodes = s->n_nodes; stats->bvh_node_bytes = FTN_NODE_BYTES; stats->bvh_tri_bytes = 48; }
     if (err & ERR_NAN) return fail(FTN_ERR_NAN_RADIANCE, "NaN radiance");
     if (err & ERR_UNSUPPORTED) return fail(FTN_ERR_UNSUPPORTED, "unsupported");
     return FTN_OK;
