@@ -108,6 +108,7 @@ struct DirectOut {
     bool has_mis; V3 mis_o, mis_d, mis_w; int mis_light;
 };
 
+template <int MAT>
 FTN_HD void sample_direct(const SceneView& sc, const Surface& s, const Bsdf& bsdf, V3 scale,
                           uint64_t key, uint32_t dim0, DirectOut* out, uint32_t* err) {
     out->has_shadow = false; out->has_mis = false;
@@ -139,8 +140,8 @@ FTN_HD void sample_direct(const SceneView& sc, const Surface& s, const Bsdf& bsd
         p1 = ps.p; p1_err = ps.p_err; p1_n = ps.n;
     }
     if (ok && pdf > 0.0f && !is_black(Li)) {
-        const V3 f = bsdf_f(bsdf, s.wo, wi, flags) * abs_dot(wi, s.ns);
-        const float spdf = bsdf_pdf(bsdf, s.wo, wi, flags);
+        const V3 f = bsdf_f<MAT>(bsdf, s.wo, wi, flags) * abs_dot(wi, s.ns);
+        const float spdf = bsdf_pdf<MAT>(bsdf, s.wo, wi, flags);
         if (!is_black(f)) {
             // VisibilityTester -> SurfaceHit::spawn_ray_to_hit, interaction.rs:48-58
             const V3 origin = offset_ray_origin(s.p, s.p_err, s.n, x_sub(p1, s.p));
@@ -152,7 +153,7 @@ FTN_HD void sample_direct(const SceneView& sc, const Surface& s, const Bsdf& bsd
     }
     // --- BSDF sample ---
     ScatterSample bs;
-    if (bsdf_sample_f(bsdf, s.wo, us0, us1, flags, &bs)) {
+    if (bsdf_sample_f<MAT>(bsdf, s.wo, us0, us1, flags, &bs)) {
         const V3 f = bs.f * abs_dot(bs.wi, s.ns);
         if (is_black(f)) return;
         float lpdf;
@@ -174,6 +175,9 @@ struct ShadeOut {
 };
 
 // `ray` is the ray that produced `slot`; state/beta/L are the path's values on entry.
+// MAT = the material class of the queue this path sits in (FtnMaterialType), or -1 for the
+// null-BSDF queue.
+template <int MAT>
 FTN_HD void shade_surface(const SceneView& sc, const PassParams& pp, uint32_t path, const RayF& ray, uint32_t slot,
                           uint32_t state, V3 beta, V3 L, ShadeOut* out, uint32_t* err) {
     out->L = L; out->beta = beta; out->state = state; out->alive = false;
@@ -187,25 +191,26 @@ FTN_HD void shade_surface(const SceneView& sc, const PassParams& pp, uint32_t pa
         L = L + beta * area_emitted(sc.lights[s.light], s.n, direct_only ? s.wo : x_neg(ray.d));
     out->L = L;
     if (!direct_only && bounces >= pp.max_depth) return;   // path.rs:54
-    if (s.material < 0) {
+    if (MAT < 0) {
         // null BSDF: respawn in the same direction without counting a bounce (path.rs:76-80);
         // unimplemented!() under the direct-lighting integrator (direct_lighting.rs:98)
         if (direct_only) { flag_error(err, ERR_UNSUPPORTED); return; }
         out->alive = true; out->next_o = spawn_origin(s, ray.d); out->next_d = ray.d;
         return;
     }
+    constexpr int M = MAT < 0 ? 0 : MAT;
     Bsdf bsdf;
     bsdf_init(&bsdf, s.ns, s.n, s.sdpdu);
-    material_bsdf(sc.materials[s.material], &bsdf);
+    material_bsdf<M>(sc.materials[s.material], &bsdf);
     const uint64_t key = path_sample_key(pp, path, nullptr, nullptr);
     const uint32_t dim0 = DIM_CAMERA + (direct_only ? 0u : (uint32_t)DIM_PER_BOUNCE * (uint32_t)bounces);
-    if (bsdf_num_components(bsdf, BXDF_ALL & ~BXDF_SPECULAR) > 0)
-        sample_direct(sc, s, bsdf, direct_only ? v3s(1.0f) : beta, key, dim0, &out->direct, err);
+    if (bsdf_num_components<M>(bsdf, BXDF_ALL & ~BXDF_SPECULAR) > 0)
+        sample_direct<M>(sc, s, bsdf, direct_only ? v3s(1.0f) : beta, key, dim0, &out->direct, err);
     if (direct_only) return;
     // continuation: Bsdf::sample_f(wo, get_2d(), ALL), path.rs:68-76
     const float u0 = sampler_uniform(key, dim0 + 5), u1 = sampler_uniform(key, dim0 + 6);
     ScatterSample cs;
-    if (!bsdf_sample_f(bsdf, x_neg(ray.d), u0, u1, BXDF_ALL, &cs) || is_black(cs.f)) return;
+    if (!bsdf_sample_f<M>(bsdf, x_neg(ray.d), u0, u1, BXDF_ALL, &cs) || is_black(cs.f)) return;
     beta = beta * (cs.f * abs_dot(cs.wi, s.ns) / cs.pdf);
     const uint32_t spec = (cs.type & BXDF_SPECULAR) ? FTN_STATE_SPECULAR : 0u;
     const float mb = max_component(beta);

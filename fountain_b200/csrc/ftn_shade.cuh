@@ -207,15 +207,26 @@ FTN_HD bool is_inf(float f) { return fabsf(f) == FTN_INF; }
 enum { BXDF_REFLECTION = 1, BXDF_TRANSMISSION = 2, BXDF_DIFFUSE = 4, BXDF_GLOSSY = 8, BXDF_SPECULAR = 16, BXDF_ALL = 31 };
 
 // One lobe of a Bsdf (bsdf.rs holds up to 8 `dyn BxDF`; the in-scope materials produce at most 2).
+// KIND is a compile-time property of (material class, lobe slot): 0 LambertianReflection,
+// 1 MicrofacetReflection<TrowbridgeReitz, F>, -1 no such lobe.  Shading runs one kernel launch per
+// material class over its queue, so the class is a template argument and the matte kernel
+// contains no microfacet / Fresnel code at all (it used 167 registers when the lobe kind was a
+// run-time field).
 struct Lobe {
-    int kind;          // 0 LambertianReflection, 1 MicrofacetReflection<TrowbridgeReitz, F>
     V3 r;
     float ax, ay;
-    int fresnel;       // 0 FresnelConductor{1, eta, k}, 1 FresnelDielectric{1.5, 1.0}
     V3 eta, k;
 };
-FTN_HD int lobe_type(const Lobe& l) { return l.kind == 0 ? (BXDF_REFLECTION | BXDF_DIFFUSE) : (BXDF_REFLECTION | BXDF_GLOSSY); }
-FTN_HD bool lobe_matches(const Lobe& l, int flags) { const int t = lobe_type(l); return (flags & t) == t; }
+template <int MAT, int I> struct LobeKind { static constexpr int value = -1; };
+template <> struct LobeKind<FTN_MATERIAL_MATTE, 0> { static constexpr int value = 0; };
+template <> struct LobeKind<FTN_MATERIAL_METAL, 0> { static constexpr int value = 1; };
+template <> struct LobeKind<FTN_MATERIAL_PLASTIC, 0> { static constexpr int value = 0; };
+template <> struct LobeKind<FTN_MATERIAL_PLASTIC, 1> { static constexpr int value = 1; };
+// Fresnel of the microfacet lobe: 0 FresnelConductor{1, eta, k} (metal.rs:52-56), 1 FresnelDielectric{1.5, 1.0} (plastic.rs:34)
+template <int MAT> struct LobeFresnel { static constexpr int value = (MAT == FTN_MATERIAL_PLASTIC) ? 1 : 0; };
+
+template <int KIND> FTN_HD constexpr int lobe_type() { return KIND == 0 ? (BXDF_REFLECTION | BXDF_DIFFUSE) : (BXDF_REFLECTION | BXDF_GLOSSY); }
+template <int KIND> FTN_HD constexpr bool lobe_matches(int flags) { return KIND >= 0 && (flags & lobe_type<KIND>()) == lobe_type<KIND>(); }
 
 // microfacet.rs:135-160
 FTN_HD float tr_d(const Lobe& l, V3 wh) {
@@ -254,120 +265,131 @@ FTN_HD V3 tr_sample_wh(const Lobe& l, V3 wo, float u0, float u1) {
     const V3 wh = V3(sin_t * cosf(phi), sin_t * sinf(phi), cos_t);   // spherical_direction, math.rs:74-80
     return same_hemisphere(wo, wh) ? wh : -wh;
 }
-FTN_HD V3 lobe_fresnel(const Lobe& l, float cos_i) {
-    if (l.fresnel == 0) return fresnel_conductor(fabsf(cos_i), l.eta, l.k);   // fresnel.rs:70-73
-    return v3s(fresnel_dielectric(cos_i, 1.5f, 1.0f));                         // plastic.rs:34
+template <int FRESNEL> FTN_HD V3 lobe_fresnel(const Lobe& l, float cos_i) {
+    if (FRESNEL == 0) return fresnel_conductor(fabsf(cos_i), l.eta, l.k);   // fresnel.rs:70-73
+    return v3s(fresnel_dielectric(cos_i, 1.5f, 1.0f));
 }
-FTN_HD V3 lobe_f(const Lobe& l, V3 wo, V3 wi) {
-    if (l.kind == 0) return l.r * FTN_INV_PI;   // reflection/mod.rs:159-161
+template <int KIND, int FRESNEL> FTN_HD V3 lobe_f(const Lobe& l, V3 wo, V3 wi) {
+    if (KIND == 0) return l.r * FTN_INV_PI;   // reflection/mod.rs:159-161
     const float cos_o = abs_cos_theta(wo), cos_i = abs_cos_theta(wi);   // :318-336
     V3 wh = wi + wo;
     if (cos_i == 0.0f || cos_o == 0.0f || (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f)) return v3s(0.0f);
     wh = normalize(wh);
     const V3 whf = (wh.z < 0.0f) ? -wh : wh;   // faceforward(wh, (0,0,1)): dot = wh.z
-    const V3 F = lobe_fresnel(l, dot(wi, whf));
+    const V3 F = lobe_fresnel<FRESNEL>(l, dot(wi, whf));
     const float G = 1.0f / (1.0f + tr_lambda(l, wo) + tr_lambda(l, wi));   // microfacet.rs:21-23
     return l.r * tr_d(l, wh) * G * F / (4.0f * cos_i * cos_o);
 }
-FTN_HD float lobe_pdf(const Lobe& l, V3 wo, V3 wi) {
-    if (l.kind == 0) return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * FTN_INV_PI : 0.0f;   // :140-146
+template <int KIND> FTN_HD float lobe_pdf(const Lobe& l, V3 wo, V3 wi) {
+    if (KIND == 0) return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * FTN_INV_PI : 0.0f;   // :140-146
     if (!same_hemisphere(wo, wi)) return 0.0f;   // :354-360
     const V3 wh = normalize(wo + wi);
     return tr_pdf(l, wh) / (4.0f * dot(wo, wh));
 }
 struct ScatterSample { V3 f, wi; float pdf; int type; };
-FTN_HD bool lobe_sample_f(const Lobe& l, V3 wo, float u0, float u1, ScatterSample* s) {
-    if (l.kind == 0) {   // :131-138
+template <int KIND, int FRESNEL> FTN_HD bool lobe_sample_f(const Lobe& l, V3 wo, float u0, float u1, ScatterSample* s) {
+    if (KIND == 0) {   // :131-138
         V3 wi = cosine_sample_hemisphere(u0, u1);
         if (wo.z < 0.0f) wi.z *= -1.0f;
-        s->pdf = lobe_pdf(l, wo, wi); s->f = lobe_f(l, wo, wi); s->wi = wi; s->type = lobe_type(l);
+        s->pdf = lobe_pdf<KIND>(l, wo, wi); s->f = lobe_f<KIND, FRESNEL>(l, wo, wi); s->wi = wi; s->type = lobe_type<KIND>();
         return true;
     }
     const V3 wh = tr_sample_wh(l, wo, u0, u1);   // :338-352
     const V3 wi = reflect(wo, wh);
     if (!same_hemisphere(wo, wi)) return false;
     s->pdf = tr_pdf(l, wh) / (4.0f * dot(wo, wh));
-    s->f = lobe_f(l, wo, wi); s->wi = wi; s->type = lobe_type(l);
+    s->f = lobe_f<KIND, FRESNEL>(l, wo, wi); s->wi = wi; s->type = lobe_type<KIND>();
     return true;
 }
 
-// reflection/bsdf.rs:8-148
+// reflection/bsdf.rs:8-148.  `on[i]`: lobe slot i of this material class is present at run time
+// (matte with Kd == 0 or plastic with Kd / Ks == 0 drop the lobe, matte.rs:41, plastic.rs:28-33).
 struct Bsdf {
     V3 ns, ng, ss, ts;
-    Lobe lobes[2];
-    int n;
+    Lobe l0, l1;
+    bool on0, on1;
 };
 FTN_HD void bsdf_init(Bsdf* b, V3 ns, V3 ng, V3 shading_dpdu) {   // :31-46
     b->ns = ns; b->ng = ng;
     b->ss = x_normalize(shading_dpdu);
     b->ts = x_normalize(x_cross(ns, b->ss));
-    b->n = 0;
+    b->on0 = false; b->on1 = false;
 }
-FTN_HD int bsdf_num_components(const Bsdf& b, int flags) { int c = 0; for (int i = 0; i < b.n; ++i) if (lobe_matches(b.lobes[i], flags)) ++c; return c; }
+template <int MAT> FTN_HD int bsdf_num_components(const Bsdf& b, int flags) {
+    return (int)(b.on0 && lobe_matches<LobeKind<MAT, 0>::value>(flags)) + (int)(b.on1 && lobe_matches<LobeKind<MAT, 1>::value>(flags));
+}
 FTN_HD V3 bsdf_to_local(const Bsdf& b, V3 v) { return V3(dot(v, b.ss), dot(v, b.ts), dot(v, b.ns)); }
 FTN_HD V3 bsdf_to_world(const Bsdf& b, V3 v) {
     return V3(b.ss.x * v.x + b.ts.x * v.y + b.ns.x * v.z, b.ss.y * v.x + b.ts.y * v.y + b.ns.y * v.z, b.ss.z * v.x + b.ts.z * v.y + b.ns.z * v.z);
 }
-FTN_HD V3 bsdf_sum_f(const Bsdf& b, V3 wo, V3 wi, bool refl, int flags) {
+// Sum of f over the matching lobes that pass the reflect/transmit gate (all in-scope lobes are
+// REFLECTION lobes, so only `refl` opens the gate).
+template <int MAT> FTN_HD V3 bsdf_sum_f(const Bsdf& b, V3 wo, V3 wi, bool refl, int flags) {
+    constexpr int K0 = LobeKind<MAT, 0>::value, K1 = LobeKind<MAT, 1>::value, FR = LobeFresnel<MAT>::value;
     V3 sum = v3s(0.0f);
-    for (int i = 0; i < b.n; ++i) {
-        if (!lobe_matches(b.lobes[i], flags)) continue;
-        const int ty = lobe_type(b.lobes[i]);
-        if ((refl && (ty & BXDF_REFLECTION)) || (!refl && (ty & BXDF_TRANSMISSION))) sum = sum + lobe_f(b.lobes[i], wo, wi);
-    }
+    if (K0 >= 0 && b.on0 && lobe_matches<K0>(flags) && refl) sum = sum + lobe_f<K0 < 0 ? 0 : K0, FR>(b.l0, wo, wi);
+    if (K1 >= 0 && b.on1 && lobe_matches<K1>(flags) && refl) sum = sum + lobe_f<K1 < 0 ? 0 : K1, FR>(b.l1, wo, wi);
     return sum;
 }
-FTN_HD V3 bsdf_f(const Bsdf& b, V3 wo_w, V3 wi_w, int flags) {   // :67-82
+template <int MAT> FTN_HD V3 bsdf_f(const Bsdf& b, V3 wo_w, V3 wi_w, int flags) {   // :67-82
     const V3 wi = bsdf_to_local(b, wi_w), wo = bsdf_to_local(b, wo_w);
     if (wo.z == 0.0f) return v3s(0.0f);
     const bool refl = dot(wi_w, b.ng) * dot(wo_w, b.ng) > 0.0f;
-    return bsdf_sum_f(b, wo, wi, refl, flags);
+    return bsdf_sum_f<MAT>(b, wo, wi, refl, flags);
 }
-FTN_HD float bsdf_pdf(const Bsdf& b, V3 wo_w, V3 wi_w, int flags) {   // :131-144
+template <int MAT> FTN_HD float bsdf_pdf(const Bsdf& b, V3 wo_w, V3 wi_w, int flags) {   // :131-144
+    constexpr int K0 = LobeKind<MAT, 0>::value, K1 = LobeKind<MAT, 1>::value;
     const V3 wo = bsdf_to_local(b, wo_w), wi = bsdf_to_local(b, wi_w);
     if (wo.z == 0.0f) return 0.0f;
     float p = 0.0f; int nm = 0;
-    for (int i = 0; i < b.n; ++i) if (lobe_matches(b.lobes[i], flags)) { p += lobe_pdf(b.lobes[i], wo, wi); ++nm; }
+    if (K0 >= 0 && b.on0 && lobe_matches<K0>(flags)) { p += lobe_pdf<K0 < 0 ? 0 : K0>(b.l0, wo, wi); ++nm; }
+    if (K1 >= 0 && b.on1 && lobe_matches<K1>(flags)) { p += lobe_pdf<K1 < 0 ? 0 : K1>(b.l1, wo, wi); ++nm; }
     return nm > 0 ? p / (float)nm : 0.0f;
 }
-FTN_HD bool bsdf_sample_f(const Bsdf& b, V3 wo_w, float u0, float u1, int flags, ScatterSample* out) {   // :85-129
-    const int nm = bsdf_num_components(b, flags);
+template <int MAT> FTN_HD bool bsdf_sample_f(const Bsdf& b, V3 wo_w, float u0, float u1, int flags, ScatterSample* out) {   // :85-129
+    constexpr int K0 = LobeKind<MAT, 0>::value, K1 = LobeKind<MAT, 1>::value, FR = LobeFresnel<MAT>::value;
+    const bool m0 = K0 >= 0 && b.on0 && lobe_matches<K0>(flags), m1 = K1 >= 0 && b.on1 && lobe_matches<K1>(flags);
+    const int nm = (int)m0 + (int)m1;
     if (nm == 0) return false;
     const float matching = (float)nm;
     const int comp = (int)fminf(floorf(u0 * matching), matching - 1.0f);
-    int which = -1, cnt = comp;
-    for (int i = 0; i < b.n; ++i) if (lobe_matches(b.lobes[i], flags)) { if (cnt-- == 0) { which = i; break; } }
+    // the comp-th matching lobe: slot 0 if it matches and comp == 0, otherwise slot 1
+    const bool pick0 = m0 && comp == 0;
     const float ur0 = u0 * matching - (float)comp;
     const V3 wo = bsdf_to_local(b, wo_w);
     ScatterSample s;
-    if (!lobe_sample_f(b.lobes[which], wo, ur0, u1, &s)) return false;
+    bool ok;
+    if (pick0) ok = lobe_sample_f<K0 < 0 ? 0 : K0, FR>(b.l0, wo, ur0, u1, &s);
+    else ok = lobe_sample_f<K1 < 0 ? 0 : K1, FR>(b.l1, wo, ur0, u1, &s);
+    if (!ok) return false;
     if (s.pdf == 0.0f) return false;
     const V3 wi = s.wi;
     const V3 wi_w = bsdf_to_world(b, wi);
     float pdf = s.pdf;
     if (nm > 1) {
-        for (int i = 0; i < b.n; ++i) if (i != which && lobe_matches(b.lobes[i], flags)) pdf += lobe_pdf(b.lobes[i], wo, wi);
+        if (pick0) pdf += lobe_pdf<K1 < 0 ? 0 : K1>(b.l1, wo, wi);
+        else pdf += lobe_pdf<K0 < 0 ? 0 : K0>(b.l0, wo, wi);
         pdf /= matching;
     }
     const bool refl = dot(wi_w, b.ng) * dot(wo_w, b.ng) > 0.0f;
-    out->f = bsdf_sum_f(b, wo, wi, refl, flags);
+    out->f = bsdf_sum_f<MAT>(b, wo, wi, refl, flags);
     out->wi = wi_w; out->pdf = pdf; out->type = s.type;
     return true;
 }
 
 // Material::compute_scattering_functions: matte.rs:36-52, metal.rs:38-65, plastic.rs:24-48
-FTN_HD void material_bsdf(const MaterialData& m, Bsdf* b) {
-    if (m.type == FTN_MATERIAL_MATTE) {
+template <int MAT> FTN_HD void material_bsdf(const MaterialData& m, Bsdf* b) {
+    if (MAT == FTN_MATERIAL_MATTE) {
         const V3 r = V3(clampf(m.kd[0], 0.0f, FTN_INF), clampf(m.kd[1], 0.0f, FTN_INF), clampf(m.kd[2], 0.0f, FTN_INF));
-        if (!is_black(r)) { Lobe& l = b->lobes[b->n++]; l.kind = 0; l.r = r; }
-    } else if (m.type == FTN_MATERIAL_METAL) {
-        Lobe& l = b->lobes[b->n++];
-        l.kind = 1; l.r = v3s(1.0f); l.ax = m.alpha_x; l.ay = m.alpha_y; l.fresnel = 0;
-        l.eta = V3(m.eta[0], m.eta[1], m.eta[2]); l.k = V3(m.k[0], m.k[1], m.k[2]);
+        if (!is_black(r)) { b->on0 = true; b->l0.r = r; }
+    } else if (MAT == FTN_MATERIAL_METAL) {
+        b->on0 = true;
+        b->l0.r = v3s(1.0f); b->l0.ax = m.alpha_x; b->l0.ay = m.alpha_y;
+        b->l0.eta = V3(m.eta[0], m.eta[1], m.eta[2]); b->l0.k = V3(m.k[0], m.k[1], m.k[2]);
     } else {
         const V3 kd = V3(m.kd[0], m.kd[1], m.kd[2]), ks = V3(m.ks[0], m.ks[1], m.ks[2]);
-        if (!is_black(kd)) { Lobe& l = b->lobes[b->n++]; l.kind = 0; l.r = kd; }
-        if (!is_black(ks)) { Lobe& l = b->lobes[b->n++]; l.kind = 1; l.r = ks; l.ax = m.alpha_x; l.ay = m.alpha_x; l.fresnel = 1; l.eta = v3s(0.0f); l.k = v3s(0.0f); }
+        if (!is_black(kd)) { b->on0 = true; b->l0.r = kd; }
+        if (!is_black(ks)) { b->on1 = true; b->l1.r = ks; b->l1.ax = m.alpha_x; b->l1.ay = m.alpha_x; b->l1.eta = v3s(0.0f); b->l1.k = v3s(0.0f); }
     }
 }
 

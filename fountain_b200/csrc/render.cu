@@ -159,7 +159,7 @@ k_shade(SceneView sc, PassParams pp, PathArrays pa, const uint32_t* __restrict__
             path = queue[k];
             const RayF ray = load_ray(pa, path);
             ShadeOut o;
-            shade_surface(sc, pp, path, ray, pa.hit[path], pa.state[path], ld3(pa.beta, path), ld3(pa.L, path), &o, err);
+            shade_surface<QUEUE == Q_NULL ? -1 : QUEUE - Q_MAT0>(sc, pp, path, ray, pa.hit[path], pa.state[path], ld3(pa.beta, path), ld3(pa.L, path), &o, err);
             st3(pa.L, path, o.L);
             if (o.direct.has_shadow) { st3(pa.sh_o, path, o.direct.sh_o); st3(pa.sh_d, path, o.direct.sh_d); st3(pa.sh_L, path, o.direct.sh_L); t_shadow = Q_SHADOW; }
             if (o.direct.has_mis) {

@@ -282,7 +282,14 @@ SIM_API int sim_render(const SimScene* s, const FtnCamera* cam, const FtnFilm* f
                     break;
                 }
                 ShadeOut o;
-                shade_surface(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err);   // k_shade<...>
+                const int material = hit_material(sc, h.slot);   // the queue k_extend would bin this path into
+                const int mclass = material < 0 ? -1 : sc.materials[material].type;
+                switch (mclass) {   // k_shade<QUEUE>
+                    case FTN_MATERIAL_MATTE: shade_surface<FTN_MATERIAL_MATTE>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err); break;
+                    case FTN_MATERIAL_METAL: shade_surface<FTN_MATERIAL_METAL>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err); break;
+                    case FTN_MATERIAL_PLASTIC: shade_surface<FTN_MATERIAL_PLASTIC>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err); break;
+                    default: shade_surface<-1>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err); break;
+                }
                 Lp = o.L;
                 if (o.direct.has_shadow) {   // k_shadow
                     RayF sr; sr.o = o.direct.sh_o; sr.d = o.direct.sh_d; sr.t_max = rn_sub(1.0f, 0.0001f); sr.time = ray.time;
@@ -344,11 +351,14 @@ SIM_API void sim_kat_bsdf(const FtnMaterial* m, const float wo[3], const float w
     FtnSceneDesc d; std::memset(&d, 0, sizeof(d)); d.abi_version = FTN_ABI_VERSION; d.materials = m; d.n_materials = 1;
     SimScene* s; sim_scene_create(&d, &s);
     Bsdf b; bsdf_init(&b, V3(0, 0, 1), V3(0, 0, 1), V3(1, 0, 0));
-    material_bsdf(s->mats[0], &b);
     const V3 o(wo[0], wo[1], wo[2]), i(wi[0], wi[1], wi[2]);
-    const V3 f = bsdf_f(b, o, i, BXDF_ALL);
-    out[0] = f.x; out[1] = f.y; out[2] = f.z; out[3] = bsdf_pdf(b, o, i, BXDF_ALL);
-    ScatterSample sm; const bool ok = bsdf_sample_f(b, o, u[0], u[1], BXDF_ALL, &sm);
+    V3 f; float pdf; ScatterSample sm; bool ok;
+#define SIM_BSDF(M) { material_bsdf<M>(s->mats[0], &b); f = bsdf_f<M>(b, o, i, BXDF_ALL); pdf = bsdf_pdf<M>(b, o, i, BXDF_ALL); ok = bsdf_sample_f<M>(b, o, u[0], u[1], BXDF_ALL, &sm); }
+    if (m->type == FTN_MATERIAL_MATTE) SIM_BSDF(FTN_MATERIAL_MATTE)
+    else if (m->type == FTN_MATERIAL_METAL) SIM_BSDF(FTN_MATERIAL_METAL)
+    else SIM_BSDF(FTN_MATERIAL_PLASTIC)
+#undef SIM_BSDF
+    out[0] = f.x; out[1] = f.y; out[2] = f.z; out[3] = pdf;
     out[4] = ok ? 1.0f : 0.0f;
     if (ok) { out[5] = sm.f.x; out[6] = sm.f.y; out[7] = sm.f.z; out[8] = sm.wi.x; out[9] = sm.wi.y; out[10] = sm.wi.z; out[11] = sm.pdf; }
     else for (int k = 5; k < 12; ++k) out[k] = 0.0f;
