@@ -56,13 +56,23 @@ FTN_HD uint64_t path_sample_key(const PassParams& pp, uint32_t path, int* x_out,
     return sampler_sample_key(pp.seed_key, sample_index);
 }
 
+// true when the footprint of a film sample (film.rs:138-141) is anything but exactly the pixel
+// (x, y) the sample was generated for
+FTN_HD bool film_sample_spills(const FilmGeom& f, int x, int y, float fx, float fy) {
+    const float dx = rn_sub(fx, 0.5f), dy = rn_sub(fy, 0.5f);
+    const int p0x = (int)ceilf(rn_sub(dx, f.radius[0])), p1x = (int)floorf(rn_add(dx, f.radius[0])) + 1;
+    const int p0y = (int)ceilf(rn_sub(dy, f.radius[1])), p1y = (int)floorf(rn_add(dy, f.radius[1])) + 1;
+    return !(p0x == x && p1x == x + 1 && p0y == y && p1y == y + 1);
+}
+
 // Sampler::get_camera_sample (sampler/mod.rs:43-51) + Camera::generate_ray
-FTN_HD RayF raygen_path(const PassParams& pp, uint32_t path, float* fx, float* fy) {
+FTN_HD RayF raygen_path(const PassParams& pp, uint32_t path, float* fx, float* fy, bool* spills) {
     int x, y;
     const uint64_t key = path_sample_key(pp, path, &x, &y);
     const float jx = sampler_uniform(key, 0), jy = sampler_uniform(key, 1);
     const float lx = sampler_uniform(key, 2), ly = sampler_uniform(key, 3), tu = sampler_uniform(key, 4);
     *fx = rn_add((float)x, jx); *fy = rn_add((float)y, jy);
+    *spills = film_sample_spills(pp.film, x, y, *fx, *fy);
     return camera_ray(pp.cam, *fx, *fy, lx, ly, tu);
 }
 
@@ -246,7 +256,10 @@ FTN_HD int imax(int a, int b) { return a > b ? a : b; }
 // samples of this pass, gathered in a fixed order (sample rows, sample columns, samples).  The
 // footprint is p0 = ceil(pd - r), p1 = floor(pd + r) + 1 clipped to the pixel bounds of the
 // sample's 16x16 tile (get_film_tile, film.rs:95-113, including its `- radius` in p1y).
-FTN_HD void film_gather_pixel(const PassParams& pp, const float2* p_film, const float4* Lbuf, int i, int reach,
+// `spill[sample pixel]` != 0 marks sample pixels with at least one sample whose footprint is not
+// exactly its own pixel (for the box filter of radius 0.5 that only happens when x + jitter rounds
+// to x or x + 1); neighbours without the mark are skipped without reading their samples.
+FTN_HD void film_gather_pixel(const PassParams& pp, const float2* p_film, const float4* Lbuf, const uint8_t* spill, int i, int reach,
                               float4* acc_io, uint32_t* err) {
     const FilmGeom& f = pp.film;
     const int fw = f.crop_max[0] - f.crop_min[0];
@@ -263,7 +276,9 @@ FTN_HD void film_gather_pixel(const PassParams& pp, const float2* p_film, const 
             const int tp0x = imax(iceil(rn_sub(rn_sub((float)tx0, 0.5f), f.radius[0])), f.crop_min[0]);
             const int tp1x = imin(iceil(rn_add(rn_add(rn_sub((float)tx1, 0.5f), f.radius[0]), 1.0f)), f.crop_max[0]);
             if (px < tp0x || px >= tp1x) continue;
-            const uint32_t base = ((uint32_t)(sy - f.sb_min[1]) * (uint32_t)sbw + (uint32_t)(sx - f.sb_min[0])) * (uint32_t)pp.s_count;
+            const uint32_t spix = (uint32_t)(sy - f.sb_min[1]) * (uint32_t)sbw + (uint32_t)(sx - f.sb_min[0]);
+            if ((sx != px || sy != py) && !spill[spix]) continue;
+            const uint32_t base = spix * (uint32_t)pp.s_count;
             for (int s = 0; s < pp.s_count; ++s) {
                 const float2 pf = p_film[base + s];
                 const float dx = rn_sub(pf.x, 0.5f), dy = rn_sub(pf.y, 0.5f);

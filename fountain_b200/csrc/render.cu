@@ -44,6 +44,7 @@ struct PathArrays {
     float4* mis_d;      // MIS ray dir
     float4* mis_w;      // weight rgb, light index (bits)
     float2* p_film;     // CameraSample.p_film
+    uint8_t* spill;     // per sample pixel: some sample's footprint is not exactly its own pixel
 };
 
 __device__ __forceinline__ V3 ld3(const float4* p, size_t i) { const float4 v = p[i]; return V3(v.x, v.y, v.z); }
@@ -85,8 +86,9 @@ __global__ void __launch_bounds__(256)
 k_raygen(PassParams pp, PathArrays pa) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pp.n_paths) return;
-    float fx, fy;
-    const RayF ray = raygen_path(pp, i, &fx, &fy);
+    float fx, fy; bool spills;
+    const RayF ray = raygen_path(pp, i, &fx, &fy, &spills);
+    if (spills) pa.spill[i / (uint32_t)pp.s_count] = 1;   // benign race: every writer stores 1
     st3(pa.ray_o, i, ray.o, ray.time);
     st3(pa.ray_d, i, ray.d, ray.t_max);
     st3(pa.beta, i, v3s(1.0f));
@@ -106,14 +108,18 @@ struct PathRaySource {
     }
 };
 struct ExtendSink {
-    SceneView sc; PathArrays pa; const uint32_t* queue; Queues qs; uint32_t* counts;
+    SceneView sc; PathArrays pa; const uint32_t* queue; Queues qs; uint32_t* counts; bool miss_always;
     __device__ __forceinline__ void store(bool valid, uint32_t k, const RayF&, const SceneHit& h) const {
         int target = -1; uint32_t path = 0;
         if (valid) {
             path = queue ? queue[k] : k;
             pa.hit[path] = h.slot;
-            if (h.slot == FTN_NO_HIT_SLOT) target = Q_MISS;
-            else {
+            if (h.slot == FTN_NO_HIT_SLOT) {
+                // an escaped path adds environment radiance only at bounce 0 or after a specular bounce
+                // (path.rs:45-51); otherwise it simply ends here and needs no miss kernel
+                const uint32_t st = pa.state[path];
+                if (miss_always || (st & FTN_STATE_BOUNCES) == 0u || (st & FTN_STATE_SPECULAR)) target = Q_MISS;
+            } else {
                 const int material = hit_material(sc, h.slot);
                 target = (material < 0) ? Q_NULL : (Q_MAT0 + sc.materials[material].type);
             }
@@ -124,9 +130,9 @@ struct ExtendSink {
 template <bool COUNT, bool SPH>
 __global__ void __launch_bounds__(FTN_TRACE_THREADS)
 k_extend(SceneView sc, PathArrays pa, const uint32_t* __restrict__ queue_in, uint32_t n_in, Queues qs, uint32_t* __restrict__ counts,
-         unsigned long long* __restrict__ trav) {
+         unsigned long long* __restrict__ trav, bool miss_always) {
     PathRaySource src; src.pa = pa; src.queue = queue_in;
-    ExtendSink sink; sink.sc = sc; sink.pa = pa; sink.queue = queue_in; sink.qs = qs; sink.counts = counts;
+    ExtendSink sink; sink.sc = sc; sink.pa = pa; sink.queue = queue_in; sink.qs = qs; sink.counts = counts; sink.miss_always = miss_always;
     TraceCounters tc; tc.nodes = 0; tc.tris = 0;
     trace_persistent<false, COUNT, SPH>(sc, n_in, &counts[W_EXTEND], src, sink, tc);
     if (COUNT) flush_trace_counters(tc, trav);
@@ -246,7 +252,7 @@ k_film_accumulate(PassParams pp, PathArrays pa, float4* __restrict__ accum, int 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= fw * fh) return;
     float4 acc = accum[i];
-    film_gather_pixel(pp, pa.p_film, pa.L, i, reach, &acc, err);
+    film_gather_pixel(pp, pa.p_film, pa.L, pa.spill, i, reach, &acc, err);
     accum[i] = acc;
 }
 
@@ -357,7 +363,7 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
     FTN_CUDA(cudaEventRecord(ev0, st));
 
     const size_t ws_bytes = 10 * (P * sizeof(float4) + 256) + 2 * (P * 4 + 256) + P * sizeof(float2) + 256 +
-                            (size_t)fw * fh * sizeof(float4) + 256 + (size_t)(Q_COUNT + 1) * (P * 4 + 256) + 4096;
+                            (size_t)fw * fh * sizeof(float4) + 256 + (size_t)(Q_COUNT + 1) * (P * 4 + 256) + n_spix + 4096;
     Carver cv; 
     FTN_TRY(workspace_reserve(s, ws_bytes, &cv.p));
     PathArrays pa;
@@ -365,6 +371,7 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
     pa.sh_o = cv.take<float4>(P); pa.sh_d = cv.take<float4>(P); pa.sh_L = cv.take<float4>(P);
     pa.mis_o = cv.take<float4>(P); pa.mis_d = cv.take<float4>(P); pa.mis_w = cv.take<float4>(P);
     pa.hit = cv.take<uint32_t>(P); pa.state = cv.take<uint32_t>(P); pa.p_film = cv.take<float2>(P);
+    pa.spill = cv.take<uint8_t>(n_spix);
     float4* accum = cv.take<float4>((size_t)fw * fh);
     Queues qs;
     for (int q = 0; q < Q_COUNT; ++q) qs.q[q] = cv.take<uint32_t>(P);
@@ -396,6 +403,7 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
         pp.s_first = smp->sample_begin + done * smp->sample_stride;
         pp.s_count = sc_n;
         pp.n_paths = (uint32_t)(n_spix * (size_t)sc_n);
+        FTN_CUDA(cudaMemsetAsync(pa.spill, 0, n_spix, st));
         k_raygen<<<(pp.n_paths + 255) / 256, 256, 0, st>>>(pp, pa);
         FTN_LAUNCHED();
         camera_samples += pp.n_paths;
@@ -409,7 +417,7 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
             Queues q = qs; q.q[Q_ACTIVE_OUT] = q_out;
             const unsigned ge = trace_grid(n_active, FTN_TRACE_BLOCKS_PER_SM);
             timer.begin(0);
-            FTN_BOOL2(count_traversal, sph, (k_extend<B0, B1><<<ge, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q_in, n_active, q, counts, d_trav)));
+            FTN_BOOL2(count_traversal, sph, (k_extend<B0, B1><<<ge, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q_in, n_active, q, counts, d_trav, integ->type == FTN_INTEGRATOR_DIRECT_LIGHTING)));
             timer.end();
             FTN_LAUNCHED();
             class_rays[0] += n_active;

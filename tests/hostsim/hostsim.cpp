@@ -252,7 +252,7 @@ SIM_API int sim_render(const SimScene* s, const FtnCamera* cam, const FtnFilm* f
     int s_per_pass = (int)std::max<size_t>(1, ((size_t)1 << 16) / std::max<size_t>(1, n_spix));   // small passes: exercises multi-pass accumulation
     s_per_pass = std::min(s_per_pass, std::max(1, n_samples));
     const size_t P = n_spix * (size_t)s_per_pass;
-    std::vector<float4> L(P); std::vector<float2> pfilm(P);
+    std::vector<float4> L(P); std::vector<float2> pfilm(P); std::vector<uint8_t> spill(n_spix);
     std::vector<float4> accum((size_t)fw * fh, make_float4(0, 0, 0, 0));
     const SceneView sc = s->view();
     uint32_t err = 0;
@@ -266,9 +266,11 @@ SIM_API int sim_render(const SimScene* s, const FtnCamera* cam, const FtnFilm* f
     for (int done = 0; done < n_samples; done += s_per_pass) {
         const int sc_n = std::min(s_per_pass, n_samples - done);
         pp.s_first = smp->sample_begin + done * smp->sample_stride; pp.s_count = sc_n; pp.n_paths = (uint32_t)(n_spix * (size_t)sc_n);
+        std::fill(spill.begin(), spill.end(), 0);
         for (uint32_t path = 0; path < pp.n_paths; ++path) {
-            float fx, fy;
-            RayF ray = raygen_path(pp, path, &fx, &fy);   // k_raygen
+            float fx, fy; bool spills;
+            RayF ray = raygen_path(pp, path, &fx, &fy, &spills);   // k_raygen
+            if (spills) spill[path / (uint32_t)pp.s_count] = 1;
             pfilm[path] = make_float2(fx, fy);
             V3 Lp = v3s(0.0f), beta = v3s(1.0f); uint32_t state = 0;
             ++camera_samples;
@@ -309,7 +311,7 @@ SIM_API int sim_render(const SimScene* s, const FtnCamera* cam, const FtnFilm* f
             }
             L[path] = make_float4(Lp.x, Lp.y, Lp.z, 0.0f);
         }
-        for (int i = 0; i < fw * fh; ++i) film_gather_pixel(pp, pfilm.data(), L.data(), i, reach, &accum[i], &err);   // k_film_accumulate
+        for (int i = 0; i < fw * fh; ++i) film_gather_pixel(pp, pfilm.data(), L.data(), spill.data(), i, reach, &accum[i], &err);   // k_film_accumulate
     }
     for (int i = 0; i < fw * fh; ++i) {   // k_film_resolve into a zeroed film
         float4 p = make_float4(0, 0, 0, 0);
