@@ -182,6 +182,9 @@ def run_ours_render(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL's version banner (NCCL_DEBUG=VERSION on the box) goes to stdout by default;
+        # stdout carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -341,6 +344,7 @@ def run_ours_raybatch(args):
     gpu = api.default_backend()
     gpu.call("set_device", local_rank)
     n_lon = int(round(args.tris ** 0.5)); side = (n_lon, n_lon // 2)          # n_lon * n_lat * 2 triangles
+    scenes.synthetic_mesh_scene(side[0], side[1], backend=gpu, resolution=(2048, 2048))[0].close()   # warm: module load, mesh cache
     t0 = time.perf_counter()
     scene, camera = scenes.synthetic_mesh_scene(side[0], side[1], backend=gpu, resolution=(2048, 2048))
     build_wall = time.perf_counter() - t0

@@ -1,6 +1,7 @@
 """Builders for the workloads BASELINE.json names.  Pure host-side
 scene description (numpy) -- the same arrays feed the CUDA library and, in tests, the oracle.
 """
+import functools
 import math
 import os
 
@@ -54,6 +55,7 @@ def _hash01(ix, iy, seed):
     return x.astype(np.float64) / 4294967296.0
 
 
+@functools.lru_cache(maxsize=4)
 def displaced_sphere_mesh(n_lon, n_lat, radius=10.0, amplitude=0.05, seed=1, with_normals=True):
     """Lat-long grid of n_lon x n_lat quads x 2 triangles (1000 x 500 -> 1M tris).
     Radius is scaled by 1 + amplitude * smooth value noise so the BVH is not trivial.  Poles are
@@ -149,6 +151,7 @@ def diffuse_bounce_batch(rays, hits, positions, indices, seed=2):
 
 
 # ---- C4: "Rust-logo-style": gear-ring mesh, TR metal, thin lens, image env -----------------------
+@functools.lru_cache(maxsize=4)
 def gear_ring_mesh(n_teeth=48, seg_per_tooth=16, n_height=24, n_radial=24, r_in=4.0, r_out=7.0, tooth=0.8,
                    height=1.5):
     """Extruded gear ring (outer wall with teeth, inner wall, top and bottom annuli), uniformly
@@ -191,6 +194,7 @@ def gear_ring_mesh(n_teeth=48, seg_per_tooth=16, n_height=24, n_radial=24, r_in=
     return np.concatenate(verts).astype(np.float32), np.concatenate(tris).astype(np.uint32)
 
 
+@functools.lru_cache(maxsize=4)
 def sky_sun_envmap(width=2048, height=1024, seed=3, peak=1.0e4):
     """Procedural lat-long sky + sun map (the reference's HDR is not in the repository)."""
     rng = np.random.default_rng(seed)
