@@ -50,28 +50,46 @@ struct BvhView {
     uint32_t n_tris;
 };
 
+#ifndef FTN_PREFETCH_CHILDREN
+#define FTN_PREFETCH_CHILDREN 0
+#endif
 #if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 FTN_HD F4 ld4(const F4* p) {
     float4 v = __ldg(reinterpret_cast<const float4*>(p));
     F4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r;
 }
+// One 256-bit read-only load (LDG.E.256, sm_100+) of two consecutive F4; p must be 32-byte aligned.
+// ncu on the 128-bit version showed the traversal kernels bound by the L1 data pipe
+// (l1tex__data_pipe_lsu_wavefronts 90 % of peak): every lane reads its own node, so each load
+// instruction costs one L1 wavefront PER LANE however few bytes it moves -- halving the number of
+// load instructions per node halves that traffic.
+__device__ __forceinline__ void ld8(const F4* p, F4& a, F4& b) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
 #else
 FTN_HD F4 ld4(const F4* p) { return *p; }
+FTN_HD void ld8(const F4* p, F4& a, F4& b) { a = p[0]; b = p[1]; }
 #endif
 
-struct RaySlab { V3 o; V3 inv_d; float widen; };
+// `nan_free`: every component of 1/d is finite and non-zero, so (bound - o) * (1/d) can never be
+// 0 * inf = NaN and the cheaper, bit-identical form of the slab test below applies.
+struct RaySlab { V3 o; V3 inv_d; float widen; bool nan_free; };
+FTN_HD bool slab_component_regular(float v) { return v != 0.0f && fabsf(v) <= 3.402823466e+38f; }   // finite, non-zero, not NaN
 FTN_HD RaySlab make_ray_slab(V3 o, V3 d) {
     RaySlab s; s.o = o;
     s.inv_d = V3(rn_div(1.0f, d.x), rn_div(1.0f, d.y), rn_div(1.0f, d.z));
     s.widen = rn_add(1.0f, rn_mul(2.0f, gamma_n(3)));
+    s.nan_free = slab_component_regular(s.inv_d.x) && slab_component_regular(s.inv_d.y) && slab_component_regular(s.inv_d.z);
     return s;
 }
 // bounds.rs:214-233 for one box given as (lo,hi) per axis; returns hit and the entry distance.
 // Branch-free: the reference returns early as soon as t0 > t1; t0 only grows and t1 only shrinks
 // (f32::max/min ignore NaNs, like fmaxf/fminf), so testing once at the end accepts exactly the
 // same boxes without divergent branches inside the warp.
-FTN_HD bool slab_test(const RaySlab& r, float lox, float hix, float loy, float hiy, float loz, float hiz,
-                      float t_max, float* t_entry) {
+FTN_HD bool slab_test_exact(const RaySlab& r, float lox, float hix, float loy, float hiy, float loz, float hiz,
+                            float t_max, float* t_entry) {
     const float ax = rn_mul(rn_sub(lox, r.o.x), r.inv_d.x), bx = rn_mul(rn_sub(hix, r.o.x), r.inv_d.x);
     const float ay = rn_mul(rn_sub(loy, r.o.y), r.inv_d.y), by = rn_mul(rn_sub(hiy, r.o.y), r.inv_d.y);
     const float az = rn_mul(rn_sub(loz, r.o.z), r.inv_d.z), bz = rn_mul(rn_sub(hiz, r.o.z), r.inv_d.z);
@@ -84,6 +102,27 @@ FTN_HD bool slab_test(const RaySlab& r, float lox, float hix, float loy, float h
     const float t1 = fminf(fminf(fminf(t_max, fx), fy), fz);
     *t_entry = t0;
     return !(t0 > t1);
+}
+// The same test for a ray with r.nan_free: without NaNs the swap is min/max, and because
+// x -> round(x * widen) is monotone (widen > 0) the three widened far distances share one multiply:
+// min(fx*w, fy*w, fz*w) == min(fx, fy, fz)*w bit for bit.  Identical accept/reject and entry
+// distance as slab_test_exact (tests/test_hostsim_parity.py checks both forms against the oracle).
+FTN_HD bool slab_test_nan_free(const RaySlab& r, float lox, float hix, float loy, float hiy, float loz, float hiz,
+                               float t_max, float* t_entry) {
+    const float ax = rn_mul(rn_sub(lox, r.o.x), r.inv_d.x), bx = rn_mul(rn_sub(hix, r.o.x), r.inv_d.x);
+    const float ay = rn_mul(rn_sub(loy, r.o.y), r.inv_d.y), by = rn_mul(rn_sub(hiy, r.o.y), r.inv_d.y);
+    const float az = rn_mul(rn_sub(loz, r.o.z), r.inv_d.z), bz = rn_mul(rn_sub(hiz, r.o.z), r.inv_d.z);
+    const float t0 = fmaxf(fmaxf(fmaxf(0.0f, fminf(ax, bx)), fminf(ay, by)), fminf(az, bz));
+    const float far_ = rn_mul(fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)), r.widen);
+    const float t1 = fminf(t_max, far_);
+    *t_entry = t0;
+    return !(t0 > t1);
+}
+template <bool NAN_FREE>
+FTN_HD bool slab_test(const RaySlab& r, float lox, float hix, float loy, float hiy, float loz, float hiz,
+                      float t_max, float* t_entry) {
+    return NAN_FREE ? slab_test_nan_free(r, lox, hix, loy, hiy, loz, hiz, t_max, t_entry)
+                    : slab_test_exact(r, lox, hix, loy, hiy, loz, hiz, t_max, t_entry);
 }
 
 struct TraceCounters { uint32_t nodes, tris; };
@@ -99,7 +138,8 @@ FTN_HD void cswap(float& ka, int& va, float& kb, int& vb) {   // compare-exchang
 // entered child (the others are pushed far-to-near), or a popped entry, or FTN_TRAVERSAL_DONE.
 // Front-to-back by entry distance (the reference orders by split-axis sign, bvh.rs:194-201; the
 // order only decides which of two exactly tied hits is kept).
-FTN_HD int node_step(const BvhView& bvh, int cur, const RaySlab& slab, float t_max, int* stack, int& sp) {
+template <bool NAN_FREE>
+FTN_HD int node_step_impl(const BvhView& bvh, int cur, const RaySlab& slab, float t_max, int* stack, int& sp) {
     const F4* nd = bvh.nodes + (size_t)FTN_NODE_F4 * (size_t)cur;
 #if FTN_BVH_WIDTH == 4
     const F4 lx = ld4(nd), hx = ld4(nd + 1), ly = ld4(nd + 2), hy = ld4(nd + 3), lz = ld4(nd + 4), hz = ld4(nd + 5), cr = ld4(nd + 6);
@@ -108,10 +148,10 @@ FTN_HD int node_step(const BvhView& bvh, int cur, const RaySlab& slab, float t_m
     int c0 = (int)f2u(cr.x), c1 = (int)f2u(cr.y), c2 = (int)f2u(cr.z), c3 = (int)f2u(cr.w);
     // an unused slot is marked by its child reference (the swap-on-inverted rule of the slab test
     // would otherwise read an inverted or NaN box as an infinite one)
-    const bool h0 = slab_test(slab, lx.x, hx.x, ly.x, hy.x, lz.x, hz.x, t_max, &e0) && c0 != FTN_TRAVERSAL_DONE;
-    const bool h1 = slab_test(slab, lx.y, hx.y, ly.y, hy.y, lz.y, hz.y, t_max, &e1) && c1 != FTN_TRAVERSAL_DONE;
-    const bool h2 = slab_test(slab, lx.z, hx.z, ly.z, hy.z, lz.z, hz.z, t_max, &e2) && c2 != FTN_TRAVERSAL_DONE;
-    const bool h3 = slab_test(slab, lx.w, hx.w, ly.w, hy.w, lz.w, hz.w, t_max, &e3) && c3 != FTN_TRAVERSAL_DONE;
+    const bool h0 = slab_test<NAN_FREE>(slab, lx.x, hx.x, ly.x, hy.x, lz.x, hz.x, t_max, &e0) && c0 != FTN_TRAVERSAL_DONE;
+    const bool h1 = slab_test<NAN_FREE>(slab, lx.y, hx.y, ly.y, hy.y, lz.y, hz.y, t_max, &e1) && c1 != FTN_TRAVERSAL_DONE;
+    const bool h2 = slab_test<NAN_FREE>(slab, lx.z, hx.z, ly.z, hy.z, lz.z, hz.z, t_max, &e2) && c2 != FTN_TRAVERSAL_DONE;
+    const bool h3 = slab_test<NAN_FREE>(slab, lx.w, hx.w, ly.w, hy.w, lz.w, hz.w, t_max, &e3) && c3 != FTN_TRAVERSAL_DONE;
     e0 = h0 ? e0 : inf; e1 = h1 ? e1 : inf; e2 = h2 ? e2 : inf; e3 = h3 ? e3 : inf;
     // 5-comparator sorting network on (entry distance, child); misses sort to the back with +inf.
     // Entry distances are >= 0 and finite for entered boxes, so +inf marks exactly the misses.
@@ -123,11 +163,21 @@ FTN_HD int node_step(const BvhView& bvh, int cur, const RaySlab& slab, float t_m
     if (nh > 1) stack[sp++] = c1;
     return c0;
 #else
-    const F4 n0 = ld4(nd), n1 = ld4(nd + 1), nz = ld4(nd + 2), ci = ld4(nd + 3);
+    F4 n0, n1, nz, ci;
+    ld8(nd, n0, n1); ld8(nd + 2, nz, ci);
     float e0, e1;
     const int c0 = (int)f2u(ci.x), c1 = (int)f2u(ci.y);
-    const bool h0 = slab_test(slab, n0.x, n0.y, n0.z, n0.w, nz.x, nz.y, t_max, &e0);
-    const bool h1 = slab_test(slab, n1.x, n1.y, n1.z, n1.w, nz.z, nz.w, t_max, &e1) && c1 != FTN_TRAVERSAL_DONE;
+#if defined(__CUDA_ARCH__) && FTN_PREFETCH_CHILDREN
+    // the next record this ray reads is one of the two children: start both L2 -> L1 fetches now,
+    // under the ~60 instructions of the two slab tests, instead of after them
+    prefetch_l1(c0 >= 0 ? (const void*)(bvh.nodes + (size_t)FTN_NODE_F4 * (size_t)c0)
+                        : (FTN_PREFETCH_CHILDREN > 1 ? (const void*)(bvh.tris + 3 * (size_t)((~(uint32_t)c0) >> 2)) : (const void*)nd));
+    if (c1 != FTN_TRAVERSAL_DONE)
+        prefetch_l1(c1 >= 0 ? (const void*)(bvh.nodes + (size_t)FTN_NODE_F4 * (size_t)c1)
+                            : (FTN_PREFETCH_CHILDREN > 1 ? (const void*)(bvh.tris + 3 * (size_t)((~(uint32_t)c1) >> 2)) : (const void*)nd));
+#endif
+    const bool h0 = slab_test<NAN_FREE>(slab, n0.x, n0.y, n0.z, n0.w, nz.x, nz.y, t_max, &e0);
+    const bool h1 = slab_test<NAN_FREE>(slab, n1.x, n1.y, n1.z, n1.w, nz.z, nz.w, t_max, &e1) && c1 != FTN_TRAVERSAL_DONE;
     if (h0 && h1) {
         const bool swap = e1 < e0;
         stack[sp++] = swap ? c0 : c1;
@@ -137,6 +187,10 @@ FTN_HD int node_step(const BvhView& bvh, int cur, const RaySlab& slab, float t_m
     if (h1) return c1;
     return (sp > 0) ? stack[--sp] : FTN_TRAVERSAL_DONE;
 #endif
+}
+FTN_HD int node_step(const BvhView& bvh, int cur, const RaySlab& slab, float t_max, int* stack, int& sp) {
+    // per-ray choice; rays with a zero / denormal direction component are rare, so warps seldom diverge here
+    return slab.nan_free ? node_step_impl<true>(bvh, cur, slab, t_max, stack, sp) : node_step_impl<false>(bvh, cur, slab, t_max, stack, sp);
 }
 
 // Tests the triangles of leaf reference `leaf` (< 0); returns true if ANY and a hit was accepted.

@@ -7,6 +7,18 @@
 #include "../../include/fountain_gpu.h"
 #include "ftn_bvh.cuh"
 
+// runtime bools -> template arguments B0, B1
+#define FTN_BOOL2(f0, f1, CALL)                                                      \
+    do {                                                                             \
+        if (f0) { constexpr bool B0 = true;  if (f1) { constexpr bool B1 = true; CALL; } else { constexpr bool B1 = false; CALL; } } \
+        else    { constexpr bool B0 = false; if (f1) { constexpr bool B1 = true; CALL; } else { constexpr bool B1 = false; CALL; } } \
+    } while (0)
+#define FTN_BOOL3(f0, f1, f2, CALL)                                                  \
+    do {                                                                             \
+        if (f2) { constexpr bool B2 = true;  FTN_BOOL2(f0, f1, CALL); }              \
+        else    { constexpr bool B2 = false; FTN_BOOL2(f0, f1, CALL); }              \
+    } while (0)
+
 namespace ftn {
 
 // ---- error plumbing ------------------------------------------------------------------------------
@@ -77,6 +89,8 @@ struct SceneView {
     const LightData* lights; uint32_t n_lights;
     uint32_t n_tris;
     int refill_threshold;    // persistent traversal: leave the traverse loop when fewer lanes are active
+    bool vote;               // persistent traversal: per-step node/leaf vote (large scenes) or while-while (small)
+    int vote_bias;           // persistent traversal: node step when 16 * #node lanes >= vote_bias * #leaf lanes
 };
 
 }  // namespace ftn

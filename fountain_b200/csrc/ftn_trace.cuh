@@ -8,7 +8,14 @@
 namespace ftn {
 
 #define FTN_TRACE_THREADS 128
-#define FTN_TRACE_BLOCKS_PER_SM 8
+#ifndef FTN_TRACE_BLOCKS_PER_SM
+#define FTN_TRACE_BLOCKS_PER_SM 8     /* 64 registers/thread: 8 x 128 threads fill the register file */
+#endif
+#ifdef FTN_TRACE_MIN_BLOCKS              /* A/B: force a register budget for more resident warps */
+#define FTN_TRACE_LAUNCH_BOUNDS __launch_bounds__(FTN_TRACE_THREADS, FTN_TRACE_MIN_BLOCKS)
+#else
+#define FTN_TRACE_LAUNCH_BOUNDS __launch_bounds__(FTN_TRACE_THREADS)
+#endif
 
 struct SceneHit {
     uint32_t slot;     // FTN_NO_HIT_SLOT | triangle leaf-order slot | FTN_SPHERE_SLOT_FLAG + sphere index

@@ -8,10 +8,10 @@
 // (node cursor, short stack in local memory, t_max, best hit); the warp runs
 //     flush finished lanes -> refill idle lanes from a global work counter (one atomicAdd for all
 //     idle lanes of the warp, __ballot_sync/__popc ranks) -> traverse
-// and leaves the traverse loop as soon as fewer than FTN_REFILL_THRESHOLD lanes are still active.
-// Inside the traverse loop interior-node steps and leaf steps are separate phases (while-while):
-// a lane that reaches a leaf waits for the leaf phase instead of serialising against lanes
-// that are still testing boxes.
+// and leaves the traverse loop as soon as fewer than `refill_threshold` lanes are still active.
+// Inside the traverse loop interior-node steps and leaf steps are separate, warp-uniform phases:
+// a lane that reaches a leaf waits for a leaf step instead of serialising against lanes that are
+// still testing boxes, and the warp picks the phase most of its lanes are waiting for.
 //
 // The arithmetic per (ray, node) and (ray, triangle) is exactly that of ftn_bvh.cuh /
 // ftn_geom.cuh (the single-ray bvh2_traverse stays as the host-testable statement of it).
@@ -20,16 +20,13 @@
 
 namespace ftn {
 
-#ifndef FTN_REFILL_THRESHOLD
-#define FTN_REFILL_THRESHOLD 20
-#endif
-
 // Source:  __device__ bool load(uint32_t item, RayF* ray)       -- false: nothing to trace for this item
 // Sink:    __device__ void store(bool valid, uint32_t item, const RayF& ray, const SceneHit& hit)
 //          called by ALL 32 lanes together (valid = this lane has a finished ray), so it may use
 //          warp collectives (queue_push).
 // SPHERES = false compiles the EFloat sphere side list out of the kernel (scenes without spheres).
-template <bool ANY, bool COUNT, bool SPHERES, class Source, class Sink>
+// VOTE selects the form of the traverse loop (see below); SceneView::vote picks it per scene.
+template <bool ANY, bool COUNT, bool SPHERES, bool VOTE, class Source, class Sink>
 __device__ __forceinline__ void trace_persistent(const SceneView& sc, uint32_t n_items, uint32_t* work_counter,
                                                  Source& src, Sink& sink, TraceCounters& tc) {
     const int lane = threadIdx.x & 31;
@@ -84,12 +81,42 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sc, uint32_t n
         }
         if (__ballot_sync(0xffffffffu, has_ray) == 0u) break;
         // ---- traverse ----
+        // One loop, one warp-uniform decision per step: the warp runs an interior-node step or a
+        // leaf step, whichever more of its lanes are waiting for (vote by __ballot_sync/__popc).
+        // A lane that reaches a leaf parks it in `leaf` and keeps walking nodes (speculative
+        // traversal) until it meets a second one.  The SIMT model of this loop
+        // (tests/hostsim sim_warp_model, scripts/warp_model.py) predicts 12.9 -> 20 lanes per
+        // node step and 10.4 -> 13 per triangle test on the C3 incoherent batch against the
+        // earlier "all lanes finish their nodes, then all leaves" form.
         const int thresh = exhausted ? 1 : sc.refill_threshold;
+        if (VOTE) {
+        const int bias = sc.vote_bias;                     // node step wins when 16 * #node lanes >= bias * #leaf lanes
+        // Lane state is carried by (cur, leaf) alone: a lane without a ray or with a finished one has
+        // cur == DONE and leaf == 0 and takes no part.
+        for (;;) {
+            if (leaf >= 0 && cur < 0 && cur != FTN_TRAVERSAL_DONE) {             // park the leaf, pop the next node
+                leaf = cur;
+                cur = (sp > 0) ? stack[--sp] : FTN_TRAVERSAL_DONE;
+            }
+            const unsigned m_node = __ballot_sync(0xffffffffu, cur >= 0), m_leaf = __ballot_sync(0xffffffffu, leaf < 0);
+            // every unfinished lane wants one or the other; leave when the warp is too empty
+            if (__popc(m_node | m_leaf) < thresh) break;
+            if (16 * __popc(m_node) >= bias * __popc(m_leaf)) {
+                if (cur >= 0) {
+                    if (COUNT) tc.nodes++;
+                    cur = node_step(bvh, cur, slab, t_max, stack, sp);
+                }
+            } else if (leaf < 0) {
+                const bool stop = leaf_step<ANY, COUNT>(bvh, leaf, ray.o, shear, &t_max, &hit.slot, &hit.tri, &tc);
+                leaf = 0;
+                if (stop) cur = FTN_TRAVERSAL_DONE;
+            }
+        }
+        if (has_ray && cur == FTN_TRAVERSAL_DONE && leaf >= 0) finished = true;
+        } else {
+        // while-while form: all lanes finish their node walk (parking one leaf), then all leaves
         for (;;) {
             const bool act = has_ray && !finished;
-            // phase 1: interior nodes.  The first leaf a lane meets is POSTPONED (speculative
-            // traversal): the lane keeps walking until it meets a second leaf or runs out of nodes, so
-            // lanes wait for each other only every other leaf.
             while (act && cur >= 0) {
                 if (COUNT) tc.nodes++;
                 cur = node_step(bvh, cur, slab, t_max, stack, sp);
@@ -98,7 +125,6 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sc, uint32_t n
                     cur = (sp > 0) ? stack[--sp] : FTN_TRAVERSAL_DONE;
                 }
             }
-            // phase 2: the postponed leaf, then the second one if the lane stopped on it
             while (act && leaf < 0) {
                 const bool stop = leaf_step<ANY, COUNT>(bvh, leaf, ray.o, shear, &t_max, &hit.slot, &hit.tri, &tc);
                 leaf = 0;
@@ -106,8 +132,8 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sc, uint32_t n
                 else if (cur < 0 && cur != FTN_TRAVERSAL_DONE) { leaf = cur; cur = (sp > 0) ? stack[--sp] : FTN_TRAVERSAL_DONE; }
             }
             if (act && cur == FTN_TRAVERSAL_DONE) finished = true;
-            // phase 3: leave when the warp is too empty (idle lanes then flush + refill)
             if (__popc(__ballot_sync(0xffffffffu, has_ray && !finished)) < thresh) break;
+        }
         }
     }
 }

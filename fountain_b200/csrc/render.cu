@@ -127,14 +127,14 @@ struct ExtendSink {
         queue_push(qs.q, counts, target, path);   // all 32 lanes arrive here together
     }
 };
-template <bool COUNT, bool SPH>
-__global__ void __launch_bounds__(FTN_TRACE_THREADS)
+template <bool COUNT, bool SPH, bool VOTE>
+__global__ void FTN_TRACE_LAUNCH_BOUNDS
 k_extend(SceneView sc, PathArrays pa, const uint32_t* __restrict__ queue_in, uint32_t n_in, Queues qs, uint32_t* __restrict__ counts,
          unsigned long long* __restrict__ trav, bool miss_always) {
     PathRaySource src; src.pa = pa; src.queue = queue_in;
     ExtendSink sink; sink.sc = sc; sink.pa = pa; sink.queue = queue_in; sink.qs = qs; sink.counts = counts; sink.miss_always = miss_always;
     TraceCounters tc; tc.nodes = 0; tc.tris = 0;
-    trace_persistent<false, COUNT, SPH>(sc, n_in, &counts[W_EXTEND], src, sink, tc);
+    trace_persistent<false, COUNT, SPH, VOTE>(sc, n_in, &counts[W_EXTEND], src, sink, tc);
     if (COUNT) flush_trace_counters(tc, trav);
 }
 
@@ -205,13 +205,13 @@ struct ShadowSink {
         st3(pa.L, path, ld3(pa.L, path) + ld3(pa.sh_L, path));
     }
 };
-template <bool COUNT, bool SPH>
-__global__ void __launch_bounds__(FTN_TRACE_THREADS)
+template <bool COUNT, bool SPH, bool VOTE>
+__global__ void FTN_TRACE_LAUNCH_BOUNDS
 k_shadow(SceneView sc, PathArrays pa, const uint32_t* __restrict__ queue, uint32_t* __restrict__ counts, unsigned long long* __restrict__ trav) {
     ShadowSource src; src.pa = pa; src.queue = queue;
     ShadowSink sink; sink.pa = pa; sink.queue = queue;
     TraceCounters tc; tc.nodes = 0; tc.tris = 0;
-    trace_persistent<true, COUNT, SPH>(sc, counts[Q_SHADOW], &counts[W_SHADOW], src, sink, tc);
+    trace_persistent<true, COUNT, SPH, VOTE>(sc, counts[Q_SHADOW], &counts[W_SHADOW], src, sink, tc);
     if (COUNT) flush_trace_counters(tc, trav);
 }
 
@@ -235,13 +235,13 @@ struct MisSink {
     }
 };
 // ENV_ONLY: with only infinite lights a hit contributes nothing whatever it is, so any-hit suffices
-template <bool ENV_ONLY, bool COUNT, bool SPH>
-__global__ void __launch_bounds__(FTN_TRACE_THREADS)
+template <bool ENV_ONLY, bool COUNT, bool SPH, bool VOTE>
+__global__ void FTN_TRACE_LAUNCH_BOUNDS
 k_mis(SceneView sc, PathArrays pa, const uint32_t* __restrict__ queue, uint32_t* __restrict__ counts, unsigned long long* __restrict__ trav) {
     MisSource src; src.pa = pa; src.queue = queue;
     MisSink sink; sink.sc = sc; sink.pa = pa; sink.queue = queue;
     TraceCounters tc; tc.nodes = 0; tc.tris = 0;
-    trace_persistent<ENV_ONLY, COUNT, SPH>(sc, counts[Q_MIS], &counts[W_MIS], src, sink, tc);
+    trace_persistent<ENV_ONLY, COUNT, SPH, VOTE>(sc, counts[Q_MIS], &counts[W_MIS], src, sink, tc);
     if (COUNT) flush_trace_counters(tc, trav);
 }
 
@@ -313,12 +313,6 @@ static size_t g_max_paths_per_pass = 4u << 20;
 
 // CUDA-event pairs around every traversal launch, per kernel class (extend / shadow / mis): the
 // live per-kernel durations bench.py's roofline uses.
-// runtime bools -> template arguments B0, B1
-#define FTN_BOOL2(f0, f1, CALL)                                                      \
-    do {                                                                             \
-        if (f0) { constexpr bool B0 = true;  if (f1) { constexpr bool B1 = true; CALL; } else { constexpr bool B1 = false; CALL; } } \
-        else    { constexpr bool B0 = false; if (f1) { constexpr bool B1 = true; CALL; } else { constexpr bool B1 = false; CALL; } } \
-    } while (0)
 
 struct TraceTimer {
     std::vector<cudaEvent_t> ev; std::vector<int> cls;
@@ -417,7 +411,7 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
             Queues q = qs; q.q[Q_ACTIVE_OUT] = q_out;
             const unsigned ge = trace_grid(n_active, FTN_TRACE_BLOCKS_PER_SM);
             timer.begin(0);
-            FTN_BOOL2(count_traversal, sph, (k_extend<B0, B1><<<ge, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q_in, n_active, q, counts, d_trav, integ->type == FTN_INTEGRATOR_DIRECT_LIGHTING)));
+            FTN_BOOL3(count_traversal, sph, sc.vote, (k_extend<B0, B1, B2><<<ge, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q_in, n_active, q, counts, d_trav, integ->type == FTN_INTEGRATOR_DIRECT_LIGHTING)));
             timer.end();
             FTN_LAUNCHED();
             class_rays[0] += n_active;
@@ -433,7 +427,7 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
             if (hc[Q_SHADOW]) {
                 const unsigned g = trace_grid(hc[Q_SHADOW], FTN_TRACE_BLOCKS_PER_SM);
                 timer.begin(1);
-                FTN_BOOL2(count_traversal, sph, (k_shadow<B0, B1><<<g, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_SHADOW], counts, d_trav + 2)));
+                FTN_BOOL3(count_traversal, sph, sc.vote, (k_shadow<B0, B1, B2><<<g, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_SHADOW], counts, d_trav + 2)));
                 timer.end();
                 FTN_LAUNCHED();
                 class_rays[1] += hc[Q_SHADOW];
@@ -441,8 +435,8 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
             if (hc[Q_MIS]) {
                 const unsigned g = trace_grid(hc[Q_MIS], FTN_TRACE_BLOCKS_PER_SM);
                 timer.begin(2);
-                if (has_area) { FTN_BOOL2(count_traversal, sph, (k_mis<false, B0, B1><<<g, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts, d_trav + 4))); }
-                else { FTN_BOOL2(count_traversal, sph, (k_mis<true, B0, B1><<<g, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts, d_trav + 4))); }
+                if (has_area) { FTN_BOOL3(count_traversal, sph, sc.vote, (k_mis<false, B0, B1, B2><<<g, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts, d_trav + 4))); }
+                else { FTN_BOOL3(count_traversal, sph, sc.vote, (k_mis<true, B0, B1, B2><<<g, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts, d_trav + 4))); }
                 timer.end();
                 FTN_LAUNCHED();
                 class_rays[2] += hc[Q_MIS];

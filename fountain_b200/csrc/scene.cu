@@ -14,6 +14,8 @@
 #include "ftn_lbvh.cuh"
 #include <cstdlib>
 #define FTN_REFILL_THRESHOLD_DEFAULT 16
+#define FTN_VOTE_BIAS_DEFAULT 14
+#define FTN_VOTE_MIN_TRIS 65536u
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -169,6 +171,12 @@ SceneView make_view(const FtnScene& s) {
     v.n_tris = s.n_tris;
     static const int thr = [] { const char* e = getenv("FTN_REFILL_THRESHOLD"); int t = e ? atoi(e) : FTN_REFILL_THRESHOLD_DEFAULT; return t < 1 ? 1 : (t > 32 ? 32 : t); }();
     v.refill_threshold = thr;
+    static const int bias = [] { const char* e = getenv("FTN_VOTE_BIAS"); int t = e ? atoi(e) : FTN_VOTE_BIAS_DEFAULT; return t < 1 ? 1 : (t > 256 ? 256 : t); }();
+    v.vote_bias = bias;
+    // measured (profiles/r01_ab_vote_ldg256.txt): the vote pays on deep trees (1M triangles: +6..9 %) and costs
+    // on shallow ones (4332 triangles: -9 %), where its per-step bookkeeping is not amortised
+    static const int vote_env = [] { const char* e = getenv("FTN_TRAVERSE_VOTE"); return e ? atoi(e) : -1; }();
+    v.vote = vote_env >= 0 ? vote_env != 0 : s.n_tris >= FTN_VOTE_MIN_TRIS;
     return v;
 }
 

@@ -34,14 +34,14 @@ struct BatchSink {
     }
 };
 
-template <bool ANY, bool COUNT, bool SPH>
-__global__ void __launch_bounds__(FTN_TRACE_THREADS)
+template <bool ANY, bool COUNT, bool SPH, bool VOTE>
+__global__ void FTN_TRACE_LAUNCH_BOUNDS
 k_intersect_batch(SceneView sc, const FtnRay* __restrict__ rays, FtnHit* __restrict__ hits, uint8_t* __restrict__ any_out,
                   uint32_t n, uint32_t* __restrict__ work_counter, unsigned long long* __restrict__ counters) {
     BatchSource src; src.rays = rays;
     BatchSink<ANY> sink; sink.sc = sc; sink.hits = hits; sink.any_out = any_out;
     TraceCounters tc; tc.nodes = 0; tc.tris = 0;
-    trace_persistent<ANY, COUNT, SPH>(sc, n, work_counter, src, sink, tc);
+    trace_persistent<ANY, COUNT, SPH, VOTE>(sc, n, work_counter, src, sink, tc);
     if (COUNT) {
         unsigned long long nn = tc.nodes, tt = tc.tris;
 #pragma unroll
@@ -82,15 +82,10 @@ int intersect_device(const FtnScene* s, size_t n, const FtnRay* d_rays, FtnHit* 
         const FtnRay* r = d_rays + off;
         FtnHit* h = d_hits ? d_hits + off : nullptr;
         uint8_t* a = d_any ? d_any + off : nullptr;
-        if (s->n_spheres) {
-            if (any) k_intersect_batch<true, false, true><<<grid, FTN_TRACE_THREADS, 0, st>>>(sc, r, nullptr, a, m, d_work, nullptr);
-            else if (d_counters) k_intersect_batch<false, true, true><<<grid, FTN_TRACE_THREADS, 0, st>>>(sc, r, h, nullptr, m, d_work, d_counters);
-            else k_intersect_batch<false, false, true><<<grid, FTN_TRACE_THREADS, 0, st>>>(sc, r, h, nullptr, m, d_work, nullptr);
-        } else {
-            if (any) k_intersect_batch<true, false, false><<<grid, FTN_TRACE_THREADS, 0, st>>>(sc, r, nullptr, a, m, d_work, nullptr);
-            else if (d_counters) k_intersect_batch<false, true, false><<<grid, FTN_TRACE_THREADS, 0, st>>>(sc, r, h, nullptr, m, d_work, d_counters);
-            else k_intersect_batch<false, false, false><<<grid, FTN_TRACE_THREADS, 0, st>>>(sc, r, h, nullptr, m, d_work, nullptr);
-        }
+        const bool sph = s->n_spheres != 0, count = d_counters != nullptr;
+        if (any) { FTN_BOOL2(sph, sc.vote, (k_intersect_batch<true, false, B0, B1><<<grid, FTN_TRACE_THREADS, 0, st>>>(sc, r, nullptr, a, m, d_work, nullptr))); }
+        else if (count) { FTN_BOOL2(sph, sc.vote, (k_intersect_batch<false, true, B0, B1><<<grid, FTN_TRACE_THREADS, 0, st>>>(sc, r, h, nullptr, m, d_work, d_counters))); }
+        else { FTN_BOOL2(sph, sc.vote, (k_intersect_batch<false, false, B0, B1><<<grid, FTN_TRACE_THREADS, 0, st>>>(sc, r, h, nullptr, m, d_work, nullptr))); }
         if (off + chunk < n) { FTN_LAUNCHED(); }
     }
     FTN_LAUNCHED();

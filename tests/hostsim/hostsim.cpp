@@ -35,7 +35,7 @@ struct SimScene {
         v.bvh.nodes = nodes.data(); v.bvh.tris = tris.data(); v.bvh.n_nodes = n_nodes; v.bvh.n_tris = n_tris;
         v.pos = pos.data(); v.nrm = nrm.empty() ? nullptr : nrm.data(); v.uv = uv.empty() ? nullptr : uv.data(); v.idx = idx.data();
         v.meshes = meshes.data(); v.materials = mats.data(); v.spheres = spheres.data(); v.n_spheres = (uint32_t)spheres.size();
-        v.lights = lights.data(); v.n_lights = (uint32_t)lights.size(); v.n_tris = n_tris; v.refill_threshold = 20;
+        v.lights = lights.data(); v.n_lights = (uint32_t)lights.size(); v.n_tris = n_tris; v.refill_threshold = 20; v.vote_bias = 14; v.vote = true;
         return v;
     }
 };
@@ -381,4 +381,155 @@ SIM_API float sim_kat_counter_uniform(uint64_t seed, uint64_t sample_index, uint
 SIM_API float sim_kat_gamma(int n) {
     switch (n) { case 1: return gamma_n(1); case 2: return gamma_n(2); case 3: return gamma_n(3); case 4: return gamma_n(4);
                  case 5: return gamma_n(5); case 6: return gamma_n(6); case 7: return gamma_n(7); default: return gamma_n(8); }
+}
+
+// ---- SIMT execution model of the persistent traversal loop (design tool, not a test) -----------------
+// Replays ftn_trace_persistent.cuh's loop structure for warps of 32 lanes over a ray batch and
+// counts ISSUE SLOTS per phase (one slot = one warp-wide pass through a phase body, whatever the
+// number of participating lanes) next to the lane-level work, for different loop policies.
+//   ip[0] refill threshold   ip[1] node-phase exit: leave when fewer than this many lanes want a node
+//   ip[2] leaf-phase exit: leave when fewer than this many lanes still hold a leaf (1 = drain)
+//   ip[3] postponed leaves a lane may hold before it must stop walking (0, 1)
+//   ip[4] warps simulated round-robin
+// out: [0] node slots [1] node lane-steps [2] triangle slots [3] triangle lane-tests
+//      [4] leaf-phase entries (slots) [5] leaf lane-entries [6] refill rounds [7] rays
+SIM_API int sim_warp_model(const SimScene* s, size_t n, const FtnRay* rays, const int* ip, double* out) {
+    const SceneView sc = s->view();
+    const BvhView bvh = sc.bvh;
+    const int refill_thresh = ip[0], node_exit = ip[1], leaf_exit = ip[2], postpone = ip[3], n_warps = std::max(1, ip[4]);
+    struct Lane {
+        bool has_ray = false, finished = false;
+        RayF ray; RaySlab slab; RayShear shear; float t_max = 0; uint32_t slot = FTN_NO_HIT_SLOT; TriHit tri;
+        int stack[FTN_STACK_SIZE]; int sp = 0, cur = FTN_TRAVERSAL_DONE, leaf = 0;
+        uint32_t tri_i = 0;   // progress inside the current leaf
+    };
+    struct Warp { Lane l[32]; bool done = false; };
+    std::vector<Warp> warps(n_warps);
+    size_t next = 0;
+    double node_slots = 0, node_work = 0, tri_slots = 0, tri_work = 0, leaf_slots = 0, leaf_work = 0, refills = 0;
+    TraceCounters tc; tc.nodes = tc.tris = 0;
+    int live = n_warps;
+    while (live > 0) {
+        for (Warp& w : warps) {
+            if (w.done) continue;
+            // flush + refill
+            int idle = 0;
+            for (Lane& L : w.l) { if (L.finished) { L.has_ray = false; L.finished = false; } if (!L.has_ray) ++idle; }
+            if (idle && next < n) {
+                refills += 1;
+                for (Lane& L : w.l) {
+                    if (L.has_ray || next >= n) continue;
+                    L.ray = to_rayf(rays[next++]); L.has_ray = true; L.slot = FTN_NO_HIT_SLOT; L.t_max = L.ray.t_max;
+                    L.slab = make_ray_slab(L.ray.o, L.ray.d); L.shear = make_ray_shear(L.ray.d); L.sp = 0; L.cur = 0; L.leaf = 0;
+                }
+            }
+            int with_ray = 0; for (Lane& L : w.l) with_ray += L.has_ray;
+            if (!with_ray) { w.done = true; --live; continue; }
+            const int thresh = (next >= n) ? 1 : refill_thresh;
+            auto promote = [&]() {   // a lane stopped on a leaf with a free postponed slot takes it and pops
+                for (Lane& L : w.l) {
+                    if (!(L.has_ray && !L.finished)) continue;
+                    if (L.leaf >= 0 && L.cur < 0 && L.cur != FTN_TRAVERSAL_DONE) { L.leaf = L.cur; L.cur = (L.sp > 0) ? L.stack[--L.sp] : FTN_TRAVERSAL_DONE; }
+                }
+            };
+            auto count_node = [&]() { int c = 0; for (Lane& L : w.l) c += (L.has_ray && !L.finished && L.cur >= 0); return c; };
+            auto count_leaf = [&]() { int c = 0; for (Lane& L : w.l) c += (L.has_ray && !L.finished && L.leaf < 0); return c; };
+            auto node_slot = [&]() {
+                node_slots += 1;
+                for (Lane& L : w.l) {
+                    if (!(L.has_ray && !L.finished && L.cur >= 0)) continue;
+                    node_work += 1;
+                    L.cur = node_step(bvh, L.cur, L.slab, L.t_max, L.stack, L.sp);
+                    if (postpone && L.cur < 0 && L.cur != FTN_TRAVERSAL_DONE && L.leaf >= 0) {
+                        L.leaf = L.cur; L.cur = (L.sp > 0) ? L.stack[--L.sp] : FTN_TRAVERSAL_DONE;
+                    }
+                }
+            };
+            auto leaf_slot = [&]() {
+                leaf_slots += 1;
+                uint32_t maxc = 0;
+                for (Lane& L : w.l) if (L.has_ray && !L.finished && L.leaf < 0) maxc = std::max(maxc, ((~(uint32_t)L.leaf) & 3u) + 1u);
+                tri_slots += maxc;
+                for (Lane& L : w.l) {
+                    if (!(L.has_ray && !L.finished && L.leaf < 0)) continue;
+                    leaf_work += 1;
+                    tri_work += ((~(uint32_t)L.leaf) & 3u) + 1u;
+                    leaf_step<false, false>(bvh, L.leaf, L.ray.o, L.shear, &L.t_max, &L.slot, &L.tri, &tc);
+                    L.leaf = 0;
+                }
+            };
+            for (;;) {
+                if (ip[5] == 2) {
+                    // per-step vote, ONE triangle per leaf slot (lanes keep a cursor into their leaf)
+                    for (;;) {
+                        promote();
+                        const int nn = count_node(), nl = count_leaf();
+                        if (nn == 0 && nl == 0) break;
+                        if (nl == 0 || nn * 16 >= nl * ip[6]) node_slot();
+                        else {
+                            leaf_slots += 1; tri_slots += 1;
+                            for (Lane& L : w.l) {
+                                if (!(L.has_ray && !L.finished && L.leaf < 0)) continue;
+                                leaf_work += 1; tri_work += 1;
+                                const uint32_t ref = ~(uint32_t)L.leaf, first = ref >> 2, cnt = ref & 3u;
+                                const int one = (int)~((first << 2) | 0u);
+                                leaf_step<false, false>(bvh, one, L.ray.o, L.shear, &L.t_max, &L.slot, &L.tri, &tc);
+                                L.leaf = cnt ? (int)~(((first + 1) << 2) | (cnt - 1)) : 0;
+                            }
+                        }
+                        int active = 0;
+                        for (Lane& L : w.l) active += (L.has_ray && !L.finished && !(L.cur == FTN_TRAVERSAL_DONE && L.leaf >= 0));
+                        if (active < thresh) break;
+                    }
+                } else if (ip[5] == 1) {
+                    // per-step vote: run the phase the (weighted) majority of lanes wants
+                    for (;;) {
+                        promote();
+                        const int nn = count_node(), nl = count_leaf();
+                        if (nn == 0 && nl == 0) break;
+                        if (nl == 0 || nn * 16 >= nl * ip[6]) node_slot(); else leaf_slot();
+                        int active = 0;
+                        for (Lane& L : w.l) active += (L.has_ray && !L.finished && !(L.cur == FTN_TRAVERSAL_DONE && L.leaf >= 0));
+                        if (active < thresh) break;
+                    }
+                } else {
+                    // phase 1: nodes
+                    for (;;) {
+                        const int want = count_node();
+                        if (want == 0) break;
+                        promote();
+                        const int nl = count_leaf();
+                        if (want < node_exit && nl > want) break;
+                        node_slot();
+                    }
+                    // phase 2: leaves
+                    for (;;) {
+                        promote();
+                        const int holding = count_leaf();
+                        if (holding == 0) break;
+                        if (holding < leaf_exit && count_node() > holding) break;
+                        leaf_slot();
+                    }
+                }
+                int active = 0;
+                for (Lane& L : w.l) {
+                    if (L.has_ray && !L.finished && L.cur == FTN_TRAVERSAL_DONE && L.leaf >= 0) L.finished = true;
+                    active += (L.has_ray && !L.finished);
+                }
+                if (active < thresh) break;
+            }
+        }
+    }
+    out[0] = node_slots; out[1] = node_work; out[2] = tri_slots; out[3] = tri_work; out[4] = leaf_slots; out[5] = leaf_work; out[6] = refills; out[7] = (double)n;
+    return FTN_OK;
+}
+// slab test as the kernels run it: mode 0 = per-ray dispatch (nan_free fast form when allowed), 1 = exact form.
+// returns bit0 = accepted, bit1 = ray is nan_free; out[0] = entry distance
+SIM_API int sim_kat_slab_test(const float bmin[3], const float bmax[3], const FtnRay* ray, float out[1], int mode) {
+    const RaySlab s = make_ray_slab(V3(ray->o[0], ray->o[1], ray->o[2]), V3(ray->d[0], ray->d[1], ray->d[2]));
+    float e = 0.0f;
+    const bool hit = (mode == 0 && s.nan_free) ? slab_test<true>(s, bmin[0], bmax[0], bmin[1], bmax[1], bmin[2], bmax[2], ray->t_max, &e)
+                                               : slab_test<false>(s, bmin[0], bmax[0], bmin[1], bmax[1], bmin[2], bmax[2], ray->t_max, &e);
+    out[0] = e;
+    return (hit ? 1 : 0) | (s.nan_free ? 2 : 0);
 }

@@ -39,6 +39,7 @@ def library():
             "sim_kat_env": (C.c_int, [C.c_void_p, P(f32), P(f32)]),
             "sim_kat_counter_uniform": (f32, [u64, u64, u32]),
             "sim_kat_gamma": (f32, [C.c_int]),
+            "sim_kat_slab_test": (C.c_int, [P(f32), P(f32), P(A.FtnRay), P(f32), C.c_int]),
         }
         for name, (res, args) in protos.items():
             fn = getattr(_lib, name)

@@ -263,3 +263,47 @@ def test_env_light_matches_oracle(sim, oracle, sim_backend, orc_backend, w, h):
         x, y = np.array(oa[:], dtype=np.float64), np.array(ob[:], dtype=np.float64)
         assert np.allclose(x[:3], y[:3], atol=2e-6)                      # wi
         assert np.allclose(x[3:], y[3:], rtol=2e-4, atol=1e-6), (x, y)    # pdfs and radiances
+
+
+def test_slab_test_forms_match_reference(sim, oracle):
+    """bounds.rs:214-233.  The kernels' slab test (per-ray dispatch between the exact form and the
+    cheaper NaN-free form) accepts exactly the boxes the reference accepts, with the same entry
+    distance -- including rays with zero / denormal direction components, origins on slab planes,
+    rays starting inside the box and boxes behind t_max."""
+    rng = np.random.default_rng(11)
+    slib, olib = sim.library(), oracle.library()
+    n_fast = n_hit = 0
+    for i in range(6000):
+        lo = rng.uniform(-2, 2, 3).astype(np.float32)
+        hi = (lo + rng.uniform(0, 2, 3).astype(np.float32) * (rng.random(3) > 0.1)).astype(np.float32)   # some flat boxes
+        o = rng.uniform(-3, 3, 3).astype(np.float32)
+        d = rng.normal(size=3).astype(np.float32)
+        kind = i % 6
+        if kind == 1:
+            d[rng.integers(3)] = 0.0
+        elif kind == 2:
+            d[rng.integers(3)] = -0.0
+            o[rng.integers(3)] = lo[rng.integers(3)]
+        elif kind == 3:                                   # origin on a slab plane, axis-parallel ray
+            ax = rng.integers(3); o[ax] = (lo if rng.random() < 0.5 else hi)[ax]; d[ax] = 0.0
+        elif kind == 4:
+            d[rng.integers(3)] = np.float32(1e-42)        # denormal: 1/d overflows to inf
+        elif kind == 5:
+            o = (lo + (hi - lo) * rng.random(3).astype(np.float32)).astype(np.float32)   # inside
+        t_max = np.float32(np.inf if rng.random() < 0.5 else rng.uniform(0, 6))
+        r = A.FtnRay()
+        r.o[:] = o.tolist(); r.d[:] = d.tolist(); r.t_max = float(t_max); r.time = 0.0
+        blo, bhi = (A.f32 * 3)(*lo.tolist()), (A.f32 * 3)(*hi.tolist())
+        ref_t = (A.f32 * 2)()
+        ref_hit = olib.orc_kat_bounds_intersect(blo, bhi, C.byref(r), ref_t)
+        e_k, e_x = (A.f32 * 1)(), (A.f32 * 1)()
+        got = slib.sim_kat_slab_test(blo, bhi, C.byref(r), e_k, 0)
+        exact = slib.sim_kat_slab_test(blo, bhi, C.byref(r), e_x, 1)
+        assert (got & 1) == ref_hit and (exact & 1) == ref_hit, (i, lo, hi, o, d, t_max)
+        if ref_hit:
+            n_hit += 1
+            assert np.float32(e_k[0]) == np.float32(ref_t[0]) and np.float32(e_x[0]) == np.float32(ref_t[0])
+        n_fast += (got >> 1) & 1
+        if kind in (1, 2, 3, 4):
+            assert not (got >> 1) & 1                     # irregular rays must take the exact form
+    assert n_fast > 1500 and n_hit > 500
