@@ -126,6 +126,7 @@ PROTOTYPES = {
     "render_device": (C.c_int, [VOIDP, P(FtnCamera), P(FtnFilm), P(FtnSampler), P(FtnIntegrator), VOIDP, P(FtnStats), VOIDP]),
     "film_to_rgb_device": (C.c_int, [C.c_size_t, VOIDP, VOIDP, VOIDP]),
     "film_pixel_count": (C.c_int, [P(FtnFilm), P(i32), P(i32)]),
+    "release_cached_memory": (C.c_int, []),
 }
 
 # Subset the CPU oracle implements (host buffers only), plus its own extras bound in oracle/orc.py.

@@ -10,6 +10,8 @@ static thread_local std::string g_last_error;
 static std::atomic<uint64_t> g_launches{0};
 
 int set_error(int code, const std::string& msg) { g_last_error = msg; return code; }
+std::string last_error_string() { return g_last_error; }
+void restore_error_string(const std::string& s) { g_last_error = s; }
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     char buf[512];
     snprintf(buf, sizeof(buf), "%s failed: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
@@ -26,6 +28,9 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
                   const FtnIntegrator* integ, FtnPixel* d_pixels, FtnStats* stats, cudaStream_t st);
 int film_to_rgb_device(size_t n, const FtnPixel* d_pixels, float* d_rgb, cudaStream_t st);
 int film_pixel_count(const FtnFilm* f, int32_t* w, int32_t* h);
+int render_host(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, const FtnSampler* smp,
+                const FtnIntegrator* integ, FtnPixel* out_pixels, FtnStats* stats);
+int release_cached_memory();
 }  // namespace ftn
 
 using namespace ftn;
@@ -115,26 +120,9 @@ FTN_API int ftn_render_device(const FtnScene* s, const FtnCamera* cam, const Ftn
 }
 FTN_API int ftn_render(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, const FtnSampler* smp,
                        const FtnIntegrator* integ, FtnPixel* out_pixels, FtnStats* stats) {
-    if (!s || !film || !out_pixels) return set_error(FTN_ERR_INVALID_ARGUMENT, "null argument");
-    int32_t w = 0, h = 0;
-    FTN_TRY(film_pixel_count(film, &w, &h));
-    FTN_CUDA(cudaSetDevice(s->device));
-    const size_t bytes = (size_t)w * h * sizeof(FtnPixel);
-    FtnPixel* d_px = nullptr;
-    FTN_CUDA(cudaMalloc(&d_px, bytes));
-    cudaError_t e = cudaMemset(d_px, 0, bytes);
-    int rc = (e == cudaSuccess) ? FTN_OK : cuda_fail(e, "memset film", __FILE__, __LINE__);
-    int render_rc = FTN_OK;
-    if (rc == FTN_OK) render_rc = ftn_render_device(s, cam, film, smp, integ, d_px, stats, nullptr);
-    // like the reference's panic, a NaN / unsupported render still leaves the film readable
-    if (rc == FTN_OK && (render_rc == FTN_OK || render_rc == FTN_ERR_NAN_RADIANCE || render_rc == FTN_ERR_UNSUPPORTED)) {
-        std::string keep = g_last_error;
-        if ((e = cudaMemcpy(out_pixels, d_px, bytes, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "D2H film", __FILE__, __LINE__);
-        else g_last_error = keep;
-    }
-    cudaFree(d_px);
-    return rc != FTN_OK ? rc : render_rc;
+    return render_host(s, cam, film, smp, integ, out_pixels, stats);
 }
+FTN_API int ftn_release_cached_memory(void) { return release_cached_memory(); }
 FTN_API int ftn_film_to_rgb_device(size_t n, const FtnPixel* d_pixels, float* d_rgb, void* stream) {
     return film_to_rgb_device(n, d_pixels, d_rgb, (cudaStream_t)stream);
 }

@@ -22,7 +22,10 @@
 namespace ftn {
 
 // ---- error plumbing ------------------------------------------------------------------------------
+#define FTN_MAX_DEVICES 64
 int set_error(int code, const std::string& msg);
+std::string last_error_string();
+void restore_error_string(const std::string& s);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 void count_launch(uint64_t n = 1);
 
@@ -117,8 +120,6 @@ struct FtnScene {
     unsigned long long* d_work = nullptr;   // dynamic work-fetch counter of the batch queries
     bool material_present[3] = {false, false, false};   // which shade kernels a render launches
     bool has_null_material = false;         // any primitive with a null BSDF (path.rs:76-80)
-    mutable void* ws = nullptr;             // cached render workspace (one render at a time per scene)
-    mutable size_t ws_bytes = 0;
     ftn::SceneView view() const;
 };
 

@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <cstring>
 #include <cmath>
+#include <mutex>
 
 namespace ftn {
 
@@ -292,16 +293,30 @@ int film_pixel_count(const FtnFilm* f, int32_t* w, int32_t* h) {
     return FTN_OK;
 }
 
-// Device workspace of the wavefront state, cached on the scene between renders (a render of the
-// same size allocates nothing).
-static int workspace_reserve(const FtnScene* s, size_t bytes, char** base) {
-    if (s->ws_bytes < bytes) {
-        if (s->ws) { cudaFree(s->ws); s->ws = nullptr; s->ws_bytes = 0; }
-        cudaError_t e = cudaMalloc(&s->ws, bytes);
-        if (e != cudaSuccess) { s->ws = nullptr; return cuda_fail(e, "cudaMalloc (render workspace)", __FILE__, __LINE__); }
-        s->ws_bytes = bytes;
+// Device workspace of the wavefront state: one grow-only arena per device for the whole process,
+// so that neither a second render nor a render of a NEW scene (the end-to-end path: upload, build,
+// render, read back) pays cudaMalloc/cudaFree of the path state.  Renders on one device serialise
+// on the arena's mutex (they would contend for the SMs anyway).  ftn_release_cached_memory() frees it.
+struct DeviceArena { void* p = nullptr; size_t bytes = 0; void* film = nullptr; size_t film_bytes = 0; std::mutex m; };
+static DeviceArena g_arena[FTN_MAX_DEVICES];
+static int arena_reserve(void** p, size_t* have, size_t bytes, const char* what) {
+    if (*have < bytes) {
+        if (*p) { cudaFree(*p); *p = nullptr; *have = 0; }
+        cudaError_t e = cudaMalloc(p, bytes);
+        if (e != cudaSuccess) { *p = nullptr; return cuda_fail(e, what, __FILE__, __LINE__); }
+        *have = bytes;
     }
-    *base = (char*)s->ws;
+    return FTN_OK;
+}
+int release_cached_memory() {
+    for (int d = 0; d < FTN_MAX_DEVICES; ++d) {
+        DeviceArena& a = g_arena[d];
+        std::lock_guard<std::mutex> lock(a.m);
+        if (!a.p && !a.film) continue;
+        if (cudaSetDevice(d) != cudaSuccess) continue;
+        cudaFree(a.p); cudaFree(a.film);
+        a.p = a.film = nullptr; a.bytes = a.film_bytes = 0;
+    }
     return FTN_OK;
 }
 struct Carver {
@@ -309,7 +324,10 @@ struct Carver {
     template <class T> T* take(size_t count) { off = (off + 255) & ~(size_t)255; T* r = reinterpret_cast<T*>(p + off); off += count * sizeof(T); return r; }
 };
 
-static size_t g_max_paths_per_pass = 4u << 20;
+// Paths per wavefront pass.  Measured on C2 (profiles/r01_ab_pass_size.txt): 4Mi -> 7.6 ms, 8Mi -> 6.7 ms,
+// 16Mi -> 6.0 ms per 16.8M-path step: every launch has a tail in which SMs idle, so fewer, larger
+// launches win; 16Mi paths cost 3.4 GB of the 180 GB.
+static size_t g_max_paths_per_pass = 16u << 20;
 
 // CUDA-event pairs around every traversal launch, per kernel class (extend / shadow / mis): the
 // live per-kernel durations bench.py's roofline uses.
@@ -358,8 +376,12 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
 
     const size_t ws_bytes = 10 * (P * sizeof(float4) + 256) + 2 * (P * 4 + 256) + P * sizeof(float2) + 256 +
                             (size_t)fw * fh * sizeof(float4) + 256 + (size_t)(Q_COUNT + 1) * (P * 4 + 256) + n_spix + 4096;
-    Carver cv; 
-    FTN_TRY(workspace_reserve(s, ws_bytes, &cv.p));
+    if (s->device < 0 || s->device >= FTN_MAX_DEVICES) return set_error(FTN_ERR_INVALID_ARGUMENT, "device index out of range");
+    DeviceArena& arena = g_arena[s->device];
+    std::lock_guard<std::mutex> arena_lock(arena.m);
+    Carver cv;
+    FTN_TRY(arena_reserve(&arena.p, &arena.bytes, ws_bytes, "cudaMalloc (render workspace)"));
+    cv.p = (char*)arena.p;
     PathArrays pa;
     pa.ray_o = cv.take<float4>(P); pa.ray_d = cv.take<float4>(P); pa.beta = cv.take<float4>(P); pa.L = cv.take<float4>(P);
     pa.sh_o = cv.take<float4>(P); pa.sh_d = cv.take<float4>(P); pa.sh_L = cv.take<float4>(P);
@@ -472,6 +494,34 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
     if (h_err & ERR_NAN) return set_error(FTN_ERR_NAN_RADIANCE, "NaN radiance value (check_radiance, integrator/mod.rs:285)");
     if (h_err & ERR_UNSUPPORTED) return set_error(FTN_ERR_UNSUPPORTED, "the reference hits unimplemented!() on this input (env map_pdf == 0 or a null BSDF under the direct-lighting integrator)");
     return FTN_OK;
+}
+
+// ftn_render: device film from the arena (no per-call cudaMalloc/cudaFree), then one D2H copy.
+int render_host(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, const FtnSampler* smp,
+                const FtnIntegrator* integ, FtnPixel* out_pixels, FtnStats* stats) {
+    if (!s || !film || !out_pixels) return set_error(FTN_ERR_INVALID_ARGUMENT, "null argument");
+    int32_t w = 0, h = 0;
+    FTN_TRY(film_pixel_count(film, &w, &h));
+    if (s->device < 0 || s->device >= FTN_MAX_DEVICES) return set_error(FTN_ERR_INVALID_ARGUMENT, "device index out of range");
+    FTN_CUDA(cudaSetDevice(s->device));
+    const size_t bytes = (size_t)w * h * sizeof(FtnPixel);
+    DeviceArena& arena = g_arena[s->device];
+    FtnPixel* d_px = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(arena.m);
+        FTN_TRY(arena_reserve(&arena.film, &arena.film_bytes, bytes, "cudaMalloc (film)"));
+        d_px = (FtnPixel*)arena.film;
+    }
+    FTN_CUDA(cudaMemsetAsync(d_px, 0, bytes, nullptr));
+    const int render_rc = render_device(s, cam, film, smp, integ, d_px, stats, nullptr);
+    // like the reference's panic, a NaN / unsupported render still leaves the film readable
+    if (render_rc == FTN_OK || render_rc == FTN_ERR_NAN_RADIANCE || render_rc == FTN_ERR_UNSUPPORTED) {
+        const std::string keep = last_error_string();
+        cudaError_t e = cudaMemcpy(out_pixels, d_px, bytes, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return cuda_fail(e, "D2H film", __FILE__, __LINE__);
+        restore_error_string(keep);
+    }
+    return render_rc;
 }
 
 int film_to_rgb_device(size_t n, const FtnPixel* d_pixels, float* d_rgb, cudaStream_t st) {

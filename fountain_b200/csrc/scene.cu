@@ -330,7 +330,7 @@ int scene_destroy(FtnScene* s) {
     if (!s) return FTN_OK;
     cudaFree(s->d_pos); cudaFree(s->d_nrm); cudaFree(s->d_uv); cudaFree(s->d_idx);
     cudaFree(s->d_meshes); cudaFree(s->d_materials); cudaFree(s->d_spheres); cudaFree(s->d_lights);
-    cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_codes); cudaFree(s->d_order); cudaFree(s->d_work); cudaFree(s->ws);
+    cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_codes); cudaFree(s->d_order); cudaFree(s->d_work);
     for (void* p : s->owned) cudaFree(p);
     delete s;
     return FTN_OK;

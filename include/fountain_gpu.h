@@ -288,6 +288,11 @@ FTN_API int ftn_render_device(const FtnScene* scene, const FtnCamera* camera, co
  * n pixels; out_rgb is 3 floats per pixel.  Device buffers. */
 FTN_API int ftn_film_to_rgb_device(size_t n, const FtnPixel* d_pixels, float* d_rgb, void* stream);
 
+/* The library keeps one grow-only device arena per GPU for the wavefront path state (sized by the
+ * largest render so far) so that renders -- also of newly created scenes -- allocate nothing.
+ * This returns that memory to the driver; the next render allocates again. */
+FTN_API int ftn_release_cached_memory(void);
+
 /* Number of pixels ftn_render writes for this film (cropped_pixel_bounds area, film.rs:49-58). */
 FTN_API int ftn_film_pixel_count(const FtnFilm* film, int32_t* out_w, int32_t* out_h);
 
