@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "../../include/fountain_gpu.h"
@@ -127,8 +128,21 @@ namespace ftn {
 int scene_create(const FtnSceneDesc* d, FtnScene** out);
 int scene_destroy(FtnScene* s);
 int bvh_build(FtnScene* s);
-// device-wide exclusive scan of n uint32 (in place allowed: out may equal in)
-int exclusive_scan_u32(const uint32_t* d_in, uint32_t* d_out, size_t n, cudaStream_t st);
-// stable LSD radix sort of (key,value) pairs on `bits` low bits; result in d_keys/d_vals
-int radix_sort_pairs(uint32_t* d_keys, uint32_t* d_vals, size_t n, int bits, cudaStream_t st);
+// device-wide exclusive scan of n uint32 (in place allowed: out may equal in); scratch =
+// scan_scratch_elems(n) uint32.  Enqueue-only (no allocation, no synchronisation).
+size_t scan_scratch_elems(size_t n);
+int exclusive_scan_u32(const uint32_t* d_in, uint32_t* d_out, size_t n, uint32_t* d_scratch, cudaStream_t st);
+// stable LSD radix sort of (key,value) pairs on `bits` low bits; result in d_keys/d_vals; scratch =
+// radix_sort_scratch_bytes(n) bytes.  Enqueue-only.
+size_t radix_sort_scratch_bytes(size_t n);
+int radix_sort_pairs(uint32_t* d_keys, uint32_t* d_vals, size_t n, int bits, void* d_scratch, cudaStream_t st);
+// Process-wide grow-only device arenas (one set per GPU): the wavefront path state, the film of
+// host-buffer renders, the temporaries of a BVH build.  Callers hold the arena's mutex while they use it.
+struct DeviceArena {
+    void* p[3] = {nullptr, nullptr, nullptr}; size_t bytes[3] = {0, 0, 0}; std::mutex m;
+    enum { PATHS = 0, FILM = 1, BUILD = 2 };
+    int reserve(int which, size_t need, const char* what, void** out);
+};
+DeviceArena& device_arena(int device);
+int release_cached_memory();
 }  // namespace ftn

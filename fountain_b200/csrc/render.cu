@@ -293,32 +293,10 @@ int film_pixel_count(const FtnFilm* f, int32_t* w, int32_t* h) {
     return FTN_OK;
 }
 
-// Device workspace of the wavefront state: one grow-only arena per device for the whole process,
-// so that neither a second render nor a render of a NEW scene (the end-to-end path: upload, build,
-// render, read back) pays cudaMalloc/cudaFree of the path state.  Renders on one device serialise
-// on the arena's mutex (they would contend for the SMs anyway).  ftn_release_cached_memory() frees it.
-struct DeviceArena { void* p = nullptr; size_t bytes = 0; void* film = nullptr; size_t film_bytes = 0; std::mutex m; };
-static DeviceArena g_arena[FTN_MAX_DEVICES];
-static int arena_reserve(void** p, size_t* have, size_t bytes, const char* what) {
-    if (*have < bytes) {
-        if (*p) { cudaFree(*p); *p = nullptr; *have = 0; }
-        cudaError_t e = cudaMalloc(p, bytes);
-        if (e != cudaSuccess) { *p = nullptr; return cuda_fail(e, what, __FILE__, __LINE__); }
-        *have = bytes;
-    }
-    return FTN_OK;
-}
-int release_cached_memory() {
-    for (int d = 0; d < FTN_MAX_DEVICES; ++d) {
-        DeviceArena& a = g_arena[d];
-        std::lock_guard<std::mutex> lock(a.m);
-        if (!a.p && !a.film) continue;
-        if (cudaSetDevice(d) != cudaSuccess) continue;
-        cudaFree(a.p); cudaFree(a.film);
-        a.p = a.film = nullptr; a.bytes = a.film_bytes = 0;
-    }
-    return FTN_OK;
-}
+// Device workspace of the wavefront state: the process-wide grow-only arena of the device
+// (ftn_scene.h), so that neither a second render nor a render of a NEW scene (the end-to-end path:
+// upload, build, render, read back) pays cudaMalloc/cudaFree of the path state.  Renders on one
+// device serialise on the arena's mutex (they would contend for the SMs anyway).
 struct Carver {
     char* p; size_t off = 0;
     template <class T> T* take(size_t count) { off = (off + 255) & ~(size_t)255; T* r = reinterpret_cast<T*>(p + off); off += count * sizeof(T); return r; }
@@ -377,11 +355,10 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
     const size_t ws_bytes = 10 * (P * sizeof(float4) + 256) + 2 * (P * 4 + 256) + P * sizeof(float2) + 256 +
                             (size_t)fw * fh * sizeof(float4) + 256 + (size_t)(Q_COUNT + 1) * (P * 4 + 256) + n_spix + 4096;
     if (s->device < 0 || s->device >= FTN_MAX_DEVICES) return set_error(FTN_ERR_INVALID_ARGUMENT, "device index out of range");
-    DeviceArena& arena = g_arena[s->device];
+    DeviceArena& arena = device_arena(s->device);
     std::lock_guard<std::mutex> arena_lock(arena.m);
     Carver cv;
-    FTN_TRY(arena_reserve(&arena.p, &arena.bytes, ws_bytes, "cudaMalloc (render workspace)"));
-    cv.p = (char*)arena.p;
+    FTN_TRY(arena.reserve(DeviceArena::PATHS, ws_bytes, "cudaMalloc (render workspace)", (void**)&cv.p));
     PathArrays pa;
     pa.ray_o = cv.take<float4>(P); pa.ray_d = cv.take<float4>(P); pa.beta = cv.take<float4>(P); pa.L = cv.take<float4>(P);
     pa.sh_o = cv.take<float4>(P); pa.sh_d = cv.take<float4>(P); pa.sh_L = cv.take<float4>(P);
@@ -505,12 +482,11 @@ int render_host(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, co
     if (s->device < 0 || s->device >= FTN_MAX_DEVICES) return set_error(FTN_ERR_INVALID_ARGUMENT, "device index out of range");
     FTN_CUDA(cudaSetDevice(s->device));
     const size_t bytes = (size_t)w * h * sizeof(FtnPixel);
-    DeviceArena& arena = g_arena[s->device];
+    DeviceArena& arena = device_arena(s->device);
     FtnPixel* d_px = nullptr;
     {
         std::lock_guard<std::mutex> lock(arena.m);
-        FTN_TRY(arena_reserve(&arena.film, &arena.film_bytes, bytes, "cudaMalloc (film)"));
-        d_px = (FtnPixel*)arena.film;
+        FTN_TRY(arena.reserve(DeviceArena::FILM, bytes, "cudaMalloc (film)", (void**)&d_px));
     }
     FTN_CUDA(cudaMemsetAsync(d_px, 0, bytes, nullptr));
     const int render_rc = render_device(s, cam, film, smp, integ, d_px, stats, nullptr);

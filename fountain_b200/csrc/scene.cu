@@ -161,6 +161,29 @@ k_env_row_cdf(const float* __restrict__ func, int nu, int nv, float* __restrict_
     if (v < nv) dist_row_build(func + (size_t)v * nu, nu, cdf + (size_t)v * (nu + 1), integral + v);
 }
 
+static DeviceArena g_arena[FTN_MAX_DEVICES];
+DeviceArena& device_arena(int device) { return g_arena[(device >= 0 && device < FTN_MAX_DEVICES) ? device : 0]; }
+int DeviceArena::reserve(int which, size_t need, const char* what, void** out) {
+    if (bytes[which] < need) {
+        if (p[which]) { cudaFree(p[which]); p[which] = nullptr; bytes[which] = 0; }
+        cudaError_t e = cudaMalloc(&p[which], need);
+        if (e != cudaSuccess) { p[which] = nullptr; return cuda_fail(e, what, __FILE__, __LINE__); }
+        bytes[which] = need;
+    }
+    *out = p[which];
+    return FTN_OK;
+}
+int release_cached_memory() {
+    for (int d = 0; d < FTN_MAX_DEVICES; ++d) {
+        DeviceArena& a = g_arena[d];
+        std::lock_guard<std::mutex> lock(a.m);
+        if (!a.p[0] && !a.p[1] && !a.p[2]) continue;
+        if (cudaSetDevice(d) != cudaSuccess) continue;
+        for (int i = 0; i < 3; ++i) { cudaFree(a.p[i]); a.p[i] = nullptr; a.bytes[i] = 0; }
+    }
+    return FTN_OK;
+}
+
 SceneView make_view(const FtnScene& s) {
     SceneView v;
     v.bvh.nodes = s.d_nodes; v.bvh.tris = s.d_tris; v.bvh.n_nodes = s.n_nodes; v.bvh.n_tris = s.n_tris;
@@ -367,14 +390,27 @@ int bvh_build(FtnScene* s) {
         F4 *tri_lo = nullptr, *tri_hi = nullptr, *leaf_lo = nullptr, *leaf_hi = nullptr;
         uint32_t *keys = nullptr, *survive = nullptr, *is_record = nullptr;
         LbvhArrays a; std::memset(&a, 0, sizeof(a));
-        std::vector<void*> tmp;
+        // all temporaries come from the device's build arena: one (cached) allocation, no cudaFree
+        // (each of which would synchronise the device) per build
+        const size_t ni_max = n > 1 ? n - 1 : 1;
+        auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+        const size_t tmp_bytes = al(sizeof(BuildBounds)) + 4 * al((size_t)n * sizeof(F4)) + al((size_t)n * 4)
+                               + 7 * al(ni_max * 4) + al((2 * (size_t)n - 1) * 4) + 2 * al(ni_max * sizeof(F4))
+                               + al(radix_sort_scratch_bytes(n)) + al(scan_scratch_elems(ni_max) * 4) + 4096;
+        DeviceArena& arena = device_arena(s->device);
+        std::lock_guard<std::mutex> arena_lock(arena.m);
+        char* tmp_base = nullptr; size_t tmp_off = 0;
+        if ((rc = arena.reserve(DeviceArena::BUILD, tmp_bytes, "cudaMalloc (bvh build temporaries)", (void**)&tmp_base)) != FTN_OK) {
+            cudaEventDestroy(ev0); cudaEventDestroy(ev1); return rc;
+        }
         auto dalloc = [&](void** p, size_t bytes) -> int {
-            cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
-            if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc (bvh build)", __FILE__, __LINE__);
-            tmp.push_back(*p);
+            tmp_off = al(tmp_off);
+            if (tmp_off + bytes > tmp_bytes) return set_error(FTN_ERR_OUT_OF_MEMORY, "bvh build arena under-sized");
+            *p = tmp_base + tmp_off; tmp_off += bytes;
             return FTN_OK;
         };
-        auto cleanup = [&]() { for (void* p : tmp) cudaFree(p); };
+        auto cleanup = [&]() {};
+        void* sort_scratch = nullptr; uint32_t* scan_scratch = nullptr;
         const unsigned gb256 = (n + 255) / 256;
         do {
             if ((rc = dalloc((void**)&d_gb, sizeof(BuildBounds))) != FTN_OK) break;
@@ -388,7 +424,8 @@ int bvh_build(FtnScene* s) {
             k_tri_bounds<<<gb256, 256, 0, st>>>(s->d_pos, s->d_idx, n, tri_lo, tri_hi, d_gb); count_launch();
             k_morton<<<gb256, 256, 0, st>>>(tri_lo, tri_hi, n, d_gb, s->d_codes, keys, s->d_order); count_launch();
             if ((e = cudaGetLastError()) != cudaSuccess) { rc = cuda_fail(e, "bounds/morton kernels", __FILE__, __LINE__); break; }
-            if ((rc = radix_sort_pairs(keys, s->d_order, n, 30, st)) != FTN_OK) break;
+            if ((rc = dalloc(&sort_scratch, radix_sort_scratch_bytes(n))) != FTN_OK) break;
+            if ((rc = radix_sort_pairs(keys, s->d_order, n, 30, sort_scratch, st)) != FTN_OK) break;
             if ((rc = dalloc((void**)&leaf_lo, (size_t)n * sizeof(F4))) != FTN_OK) break;
             if ((rc = dalloc((void**)&leaf_hi, (size_t)n * sizeof(F4))) != FTN_OK) break;
             k_gather_leaf_boxes<<<gb256, 256, 0, st>>>(tri_lo, tri_hi, s->d_order, n, leaf_lo, leaf_hi); count_launch();
@@ -421,7 +458,8 @@ int bvh_build(FtnScene* s) {
                 k_lbvh_mark_records<<<gi, 256, 0, st>>>((int)n, a, survive, is_record); count_launch();
                 if ((e = cudaMemcpyAsync(&last_flag, is_record + ni - 1, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { rc = cuda_fail(e, "read record flags", __FILE__, __LINE__); break; }
                 uint32_t* new_index = a.arrive;   // reuse: arrival counters are dead after the refit
-                if ((rc = exclusive_scan_u32(is_record, new_index, ni, st)) != FTN_OK) break;
+                if ((rc = dalloc((void**)&scan_scratch, scan_scratch_elems(ni) * 4)) != FTN_OK) break;
+                if ((rc = exclusive_scan_u32(is_record, new_index, ni, scan_scratch, st)) != FTN_OK) break;
                 if ((e = cudaMemcpyAsync(&last_idx, new_index + ni - 1, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { rc = cuda_fail(e, "read scan", __FILE__, __LINE__); break; }
                 if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { rc = cuda_fail(e, "lbvh sync", __FILE__, __LINE__); break; }
                 s->n_nodes = last_idx + last_flag;

@@ -48,7 +48,13 @@ k_scan_add_offsets(uint32_t* __restrict__ out, const uint32_t* __restrict__ tile
     for (int i = 0; i < SCAN_ITEMS; ++i) if (base + i < n) out[base + i] += off;
 }
 
-int exclusive_scan_u32(const uint32_t* d_in, uint32_t* d_out, size_t n, cudaStream_t st) {
+// scratch: scan_scratch_elems(n) uint32.  Enqueues only: no allocation, no synchronisation.
+size_t scan_scratch_elems(size_t n) {
+    size_t total = 0;
+    while (n > (size_t)SCAN_TILE) { n = (n + SCAN_TILE - 1) / SCAN_TILE; total += (n + 63) & ~(size_t)63; }
+    return total + 64;
+}
+int exclusive_scan_u32(const uint32_t* d_in, uint32_t* d_out, size_t n, uint32_t* d_scratch, cudaStream_t st) {
     if (n == 0) return FTN_OK;
     const size_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     if (tiles == 1) {
@@ -56,21 +62,13 @@ int exclusive_scan_u32(const uint32_t* d_in, uint32_t* d_out, size_t n, cudaStre
         FTN_LAUNCHED();
         return FTN_OK;
     }
-    uint32_t* d_sums = nullptr;
-    FTN_CUDA(cudaMalloc(&d_sums, tiles * sizeof(uint32_t)));
+    uint32_t* d_sums = d_scratch;
     k_scan_tiles<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(d_in, d_out, d_sums, n);
     FTN_LAUNCHED();
-    int rc = exclusive_scan_u32(d_sums, d_sums, tiles, st);
-    if (rc == FTN_OK) {
-        k_scan_add_offsets<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(d_out, d_sums, n);
-        count_launch();
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) rc = cuda_fail(e, "k_scan_add_offsets", __FILE__, __LINE__);
-    }
-    cudaError_t e2 = cudaStreamSynchronize(st);
-    cudaFree(d_sums);
-    if (rc == FTN_OK && e2 != cudaSuccess) rc = cuda_fail(e2, "scan sync", __FILE__, __LINE__);
-    return rc;
+    FTN_TRY(exclusive_scan_u32(d_sums, d_sums, tiles, d_scratch + ((tiles + 63) & ~(size_t)63), st));
+    k_scan_add_offsets<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(d_out, d_sums, n);
+    FTN_LAUNCHED();
+    return FTN_OK;
 }
 
 // ---- radix sort ---------------------------------------------------------------------------------------
@@ -148,42 +146,42 @@ k_radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict
     }
 }
 
-int radix_sort_pairs(uint32_t* d_keys, uint32_t* d_vals, size_t n, int bits, cudaStream_t st) {
+// scratch: radix_sort_scratch_bytes(n) bytes, 256-byte aligned.  Enqueues only: no allocation, no
+// synchronisation.  The result lands in d_keys / d_vals.
+static size_t rs_tiles(size_t n) { return (n + RS_TILE - 1) / RS_TILE; }
+static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+size_t radix_sort_scratch_bytes(size_t n) {
+    const size_t hist = (size_t)RS_RADIX * rs_tiles(n);
+    return 2 * align256(n * 4) + align256(hist * 4) + align256(scan_scratch_elems(hist) * 4);
+}
+int radix_sort_pairs(uint32_t* d_keys, uint32_t* d_vals, size_t n, int bits, void* d_scratch, cudaStream_t st) {
     if (n < 2) return FTN_OK;
-    const uint32_t n_tiles = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
-    uint32_t *d_k2 = nullptr, *d_v2 = nullptr, *d_hist = nullptr;
-    int rc = FTN_OK;
-    cudaError_t e;
-    if ((e = cudaMalloc(&d_k2, n * sizeof(uint32_t))) != cudaSuccess) return cuda_fail(e, "cudaMalloc radix keys", __FILE__, __LINE__);
-    if ((e = cudaMalloc(&d_v2, n * sizeof(uint32_t))) != cudaSuccess) { cudaFree(d_k2); return cuda_fail(e, "cudaMalloc radix vals", __FILE__, __LINE__); }
-    if ((e = cudaMalloc(&d_hist, (size_t)RS_RADIX * n_tiles * sizeof(uint32_t))) != cudaSuccess) { cudaFree(d_k2); cudaFree(d_v2); return cuda_fail(e, "cudaMalloc radix hist", __FILE__, __LINE__); }
+    const uint32_t n_tiles = (uint32_t)rs_tiles(n);
+    char* p = (char*)d_scratch;
+    uint32_t* d_k2 = (uint32_t*)p; p += align256(n * 4);
+    uint32_t* d_v2 = (uint32_t*)p; p += align256(n * 4);
+    uint32_t* d_hist = (uint32_t*)p; p += align256((size_t)RS_RADIX * n_tiles * 4);
+    uint32_t* d_scan = (uint32_t*)p;
     uint32_t *kin = d_keys, *vin = d_vals, *kout = d_k2, *vout = d_v2;
     int passes = (bits + 7) / 8;
     if (passes & 1) passes += 1;   // even number of passes: the result lands in the caller's buffers
-    for (int p = 0; p < passes && rc == FTN_OK; ++p) {
-        const int shift = 8 * p;
+    for (int pass = 0; pass < passes; ++pass) {
+        const int shift = 8 * pass;
         if (shift >= 32) {   // padding pass: plain copy keeps the ping-pong parity
-            if ((e = cudaMemcpyAsync(kout, kin, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st)) != cudaSuccess ||
-                (e = cudaMemcpyAsync(vout, vin, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st)) != cudaSuccess)
-                rc = cuda_fail(e, "radix pad copy", __FILE__, __LINE__);
+            FTN_CUDA(cudaMemcpyAsync(kout, kin, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+            FTN_CUDA(cudaMemcpyAsync(vout, vin, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
         } else {
             k_radix_hist<<<n_tiles, RS_THREADS, 0, st>>>(kin, n, shift, d_hist, n_tiles);
-            count_launch();
-            if ((e = cudaGetLastError()) != cudaSuccess) { rc = cuda_fail(e, "k_radix_hist", __FILE__, __LINE__); break; }
-            rc = exclusive_scan_u32(d_hist, d_hist, (size_t)RS_RADIX * n_tiles, st);
-            if (rc != FTN_OK) break;
+            FTN_LAUNCHED();
+            FTN_TRY(exclusive_scan_u32(d_hist, d_hist, (size_t)RS_RADIX * n_tiles, d_scan, st));
             k_radix_scatter<<<n_tiles, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift, d_hist, n_tiles);
-            count_launch();
-            if ((e = cudaGetLastError()) != cudaSuccess) { rc = cuda_fail(e, "k_radix_scatter", __FILE__, __LINE__); break; }
+            FTN_LAUNCHED();
         }
         uint32_t* t;
         t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;
     }
-    e = cudaStreamSynchronize(st);
-    if (rc == FTN_OK && e != cudaSuccess) rc = cuda_fail(e, "radix sync", __FILE__, __LINE__);
-    cudaFree(d_k2); cudaFree(d_v2); cudaFree(d_hist);
-    return rc;
+    return FTN_OK;
 }
 
 }  // namespace ftn
