@@ -20,6 +20,8 @@ FTN_ERR_OUT_OF_MEMORY = -6
 FTN_MESH_FLIP_NORMALS = 1
 FTN_MATERIAL_MATTE, FTN_MATERIAL_METAL, FTN_MATERIAL_PLASTIC = 0, 1, 2
 FTN_LIGHT_INFINITE = 0
+FTN_LIGHT_POINT = 1
+FTN_LIGHT_DISTANT = 2
 FTN_SAMPLER_COUNTER, FTN_SAMPLER_REFERENCE_TILE_STREAM = 0, 1
 FTN_INTEGRATOR_PATH, FTN_INTEGRATOR_DIRECT_LIGHTING = 0, 1
 
@@ -54,7 +56,8 @@ class FtnSphere(C.Structure):
 
 class FtnLight(C.Structure):
     _fields_ = [("type", i32), ("texels", C.POINTER(f32)), ("width", i32), ("height", i32),
-                ("light_to_world", f32 * 16), ("world_to_light", f32 * 16)]
+                ("light_to_world", f32 * 16), ("world_to_light", f32 * 16),
+                ("point", f32 * 3), ("direction", f32 * 3), ("intensity", f32 * 3)]
 
 
 class FtnSceneDesc(C.Structure):

@@ -208,6 +208,38 @@ class InfiniteAreaLight:
         return InfiniteAreaLight(texels, light_to_world or Transform.identity())
 
 
+class PointLight:
+    """light/point.rs:16-28.  `make_point_light` (constructors.rs:330-337) builds light_to_world as a
+    translation to `from` only, so `PointLight.from_params(I, scale, from_)` ignores the CTM too."""
+
+    def __init__(self, light_to_world, intensity):
+        self.intensity = _spectrum(intensity)
+        self.world_point = light_to_world.apply_points_f32(np.zeros((1, 3), np.float32))[0]
+
+    @staticmethod
+    def from_params(I=1.0, scale=1.0, from_=(0.0, 0.0, 0.0)):
+        return PointLight(Transform.translate(from_), _spectrum(I) * _spectrum(scale))
+
+
+class DistantLight:
+    """light/distant.rs:18-31: `from_to(from, to, L)` -> direction towards the light = normalize(from - to)
+    (cgmath: v * (1 / |v|), evaluated here in f32 so that every backend receives the same vector)."""
+
+    def __init__(self, radiance, dir_to_light):
+        self.radiance = _spectrum(radiance)
+        d = _f32(dir_to_light).reshape(3)
+        mag = np.sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2], dtype=np.float32)
+        self.dir_to_light = d * (np.float32(1.0) / mag)
+
+    @staticmethod
+    def from_to(from_, to, radiance):
+        return DistantLight(radiance, _f32(from_).reshape(3) - _f32(to).reshape(3))
+
+    @staticmethod
+    def from_params(L=1.0, scale=1.0, from_=(0.0, 0.0, 0.0), to=(0.0, 0.0, 1.0)):   # constructors.rs:321-328
+        return DistantLight.from_to(from_, to, _spectrum(L) * _spectrum(scale))
+
+
 class GeometricPrimitive:
     """primitive.rs:25-29: a shape (TriangleMesh expands to one primitive per triangle, as
     PbrtSceneBuilder::shape does, loaders/pbrt.rs:275-317) with its material and area light."""
@@ -308,16 +340,28 @@ class Scene:
         self._light_texels = []
         c_lights = (A.FtnLight * max(1, len(lights)))()
         for i, l in enumerate(lights):
-            if not isinstance(l, InfiniteAreaLight):
-                raise NotImplementedError("only infinite area lights may be listed explicitly")
-            tex = _f32(l.texels)
-            self._light_texels.append(tex)
             cl = c_lights[i]
-            cl.type = A.FTN_LIGHT_INFINITE
-            cl.texels = _ptr(tex, A.f32)
-            cl.width, cl.height = l.width, l.height
-            cl.light_to_world[:] = l.light_to_world.flat().tolist()
-            cl.world_to_light[:] = l.light_to_world.flat_inv().tolist()
+            ident = Transform.identity()
+            if isinstance(l, InfiniteAreaLight):
+                tex = _f32(l.texels)
+                self._light_texels.append(tex)
+                cl.type = A.FTN_LIGHT_INFINITE
+                cl.texels = _ptr(tex, A.f32)
+                cl.width, cl.height = l.width, l.height
+                cl.light_to_world[:] = l.light_to_world.flat().tolist()
+                cl.world_to_light[:] = l.light_to_world.flat_inv().tolist()
+            elif isinstance(l, PointLight):
+                cl.type = A.FTN_LIGHT_POINT
+                cl.light_to_world[:] = ident.flat().tolist(); cl.world_to_light[:] = ident.flat().tolist()
+                cl.point[:] = l.world_point.tolist()
+                cl.intensity[:] = l.intensity.tolist()
+            elif isinstance(l, DistantLight):
+                cl.type = A.FTN_LIGHT_DISTANT
+                cl.light_to_world[:] = ident.flat().tolist(); cl.world_to_light[:] = ident.flat().tolist()
+                cl.direction[:] = l.dir_to_light.tolist()
+                cl.intensity[:] = l.radiance.tolist()
+            else:
+                raise NotImplementedError("lights listed explicitly must be infinite, point or distant")
 
         d = A.FtnSceneDesc()
         d.abi_version = A.FTN_ABI_VERSION

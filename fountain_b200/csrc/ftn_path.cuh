@@ -141,6 +141,18 @@ FTN_HD void sample_direct(const SceneView& sc, const Surface& s, const Bsdf& bsd
             const float two_r = rn_mul(2.0f, light.env.world_radius);
             p1 = x_add(s.p, x_scale(wi, two_r));   // infinite.rs:121-129: far endpoint, n = 0, p_err = 0
         }
+    } else if (light.type == 2) {   // point.rs:44-64
+        const V3 lp = V3(light.vec[0], light.vec[1], light.vec[2]);
+        const V3 d = x_sub(lp, s.p);
+        wi = x_normalize(d);
+        pdf = 1.0f;
+        Li = V3(light.emit[0], light.emit[1], light.emit[2]) / x_dot(d, d);
+        p1 = lp;
+    } else if (light.type == 3) {   // distant.rs:52-71
+        wi = V3(light.vec[0], light.vec[1], light.vec[2]);
+        pdf = 1.0f;
+        Li = V3(light.emit[0], light.emit[1], light.emit[2]);
+        p1 = x_add(s.p, x_scale(wi, rn_mul(2.0f, light.env.world_radius)));
     } else {   // diffuse.rs:74-89
         const SphereData& sd = sc.spheres[light.sphere];
         const ShapeSample ps = sphere_sample(sd, ul0, ul1);
@@ -156,12 +168,13 @@ FTN_HD void sample_direct(const SceneView& sc, const Surface& s, const Bsdf& bsd
             // VisibilityTester -> SurfaceHit::spawn_ray_to_hit, interaction.rs:48-58
             const V3 origin = offset_ray_origin(s.p, s.p_err, s.n, x_sub(p1, s.p));
             const V3 target = offset_ray_origin(p1, p1_err, p1_n, x_sub(origin, p1));
-            const float w = power_heuristic1(pdf, spdf);
+            const float w = (light.type >= 2) ? 1.0f : power_heuristic1(pdf, spdf);   // delta lights: f * Li / pdf (:331-332)
             out->has_shadow = true; out->sh_o = origin; out->sh_d = x_sub(target, origin);
             out->sh_L = scale * (nl * (f * Li * w / pdf));
         }
     }
     // --- BSDF sample ---
+    if (light.type >= 2) return;   // a delta light cannot be reached by sampling the BSDF (integrator/mod.rs:343)
     ScatterSample bs;
     if (bsdf_sample_f<MAT>(bsdf, s.wo, us0, us1, flags, &bs)) {
         const V3 f = bs.f * abs_dot(bs.wi, s.ns);

@@ -77,9 +77,10 @@ struct EnvLightData {
 };
 
 struct LightData {
-    int32_t type;            // 0 infinite, 1 diffuse area on a sphere
+    int32_t type;            // 0 infinite, 1 diffuse area on a sphere, 2 point, 3 distant
     int32_t sphere;          // area: sphere index
-    float emit[3];
+    float emit[3];           // area: L; point: I; distant: L
+    float vec[3];            // point: world position; distant: normalised direction towards the light
     EnvLightData env;
 };
 

@@ -154,8 +154,13 @@ k_shade_miss(SceneView sc, PassParams pp, PathArrays pa, const uint32_t* __restr
 }
 
 // ---- material-sorted shading: one launch per material class (QUEUE = Q_NULL, Q_MAT0..2) -------------------------
+#ifdef FTN_SHADE_MIN_BLOCKS             /* A/B: cap registers for more resident warps */
+#define FTN_SHADE_LAUNCH_BOUNDS __launch_bounds__(128, FTN_SHADE_MIN_BLOCKS)
+#else
+#define FTN_SHADE_LAUNCH_BOUNDS __launch_bounds__(128)
+#endif
 template <int QUEUE>
-__global__ void __launch_bounds__(128)
+__global__ void FTN_SHADE_LAUNCH_BOUNDS
 k_shade(SceneView sc, PassParams pp, PathArrays pa, const uint32_t* __restrict__ queue, Queues qs, uint32_t* __restrict__ counts, uint32_t* __restrict__ err) {
     const uint32_t n = counts[QUEUE];
     const uint32_t n32 = (n + 31u) & ~31u;

@@ -306,6 +306,13 @@ int scene_create(const FtnSceneDesc* d, FtnScene** out) {
     // explicit lights first, then area lights of emissive spheres in primitive order (scene/mod.rs:32-49)
     for (uint32_t l = 0; l < d->n_lights; ++l) {
         const FtnLight& fl = d->lights[l];
+        if (fl.type == FTN_LIGHT_POINT || fl.type == FTN_LIGHT_DISTANT) {   // light/point.rs, light/distant.rs
+            LightData ld; std::memset(&ld, 0, sizeof(ld));
+            ld.type = fl.type == FTN_LIGHT_POINT ? 2 : 3; ld.sphere = -1;
+            for (int c = 0; c < 3; ++c) { ld.emit[c] = fl.intensity[c]; ld.vec[c] = fl.type == FTN_LIGHT_POINT ? fl.point[c] : fl.direction[c]; }
+            s->h_lights.push_back(ld);
+            continue;
+        }
         if (fl.type != FTN_LIGHT_INFINITE || fl.width < 1 || fl.height < 1 || !fl.texels) return bail(set_error(FTN_ERR_INVALID_ARGUMENT, "bad light"));
         LightData ld; std::memset(&ld, 0, sizeof(ld));
         ld.type = 0; ld.sphere = -1;
@@ -489,7 +496,7 @@ int bvh_build(FtnScene* s) {
     // Scene::new -> Light::preprocess (infinite.rs:93-97): bounding sphere of the world bound (bounds.rs:208-212)
     bool lights_changed = false;
     for (LightData& ld : s->h_lights) {
-        if (ld.type != 0) continue;
+        if (ld.type != 0 && ld.type != 3) continue;   // infinite.rs:93-97, distant.rs:46-50
         float c[3], r2 = 0.0f;
         for (int a = 0; a < 3; ++a) c[a] = (lo[a] + hi[a]) / 2.0f;
         const float dx = hi[0] - c[0], dy = hi[1] - c[1], dz = hi[2] - c[2];

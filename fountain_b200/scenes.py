@@ -233,3 +233,30 @@ def logo_style_scene(backend=None, resolution=(1920, 1080), detail=1.0, env_size
                                    focal_dist=float(np.linalg.norm(look - eye)))
     film = api.Film(resolution, backend=backend)
     return scene, camera, film
+
+
+# ---- delta lights: a lit floor with an occluder ----------------------------------
+def delta_lights_scene(backend=None, resolution=(48, 48), lights=("point", "distant"), occluder=True, material=None, fov=50.0):
+    """A 10x10 floor quad at z = 0 (normal +z), an optional occluding quad at z = 1 over x in [1, 3],
+    a point light at (0, 0, 4) and/or a distant light arriving from direction (1, 0, 2); camera at
+    (0, -9, 7) looking at the origin.  No environment: unlit pixels are exactly black."""
+    def quad(x0, x1, y0, y1, z):
+        v = np.array([[x0, y0, z], [x1, y0, z], [x1, y1, z], [x0, y1, z]], np.float32)
+        return api.TriangleMesh(Transform.identity(), np.array([0, 1, 2, 0, 2, 3], np.uint32), v)
+    mat = material or api.MatteMaterial((0.6, 0.5, 0.4))
+    prims = [api.GeometricPrimitive(quad(-5, 5, -5, 5, 0.0), mat)]
+    if occluder:
+        prims.append(api.GeometricPrimitive(quad(1, 3, -1, 1, 1.0), mat))
+    ls = []
+    for name in lights:
+        if name == "point":
+            ls.append(api.PointLight.from_params(I=(30.0, 28.0, 26.0), from_=(0.0, 0.0, 4.0)))
+        elif name == "distant":
+            ls.append(api.DistantLight.from_params(L=(1.5, 1.6, 1.7), from_=(1.0, 0.0, 2.0), to=(0.0, 0.0, 0.0)))
+        else:
+            raise ValueError(name)
+    scene = api.Scene(prims, ls, backend=backend)
+    cam_to_world = Transform.look_at((0, -9, 7), (0, 0, 0), (0, 0, 1)).inverse()
+    camera = api.PerspectiveCamera(cam_to_world, resolution, fov=fov)
+    film = api.Film(resolution, backend=backend)
+    return scene, camera, film

@@ -119,17 +119,22 @@ typedef struct FtnSphere {
 } FtnSphere;
 
 typedef enum FtnLightType {
-    FTN_LIGHT_INFINITE = 0   /* light/infinite.rs:13-165 */
+    FTN_LIGHT_INFINITE = 0,  /* light/infinite.rs:13-165 */
+    FTN_LIGHT_POINT = 1,     /* light/point.rs:9-66   (delta position) */
+    FTN_LIGHT_DISTANT = 2    /* light/distant.rs:10-75 (delta direction) */
 } FtnLightType;
 
 /* Explicit `LightSource`s in file order (scene/mod.rs:32-49).  Area lights are implied by
  * emissive spheres and are appended after these, in primitive order. */
 typedef struct FtnLight {
     int32_t type;            /* FtnLightType */
-    const float* texels;     /* RGB f32, w*h*3, row-major (s fastest); level-0 of the MIPMap */
-    int32_t width, height;   /* 1x1 for new_uniform (infinite.rs:42-61) */
+    const float* texels;     /* INFINITE: RGB f32, w*h*3, row-major (s fastest); level-0 of the MIPMap */
+    int32_t width, height;   /* INFINITE: 1x1 for new_uniform (infinite.rs:42-61) */
     float light_to_world[16];
     float world_to_light[16];
+    float point[3];          /* POINT: world-space position, light_to_world * origin (point.rs:20) */
+    float direction[3];      /* DISTANT: NORMALISED direction towards the light (distant.rs:22; the host normalises) */
+    float intensity[3];      /* POINT: I, radiance = I / distance^2 (point.rs:56); DISTANT: L (distant.rs:66) */
 } FtnLight;
 
 typedef struct FtnSceneDesc {

@@ -504,6 +504,34 @@ struct InfiniteAreaLight {               // light/infinite.rs:23-61
     }
 };
 
+struct PointLight {                      // light/point.rs:16-28
+    Point3f world_point;
+    Spectrum intensity;
+    PointLight(const Transform& light_to_world, Spectrum i) : world_point(light_to_world.apply_point_f32({0, 0, 0})), intensity(i) {}
+};
+
+struct DistantLight {                    // light/distant.rs:18-31
+    Spectrum radiance;
+    Vec3f dir_to_light;                  // normalised in f32, cgmath order: v * (1 / |v|)
+    DistantLight(Spectrum l, Vec3f d) : radiance(l) {
+        float inv = 1.0f / std::sqrt((d.x * d.x + d.y * d.y) + d.z * d.z);
+        dir_to_light = Vec3f(d.x * inv, d.y * inv, d.z * inv);
+    }
+    static DistantLight from_to(Point3f from, Point3f to, Spectrum l) {
+        return DistantLight(l, Vec3f(from.x - to.x, from.y - to.y, from.z - to.z));
+    }
+};
+
+// One explicit `LightSource` (scene/mod.rs:32-49 takes them in file order)
+struct Light {
+    int type = FTN_LIGHT_INFINITE;
+    InfiniteAreaLight infinite;
+    Point3f point; Vec3f direction; Spectrum intensity;
+    Light(InfiniteAreaLight l) : type(FTN_LIGHT_INFINITE), infinite(std::move(l)) {}
+    Light(const PointLight& l) : type(FTN_LIGHT_POINT), point(l.world_point), intensity(l.intensity) {}
+    Light(const DistantLight& l) : type(FTN_LIGHT_DISTANT), direction(l.dir_to_light), intensity(l.radiance) {}
+};
+
 // primitive.rs:25-29; a TriangleMesh stands for one primitive per triangle (loaders/pbrt.rs:275-317)
 struct GeometricPrimitive {
     std::shared_ptr<TriangleMesh> mesh;
@@ -522,7 +550,7 @@ struct GeometricPrimitive {
 // ------------------------------------------------------------------------------------------
 class Scene {
 public:
-    Scene(LibraryPtr lib, const std::vector<GeometricPrimitive>& prims, const std::vector<InfiniteAreaLight>& lights = {},
+    Scene(LibraryPtr lib, const std::vector<GeometricPrimitive>& prims, const std::vector<Light>& lights = {},
           bool build = true)
         : lib_(std::move(lib)) {
         std::vector<const Material*> mats;
@@ -574,11 +602,17 @@ public:
         std::vector<FtnLight> cl(lights.size());
         for (size_t i = 0; i < lights.size(); ++i) {
             cl[i] = FtnLight{};
-            cl[i].type = FTN_LIGHT_INFINITE;
-            cl[i].texels = lights[i].texels.data();
-            cl[i].width = lights[i].width; cl[i].height = lights[i].height;
-            lights[i].light_to_world.flat(cl[i].light_to_world);
-            lights[i].light_to_world.flat_inv(cl[i].world_to_light);
+            cl[i].type = lights[i].type;
+            Transform l2w = lights[i].type == FTN_LIGHT_INFINITE ? lights[i].infinite.light_to_world : Transform::identity();
+            l2w.flat(cl[i].light_to_world);
+            l2w.flat_inv(cl[i].world_to_light);
+            if (lights[i].type == FTN_LIGHT_INFINITE) {
+                cl[i].texels = lights[i].infinite.texels.data();
+                cl[i].width = lights[i].infinite.width; cl[i].height = lights[i].infinite.height;
+            }
+            cl[i].point[0] = lights[i].point.x; cl[i].point[1] = lights[i].point.y; cl[i].point[2] = lights[i].point.z;
+            cl[i].direction[0] = lights[i].direction.x; cl[i].direction[1] = lights[i].direction.y; cl[i].direction[2] = lights[i].direction.z;
+            cl[i].intensity[0] = lights[i].intensity.r; cl[i].intensity[1] = lights[i].intensity.g; cl[i].intensity[2] = lights[i].intensity.b;
         }
         FtnSceneDesc d{};
         d.abi_version = FTN_ABI_VERSION;

@@ -101,6 +101,16 @@ ORC_API int orc_scene_create(const FtnSceneDesc* d, OrcScene** out) {
     }
     for (uint32_t i = 0; i < d->n_lights; ++i) {
         const FtnLight& fl = d->lights[i];
+        if (fl.type == FTN_LIGHT_POINT || fl.type == FTN_LIGHT_DISTANT) {
+            s.lights.emplace_back();
+            Light& l = s.lights.back();
+            l.type = fl.type == FTN_LIGHT_POINT ? 2 : 3; l.prims = &s.prims; l.prim = -1;
+            l.world_point = Point3(fl.point[0], fl.point[1], fl.point[2]);
+            l.dir_to_light = Vec3(fl.direction[0], fl.direction[1], fl.direction[2]);
+            l.intensity = Spectrum(fl.intensity[0], fl.intensity[1], fl.intensity[2]);
+            l.world_center = Point3(0, 0, 0); l.world_radius = 0.0f;
+            continue;
+        }
         if (fl.type != FTN_LIGHT_INFINITE || fl.width < 1 || fl.height < 1 || !fl.texels) { delete os; return fail(FTN_ERR_INVALID_ARGUMENT, "bad light"); }
         s.lights.emplace_back();
         Light& l = s.lights.back();

@@ -70,7 +70,8 @@ struct LiSample { Spectrum radiance; Vec3 wi; Float pdf; SurfaceHit p0, p1; };
 struct Scene;
 
 struct Light {
-    int type;   // 0 infinite, 1 diffuse area
+    int type;   // 0 infinite, 1 diffuse area, 2 point (light/point.rs), 3 distant (light/distant.rs)
+    Point3 world_point; Vec3 dir_to_light; Spectrum intensity;   // point: position + I; distant: direction + L
     // infinite (light/infinite.rs)
     EnvMap map; Distribution2D distribution;
     Transform light_to_world, world_to_light;
@@ -95,7 +96,7 @@ struct Light {
         }
         distribution.init(img.data(), width, height);
     }
-    bool is_delta() const { return false; }
+    bool is_delta() const { return type == 2 || type == 3; }   // LightFlags::is_delta_light, light/mod.rs:66-73
 
     // DiffuseAreaLight::emitted_radiance, diffuse.rs:45-51
     Spectrum area_emitted(const SurfaceHit& hit, Vec3 w) const { return (dot(hit.n, w) > 0.0f) ? emit : Spectrum(0.0f); }
@@ -126,6 +127,21 @@ struct Light {
             out->wi = wi; out->pdf = pdf;
             return true;
         }
+        if (type == 2) {   // point.rs:44-64
+            out->wi = normalize(world_point - reference.p);
+            out->pdf = 1.0f;
+            out->p0 = reference;
+            out->p1.p = world_point; out->p1.p_err = Vec3(0, 0, 0); out->p1.time = reference.time; out->p1.n = Vec3(0, 0, 0);
+            out->radiance = intensity / magnitude2(world_point - reference.p);
+            return true;
+        }
+        if (type == 3) {   // distant.rs:52-71
+            out->p0 = reference;
+            out->p1.p = reference.p + dir_to_light * (2.0f * world_radius);
+            out->p1.p_err = Vec3(0, 0, 0); out->p1.time = reference.time; out->p1.n = Vec3(0, 0, 0);
+            out->radiance = intensity; out->wi = dir_to_light; out->pdf = 1.0f;
+            return true;
+        }
         // diffuse.rs:74-89
         SurfaceHit p_shape = (*prims)[prim].sample(u0, u1);
         Vec3 wi = normalize(p_shape.p - reference.p);
@@ -142,6 +158,7 @@ struct Light {
             if (std::sin(theta) == 0.0f) return 0.0f;
             return distribution.pdf(phi * (1.0f / (2.0f * PI)), theta * FRAC_1_PI) / (2.0f * PI * PI * std::sin(theta));
         }
+        if (is_delta()) return 0.0f;                  // point.rs:65, distant.rs:73
         return shape_pdf_from_ref(reference, wi_w);   // diffuse.rs:91-93
     }
     Spectrum environment_emitted_radiance(const Ray& ray) const {   // infinite.rs:156-164; light/mod.rs:32 default
@@ -176,7 +193,7 @@ struct Scene {
     // Scene::new, :32-49: preprocess explicit lights, then append area lights in BVH-permuted order.
     void finish() {
         bvh.build(&prims);
-        for (Light& l : lights) if (l.type == 0) bvh.bounds.bounding_sphere(&l.world_center, &l.world_radius);
+        for (Light& l : lights) if (l.type == 0 || l.type == 3) bvh.bounds.bounding_sphere(&l.world_center, &l.world_radius);   // infinite.rs / distant.rs:46-50
         for (int slot = 0; slot < (int)bvh.prim_order.size(); ++slot) {
             Primitive& p = prims[bvh.prim_order[slot]];
             if (p.light == -2) {   // marked emissive by the builder
@@ -214,12 +231,16 @@ inline Spectrum estimate_direct(const Bsdf& bsdf, const SurfaceInteraction& isec
                 cx.ctr->rays_any++;
                 bool occluded = scene.intersect_test(ls.p0.spawn_ray_to_hit(ls.p1), tc);   // light/mod.rs:82-84
                 if (!occluded) {
-                    Float weight = power_heuristic(1, ls.pdf, 1, scattering_pdf);
-                    radiance = radiance + f * ls.radiance * weight / ls.pdf;
+                    if (light.is_delta()) radiance = radiance + f * ls.radiance / ls.pdf;   // :331-332
+                    else {
+                        Float weight = power_heuristic(1, ls.pdf, 1, scattering_pdf);
+                        radiance = radiance + f * ls.radiance * weight / ls.pdf;
+                    }
                 }
             }
         }
     }
+    if (light.is_delta()) return radiance;   // :343: a delta light cannot be hit by BSDF sampling
     ScatterSample sc;
     if (bsdf.sample_f(isect.wo, us0, us1, flags, &sc)) {
         Spectrum f = sc.f * abs_dot(sc.wi, isect.shading_n);

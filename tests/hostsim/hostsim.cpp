@@ -72,6 +72,12 @@ SIM_API int sim_scene_create(const FtnSceneDesc* d, SimScene** out) {
     for (uint32_t l = 0; l < d->n_lights; ++l) {
         const FtnLight& fl = d->lights[l];
         LightData ld; std::memset(&ld, 0, sizeof(ld)); ld.type = 0; ld.sphere = -1;
+        if (fl.type == FTN_LIGHT_POINT || fl.type == FTN_LIGHT_DISTANT) {   // as scene.cu
+            ld.type = fl.type == FTN_LIGHT_POINT ? 2 : 3;
+            for (int c = 0; c < 3; ++c) { ld.emit[c] = fl.intensity[c]; ld.vec[c] = fl.type == FTN_LIGHT_POINT ? fl.point[c] : fl.direction[c]; }
+            s->lights.push_back(ld);
+            continue;
+        }
         EnvLightData& e = ld.env;
         e.w = fl.width; e.h = fl.height; e.nu = fl.height; e.nv = fl.width;
         int mx = std::max(fl.width, fl.height), lv = 0; while ((1 << (lv + 1)) <= mx) ++lv;
@@ -176,7 +182,7 @@ SIM_API int sim_bvh_build(SimScene* s) {
     }
     for (int c = 0; c < 3; ++c) { s->bounds[c] = lo[c]; s->bounds[3 + c] = hi[c]; }
     for (LightData& ld : s->lights) {
-        if (ld.type != 0) continue;
+        if (ld.type != 0 && ld.type != 3) continue;
         float c[3]; for (int a = 0; a < 3; ++a) c[a] = (lo[a] + hi[a]) / 2.0f;
         const float dx = hi[0] - c[0], dy = hi[1] - c[1], dz = hi[2] - c[2];
         ld.env.world_radius = std::sqrt((dx * dx + dy * dy) + dz * dz);

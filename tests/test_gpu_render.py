@@ -148,3 +148,34 @@ def test_nan_radiance_is_reported(gpu_backend):
     with pytest.raises(api.FountainError) as e:
         api.SamplerIntegrator(camera, api.PathIntegrator(2, 1.0)).render_parallel(scene, film, api.RandomSampler.new_with_seed(1, 0))
     assert e.value.code in (A.FTN_ERR_NAN_RADIANCE, A.FTN_ERR_UNSUPPORTED)
+
+
+# ---- delta lights (light/point.rs, light/distant.rs) -------------------------------------------------
+@pytest.mark.parametrize("integrator", ["path", "direct"])
+def test_delta_lights_image_matches_oracle(gpu_backend, orc_backend, integrator):
+    integ = api.PathIntegrator(4, 1.0) if integrator == "path" else api.DirectLightingIntegrator(3)
+    a, apx, ast = parity.render(gpu_backend, scenes.delta_lights_scene, integ, 16, seed=5, resolution=(96, 96))
+    b, bpx, bst = parity.render(orc_backend, scenes.delta_lights_scene, integ, 16, seed=5, resolution=(96, 96))
+    mean_rel, frac_off = parity.image_diff(a, b)
+    assert mean_rel < 2e-3 and frac_off < 0.02, (mean_rel, frac_off)
+    assert np.array_equal(apx[..., 3], bpx[..., 3])
+    assert abs(ast["rays_any"] - bst["rays_any"]) <= 0.002 * bst["rays_any"]
+    assert abs(ast["rays_closest"] - bst["rays_closest"]) <= 0.002 * bst["rays_closest"]
+    assert b.max() > 0.1 and (b == 0.0).any()
+
+
+def test_delta_lights_with_envmap_and_metal(gpu_backend, orc_backend):
+    """Mixed light list (infinite + point + distant) on a TR conductor: the light pick, the MIS
+    branch for the infinite light and the no-MIS branch for the delta lights in one render."""
+    def build(backend, **kw):
+        scene, camera, film = scenes.rounded_cube_scene(backend=backend, resolution=(64, 64),
+                                                        material=api.MetalMaterial((0.2, 0.92, 1.1), (3.9, 2.45, 2.14), roughness=0.2))
+        mesh_prim = api.GeometricPrimitive(api.TriangleMesh.from_ply(scenes.ROUNDED_CUBE_PLY), api.MetalMaterial((0.2, 0.92, 1.1), (3.9, 2.45, 2.14), roughness=0.2))
+        lights = [api.InfiniteAreaLight.new_uniform(0.3), api.PointLight.from_params(I=4000.0, from_=(10.0, -30.0, 20.0)),
+                  api.DistantLight.from_params(L=2.0, from_=(-1.0, -1.0, 1.0), to=(0.0, 0.0, 0.0))]
+        scene.close()
+        return api.Scene([mesh_prim], lights, backend=backend), camera, film
+    a, _, _ = parity.render(gpu_backend, build, api.PathIntegrator(5, 1.0), 16, seed=9)
+    b, _, _ = parity.render(orc_backend, build, api.PathIntegrator(5, 1.0), 16, seed=9)
+    mean_rel, frac_off = parity.image_diff(a, b)
+    assert mean_rel < 3e-3 and frac_off < 0.03, (mean_rel, frac_off)

@@ -113,3 +113,16 @@ def test_reference_stream_is_rejected(sim_backend):
         api.SamplerIntegrator(camera, api.PathIntegrator(2, 1.0)).render_parallel(
             scene, film, api.RandomSampler.new_with_seed(1, 0, mode=A.FTN_SAMPLER_REFERENCE_TILE_STREAM))
     assert e.value.code == A.FTN_ERR_UNSUPPORTED
+
+
+# ---- delta lights (point.rs, distant.rs): device path logic vs oracle, same counter stream -----------
+@pytest.mark.parametrize("integrator", ["path", "direct"])
+def test_delta_lights_image_matches_oracle(sim_backend, orc_backend, integrator):
+    integ = api.PathIntegrator(4, 1.0) if integrator == "path" else api.DirectLightingIntegrator(3)
+    a, apx, ast = parity.render(sim_backend, scenes.delta_lights_scene, integ, 4, seed=5, resolution=(40, 40))
+    b, bpx, bst = parity.render(orc_backend, scenes.delta_lights_scene, integ, 4, seed=5, resolution=(40, 40))
+    mean_rel, frac_off = parity.image_diff(a, b)
+    assert mean_rel < 2e-3 and frac_off < 0.02, (mean_rel, frac_off)
+    assert np.array_equal(apx[..., 3], bpx[..., 3])
+    assert ast["rays_any"] == bst["rays_any"] and ast["rays_closest"] == bst["rays_closest"]
+    assert b.max() > 0.1 and (b == 0.0).any()            # lit floor, black shadow / background

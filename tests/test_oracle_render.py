@@ -76,3 +76,55 @@ def test_rounded_cube_render_sane(orc_backend):
     assert np.allclose(img[0, 0], 1.0, atol=1e-5)           # corner pixel sees only the environment
     assert 0.2 < img[24, 24].mean() < 1.0                    # the cube is darker than the sky
     assert stats["rays_any"] > 0 and stats["rays_closest"] > stats["camera_samples"]
+
+
+# ---- delta lights (light/point.rs, light/distant.rs) --------------------------------
+# The reference holds no test for them, so the restatement is pinned against the closed form of
+# direct lighting on a Lambertian floor: L = Kd/pi * I cos(theta) / d^2 (point), Kd/pi * L cos(theta) (distant).
+def _floor_radiance(scene_kw, integrator, orc_backend, spp):
+    from fountain_b200 import scenes
+    scene, camera, film = scenes.delta_lights_scene(backend=orc_backend, resolution=(9, 9), fov=2.0, occluder=False, **scene_kw)
+    # look straight down at the origin from (0, 0, 20): every pixel sees the floor within 0.4 units of the origin
+    from fountain_b200.transform import Transform
+    camera = api.PerspectiveCamera(Transform.look_at((0, 0, 20), (0, 0, 0), (0, 1, 0)).inverse(), (9, 9), fov=2.0)
+    api.SamplerIntegrator(camera, integrator).render_parallel(scene, film, api.RandomSampler.new_with_seed(spp, 1))
+    rgb, _ = film.into_spectrum_buffer()
+    return rgb.reshape(9, 9, 3)
+
+
+def test_point_light_closed_form(orc_backend):
+    rgb = _floor_radiance(dict(lights=("point",)), api.DirectLightingIntegrator(3), orc_backend, 4)
+    kd, inten, h = np.array([0.6, 0.5, 0.4]), np.array([30.0, 28.0, 26.0]), 4.0
+    expected = kd / np.pi * inten / h ** 2          # at the origin: d = 4, cos(theta) = 1
+    assert np.allclose(rgb[4, 4], expected, rtol=2e-3)
+    assert np.allclose(rgb, expected[None, None, :], rtol=0.03)          # cos/d^2 fall-off over +-0.35 units
+
+
+def test_distant_light_closed_form(orc_backend):
+    rgb = _floor_radiance(dict(lights=("distant",)), api.PathIntegrator(1, 1.0), orc_backend, 4)
+    kd, rad = np.array([0.6, 0.5, 0.4]), np.array([1.5, 1.6, 1.7])
+    cos_t = 2.0 / np.sqrt(5.0)                      # direction towards the light = normalize(1, 0, 2)
+    assert np.allclose(rgb, (kd / np.pi * rad * cos_t)[None, None, :], rtol=1e-4)
+
+
+def test_two_delta_lights_one_is_picked_per_sample(orc_backend):
+    """uniform_sample_one_light (integrator/mod.rs:289-305): one of the two lights, weighted by 2."""
+    rgb = _floor_radiance(dict(lights=("point", "distant")), api.DirectLightingIntegrator(3), orc_backend, 2048)
+    kd = np.array([0.6, 0.5, 0.4])
+    expected = kd / np.pi * (np.array([30.0, 28.0, 26.0]) / 16.0 + np.array([1.5, 1.6, 1.7]) * 2.0 / np.sqrt(5.0))
+    assert np.allclose(rgb[4, 4], expected, rtol=0.05)
+
+
+def test_delta_light_shadow(orc_backend):
+    """The occluder at z = 1 over x in [1, 3] shadows the floor from the point light at (0, 0, 4):
+    the shadow covers x in [4/3, 4] at y = 0; floor points there are exactly black."""
+    from fountain_b200 import scenes
+    from fountain_b200.transform import Transform
+    scene, _, film = scenes.delta_lights_scene(backend=orc_backend, resolution=(5, 5), lights=("point",))
+    camera = api.PerspectiveCamera(Transform.look_at((4.5, 0, 20), (4.5, 0, 0), (0, 1, 0)).inverse(), (5, 5), fov=1.0)   # x ~ 4.5: lit
+    api.SamplerIntegrator(camera, api.DirectLightingIntegrator(3)).render_parallel(scene, film, api.RandomSampler.new_with_seed(4, 0))
+    lit = film.into_spectrum_buffer()[0]
+    camera = api.PerspectiveCamera(Transform.look_at((3.5, 0, 20), (3.5, 0, 0), (0, 1, 0)).inverse(), (5, 5), fov=1.0)   # x ~ 3.5: in shadow
+    api.SamplerIntegrator(camera, api.DirectLightingIntegrator(3)).render_parallel(scene, film, api.RandomSampler.new_with_seed(4, 0))
+    dark = film.into_spectrum_buffer()[0]
+    assert np.all(lit > 0.05) and np.all(dark == 0.0)
