@@ -35,7 +35,9 @@ namespace ftn {
 #endif
 #define FTN_NODE_BYTES (16 * FTN_NODE_F4)
 
+#ifndef FTN_LEAF_MAX
 #define FTN_LEAF_MAX 4
+#endif
 #define FTN_STACK_SIZE 96   /* binary depth <= 62 (30 code bits + index bits); BVH4 pushes <= 3 per level of <= 31 */
 #define FTN_NO_HIT_SLOT 0xFFFFFFFFu
 #define FTN_SPHERE_SLOT_FLAG 0x80000000u

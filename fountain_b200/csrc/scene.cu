@@ -12,10 +12,12 @@
 //   k_gather_tris     48-byte pre-gathered triangle records in leaf order
 #include "ftn_scene.h"
 #include "ftn_lbvh.cuh"
+#include "ftn_ploc.cuh"
 #include <cstdlib>
 #define FTN_REFILL_THRESHOLD_DEFAULT 16
 #define FTN_VOTE_BIAS_DEFAULT 14
 #define FTN_VOTE_MIN_TRIS 65536u
+#define FTN_PLOC_MIN_TRIS 65536u
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -100,6 +102,73 @@ k_lbvh_refit(int n, LbvhArrays a, const F4* __restrict__ leaf_lo, const F4* __re
         lbvh_join_children(a, leaf_lo, leaf_hi, node);
         node = a.parent[node];
     }
+}
+
+// ---- PLOC topology (bodies in ftn_ploc.cuh) -------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_ploc_init(uint32_t n, uint32_t* __restrict__ cl) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) cl[i] = LBVH_LEAF_FLAG | i;
+}
+__global__ void __launch_bounds__(256)
+k_ploc_nearest(LbvhArrays a, const F4* __restrict__ leaf_lo, const F4* __restrict__ leaf_hi, const uint32_t* __restrict__ cl, uint32_t c,
+               uint32_t* __restrict__ nn) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < c) nn[i] = ploc_nearest(a, leaf_lo, leaf_hi, cl, c, i);
+}
+__global__ void __launch_bounds__(256)
+k_ploc_flags(const uint32_t* __restrict__ nn, uint32_t c, uint32_t* __restrict__ merge, uint32_t* __restrict__ valid) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < c) ploc_flags(nn, i, merge, valid);
+}
+// also leaves the number of merges of this round in *n_merged (read by the host to size the next round)
+__global__ void __launch_bounds__(256)
+k_ploc_merge(LbvhArrays a, const F4* __restrict__ leaf_lo, const F4* __restrict__ leaf_hi, const uint32_t* __restrict__ cl_in,
+             uint32_t* __restrict__ cl_out, const uint32_t* __restrict__ nn, const uint32_t* __restrict__ merge, const uint32_t* __restrict__ valid,
+             const uint32_t* __restrict__ mscan, const uint32_t* __restrict__ vscan, uint32_t n, uint32_t created, uint32_t c,
+             uint32_t* __restrict__ n_merged) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    ploc_merge(a, leaf_lo, leaf_hi, cl_in, cl_out, nn, merge, valid, mscan, vscan, n, created, i);
+    if (i == c - 1u) *n_merged = mscan[i] + merge[i];
+}
+// depth-first position of every leaf (and the deepest leaf), range of every internal node
+__global__ void __launch_bounds__(256)
+k_ploc_leaf_positions(LbvhArrays a, uint32_t n, uint32_t* __restrict__ newpos, uint32_t* __restrict__ max_depth) {
+    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n) return;
+    uint32_t d;
+    newpos[l] = ploc_dfs_position(a, n, LBVH_LEAF_FLAG | l, &d);
+    atomicMax(max_depth, d);
+}
+__global__ void __launch_bounds__(256)
+k_ploc_node_ranges(LbvhArrays a, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1u) return;
+    uint32_t d;
+    const uint32_t f = ploc_dfs_position(a, n, i, &d);
+    a.first[i] = f; a.last[i] = f + a.arrive[i] - 1u;
+}
+__global__ void __launch_bounds__(256)
+k_ploc_permute_leaves(uint32_t n, const uint32_t* __restrict__ newpos, const F4* __restrict__ lo_in, const F4* __restrict__ hi_in,
+                      const uint32_t* __restrict__ order_in, F4* __restrict__ lo_out, F4* __restrict__ hi_out, uint32_t* __restrict__ order_out) {
+    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n) return;
+    const uint32_t p = newpos[l];
+    lo_out[p] = lo_in[l]; hi_out[p] = hi_in[l]; order_out[p] = order_in[l];
+}
+__global__ void __launch_bounds__(256)
+k_ploc_rewrite_refs(LbvhArrays a, uint32_t n, const uint32_t* __restrict__ newpos) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1u) return;
+    const uint32_t l = a.left[i], r = a.right[i];
+    if (l & LBVH_LEAF_FLAG) a.left[i] = LBVH_LEAF_FLAG | newpos[l & ~LBVH_LEAF_FLAG];
+    if (r & LBVH_LEAF_FLAG) a.right[i] = LBVH_LEAF_FLAG | newpos[r & ~LBVH_LEAF_FLAG];
+}
+__global__ void __launch_bounds__(256)
+k_ploc_survive(int n, LbvhArrays a, uint32_t* __restrict__ survive) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n - 1) survive[i] = ploc_survives(a, i);
 }
 
 __global__ void __launch_bounds__(256)
@@ -397,13 +466,21 @@ int bvh_build(FtnScene* s) {
         F4 *tri_lo = nullptr, *tri_hi = nullptr, *leaf_lo = nullptr, *leaf_hi = nullptr;
         uint32_t *keys = nullptr, *survive = nullptr, *is_record = nullptr;
         LbvhArrays a; std::memset(&a, 0, sizeof(a));
+        // Topology builder: PLOC for scenes of >= FTN_PLOC_MIN_TRIS triangles, the Karras radix tree below that
+        // (and as the fallback for degenerate depth); FTN_BVH_BUILDER=ploc|lbvh overrides.  Measured on B200
+        // (profiles/r01_ab_ploc.txt): PLOC +2..6 % rays/s on the 1M-triangle sphere, +15 % on the gear-ring scene,
+        // +2.5 % on the 4332-triangle cube -- where its ~15 merge rounds (one host read-back each) cost 1.3 ms
+        // of build time against 0.15 ms saved per render, hence the size threshold.
+        const char* builder_env = getenv("FTN_BVH_BUILDER");
+        const bool use_ploc = builder_env ? std::string(builder_env) == "ploc" : n >= FTN_PLOC_MIN_TRIS;
         // all temporaries come from the device's build arena: one (cached) allocation, no cudaFree
         // (each of which would synchronise the device) per build
         const size_t ni_max = n > 1 ? n - 1 : 1;
         auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
         const size_t tmp_bytes = al(sizeof(BuildBounds)) + 4 * al((size_t)n * sizeof(F4)) + al((size_t)n * 4)
                                + 7 * al(ni_max * 4) + al((2 * (size_t)n - 1) * 4) + 2 * al(ni_max * sizeof(F4))
-                               + al(radix_sort_scratch_bytes(n)) + al(scan_scratch_elems(ni_max) * 4) + 4096;
+                               + al(radix_sort_scratch_bytes(n)) + al(scan_scratch_elems(ni_max) * 4) + 4096
+                               + (use_ploc ? 9 * al((size_t)n * 4) + 2 * al((size_t)n * sizeof(F4)) + al(scan_scratch_elems(n) * 4) + 4096 : 0);
         DeviceArena& arena = device_arena(s->device);
         std::lock_guard<std::mutex> arena_lock(arena.m);
         char* tmp_base = nullptr; size_t tmp_off = 0;
@@ -437,9 +514,9 @@ int bvh_build(FtnScene* s) {
             if ((rc = dalloc((void**)&leaf_hi, (size_t)n * sizeof(F4))) != FTN_OK) break;
             k_gather_leaf_boxes<<<gb256, 256, 0, st>>>(tri_lo, tri_hi, s->d_order, n, leaf_lo, leaf_hi); count_launch();
             if (!s->d_tris && (e = cudaMalloc(&s->d_tris, (size_t)n * 3 * sizeof(F4))) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc tris", __FILE__, __LINE__); break; }
-            k_gather_tris<<<gb256, 256, 0, st>>>(s->d_pos, s->d_idx, s->d_order, n, s->d_meshes, s->n_meshes, s->d_tris); count_launch();
-            if ((e = cudaGetLastError()) != cudaSuccess) { rc = cuda_fail(e, "gather kernels", __FILE__, __LINE__); break; }
+            const uint32_t* final_order = s->d_order;   // leaf order of the emitted tree; PLOC: depth-first order of its tree
             if (n <= (uint32_t)FTN_LEAF_MAX) {
+                k_gather_tris<<<gb256, 256, 0, st>>>(s->d_pos, s->d_idx, final_order, n, s->d_meshes, s->n_meshes, s->d_tris); count_launch();
                 if (!s->d_nodes && (e = cudaMalloc(&s->d_nodes, FTN_NODE_F4 * sizeof(F4))) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc nodes", __FILE__, __LINE__); break; }
                 k_lbvh_emit_single<<<1, 32, 0, st>>>(n, d_gb, s->d_nodes); count_launch();
                 s->n_nodes = 1;
@@ -455,11 +532,57 @@ int bvh_build(FtnScene* s) {
                 if ((rc = dalloc((void**)&a.node_hi, ni * sizeof(F4))) != FTN_OK) break;
                 if ((rc = dalloc((void**)&survive, ni * 4)) != FTN_OK) break;
                 if ((rc = dalloc((void**)&is_record, ni * 4)) != FTN_OK) break;
-                if ((e = cudaMemsetAsync(a.arrive, 0, ni * 4, st)) != cudaSuccess) { rc = cuda_fail(e, "memset arrive", __FILE__, __LINE__); break; }
                 const unsigned gi = (unsigned)((ni + 255) / 256);
-                k_lbvh_topology<<<gi, 256, 0, st>>>(keys, (int)n, a); count_launch();
-                k_lbvh_refit<<<gb256, 256, 0, st>>>((int)n, a, leaf_lo, leaf_hi); count_launch();
-                k_lbvh_survive<<<gi, 256, 0, st>>>((int)n, a, survive); count_launch();
+                bool ploc_done = false;
+                if (use_ploc) {
+                    // ---- PLOC: merge mutual nearest neighbours of the Morton order until one cluster is left ----
+                    uint32_t *cl0 = nullptr, *cl1 = nullptr, *nn = nullptr, *mg = nullptr, *va = nullptr, *ms = nullptr, *vs = nullptr, *newpos = nullptr, *order2 = nullptr, *d_small = nullptr;
+                    uint32_t* pscan = nullptr; F4 *lo2 = nullptr, *hi2 = nullptr;
+                    if ((rc = dalloc((void**)&cl0, (size_t)n * 4)) != FTN_OK || (rc = dalloc((void**)&cl1, (size_t)n * 4)) != FTN_OK ||
+                        (rc = dalloc((void**)&nn, (size_t)n * 4)) != FTN_OK || (rc = dalloc((void**)&mg, (size_t)n * 4)) != FTN_OK ||
+                        (rc = dalloc((void**)&va, (size_t)n * 4)) != FTN_OK || (rc = dalloc((void**)&ms, (size_t)n * 4)) != FTN_OK ||
+                        (rc = dalloc((void**)&vs, (size_t)n * 4)) != FTN_OK || (rc = dalloc((void**)&newpos, (size_t)n * 4)) != FTN_OK ||
+                        (rc = dalloc((void**)&order2, (size_t)n * 4)) != FTN_OK || (rc = dalloc((void**)&d_small, 64)) != FTN_OK ||
+                        (rc = dalloc((void**)&pscan, scan_scratch_elems(n) * 4)) != FTN_OK ||
+                        (rc = dalloc((void**)&lo2, (size_t)n * sizeof(F4))) != FTN_OK || (rc = dalloc((void**)&hi2, (size_t)n * sizeof(F4))) != FTN_OK) break;
+                    if ((e = cudaMemsetAsync(a.parent, 0xFF, (2 * (size_t)n - 1) * 4, st)) != cudaSuccess) { rc = cuda_fail(e, "memset parent", __FILE__, __LINE__); break; }
+                    if ((e = cudaMemsetAsync(d_small, 0, 64, st)) != cudaSuccess) { rc = cuda_fail(e, "memset", __FILE__, __LINE__); break; }
+                    k_ploc_init<<<gb256, 256, 0, st>>>(n, cl0); count_launch();
+                    uint32_t c = n, created = 0;
+                    uint32_t *cin = cl0, *cout = cl1;
+                    while (c > 1 && rc == FTN_OK) {
+                        const unsigned gc = (c + 255) / 256;
+                        k_ploc_nearest<<<gc, 256, 0, st>>>(a, leaf_lo, leaf_hi, cin, c, nn); count_launch();
+                        k_ploc_flags<<<gc, 256, 0, st>>>(nn, c, mg, va); count_launch();
+                        if ((rc = exclusive_scan_u32(mg, ms, c, pscan, st)) != FTN_OK) break;
+                        if ((rc = exclusive_scan_u32(va, vs, c, pscan, st)) != FTN_OK) break;
+                        k_ploc_merge<<<gc, 256, 0, st>>>(a, leaf_lo, leaf_hi, cin, cout, nn, mg, va, ms, vs, n, created, c, d_small); count_launch();
+                        uint32_t merged = 0;
+                        if ((e = cudaMemcpyAsync(&merged, d_small, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess || (e = cudaStreamSynchronize(st)) != cudaSuccess) { rc = cuda_fail(e, "PLOC round", __FILE__, __LINE__); break; }
+                        if (merged == 0 || merged > c / 2) { rc = set_error(FTN_ERR_CUDA, "PLOC round without progress"); break; }
+                        created += merged; c -= merged;
+                        std::swap(cin, cout);
+                    }
+                    if (rc != FTN_OK) break;
+                    k_ploc_leaf_positions<<<gb256, 256, 0, st>>>(a, n, newpos, d_small + 1); count_launch();
+                    uint32_t max_depth = 0;
+                    if ((e = cudaMemcpyAsync(&max_depth, d_small + 1, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess || (e = cudaStreamSynchronize(st)) != cudaSuccess) { rc = cuda_fail(e, "PLOC depth", __FILE__, __LINE__); break; }
+                    if (max_depth <= (uint32_t)FTN_STACK_SIZE - 4u) {   // else: a degenerate chain; the radix tree below is depth-bounded
+                        k_ploc_node_ranges<<<gi, 256, 0, st>>>(a, n); count_launch();
+                        k_ploc_permute_leaves<<<gb256, 256, 0, st>>>(n, newpos, leaf_lo, leaf_hi, s->d_order, lo2, hi2, order2); count_launch();
+                        k_ploc_rewrite_refs<<<gi, 256, 0, st>>>(a, n, newpos); count_launch();
+                        leaf_lo = lo2; leaf_hi = hi2; final_order = order2;
+                        k_ploc_survive<<<gi, 256, 0, st>>>((int)n, a, survive); count_launch();
+                        ploc_done = true;
+                    }
+                }
+                k_gather_tris<<<gb256, 256, 0, st>>>(s->d_pos, s->d_idx, final_order, n, s->d_meshes, s->n_meshes, s->d_tris); count_launch();
+                if (!ploc_done) {
+                    if ((e = cudaMemsetAsync(a.arrive, 0, ni * 4, st)) != cudaSuccess) { rc = cuda_fail(e, "memset arrive", __FILE__, __LINE__); break; }
+                    k_lbvh_topology<<<gi, 256, 0, st>>>(keys, (int)n, a); count_launch();
+                    k_lbvh_refit<<<gb256, 256, 0, st>>>((int)n, a, leaf_lo, leaf_hi); count_launch();
+                    k_lbvh_survive<<<gi, 256, 0, st>>>((int)n, a, survive); count_launch();
+                }
                 if ((e = cudaGetLastError()) != cudaSuccess) { rc = cuda_fail(e, "lbvh kernels", __FILE__, __LINE__); break; }
                 uint32_t last_flag = 0, last_idx = 0;
                 k_lbvh_mark_records<<<gi, 256, 0, st>>>((int)n, a, survive, is_record); count_launch();

@@ -15,6 +15,7 @@
 #include <vector>
 #include "../../fountain_b200/csrc/ftn_path.cuh"
 #include "../../fountain_b200/csrc/ftn_lbvh.cuh"
+#include "../../fountain_b200/csrc/ftn_ploc.cuh"
 
 using namespace ftn;
 
@@ -142,15 +143,53 @@ SIM_API int sim_bvh_build(SimScene* s) {
         std::vector<F4> leaf_lo(n), leaf_hi(n);
         for (uint32_t i = 0; i < n; ++i) { leaf_lo[i] = tri_lo[s->order[i]]; leaf_hi[i] = tri_hi[s->order[i]]; }
         s->tris.resize(3 * (size_t)n);
-        for (uint32_t i = 0; i < n; ++i) lbvh_gather_tri(s->pos.data(), s->idx.data(), s->order.data(), i, s->meshes.data(), (uint32_t)s->meshes.size(), s->tris.data());
+        std::vector<uint32_t> final_order = s->order;   // leaf order of the emitted tree (PLOC: depth-first order)
+        const char* builder_env = getenv("FTN_BVH_BUILDER");
+        const bool use_ploc = builder_env ? std::string(builder_env) == "ploc" : n >= 65536u;   // the policy of scene.cu
         if (n <= (uint32_t)FTN_LEAF_MAX) {
+            for (uint32_t i = 0; i < n; ++i) lbvh_gather_tri(s->pos.data(), s->idx.data(), final_order.data(), i, s->meshes.data(), (uint32_t)s->meshes.size(), s->tris.data());
             s->nodes.resize(FTN_NODE_F4); lbvh_emit_single(n, lo, hi, s->nodes.data()); s->n_nodes = 1;
         } else {
             const size_t ni = n - 1;
-            std::vector<uint32_t> left(ni), right(ni), first(ni), last(ni), parent(2 * (size_t)n - 1), arrive(ni, 0), survive(ni), new_index(ni);
+            std::vector<uint32_t> left(ni), right(ni), first(ni), last(ni), parent(2 * (size_t)n - 1, PLOC_NONE), arrive(ni, 0), survive(ni), new_index(ni);
             std::vector<F4> node_lo(ni), node_hi(ni);
             LbvhArrays a; a.left = left.data(); a.right = right.data(); a.first = first.data(); a.last = last.data();
             a.parent = parent.data(); a.arrive = arrive.data(); a.node_lo = node_lo.data(); a.node_hi = node_hi.data();
+            bool ploc_done = false;
+            if (use_ploc) {   // the kernels of scene.cu's ploc_build(), one element at a time
+                std::vector<uint32_t> cl0(n), cl1(n), nn(n), mg(n), va(n), ms(n), vs(n);
+                for (uint32_t i = 0; i < n; ++i) cl0[i] = LBVH_LEAF_FLAG | i;
+                uint32_t c = n, created = 0;
+                uint32_t *cin = cl0.data(), *cout = cl1.data();
+                while (c > 1) {
+                    for (uint32_t i = 0; i < c; ++i) nn[i] = ploc_nearest(a, leaf_lo.data(), leaf_hi.data(), cin, c, i);
+                    uint32_t m = 0, v = 0;
+                    for (uint32_t i = 0; i < c; ++i) { ploc_flags(nn.data(), i, mg.data(), va.data()); }
+                    for (uint32_t i = 0; i < c; ++i) { ms[i] = m; vs[i] = v; m += mg[i]; v += va[i]; }
+                    if (m == 0) return fail(FTN_ERR_CUDA, "PLOC round without a merge");
+                    for (uint32_t i = 0; i < c; ++i) ploc_merge(a, leaf_lo.data(), leaf_hi.data(), cin, cout, nn.data(), mg.data(), va.data(), ms.data(), vs.data(), n, created, i);
+                    created += m; c -= m; std::swap(cin, cout);
+                }
+                if (created != ni || cin[0] != 0u) return fail(FTN_ERR_CUDA, "PLOC did not end at root 0");
+                std::vector<uint32_t> newpos(n); uint32_t max_depth = 0;
+                for (uint32_t l = 0; l < n; ++l) { uint32_t d; newpos[l] = ploc_dfs_position(a, n, LBVH_LEAF_FLAG | l, &d); max_depth = std::max(max_depth, d); }
+                if (max_depth <= (uint32_t)FTN_STACK_SIZE - 4u) {
+                    for (size_t i = 0; i < ni; ++i) { uint32_t d; first[i] = ploc_dfs_position(a, n, (uint32_t)i, &d); last[i] = first[i] + arrive[i] - 1u; }
+                    std::vector<F4> l2(n), h2(n); std::vector<uint32_t> seen(n, 0);
+                    for (uint32_t l = 0; l < n; ++l) { l2[newpos[l]] = leaf_lo[l]; h2[newpos[l]] = leaf_hi[l]; final_order[newpos[l]] = s->order[l]; seen[newpos[l]]++; }
+                    for (uint32_t l = 0; l < n; ++l) if (seen[l] != 1u) return fail(FTN_ERR_CUDA, "PLOC leaf positions are not a permutation");
+                    for (size_t i = 0; i < ni; ++i) {
+                        if (left[i] & LBVH_LEAF_FLAG) left[i] = LBVH_LEAF_FLAG | newpos[left[i] & ~LBVH_LEAF_FLAG];
+                        if (right[i] & LBVH_LEAF_FLAG) right[i] = LBVH_LEAF_FLAG | newpos[right[i] & ~LBVH_LEAF_FLAG];
+                    }
+                    leaf_lo = l2; leaf_hi = h2;
+                    ploc_done = true;
+                } else {
+                    std::fill(parent.begin(), parent.end(), PLOC_NONE); std::fill(arrive.begin(), arrive.end(), 0u);
+                }
+            }
+            for (uint32_t i = 0; i < n; ++i) lbvh_gather_tri(s->pos.data(), s->idx.data(), final_order.data(), i, s->meshes.data(), (uint32_t)s->meshes.size(), s->tris.data());
+            if (!ploc_done) {
             for (size_t i = 0; i < ni; ++i) lbvh_topology_node(keys.data(), (int)n, (int)i, a);   // k_lbvh_topology
             for (uint32_t leaf = 0; leaf < n; ++leaf) {   // k_lbvh_refit: second arrival joins
                 uint32_t node = parent[n - 1 + leaf];
@@ -161,8 +200,9 @@ SIM_API int sim_bvh_build(SimScene* s) {
                 }
             }
             for (size_t i = 0; i < ni; ++i) { if (arrive[i] != 2u) return fail(FTN_ERR_CUDA, "refit did not reach every node twice"); }
+            }
             uint32_t run = 0;
-            for (size_t i = 0; i < ni; ++i) survive[i] = lbvh_survives(a, (int)i);                         // k_lbvh_survive
+            for (size_t i = 0; i < ni; ++i) survive[i] = ploc_done ? ploc_survives(a, (int)i) : lbvh_survives(a, (int)i);   // k_lbvh_survive
             std::vector<uint32_t> is_record(ni);
             for (size_t i = 0; i < ni; ++i) { is_record[i] = lbvh_is_record(a, survive.data(), (int)i); new_index[i] = run; run += is_record[i]; }   // mark + scan
             s->n_nodes = run; s->nodes.resize((size_t)FTN_NODE_F4 * (size_t)run);
@@ -538,4 +578,93 @@ SIM_API int sim_kat_slab_test(const float bmin[3], const float bmax[3], const Ft
                                                : slab_test<false>(s, bmin[0], bmax[0], bmin[1], bmax[1], bmin[2], bmax[2], ray->t_max, &e);
     out[0] = e;
     return (hit ? 1 : 0) | (s.nan_free ? 2 : 0);
+}
+
+// ---- design experiment: what would a SAH-quality tree buy?  (binned top-down SAH, same node format) ----
+namespace {
+struct SahBuilder {
+    const SimScene* s; std::vector<F4> lo, hi; std::vector<float> cx[3];
+    std::vector<uint32_t> prims;      // permutation being partitioned
+    std::vector<F4> nodes; std::vector<uint32_t> order_out;
+    int leaf_max; float c_trav, c_isect;
+    static float area(const float* l, const float* h) { float dx = h[0] - l[0], dy = h[1] - l[1], dz = h[2] - l[2]; return 2.0f * (dx * dy + dy * dz + dz * dx); }
+    void bounds(uint32_t b, uint32_t e, float* l, float* h) const {
+        for (int a = 0; a < 3; ++a) { l[a] = FLT_MAX; h[a] = -FLT_MAX; }
+        for (uint32_t i = b; i < e; ++i) { const F4& L = lo[prims[i]]; const F4& H = hi[prims[i]];
+            l[0] = fminf(l[0], L.x); l[1] = fminf(l[1], L.y); l[2] = fminf(l[2], L.z); h[0] = fmaxf(h[0], H.x); h[1] = fmaxf(h[1], H.y); h[2] = fmaxf(h[2], H.z); }
+    }
+    // returns child reference (>= 0 node index, < 0 leaf)
+    int build(uint32_t b, uint32_t e) {
+        const uint32_t n = e - b;
+        float bl[3], bh[3]; bounds(b, e, bl, bh);
+        int best_axis = -1; uint32_t best_mid = 0; float best_cost = FLT_MAX;
+        if (n > 1) {
+            const int NB = 32;
+            for (int ax = 0; ax < 3; ++ax) {
+                float cmin = FLT_MAX, cmax = -FLT_MAX;
+                for (uint32_t i = b; i < e; ++i) { cmin = fminf(cmin, cx[ax][prims[i]]); cmax = fmaxf(cmax, cx[ax][prims[i]]); }
+                if (!(cmax > cmin)) continue;
+                struct Bin { float l[3], h[3]; uint32_t c; } bins[NB];
+                for (auto& bn : bins) { bn.c = 0; for (int a = 0; a < 3; ++a) { bn.l[a] = FLT_MAX; bn.h[a] = -FLT_MAX; } }
+                const float scale = NB / (cmax - cmin);
+                for (uint32_t i = b; i < e; ++i) {
+                    int k = std::min(NB - 1, (int)((cx[ax][prims[i]] - cmin) * scale));
+                    Bin& bn = bins[k]; bn.c++; const F4& L = lo[prims[i]]; const F4& H = hi[prims[i]];
+                    bn.l[0] = fminf(bn.l[0], L.x); bn.l[1] = fminf(bn.l[1], L.y); bn.l[2] = fminf(bn.l[2], L.z);
+                    bn.h[0] = fmaxf(bn.h[0], H.x); bn.h[1] = fmaxf(bn.h[1], H.y); bn.h[2] = fmaxf(bn.h[2], H.z);
+                }
+                float ra[NB]; uint32_t rc[NB]; float l[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, h[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX}; uint32_t c = 0;
+                for (int k = NB - 1; k > 0; --k) { for (int a = 0; a < 3; ++a) { l[a] = fminf(l[a], bins[k].l[a]); h[a] = fmaxf(h[a], bins[k].h[a]); } c += bins[k].c; ra[k] = c ? area(l, h) : 0.0f; rc[k] = c; }
+                for (int a = 0; a < 3; ++a) { l[a] = FLT_MAX; h[a] = -FLT_MAX; } c = 0;
+                for (int k = 0; k < NB - 1; ++k) {
+                    for (int a = 0; a < 3; ++a) { l[a] = fminf(l[a], bins[k].l[a]); h[a] = fmaxf(h[a], bins[k].h[a]); } c += bins[k].c;
+                    if (c == 0 || rc[k + 1] == 0) continue;
+                    const float cost = area(l, h) * c + ra[k + 1] * rc[k + 1];
+                    if (cost < best_cost) { best_cost = cost; best_axis = ax; best_mid = (uint32_t)k; }
+                }
+                if (best_axis == ax) {   // remember the split plane for this axis
+                    split_plane[ax] = cmin + (best_mid + 1) / scale;
+                }
+            }
+        }
+        const float leaf_cost = c_isect * n;
+        const float split_cost = best_axis >= 0 ? c_trav + c_isect * best_cost / fmaxf(area(bl, bh), 1e-30f) : FLT_MAX;
+        if (n <= (uint32_t)leaf_max && (best_axis < 0 || leaf_cost <= split_cost)) {
+            const uint32_t first = (uint32_t)order_out.size();
+            for (uint32_t i = b; i < e; ++i) order_out.push_back(prims[i]);
+            return (int)~((first << 2) | (n - 1));
+        }
+        uint32_t mid;
+        if (best_axis < 0) mid = b + n / 2;   // coincident centroids: split in the middle
+        else {
+            const float plane = split_plane[best_axis]; const int ax = best_axis;
+            mid = (uint32_t)(std::partition(prims.begin() + b, prims.begin() + e, [&](uint32_t p) { return cx[ax][p] < plane; }) - prims.begin());
+            if (mid == b || mid == e) mid = b + n / 2;
+        }
+        const size_t me = nodes.size() / 4; nodes.resize(nodes.size() + 4);
+        float l0[3], h0[3], l1[3], h1[3]; bounds(b, mid, l0, h0); bounds(mid, e, l1, h1);
+        const int c0 = build(b, mid), c1 = build(mid, e);
+        F4 n0, n1, nz, ci;
+        n0.x = l0[0]; n0.y = h0[0]; n0.z = l0[1]; n0.w = h0[1]; n1.x = l1[0]; n1.y = h1[0]; n1.z = l1[1]; n1.w = h1[1];
+        nz.x = l0[2]; nz.y = h0[2]; nz.z = l1[2]; nz.w = h1[2]; ci.x = u2f((uint32_t)c0); ci.y = u2f((uint32_t)c1); ci.z = 0; ci.w = 0;
+        nodes[4 * me] = n0; nodes[4 * me + 1] = n1; nodes[4 * me + 2] = nz; nodes[4 * me + 3] = ci;
+        return (int)me;
+    }
+    float split_plane[3];
+};
+}  // namespace
+SIM_API int sim_bvh_rebuild_sah(SimScene* s, int leaf_max, float c_trav, float c_isect) {
+    const uint32_t n = s->n_tris;
+    if (n <= (uint32_t)FTN_LEAF_MAX) return FTN_OK;
+    SahBuilder B; B.s = s; B.leaf_max = leaf_max; B.c_trav = c_trav; B.c_isect = c_isect;
+    B.lo.resize(n); B.hi.resize(n); for (int a = 0; a < 3; ++a) B.cx[a].resize(n);
+    for (uint32_t i = 0; i < n; ++i) { float c[3]; tri_bounds_centroid(s->pos.data(), s->idx.data(), i, &B.lo[i], &B.hi[i], c); for (int a = 0; a < 3; ++a) B.cx[a][i] = c[a]; }
+    B.prims.resize(n); std::iota(B.prims.begin(), B.prims.end(), 0u);
+    B.nodes.reserve(4 * (size_t)n);
+    const int root = B.build(0, n);
+    if (root != 0) return fail(FTN_ERR_CUDA, "sah root");
+    s->nodes = B.nodes; s->n_nodes = (uint32_t)(B.nodes.size() / 4);
+    s->order = B.order_out;
+    for (uint32_t i = 0; i < n; ++i) lbvh_gather_tri(s->pos.data(), s->idx.data(), s->order.data(), i, s->meshes.data(), (uint32_t)s->meshes.size(), s->tris.data());
+    return FTN_OK;
 }

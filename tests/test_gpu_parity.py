@@ -136,3 +136,50 @@ def test_million_triangle_properties(gpu_backend):
     outside = api.make_rays(dirs * 40.0, -dirs)
     h2 = scene.intersect(outside)
     assert (h2["prim"] != A.FTN_NO_HIT).all() and np.all(np.abs(h2["t"] - 30.0) < 0.6)
+
+
+# ---- both topology builders (FTN_BVH_BUILDER): results must not depend on the tree ----------------------
+@pytest.mark.parametrize("builder", ["lbvh", "ploc"])
+@pytest.mark.parametrize("n_tris", [5, 6, 33, 2049])
+def test_builders_small_scenes(gpu_backend, orc_backend, monkeypatch, builder, n_tris):
+    monkeypatch.setenv("FTN_BVH_BUILDER", builder)
+    rng = np.random.default_rng(n_tris)
+    v = rng.uniform(-1, 1, (3 * n_tris, 3)).astype(np.float32)
+    t = np.arange(3 * n_tris, dtype=np.uint32).reshape(-1, 3)
+    mesh = api.TriangleMesh(Transform.identity(), t, v)
+    a = api.Scene([api.GeometricPrimitive(mesh)], [], backend=gpu_backend)
+    b = api.Scene([api.GeometricPrimitive(mesh)], [], backend=orc_backend)
+    parity.check_morton(a, b)                      # the debug hook reports the Morton order whatever the builder
+    rays = parity.random_ray_batch(5000, 200 + n_tris, extent=1.0, far=4.0)
+    parity.compare_hits(a.intersect(rays), b.intersect(rays), builder)
+    assert np.array_equal(a.intersect_test(rays), b.intersect_test(rays))
+
+
+@pytest.mark.parametrize("builder", ["lbvh", "ploc"])
+def test_builders_cube_and_sphere(gpu_backend, orc_backend, rounded_cube_path, monkeypatch, builder):
+    monkeypatch.setenv("FTN_BVH_BUILDER", builder)
+    a, b = parity.cube_scenes(gpu_backend, orc_backend, rounded_cube_path)
+    parity.check_morton(a, b)
+    parity.check_ray_batch(a, b, parity.random_ray_batch(100_000, 15), builder + " cube")
+    parity.check_watertight(a, n=100_000)
+    v, t, n = scenes.displaced_sphere_mesh(400, 200)
+    mesh = api.TriangleMesh(Transform.identity(), t, v, n)
+    a = api.Scene([api.GeometricPrimitive(mesh)], [], backend=gpu_backend)
+    b = api.Scene([api.GeometricPrimitive(mesh)], [], backend=orc_backend)
+    parity.check_ray_batch(a, b, parity.random_ray_batch(50_000, 19, extent=10.0, far=40.0), builder + " sphere")
+
+
+@pytest.mark.parametrize("builder", ["lbvh", "ploc"])
+def test_builders_degenerate_inputs(gpu_backend, orc_backend, monkeypatch, builder):
+    """Coincident triangles (all joined areas tie) and a geometric size progression (deep PLOC chain)."""
+    monkeypatch.setenv("FTN_BVH_BUILDER", builder)
+    base = np.array([[-1, -1, 0], [1, -1, 0], [0, 2, 0]], dtype=np.float32)
+    v = np.concatenate([base] * 40 + [base * np.float32(1.1 ** k) + np.float32([0, 0, -0.01 * k]) for k in range(1, 60)]).astype(np.float32)
+    t = np.arange(len(v), dtype=np.uint32).reshape(-1, 3)
+    mesh = api.TriangleMesh(Transform.identity(), t, v)
+    a = api.Scene([api.GeometricPrimitive(mesh)], [], backend=gpu_backend)
+    b = api.Scene([api.GeometricPrimitive(mesh)], [], backend=orc_backend)
+    rays = parity.random_ray_batch(4000, 23, extent=2.0, far=6.0)
+    ha, hb = a.intersect(rays), b.intersect(rays)
+    assert np.array_equal(ha["prim"] == A.FTN_NO_HIT, hb["prim"] == A.FTN_NO_HIT) and np.array_equal(ha["t"], hb["t"])
+    assert np.array_equal(a.intersect_test(rays), b.intersect_test(rays))

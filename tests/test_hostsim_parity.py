@@ -307,3 +307,31 @@ def test_slab_test_forms_match_reference(sim, oracle):
         if kind in (1, 2, 3, 4):
             assert not (got >> 1) & 1                     # irregular rays must take the exact form
     assert n_fast > 1500 and n_hit > 500
+
+
+# ---- both topology builders on the host-compiled build code (ftn_lbvh.cuh / ftn_ploc.cuh) ----------------
+@pytest.mark.parametrize("builder", ["lbvh", "ploc"])
+def test_builders_give_identical_results(sim_backend, orc_backend, rounded_cube_path, monkeypatch, builder):
+    monkeypatch.setenv("FTN_BVH_BUILDER", builder)
+    a, b = parity.cube_scenes(sim_backend, orc_backend, rounded_cube_path)
+    parity.check_morton(a, b)
+    parity.check_ray_batch(a, b, parity.random_ray_batch(20000, 15), builder)
+    for n_tris in (5, 6, 9, 33, 500):
+        rng = np.random.default_rng(n_tris)
+        v = rng.uniform(-1, 1, (3 * n_tris, 3)).astype(np.float32)
+        t = np.arange(3 * n_tris, dtype=np.uint32).reshape(-1, 3)
+        mesh = api.TriangleMesh(Transform.identity(), t, v)
+        sa = api.Scene([api.GeometricPrimitive(mesh)], [], backend=sim_backend)
+        sb = api.Scene([api.GeometricPrimitive(mesh)], [], backend=orc_backend)
+        rays = parity.random_ray_batch(3000, 300 + n_tris, extent=1.0, far=4.0)
+        parity.compare_hits(sa.intersect(rays), sb.intersect(rays), "%s %d" % (builder, n_tris))
+    # coincident triangles + a geometric size progression
+    base = np.array([[-1, -1, 0], [1, -1, 0], [0, 2, 0]], dtype=np.float32)
+    v = np.concatenate([base] * 40 + [base * np.float32(1.1 ** k) + np.float32([0, 0, -0.01 * k]) for k in range(1, 60)]).astype(np.float32)
+    t = np.arange(len(v), dtype=np.uint32).reshape(-1, 3)
+    mesh = api.TriangleMesh(Transform.identity(), t, v)
+    sa = api.Scene([api.GeometricPrimitive(mesh)], [], backend=sim_backend)
+    sb = api.Scene([api.GeometricPrimitive(mesh)], [], backend=orc_backend)
+    rays = parity.random_ray_batch(3000, 23, extent=2.0, far=6.0)
+    ha, hb = sa.intersect(rays), sb.intersect(rays)
+    assert np.array_equal(ha["prim"] == A.FTN_NO_HIT, hb["prim"] == A.FTN_NO_HIT) and np.array_equal(ha["t"], hb["t"])
