@@ -182,6 +182,18 @@ class PlasticMaterial:
         m.remap_roughness = int(self.remap)
 
 
+class MirrorMaterial:
+    """material/mirror.rs; Kr default 0.9 (constructors.rs:207-210)."""
+    type = A.FTN_MATERIAL_MIRROR
+
+    def __init__(self, kr=0.9):
+        self.kr = _spectrum(kr)
+
+    def fill(self, m):
+        m.type = self.type
+        m.kr[:] = self.kr.tolist()
+
+
 class DiffuseAreaLight:
     """light/diffuse.rs:24-41; attached to a shape through GeometricPrimitive.light."""
 

@@ -226,10 +226,22 @@ FTN_HD void shade_surface(const SceneView& sc, const PassParams& pp, uint32_t pa
     bsdf_init(&bsdf, s.ns, s.n, s.sdpdu);
     material_bsdf<M>(sc.materials[s.material], &bsdf);
     const uint64_t key = path_sample_key(pp, path, nullptr, nullptr);
-    const uint32_t dim0 = DIM_CAMERA + (direct_only ? 0u : (uint32_t)DIM_PER_BOUNCE * (uint32_t)bounces);
-    if (bsdf_num_components<M>(bsdf, BXDF_ALL & ~BXDF_SPECULAR) > 0)
-        sample_direct<M>(sc, s, bsdf, direct_only ? v3s(1.0f) : beta, key, dim0, &out->direct, err);
-    if (direct_only) return;
+    // under the direct-lighting integrator `bounces` is the recursion depth of specular_reflect
+    const uint32_t dim0 = DIM_CAMERA + (uint32_t)DIM_PER_BOUNCE * (uint32_t)bounces;
+    if (direct_only || bsdf_num_components<M>(bsdf, BXDF_ALL & ~BXDF_SPECULAR) > 0)   // path.rs:60 guards; direct_lighting.rs:79 does not
+        sample_direct<M>(sc, s, bsdf, beta, key, dim0, &out->direct, err);
+    if (direct_only) {
+        // specular_reflect (integrator/mod.rs:40-103): follow the mirror direction with depth + 1;
+        // the recursion is a chain, so it continues this path with beta *= f |wi.n| / pdf
+        if (bounces + 1 >= pp.max_depth) return;
+        ScatterSample rs;
+        if (!bsdf_sample_f<M>(bsdf, s.wo, sampler_uniform(key, dim0 + 5), sampler_uniform(key, dim0 + 6), BXDF_REFLECTION | BXDF_SPECULAR, &rs)) return;
+        if (abs_dot(rs.wi, s.ns) == 0.0f) return;
+        out->alive = true; out->next_o = spawn_origin(s, rs.wi); out->next_d = rs.wi;
+        out->beta = beta * (rs.f * fabsf(dot(rs.wi, s.ns)) / rs.pdf);
+        out->state = (uint32_t)(bounces + 1);
+        return;
+    }
     // continuation: Bsdf::sample_f(wo, get_2d(), ALL), path.rs:68-76
     const float u0 = sampler_uniform(key, dim0 + 5), u1 = sampler_uniform(key, dim0 + 6);
     ScatterSample cs;

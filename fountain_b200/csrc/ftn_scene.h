@@ -120,7 +120,7 @@ struct FtnScene {
     float bounds[6] = {0, 0, 0, 0, 0, 0};
     double build_seconds = 0.0;
     unsigned long long* d_work = nullptr;   // dynamic work-fetch counter of the batch queries
-    bool material_present[3] = {false, false, false};   // which shade kernels a render launches
+    bool material_present[4] = {false, false, false, false};   // which shade kernels a render launches
     bool has_null_material = false;         // any primitive with a null BSDF (path.rs:76-80)
     ftn::SceneView view() const;
 };

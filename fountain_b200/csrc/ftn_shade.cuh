@@ -208,7 +208,7 @@ enum { BXDF_REFLECTION = 1, BXDF_TRANSMISSION = 2, BXDF_DIFFUSE = 4, BXDF_GLOSSY
 
 // One lobe of a Bsdf (bsdf.rs holds up to 8 `dyn BxDF`; the in-scope materials produce at most 2).
 // KIND is a compile-time property of (material class, lobe slot): 0 LambertianReflection,
-// 1 MicrofacetReflection<TrowbridgeReitz, F>, -1 no such lobe.  Shading runs one kernel launch per
+// 1 MicrofacetReflection<TrowbridgeReitz, F>, 2 SpecularReflection<FresnelNoOp> (mirror), -1 no such lobe.  Shading runs one kernel launch per
 // material class over its queue, so the class is a template argument and the matte kernel
 // contains no microfacet / Fresnel code at all (it used 167 registers when the lobe kind was a
 // run-time field).
@@ -222,10 +222,13 @@ template <> struct LobeKind<FTN_MATERIAL_MATTE, 0> { static constexpr int value 
 template <> struct LobeKind<FTN_MATERIAL_METAL, 0> { static constexpr int value = 1; };
 template <> struct LobeKind<FTN_MATERIAL_PLASTIC, 0> { static constexpr int value = 0; };
 template <> struct LobeKind<FTN_MATERIAL_PLASTIC, 1> { static constexpr int value = 1; };
+template <> struct LobeKind<FTN_MATERIAL_MIRROR, 0> { static constexpr int value = 2; };
 // Fresnel of the microfacet lobe: 0 FresnelConductor{1, eta, k} (metal.rs:52-56), 1 FresnelDielectric{1.5, 1.0} (plastic.rs:34)
 template <int MAT> struct LobeFresnel { static constexpr int value = (MAT == FTN_MATERIAL_PLASTIC) ? 1 : 0; };
 
-template <int KIND> FTN_HD constexpr int lobe_type() { return KIND == 0 ? (BXDF_REFLECTION | BXDF_DIFFUSE) : (BXDF_REFLECTION | BXDF_GLOSSY); }
+template <int KIND> FTN_HD constexpr int lobe_type() {
+    return KIND == 0 ? (BXDF_REFLECTION | BXDF_DIFFUSE) : KIND == 1 ? (BXDF_REFLECTION | BXDF_GLOSSY) : (BXDF_REFLECTION | BXDF_SPECULAR);
+}
 template <int KIND> FTN_HD constexpr bool lobe_matches(int flags) { return KIND >= 0 && (flags & lobe_type<KIND>()) == lobe_type<KIND>(); }
 
 // microfacet.rs:135-160
@@ -271,6 +274,7 @@ template <int FRESNEL> FTN_HD V3 lobe_fresnel(const Lobe& l, float cos_i) {
 }
 template <int KIND, int FRESNEL> FTN_HD V3 lobe_f(const Lobe& l, V3 wo, V3 wi) {
     if (KIND == 0) return l.r * FTN_INV_PI;   // reflection/mod.rs:159-161
+    if (KIND == 2) return v3s(0.0f);           // reflection/mod.rs:181-183
     const float cos_o = abs_cos_theta(wo), cos_i = abs_cos_theta(wi);   // :318-336
     V3 wh = wi + wo;
     if (cos_i == 0.0f || cos_o == 0.0f || (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f)) return v3s(0.0f);
@@ -282,6 +286,7 @@ template <int KIND, int FRESNEL> FTN_HD V3 lobe_f(const Lobe& l, V3 wo, V3 wi) {
 }
 template <int KIND> FTN_HD float lobe_pdf(const Lobe& l, V3 wo, V3 wi) {
     if (KIND == 0) return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * FTN_INV_PI : 0.0f;   // :140-146
+    if (KIND == 2) return 0.0f;                // :194-196
     if (!same_hemisphere(wo, wi)) return 0.0f;   // :354-360
     const V3 wh = normalize(wo + wi);
     return tr_pdf(l, wh) / (4.0f * dot(wo, wh));
@@ -292,6 +297,11 @@ template <int KIND, int FRESNEL> FTN_HD bool lobe_sample_f(const Lobe& l, V3 wo,
         V3 wi = cosine_sample_hemisphere(u0, u1);
         if (wo.z < 0.0f) wi.z *= -1.0f;
         s->pdf = lobe_pdf<KIND>(l, wo, wi); s->f = lobe_f<KIND, FRESNEL>(l, wo, wi); s->wi = wi; s->type = lobe_type<KIND>();
+        return true;
+    }
+    if (KIND == 2) {   // reflection/mod.rs:185-192; FresnelNoOp evaluates to 1
+        const V3 wi = V3(-wo.x, -wo.y, wo.z);
+        s->pdf = 1.0f; s->f = (v3s(1.0f) * l.r) / abs_cos_theta(wi); s->wi = wi; s->type = lobe_type<KIND>();
         return true;
     }
     const V3 wh = tr_sample_wh(l, wo, u0, u1);   // :338-352
@@ -366,18 +376,24 @@ template <int MAT> FTN_HD bool bsdf_sample_f(const Bsdf& b, V3 wo_w, float u0, f
     const V3 wi = s.wi;
     const V3 wi_w = bsdf_to_world(b, wi);
     float pdf = s.pdf;
+    const bool specular = (s.type & BXDF_SPECULAR) != 0;   // bsdf.rs:106-127: a specular sample keeps its own pdf and f
     if (nm > 1) {
-        if (pick0) pdf += lobe_pdf<K1 < 0 ? 0 : K1>(b.l1, wo, wi);
-        else pdf += lobe_pdf<K0 < 0 ? 0 : K0>(b.l0, wo, wi);
+        if (!specular) {
+            if (pick0) pdf += lobe_pdf<K1 < 0 ? 0 : K1>(b.l1, wo, wi);
+            else pdf += lobe_pdf<K0 < 0 ? 0 : K0>(b.l0, wo, wi);
+        }
         pdf /= matching;
     }
-    const bool refl = dot(wi_w, b.ng) * dot(wo_w, b.ng) > 0.0f;
-    out->f = bsdf_sum_f<MAT>(b, wo, wi, refl, flags);
+    if (specular) out->f = s.f;
+    else {
+        const bool refl = dot(wi_w, b.ng) * dot(wo_w, b.ng) > 0.0f;
+        out->f = bsdf_sum_f<MAT>(b, wo, wi, refl, flags);
+    }
     out->wi = wi_w; out->pdf = pdf; out->type = s.type;
     return true;
 }
 
-// Material::compute_scattering_functions: matte.rs:36-52, metal.rs:38-65, plastic.rs:24-48
+// Material::compute_scattering_functions: matte.rs:36-52, metal.rs:38-65, plastic.rs:24-48, mirror.rs:21-30
 template <int MAT> FTN_HD void material_bsdf(const MaterialData& m, Bsdf* b) {
     if (MAT == FTN_MATERIAL_MATTE) {
         const V3 r = V3(clampf(m.kd[0], 0.0f, FTN_INF), clampf(m.kd[1], 0.0f, FTN_INF), clampf(m.kd[2], 0.0f, FTN_INF));
@@ -386,6 +402,9 @@ template <int MAT> FTN_HD void material_bsdf(const MaterialData& m, Bsdf* b) {
         b->on0 = true;
         b->l0.r = v3s(1.0f); b->l0.ax = m.alpha_x; b->l0.ay = m.alpha_y;
         b->l0.eta = V3(m.eta[0], m.eta[1], m.eta[2]); b->l0.k = V3(m.k[0], m.k[1], m.k[2]);
+    } else if (MAT == FTN_MATERIAL_MIRROR) {   // mirror.rs:21-30; Kr is carried in MaterialData::kd
+        const V3 r = V3(clampf(m.kd[0], 0.0f, FTN_INF), clampf(m.kd[1], 0.0f, FTN_INF), clampf(m.kd[2], 0.0f, FTN_INF));
+        if (!is_black(r)) { b->on0 = true; b->l0.r = r; }
     } else {
         const V3 kd = V3(m.kd[0], m.kd[1], m.kd[2]), ks = V3(m.ks[0], m.ks[1], m.ks[2]);
         if (!is_black(kd)) { b->on0 = true; b->l0.r = kd; }

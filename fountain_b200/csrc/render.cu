@@ -28,7 +28,7 @@ namespace ftn {
 int sm_count();
 unsigned trace_grid(size_t n, int blocks_per_sm);
 
-enum { Q_ACTIVE_OUT = 0, Q_MISS, Q_NULL, Q_MAT0, Q_MAT1, Q_MAT2, Q_SHADOW, Q_MIS, Q_COUNT };
+enum { Q_ACTIVE_OUT = 0, Q_MISS, Q_NULL, Q_MAT0, Q_MAT1, Q_MAT2, Q_MAT3, Q_SHADOW, Q_MIS, Q_COUNT };
 enum { W_EXTEND = Q_COUNT, W_SHADOW, W_MIS, CTR_COUNT };
 
 struct PathArrays {
@@ -425,6 +425,7 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
             if (s->material_present[0]) { k_shade<Q_MAT0><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT0], q, counts, d_err); FTN_LAUNCHED(); }
             if (s->material_present[1]) { k_shade<Q_MAT1><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT1], q, counts, d_err); FTN_LAUNCHED(); }
             if (s->material_present[2]) { k_shade<Q_MAT2><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT2], q, counts, d_err); FTN_LAUNCHED(); }
+            if (s->material_present[3]) { k_shade<Q_MAT3><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT3], q, counts, d_err); FTN_LAUNCHED(); }
             uint32_t hc[CTR_COUNT];
             FTN_CUDA(cudaMemcpyAsync(hc, counts, sizeof(hc), cudaMemcpyDeviceToHost, st));
             FTN_CUDA(cudaStreamSynchronize(st));

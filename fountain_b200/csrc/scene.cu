@@ -361,9 +361,10 @@ int scene_create(const FtnSceneDesc* d, FtnScene** out) {
         const FtnMaterial& fm = d->materials[m];
         MaterialData& md = mats[m];
         md.type = fm.type;
-        if (fm.type < FTN_MATERIAL_MATTE || fm.type > FTN_MATERIAL_PLASTIC) return bail(set_error(FTN_ERR_INVALID_ARGUMENT, "unknown material type"));
+        if (fm.type < FTN_MATERIAL_MATTE || fm.type > FTN_MATERIAL_MIRROR) return bail(set_error(FTN_ERR_INVALID_ARGUMENT, "unknown material type"));
         for (int c = 0; c < 3; ++c) { md.kd[c] = fm.kd[c]; md.ks[c] = fm.ks[c]; md.eta[c] = fm.eta[c]; md.k[c] = fm.k[c]; }
         float ur = fm.u_roughness, vr = fm.v_roughness;
+        if (fm.type == FTN_MATERIAL_MIRROR) for (int c = 0; c < 3; ++c) md.kd[c] = fm.kr[c];   // Kr travels in the kd slot
         if (fm.type == FTN_MATERIAL_PLASTIC) vr = ur;
         if (fm.remap_roughness) { ur = roughness_to_alpha_host(ur); vr = roughness_to_alpha_host(vr); }
         md.alpha_x = ur; md.alpha_y = vr;

@@ -260,3 +260,25 @@ def delta_lights_scene(backend=None, resolution=(48, 48), lights=("point", "dist
     camera = api.PerspectiveCamera(cam_to_world, resolution, fov=fov)
     film = api.Film(resolution, backend=backend)
     return scene, camera, film
+
+
+# ---- mirror (material/mirror.rs) -------------------------------------------------------
+def mirror_scene(backend=None, resolution=(48, 48), env=1.0, with_floor=True):
+    """A mirror quad (Kr .8) standing at y = 2 facing the camera, a matte floor at z = -1 and the rounded
+    cube's material-less twin replaced by a small matte box made of two quads; uniform environment plus a
+    point light so that the reflection shows lit diffuse surfaces."""
+    def quad(p0, p1, p2, p3):
+        v = np.array([p0, p1, p2, p3], np.float32)
+        return api.TriangleMesh(Transform.identity(), np.array([0, 1, 2, 0, 2, 3], np.uint32), v)
+    prims = [api.GeometricPrimitive(quad((-3, 2, -1), (3, 2, -1), (3, 2, 3), (-3, 2, 3)), api.MirrorMaterial((0.8, 0.7, 0.6)))]
+    if with_floor:
+        prims.append(api.GeometricPrimitive(quad((-6, -8, -1), (6, -8, -1), (6, 4, -1), (-6, 4, -1)), api.MatteMaterial((0.6, 0.5, 0.4))))
+        prims.append(api.GeometricPrimitive(quad((-1, -1, -1), (1, -1, -1), (1, -1, 1), (-1, -1, 1)), api.MatteMaterial((0.2, 0.6, 0.3))))
+    lights = [api.InfiniteAreaLight.new_uniform(env)]
+    if with_floor:
+        lights.append(api.PointLight.from_params(I=40.0, from_=(0.0, -2.0, 4.0)))
+    scene = api.Scene(prims, lights, backend=backend)
+    cam_to_world = Transform.look_at((0, -7, 1.5), (0, 2, 0.5), (0, 0, 1)).inverse()
+    camera = api.PerspectiveCamera(cam_to_world, resolution, fov=45.0)
+    film = api.Film(resolution, backend=backend)
+    return scene, camera, film

@@ -90,7 +90,8 @@ typedef struct FtnMeshDesc {
 typedef enum FtnMaterialType {
     FTN_MATERIAL_MATTE = 0,   /* material/matte.rs:36-52 (sigma must be 0: Lambert only) */
     FTN_MATERIAL_METAL = 1,   /* material/metal.rs:38-65 */
-    FTN_MATERIAL_PLASTIC = 2  /* material/plastic.rs:24-48 */
+    FTN_MATERIAL_PLASTIC = 2, /* material/plastic.rs:24-48 */
+    FTN_MATERIAL_MIRROR = 3   /* material/mirror.rs:21-30: SpecularReflection with FresnelNoOp */
 } FtnMaterialType;
 
 /* Constant-texture materials only (texture/mod.rs:34-42). */
@@ -103,6 +104,7 @@ typedef struct FtnMaterial {
     float u_roughness;       /* metal uroughness / plastic+metal isotropic roughness */
     float v_roughness;
     int32_t remap_roughness; /* constructors.rs:227 default true */
+    float kr[3];             /* mirror Kr (constructors.rs:207-210 default 0.9) */
 } FtnMaterial;
 
 /* shapes/sphere.rs:16-27 (+ the DiffuseAreaLight it may carry, light/diffuse.rs:24-41). */

@@ -481,6 +481,15 @@ struct PlasticMaterial : Material {      // material/plastic.rs; Kd = Ks = .25, 
     }
 };
 
+struct MirrorMaterial : Material {       // material/mirror.rs; Kr default 0.9 (constructors.rs:207-210)
+    Spectrum kr;
+    explicit MirrorMaterial(Spectrum kr_ = Spectrum(0.9f)) : kr(kr_) {}
+    void fill(FtnMaterial& m) const override {
+        m.type = FTN_MATERIAL_MIRROR;
+        m.kr[0] = kr.r; m.kr[1] = kr.g; m.kr[2] = kr.b;
+    }
+};
+
 struct DiffuseAreaLight {                // light/diffuse.rs:24-41
     Spectrum emit;
     explicit DiffuseAreaLight(Spectrum l = Spectrum(1.0f)) : emit(l) {}

@@ -334,10 +334,11 @@ inline Spectrum path_incident_radiance(Ray ray, int max_depth, Float rr_threshol
     return L;
 }
 
-// integrator/direct_lighting.rs:50-106 with LightStrategy::UniformSampleOne.  The specular
-// recursion (:93-96) only ever finds SPECULAR lobes, none of which are in scope, so
-// Bsdf::sample_f returns None before drawing (bsdf.rs:87) and both terms are zero -- but
-// sampler.get_2d() IS evaluated first as an argument (integrator/mod.rs:53,113).
+// integrator/direct_lighting.rs:50-106 with LightStrategy::UniformSampleOne, and the specular
+// recursion of integrator/mod.rs:40-178: specular_reflect / specular_transmit sample the BSDF with
+// (REFLECTION | SPECULAR) / (TRANSMISSION | SPECULAR) and recurse with depth + 1.  sampler.get_2d()
+// is evaluated as an argument even when no such lobe exists (integrator/mod.rs:53,113).  Ray
+// differentials are not carried (they only feed texture filtering, out of scope).
 inline Spectrum direct_incident_radiance(Ray ray, int max_depth, int depth, RenderCtx& cx, bool* unsupported_null) {
     const Scene& scene = *cx.scene;
     TraversalCounters* tc = cx.count_traversal ? &cx.ctr->trav : nullptr;
@@ -348,12 +349,19 @@ inline Spectrum direct_incident_radiance(Ray ray, int max_depth, int depth, Rend
     Spectrum radiance(0.0f);
     if (!compute_bsdf(scene, si, &bsdf)) { *unsupported_null = true; return radiance; }   // unimplemented!() :98
     radiance = radiance + scene.emitted_radiance(si, si.wo);
-    if (cx.sampler->mode == 0) cx.sampler->set_dim(DIM_CAMERA);
+    if (cx.sampler->mode == 0) cx.sampler->set_dim(DIM_CAMERA + DIM_PER_BOUNCE * (uint32_t)depth);
     radiance = radiance + uniform_sample_one_light(si, bsdf, cx);
     if (depth + 1 < max_depth) {
+        if (cx.sampler->mode == 0) cx.sampler->set_dim(DIM_CAMERA + DIM_PER_BOUNCE * (uint32_t)depth + 5);
         Float a, b;
-        cx.sampler->get_2d(&a, &b);   // specular_reflect's argument
-        cx.sampler->get_2d(&a, &b);   // specular_transmit's argument
+        cx.sampler->get_2d(&a, &b);   // specular_reflect, integrator/mod.rs:40-103
+        ScatterSample s;
+        if (bsdf.sample_f(si.wo, a, b, BXDF_REFLECTION | BXDF_SPECULAR, &s) && abs_dot(s.wi, si.shading_n) != 0.0f) {
+            Spectrum li = direct_incident_radiance(si.hit.spawn_ray(s.wi), max_depth, depth + 1, cx, unsupported_null);
+            radiance = radiance + s.f * li * std::fabs(dot(s.wi, si.shading_n)) / s.pdf;
+        }
+        if (cx.sampler->mode == 0) cx.sampler->set_dim(DIM_CAMERA + DIM_PER_BOUNCE * (uint32_t)depth + 7);
+        cx.sampler->get_2d(&a, &b);   // specular_transmit's argument: no transmissive specular lobe is in scope
     }
     return radiance;
 }

@@ -316,7 +316,7 @@ struct Sphere {
 // ---- materials / lights tables (constant textures) ----------------------------------------
 struct Material {
     int type;          // FtnMaterialType
-    Spectrum kd, ks, eta, k;
+    Spectrum kd, ks, eta, k, kr;
     Float u_rough, v_rough;
     bool remap;
 };

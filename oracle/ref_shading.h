@@ -173,14 +173,14 @@ struct ScatterSample { Spectrum f; Vec3 wi; Float pdf; int sampled_type; };
 // One lobe: Lambert (reflection/mod.rs:116-162) or Torrance-Sparrow with Trowbridge-Reitz
 // (reflection/mod.rs:301-361, microfacet.rs:119-186) and a conductor or dielectric Fresnel.
 struct BxDF {
-    int kind;            // 0 lambert, 1 microfacet
+    int kind;            // 0 lambert, 1 microfacet, 2 specular reflection with FresnelNoOp (reflection/mod.rs:165-197)
     Spectrum r;
     Float alpha_x, alpha_y;
     int fresnel;         // 0 conductor, 1 dielectric
     Spectrum eta_i, eta_t, k;
     Float d_eta_i, d_eta_t;
 
-    int get_type() const { return kind == 0 ? (BXDF_REFLECTION | BXDF_DIFFUSE) : (BXDF_REFLECTION | BXDF_GLOSSY); }
+    int get_type() const { return kind == 0 ? (BXDF_REFLECTION | BXDF_DIFFUSE) : kind == 1 ? (BXDF_REFLECTION | BXDF_GLOSSY) : (BXDF_REFLECTION | BXDF_SPECULAR); }
     bool matches(int flags) const { return (flags & get_type()) == get_type(); }
 
     Spectrum fresnel_eval(Float cos_i) const {
@@ -224,6 +224,7 @@ struct BxDF {
 
     Spectrum f(Vec3 wo, Vec3 wi) const {
         if (kind == 0) return r * FRAC_1_PI;   // reflection/mod.rs:159-161
+        if (kind == 2) return Spectrum(0.0f);   // :181-183
         // reflection/mod.rs:318-336
         Float cos_o = abs_cos_theta(wo), cos_i = abs_cos_theta(wi);
         Vec3 wh = wi + wo;
@@ -234,6 +235,7 @@ struct BxDF {
     }
     Float pdf(Vec3 wo, Vec3 wi) const {
         if (kind == 0) return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * FRAC_1_PI : 0.0f;   // :140-146
+        if (kind == 2) return 0.0f;   // :194-196
         if (!same_hemisphere(wo, wi)) return 0.0f;   // :354-360
         Vec3 wh = normalize(wo + wi);
         return tr_pdf(wo, wh) / (4.0f * dot(wo, wh));
@@ -243,6 +245,11 @@ struct BxDF {
             Vec3 wi = cosine_sample_hemisphere(u0, u1);
             if (wo.z < 0.0f) wi.z *= -1.0f;
             s->pdf = pdf(wo, wi); s->f = f(wo, wi); s->wi = wi; s->sampled_type = get_type();
+            return true;
+        }
+        if (kind == 2) {   // :185-192; FresnelNoOp::evaluate is Spectrum::uniform(1.0) (fresnel.rs)
+            Vec3 wi(-wo.x, -wo.y, wo.z);
+            s->pdf = 1.0f; s->f = Spectrum(1.0f) * r / abs_cos_theta(wi); s->wi = wi; s->sampled_type = get_type();
             return true;
         }
         Vec3 wh = tr_sample_wh(wo, u0, u1);   // :338-352
@@ -335,6 +342,9 @@ inline void compute_scattering_functions(const Material& m, const SurfaceInterac
         BxDF b{}; b.kind = 1; b.r = Spectrum(1.0f); b.alpha_x = ur; b.alpha_y = vr;
         b.fresnel = 0; b.eta_i = Spectrum(1.0f); b.eta_t = m.eta; b.k = m.k;
         bsdf->add(b);
+    } else if (m.type == 3) {   // mirror.rs:21-30
+        Spectrum r = m.kr.clamp_positive();
+        if (!r.is_black()) { BxDF b{}; b.kind = 2; b.r = r; bsdf->add(b); }
     } else {   // plastic.rs:24-48
         if (!m.kd.is_black()) { BxDF b{}; b.kind = 0; b.r = m.kd; bsdf->add(b); }
         if (!m.ks.is_black()) {

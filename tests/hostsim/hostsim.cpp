@@ -65,6 +65,7 @@ SIM_API int sim_scene_create(const FtnSceneDesc* d, SimScene** out) {
         const FtnMaterial& fm = d->materials[m]; MaterialData md; md.type = fm.type;
         for (int c = 0; c < 3; ++c) { md.kd[c] = fm.kd[c]; md.ks[c] = fm.ks[c]; md.eta[c] = fm.eta[c]; md.k[c] = fm.k[c]; }
         float ur = fm.u_roughness, vr = fm.v_roughness;
+        if (fm.type == FTN_MATERIAL_MIRROR) for (int c = 0; c < 3; ++c) md.kd[c] = fm.kr[c];   // Kr travels in the kd slot
         if (fm.type == FTN_MATERIAL_PLASTIC) vr = ur;
         if (fm.remap_roughness) { ur = roughness_to_alpha_host(ur); vr = roughness_to_alpha_host(vr); }
         md.alpha_x = ur; md.alpha_y = vr; s->mats.push_back(md);
@@ -336,6 +337,7 @@ SIM_API int sim_render(const SimScene* s, const FtnCamera* cam, const FtnFilm* f
                     case FTN_MATERIAL_MATTE: shade_surface<FTN_MATERIAL_MATTE>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err); break;
                     case FTN_MATERIAL_METAL: shade_surface<FTN_MATERIAL_METAL>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err); break;
                     case FTN_MATERIAL_PLASTIC: shade_surface<FTN_MATERIAL_PLASTIC>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err); break;
+                    case FTN_MATERIAL_MIRROR: shade_surface<FTN_MATERIAL_MIRROR>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err); break;
                     default: shade_surface<-1>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err); break;
                 }
                 Lp = o.L;
@@ -404,6 +406,7 @@ SIM_API void sim_kat_bsdf(const FtnMaterial* m, const float wo[3], const float w
 #define SIM_BSDF(M) { material_bsdf<M>(s->mats[0], &b); f = bsdf_f<M>(b, o, i, BXDF_ALL); pdf = bsdf_pdf<M>(b, o, i, BXDF_ALL); ok = bsdf_sample_f<M>(b, o, u[0], u[1], BXDF_ALL, &sm); }
     if (m->type == FTN_MATERIAL_MATTE) SIM_BSDF(FTN_MATERIAL_MATTE)
     else if (m->type == FTN_MATERIAL_METAL) SIM_BSDF(FTN_MATERIAL_METAL)
+    else if (m->type == FTN_MATERIAL_MIRROR) SIM_BSDF(FTN_MATERIAL_MIRROR)
     else SIM_BSDF(FTN_MATERIAL_PLASTIC)
 #undef SIM_BSDF
     out[0] = f.x; out[1] = f.y; out[2] = f.z; out[3] = pdf;

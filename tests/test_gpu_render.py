@@ -179,3 +179,23 @@ def test_delta_lights_with_envmap_and_metal(gpu_backend, orc_backend):
     b, _, _ = parity.render(orc_backend, build, api.PathIntegrator(5, 1.0), 16, seed=9)
     mean_rel, frac_off = parity.image_diff(a, b)
     assert mean_rel < 3e-3 and frac_off < 0.03, (mean_rel, frac_off)
+
+
+# ---- mirror (material/mirror.rs) ---------------------------------------------------------------------------
+@pytest.mark.parametrize("integrator", ["path", "direct2", "direct4"])
+def test_mirror_image_matches_oracle(gpu_backend, orc_backend, integrator):
+    integ = {"path": api.PathIntegrator(5, 1.0), "direct2": api.DirectLightingIntegrator(2), "direct4": api.DirectLightingIntegrator(4)}[integrator]
+    a, apx, ast = parity.render(gpu_backend, scenes.mirror_scene, integ, 16, seed=7, resolution=(96, 96))
+    b, bpx, bst = parity.render(orc_backend, scenes.mirror_scene, integ, 16, seed=7, resolution=(96, 96))
+    mean_rel, frac_off = parity.image_diff(a, b)
+    assert mean_rel < 2e-3 and frac_off < 0.02, (mean_rel, frac_off)
+    assert np.array_equal(apx[..., 3], bpx[..., 3])
+    assert abs(ast["rays_closest"] - bst["rays_closest"]) <= 0.002 * bst["rays_closest"]
+    assert abs(ast["rays_any"] - bst["rays_any"]) <= 0.002 * bst["rays_any"]
+
+
+def test_mirror_closed_form(gpu_backend):
+    scene, _, film = scenes.mirror_scene(backend=gpu_backend, resolution=(9, 9), with_floor=False)
+    camera = api.PerspectiveCamera(Transform.look_at((0, -7, 1.5), (0, 2, 1.0), (0, 0, 1)).inverse(), (9, 9), fov=5.0)
+    api.SamplerIntegrator(camera, api.PathIntegrator(5, 1.0)).render_parallel(scene, film, api.RandomSampler.new_with_seed(4, 0))
+    assert np.allclose(film.into_spectrum_buffer()[0], np.array([0.8, 0.7, 0.6])[None, :], rtol=1e-5)

@@ -126,3 +126,16 @@ def test_delta_lights_image_matches_oracle(sim_backend, orc_backend, integrator)
     assert np.array_equal(apx[..., 3], bpx[..., 3])
     assert ast["rays_any"] == bst["rays_any"] and ast["rays_closest"] == bst["rays_closest"]
     assert b.max() > 0.1 and (b == 0.0).any()            # lit floor, black shadow / background
+
+
+# ---- mirror: SpecularReflection lobe, specular-bounce flag, direct-lighting specular chain ------------
+@pytest.mark.parametrize("integrator", ["path", "direct2", "direct4"])
+def test_mirror_image_matches_oracle(sim_backend, orc_backend, integrator):
+    integ = {"path": api.PathIntegrator(5, 1.0), "direct2": api.DirectLightingIntegrator(2), "direct4": api.DirectLightingIntegrator(4)}[integrator]
+    a, apx, ast = parity.render(sim_backend, scenes.mirror_scene, integ, 4, seed=7, resolution=(40, 40))
+    b, bpx, bst = parity.render(orc_backend, scenes.mirror_scene, integ, 4, seed=7, resolution=(40, 40))
+    mean_rel, frac_off = parity.image_diff(a, b)
+    assert mean_rel < 2e-3 and frac_off < 0.02, (mean_rel, frac_off)
+    assert np.array_equal(apx[..., 3], bpx[..., 3])
+    assert abs(ast["rays_closest"] - bst["rays_closest"]) <= 0.002 * bst["rays_closest"]
+    assert abs(ast["rays_any"] - bst["rays_any"]) <= 0.002 * bst["rays_any"]

@@ -128,3 +128,41 @@ def test_delta_light_shadow(orc_backend):
     api.SamplerIntegrator(camera, api.DirectLightingIntegrator(3)).render_parallel(scene, film, api.RandomSampler.new_with_seed(4, 0))
     dark = film.into_spectrum_buffer()[0]
     assert np.all(lit > 0.05) and np.all(dark == 0.0)
+
+
+# ---- mirror (material/mirror.rs + SpecularReflection<FresnelNoOp>, reflection/mod.rs:165-197) ----------------
+# No reference test covers it: pinned against the closed form -- a mirror under a uniform environment
+# of radiance 1 returns exactly Kr (one specular bounce, pdf 1, f = Kr / |cos|, times |cos|).
+def test_mirror_closed_form_path(orc_backend):
+    from fountain_b200 import scenes
+    scene, camera, film = scenes.mirror_scene(backend=orc_backend, resolution=(9, 9), with_floor=False)
+    from fountain_b200.transform import Transform
+    camera = api.PerspectiveCamera(Transform.look_at((0, -7, 1.5), (0, 2, 1.0), (0, 0, 1)).inverse(), (9, 9), fov=5.0)
+    api.SamplerIntegrator(camera, api.PathIntegrator(5, 1.0)).render_parallel(scene, film, api.RandomSampler.new_with_seed(4, 0))
+    rgb = film.into_spectrum_buffer()[0]
+    assert np.allclose(rgb, np.array([0.8, 0.7, 0.6])[None, :], rtol=1e-5)
+    # depth 0: the camera ray hits the mirror, nothing is added (no emission, no non-specular lobe)
+    api.SamplerIntegrator(camera, api.PathIntegrator(0, 1.0)).render_parallel(scene, film, api.RandomSampler.new_with_seed(4, 0))
+    assert np.all(film.into_spectrum_buffer()[0] == 0.0)
+
+
+def test_mirror_closed_form_direct_lighting(orc_backend):
+    """specular_reflect (integrator/mod.rs:40-103): with max_depth 2 the mirror shows Kr * environment,
+    with max_depth 1 the recursion is cut (depth + 1 < max_depth fails) and the mirror is black."""
+    from fountain_b200 import scenes
+    from fountain_b200.transform import Transform
+    scene, _, film = scenes.mirror_scene(backend=orc_backend, resolution=(9, 9), with_floor=False)
+    camera = api.PerspectiveCamera(Transform.look_at((0, -7, 1.5), (0, 2, 1.0), (0, 0, 1)).inverse(), (9, 9), fov=5.0)
+    api.SamplerIntegrator(camera, api.DirectLightingIntegrator(2)).render_parallel(scene, film, api.RandomSampler.new_with_seed(4, 0))
+    assert np.allclose(film.into_spectrum_buffer()[0], np.array([0.8, 0.7, 0.6])[None, :], rtol=1e-5)
+    api.SamplerIntegrator(camera, api.DirectLightingIntegrator(1)).render_parallel(scene, film, api.RandomSampler.new_with_seed(4, 0))
+    assert np.all(film.into_spectrum_buffer()[0] == 0.0)
+
+
+@pytest.mark.parametrize("mode", [A.FTN_SAMPLER_COUNTER, A.FTN_SAMPLER_REFERENCE_TILE_STREAM])
+def test_mirror_scene_renders_in_both_sampler_modes(orc_backend, mode):
+    from fountain_b200 import scenes
+    scene, camera, film = scenes.mirror_scene(backend=orc_backend, resolution=(32, 32))
+    api.SamplerIntegrator(camera, api.PathIntegrator(5, 1.0)).render_parallel(scene, film, api.RandomSampler.new_with_seed(16, 0, mode=mode))
+    rgb = film.into_spectrum_buffer()[0]
+    assert np.isfinite(rgb).all() and rgb.mean() > 0.1
