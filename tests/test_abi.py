@@ -64,3 +64,28 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")) or f == "Makefile":
                 src = open(os.path.join(dirpath, f)).read()
                 assert not bad.search(src), os.path.join(dirpath, f)
+
+
+def test_ctypes_structs_match_the_compiled_header(tmp_path):
+    """sizeof / offsetof of every ABI struct as gcc lays the header out == the ctypes mirror in
+    fountain_b200/_abi.py (a stale mirror would silently shift array strides)."""
+    import subprocess
+    structs = ["FtnRay", "FtnHit", "FtnMeshDesc", "FtnMaterial", "FtnSphere", "FtnLight", "FtnSceneDesc", "FtnCamera", "FtnFilm",
+               "FtnSampler", "FtnIntegrator", "FtnPixel", "FtnStats"]
+    lines = []
+    for s in structs:
+        lines.append('printf("%s %%zu", sizeof(%s));' % (s, s))
+        for name, _ in getattr(A, s)._fields_:
+            lines.append('printf(" %%zu", offsetof(%s, %s));' % (s, name))
+        lines.append('printf("\\n");')
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "fountain_gpu.h"\nint main(void) {\n' + "\n".join(lines) + "\nreturn 0; }\n")
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    for line in out:
+        parts = line.split()
+        cls = getattr(A, parts[0])
+        assert C.sizeof(cls) == int(parts[1]), parts[0]
+        for (name, _), off in zip(cls._fields_, parts[2:]):
+            assert getattr(cls, name).offset == int(off), (parts[0], name)
