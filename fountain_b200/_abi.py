@@ -19,6 +19,7 @@ FTN_ERR_OUT_OF_MEMORY = -6
 
 FTN_MESH_FLIP_NORMALS = 1
 FTN_MATERIAL_MATTE, FTN_MATERIAL_METAL, FTN_MATERIAL_PLASTIC, FTN_MATERIAL_MIRROR = 0, 1, 2, 3
+FTN_TEXTURE_CONSTANT, FTN_TEXTURE_CHECKERBOARD, FTN_TEXTURE_UV = 0, 1, 2
 FTN_LIGHT_INFINITE = 0
 FTN_LIGHT_POINT = 1
 FTN_LIGHT_DISTANT = 2
@@ -45,7 +46,8 @@ class FtnMeshDesc(C.Structure):
 
 class FtnMaterial(C.Structure):
     _fields_ = [("type", i32), ("kd", f32 * 3), ("ks", f32 * 3), ("eta", f32 * 3), ("k", f32 * 3),
-                ("u_roughness", f32), ("v_roughness", f32), ("remap_roughness", i32), ("kr", f32 * 3)]
+                ("u_roughness", f32), ("v_roughness", f32), ("remap_roughness", i32), ("kr", f32 * 3),
+                ("kd_texture", i32), ("tex1", f32 * 3), ("tex2", f32 * 3), ("uv_scale", f32 * 2), ("uv_delta", f32 * 2)]
 
 
 class FtnSphere(C.Structure):

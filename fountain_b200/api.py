@@ -133,16 +133,58 @@ class Sphere:
         self.phi_max = float(phi_max)
 
 
+class UVMapping:
+    """texture/mapping.rs:13-53; defaults uscale = vscale = 1, udelta = vdelta = 0 (constructors.rs:251-254)."""
+
+    def __init__(self, scale_u=1.0, scale_v=1.0, offset_u=0.0, offset_v=0.0):
+        self.scale = (float(scale_u), float(scale_v))
+        self.offset = (float(offset_u), float(offset_v))
+
+
+class Checkerboard2DTexture:
+    """texture/checkerboard.rs:10-64 over two constant spectra (AAMethod::None)."""
+    type = A.FTN_TEXTURE_CHECKERBOARD
+
+    def __init__(self, tex1=0.0, tex2=1.0, mapping=None):
+        self.tex1, self.tex2 = _spectrum(tex1), _spectrum(tex2)
+        self.mapping = mapping or UVMapping()
+
+    @staticmethod
+    def default():   # checkerboard.rs:38-42
+        return Checkerboard2DTexture(0.0, 1.0, UVMapping(10.0, 10.0, 0.0, 0.0))
+
+
+class UVTexture:
+    """texture/uv.rs:6-24."""
+    type = A.FTN_TEXTURE_UV
+
+    def __init__(self, mapping=None):
+        self.tex1 = self.tex2 = _spectrum(0.0)
+        self.mapping = mapping or UVMapping()
+
+
+def _fill_kd(m, kd):
+    """Kd is a constant spectrum or one of the textures above."""
+    if isinstance(kd, (Checkerboard2DTexture, UVTexture)):
+        m.kd_texture = kd.type
+        m.tex1[:] = kd.tex1.tolist(); m.tex2[:] = kd.tex2.tolist()
+        m.uv_scale[:] = list(kd.mapping.scale); m.uv_delta[:] = list(kd.mapping.offset)
+    else:
+        m.kd_texture = A.FTN_TEXTURE_CONSTANT
+        m.kd[:] = _spectrum(kd).tolist()
+        m.uv_scale[:] = [1.0, 1.0]
+
+
 class MatteMaterial:
     """material/matte.rs; constant Kd, sigma = 0 (Lambert).  Default Kd 0.5 (constructors.rs:193)."""
     type = A.FTN_MATERIAL_MATTE
 
     def __init__(self, kd=0.5):
-        self.kd = _spectrum(kd)
+        self.kd = kd if isinstance(kd, (Checkerboard2DTexture, UVTexture)) else _spectrum(kd)
 
     def fill(self, m):
         m.type = self.type
-        m.kd[:] = self.kd.tolist()
+        _fill_kd(m, self.kd)
 
 
 class MetalMaterial:
@@ -171,12 +213,13 @@ class PlasticMaterial:
     type = A.FTN_MATERIAL_PLASTIC
 
     def __init__(self, kd=0.25, ks=0.25, roughness=0.1, remap_roughness=True):
-        self.kd, self.ks = _spectrum(kd), _spectrum(ks)
+        self.kd = kd if isinstance(kd, (Checkerboard2DTexture, UVTexture)) else _spectrum(kd)
+        self.ks = _spectrum(ks)
         self.roughness, self.remap = float(roughness), bool(remap_roughness)
 
     def fill(self, m):
         m.type = self.type
-        m.kd[:] = self.kd.tolist()
+        _fill_kd(m, self.kd)
         m.ks[:] = self.ks.tolist()
         m.u_roughness = m.v_roughness = self.roughness
         m.remap_roughness = int(self.remap)

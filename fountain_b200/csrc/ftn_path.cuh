@@ -224,7 +224,7 @@ FTN_HD void shade_surface(const SceneView& sc, const PassParams& pp, uint32_t pa
     constexpr int M = MAT < 0 ? 0 : MAT;
     Bsdf bsdf;
     bsdf_init(&bsdf, s.ns, s.n, s.sdpdu);
-    material_bsdf<M>(sc.materials[s.material], &bsdf);
+    material_bsdf<M>(sc.materials[s.material], s.u, s.v, &bsdf);
     const uint64_t key = path_sample_key(pp, path, nullptr, nullptr);
     // under the direct-lighting integrator `bounces` is the recursion depth of specular_reflect
     const uint32_t dim0 = DIM_CAMERA + (uint32_t)DIM_PER_BOUNCE * (uint32_t)bounces;

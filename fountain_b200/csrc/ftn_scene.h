@@ -58,6 +58,8 @@ struct MaterialData {
     int32_t type;            // FtnMaterialType
     float kd[3], ks[3], eta[3], k[3];
     float alpha_x, alpha_y;  // after the roughness remap (microfacet.rs:40-45)
+    int32_t kd_texture;      // FtnTextureType of Kd
+    float tex1[3], tex2[3], uv_scale[2], uv_delta[2];
 };
 
 // light/infinite.rs: level-0 texels + the Distribution2D tables (sampling.rs:137-180)

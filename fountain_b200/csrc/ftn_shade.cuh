@@ -394,9 +394,18 @@ template <int MAT> FTN_HD bool bsdf_sample_f(const Bsdf& b, V3 wo_w, float u0, f
 }
 
 // Material::compute_scattering_functions: matte.rs:36-52, metal.rs:38-65, plastic.rs:24-48, mirror.rs:21-30
-template <int MAT> FTN_HD void material_bsdf(const MaterialData& m, Bsdf* b) {
+// Kd through its texture: constant, checkerboard (AAMethod::None, checkerboard.rs:50-64) or uv (uv.rs:18-23),
+// st = scale * uv + delta (mapping.rs:40-52); explicitly rounded so that floor() sees the oracle's values
+FTN_HD V3 material_kd(const MaterialData& m, float u, float v) {
+    if (m.kd_texture == 0) return V3(m.kd[0], m.kd[1], m.kd[2]);
+    const float s = rn_add(rn_mul(m.uv_scale[0], u), m.uv_delta[0]), t = rn_add(rn_mul(m.uv_scale[1], v), m.uv_delta[1]);
+    if (m.kd_texture == 1) return (((int)floorf(s) + (int)floorf(t)) % 2 == 0) ? V3(m.tex1[0], m.tex1[1], m.tex1[2]) : V3(m.tex2[0], m.tex2[1], m.tex2[2]);
+    return V3(rn_sub(s, floorf(s)), rn_sub(t, floorf(t)), 0.0f);
+}
+template <int MAT> FTN_HD void material_bsdf(const MaterialData& m, float u, float v, Bsdf* b) {
     if (MAT == FTN_MATERIAL_MATTE) {
-        const V3 r = V3(clampf(m.kd[0], 0.0f, FTN_INF), clampf(m.kd[1], 0.0f, FTN_INF), clampf(m.kd[2], 0.0f, FTN_INF));
+        const V3 kd0 = material_kd(m, u, v);
+        const V3 r = V3(clampf(kd0.x, 0.0f, FTN_INF), clampf(kd0.y, 0.0f, FTN_INF), clampf(kd0.z, 0.0f, FTN_INF));
         if (!is_black(r)) { b->on0 = true; b->l0.r = r; }
     } else if (MAT == FTN_MATERIAL_METAL) {
         b->on0 = true;
@@ -406,7 +415,7 @@ template <int MAT> FTN_HD void material_bsdf(const MaterialData& m, Bsdf* b) {
         const V3 r = V3(clampf(m.kd[0], 0.0f, FTN_INF), clampf(m.kd[1], 0.0f, FTN_INF), clampf(m.kd[2], 0.0f, FTN_INF));
         if (!is_black(r)) { b->on0 = true; b->l0.r = r; }
     } else {
-        const V3 kd = V3(m.kd[0], m.kd[1], m.kd[2]), ks = V3(m.ks[0], m.ks[1], m.ks[2]);
+        const V3 kd = material_kd(m, u, v), ks = V3(m.ks[0], m.ks[1], m.ks[2]);
         if (!is_black(kd)) { b->on0 = true; b->l0.r = kd; }
         if (!is_black(ks)) { b->on1 = true; b->l1.r = ks; b->l1.ax = m.alpha_x; b->l1.ay = m.alpha_x; b->l1.eta = v3s(0.0f); b->l1.k = v3s(0.0f); }
     }
@@ -418,6 +427,7 @@ struct Surface {
     V3 p, p_err, n;      // hit.p, hit.p_err, hit.n
     V3 ns, sdpdu;        // shading_n, shading_geom.dpdu
     V3 wo;               // SurfaceInteraction.wo
+    float u, v;          // SurfaceInteraction.uv (texture lookups)
     int material;        // -1 none
     int light;           // area light index, -1 none
 };
@@ -435,6 +445,9 @@ FTN_HD void triangle_surface(const SceneView& sc, uint32_t slot, const TriHit& h
         uv[0][0] = sc.uv[2 * v0]; uv[0][1] = sc.uv[2 * v0 + 1]; uv[1][0] = sc.uv[2 * v1]; uv[1][1] = sc.uv[2 * v1 + 1];
         uv[2][0] = sc.uv[2 * v2]; uv[2][1] = sc.uv[2 * v2 + 1];
     }
+    // uv of the hit, triangle.rs:299-300: b0 uv0 + b1 uv1 + b2 uv2
+    s->u = rn_add(rn_add(rn_mul(h.b0, uv[0][0]), rn_mul(h.b1, uv[1][0])), rn_mul(h.b2, uv[2][0]));
+    s->v = rn_add(rn_add(rn_mul(h.b0, uv[0][1]), rn_mul(h.b1, uv[1][1])), rn_mul(h.b2, uv[2][1]));
     const float duv02x = rn_sub(uv[0][0], uv[2][0]), duv02y = rn_sub(uv[0][1], uv[2][1]);
     const float duv12x = rn_sub(uv[1][0], uv[2][0]), duv12y = rn_sub(uv[1][1], uv[2][1]);
     const V3 dp02 = x_sub(p0, p2), dp12 = x_sub(p1, p2);
@@ -477,7 +490,7 @@ FTN_HD void triangle_surface(const SceneView& sc, uint32_t slot, const TriHit& h
 }
 
 FTN_HD void sphere_surface(const SphereData& sd, const SphereHit& h, Surface* s) {
-    s->p = h.p; s->p_err = h.p_err; s->n = h.n; s->ns = h.ns; s->sdpdu = h.dpdu; s->wo = h.wo;
+    s->p = h.p; s->p_err = h.p_err; s->n = h.n; s->ns = h.ns; s->sdpdu = h.dpdu; s->wo = h.wo; s->u = h.u; s->v = h.v;
     s->material = sd.material; s->light = sd.light;
 }
 

@@ -282,3 +282,30 @@ def mirror_scene(backend=None, resolution=(48, 48), env=1.0, with_floor=True):
     camera = api.PerspectiveCamera(cam_to_world, resolution, fov=45.0)
     film = api.Film(resolution, backend=backend)
     return scene, camera, film
+
+
+# ---- textured Kd (texture/checkerboard.rs, texture/uv.rs through UVMapping) ----------------
+def textured_floor_scene(backend=None, resolution=(48, 48), texture="checkerboard", material="matte", look_at=None, fov=50.0):
+    """A 12x12 floor whose uv are its world (x, y), so texture cells are unit squares aligned with the
+    integer grid; lit by a distant light from straight above (+ a weak uniform environment unless a
+    narrow-fov probe camera `look_at` = (x, y) is asked for, which keeps the result closed-form)."""
+    v = np.array([[-6, -6, 0], [6, -6, 0], [6, 6, 0], [-6, 6, 0]], np.float32)
+    mesh = api.TriangleMesh(Transform.identity(), np.array([0, 1, 2, 0, 2, 3], np.uint32), v, tex_coords=v[:, :2].copy())
+    if texture == "checkerboard":
+        tex = api.Checkerboard2DTexture((0.8, 0.2, 0.2), (0.1, 0.1, 0.9), api.UVMapping(1.0, 1.0, 0.0, 0.0))
+    elif texture == "checkerboard_scaled":
+        tex = api.Checkerboard2DTexture((0.8, 0.2, 0.2), (0.1, 0.1, 0.9), api.UVMapping(2.0, 0.5, 0.25, -0.5))
+    else:
+        tex = api.UVTexture(api.UVMapping(0.5, 0.25, 0.1, 0.2))
+    mat = api.MatteMaterial(tex) if material == "matte" else api.PlasticMaterial(tex, 0.2, 0.2)
+    lights = [api.DistantLight.from_params(L=3.0, from_=(0.0, 0.0, 1.0), to=(0.0, 0.0, 0.0))]
+    if look_at is None:
+        lights.append(api.InfiniteAreaLight.new_uniform(0.2))
+    scene = api.Scene([api.GeometricPrimitive(mesh, mat)], lights, backend=backend)
+    if look_at is None:
+        cam_to_world = Transform.look_at((0, -9, 6), (0, 0, 0), (0, 0, 1)).inverse()
+    else:
+        cam_to_world = Transform.look_at((look_at[0], look_at[1], 30.0), (look_at[0], look_at[1], 0.0), (0, 1, 0)).inverse()
+    camera = api.PerspectiveCamera(cam_to_world, resolution, fov=fov)
+    film = api.Film(resolution, backend=backend)
+    return scene, camera, film

@@ -94,7 +94,16 @@ typedef enum FtnMaterialType {
     FTN_MATERIAL_MIRROR = 3   /* material/mirror.rs:21-30: SpecularReflection with FresnelNoOp */
 } FtnMaterialType;
 
-/* Constant-texture materials only (texture/mod.rs:34-42). */
+/* Texture of a spectrum parameter (src/texture): constant, the 2D checkerboard without anti-aliasing
+ * (AAMethod::None, the only one implemented, checkerboard.rs:54-64) or the uv debug texture (uv.rs), both
+ * through UVMapping (mapping.rs:36-53: st = scale * uv + delta).  Image textures are out of scope. */
+typedef enum FtnTextureType {
+    FTN_TEXTURE_CONSTANT = 0,      /* texture/mod.rs:34-42: the value in the material's kd field */
+    FTN_TEXTURE_CHECKERBOARD = 1,  /* tex1 where (floor(s) + floor(t)) % 2 == 0, else tex2 */
+    FTN_TEXTURE_UV = 2             /* (s - floor(s), t - floor(t), 0) */
+} FtnTextureType;
+
+/* Materials with constant parameters; Kd of matte / plastic may carry a texture (kd_texture). */
 typedef struct FtnMaterial {
     int32_t type;            /* FtnMaterialType */
     float kd[3];             /* matte Kd / plastic Kd */
@@ -105,6 +114,10 @@ typedef struct FtnMaterial {
     float v_roughness;
     int32_t remap_roughness; /* constructors.rs:227 default true */
     float kr[3];             /* mirror Kr (constructors.rs:207-210 default 0.9) */
+    int32_t kd_texture;      /* FtnTextureType of Kd (matte, plastic) */
+    float tex1[3], tex2[3];  /* checkerboard: the two constant sub-textures (constructors.rs:276-287) */
+    float uv_scale[2];       /* UVMapping uscale, vscale (constructors.rs:251-252, default 1) */
+    float uv_delta[2];       /* UVMapping udelta, vdelta (default 0) */
 } FtnMaterial;
 
 /* shapes/sphere.rs:16-27 (+ the DiffuseAreaLight it may carry, light/diffuse.rs:24-41). */

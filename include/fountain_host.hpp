@@ -444,12 +444,36 @@ struct Material {
     virtual ~Material() = default;
     virtual void fill(FtnMaterial& m) const = 0;
 };
+struct UVMapping {                       // texture/mapping.rs:13-53; defaults (constructors.rs:251-254)
+    float scale_u = 1.0f, scale_v = 1.0f, offset_u = 0.0f, offset_v = 0.0f;
+};
+// A spectrum texture for Kd: ConstantTexture (texture/mod.rs:34-42), Checkerboard2DTexture over two constant
+// spectra with AAMethod::None (checkerboard.rs:10-64) or UVTexture (uv.rs:6-24)
+struct SpectrumTexture {
+    int type = FTN_TEXTURE_CONSTANT;
+    Spectrum value, tex1, tex2;
+    UVMapping mapping;
+    SpectrumTexture(Spectrum constant) : value(constant) {}
+    SpectrumTexture(float constant) : value(constant) {}
+    static SpectrumTexture checkerboard(Spectrum tex1, Spectrum tex2, UVMapping m = {}) {
+        SpectrumTexture t(Spectrum(0.0f)); t.type = FTN_TEXTURE_CHECKERBOARD; t.tex1 = tex1; t.tex2 = tex2; t.mapping = m; return t;
+    }
+    static SpectrumTexture uv(UVMapping m = {}) { SpectrumTexture t(Spectrum(0.0f)); t.type = FTN_TEXTURE_UV; t.mapping = m; return t; }
+    void fill_kd(FtnMaterial& m) const {
+        m.kd_texture = type;
+        m.kd[0] = value.r; m.kd[1] = value.g; m.kd[2] = value.b;
+        m.tex1[0] = tex1.r; m.tex1[1] = tex1.g; m.tex1[2] = tex1.b;
+        m.tex2[0] = tex2.r; m.tex2[1] = tex2.g; m.tex2[2] = tex2.b;
+        m.uv_scale[0] = mapping.scale_u; m.uv_scale[1] = mapping.scale_v;
+        m.uv_delta[0] = mapping.offset_u; m.uv_delta[1] = mapping.offset_v;
+    }
+};
 struct MatteMaterial : Material {        // material/matte.rs; Kd default 0.5 (constructors.rs:193)
-    Spectrum kd;
-    explicit MatteMaterial(Spectrum kd_ = Spectrum(0.5f)) : kd(kd_) {}
+    SpectrumTexture kd;
+    explicit MatteMaterial(SpectrumTexture kd_ = SpectrumTexture(0.5f)) : kd(kd_) {}
     void fill(FtnMaterial& m) const override {
         m.type = FTN_MATERIAL_MATTE;
-        m.kd[0] = kd.r; m.kd[1] = kd.g; m.kd[2] = kd.b;
+        kd.fill_kd(m);
     }
 };
 struct MetalMaterial : Material {        // material/metal.rs; roughness 0.01, remap true (constructors.rs:213-230)
@@ -468,14 +492,15 @@ struct MetalMaterial : Material {        // material/metal.rs; roughness 0.01, r
     }
 };
 struct PlasticMaterial : Material {      // material/plastic.rs; Kd = Ks = .25, roughness .1 (constructors.rs:232-238)
-    Spectrum kd, ks;
+    SpectrumTexture kd;
+    Spectrum ks;
     float roughness;
     bool remap_roughness;
-    explicit PlasticMaterial(Spectrum kd_ = Spectrum(0.25f), Spectrum ks_ = Spectrum(0.25f), float rough = 0.1f, bool remap = true)
+    explicit PlasticMaterial(SpectrumTexture kd_ = SpectrumTexture(0.25f), Spectrum ks_ = Spectrum(0.25f), float rough = 0.1f, bool remap = true)
         : kd(kd_), ks(ks_), roughness(rough), remap_roughness(remap) {}
     void fill(FtnMaterial& m) const override {
         m.type = FTN_MATERIAL_PLASTIC;
-        m.kd[0] = kd.r; m.kd[1] = kd.g; m.kd[2] = kd.b;
+        kd.fill_kd(m);
         m.ks[0] = ks.r; m.ks[1] = ks.g; m.ks[2] = ks.b;
         m.u_roughness = m.v_roughness = roughness; m.remap_roughness = remap_roughness;
     }

@@ -317,6 +317,8 @@ struct Sphere {
 struct Material {
     int type;          // FtnMaterialType
     Spectrum kd, ks, eta, k, kr;
+    int kd_texture;    // FtnTextureType
+    Spectrum tex1, tex2; Float uv_scale[2], uv_delta[2];
     Float u_rough, v_rough;
     bool remap;
 };

@@ -330,11 +330,20 @@ struct Bsdf {
     }
 };
 
+// Kd through its texture: ConstantTexture (texture/mod.rs:34-42), Checkerboard2DTexture with
+// AAMethod::None (checkerboard.rs:50-64) or UVTexture (uv.rs:18-23), via UVMapping (mapping.rs:40-52).
+inline Spectrum evaluate_kd(const Material& m, const SurfaceInteraction& si) {
+    if (m.kd_texture == 0) return m.kd;
+    Float s = m.uv_scale[0] * si.uv[0] + m.uv_delta[0], t = m.uv_scale[1] * si.uv[1] + m.uv_delta[1];
+    if (m.kd_texture == 1) return (((int)std::floor(s) + (int)std::floor(t)) % 2 == 0) ? m.tex1 : m.tex2;
+    return Spectrum(s - std::floor(s), t - std::floor(t), 0.0f);
+}
+
 // material/{matte,metal,plastic}.rs compute_scattering_functions
 inline void compute_scattering_functions(const Material& m, const SurfaceInteraction& si, Bsdf* bsdf) {
     bsdf->init(si);
     if (m.type == 0) {   // matte.rs:36-52 (sigma == 0 only)
-        Spectrum r = m.kd.clamp_positive();
+        Spectrum r = evaluate_kd(m, si).clamp_positive();
         if (!r.is_black()) { BxDF b{}; b.kind = 0; b.r = r; bsdf->add(b); }
     } else if (m.type == 1) {   // metal.rs:38-65
         Float ur = m.u_rough, vr = m.v_rough;
@@ -346,7 +355,8 @@ inline void compute_scattering_functions(const Material& m, const SurfaceInterac
         Spectrum r = m.kr.clamp_positive();
         if (!r.is_black()) { BxDF b{}; b.kind = 2; b.r = r; bsdf->add(b); }
     } else {   // plastic.rs:24-48
-        if (!m.kd.is_black()) { BxDF b{}; b.kind = 0; b.r = m.kd; bsdf->add(b); }
+        Spectrum kd = evaluate_kd(m, si);
+        if (!kd.is_black()) { BxDF b{}; b.kind = 0; b.r = kd; bsdf->add(b); }
         if (!m.ks.is_black()) {
             Float rough = m.u_rough;
             if (m.remap) rough = roughness_to_alpha(rough);

@@ -157,6 +157,37 @@ static void world_bound_and_morton_order() {
     }
 }
 
+// checkerboard Kd (texture/checkerboard.rs) + distant light (light/distant.rs) + mirror (material/mirror.rs):
+// closed forms through the C++ host side -- Kd(texel) / pi * L under a light from straight above, Kr * L_env
+static void textured_floor_and_mirror_closed_forms() {
+    const float pi = 3.14159265358979f;
+    auto probe = [&](double x, double y) {
+        std::vector<float> v = {-6, -6, 0, 6, -6, 0, 6, 6, 0, -6, 6, 0}, uv = {-6, -6, 6, -6, 6, 6, -6, 6};
+        auto mesh = std::make_shared<TriangleMesh>(Transform::identity(), std::vector<uint32_t>{0, 1, 2, 0, 2, 3}, v, std::vector<float>{}, uv);
+        auto mat = std::make_shared<MatteMaterial>(SpectrumTexture::checkerboard(Spectrum(0.8f, 0.2f, 0.2f), Spectrum(0.1f, 0.1f, 0.9f)));
+        std::vector<GeometricPrimitive> prims; prims.emplace_back(mesh, mat);
+        Scene scene(g_lib, prims, {Light(DistantLight::from_to(Point3f(0, 0, 1), Point3f(0, 0, 0), Spectrum(3.0f)))});
+        PerspectiveCamera camera(Transform::look_at({x, y, 30.0}, {x, y, 0.0}, {0, 1, 0}).inverse(), 5, 5, 0.5f);
+        Film film(g_lib, 5, 5);
+        SamplerIntegrator<DirectLightingIntegrator> integrator(camera, DirectLightingIntegrator(LightStrategy::UniformSampleOne, 1));
+        integrator.render_parallel(scene, film, RandomSampler::new_with_seed(2, 0));
+        return film.into_spectrum_buffer().first;
+    };
+    for (const Spectrum& s : probe(0.5, 0.5)) CHECK(std::fabs(s.r - 0.8f / pi * 3.0f) < 1e-5f && std::fabs(s.b - 0.2f / pi * 3.0f) < 1e-5f, "tex1 %.7g %.7g", s.r, s.b);
+    for (const Spectrum& s : probe(-0.5, 0.5)) CHECK(std::fabs(s.r - 0.1f / pi * 3.0f) < 1e-5f && std::fabs(s.b - 0.9f / pi * 3.0f) < 1e-5f, "tex2 %.7g %.7g", s.r, s.b);
+    // mirror quad facing the camera under a uniform environment of radiance 1
+    std::vector<float> v = {-3, 2, -1, 3, 2, -1, 3, 2, 3, -3, 2, 3};
+    auto mesh = std::make_shared<TriangleMesh>(Transform::identity(), std::vector<uint32_t>{0, 1, 2, 0, 2, 3}, v);
+    std::vector<GeometricPrimitive> prims; prims.emplace_back(mesh, std::make_shared<MirrorMaterial>(Spectrum(0.8f, 0.7f, 0.6f)));
+    Scene scene(g_lib, prims, {Light(InfiniteAreaLight::new_uniform(Spectrum(1.0f)))});
+    PerspectiveCamera camera(Transform::look_at({0, -7, 1.5}, {0, 2, 1.0}, {0, 0, 1}).inverse(), 9, 9, 5.0f);
+    Film film(g_lib, 9, 9);
+    SamplerIntegrator<PathIntegrator> integrator(camera, PathIntegrator(5, 1.0f));
+    integrator.render_parallel(scene, film, RandomSampler::new_with_seed(4, 0));
+    for (const Spectrum& s : film.into_spectrum_buffer().first)
+        CHECK(std::fabs(s.r - 0.8f) < 1e-5f && std::fabs(s.g - 0.7f) < 1e-5f && std::fabs(s.b - 0.6f) < 1e-5f, "mirror %.7g %.7g %.7g", s.r, s.g, s.b);
+}
+
 static void invalid_arguments_are_errors() {
     bool threw = false;
     try {
@@ -194,6 +225,7 @@ int main(int argc, char** argv) {
         {"test_rounded_cube", test_rounded_cube},
         {"camera_raster_to_camera_fov", camera_raster_to_camera_fov},
         {"world_bound_and_morton_order", world_bound_and_morton_order},
+        {"textured_floor_and_mirror_closed_forms", textured_floor_and_mirror_closed_forms},
         {"invalid_arguments_are_errors", invalid_arguments_are_errors},
     };
     int ran = 0;

@@ -66,6 +66,9 @@ SIM_API int sim_scene_create(const FtnSceneDesc* d, SimScene** out) {
         for (int c = 0; c < 3; ++c) { md.kd[c] = fm.kd[c]; md.ks[c] = fm.ks[c]; md.eta[c] = fm.eta[c]; md.k[c] = fm.k[c]; }
         float ur = fm.u_roughness, vr = fm.v_roughness;
         if (fm.type == FTN_MATERIAL_MIRROR) for (int c = 0; c < 3; ++c) md.kd[c] = fm.kr[c];   // Kr travels in the kd slot
+        md.kd_texture = (fm.type == FTN_MATERIAL_MATTE || fm.type == FTN_MATERIAL_PLASTIC) ? fm.kd_texture : 0;
+        for (int c = 0; c < 3; ++c) { md.tex1[c] = fm.tex1[c]; md.tex2[c] = fm.tex2[c]; }
+        for (int c = 0; c < 2; ++c) { md.uv_scale[c] = fm.uv_scale[c]; md.uv_delta[c] = fm.uv_delta[c]; }
         if (fm.type == FTN_MATERIAL_PLASTIC) vr = ur;
         if (fm.remap_roughness) { ur = roughness_to_alpha_host(ur); vr = roughness_to_alpha_host(vr); }
         md.alpha_x = ur; md.alpha_y = vr; s->mats.push_back(md);
@@ -403,7 +406,7 @@ SIM_API void sim_kat_bsdf(const FtnMaterial* m, const float wo[3], const float w
     Bsdf b; bsdf_init(&b, V3(0, 0, 1), V3(0, 0, 1), V3(1, 0, 0));
     const V3 o(wo[0], wo[1], wo[2]), i(wi[0], wi[1], wi[2]);
     V3 f; float pdf; ScatterSample sm; bool ok;
-#define SIM_BSDF(M) { material_bsdf<M>(s->mats[0], &b); f = bsdf_f<M>(b, o, i, BXDF_ALL); pdf = bsdf_pdf<M>(b, o, i, BXDF_ALL); ok = bsdf_sample_f<M>(b, o, u[0], u[1], BXDF_ALL, &sm); }
+#define SIM_BSDF(M) { material_bsdf<M>(s->mats[0], 0.0f, 0.0f, &b); f = bsdf_f<M>(b, o, i, BXDF_ALL); pdf = bsdf_pdf<M>(b, o, i, BXDF_ALL); ok = bsdf_sample_f<M>(b, o, u[0], u[1], BXDF_ALL, &sm); }
     if (m->type == FTN_MATERIAL_MATTE) SIM_BSDF(FTN_MATERIAL_MATTE)
     else if (m->type == FTN_MATERIAL_METAL) SIM_BSDF(FTN_MATERIAL_METAL)
     else if (m->type == FTN_MATERIAL_MIRROR) SIM_BSDF(FTN_MATERIAL_MIRROR)

@@ -199,3 +199,22 @@ def test_mirror_closed_form(gpu_backend):
     camera = api.PerspectiveCamera(Transform.look_at((0, -7, 1.5), (0, 2, 1.0), (0, 0, 1)).inverse(), (9, 9), fov=5.0)
     api.SamplerIntegrator(camera, api.PathIntegrator(5, 1.0)).render_parallel(scene, film, api.RandomSampler.new_with_seed(4, 0))
     assert np.allclose(film.into_spectrum_buffer()[0], np.array([0.8, 0.7, 0.6])[None, :], rtol=1e-5)
+
+
+# ---- textured Kd (texture/checkerboard.rs, texture/uv.rs) ---------------------------------------------------
+@pytest.mark.parametrize("texture,material", [("checkerboard", "matte"), ("checkerboard_scaled", "plastic"), ("uv", "matte")])
+def test_textured_floor_matches_oracle(gpu_backend, orc_backend, texture, material):
+    kw = dict(resolution=(96, 96), texture=texture, material=material)
+    a, apx, ast = parity.render(gpu_backend, scenes.textured_floor_scene, api.PathIntegrator(3, 1.0), 16, seed=11, **kw)
+    b, bpx, bst = parity.render(orc_backend, scenes.textured_floor_scene, api.PathIntegrator(3, 1.0), 16, seed=11, **kw)
+    mean_rel, frac_off = parity.image_diff(a, b)
+    assert mean_rel < 2e-3 and frac_off < 0.02, (mean_rel, frac_off)
+    assert np.array_equal(apx[..., 3], bpx[..., 3])
+
+
+def test_checkerboard_closed_form(gpu_backend):
+    t1, t2 = np.array([0.8, 0.2, 0.2]) / np.pi * 3.0, np.array([0.1, 0.1, 0.9]) / np.pi * 3.0
+    for xy, expected in (((0.5, 0.5), t1), ((1.5, 0.5), t2), ((-0.5, 0.5), t2), ((-0.5, -0.5), t1)):
+        scene, camera, film = scenes.textured_floor_scene(backend=gpu_backend, resolution=(5, 5), look_at=xy, fov=0.5)
+        api.SamplerIntegrator(camera, api.DirectLightingIntegrator(1)).render_parallel(scene, film, api.RandomSampler.new_with_seed(2, 0))
+        assert np.allclose(film.into_spectrum_buffer()[0], expected[None, :], rtol=1e-5), xy

@@ -139,3 +139,15 @@ def test_mirror_image_matches_oracle(sim_backend, orc_backend, integrator):
     assert np.array_equal(apx[..., 3], bpx[..., 3])
     assert abs(ast["rays_closest"] - bst["rays_closest"]) <= 0.002 * bst["rays_closest"]
     assert abs(ast["rays_any"] - bst["rays_any"]) <= 0.002 * bst["rays_any"]
+
+
+# ---- textured Kd (checkerboard / uv through UVMapping) -----------------------------------------------------
+@pytest.mark.parametrize("texture,material", [("checkerboard", "matte"), ("checkerboard_scaled", "plastic"), ("uv", "matte")])
+def test_textured_floor_matches_oracle(sim_backend, orc_backend, texture, material):
+    kw = dict(resolution=(40, 40), texture=texture, material=material)
+    a, apx, ast = parity.render(sim_backend, scenes.textured_floor_scene, api.PathIntegrator(3, 1.0), 4, seed=11, **kw)
+    b, bpx, bst = parity.render(orc_backend, scenes.textured_floor_scene, api.PathIntegrator(3, 1.0), 4, seed=11, **kw)
+    mean_rel, frac_off = parity.image_diff(a, b)
+    assert mean_rel < 2e-3 and frac_off < 0.02, (mean_rel, frac_off)
+    assert np.array_equal(apx[..., 3], bpx[..., 3])
+    assert len(np.unique(np.round(b.reshape(-1, 3), 3), axis=0)) > 4       # the texture is visible

@@ -166,3 +166,34 @@ def test_mirror_scene_renders_in_both_sampler_modes(orc_backend, mode):
     api.SamplerIntegrator(camera, api.PathIntegrator(5, 1.0)).render_parallel(scene, film, api.RandomSampler.new_with_seed(16, 0, mode=mode))
     rgb = film.into_spectrum_buffer()[0]
     assert np.isfinite(rgb).all() and rgb.mean() > 0.1
+
+
+# ---- textured Kd: Checkerboard2DTexture (AAMethod::None), UVTexture, UVMapping -------------------------------
+# No reference test: pinned by closed form -- under a distant light from straight above a Lambertian floor
+# shows Kd(texel) / pi * L exactly; the floor's uv are its world (x, y).
+def _probe(orc_backend, xy, texture):
+    from fountain_b200 import scenes
+    scene, camera, film = scenes.textured_floor_scene(backend=orc_backend, resolution=(5, 5), texture=texture, look_at=xy, fov=0.5)
+    api.SamplerIntegrator(camera, api.DirectLightingIntegrator(1)).render_parallel(scene, film, api.RandomSampler.new_with_seed(2, 0))
+    return film.into_spectrum_buffer()[0]
+
+
+def test_checkerboard_closed_form(orc_backend):
+    t1, t2 = np.array([0.8, 0.2, 0.2]) / np.pi * 3.0, np.array([0.1, 0.1, 0.9]) / np.pi * 3.0
+    # (floor(s) + floor(t)) % 2 == 0 with Rust's truncating %: (-1 + 0) % 2 = -1 -> tex2, (-1 + -1) % 2 = 0 -> tex1
+    for xy, expected in (((0.5, 0.5), t1), ((1.5, 0.5), t2), ((1.5, 1.5), t1), ((-0.5, 0.5), t2), ((-0.5, -0.5), t1), ((-1.5, 0.5), t1), ((2.5, -3.5), t1)):
+        assert np.allclose(_probe(orc_backend, xy, "checkerboard"), expected[None, :], rtol=1e-5), xy
+    # UVMapping(2, .5, .25, -.5): s = 2x + .25, t = .5y - .5
+    for xy in ((0.1, 0.5), (0.6, 0.5), (0.1, 3.5), (0.1, 2.5), (-0.3, 2.5), (-0.9, -2.5)):
+        s, t = 2 * xy[0] + 0.25, 0.5 * xy[1] - 0.5
+        want = t1 if int(np.fmod(np.floor(s) + np.floor(t), 2)) == 0 else t2     # fmod truncates like Rust's %
+        assert np.allclose(_probe(orc_backend, xy, "checkerboard_scaled"), want[None, :], rtol=1e-5), xy
+
+
+def test_uv_texture_closed_form(orc_backend):
+    # the probe's 5x5 pixels cover +-0.13 units around the point: compare the mean (the texture is linear there)
+    rgb = _probe(orc_backend, (1.3, 2.6), "uv")            # s = .5 * 1.3 + .1 = .75, t = .25 * 2.6 + .2 = .85
+    assert np.allclose(rgb.mean(axis=0), np.array([0.75, 0.85, 0.0]) / np.pi * 3.0, rtol=5e-3, atol=1e-6)
+    rgb = _probe(orc_backend, (-1.3, -2.6), "uv")          # s = -.55 -> .45, t = -.45 -> .55
+    assert np.allclose(rgb.mean(axis=0), np.array([0.45, 0.55, 0.0]) / np.pi * 3.0, rtol=5e-3, atol=1e-6)
+    assert np.all(rgb[:, 2] == 0.0)
