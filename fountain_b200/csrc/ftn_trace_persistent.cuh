@@ -34,10 +34,7 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sc, uint32_t n
     const BvhView bvh = sc.bvh;
     bool has_ray = false, finished = false, exhausted = false;
     uint32_t item = 0;
-    // Only the ray ORIGIN stays in registers across the traverse loop (the triangle test needs it); direction,
-    // t_max and time are folded into slab / shear / t_max at refill and RE-LOADED from the source when a finished
-    // ray is flushed -- five registers less per lane in a loop that runs at the 64-register occupancy limit.
-    V3 ro = v3s(0.0f);
+    RayF ray; ray.o = v3s(0.0f); ray.d = v3s(0.0f); ray.t_max = 0.0f; ray.time = 0.0f;
     RaySlab slab; slab.o = v3s(0.0f); slab.inv_d = v3s(0.0f); slab.widen = 1.0f;
     RayShear shear; shear.kx = 0; shear.ky = 1; shear.kz = 2; shear.sx = shear.sy = shear.sz = 0.0f;
     SceneHit hit; hit.slot = FTN_NO_HIT_SLOT; hit.t = 0.0f; hit.tri.t = hit.tri.b0 = hit.tri.b1 = hit.tri.b2 = 0.0f;
@@ -48,11 +45,7 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sc, uint32_t n
     for (;;) {
         // ---- flush ----
         hit.t = t_max;
-        {
-            RayF done_ray; done_ray.o = ro; done_ray.d = v3s(0.0f); done_ray.t_max = 0.0f; done_ray.time = 0.0f;
-            if (finished) src.load(item, &done_ray);
-            sink.store(finished, item, done_ray, hit);
-        }
+        sink.store(finished, item, ray, hit);
         if (finished) { has_ray = false; finished = false; }
         // ---- refill ----
         const unsigned idle = __ballot_sync(0xffffffffu, !has_ray);
@@ -67,10 +60,8 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sc, uint32_t n
                     item = k;
                     has_ray = true;
                     hit.slot = FTN_NO_HIT_SLOT;
-                    RayF ray;
                     if (!src.load(k, &ray)) { finished = true; t_max = ray.t_max; cur = FTN_TRAVERSAL_DONE; }
                     else {
-                        ro = ray.o;
                         t_max = ray.t_max;
                         // analytic spheres first, with the ray's own t_max (see ftn_trace.cuh)
                         if (SPHERES) {
@@ -116,7 +107,7 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sc, uint32_t n
                     cur = node_step(bvh, cur, slab, t_max, stack, sp);
                 }
             } else if (leaf < 0) {
-                const bool stop = leaf_step<ANY, COUNT>(bvh, leaf, ro, shear, &t_max, &hit.slot, &hit.tri, &tc);
+                const bool stop = leaf_step<ANY, COUNT>(bvh, leaf, ray.o, shear, &t_max, &hit.slot, &hit.tri, &tc);
                 leaf = 0;
                 if (stop) cur = FTN_TRAVERSAL_DONE;
             }
@@ -135,7 +126,7 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sc, uint32_t n
                 }
             }
             while (act && leaf < 0) {
-                const bool stop = leaf_step<ANY, COUNT>(bvh, leaf, ro, shear, &t_max, &hit.slot, &hit.tri, &tc);
+                const bool stop = leaf_step<ANY, COUNT>(bvh, leaf, ray.o, shear, &t_max, &hit.slot, &hit.tri, &tc);
                 leaf = 0;
                 if (stop) cur = FTN_TRAVERSAL_DONE;
                 else if (cur < 0 && cur != FTN_TRAVERSAL_DONE) { leaf = cur; cur = (sp > 0) ? stack[--sp] : FTN_TRAVERSAL_DONE; }
