@@ -324,7 +324,7 @@ def run_ours_render(args):
                "dtype": "f32", "data": "synthetic",
                "config": {"workload": desc, "spp_per_gpu": spp, "spp_total": spp_total,
                           "parallelism": "replicated scene, sample-index sharding, NCCL film reduce" if world > 1 else "single GPU",
-                          "l2": "flushed between timed steps (256 MiB write)", "bvh": "LBVH (30-bit Morton, radix sort) -> BVH2x64, leaves <= 4 tris"},
+                          "l2": "flushed between timed steps (256 MiB write)", "bvh": "30-bit Morton codes + radix sort; topology: PLOC (>= 65536 tris) or Karras radix tree; BVH2x64 nodes, leaves <= 4 tris"},
                "samples_per_s": samples / (ms_total * 1e-3), "rays_per_step": rays // args.steps,
                "clocks": clock_info, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": base,
                "bvh_build_ms": scene.stats()["bvh_build_seconds"] * 1e3}
