@@ -132,6 +132,59 @@ k_ploc_merge(LbvhArrays a, const F4* __restrict__ leaf_lo, const F4* __restrict_
     ploc_merge(a, leaf_lo, leaf_hi, cl_in, cl_out, nn, merge, valid, mscan, vscan, n, created, i);
     if (i == c - 1u) *n_merged = mscan[i] + merge[i];
 }
+// The tail of the clustering in ONE block: once at most PLOC_FINISH_MAX clusters are left, the remaining
+// rounds (the majority: ~200 rounds for 1M triangles, ~14 of them above this size) run inside a single
+// kernel with the cluster lists in shared memory -- no launches and no host read-back per round.
+// Same per-element bodies, same prefix-sum node numbering: the tree is identical to the multi-launch form.
+#define PLOC_FINISH_MAX 1024
+__device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t v, uint32_t* warp_sums, uint32_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = warp_sums[lane];
+        uint32_t wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += y; }
+        warp_sums[lane] = wi - w;
+        if (lane == 31) *total = wi;
+    }
+    __syncthreads();
+    const uint32_t r = warp_sums[warp] + incl - v;
+    __syncthreads();   // warp_sums / total are reused by the next scan
+    return r;
+}
+__global__ void __launch_bounds__(PLOC_FINISH_MAX)
+k_ploc_finish(LbvhArrays a, const F4* __restrict__ leaf_lo, const F4* __restrict__ leaf_hi, const uint32_t* __restrict__ cl_global,
+              uint32_t c, uint32_t n, uint32_t created, uint32_t* __restrict__ status) {
+    __shared__ uint32_t cl[2][PLOC_FINISH_MAX], nn[PLOC_FINISH_MAX], mg[PLOC_FINISH_MAX], va[PLOC_FINISH_MAX], ms[PLOC_FINISH_MAX], vs[PLOC_FINISH_MAX];
+    __shared__ uint32_t warp_sums[32], tot_m, tot_v;
+    const uint32_t i = threadIdx.x;
+    if (i < c) cl[0][i] = cl_global[i];
+    __syncthreads();
+    int cur = 0;
+    while (c > 1u) {
+        if (i < c) nn[i] = ploc_nearest(a, leaf_lo, leaf_hi, cl[cur], c, i);
+        __syncthreads();
+        if (i < c) ploc_flags(nn, i, mg, va);
+        __syncthreads();
+        const uint32_t m_ex = block_exclusive_scan_1024(i < c ? mg[i] : 0u, warp_sums, &tot_m);
+        const uint32_t merged = tot_m;
+        const uint32_t v_ex = block_exclusive_scan_1024(i < c ? va[i] : 0u, warp_sums, &tot_v);
+        if (i < c) { ms[i] = m_ex; vs[i] = v_ex; }
+        __syncthreads();
+        if (merged == 0u) { if (i == 0) status[0] = 1u; return; }   // cannot happen (see ploc_nearest); reported, not spun on
+        if (i < c) ploc_merge(a, leaf_lo, leaf_hi, cl[cur], cl[cur ^ 1], nn, mg, va, ms, vs, n, created, i);
+        __threadfence_block();
+        __syncthreads();
+        created += merged; c -= merged; cur ^= 1;
+    }
+    if (i == 0) { status[1] = created; status[2] = cl[cur][0]; }
+}
+
 // depth-first position of every leaf (and the deepest leaf), range of every internal node
 __global__ void __launch_bounds__(256)
 k_ploc_leaf_positions(LbvhArrays a, uint32_t n, uint32_t* __restrict__ newpos, uint32_t* __restrict__ max_depth) {
@@ -554,7 +607,7 @@ int bvh_build(FtnScene* s) {
                     k_ploc_init<<<gb256, 256, 0, st>>>(n, cl0); count_launch();
                     uint32_t c = n, created = 0;
                     uint32_t *cin = cl0, *cout = cl1;
-                    while (c > 1 && rc == FTN_OK) {
+                    while (c > (uint32_t)PLOC_FINISH_MAX && rc == FTN_OK) {
                         const unsigned gc = (c + 255) / 256;
                         k_ploc_nearest<<<gc, 256, 0, st>>>(a, leaf_lo, leaf_hi, cin, c, nn); count_launch();
                         k_ploc_flags<<<gc, 256, 0, st>>>(nn, c, mg, va); count_launch();
@@ -568,9 +621,12 @@ int bvh_build(FtnScene* s) {
                         std::swap(cin, cout);
                     }
                     if (rc != FTN_OK) break;
+                    if (c > 1u) { k_ploc_finish<<<1, PLOC_FINISH_MAX, 0, st>>>(a, leaf_lo, leaf_hi, cin, c, n, created, d_small + 4); count_launch(); }
                     k_ploc_leaf_positions<<<gb256, 256, 0, st>>>(a, n, newpos, d_small + 1); count_launch();
-                    uint32_t max_depth = 0;
-                    if ((e = cudaMemcpyAsync(&max_depth, d_small + 1, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess || (e = cudaStreamSynchronize(st)) != cudaSuccess) { rc = cuda_fail(e, "PLOC depth", __FILE__, __LINE__); break; }
+                    uint32_t h_small[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    if ((e = cudaMemcpyAsync(h_small, d_small, sizeof(h_small), cudaMemcpyDeviceToHost, st)) != cudaSuccess || (e = cudaStreamSynchronize(st)) != cudaSuccess) { rc = cuda_fail(e, "PLOC depth", __FILE__, __LINE__); break; }
+                    if (c > 1u && (h_small[4] != 0u || h_small[5] != (uint32_t)ni || h_small[6] != 0u)) { rc = set_error(FTN_ERR_CUDA, "PLOC finish kernel did not end at root 0"); break; }
+                    const uint32_t max_depth = h_small[1];
                     if (max_depth <= (uint32_t)FTN_STACK_SIZE - 4u) {   // else: a degenerate chain; the radix tree below is depth-bounded
                         k_ploc_node_ranges<<<gi, 256, 0, st>>>(a, n); count_launch();
                         k_ploc_permute_leaves<<<gb256, 256, 0, st>>>(n, newpos, leaf_lo, leaf_hi, s->d_order, lo2, hi2, order2); count_launch();
