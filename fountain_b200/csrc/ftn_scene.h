@@ -145,6 +145,8 @@ struct DeviceArena {
     void* p[3] = {nullptr, nullptr, nullptr}; size_t bytes[3] = {0, 0, 0}; std::mutex m;
     enum { PATHS = 0, FILM = 1, BUILD = 2 };
     int reserve(int which, size_t need, const char* what, void** out);
+    void* h_pinned = nullptr; size_t h_pinned_bytes = 0;   // small pinned host block (queue-counter read-back)
+    int pinned_counts(uint32_t** out, size_t bytes);
 };
 DeviceArena& device_arena(int device);
 int release_cached_memory();

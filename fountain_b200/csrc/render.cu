@@ -390,6 +390,10 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
     const unsigned shade_grid = (unsigned)(sm_count() * 8);
     const int reach = (int)std::ceil(std::max(fg.radius[0], fg.radius[1]) + 0.5f);
     TraceTimer timer; timer.st = st;
+    uint32_t* h_counts = nullptr;           // pinned read-back slot of the queue counters, one per device
+    FTN_TRY(arena.pinned_counts(&h_counts, CTR_COUNT * sizeof(uint32_t)));
+    cudaEvent_t ev_counts;
+    FTN_CUDA(cudaEventCreateWithFlags(&ev_counts, cudaEventDisableTiming));
 
     PassParams pp; std::memset(&pp, 0, sizeof(pp));
     pp.film = fg; pp.cam = *cam; pp.seed_key = sampler_seed_key(smp->seed);
@@ -426,26 +430,28 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
             if (s->material_present[1]) { k_shade<Q_MAT1><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT1], q, counts, d_err); FTN_LAUNCHED(); }
             if (s->material_present[2]) { k_shade<Q_MAT2><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT2], q, counts, d_err); FTN_LAUNCHED(); }
             if (s->material_present[3]) { k_shade<Q_MAT3><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT3], q, counts, d_err); FTN_LAUNCHED(); }
-            uint32_t hc[CTR_COUNT];
-            FTN_CUDA(cudaMemcpyAsync(hc, counts, sizeof(hc), cudaMemcpyDeviceToHost, st));
-            FTN_CUDA(cudaStreamSynchronize(st));
-            if (hc[Q_SHADOW]) {
-                const unsigned g = trace_grid(hc[Q_SHADOW], FTN_TRACE_BLOCKS_PER_SM);
-                timer.begin(1);
-                FTN_BOOL3(count_traversal, sph, sc.vote, (k_shadow<B0, B1, B2><<<g, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_SHADOW], counts, d_trav + 2)));
-                timer.end();
-                FTN_LAUNCHED();
-                class_rays[1] += hc[Q_SHADOW];
-            }
-            if (hc[Q_MIS]) {
-                const unsigned g = trace_grid(hc[Q_MIS], FTN_TRACE_BLOCKS_PER_SM);
-                timer.begin(2);
-                if (has_area) { FTN_BOOL3(count_traversal, sph, sc.vote, (k_mis<false, B0, B1, B2><<<g, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts, d_trav + 4))); }
-                else { FTN_BOOL3(count_traversal, sph, sc.vote, (k_mis<true, B0, B1, B2><<<g, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts, d_trav + 4))); }
-                timer.end();
-                FTN_LAUNCHED();
-                class_rays[2] += hc[Q_MIS];
-            }
+            // The shadow and MIS queues cannot be longer than this iteration's input queue, and their kernels
+            // read the exact lengths on the device: launch them sized by that bound BEFORE waiting for the
+            // counts, so that the host round trip (needed to size the next iteration and to stop) is hidden
+            // behind them instead of leaving the GPU idle once per bounce.
+            // (the copy goes to PINNED memory and is waited for through an event recorded right behind it: the
+            //  shadow / MIS kernels are already queued when the host wakes up)
+            FTN_CUDA(cudaMemcpyAsync(h_counts, counts, CTR_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            FTN_CUDA(cudaEventRecord(ev_counts, st));
+            const unsigned gq = trace_grid(n_active, FTN_TRACE_BLOCKS_PER_SM);
+            timer.begin(1);
+            FTN_BOOL3(count_traversal, sph, sc.vote, (k_shadow<B0, B1, B2><<<gq, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_SHADOW], counts, d_trav + 2)));
+            timer.end();
+            FTN_LAUNCHED();
+            timer.begin(2);
+            if (has_area) { FTN_BOOL3(count_traversal, sph, sc.vote, (k_mis<false, B0, B1, B2><<<gq, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts, d_trav + 4))); }
+            else { FTN_BOOL3(count_traversal, sph, sc.vote, (k_mis<true, B0, B1, B2><<<gq, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts, d_trav + 4))); }
+            timer.end();
+            FTN_LAUNCHED();
+            FTN_CUDA(cudaEventSynchronize(ev_counts));
+            const uint32_t* hc = h_counts;
+            class_rays[1] += hc[Q_SHADOW];
+            class_rays[2] += hc[Q_MIS];
             n_active = hc[Q_ACTIVE_OUT];
             q_in = q_out;
             std::swap(q_out, q_spare);
@@ -453,6 +459,7 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
         k_film_accumulate<<<(fw * fh + 127) / 128, 128, 0, st>>>(pp, pa, accum, reach, d_err);
         FTN_LAUNCHED();
     }
+    cudaEventDestroy(ev_counts);
     k_film_resolve<<<(fw * fh + 255) / 256, 256, 0, st>>>(accum, d_pixels, fw * fh);
     FTN_LAUNCHED();
     uint32_t h_err = 0;

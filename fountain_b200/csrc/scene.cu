@@ -295,13 +295,24 @@ int DeviceArena::reserve(int which, size_t need, const char* what, void** out) {
     *out = p[which];
     return FTN_OK;
 }
+int DeviceArena::pinned_counts(uint32_t** out, size_t need) {
+    if (h_pinned_bytes < need) {
+        if (h_pinned) { cudaFreeHost(h_pinned); h_pinned = nullptr; h_pinned_bytes = 0; }
+        cudaError_t e = cudaHostAlloc(&h_pinned, need < 256 ? 256 : need, cudaHostAllocDefault);
+        if (e != cudaSuccess) { h_pinned = nullptr; return cuda_fail(e, "cudaHostAlloc (counter read-back)", __FILE__, __LINE__); }
+        h_pinned_bytes = need < 256 ? 256 : need;
+    }
+    *out = (uint32_t*)h_pinned;
+    return FTN_OK;
+}
 int release_cached_memory() {
     for (int d = 0; d < FTN_MAX_DEVICES; ++d) {
         DeviceArena& a = g_arena[d];
         std::lock_guard<std::mutex> lock(a.m);
-        if (!a.p[0] && !a.p[1] && !a.p[2]) continue;
+        if (!a.p[0] && !a.p[1] && !a.p[2] && !a.h_pinned) continue;
         if (cudaSetDevice(d) != cudaSuccess) continue;
         for (int i = 0; i < 3; ++i) { cudaFree(a.p[i]); a.p[i] = nullptr; a.bytes[i] = 0; }
+        if (a.h_pinned) { cudaFreeHost(a.h_pinned); a.h_pinned = nullptr; a.h_pinned_bytes = 0; }
     }
     return FTN_OK;
 }

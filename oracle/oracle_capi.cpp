@@ -7,7 +7,9 @@
 // The oracle is pinned against every known-answer test the reference's own test-suite holds
 // for this path (tests/test_oracle_kat.py lists them with file:line).  The RNG stream
 // (rand/rand_xoshiro, un-vendored) and cgmath ulp-level behaviour are restated from their
-// published sources and are "parity unpinned" -- no reference test pins them.
+// published sources and are "parity unpinned" -- no reference test pins them.  The round-1 widenings
+// (point / distant lights, mirror, checkerboard / uv textures) have no reference test either: their
+// restatements are pinned against closed forms only (tests/test_oracle_render.py).
 #include "../include/fountain_gpu.h"
 #include "ref_render.h"
 #include <chrono>
