@@ -218,3 +218,12 @@ def test_checkerboard_closed_form(gpu_backend):
         scene, camera, film = scenes.textured_floor_scene(backend=gpu_backend, resolution=(5, 5), look_at=xy, fov=0.5)
         api.SamplerIntegrator(camera, api.DirectLightingIntegrator(1)).render_parallel(scene, film, api.RandomSampler.new_with_seed(2, 0))
         assert np.allclose(film.into_spectrum_buffer()[0], expected[None, :], rtol=1e-5), xy
+
+
+def test_release_cached_memory_and_render_again(gpu_backend):
+    """ftn_release_cached_memory frees the per-device arenas; the next render re-allocates and gives the
+    same film bit for bit."""
+    a, apx, _ = parity.render(gpu_backend, scenes.furnace_scene, api.PathIntegrator(4, 1.0), 8, seed=2)
+    gpu_backend.call("release_cached_memory")
+    b, bpx, _ = parity.render(gpu_backend, scenes.furnace_scene, api.PathIntegrator(4, 1.0), 8, seed=2)
+    assert np.array_equal(apx, bpx)
