@@ -62,10 +62,20 @@ k_tri_bounds(const float* __restrict__ pos, const uint32_t* __restrict__ idx, ui
             clo[a] = fminf(clo[a], __shfl_xor_sync(0xffffffffu, clo[a], o));
             chi[a] = fmaxf(chi[a], __shfl_xor_sync(0xffffffffu, chi[a], o));
         }
-        if ((threadIdx.x & 31) == 0) {
-            atomicMin(&gb->scene_lo[a], float_flip(lo[a])); atomicMax(&gb->scene_hi[a], float_flip(hi[a]));
-            atomicMin(&gb->cen_lo[a], float_flip(clo[a])); atomicMax(&gb->cen_hi[a], float_flip(chi[a]));
-        }
+    }
+    // ... then a block reduce in shared memory and ONE atomic per block per component (12 contended
+    // addresses: per-warp atomics made this kernel 240 us for 1M triangles)
+    __shared__ float red[8][12];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) for (int a = 0; a < 3; ++a) { red[warp][a] = lo[a]; red[warp][3 + a] = hi[a]; red[warp][6 + a] = clo[a]; red[warp][9 + a] = chi[a]; }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        const int k = threadIdx.x;
+        const bool is_min = (k < 3) || (k >= 6 && k < 9);
+        float v = red[0][k];
+        for (int w = 1; w < 8; ++w) v = is_min ? fminf(v, red[w][k]) : fmaxf(v, red[w][k]);
+        uint32_t* dst = (k < 3) ? &gb->scene_lo[k] : (k < 6) ? &gb->scene_hi[k - 3] : (k < 9) ? &gb->cen_lo[k - 6] : &gb->cen_hi[k - 9];
+        if (is_min) atomicMin(dst, float_flip(v)); else atomicMax(dst, float_flip(v));
     }
 }
 
