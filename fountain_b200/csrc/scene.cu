@@ -120,27 +120,34 @@ k_ploc_init(uint32_t n, uint32_t* __restrict__ cl) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) cl[i] = LBVH_LEAF_FLAG | i;
 }
+// The multi-launch rounds keep the cluster count and the number of nodes created so far ON THE DEVICE
+// (state = {c, created}, double-buffered per round) and are launched for an upper bound c_bound of the
+// count (it only shrinks): the host reads the state back once per GROUP of rounds, not once per round.
 __global__ void __launch_bounds__(256)
-k_ploc_nearest(LbvhArrays a, const F4* __restrict__ leaf_lo, const F4* __restrict__ leaf_hi, const uint32_t* __restrict__ cl, uint32_t c,
-               uint32_t* __restrict__ nn) {
+k_ploc_nearest(LbvhArrays a, const F4* __restrict__ leaf_lo, const F4* __restrict__ leaf_hi, const uint32_t* __restrict__ cl,
+               const uint32_t* __restrict__ state, uint32_t* __restrict__ nn) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t c = state[0];
     if (i < c) nn[i] = ploc_nearest(a, leaf_lo, leaf_hi, cl, c, i);
 }
 __global__ void __launch_bounds__(256)
-k_ploc_flags(const uint32_t* __restrict__ nn, uint32_t c, uint32_t* __restrict__ merge, uint32_t* __restrict__ valid) {
+k_ploc_flags(const uint32_t* __restrict__ nn, const uint32_t* __restrict__ state, uint32_t c_bound, uint32_t* __restrict__ merge,
+             uint32_t* __restrict__ valid) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < c) ploc_flags(nn, i, merge, valid);
+    if (i >= c_bound) return;
+    if (i < state[0]) ploc_flags(nn, i, merge, valid);
+    else { merge[i] = 0u; valid[i] = 0u; }     // beyond the live clusters: nothing to scan
 }
-// also leaves the number of merges of this round in *n_merged (read by the host to size the next round)
 __global__ void __launch_bounds__(256)
 k_ploc_merge(LbvhArrays a, const F4* __restrict__ leaf_lo, const F4* __restrict__ leaf_hi, const uint32_t* __restrict__ cl_in,
              uint32_t* __restrict__ cl_out, const uint32_t* __restrict__ nn, const uint32_t* __restrict__ merge, const uint32_t* __restrict__ valid,
-             const uint32_t* __restrict__ mscan, const uint32_t* __restrict__ vscan, uint32_t n, uint32_t created, uint32_t c,
-             uint32_t* __restrict__ n_merged) {
+             const uint32_t* __restrict__ mscan, const uint32_t* __restrict__ vscan, uint32_t n, const uint32_t* __restrict__ state,
+             uint32_t* __restrict__ state_next) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t c = state[0], created = state[1];
     if (i >= c) return;
     ploc_merge(a, leaf_lo, leaf_hi, cl_in, cl_out, nn, merge, valid, mscan, vscan, n, created, i);
-    if (i == c - 1u) *n_merged = mscan[i] + merge[i];
+    if (i == c - 1u) { const uint32_t merged = mscan[i] + merge[i]; state_next[0] = c - merged; state_next[1] = created + merged; }
 }
 // The tail of the clustering in ONE block: once at most PLOC_FINISH_MAX clusters are left, the remaining
 // rounds (the majority: ~200 rounds for 1M triangles, ~14 of them above this size) run inside a single
@@ -628,18 +635,29 @@ int bvh_build(FtnScene* s) {
                     k_ploc_init<<<gb256, 256, 0, st>>>(n, cl0); count_launch();
                     uint32_t c = n, created = 0;
                     uint32_t *cin = cl0, *cout = cl1;
+                    uint32_t* d_state = d_small + 8;            // {c, created} x 2 (double buffer)
+                    const uint32_t h_state0[2] = {n, 0u};
+                    if ((e = cudaMemcpyAsync(d_state, h_state0, 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) { rc = cuda_fail(e, "PLOC state", __FILE__, __LINE__); break; }
+                    int parity = 0;
+                    const int group = 4;                        // rounds per host read-back
                     while (c > (uint32_t)PLOC_FINISH_MAX && rc == FTN_OK) {
-                        const unsigned gc = (c + 255) / 256;
-                        k_ploc_nearest<<<gc, 256, 0, st>>>(a, leaf_lo, leaf_hi, cin, c, nn); count_launch();
-                        k_ploc_flags<<<gc, 256, 0, st>>>(nn, c, mg, va); count_launch();
-                        if ((rc = exclusive_scan_u32(mg, ms, c, pscan, st)) != FTN_OK) break;
-                        if ((rc = exclusive_scan_u32(va, vs, c, pscan, st)) != FTN_OK) break;
-                        k_ploc_merge<<<gc, 256, 0, st>>>(a, leaf_lo, leaf_hi, cin, cout, nn, mg, va, ms, vs, n, created, c, d_small); count_launch();
-                        uint32_t merged = 0;
-                        if ((e = cudaMemcpyAsync(&merged, d_small, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess || (e = cudaStreamSynchronize(st)) != cudaSuccess) { rc = cuda_fail(e, "PLOC round", __FILE__, __LINE__); break; }
-                        if (merged == 0 || merged > c / 2) { rc = set_error(FTN_ERR_CUDA, "PLOC round without progress"); break; }
-                        created += merged; c -= merged;
-                        std::swap(cin, cout);
+                        const unsigned gc = (c + 255) / 256;    // c: exact at the start of the group, an upper bound inside it
+                        for (int r = 0; r < group && rc == FTN_OK; ++r) {
+                            const uint32_t* st_in = d_state + 2 * parity;
+                            uint32_t* st_out = d_state + 2 * (parity ^ 1);
+                            k_ploc_nearest<<<gc, 256, 0, st>>>(a, leaf_lo, leaf_hi, cin, st_in, nn); count_launch();
+                            k_ploc_flags<<<gc, 256, 0, st>>>(nn, st_in, c, mg, va); count_launch();
+                            if ((rc = exclusive_scan_u32(mg, ms, c, pscan, st)) != FTN_OK) break;
+                            if ((rc = exclusive_scan_u32(va, vs, c, pscan, st)) != FTN_OK) break;
+                            k_ploc_merge<<<gc, 256, 0, st>>>(a, leaf_lo, leaf_hi, cin, cout, nn, mg, va, ms, vs, n, st_in, st_out); count_launch();
+                            std::swap(cin, cout);
+                            parity ^= 1;
+                        }
+                        if (rc != FTN_OK) break;
+                        uint32_t h_state[2] = {0, 0};
+                        if ((e = cudaMemcpyAsync(h_state, d_state + 2 * parity, 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess || (e = cudaStreamSynchronize(st)) != cudaSuccess) { rc = cuda_fail(e, "PLOC round", __FILE__, __LINE__); break; }
+                        if (h_state[0] == 0u || h_state[0] >= c || h_state[0] + h_state[1] != n) { rc = set_error(FTN_ERR_CUDA, "PLOC rounds without progress"); break; }
+                        c = h_state[0]; created = h_state[1];
                     }
                     if (rc != FTN_OK) break;
                     if (c > 1u) { k_ploc_finish<<<1, PLOC_FINISH_MAX, 0, st>>>(a, leaf_lo, leaf_hi, cin, c, n, created, d_small + 4); count_launch(); }
