@@ -666,7 +666,9 @@ int bvh_build(FtnScene* s) {
                     if ((e = cudaMemcpyAsync(h_small, d_small, sizeof(h_small), cudaMemcpyDeviceToHost, st)) != cudaSuccess || (e = cudaStreamSynchronize(st)) != cudaSuccess) { rc = cuda_fail(e, "PLOC depth", __FILE__, __LINE__); break; }
                     if (c > 1u && (h_small[4] != 0u || h_small[5] != (uint32_t)ni || h_small[6] != 0u)) { rc = set_error(FTN_ERR_CUDA, "PLOC finish kernel did not end at root 0"); break; }
                     const uint32_t max_depth = h_small[1];
-                    if (max_depth <= (uint32_t)FTN_STACK_SIZE - 4u) {   // else: a degenerate chain; the radix tree below is depth-bounded
+                    const char* depth_env = getenv("FTN_PLOC_MAX_DEPTH");   // test hook: force the fallback
+                    const uint32_t depth_limit = depth_env ? (uint32_t)atoi(depth_env) : (uint32_t)FTN_STACK_SIZE - 4u;
+                    if (max_depth <= depth_limit) {   // else: a degenerate chain; the radix tree below is depth-bounded
                         k_ploc_node_ranges<<<gi, 256, 0, st>>>(a, n); count_launch();
                         k_ploc_permute_leaves<<<gb256, 256, 0, st>>>(n, newpos, leaf_lo, leaf_hi, s->d_order, lo2, hi2, order2); count_launch();
                         k_ploc_rewrite_refs<<<gi, 256, 0, st>>>(a, n, newpos); count_launch();

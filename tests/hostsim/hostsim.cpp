@@ -177,7 +177,9 @@ SIM_API int sim_bvh_build(SimScene* s) {
                 if (created != ni || cin[0] != 0u) return fail(FTN_ERR_CUDA, "PLOC did not end at root 0");
                 std::vector<uint32_t> newpos(n); uint32_t max_depth = 0;
                 for (uint32_t l = 0; l < n; ++l) { uint32_t d; newpos[l] = ploc_dfs_position(a, n, LBVH_LEAF_FLAG | l, &d); max_depth = std::max(max_depth, d); }
-                if (max_depth <= (uint32_t)FTN_STACK_SIZE - 4u) {
+                const char* depth_env = getenv("FTN_PLOC_MAX_DEPTH");
+                const uint32_t depth_limit = depth_env ? (uint32_t)atoi(depth_env) : (uint32_t)FTN_STACK_SIZE - 4u;
+                if (max_depth <= depth_limit) {
                     for (size_t i = 0; i < ni; ++i) { uint32_t d; first[i] = ploc_dfs_position(a, n, (uint32_t)i, &d); last[i] = first[i] + arrive[i] - 1u; }
                     std::vector<F4> l2(n), h2(n); std::vector<uint32_t> seen(n, 0);
                     for (uint32_t l = 0; l < n; ++l) { l2[newpos[l]] = leaf_lo[l]; h2[newpos[l]] = leaf_hi[l]; final_order[newpos[l]] = s->order[l]; seen[newpos[l]]++; }

@@ -183,3 +183,13 @@ def test_builders_degenerate_inputs(gpu_backend, orc_backend, monkeypatch, build
     ha, hb = a.intersect(rays), b.intersect(rays)
     assert np.array_equal(ha["prim"] == A.FTN_NO_HIT, hb["prim"] == A.FTN_NO_HIT) and np.array_equal(ha["t"], hb["t"])
     assert np.array_equal(a.intersect_test(rays), b.intersect_test(rays))
+
+
+def test_ploc_depth_fallback_to_radix_tree(gpu_backend, orc_backend, rounded_cube_path, monkeypatch):
+    monkeypatch.setenv("FTN_BVH_BUILDER", "ploc")
+    monkeypatch.setenv("FTN_PLOC_MAX_DEPTH", "3")
+    a, b = parity.cube_scenes(gpu_backend, orc_backend, rounded_cube_path)
+    assert a.stats()["bvh_nodes"] == 1355
+    parity.check_morton(a, b)
+    parity.check_ray_batch(a, b, parity.random_ray_batch(100_000, 15), "fallback")
+    parity.check_watertight(a, n=100_000)

@@ -335,3 +335,14 @@ def test_builders_give_identical_results(sim_backend, orc_backend, rounded_cube_
     rays = parity.random_ray_batch(3000, 23, extent=2.0, far=6.0)
     ha, hb = sa.intersect(rays), sb.intersect(rays)
     assert np.array_equal(ha["prim"] == A.FTN_NO_HIT, hb["prim"] == A.FTN_NO_HIT) and np.array_equal(ha["t"], hb["t"])
+
+
+def test_ploc_depth_fallback_to_radix_tree(sim_backend, orc_backend, rounded_cube_path, monkeypatch):
+    """A PLOC tree deeper than the traversal stack allows is discarded for the depth-bounded radix tree
+    (forced here through the test hook FTN_PLOC_MAX_DEPTH)."""
+    monkeypatch.setenv("FTN_BVH_BUILDER", "ploc")
+    monkeypatch.setenv("FTN_PLOC_MAX_DEPTH", "3")
+    a, b = parity.cube_scenes(sim_backend, orc_backend, rounded_cube_path)
+    assert a.stats()["bvh_nodes"] == 1355          # the radix tree's node count for this mesh
+    parity.check_morton(a, b)
+    parity.check_ray_batch(a, b, parity.random_ray_batch(20000, 15), "fallback")
