@@ -74,6 +74,25 @@ __device__ __forceinline__ void queue_push(uint32_t* const* queues, uint32_t* co
 
 struct Queues { uint32_t* q[Q_COUNT]; };
 
+// The three appends of the shade stage (next-bounce, shadow and MIS queues) with ONE atomic round trip:
+// lanes 0..2 reserve the three ranges in a single atomic instruction (the three sequential queue_push calls
+// left 11 % of k_shade's stall samples waiting on their atomics).  All 32 lanes call.
+__device__ __forceinline__ void queue_push3(const Queues& qs, uint32_t* counts, bool to_active, bool to_shadow, bool to_mis, uint32_t path) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned m_a = __ballot_sync(0xffffffffu, to_active), m_s = __ballot_sync(0xffffffffu, to_shadow), m_m = __ballot_sync(0xffffffffu, to_mis);
+    uint32_t base = 0;
+    if (lane < 3) {
+        const unsigned m = lane == 0 ? m_a : (lane == 1 ? m_s : m_m);
+        const int q = lane == 0 ? Q_ACTIVE_OUT : (lane == 1 ? Q_SHADOW : Q_MIS);
+        if (m) base = atomicAdd(&counts[q], (uint32_t)__popc(m));
+    }
+    const uint32_t b_a = __shfl_sync(0xffffffffu, base, 0), b_s = __shfl_sync(0xffffffffu, base, 1), b_m = __shfl_sync(0xffffffffu, base, 2);
+    if (to_active) qs.q[Q_ACTIVE_OUT][b_a + __popc(m_a & lt)] = path;
+    if (to_shadow) qs.q[Q_SHADOW][b_s + __popc(m_s & lt)] = path;
+    if (to_mis) qs.q[Q_MIS][b_m + __popc(m_m & lt)] = path;
+}
+
 // node-visit / triangle-test totals of the counting variants (the bytes-per-ray roofline input)
 __device__ __forceinline__ void flush_trace_counters(const TraceCounters& tc, unsigned long long* trav) {
     unsigned long long n = tc.nodes, t = tc.tris;
@@ -186,9 +205,7 @@ k_shade(SceneView sc, PassParams pp, PathArrays pa, const uint32_t* __restrict__
                 t_active = Q_ACTIVE_OUT;
             }
         }
-        queue_push(qs.q, counts, t_active, path);
-        queue_push(qs.q, counts, t_shadow, path);
-        queue_push(qs.q, counts, t_mis, path);
+        queue_push3(qs, counts, t_active >= 0, t_shadow >= 0, t_mis >= 0, path);
     }
 }
 
