@@ -46,8 +46,13 @@ FTN_HD float power_heuristic1(float f, float g) { return (f * f) / (f * f + g * 
 
 // ---- level-0 MIPMap lookup, mipmap.rs:245-312, ImageWrap::Repeat -------------------------------------
 FTN_HD V3 env_texel(const EnvLightData& e, int s, int t) {
-    int ss = s % e.w; if (ss < 0) ss += e.w;
-    int tt = t % e.h; if (tt < 0) tt += e.h;
+    // Euclidean s mod w.  Lookups arrive with s in [-1, w] (one texel beyond the image): one conditional add
+    // instead of an integer division; anything further out takes the general form.
+    int ss, tt;
+    if (s >= -e.w && s < 2 * e.w) ss = s < 0 ? s + e.w : (s >= e.w ? s - e.w : s);
+    else { ss = s % e.w; if (ss < 0) ss += e.w; }
+    if (t >= -e.h && t < 2 * e.h) tt = t < 0 ? t + e.h : (t >= e.h ? t - e.h : t);
+    else { tt = t % e.h; if (tt < 0) tt += e.h; }
     const F4 v = ld4(e.texels + (size_t)tt * e.w + ss);
     return V3(v.x, v.y, v.z);
 }
