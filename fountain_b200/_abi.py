@@ -132,6 +132,8 @@ PROTOTYPES = {
     "film_to_rgb_device": (C.c_int, [C.c_size_t, VOIDP, VOIDP, VOIDP]),
     "film_pixel_count": (C.c_int, [P(FtnFilm), P(i32), P(i32)]),
     "release_cached_memory": (C.c_int, []),
+    "host_alloc": (C.c_int, [C.c_size_t, P(VOIDP)]),
+    "host_free": (C.c_int, [VOIDP]),
 }
 
 # Subset the CPU oracle implements (host buffers only), plus its own extras bound in oracle/orc.py.

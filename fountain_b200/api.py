@@ -537,6 +537,29 @@ class BoxFilter:
         self.radius = (float(radius[0]), float(radius[1]))
 
 
+class _PinnedPool:
+    """Page-locked host buffers (ftn_host_alloc) recycled by size: a Film's pixel buffer is written by the
+    device every render, so it lives in pinned memory when the backend offers it -- and cudaHostAlloc is far
+    too slow to pay per Film."""
+
+    def __init__(self):
+        self.free = {}     # (backend id, bytes) -> [pointer]
+
+    def take(self, backend, nbytes):
+        key = (id(backend), nbytes)
+        if self.free.get(key):
+            return self.free[key].pop()
+        p = A.VOIDP()
+        backend.call("host_alloc", nbytes, C.byref(p))
+        return p.value
+
+    def give(self, backend, nbytes, ptr):
+        self.free.setdefault((id(backend), nbytes), []).append(ptr)
+
+
+_PINNED = _PinnedPool()
+
+
 class Film:
     """film.rs:18-81.  After a render `pixels` is an (h, w, 4) float32 array of XYZ sums and
     filter-weight sums -- `Film.pixels` (film.rs:24)."""
@@ -552,7 +575,23 @@ class Film:
         w, h = A.i32(), A.i32()
         self.backend.call("film_pixel_count", C.byref(self.to_abi()), C.byref(w), C.byref(h))
         self.width, self.height = w.value, h.value
-        self.pixels = np.zeros((self.height, self.width, 4), dtype=np.float32)
+        self._pinned = None
+        nbytes = self.height * self.width * 16
+        if nbytes and self.backend.has("host_alloc"):
+            self._pinned = _PINNED.take(self.backend, nbytes)
+            buf = (C.c_float * (self.height * self.width * 4)).from_address(self._pinned)
+            self.pixels = np.frombuffer(buf, dtype=np.float32).reshape(self.height, self.width, 4)
+            self.pixels[...] = 0.0
+        else:
+            self.pixels = np.zeros((self.height, self.width, 4), dtype=np.float32)
+
+    def __del__(self):
+        try:
+            if self._pinned is not None:
+                _PINNED.give(self.backend, self.height * self.width * 16, self._pinned)
+                self._pinned = None
+        except Exception:
+            pass
 
     def to_abi(self):
         f = A.FtnFilm()
@@ -632,11 +671,10 @@ class SamplerIntegrator:
         """Renders into film.pixels.  Raises FountainError(FTN_ERR_NAN_RADIANCE) where the
         reference panics in check_radiance (integrator/mod.rs:285)."""
         st = A.FtnStats()
-        out = np.zeros((film.height, film.width, 4), dtype=np.float32)
+        out = film.pixels          # ftn_render overwrites every pixel of the cropped bounds
         cam, f, s, it = self.camera.to_abi(), film.to_abi(), sampler.to_abi(sample_begin, sample_stride), self.radiance.to_abi()
         scene.backend.call("render", scene.handle, C.byref(cam), C.byref(f), C.byref(s), C.byref(it),
                            out.ctypes.data_as(C.POINTER(A.FtnPixel)), C.byref(st))
-        film.pixels = out
         self.last_stats = st.as_dict()
         return self.last_stats
 

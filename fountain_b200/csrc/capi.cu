@@ -123,6 +123,16 @@ FTN_API int ftn_render(const FtnScene* s, const FtnCamera* cam, const FtnFilm* f
     return render_host(s, cam, film, smp, integ, out_pixels, stats);
 }
 FTN_API int ftn_release_cached_memory(void) { return release_cached_memory(); }
+FTN_API int ftn_host_alloc(size_t bytes, void** out) {
+    if (!out) return set_error(FTN_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    FTN_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return FTN_OK;
+}
+FTN_API int ftn_host_free(void* p) {
+    if (p) FTN_CUDA(cudaFreeHost(p));
+    return FTN_OK;
+}
 FTN_API int ftn_film_to_rgb_device(size_t n, const FtnPixel* d_pixels, float* d_rgb, void* stream) {
     return film_to_rgb_device(n, d_pixels, d_rgb, (cudaStream_t)stream);
 }

@@ -313,6 +313,11 @@ FTN_API int ftn_film_to_rgb_device(size_t n, const FtnPixel* d_pixels, float* d_
  * This returns that memory to the driver; the next render allocates again. */
 FTN_API int ftn_release_cached_memory(void);
 
+/* Page-locked host memory for buffers that cross the boundary every call (the film of ftn_render, ray / hit
+ * batches of ftn_intersect): copies to and from it run at full PCIe rate and need no staging. */
+FTN_API int ftn_host_alloc(size_t bytes, void** out);
+FTN_API int ftn_host_free(void* p);
+
 /* Number of pixels ftn_render writes for this film (cropped_pixel_bounds area, film.rs:49-58). */
 FTN_API int ftn_film_pixel_count(const FtnFilm* film, int32_t* out_w, int32_t* out_h);
 
