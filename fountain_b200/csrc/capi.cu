@@ -1,6 +1,7 @@
 // extern "C" surface of libfountain_gpu.so (include/fountain_gpu.h).  No CPU fallback: every
 // compute entry point needs a CUDA device and says so when there is none.
 #include "ftn_scene.h"
+#include <mutex>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -90,22 +91,55 @@ FTN_API int ftn_intersect_count_device(const FtnScene* s, size_t n, const FtnRay
     return intersect_device(s, n, d_rays, d_hits, nullptr, false, (unsigned long long*)d_counters, (cudaStream_t)stream);
 }
 
+// Host-buffer queries: device staging from the per-device arena (no allocation per call) and a three-stream
+// pipeline over chunks of the batch -- upload of chunk i+1, traversal of chunk i and download of chunk i-1
+// overlap (truly so when the caller's buffers are page-locked, e.g. from ftn_host_alloc; with pageable memory the
+// copies degrade to staged ones and the result is the same).
 static int intersect_host(const FtnScene* s, size_t n, const FtnRay* rays, FtnHit* hits, uint8_t* any_out, bool any) {
     if (!s) return set_error(FTN_ERR_INVALID_ARGUMENT, "null scene");
     if (n == 0) return FTN_OK;
     if (!rays || (!any && !hits) || (any && !any_out)) return set_error(FTN_ERR_INVALID_ARGUMENT, "null buffer");
     FTN_CUDA(cudaSetDevice(s->device));
-    FtnRay* d_rays = nullptr; void* d_out = nullptr;
-    const size_t out_bytes = any ? n : n * sizeof(FtnHit);
-    cudaError_t e = cudaMalloc(&d_rays, n * sizeof(FtnRay));
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc rays", __FILE__, __LINE__);
-    e = cudaMalloc(&d_out, out_bytes);
-    if (e != cudaSuccess) { cudaFree(d_rays); return cuda_fail(e, "cudaMalloc hits", __FILE__, __LINE__); }
+    const size_t out_elem = any ? 1 : sizeof(FtnHit);
+    const size_t in_bytes = (n * sizeof(FtnRay) + 255) & ~(size_t)255;
+    DeviceArena& arena = device_arena(s->device);
+    std::lock_guard<std::mutex> lock(arena.m);
+    char* base = nullptr;
+    FTN_TRY(arena.reserve(DeviceArena::BATCH, in_bytes + n * out_elem + 256, "cudaMalloc (ray batch staging)", (void**)&base));
+    FtnRay* d_rays = (FtnRay*)base;
+    char* d_out = base + in_bytes;
+    cudaStream_t st_in = nullptr, st_k = nullptr, st_out = nullptr;
+    const int RING = 4;
+    cudaEvent_t ev_in[RING], ev_k[RING], ev_out[RING];
+    int n_ev = 0;
     int rc = FTN_OK;
-    if ((e = cudaMemcpy(d_rays, rays, n * sizeof(FtnRay), cudaMemcpyHostToDevice)) != cudaSuccess) rc = cuda_fail(e, "H2D rays", __FILE__, __LINE__);
-    if (rc == FTN_OK) rc = intersect_device(s, n, d_rays, any ? nullptr : (FtnHit*)d_out, any ? (uint8_t*)d_out : nullptr, any, nullptr, 0);
-    if (rc == FTN_OK && (e = cudaMemcpy(any ? (void*)any_out : (void*)hits, d_out, out_bytes, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "D2H hits", __FILE__, __LINE__);
-    cudaFree(d_rays); cudaFree(d_out);
+    cudaError_t e = cudaSuccess;
+    auto fail = [&](const char* what) { rc = cuda_fail(e, what, __FILE__, __LINE__); };
+    if ((e = cudaStreamCreateWithFlags(&st_in, cudaStreamNonBlocking)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&st_k, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&st_out, cudaStreamNonBlocking)) != cudaSuccess) fail("cudaStreamCreate");
+    for (; rc == FTN_OK && n_ev < RING; ++n_ev)
+        if ((e = cudaEventCreateWithFlags(&ev_in[n_ev], cudaEventDisableTiming)) != cudaSuccess || (e = cudaEventCreateWithFlags(&ev_k[n_ev], cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&ev_out[n_ev], cudaEventDisableTiming)) != cudaSuccess) { fail("cudaEventCreate"); break; }
+    const size_t chunk = (size_t)1 << 19;     // 16 MiB of rays per stage
+    size_t ci = 0;
+    for (size_t off = 0; off < n && rc == FTN_OK; off += chunk, ++ci) {
+        const size_t m = n - off < chunk ? n - off : chunk;
+        const int r = (int)(ci % RING);
+        if (ci >= (size_t)RING && (e = cudaEventSynchronize(ev_out[r])) != cudaSuccess) { fail("event sync"); break; }   // ring slot free again
+        if ((e = cudaMemcpyAsync(d_rays + off, rays + off, m * sizeof(FtnRay), cudaMemcpyHostToDevice, st_in)) != cudaSuccess) { fail("H2D rays"); break; }
+        cudaEventRecord(ev_in[r], st_in);
+        cudaStreamWaitEvent(st_k, ev_in[r], 0);
+        rc = intersect_device(s, m, d_rays + off, any ? nullptr : (FtnHit*)d_out + off, any ? (uint8_t*)d_out + off : nullptr, any, nullptr, st_k);
+        if (rc != FTN_OK) break;
+        cudaEventRecord(ev_k[r], st_k);
+        cudaStreamWaitEvent(st_out, ev_k[r], 0);
+        void* dst = any ? (void*)(any_out + off) : (void*)(hits + off);
+        if ((e = cudaMemcpyAsync(dst, d_out + off * out_elem, m * out_elem, cudaMemcpyDeviceToHost, st_out)) != cudaSuccess) { fail("D2H hits"); break; }
+        cudaEventRecord(ev_out[r], st_out);
+    }
+    for (cudaStream_t st : {st_in, st_k, st_out}) if (st) { cudaError_t e2 = cudaStreamSynchronize(st); if (rc == FTN_OK && e2 != cudaSuccess) { e = e2; fail("batch sync"); } }
+    for (int i = 0; i < n_ev; ++i) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_k[i]); cudaEventDestroy(ev_out[i]); }
+    for (cudaStream_t st : {st_in, st_k, st_out}) if (st) cudaStreamDestroy(st);
     return rc;
 }
 FTN_API int ftn_intersect(const FtnScene* s, size_t n, const FtnRay* rays, FtnHit* hits) { return intersect_host(s, n, rays, hits, nullptr, false); }

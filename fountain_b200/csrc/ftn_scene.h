@@ -142,8 +142,8 @@ int radix_sort_pairs(uint32_t* d_keys, uint32_t* d_vals, size_t n, int bits, voi
 // Process-wide grow-only device arenas (one set per GPU): the wavefront path state, the film of
 // host-buffer renders, the temporaries of a BVH build.  Callers hold the arena's mutex while they use it.
 struct DeviceArena {
-    void* p[3] = {nullptr, nullptr, nullptr}; size_t bytes[3] = {0, 0, 0}; std::mutex m;
-    enum { PATHS = 0, FILM = 1, BUILD = 2 };
+    void* p[4] = {nullptr, nullptr, nullptr, nullptr}; size_t bytes[4] = {0, 0, 0, 0}; std::mutex m;
+    enum { PATHS = 0, FILM = 1, BUILD = 2, BATCH = 3 };
     int reserve(int which, size_t need, const char* what, void** out);
     void* h_pinned = nullptr; size_t h_pinned_bytes = 0;   // small pinned host block (queue-counter read-back)
     int pinned_counts(uint32_t** out, size_t bytes);

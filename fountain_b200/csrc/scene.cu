@@ -326,9 +326,9 @@ int release_cached_memory() {
     for (int d = 0; d < FTN_MAX_DEVICES; ++d) {
         DeviceArena& a = g_arena[d];
         std::lock_guard<std::mutex> lock(a.m);
-        if (!a.p[0] && !a.p[1] && !a.p[2] && !a.h_pinned) continue;
+        if (!a.p[0] && !a.p[1] && !a.p[2] && !a.p[3] && !a.h_pinned) continue;
         if (cudaSetDevice(d) != cudaSuccess) continue;
-        for (int i = 0; i < 3; ++i) { cudaFree(a.p[i]); a.p[i] = nullptr; a.bytes[i] = 0; }
+        for (int i = 0; i < 4; ++i) { cudaFree(a.p[i]); a.p[i] = nullptr; a.bytes[i] = 0; }
         if (a.h_pinned) { cudaFreeHost(a.h_pinned); a.h_pinned = nullptr; a.h_pinned_bytes = 0; }
     }
     return FTN_OK;
