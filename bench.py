@@ -277,6 +277,7 @@ def run_ours_render(args):
 
     # ---- e2e: host buffers in, host film out; scene upload + BVH build + render + read-back per step ----
     e2e_samples = []          # (seconds, rays) per e2e step; the median step is reported
+    pinned_film = None
     h2d = d2h = 0
     n_e2e = 0 if args.no_e2e else max(3, min(args.steps, 5))
     for i in range(n_e2e):
@@ -296,7 +297,13 @@ def run_ours_render(args):
             gpu.call("render_device", sc2.handle, C.byref(cam2.to_abi()), C.byref(film2.to_abi()), C.byref(smp_abi), C.byref(integ2.to_abi()),
                      C.c_void_p(d_film.data_ptr()), C.byref(s2), C.c_void_p(stream.cuda_stream))
             dist.reduce(d_film, dst=0, op=dist.ReduceOp.SUM)
-            host_film = d_film.cpu() if rank == 0 else None
+            if rank == 0:
+                if pinned_film is None:
+                    pinned_film = torch.empty(d_film.shape, dtype=d_film.dtype, pin_memory=True)
+                pinned_film.copy_(d_film)            # D2H into page-locked memory
+                host_film = pinned_film
+            else:
+                host_film = None
             r = s2.rays_closest + s2.rays_any
             d2h = (host_film.numel() * 4) if rank == 0 else 0
         torch.cuda.synchronize()
