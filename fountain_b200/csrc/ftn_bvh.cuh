@@ -38,7 +38,7 @@ namespace ftn {
 #ifndef FTN_LEAF_MAX
 #define FTN_LEAF_MAX 4
 #endif
-#define FTN_STACK_SIZE 96   /* binary depth <= 62 (30 code bits + index bits); BVH4 pushes <= 3 per level of <= 31 */
+#define FTN_STACK_SIZE 256  /* traversal stack (local memory, touched only as deep as the tree): radix trees are <= 62 deep, PLOC trees reach 175 at 50M triangles */
 #define FTN_NO_HIT_SLOT 0xFFFFFFFFu
 #define FTN_SPHERE_SLOT_FLAG 0x80000000u
 #define FTN_TRAVERSAL_DONE ((int)0x80000000)

@@ -43,21 +43,29 @@ FTN_HD float ploc_join_area(F4 alo, F4 ahi, F4 blo, F4 bhi) {
     return rn_add(rn_add(rn_mul(dx, dy), rn_mul(dy, dz)), rn_mul(dz, dx));
 }
 
-// nearest neighbour of cluster i among positions [i-R, i+R]: smallest joined area, ties to the
-// smaller position.  (With this tie rule the smallest position taking part in a globally
-// minimal pair and its smallest partner always choose each other, so every round merges.)
+// nearest neighbour of cluster i among positions [i-R, i+R]: smallest joined area; equal areas are ordered by a
+// SYMMETRIC key of the pair -- adjacent positions (2k, 2k+1) first, then distance, then the smaller position.
+// Any strict total order on pairs guarantees progress (the globally smallest pair is mutual); this one makes
+// runs of equal areas (regular tessellations) pair up (0,1), (2,3), ... in ONE round instead of growing a
+// chain one merge per round (184 rounds / depth 65 for the 1M-triangle sphere with a plain smaller-position rule).
+FTN_HD uint32_t ploc_pair_key(uint32_t i, uint32_t j) {
+    const uint32_t lo = i < j ? i : j, hi = i < j ? j : i;
+    const uint32_t even_adjacent = (hi == lo + 1u && (lo & 1u) == 0u) ? 0u : 1u;
+    return (even_adjacent << 31) | ((hi - lo) << 24) | (lo & 0x00FFFFFFu);   // distance <= 2R < 128
+}
 FTN_HD uint32_t ploc_nearest(const LbvhArrays& a, const F4* leaf_lo, const F4* leaf_hi, const uint32_t* cl, uint32_t c, uint32_t i) {
     F4 lo, hi;
     ploc_box(a, leaf_lo, leaf_hi, cl[i], &lo, &hi);
     const uint32_t j0 = i > (uint32_t)FTN_PLOC_RADIUS ? i - FTN_PLOC_RADIUS : 0u;
     const uint32_t j1 = (i + FTN_PLOC_RADIUS < c - 1u) ? i + FTN_PLOC_RADIUS : c - 1u;
-    float best = FTN_INF; uint32_t bj = PLOC_NONE;
+    float best = FTN_INF; uint32_t best_key = 0xFFFFFFFFu, bj = PLOC_NONE;
     for (uint32_t j = j0; j <= j1; ++j) {
         if (j == i) continue;
         F4 l2, h2;
         ploc_box(a, leaf_lo, leaf_hi, cl[j], &l2, &h2);
         const float ar = ploc_join_area(lo, hi, l2, h2);
-        if (ar < best || bj == PLOC_NONE) { best = ar; bj = j; }
+        const uint32_t key = ploc_pair_key(i, j);
+        if (bj == PLOC_NONE || ar < best || (ar == best && key < best_key)) { best = ar; best_key = key; bj = j; }
     }
     return bj;
 }

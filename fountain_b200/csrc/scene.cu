@@ -13,6 +13,7 @@
 #include "ftn_scene.h"
 #include "ftn_lbvh.cuh"
 #include "ftn_ploc.cuh"
+#include <cstdio>
 #include <cstdlib>
 #define FTN_REFILL_THRESHOLD_DEFAULT 16
 #define FTN_VOTE_BIAS_DEFAULT 14
@@ -668,6 +669,7 @@ int bvh_build(FtnScene* s) {
                     const uint32_t max_depth = h_small[1];
                     const char* depth_env = getenv("FTN_PLOC_MAX_DEPTH");   // test hook: force the fallback
                     const uint32_t depth_limit = depth_env ? (uint32_t)atoi(depth_env) : (uint32_t)FTN_STACK_SIZE - 4u;
+                    if (getenv("FTN_DEBUG_BUILD")) fprintf(stderr, "[ftn] PLOC: %u triangles, tree depth %u (limit %u)%s\n", n, max_depth, depth_limit, max_depth <= depth_limit ? "" : " -> radix-tree fallback");
                     if (max_depth <= depth_limit) {   // else: a degenerate chain; the radix tree below is depth-bounded
                         k_ploc_node_ranges<<<gi, 256, 0, st>>>(a, n); count_launch();
                         k_ploc_permute_leaves<<<gb256, 256, 0, st>>>(n, newpos, leaf_lo, leaf_hi, s->d_order, lo2, hi2, order2); count_launch();

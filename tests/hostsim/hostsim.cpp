@@ -9,6 +9,7 @@
 // glue) is covered by the `-m gpu` tests.  libfountain_gpu.so never links this file and has no
 // CPU execution path.
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -163,9 +164,10 @@ SIM_API int sim_bvh_build(SimScene* s) {
             if (use_ploc) {   // the kernels of scene.cu's ploc_build(), one element at a time
                 std::vector<uint32_t> cl0(n), cl1(n), nn(n), mg(n), va(n), ms(n), vs(n);
                 for (uint32_t i = 0; i < n; ++i) cl0[i] = LBVH_LEAF_FLAG | i;
-                uint32_t c = n, created = 0;
+                uint32_t c = n, created = 0, rounds = 0;
                 uint32_t *cin = cl0.data(), *cout = cl1.data();
                 while (c > 1) {
+                    ++rounds;
                     for (uint32_t i = 0; i < c; ++i) nn[i] = ploc_nearest(a, leaf_lo.data(), leaf_hi.data(), cin, c, i);
                     uint32_t m = 0, v = 0;
                     for (uint32_t i = 0; i < c; ++i) { ploc_flags(nn.data(), i, mg.data(), va.data()); }
@@ -175,8 +177,10 @@ SIM_API int sim_bvh_build(SimScene* s) {
                     created += m; c -= m; std::swap(cin, cout);
                 }
                 if (created != ni || cin[0] != 0u) return fail(FTN_ERR_CUDA, "PLOC did not end at root 0");
+                const uint32_t ploc_rounds = rounds;
                 std::vector<uint32_t> newpos(n); uint32_t max_depth = 0;
                 for (uint32_t l = 0; l < n; ++l) { uint32_t d; newpos[l] = ploc_dfs_position(a, n, LBVH_LEAF_FLAG | l, &d); max_depth = std::max(max_depth, d); }
+                if (getenv("FTN_DEBUG_BUILD")) fprintf(stderr, "[sim] PLOC: %u triangles, %u rounds, tree depth %u\n", n, ploc_rounds, max_depth);
                 const char* depth_env = getenv("FTN_PLOC_MAX_DEPTH");
                 const uint32_t depth_limit = depth_env ? (uint32_t)atoi(depth_env) : (uint32_t)FTN_STACK_SIZE - 4u;
                 if (max_depth <= depth_limit) {
