@@ -179,12 +179,14 @@ class MatteMaterial:
     """material/matte.rs; constant Kd, sigma = 0 (Lambert).  Default Kd 0.5 (constructors.rs:193)."""
     type = A.FTN_MATERIAL_MATTE
 
-    def __init__(self, kd=0.5):
+    def __init__(self, kd=0.5, sigma=0.0):
         self.kd = kd if isinstance(kd, (Checkerboard2DTexture, UVTexture)) else _spectrum(kd)
+        self.sigma = float(sigma)            # degrees; != 0 selects Oren-Nayar (matte.rs:42-49)
 
     def fill(self, m):
         m.type = self.type
         _fill_kd(m, self.kd)
+        m.sigma = self.sigma
 
 
 class MetalMaterial:

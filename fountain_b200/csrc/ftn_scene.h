@@ -54,8 +54,10 @@ struct MeshData {
     uint32_t flags;          // FTN_MESH_*
 };
 
+#define FTN_CLASS_OREN_NAYAR 4   /* matte.rs:45-49: its own class keeps the Lambert shade kernel free of the rough-diffuse code */
+#define FTN_N_CLASSES 5
 struct MaterialData {
-    int32_t type;            // FtnMaterialType
+    int32_t type;            // material CLASS = shade queue: FtnMaterialType, or FTN_CLASS_OREN_NAYAR for a matte with sigma != 0
     float kd[3], ks[3], eta[3], k[3];
     float alpha_x, alpha_y;  // after the roughness remap (microfacet.rs:40-45)
     int32_t kd_texture;      // FtnTextureType of Kd
@@ -122,7 +124,7 @@ struct FtnScene {
     float bounds[6] = {0, 0, 0, 0, 0, 0};
     double build_seconds = 0.0;
     unsigned long long* d_work = nullptr;   // dynamic work-fetch counter of the batch queries
-    bool material_present[4] = {false, false, false, false};   // which shade kernels a render launches
+    bool material_present[FTN_N_CLASSES] = {false, false, false, false, false};   // which shade kernels a render launches
     bool has_null_material = false;         // any primitive with a null BSDF (path.rs:76-80)
     ftn::SceneView view() const;
 };

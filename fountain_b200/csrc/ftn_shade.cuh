@@ -213,7 +213,8 @@ enum { BXDF_REFLECTION = 1, BXDF_TRANSMISSION = 2, BXDF_DIFFUSE = 4, BXDF_GLOSSY
 
 // One lobe of a Bsdf (bsdf.rs holds up to 8 `dyn BxDF`; the in-scope materials produce at most 2).
 // KIND is a compile-time property of (material class, lobe slot): 0 LambertianReflection,
-// 1 MicrofacetReflection<TrowbridgeReitz, F>, 2 SpecularReflection<FresnelNoOp> (mirror), -1 no such lobe.  Shading runs one kernel launch per
+// 1 MicrofacetReflection<TrowbridgeReitz, F>, 2 SpecularReflection<FresnelNoOp> (mirror), 3 OrenNayar
+// (a, b ride in ax, ay), -1 no such lobe.  Shading runs one kernel launch per
 // material class over its queue, so the class is a template argument and the matte kernel
 // contains no microfacet / Fresnel code at all (it used 167 registers when the lobe kind was a
 // run-time field).
@@ -228,11 +229,12 @@ template <> struct LobeKind<FTN_MATERIAL_METAL, 0> { static constexpr int value 
 template <> struct LobeKind<FTN_MATERIAL_PLASTIC, 0> { static constexpr int value = 0; };
 template <> struct LobeKind<FTN_MATERIAL_PLASTIC, 1> { static constexpr int value = 1; };
 template <> struct LobeKind<FTN_MATERIAL_MIRROR, 0> { static constexpr int value = 2; };
+template <> struct LobeKind<FTN_CLASS_OREN_NAYAR, 0> { static constexpr int value = 3; };
 // Fresnel of the microfacet lobe: 0 FresnelConductor{1, eta, k} (metal.rs:52-56), 1 FresnelDielectric{1.5, 1.0} (plastic.rs:34)
 template <int MAT> struct LobeFresnel { static constexpr int value = (MAT == FTN_MATERIAL_PLASTIC) ? 1 : 0; };
 
 template <int KIND> FTN_HD constexpr int lobe_type() {
-    return KIND == 0 ? (BXDF_REFLECTION | BXDF_DIFFUSE) : KIND == 1 ? (BXDF_REFLECTION | BXDF_GLOSSY) : (BXDF_REFLECTION | BXDF_SPECULAR);
+    return (KIND == 0 || KIND == 3) ? (BXDF_REFLECTION | BXDF_DIFFUSE) : KIND == 1 ? (BXDF_REFLECTION | BXDF_GLOSSY) : (BXDF_REFLECTION | BXDF_SPECULAR);
 }
 template <int KIND> FTN_HD constexpr bool lobe_matches(int flags) { return KIND >= 0 && (flags & lobe_type<KIND>()) == lobe_type<KIND>(); }
 
@@ -280,6 +282,18 @@ template <int FRESNEL> FTN_HD V3 lobe_fresnel(const Lobe& l, float cos_i) {
 template <int KIND, int FRESNEL> FTN_HD V3 lobe_f(const Lobe& l, V3 wo, V3 wi) {
     if (KIND == 0) return l.r * FTN_INV_PI;   // reflection/mod.rs:159-161
     if (KIND == 2) return v3s(0.0f);           // reflection/mod.rs:181-183
+    if (KIND == 3) {                           // OrenNayar::f, reflection/mod.rs:274-296
+        const float sin_i = sin_theta(wi), sin_o = sin_theta(wo);
+        float max_cos = 0.0f;
+        if (sin_i > 1.0e-4f && sin_o > 1.0e-4f) {
+            const float d_cos = cos_phi(wi) * cos_phi(wo) + sin_phi(wi) * sin_phi(wo);
+            max_cos = fmaxf(0.0f, d_cos);
+        }
+        float sin_alpha, tan_beta;
+        if (abs_cos_theta(wi) > abs_cos_theta(wo)) { sin_alpha = sin_o; tan_beta = sin_i / abs_cos_theta(wi); }
+        else { sin_alpha = sin_i; tan_beta = sin_o / abs_cos_theta(wo); }
+        return l.r * FTN_INV_PI * (l.ax + (l.ay * max_cos * sin_alpha * tan_beta));
+    }
     const float cos_o = abs_cos_theta(wo), cos_i = abs_cos_theta(wi);   // :318-336
     V3 wh = wi + wo;
     if (cos_i == 0.0f || cos_o == 0.0f || (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f)) return v3s(0.0f);
@@ -290,7 +304,7 @@ template <int KIND, int FRESNEL> FTN_HD V3 lobe_f(const Lobe& l, V3 wo, V3 wi) {
     return l.r * tr_d(l, wh) * G * F / (4.0f * cos_i * cos_o);
 }
 template <int KIND> FTN_HD float lobe_pdf(const Lobe& l, V3 wo, V3 wi) {
-    if (KIND == 0) return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * FTN_INV_PI : 0.0f;   // :140-146
+    if (KIND == 0 || KIND == 3) return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * FTN_INV_PI : 0.0f;   // DefaultSampleF :140-146
     if (KIND == 2) return 0.0f;                // :194-196
     if (!same_hemisphere(wo, wi)) return 0.0f;   // :354-360
     const V3 wh = normalize(wo + wi);
@@ -298,7 +312,7 @@ template <int KIND> FTN_HD float lobe_pdf(const Lobe& l, V3 wo, V3 wi) {
 }
 struct ScatterSample { V3 f, wi; float pdf; int type; };
 template <int KIND, int FRESNEL> FTN_HD bool lobe_sample_f(const Lobe& l, V3 wo, float u0, float u1, ScatterSample* s) {
-    if (KIND == 0) {   // :131-138
+    if (KIND == 0 || KIND == 3) {   // DefaultSampleF :131-138
         V3 wi = cosine_sample_hemisphere(u0, u1);
         if (wo.z < 0.0f) wi.z *= -1.0f;
         s->pdf = lobe_pdf<KIND>(l, wo, wi); s->f = lobe_f<KIND, FRESNEL>(l, wo, wi); s->wi = wi; s->type = lobe_type<KIND>();
@@ -416,6 +430,10 @@ template <int MAT> FTN_HD void material_bsdf(const MaterialData& m, float u, flo
         b->on0 = true;
         b->l0.r = v3s(1.0f); b->l0.ax = m.alpha_x; b->l0.ay = m.alpha_y;
         b->l0.eta = V3(m.eta[0], m.eta[1], m.eta[2]); b->l0.k = V3(m.k[0], m.k[1], m.k[2]);
+    } else if (MAT == FTN_CLASS_OREN_NAYAR) {   // matte.rs:45-49: OrenNayar::new(r, Deg(sigma)); (a, b) precomputed at scene creation
+        const V3 kd0 = material_kd(m, u, v);
+        const V3 r = V3(clampf(kd0.x, 0.0f, FTN_INF), clampf(kd0.y, 0.0f, FTN_INF), clampf(kd0.z, 0.0f, FTN_INF));
+        if (!is_black(r)) { b->on0 = true; b->l0.r = r; b->l0.ax = m.alpha_x; b->l0.ay = m.alpha_y; }
     } else if (MAT == FTN_MATERIAL_MIRROR) {   // mirror.rs:21-30; Kr is carried in MaterialData::kd
         const V3 r = V3(clampf(m.kd[0], 0.0f, FTN_INF), clampf(m.kd[1], 0.0f, FTN_INF), clampf(m.kd[2], 0.0f, FTN_INF));
         if (!is_black(r)) { b->on0 = true; b->l0.r = r; }

@@ -28,7 +28,8 @@ namespace ftn {
 int sm_count();
 unsigned trace_grid(size_t n, int blocks_per_sm);
 
-enum { Q_ACTIVE_OUT = 0, Q_MISS, Q_NULL, Q_MAT0, Q_MAT1, Q_MAT2, Q_MAT3, Q_SHADOW, Q_MIS, Q_COUNT };
+enum { Q_ACTIVE_OUT = 0, Q_MISS, Q_NULL, Q_MAT0, Q_MAT1, Q_MAT2, Q_MAT3, Q_MAT4, Q_SHADOW, Q_MIS, Q_COUNT };
+static_assert(Q_MAT4 - Q_MAT0 + 1 == FTN_N_CLASSES, "one shade queue per material class");
 enum { W_EXTEND = Q_COUNT, W_SHADOW, W_MIS, CTR_COUNT };
 
 struct PathArrays {
@@ -447,6 +448,7 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
             if (s->material_present[1]) { k_shade<Q_MAT1><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT1], q, counts, d_err); FTN_LAUNCHED(); }
             if (s->material_present[2]) { k_shade<Q_MAT2><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT2], q, counts, d_err); FTN_LAUNCHED(); }
             if (s->material_present[3]) { k_shade<Q_MAT3><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT3], q, counts, d_err); FTN_LAUNCHED(); }
+            if (s->material_present[4]) { k_shade<Q_MAT4><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT4], q, counts, d_err); FTN_LAUNCHED(); }
             // The shadow and MIS queues cannot be longer than this iteration's input queue, and their kernels
             // read the exact lengths on the device: launch them sized by that bound BEFORE waiting for the
             // counts, so that the host round trip (needed to size the next iteration and to stop) is hidden

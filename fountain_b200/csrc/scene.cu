@@ -448,12 +448,21 @@ int scene_create(const FtnSceneDesc* d, FtnScene** out) {
         float ur = fm.u_roughness, vr = fm.v_roughness;
         if (fm.type == FTN_MATERIAL_MIRROR) for (int c = 0; c < 3; ++c) md.kd[c] = fm.kr[c];   // Kr travels in the kd slot
         md.kd_texture = (fm.type == FTN_MATERIAL_MATTE || fm.type == FTN_MATERIAL_PLASTIC) ? fm.kd_texture : 0;
+        if (fm.type == FTN_MATERIAL_MATTE) {   // matte.rs:42-49: sigma clamped to [0, 90] degrees; != 0 -> OrenNayar::new (reflection/mod.rs:259-267)
+            const float sigma = std::fmin(std::fmax(fm.sigma, 0.0f), 90.0f);
+            if (sigma != 0.0f) {
+                const float sr = sigma * (float)(3.14159265358979323846 / 180.0), s2 = sr * sr;
+                md.type = FTN_CLASS_OREN_NAYAR;
+                md.alpha_x = 1.0f - (s2 / (2.0f * (s2 + 0.33f)));   // a
+                md.alpha_y = 0.45f * s2 / (s2 + 0.09f);              // b
+            }
+        }
         for (int c = 0; c < 3; ++c) { md.tex1[c] = fm.tex1[c]; md.tex2[c] = fm.tex2[c]; }
         for (int c = 0; c < 2; ++c) { md.uv_scale[c] = fm.uv_scale[c]; md.uv_delta[c] = fm.uv_delta[c]; }
         if (fm.type == FTN_MATERIAL_PLASTIC) vr = ur;
         if (fm.remap_roughness) { ur = roughness_to_alpha_host(ur); vr = roughness_to_alpha_host(vr); }
-        md.alpha_x = ur; md.alpha_y = vr;
-        s->material_present[fm.type] = true;
+        if (md.type != FTN_CLASS_OREN_NAYAR) { md.alpha_x = ur; md.alpha_y = vr; }   // Oren-Nayar keeps (a, b) there
+        s->material_present[md.type] = true;
     }
     for (uint32_t m = 0; m < d->n_meshes; ++m) if (d->meshes[m].material_id < 0 && d->meshes[m].n_tris) s->has_null_material = true;
     for (uint32_t i = 0; i < d->n_spheres; ++i) if (d->spheres[i].material_id < 0) s->has_null_material = true;

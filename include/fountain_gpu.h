@@ -88,7 +88,7 @@ typedef struct FtnMeshDesc {
 } FtnMeshDesc;
 
 typedef enum FtnMaterialType {
-    FTN_MATERIAL_MATTE = 0,   /* material/matte.rs:36-52 (sigma must be 0: Lambert only) */
+    FTN_MATERIAL_MATTE = 0,   /* material/matte.rs:36-52: Lambert for sigma == 0, Oren-Nayar otherwise */
     FTN_MATERIAL_METAL = 1,   /* material/metal.rs:38-65 */
     FTN_MATERIAL_PLASTIC = 2, /* material/plastic.rs:24-48 */
     FTN_MATERIAL_MIRROR = 3   /* material/mirror.rs:21-30: SpecularReflection with FresnelNoOp */
@@ -118,6 +118,7 @@ typedef struct FtnMaterial {
     float tex1[3], tex2[3];  /* checkerboard: the two constant sub-textures (constructors.rs:276-287) */
     float uv_scale[2];       /* UVMapping uscale, vscale (constructors.rs:251-252, default 1) */
     float uv_delta[2];       /* UVMapping udelta, vdelta (default 0) */
+    float sigma;             /* matte: Oren-Nayar roughness in DEGREES, clamped to [0, 90] (matte.rs:42); 0 = Lambert */
 } FtnMaterial;
 
 /* shapes/sphere.rs:16-27 (+ the DiffuseAreaLight it may carry, light/diffuse.rs:24-41). */

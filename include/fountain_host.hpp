@@ -468,12 +468,14 @@ struct SpectrumTexture {
         m.uv_delta[0] = mapping.offset_u; m.uv_delta[1] = mapping.offset_v;
     }
 };
-struct MatteMaterial : Material {        // material/matte.rs; Kd default 0.5 (constructors.rs:193)
+struct MatteMaterial : Material {        // material/matte.rs; Kd default 0.5, sigma default 0 (constructors.rs:192-196)
     SpectrumTexture kd;
-    explicit MatteMaterial(SpectrumTexture kd_ = SpectrumTexture(0.5f)) : kd(kd_) {}
+    float sigma;                         // degrees; != 0 selects Oren-Nayar (matte.rs:42-49)
+    explicit MatteMaterial(SpectrumTexture kd_ = SpectrumTexture(0.5f), float sigma_ = 0.0f) : kd(kd_), sigma(sigma_) {}
     void fill(FtnMaterial& m) const override {
         m.type = FTN_MATERIAL_MATTE;
         kd.fill_kd(m);
+        m.sigma = sigma;
     }
 };
 struct MetalMaterial : Material {        // material/metal.rs; roughness 0.01, remap true (constructors.rs:213-230)

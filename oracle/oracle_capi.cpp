@@ -54,7 +54,7 @@ ORC_API int orc_scene_create(const FtnSceneDesc* d, OrcScene** out) {
         mm.kd = Spectrum(m.kd[0], m.kd[1], m.kd[2]); mm.ks = Spectrum(m.ks[0], m.ks[1], m.ks[2]);
         mm.eta = Spectrum(m.eta[0], m.eta[1], m.eta[2]); mm.k = Spectrum(m.k[0], m.k[1], m.k[2]);
         mm.u_rough = m.u_roughness; mm.v_rough = m.v_roughness; mm.remap = m.remap_roughness != 0;
-        mm.kr = Spectrum(m.kr[0], m.kr[1], m.kr[2]);
+        mm.kr = Spectrum(m.kr[0], m.kr[1], m.kr[2]); mm.sigma = m.sigma;
         mm.kd_texture = m.kd_texture; mm.tex1 = Spectrum(m.tex1[0], m.tex1[1], m.tex1[2]); mm.tex2 = Spectrum(m.tex2[0], m.tex2[1], m.tex2[2]);
         for (int c = 0; c < 2; ++c) { mm.uv_scale[c] = m.uv_scale[c]; mm.uv_delta[c] = m.uv_delta[c]; }
         s.materials.push_back(mm);
@@ -357,7 +357,7 @@ ORC_API void orc_kat_bsdf(const FtnMaterial* m, const float wo[3], const float w
     mm.kd = Spectrum(m->kd[0], m->kd[1], m->kd[2]); mm.ks = Spectrum(m->ks[0], m->ks[1], m->ks[2]);
     mm.eta = Spectrum(m->eta[0], m->eta[1], m->eta[2]); mm.k = Spectrum(m->k[0], m->k[1], m->k[2]);
     mm.u_rough = m->u_roughness; mm.v_rough = m->v_roughness; mm.remap = m->remap_roughness != 0;
-    mm.kr = Spectrum(m->kr[0], m->kr[1], m->kr[2]); mm.kd_texture = 0;
+    mm.kr = Spectrum(m->kr[0], m->kr[1], m->kr[2]); mm.kd_texture = 0; mm.sigma = m->sigma;
     SurfaceInteraction si{};
     si.hit.n = Vec3(0, 0, 1); si.shading_n = Vec3(0, 0, 1); si.shading_dpdu = Vec3(1, 0, 0); si.dpdu = Vec3(1, 0, 0);
     Bsdf b; compute_scattering_functions(mm, si, &b);

@@ -319,7 +319,7 @@ struct Material {
     Spectrum kd, ks, eta, k, kr;
     int kd_texture;    // FtnTextureType
     Spectrum tex1, tex2; Float uv_scale[2], uv_delta[2];
-    Float u_rough, v_rough;
+    Float u_rough, v_rough, sigma;
     bool remap;
 };
 

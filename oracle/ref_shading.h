@@ -173,14 +173,15 @@ struct ScatterSample { Spectrum f; Vec3 wi; Float pdf; int sampled_type; };
 // One lobe: Lambert (reflection/mod.rs:116-162) or Torrance-Sparrow with Trowbridge-Reitz
 // (reflection/mod.rs:301-361, microfacet.rs:119-186) and a conductor or dielectric Fresnel.
 struct BxDF {
-    int kind;            // 0 lambert, 1 microfacet, 2 specular reflection with FresnelNoOp (reflection/mod.rs:165-197)
+    int kind;            // 0 lambert, 1 microfacet, 2 specular reflection with FresnelNoOp (reflection/mod.rs:165-197), 3 Oren-Nayar (:252-296)
+    Float on_a, on_b;    // Oren-Nayar coefficients
     Spectrum r;
     Float alpha_x, alpha_y;
     int fresnel;         // 0 conductor, 1 dielectric
     Spectrum eta_i, eta_t, k;
     Float d_eta_i, d_eta_t;
 
-    int get_type() const { return kind == 0 ? (BXDF_REFLECTION | BXDF_DIFFUSE) : kind == 1 ? (BXDF_REFLECTION | BXDF_GLOSSY) : (BXDF_REFLECTION | BXDF_SPECULAR); }
+    int get_type() const { return (kind == 0 || kind == 3) ? (BXDF_REFLECTION | BXDF_DIFFUSE) : kind == 1 ? (BXDF_REFLECTION | BXDF_GLOSSY) : (BXDF_REFLECTION | BXDF_SPECULAR); }
     bool matches(int flags) const { return (flags & get_type()) == get_type(); }
 
     Spectrum fresnel_eval(Float cos_i) const {
@@ -225,6 +226,19 @@ struct BxDF {
     Spectrum f(Vec3 wo, Vec3 wi) const {
         if (kind == 0) return r * FRAC_1_PI;   // reflection/mod.rs:159-161
         if (kind == 2) return Spectrum(0.0f);   // :181-183
+        if (kind == 3) {   // OrenNayar::f, reflection/mod.rs:274-296
+            Float sin_theta_i = sin_theta(wi), sin_theta_o = sin_theta(wo);
+            Float max_cos = 0.0f;
+            if (sin_theta_i > 1.0e-4f && sin_theta_o > 1.0e-4f) {
+                Float sin_phi_i = sin_phi(wi), cos_phi_i = cos_phi(wi), sin_phi_o = sin_phi(wo), cos_phi_o = cos_phi(wo);
+                Float d_cos = cos_phi_i * cos_phi_o + sin_phi_i * sin_phi_o;
+                max_cos = fmax_(0.0f, d_cos);
+            }
+            Float sin_alpha, tan_beta;
+            if (abs_cos_theta(wi) > abs_cos_theta(wo)) { sin_alpha = sin_theta_o; tan_beta = sin_theta_i / abs_cos_theta(wi); }
+            else { sin_alpha = sin_theta_i; tan_beta = sin_theta_o / abs_cos_theta(wo); }
+            return r * FRAC_1_PI * (on_a + (on_b * max_cos * sin_alpha * tan_beta));
+        }
         // reflection/mod.rs:318-336
         Float cos_o = abs_cos_theta(wo), cos_i = abs_cos_theta(wi);
         Vec3 wh = wi + wo;
@@ -234,14 +248,14 @@ struct BxDF {
         return r * tr_d(wh) * tr_g(wo, wi) * F / (4.0f * cos_i * cos_o);
     }
     Float pdf(Vec3 wo, Vec3 wi) const {
-        if (kind == 0) return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * FRAC_1_PI : 0.0f;   // :140-146
+        if (kind == 0 || kind == 3) return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * FRAC_1_PI : 0.0f;   // DefaultSampleF :140-146
         if (kind == 2) return 0.0f;   // :194-196
         if (!same_hemisphere(wo, wi)) return 0.0f;   // :354-360
         Vec3 wh = normalize(wo + wi);
         return tr_pdf(wo, wh) / (4.0f * dot(wo, wh));
     }
     bool sample_f(Vec3 wo, Float u0, Float u1, ScatterSample* s) const {
-        if (kind == 0) {   // :131-138
+        if (kind == 0 || kind == 3) {   // DefaultSampleF :131-138
             Vec3 wi = cosine_sample_hemisphere(u0, u1);
             if (wo.z < 0.0f) wi.z *= -1.0f;
             s->pdf = pdf(wo, wi); s->f = f(wo, wi); s->wi = wi; s->sampled_type = get_type();
@@ -344,7 +358,16 @@ inline void compute_scattering_functions(const Material& m, const SurfaceInterac
     bsdf->init(si);
     if (m.type == 0) {   // matte.rs:36-52 (sigma == 0 only)
         Spectrum r = evaluate_kd(m, si).clamp_positive();
-        if (!r.is_black()) { BxDF b{}; b.kind = 0; b.r = r; bsdf->add(b); }
+        Float sigma = clampf(m.sigma, 0.0f, 90.0f);
+        if (!r.is_black()) {
+            BxDF b{}; b.r = r;
+            if (sigma == 0.0f) b.kind = 0;
+            else {   // OrenNayar::new(r, Deg(sigma)), reflection/mod.rs:259-267; cgmath Deg -> Rad: deg * (PI / 180)
+                Float s = sigma * (Float)(3.14159265358979323846 / 180.0), s2 = s * s;   // the factor is an f64 constant cast to f32 in cgmath
+                b.kind = 3; b.on_a = 1.0f - (s2 / (2.0f * (s2 + 0.33f))); b.on_b = 0.45f * s2 / (s2 + 0.09f);
+            }
+            bsdf->add(b);
+        }
     } else if (m.type == 1) {   // metal.rs:38-65
         Float ur = m.u_rough, vr = m.v_rough;
         if (m.remap) { ur = roughness_to_alpha(ur); vr = roughness_to_alpha(vr); }

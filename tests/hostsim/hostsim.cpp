@@ -68,11 +68,21 @@ SIM_API int sim_scene_create(const FtnSceneDesc* d, SimScene** out) {
         float ur = fm.u_roughness, vr = fm.v_roughness;
         if (fm.type == FTN_MATERIAL_MIRROR) for (int c = 0; c < 3; ++c) md.kd[c] = fm.kr[c];   // Kr travels in the kd slot
         md.kd_texture = (fm.type == FTN_MATERIAL_MATTE || fm.type == FTN_MATERIAL_PLASTIC) ? fm.kd_texture : 0;
+        if (fm.type == FTN_MATERIAL_MATTE) {   // matte.rs:42-49: sigma clamped to [0, 90] degrees; != 0 -> OrenNayar::new (reflection/mod.rs:259-267)
+            const float sigma = std::fmin(std::fmax(fm.sigma, 0.0f), 90.0f);
+            if (sigma != 0.0f) {
+                const float sr = sigma * (float)(3.14159265358979323846 / 180.0), s2 = sr * sr;
+                md.type = FTN_CLASS_OREN_NAYAR;
+                md.alpha_x = 1.0f - (s2 / (2.0f * (s2 + 0.33f)));   // a
+                md.alpha_y = 0.45f * s2 / (s2 + 0.09f);              // b
+            }
+        }
         for (int c = 0; c < 3; ++c) { md.tex1[c] = fm.tex1[c]; md.tex2[c] = fm.tex2[c]; }
         for (int c = 0; c < 2; ++c) { md.uv_scale[c] = fm.uv_scale[c]; md.uv_delta[c] = fm.uv_delta[c]; }
         if (fm.type == FTN_MATERIAL_PLASTIC) vr = ur;
         if (fm.remap_roughness) { ur = roughness_to_alpha_host(ur); vr = roughness_to_alpha_host(vr); }
-        md.alpha_x = ur; md.alpha_y = vr; s->mats.push_back(md);
+        if (md.type != FTN_CLASS_OREN_NAYAR) { md.alpha_x = ur; md.alpha_y = vr; }   // Oren-Nayar keeps (a, b) there
+        s->mats.push_back(md);
     }
     s->env_tex.reserve(d->n_lights); s->env_f.reserve(5 * d->n_lights);
     for (uint32_t l = 0; l < d->n_lights; ++l) {
@@ -347,6 +357,7 @@ SIM_API int sim_render(const SimScene* s, const FtnCamera* cam, const FtnFilm* f
                     case FTN_MATERIAL_METAL: shade_surface<FTN_MATERIAL_METAL>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err); break;
                     case FTN_MATERIAL_PLASTIC: shade_surface<FTN_MATERIAL_PLASTIC>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err); break;
                     case FTN_MATERIAL_MIRROR: shade_surface<FTN_MATERIAL_MIRROR>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err); break;
+                    case FTN_CLASS_OREN_NAYAR: shade_surface<FTN_CLASS_OREN_NAYAR>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err); break;
                     default: shade_surface<-1>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err); break;
                 }
                 Lp = o.L;
@@ -413,7 +424,8 @@ SIM_API void sim_kat_bsdf(const FtnMaterial* m, const float wo[3], const float w
     const V3 o(wo[0], wo[1], wo[2]), i(wi[0], wi[1], wi[2]);
     V3 f; float pdf; ScatterSample sm; bool ok;
 #define SIM_BSDF(M) { material_bsdf<M>(s->mats[0], 0.0f, 0.0f, &b); f = bsdf_f<M>(b, o, i, BXDF_ALL); pdf = bsdf_pdf<M>(b, o, i, BXDF_ALL); ok = bsdf_sample_f<M>(b, o, u[0], u[1], BXDF_ALL, &sm); }
-    if (m->type == FTN_MATERIAL_MATTE) SIM_BSDF(FTN_MATERIAL_MATTE)
+    if (s->mats[0].type == FTN_CLASS_OREN_NAYAR) SIM_BSDF(FTN_CLASS_OREN_NAYAR)
+    else if (m->type == FTN_MATERIAL_MATTE) SIM_BSDF(FTN_MATERIAL_MATTE)
     else if (m->type == FTN_MATERIAL_METAL) SIM_BSDF(FTN_MATERIAL_METAL)
     else if (m->type == FTN_MATERIAL_MIRROR) SIM_BSDF(FTN_MATERIAL_MIRROR)
     else SIM_BSDF(FTN_MATERIAL_PLASTIC)

@@ -227,3 +227,19 @@ def test_release_cached_memory_and_render_again(gpu_backend):
     gpu_backend.call("release_cached_memory")
     b, bpx, _ = parity.render(gpu_backend, scenes.furnace_scene, api.PathIntegrator(4, 1.0), 8, seed=2)
     assert np.array_equal(apx, bpx)
+
+
+# ---- Oren-Nayar (matte with sigma != 0) ----------------------------------------------------------------------
+def test_oren_nayar_image_matches_oracle(gpu_backend, orc_backend):
+    build = lambda backend, **k: scenes.rounded_cube_scene(backend=backend, material=api.MatteMaterial((0.6, 0.5, 0.4), sigma=35.0), **k)
+    a, apx, ast = parity.render(gpu_backend, build, api.PathIntegrator(5, 1.0), 8, seed=3, resolution=(96, 96))
+    b, bpx, bst = parity.render(orc_backend, build, api.PathIntegrator(5, 1.0), 8, seed=3, resolution=(96, 96))
+    mean_rel, frac_off = parity.image_diff(a, b)
+    assert mean_rel < 2e-3 and frac_off < 0.02, (mean_rel, frac_off)
+    assert np.array_equal(apx[..., 3], bpx[..., 3])
+
+
+def test_oren_nayar_closed_form(gpu_backend):
+    from tests.test_oracle_render import _oren_nayar_probe, _oren_nayar_expected
+    for case in ((20.0, 0.0, 0.0, 0.0), (20.0, 50.0, 30.0, 0.0), (35.0, 30.0, 55.0, 0.0), (20.0, 50.0, 30.0, 180.0)):
+        assert np.allclose(_oren_nayar_probe(gpu_backend, *case), _oren_nayar_expected(*case)[None, :], rtol=3e-3), case

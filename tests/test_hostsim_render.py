@@ -151,3 +151,15 @@ def test_textured_floor_matches_oracle(sim_backend, orc_backend, texture, materi
     assert mean_rel < 2e-3 and frac_off < 0.02, (mean_rel, frac_off)
     assert np.array_equal(apx[..., 3], bpx[..., 3])
     assert len(np.unique(np.round(b.reshape(-1, 3), 3), axis=0)) > 4       # the texture is visible
+
+
+# ---- Oren-Nayar (its own material class on the device) ------------------------------------------------------
+def test_oren_nayar_image_matches_oracle(sim_backend, orc_backend):
+    build = lambda backend, **k: scenes.rounded_cube_scene(backend=backend, material=api.MatteMaterial((0.6, 0.5, 0.4), sigma=35.0), **k)
+    a, apx, ast = parity.render(sim_backend, build, api.PathIntegrator(5, 1.0), 4, seed=3, resolution=(40, 40))
+    b, bpx, bst = parity.render(orc_backend, build, api.PathIntegrator(5, 1.0), 4, seed=3, resolution=(40, 40))
+    mean_rel, frac_off = parity.image_diff(a, b)
+    assert mean_rel < 2e-3 and frac_off < 0.02, (mean_rel, frac_off)
+    lam, _, _ = parity.render(orc_backend, lambda backend, **k: scenes.rounded_cube_scene(backend=backend, material=api.MatteMaterial((0.6, 0.5, 0.4)), **k),
+                              api.PathIntegrator(5, 1.0), 4, seed=3, resolution=(40, 40))
+    assert parity.image_diff(b, lam)[0] > 1e-2            # and it is not the Lambert image

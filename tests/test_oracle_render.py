@@ -197,3 +197,43 @@ def test_uv_texture_closed_form(orc_backend):
     rgb = _probe(orc_backend, (-1.3, -2.6), "uv")          # s = -.55 -> .45, t = -.45 -> .55
     assert np.allclose(rgb.mean(axis=0), np.array([0.45, 0.55, 0.0]) / np.pi * 3.0, rtol=5e-3, atol=1e-6)
     assert np.all(rgb[:, 2] == 0.0)
+
+
+# ---- Oren-Nayar (matte with sigma != 0: matte.rs:42-49, reflection/mod.rs:252-296) -------------------------
+# No reference test: pinned by closed form under a distant light: L_o = r/pi (a + b max(0, cos dphi) sin(alpha) tan(beta)) L cos(theta_i).
+def _oren_nayar_probe(backend, sigma, theta_i, theta_o, dphi):
+    from fountain_b200.transform import Transform
+    v = np.array([[-6, -6, 0], [6, -6, 0], [6, 6, 0], [-6, 6, 0]], np.float32)
+    mesh = api.TriangleMesh(Transform.identity(), np.array([0, 1, 2, 0, 2, 3], np.uint32), v)
+    ti, to = np.radians(theta_i), np.radians(theta_o)
+    light = api.DistantLight.from_params(L=2.0, from_=(np.sin(ti), 0.0, np.cos(ti)), to=(0.0, 0.0, 0.0))
+    scene = api.Scene([api.GeometricPrimitive(mesh, api.MatteMaterial((0.7, 0.5, 0.3), sigma=sigma))], [light], backend=backend)
+    eye = 30.0 * np.array([np.sin(to) * np.cos(np.radians(dphi)), np.sin(to) * np.sin(np.radians(dphi)), np.cos(to)])
+    camera = api.PerspectiveCamera(Transform.look_at(tuple(eye), (0, 0, 0), (0, 1, 0) if theta_o == 0 else (0, 0, 1)).inverse(), (5, 5), fov=0.3)
+    film = api.Film((5, 5), backend=backend)
+    api.SamplerIntegrator(camera, api.DirectLightingIntegrator(1)).render_parallel(scene, film, api.RandomSampler.new_with_seed(2, 0))
+    return film.into_spectrum_buffer()[0]
+
+
+def _oren_nayar_expected(sigma, theta_i, theta_o, dphi):
+    s = np.radians(min(max(sigma, 0.0), 90.0)); s2 = s * s
+    a, b = 1.0 - s2 / (2.0 * (s2 + 0.33)), 0.45 * s2 / (s2 + 0.09)
+    ti, to = np.radians(theta_i), np.radians(theta_o)
+    max_cos = max(0.0, np.cos(np.radians(dphi))) if (np.sin(ti) > 1e-4 and np.sin(to) > 1e-4) else 0.0
+    if abs(np.cos(ti)) > abs(np.cos(to)):
+        sin_alpha, tan_beta = np.sin(to), np.sin(ti) / abs(np.cos(ti))
+    else:
+        sin_alpha, tan_beta = np.sin(ti), np.sin(to) / abs(np.cos(to))
+    return np.array([0.7, 0.5, 0.3]) / np.pi * (a + b * max_cos * sin_alpha * tan_beta) * 2.0 * np.cos(ti)
+
+
+@pytest.mark.parametrize("sigma,theta_i,theta_o,dphi", [(20.0, 0.0, 0.0, 0.0), (20.0, 50.0, 30.0, 0.0), (35.0, 30.0, 55.0, 0.0),
+                                                       (20.0, 50.0, 30.0, 180.0), (60.0, 40.0, 40.0, 60.0), (120.0, 25.0, 45.0, 0.0)])
+def test_oren_nayar_closed_form(orc_backend, sigma, theta_i, theta_o, dphi):
+    rgb = _oren_nayar_probe(orc_backend, sigma, theta_i, theta_o, dphi)
+    assert np.allclose(rgb, _oren_nayar_expected(sigma, theta_i, theta_o, dphi)[None, :], rtol=3e-3)
+
+
+def test_oren_nayar_sigma_zero_is_lambert(orc_backend):
+    a = _oren_nayar_probe(orc_backend, 0.0, 40.0, 20.0, 30.0)
+    assert np.allclose(a, (np.array([0.7, 0.5, 0.3]) / np.pi * 2.0 * np.cos(np.radians(40.0)))[None, :], rtol=1e-5)
