@@ -692,3 +692,55 @@ SIM_API int sim_bvh_rebuild_sah(SimScene* s, int leaf_max, float c_trav, float c
     for (uint32_t i = 0; i < n; ++i) lbvh_gather_tri(s->pos.data(), s->idx.data(), s->order.data(), i, s->meshes.data(), (uint32_t)s->meshes.size(), s->tris.data());
     return FTN_OK;
 }
+
+// ---- design experiment: SAH tree rotations (Kensler 2008) on the emitted BVH2x64 records --------------------
+// One bottom-up pass (children carry larger indices than their parents in both builders): at node X = (A, B)
+// with A = (A0, A1) interior, swapping B with A0 or A1 (or symmetrically a child of B with A) is applied when it
+// shrinks the surface area of the rebuilt child.  Returns the number of rotations applied.
+namespace {
+struct Box6 { float lx, hx, ly, hy, lz, hz; };
+inline float area6(const Box6& b) { const float dx = b.hx - b.lx, dy = b.hy - b.ly, dz = b.hz - b.lz; return 2.0f * (dx * dy + dy * dz + dz * dx); }
+inline Box6 join6(const Box6& a, const Box6& b) { return {fminf(a.lx, b.lx), fmaxf(a.hx, b.hx), fminf(a.ly, b.ly), fmaxf(a.hy, b.hy), fminf(a.lz, b.lz), fmaxf(a.hz, b.hz)}; }
+inline Box6 child_box(const F4* nd, int k) {
+    return k == 0 ? Box6{nd[0].x, nd[0].y, nd[0].z, nd[0].w, nd[2].x, nd[2].y} : Box6{nd[1].x, nd[1].y, nd[1].z, nd[1].w, nd[2].z, nd[2].w};
+}
+inline void set_child(F4* nd, int k, const Box6& b, int ref) {
+    if (k == 0) { nd[0].x = b.lx; nd[0].y = b.hx; nd[0].z = b.ly; nd[0].w = b.hy; nd[2].x = b.lz; nd[2].y = b.hz; nd[3].x = u2f((uint32_t)ref); }
+    else { nd[1].x = b.lx; nd[1].y = b.hx; nd[1].z = b.ly; nd[1].w = b.hy; nd[2].z = b.lz; nd[2].w = b.hz; nd[3].y = u2f((uint32_t)ref); }
+}
+inline int child_ref(const F4* nd, int k) { return (int)f2u(k == 0 ? nd[3].x : nd[3].y); }
+}  // namespace
+SIM_API int sim_bvh_rotate(SimScene* s) {
+#if FTN_BVH_WIDTH == 2
+    int applied = 0;
+    for (int x = (int)s->n_nodes - 1; x >= 0; --x) {
+        F4* X = s->nodes.data() + 4 * (size_t)x;
+        if (child_ref(X, 1) == FTN_TRAVERSAL_DONE) continue;
+        float best = 0.0f; int best_side = -1, best_g = -1;
+        for (int side = 0; side < 2; ++side) {          // side: the child of X that is rebuilt (A); the other one (B) moves down
+            const int a = child_ref(X, side);
+            if (a < 0) continue;
+            const F4* A = s->nodes.data() + 4 * (size_t)a;
+            const Box6 bB = child_box(X, 1 - side), bA = child_box(X, side);
+            for (int g = 0; g < 2; ++g) {               // g: the grandchild that moves up
+                const Box6 keep = child_box(A, 1 - g);
+                const float delta = area6(join6(bB, keep)) - area6(bA);
+                if (delta < best) { best = delta; best_side = side; best_g = g; }
+            }
+        }
+        if (best_side < 0) continue;
+        const int a = child_ref(X, best_side);
+        F4* A = s->nodes.data() + 4 * (size_t)a;
+        const Box6 bB = child_box(X, 1 - best_side); const int rB = child_ref(X, 1 - best_side);
+        const Box6 bG = child_box(A, best_g); const int rG = child_ref(A, best_g);
+        const Box6 keep = child_box(A, 1 - best_g);
+        set_child(A, best_g, bB, rB);                   // A = (B, kept grandchild)
+        set_child(X, best_side, join6(bB, keep), a);    // X's box of A
+        set_child(X, 1 - best_side, bG, rG);            // the grandchild takes B's place
+        ++applied;
+    }
+    return applied;
+#else
+    (void)s; return 0;
+#endif
+}
