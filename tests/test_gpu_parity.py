@@ -193,3 +193,20 @@ def test_ploc_depth_fallback_to_radix_tree(gpu_backend, orc_backend, rounded_cub
     parity.check_morton(a, b)
     parity.check_ray_batch(a, b, parity.random_ray_batch(100_000, 15), "fallback")
     parity.check_watertight(a, n=100_000)
+
+
+def test_host_batch_pipeline_many_chunks(gpu_backend, rounded_cube_path):
+    """ftn_intersect / ftn_intersect_test stream the batch through in 512 Ki-ray chunks on three streams: a
+    batch of several chunks (not a multiple of the chunk size, more chunks than pipeline slots) must give what
+    its pieces give."""
+    mesh = api.TriangleMesh.from_ply(rounded_cube_path)
+    scene = api.Scene([api.GeometricPrimitive(mesh)], [], backend=gpu_backend)
+    n = 5 * (1 << 19) + 12345
+    rays = parity.random_ray_batch(n, 77)
+    whole = scene.intersect(rays)
+    cut = (1 << 19) + 777
+    parts = np.concatenate([scene.intersect(rays[:cut]), scene.intersect(rays[cut:])])
+    assert np.array_equal(whole.view(np.uint32), parts.view(np.uint32))
+    any_whole = scene.intersect_test(rays)
+    assert np.array_equal(any_whole, np.concatenate([scene.intersect_test(rays[:cut]), scene.intersect_test(rays[cut:])]))
+    assert np.array_equal(any_whole, whole["prim"] != A.FTN_NO_HIT)
