@@ -174,11 +174,13 @@ k_shade_miss(SceneView sc, PassParams pp, PathArrays pa, const uint32_t* __restr
 }
 
 // ---- material-sorted shading: one launch per material class (QUEUE = Q_NULL, Q_MAT0..2) -------------------------
-#ifdef FTN_SHADE_MIN_BLOCKS             /* A/B: cap registers for more resident warps */
-#define FTN_SHADE_LAUNCH_BOUNDS __launch_bounds__(128, FTN_SHADE_MIN_BLOCKS)
-#else
-#define FTN_SHADE_LAUNCH_BOUNDS __launch_bounds__(128)
+// 4 blocks of 128 threads per SM = a cap of 128 registers: the conductor / plastic shaders would take 162-166
+// (3 blocks, 18 % occupancy); capped they spill a little and run 4.5 % faster on C4 (3550 -> 3710 Mrays/s).
+// Caps of 5 / 6 blocks were slower (profiles/r01_ab_vote_ldg256.txt).
+#ifndef FTN_SHADE_MIN_BLOCKS
+#define FTN_SHADE_MIN_BLOCKS 4
 #endif
+#define FTN_SHADE_LAUNCH_BOUNDS __launch_bounds__(128, FTN_SHADE_MIN_BLOCKS)
 template <int QUEUE>
 __global__ void FTN_SHADE_LAUNCH_BOUNDS
 k_shade(SceneView sc, PassParams pp, PathArrays pa, const uint32_t* __restrict__ queue, Queues qs, uint32_t* __restrict__ counts, uint32_t* __restrict__ err) {
