@@ -19,7 +19,9 @@ FTN_ERR_OUT_OF_MEMORY = -6
 
 FTN_MESH_FLIP_NORMALS = 1
 FTN_MATERIAL_MATTE, FTN_MATERIAL_METAL, FTN_MATERIAL_PLASTIC, FTN_MATERIAL_MIRROR = 0, 1, 2, 3
-FTN_TEXTURE_CONSTANT, FTN_TEXTURE_CHECKERBOARD, FTN_TEXTURE_UV = 0, 1, 2
+FTN_TEXTURE_CONSTANT, FTN_TEXTURE_CHECKERBOARD, FTN_TEXTURE_UV, FTN_TEXTURE_IMAGE = 0, 1, 2, 3
+FTN_WRAP_REPEAT, FTN_WRAP_BLACK, FTN_WRAP_CLAMP = 0, 1, 2
+FTN_MAX_MIP_LEVELS = 16
 FTN_LIGHT_INFINITE = 0
 FTN_LIGHT_POINT = 1
 FTN_LIGHT_DISTANT = 2
@@ -47,7 +49,8 @@ class FtnMeshDesc(C.Structure):
 class FtnMaterial(C.Structure):
     _fields_ = [("type", i32), ("kd", f32 * 3), ("ks", f32 * 3), ("eta", f32 * 3), ("k", f32 * 3),
                 ("u_roughness", f32), ("v_roughness", f32), ("remap_roughness", i32), ("kr", f32 * 3),
-                ("kd_texture", i32), ("tex1", f32 * 3), ("tex2", f32 * 3), ("uv_scale", f32 * 2), ("uv_delta", f32 * 2), ("sigma", f32)]
+                ("kd_texture", i32), ("tex1", f32 * 3), ("tex2", f32 * 3), ("uv_scale", f32 * 2), ("uv_delta", f32 * 2), ("sigma", f32),
+                ("image", C.POINTER(f32)), ("image_width", i32), ("image_height", i32), ("image_levels", i32), ("image_wrap", i32)]
 
 
 class FtnSphere(C.Structure):

@@ -163,12 +163,82 @@ class UVTexture:
         self.mapping = mapping or UVMapping()
 
 
+class MIPMap:
+    """mipmap.rs:19-143 `MIPMap<Spectrum>`: the image pyramid an ImageTexture filters.  Level l is
+    max(1, w >> l) x max(1, h >> l); there are 1 + floor(log2(max(w, h))) levels (:107-121).  The reference
+    halves each level with the `resize` crate's Triangle filter (0.4.3, a third-party dependency that is not
+    in the repository); `downsample` restates that filter for a factor of two -- weights (1, 3, 3, 1) / 8 per
+    axis, renormalised at the borders -- and is host-side setup, outside the device path.  A caller that owns
+    a pyramid (the Rust host) passes its levels through `levels=` unchanged."""
+
+    WRAP = {"repeat": A.FTN_WRAP_REPEAT, "black": A.FTN_WRAP_BLACK, "clamp": A.FTN_WRAP_CLAMP}
+
+    def __init__(self, image=None, wrap="repeat", levels=None):
+        self.wrap = self.WRAP[wrap] if isinstance(wrap, str) else int(wrap)
+        if levels is None:
+            img = np.ascontiguousarray(image, dtype=np.float32)
+            if img.ndim != 3 or img.shape[2] != 3:
+                raise ValueError("MIPMap image must be (height, width, 3)")
+            h, w = img.shape[:2]
+            levels = [img]
+            for _ in range(1, 1 + int(np.floor(np.log2(max(w, h))))):
+                levels.append(self.downsample(levels[-1]))
+        self.levels = [np.ascontiguousarray(l, dtype=np.float32) for l in levels]
+        self.height, self.width = self.levels[0].shape[:2]
+        for l, lv in enumerate(self.levels):
+            if lv.shape != (max(1, self.height >> l), max(1, self.width >> l), 3):
+                raise ValueError("MIPMap level %d has shape %s" % (l, lv.shape))
+        self.packed = np.concatenate([lv.reshape(-1) for lv in self.levels]).astype(np.float32)
+
+    @staticmethod
+    def _halve(a, axis):
+        a = np.moveaxis(a, axis, 0).astype(np.float64)
+        n = a.shape[0]
+        m = max(1, n // 2)
+        out = np.zeros((m,) + a.shape[1:])
+        wsum = np.zeros(m)
+        for k, wt in zip((-1, 0, 1, 2), (1.0, 3.0, 3.0, 1.0)):
+            src = 2 * np.arange(m) + k
+            ok = (src >= 0) & (src < n)
+            out[ok] += wt * a[src[ok]]
+            wsum[ok] += wt
+        out /= wsum.reshape((m,) + (1,) * (a.ndim - 1))
+        return np.moveaxis(out, 0, axis)
+
+    @classmethod
+    def downsample(cls, img):
+        out = img
+        if img.shape[1] > 1:
+            out = cls._halve(out, 1)
+        if img.shape[0] > 1:
+            out = cls._halve(out, 0)
+        return out.astype(np.float32)
+
+
+class ImageTexture:
+    """texture/image.rs:8-34 `ImageTexture<Spectrum, UVMapping>` (make_imagemap_spect, constructors.rs:295-319;
+    file loading, scale and gamma are the host's, before the pyramid is built)."""
+    type = A.FTN_TEXTURE_IMAGE
+
+    def __init__(self, mipmap, mapping=None):
+        self.mipmap = mipmap
+        self.mapping = mapping or UVMapping()
+        self.tex1 = self.tex2 = _spectrum(0.0)
+
+
+_TEXTURES = (Checkerboard2DTexture, UVTexture, ImageTexture)
+
+
 def _fill_kd(m, kd):
     """Kd is a constant spectrum or one of the textures above."""
-    if isinstance(kd, (Checkerboard2DTexture, UVTexture)):
+    if isinstance(kd, _TEXTURES):
         m.kd_texture = kd.type
         m.tex1[:] = kd.tex1.tolist(); m.tex2[:] = kd.tex2.tolist()
         m.uv_scale[:] = list(kd.mapping.scale); m.uv_delta[:] = list(kd.mapping.offset)
+        if isinstance(kd, ImageTexture):   # the numpy array stays alive with the material object
+            mp = kd.mipmap
+            m.image = mp.packed.ctypes.data_as(C.POINTER(C.c_float))
+            m.image_width, m.image_height, m.image_levels, m.image_wrap = mp.width, mp.height, len(mp.levels), mp.wrap
     else:
         m.kd_texture = A.FTN_TEXTURE_CONSTANT
         m.kd[:] = _spectrum(kd).tolist()
@@ -180,7 +250,7 @@ class MatteMaterial:
     type = A.FTN_MATERIAL_MATTE
 
     def __init__(self, kd=0.5, sigma=0.0):
-        self.kd = kd if isinstance(kd, (Checkerboard2DTexture, UVTexture)) else _spectrum(kd)
+        self.kd = kd if isinstance(kd, _TEXTURES) else _spectrum(kd)
         self.sigma = float(sigma)            # degrees; != 0 selects Oren-Nayar (matte.rs:42-49)
 
     def fill(self, m):
@@ -215,7 +285,7 @@ class PlasticMaterial:
     type = A.FTN_MATERIAL_PLASTIC
 
     def __init__(self, kd=0.25, ks=0.25, roughness=0.1, remap_roughness=True):
-        self.kd = kd if isinstance(kd, (Checkerboard2DTexture, UVTexture)) else _spectrum(kd)
+        self.kd = kd if isinstance(kd, _TEXTURES) else _spectrum(kd)
         self.ks = _spectrum(ks)
         self.roughness, self.remap = float(roughness), bool(remap_roughness)
 

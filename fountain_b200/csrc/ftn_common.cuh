@@ -18,9 +18,11 @@
 #if defined(__CUDACC__)
 #define FTN_HD __host__ __device__ __forceinline__
 #define FTN_D __device__ __forceinline__
+#define FTN_HD_COLD static __host__ __device__ __noinline__   // rare, register-hungry side paths kept out of the callers' budget
 #else
 #define FTN_HD inline
 #define FTN_D inline
+#define FTN_HD_COLD inline
 #include <string.h>
 #endif
 

@@ -135,7 +135,7 @@ struct SphereHit {
     float t;
     V3 p, p_err, n;    // world space (SurfaceHit after SurfaceInteraction::transform)
     V3 wo;             // normalised, world
-    V3 dpdu;           // world
+    V3 dpdu, dpdv;     // world (dpdv only feeds texture differentials)
     V3 ns;             // shading normal (== transformed geometric normal)
     float u, v;        // phi / phi_max, (theta - theta_min) / (theta_max - theta_min), sphere.rs:146-148
 };
@@ -185,6 +185,7 @@ FTN_HD bool sphere_intersect(const SphereData& s, const RayF& wray, SphereHit* h
     h->ns = h->n;
     h->wo = x_normalize(transform_vector(s.o2w, x_neg(ray.d)));
     h->dpdu = transform_vector(s.o2w, dpdu);
+    h->dpdv = transform_vector(s.o2w, dpdv);
     h->u = rn_div(phi, s.phi_max); h->v = rn_div(rn_sub(theta, s.theta_min), dth);   // sphere.rs:146-148
     h->t = th.v;
     return true;

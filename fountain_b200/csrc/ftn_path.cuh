@@ -197,10 +197,31 @@ struct ShadeOut {
     DirectOut direct;
 };
 
+// Texture differentials of the hit (interaction.rs:117).  The path integrator hands the CAMERA ray's differential on
+// to every spawned ray unchanged (path.rs:73,79), so each hit of a path intersects the camera's two offset rays with
+// its own tangent plane; they are re-derived here from the path's camera sample instead of being carried.
+FTN_HD_COLD TexDiffs path_tex_differentials(const SceneView& sc, const PassParams& pp, uint32_t path, uint32_t slot, const RayF& ray, V3 p, V3 n) {
+    int x, y;
+    const uint64_t key = path_sample_key(pp, path, &x, &y);
+    const float fx = rn_add((float)x, sampler_uniform(key, 0)), fy = rn_add((float)y, sampler_uniform(key, 1));
+    const float lx = sampler_uniform(key, 2), ly = sampler_uniform(key, 3), tu = sampler_uniform(key, 4);
+    const RayF main_ray = camera_ray(pp.cam, fx, fy, lx, ly, tu);
+    const RayDiff df = camera_differential(pp.cam, main_ray, fx, fy, lx, ly, 1.0f / sqrtf((float)pp.spp));
+    V3 dpdu, dpdv;
+    if (slot & FTN_SPHERE_SLOT_FLAG) {
+        SphereHit sh;
+        if (!sphere_intersect(sc.spheres[slot & ~FTN_SPHERE_SLOT_FLAG], ray, &sh)) { TexDiffs z; z.dudx = z.dvdx = z.dudy = z.dvdy = 0.0f; return z; }
+        dpdu = sh.dpdu; dpdv = sh.dpdv;
+    } else {
+        triangle_dpduv(sc, slot, &dpdu, &dpdv);
+    }
+    return tex_differentials(p, n, dpdu, dpdv, df);
+}
+
 // `ray` is the ray that produced `slot`; state/beta/L are the path's values on entry.
 // MAT = the material class of the queue this path sits in (FtnMaterialType), or -1 for the
 // null-BSDF queue.
-template <int MAT>
+template <int MAT, bool IMG = true>
 FTN_HD void shade_surface(const SceneView& sc, const PassParams& pp, uint32_t path, const RayF& ray, uint32_t slot,
                           uint32_t state, V3 beta, V3 L, ShadeOut* out, uint32_t* err) {
     out->L = L; out->beta = beta; out->state = state; out->alive = false;
@@ -224,7 +245,11 @@ FTN_HD void shade_surface(const SceneView& sc, const PassParams& pp, uint32_t pa
     constexpr int M = MAT < 0 ? 0 : MAT;
     Bsdf bsdf;
     bsdf_init(&bsdf, s.ns, s.n, s.sdpdu);
-    material_bsdf<M>(sc.materials[s.material], s.u, s.v, &bsdf);
+    TexDiffs td; td.dudx = td.dvdx = td.dudy = td.dvdy = 0.0f;
+    if (IMG && (M == FTN_MATERIAL_MATTE || M == FTN_MATERIAL_PLASTIC || M == FTN_CLASS_OREN_NAYAR) && sc.materials[s.material].kd_texture == FTN_TEXTURE_IMAGE
+        && !(direct_only && bounces > 0))   // stated deviation: no differentials behind a mirror under direct lighting
+        td = path_tex_differentials(sc, pp, path, slot, ray, s.p, s.n);
+    material_bsdf<M>(sc.materials[s.material], s.u, s.v, td, &bsdf);
     const uint64_t key = path_sample_key(pp, path, nullptr, nullptr);
     // under the direct-lighting integrator `bounces` is the recursion depth of specular_reflect
     const uint32_t dim0 = DIM_CAMERA + (uint32_t)DIM_PER_BOUNCE * (uint32_t)bounces;

@@ -62,7 +62,29 @@ struct MaterialData {
     float alpha_x, alpha_y;  // after the roughness remap (microfacet.rs:40-45)
     int32_t kd_texture;      // FtnTextureType of Kd
     float tex1[3], tex2[3], uv_scale[2], uv_delta[2];
+    // FTN_TEXTURE_IMAGE: MIPMap::pyramid (mipmap.rs:19-23) as RGBA texels (A unused), levels concatenated from 0;
+    // level l is max(1, w >> l) x max(1, h >> l)
+    const F4* image;
+    int32_t img_w, img_h, img_levels, img_wrap;
 };
+
+// FtnMaterial's pyramid (RGB f32, include/fountain_gpu.h) -> RGBA texels; false when the description breaks the
+// level rule of mipmap.rs:107-121.  Host-side, shared by scene.cu and the host harness of the tests.
+template <class Vec>
+inline bool pack_image_pyramid(const FtnMaterial& fm, Vec* out) {
+    if (!fm.image || fm.image_width < 1 || fm.image_height < 1 || fm.image_wrap < FTN_WRAP_REPEAT || fm.image_wrap > FTN_WRAP_CLAMP) return false;
+    int expect = 1;
+    for (int m = fm.image_width > fm.image_height ? fm.image_width : fm.image_height; m > 1; m >>= 1) ++expect;
+    if (fm.image_levels != expect || expect > FTN_MAX_MIP_LEVELS) return false;
+    size_t n = 0;
+    for (int l = 0; l < expect; ++l) {
+        const int lw = (fm.image_width >> l) > 1 ? (fm.image_width >> l) : 1, lh = (fm.image_height >> l) > 1 ? (fm.image_height >> l) : 1;
+        n += (size_t)lw * lh;
+    }
+    out->resize(n);
+    for (size_t k = 0; k < n; ++k) { F4 t; t.x = fm.image[3 * k]; t.y = fm.image[3 * k + 1]; t.z = fm.image[3 * k + 2]; t.w = 0.0f; (*out)[k] = t; }
+    return true;
+}
 
 // light/infinite.rs: level-0 texels + the Distribution2D tables (sampling.rs:137-180)
 struct EnvLightData {
@@ -125,6 +147,7 @@ struct FtnScene {
     double build_seconds = 0.0;
     unsigned long long* d_work = nullptr;   // dynamic work-fetch counter of the batch queries
     bool material_present[FTN_N_CLASSES] = {false, false, false, false, false};   // which shade kernels a render launches
+    bool has_image_texture = false;         // any Kd image texture: selects the shade kernels that carry the mip lookup
     bool has_null_material = false;         // any primitive with a null BSDF (path.rs:76-80)
     ftn::SceneView view() const;
 };

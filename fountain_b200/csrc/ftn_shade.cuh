@@ -412,18 +412,61 @@ template <int MAT> FTN_HD bool bsdf_sample_f(const Bsdf& b, V3 wo_w, float u0, f
     return true;
 }
 
+// ---- MIPMap lookups of an image texture (mipmap.rs:245-311) -----------------------------------------------------
+// SurfaceInteraction::tex_diffs (interaction.rs:193-215); all zero when there is no differential
+struct TexDiffs { float dudx, dvdx, dudy, dvdy; };
+
+FTN_HD int max_i(int a, int b) { return a > b ? a : b; }
+FTN_HD int min_i(int a, int b) { return a < b ? a : b; }
+struct MipLevel { const F4* texels; int w, h; };
+FTN_HD MipLevel mip_level(const MaterialData& m, int level) {
+    size_t off = 0;
+    for (int l = 0; l < level; ++l) off += (size_t)max_i(1, m.img_w >> l) * (size_t)max_i(1, m.img_h >> l);
+    MipLevel lv; lv.texels = m.image + off; lv.w = max_i(1, m.img_w >> level); lv.h = max_i(1, m.img_h >> level);
+    return lv;
+}
+// get_texel_from_level, mipmap.rs:297-311
+FTN_HD V3 mip_texel(const MipLevel& lv, int wrap, int s, int t) {
+    if (wrap == FTN_WRAP_REPEAT) { s %= lv.w; if (s < 0) s += lv.w; t %= lv.h; if (t < 0) t += lv.h; }   // rem_euclid
+    else if (wrap == FTN_WRAP_CLAMP) { s = min_i(max_i(s, 0), lv.w - 1); t = min_i(max_i(t, 0), lv.h - 1); }
+    else if (s < 0 || s >= lv.w || t < 0 || t >= lv.h) return v3s(0.0f);
+    const F4 v = ld4(lv.texels + (size_t)t * lv.w + s);
+    return V3(v.x, v.y, v.z);
+}
+// triangle, mipmap.rs:265-279: the four texels around the continuous coordinate
+FTN_HD V3 mip_triangle(const MaterialData& m, int level, float st0, float st1) {
+    const MipLevel lv = mip_level(m, min_i(max_i(level, 0), m.img_levels - 1));
+    const float s = st0 * (float)lv.w - 0.5f, t = st1 * (float)lv.h - 0.5f;
+    const float fs = floorf(s), ft = floorf(t);
+    const int s0 = (int)fs, t0 = (int)ft;
+    const float ds = s - fs, dt = t - ft;
+    return mip_texel(lv, m.img_wrap, s0, t0) * ((1.0f - ds) * (1.0f - dt)) + mip_texel(lv, m.img_wrap, s0, t0 + 1) * ((1.0f - ds) * dt)
+         + mip_texel(lv, m.img_wrap, s0 + 1, t0) * (ds * (1.0f - dt)) + mip_texel(lv, m.img_wrap, s0 + 1, t0 + 1) * (ds * dt);
+}
+// lookup_trilinear + lookup_trilinear_width, mipmap.rs:245-262 (`dst0.y` without abs(), as there)
+FTN_HD_COLD V3 mip_lookup_trilinear(const MaterialData& m, float st0, float st1, float dsdx, float dtdx, float dsdy, float dtdy) {
+    const float width = 2.0f * fmaxf(fmaxf(fabsf(dsdx), dtdx), fmaxf(fabsf(dsdy), fabsf(dtdy)));
+    const float level = (float)m.img_levels - 1.0f + log2f(fmaxf(width, 1.0e-8f));
+    if (level < 0.0f) return mip_triangle(m, 0, st0, st1);
+    if (level >= (float)(m.img_levels - 1)) return mip_texel(mip_level(m, m.img_levels - 1), m.img_wrap, 0, 0);
+    const float lf = floorf(level), delta = level - lf;
+    return mip_triangle(m, (int)lf, st0, st1) * (1.0f - delta) + mip_triangle(m, (int)lf + 1, st0, st1) * delta;
+}
+
 // Material::compute_scattering_functions: matte.rs:36-52, metal.rs:38-65, plastic.rs:24-48, mirror.rs:21-30
-// Kd through its texture: constant, checkerboard (AAMethod::None, checkerboard.rs:50-64) or uv (uv.rs:18-23),
-// st = scale * uv + delta (mapping.rs:40-52); explicitly rounded so that floor() sees the oracle's values
-FTN_HD V3 material_kd(const MaterialData& m, float u, float v) {
+// Kd through its texture: constant, checkerboard (AAMethod::None, checkerboard.rs:50-64), uv (uv.rs:18-23) or image
+// (image.rs:30-33); st = scale * uv + delta (mapping.rs:40-52), explicitly rounded so that floor() sees the oracle's values
+FTN_HD V3 material_kd(const MaterialData& m, float u, float v, const TexDiffs& td) {
     if (m.kd_texture == 0) return V3(m.kd[0], m.kd[1], m.kd[2]);
     const float s = rn_add(rn_mul(m.uv_scale[0], u), m.uv_delta[0]), t = rn_add(rn_mul(m.uv_scale[1], v), m.uv_delta[1]);
     if (m.kd_texture == 1) return (((int)floorf(s) + (int)floorf(t)) % 2 == 0) ? V3(m.tex1[0], m.tex1[1], m.tex1[2]) : V3(m.tex2[0], m.tex2[1], m.tex2[2]);
+    if (m.kd_texture == FTN_TEXTURE_IMAGE)   // dst_dx = (su dudx, sv dvdx), dst_dy = (su dudy, sv dvdy), mapping.rs:43-44
+        return mip_lookup_trilinear(m, s, t, m.uv_scale[0] * td.dudx, m.uv_scale[1] * td.dvdx, m.uv_scale[0] * td.dudy, m.uv_scale[1] * td.dvdy);
     return V3(rn_sub(s, floorf(s)), rn_sub(t, floorf(t)), 0.0f);
 }
-template <int MAT> FTN_HD void material_bsdf(const MaterialData& m, float u, float v, Bsdf* b) {
+template <int MAT> FTN_HD void material_bsdf(const MaterialData& m, float u, float v, const TexDiffs& td, Bsdf* b) {
     if (MAT == FTN_MATERIAL_MATTE) {
-        const V3 kd0 = material_kd(m, u, v);
+        const V3 kd0 = material_kd(m, u, v, td);
         const V3 r = V3(clampf(kd0.x, 0.0f, FTN_INF), clampf(kd0.y, 0.0f, FTN_INF), clampf(kd0.z, 0.0f, FTN_INF));
         if (!is_black(r)) { b->on0 = true; b->l0.r = r; }
     } else if (MAT == FTN_MATERIAL_METAL) {
@@ -431,14 +474,14 @@ template <int MAT> FTN_HD void material_bsdf(const MaterialData& m, float u, flo
         b->l0.r = v3s(1.0f); b->l0.ax = m.alpha_x; b->l0.ay = m.alpha_y;
         b->l0.eta = V3(m.eta[0], m.eta[1], m.eta[2]); b->l0.k = V3(m.k[0], m.k[1], m.k[2]);
     } else if (MAT == FTN_CLASS_OREN_NAYAR) {   // matte.rs:45-49: OrenNayar::new(r, Deg(sigma)); (a, b) precomputed at scene creation
-        const V3 kd0 = material_kd(m, u, v);
+        const V3 kd0 = material_kd(m, u, v, td);
         const V3 r = V3(clampf(kd0.x, 0.0f, FTN_INF), clampf(kd0.y, 0.0f, FTN_INF), clampf(kd0.z, 0.0f, FTN_INF));
         if (!is_black(r)) { b->on0 = true; b->l0.r = r; b->l0.ax = m.alpha_x; b->l0.ay = m.alpha_y; }
     } else if (MAT == FTN_MATERIAL_MIRROR) {   // mirror.rs:21-30; Kr is carried in MaterialData::kd
         const V3 r = V3(clampf(m.kd[0], 0.0f, FTN_INF), clampf(m.kd[1], 0.0f, FTN_INF), clampf(m.kd[2], 0.0f, FTN_INF));
         if (!is_black(r)) { b->on0 = true; b->l0.r = r; }
     } else {
-        const V3 kd = material_kd(m, u, v), ks = V3(m.ks[0], m.ks[1], m.ks[2]);
+        const V3 kd = material_kd(m, u, v, td), ks = V3(m.ks[0], m.ks[1], m.ks[2]);
         if (!is_black(kd)) { b->on0 = true; b->l0.r = kd; }
         if (!is_black(ks)) { b->on1 = true; b->l1.r = ks; b->l1.ax = m.alpha_x; b->l1.ay = m.alpha_x; b->l1.eta = v3s(0.0f); b->l1.k = v3s(0.0f); }
     }
@@ -575,6 +618,88 @@ FTN_HD RayF camera_ray(const FtnCamera& cam, float fx, float fy, float lx, float
     }
     V3 oe, de;
     return ray_transform_err(c2w, ray, &oe, &de);
+}
+
+// The two offset rays of generate_ray_differential (camera/mod.rs:145-205), transformed like points / vectors
+// (transform.rs:324-338) and pulled towards the main ray by `scale` (geometry/mod.rs:125-132; the integrator passes
+// 1 / sqrt(spp), integrator/mod.rs:249-251).  With a lens BOTH offsets use dx_camera (:178 repeats :172), as there.
+struct RayDiff { V3 rx_o, rx_d, ry_o, ry_d; };
+FTN_HD RayDiff camera_differential(const FtnCamera& cam, const RayF& main_ray, float fx, float fy, float lx, float ly, float scale) {
+    M4 r2c, c2w;
+    for (int i = 0; i < 16; ++i) { r2c.m[i] = cam.raster_to_camera[i]; c2w.m[i] = cam.camera_to_world[i]; }
+    const V3 pc = transform_point(r2c, V3(fx, fy, 0.0f)), o0 = transform_point(r2c, V3(0.0f, 0.0f, 0.0f));
+    const V3 dxc = transform_point(r2c, V3(1.0f, 0.0f, 0.0f)) - o0, dyc = transform_point(r2c, V3(0.0f, 1.0f, 0.0f)) - o0;
+    RayDiff df;
+    if (cam.lens_radius > 0.0f) {
+        float dx = 0.0f, dy = 0.0f;
+        const float ox = 2.0f * lx - 1.0f, oy = 2.0f * ly - 1.0f;   // concentric_sample_disk
+        if (!(ox == 0.0f && oy == 0.0f)) {
+            float theta, r;
+            if (fabsf(ox) > fabsf(oy)) { theta = FTN_PI_4 * (oy / ox); r = ox; }
+            else { theta = FTN_PI_2 - FTN_PI_4 * (ox / oy); r = oy; }
+            dx = r * cosf(theta); dy = r * sinf(theta);
+        }
+        const V3 pl = V3(cam.lens_radius * dx, cam.lens_radius * dy, 0.0f);
+        const V3 ddx = normalize(pc + dxc);
+        const V3 pfx = ddx * (cam.focal_distance / ddx.z);
+        df.rx_o = pl; df.rx_d = normalize(pfx - pl);
+        df.ry_o = pl; df.ry_d = df.rx_d;
+    } else {
+        df.rx_o = v3s(0.0f); df.ry_o = v3s(0.0f);
+        df.rx_d = normalize(pc + dxc); df.ry_d = normalize(pc + dyc);
+    }
+    df.rx_o = transform_point(c2w, df.rx_o); df.ry_o = transform_point(c2w, df.ry_o);
+    df.rx_d = transform_vector(c2w, df.rx_d); df.ry_d = transform_vector(c2w, df.ry_d);
+    df.rx_o = main_ray.o + (df.rx_o - main_ray.o) * scale; df.ry_o = main_ray.o + (df.ry_o - main_ray.o) * scale;
+    df.rx_d = main_ray.d + (df.rx_d - main_ray.d) * scale; df.ry_d = main_ray.d + (df.ry_d - main_ray.d) * scale;
+    return df;
+}
+
+// math.rs:56-72 solve_linear_system_2x2, A = from_cols((a00, a01), (a10, a11))
+FTN_HD bool solve_2x2(float a00, float a01, float a10, float a11, float b0, float b1, float* x0, float* x1) {
+    const float det = a00 * a11 - a10 * a01;
+    if (fabsf(det) < 1.0e-10f) return false;
+    *x0 = (a11 * b0 - a10 * b1) / det;
+    *x1 = (a00 * b1 - a01 * b0) / det;
+    return !(*x0 != *x0 || *x1 != *x1);
+}
+FTN_HD float v3_at(V3 v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+
+// SurfaceInteraction::compute_tex_differentials, interaction.rs:124-176 (None -> zeros, :117)
+FTN_HD TexDiffs tex_differentials(V3 p, V3 n, V3 dpdu, V3 dpdv, const RayDiff& df) {
+    TexDiffs td; td.dudx = td.dvdx = td.dudy = td.dvdy = 0.0f;
+    const float d = dot(n, p);
+    const float tx = -(dot(n, df.rx_o) - d) / dot(n, df.rx_d), ty = -(dot(n, df.ry_o) - d) / dot(n, df.ry_d);
+    const V3 dpdx = (df.rx_o + df.rx_d * tx) - p, dpdy = (df.ry_o + df.ry_d * ty) - p;
+    int d0, d1;
+    if (fabsf(n.x) > fabsf(n.y) && fabsf(n.x) > fabsf(n.z)) { d0 = 1; d1 = 2; }
+    else if (fabsf(n.y) > fabsf(n.z)) { d0 = 0; d1 = 2; }
+    else { d0 = 0; d1 = 1; }
+    float dudx, dvdx, dudy, dvdy;
+    if (!solve_2x2(v3_at(dpdu, d0), v3_at(dpdu, d1), v3_at(dpdv, d0), v3_at(dpdv, d1), v3_at(dpdx, d0), v3_at(dpdx, d1), &dudx, &dvdx)) return td;
+    if (!solve_2x2(v3_at(dpdu, d0), v3_at(dpdu, d1), v3_at(dpdv, d0), v3_at(dpdv, d1), v3_at(dpdy, d0), v3_at(dpdy, d1), &dudy, &dvdy)) return td;
+    td.dudx = dudx; td.dvdx = dvdx; td.dudy = dudy; td.dvdy = dvdy;
+    return td;
+}
+
+// DiffGeom::dpdu / dpdv of a triangle (triangle.rs:258-295), for the texture differentials only
+FTN_HD void triangle_dpduv(const SceneView& sc, uint32_t slot, V3* dpdu, V3* dpdv) {
+    const F4 a = ld4(sc.bvh.tris + 3 * (size_t)slot), b = ld4(sc.bvh.tris + 3 * (size_t)slot + 1), c = ld4(sc.bvh.tris + 3 * (size_t)slot + 2);
+    const V3 p0 = V3(a.x, a.y, a.z), p1 = V3(b.x, b.y, b.z), p2 = V3(c.x, c.y, c.z);
+    const uint32_t prim = f2u(a.w);
+    const uint32_t v0 = sc.idx[3 * (size_t)prim], v1 = sc.idx[3 * (size_t)prim + 1], v2 = sc.idx[3 * (size_t)prim + 2];
+    float uv[3][2] = {{0.0f, 0.0f}, {1.0f, 0.0f}, {1.0f, 1.0f}};
+    if (sc.uv) {
+        uv[0][0] = sc.uv[2 * v0]; uv[0][1] = sc.uv[2 * v0 + 1]; uv[1][0] = sc.uv[2 * v1]; uv[1][1] = sc.uv[2 * v1 + 1];
+        uv[2][0] = sc.uv[2 * v2]; uv[2][1] = sc.uv[2 * v2 + 1];
+    }
+    const float duv02x = uv[0][0] - uv[2][0], duv02y = uv[0][1] - uv[2][1], duv12x = uv[1][0] - uv[2][0], duv12y = uv[1][1] - uv[2][1];
+    const V3 dp02 = p0 - p2, dp12 = p1 - p2;
+    const float determinant = rn_sub(rn_mul(duv02x, duv12y), rn_mul(duv02y, duv12x));
+    if (fabsf(determinant) < 1.0e-8f) { coordinate_system(x_normalize(x_cross(x_sub(p2, p0), x_sub(p1, p0))), dpdu, dpdv); return; }
+    const float inv = 1.0f / determinant;
+    *dpdu = (dp02 * duv12y - dp12 * duv02y) * inv;
+    *dpdv = (dp12 * duv02x - dp02 * duv12x) * inv;
 }
 
 }  // namespace ftn

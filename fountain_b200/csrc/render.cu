@@ -181,7 +181,9 @@ k_shade_miss(SceneView sc, PassParams pp, PathArrays pa, const uint32_t* __restr
 #define FTN_SHADE_MIN_BLOCKS 4
 #endif
 #define FTN_SHADE_LAUNCH_BOUNDS __launch_bounds__(128, FTN_SHADE_MIN_BLOCKS)
-template <int QUEUE>
+// IMG: the scene holds an image texture -- only then is the mip lookup (and its call frame) compiled into the
+// matte / plastic / Oren-Nayar shaders, so scenes without one run the kernels they always ran
+template <int QUEUE, bool IMG = false>
 __global__ void FTN_SHADE_LAUNCH_BOUNDS
 k_shade(SceneView sc, PassParams pp, PathArrays pa, const uint32_t* __restrict__ queue, Queues qs, uint32_t* __restrict__ counts, uint32_t* __restrict__ err) {
     const uint32_t n = counts[QUEUE];
@@ -193,7 +195,7 @@ k_shade(SceneView sc, PassParams pp, PathArrays pa, const uint32_t* __restrict__
             path = queue[k];
             const RayF ray = load_ray(pa, path);
             ShadeOut o;
-            shade_surface<QUEUE == Q_NULL ? -1 : QUEUE - Q_MAT0>(sc, pp, path, ray, pa.hit[path], pa.state[path], ld3(pa.beta, path), ld3(pa.L, path), &o, err);
+            shade_surface<QUEUE == Q_NULL ? -1 : QUEUE - Q_MAT0, IMG>(sc, pp, path, ray, pa.hit[path], pa.state[path], ld3(pa.beta, path), ld3(pa.L, path), &o, err);
             st3(pa.L, path, o.L);
             if (o.direct.has_shadow) { st3(pa.sh_o, path, o.direct.sh_o); st3(pa.sh_d, path, o.direct.sh_d); st3(pa.sh_L, path, o.direct.sh_L); t_shadow = Q_SHADOW; }
             if (o.direct.has_mis) {
@@ -446,11 +448,23 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
             k_shade_miss<<<shade_grid, 256, 0, st>>>(sc, pp, pa, q.q[Q_MISS], counts);
             FTN_LAUNCHED();
             if (s->has_null_material) { k_shade<Q_NULL><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_NULL], q, counts, d_err); FTN_LAUNCHED(); }
-            if (s->material_present[0]) { k_shade<Q_MAT0><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT0], q, counts, d_err); FTN_LAUNCHED(); }
+            if (s->material_present[0]) {
+                if (s->has_image_texture) k_shade<Q_MAT0, true><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT0], q, counts, d_err);
+                else k_shade<Q_MAT0><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT0], q, counts, d_err);
+                FTN_LAUNCHED();
+            }
             if (s->material_present[1]) { k_shade<Q_MAT1><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT1], q, counts, d_err); FTN_LAUNCHED(); }
-            if (s->material_present[2]) { k_shade<Q_MAT2><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT2], q, counts, d_err); FTN_LAUNCHED(); }
+            if (s->material_present[2]) {
+                if (s->has_image_texture) k_shade<Q_MAT2, true><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT2], q, counts, d_err);
+                else k_shade<Q_MAT2><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT2], q, counts, d_err);
+                FTN_LAUNCHED();
+            }
             if (s->material_present[3]) { k_shade<Q_MAT3><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT3], q, counts, d_err); FTN_LAUNCHED(); }
-            if (s->material_present[4]) { k_shade<Q_MAT4><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT4], q, counts, d_err); FTN_LAUNCHED(); }
+            if (s->material_present[4]) {
+                if (s->has_image_texture) k_shade<Q_MAT4, true><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT4], q, counts, d_err);
+                else k_shade<Q_MAT4><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT4], q, counts, d_err);
+                FTN_LAUNCHED();
+            }
             // The shadow and MIS queues cannot be longer than this iteration's input queue, and their kernels
             // read the exact lengths on the device: launch them sized by that bound BEFORE waiting for the
             // counts, so that the host round trip (needed to size the next iteration and to stop) is hidden

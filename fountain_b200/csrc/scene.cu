@@ -459,6 +459,17 @@ int scene_create(const FtnSceneDesc* d, FtnScene** out) {
         }
         for (int c = 0; c < 3; ++c) { md.tex1[c] = fm.tex1[c]; md.tex2[c] = fm.tex2[c]; }
         for (int c = 0; c < 2; ++c) { md.uv_scale[c] = fm.uv_scale[c]; md.uv_delta[c] = fm.uv_delta[c]; }
+        md.image = nullptr; md.img_w = md.img_h = md.img_levels = md.img_wrap = 0;
+        if (md.kd_texture < FTN_TEXTURE_CONSTANT || md.kd_texture > FTN_TEXTURE_IMAGE) return bail(set_error(FTN_ERR_INVALID_ARGUMENT, "unknown texture type"));
+        if (md.kd_texture == FTN_TEXTURE_IMAGE) {   // the host's MIPMap pyramid (mipmap.rs:78-143), copied as RGBA texels
+            std::vector<F4> texels;
+            if (!pack_image_pyramid(fm, &texels)) return bail(set_error(FTN_ERR_INVALID_ARGUMENT, "image texture: bad pyramid description"));
+            F4* d_img = nullptr;
+            if ((rc = upload(&d_img, texels.data(), texels.size())) != FTN_OK) return bail(rc);
+            s->owned.push_back(d_img);
+            s->has_image_texture = true;
+            md.image = d_img; md.img_w = fm.image_width; md.img_h = fm.image_height; md.img_levels = fm.image_levels; md.img_wrap = fm.image_wrap;
+        }
         if (fm.type == FTN_MATERIAL_PLASTIC) vr = ur;
         if (fm.remap_roughness) { ur = roughness_to_alpha_host(ur); vr = roughness_to_alpha_host(vr); }
         if (md.type != FTN_CLASS_OREN_NAYAR) { md.alpha_x = ur; md.alpha_y = vr; }   // Oren-Nayar keeps (a, b) there

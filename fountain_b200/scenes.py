@@ -295,8 +295,10 @@ def textured_floor_scene(backend=None, resolution=(48, 48), texture="checkerboar
         tex = api.Checkerboard2DTexture((0.8, 0.2, 0.2), (0.1, 0.1, 0.9), api.UVMapping(1.0, 1.0, 0.0, 0.0))
     elif texture == "checkerboard_scaled":
         tex = api.Checkerboard2DTexture((0.8, 0.2, 0.2), (0.1, 0.1, 0.9), api.UVMapping(2.0, 0.5, 0.25, -0.5))
-    else:
+    elif texture == "uv":
         tex = api.UVTexture(api.UVMapping(0.5, 0.25, 0.1, 0.2))
+    else:
+        tex = texture   # a texture object, e.g. api.ImageTexture
     mat = api.MatteMaterial(tex) if material == "matte" else api.PlasticMaterial(tex, 0.2, 0.2)
     lights = [api.DistantLight.from_params(L=3.0, from_=(0.0, 0.0, 1.0), to=(0.0, 0.0, 0.0))]
     if look_at is None:
@@ -307,5 +309,41 @@ def textured_floor_scene(backend=None, resolution=(48, 48), texture="checkerboar
     else:
         cam_to_world = Transform.look_at((look_at[0], look_at[1], 30.0), (look_at[0], look_at[1], 0.0), (0, 1, 0)).inverse()
     camera = api.PerspectiveCamera(cam_to_world, resolution, fov=fov)
+    film = api.Film(resolution, backend=backend)
+    return scene, camera, film
+
+
+# ---- image-textured Kd (texture/image.rs + mipmap.rs) ------------------------------------------
+@functools.lru_cache(maxsize=4)
+def procedural_image(width=64, height=48, seed=5):
+    """A deterministic colourful image with fine and coarse detail (fine stripes over smooth blobs), so that
+    different pyramid levels differ visibly."""
+    rng = np.random.default_rng(seed)
+    s = (np.arange(width)[None, :] + 0.5) / width
+    t = (np.arange(height)[:, None] + 0.5) / height
+    img = np.zeros((height, width, 3), np.float32)
+    img[..., 0] = 0.5 + 0.4 * np.sin(2 * np.pi * 3 * s) * np.cos(2 * np.pi * 2 * t)
+    img[..., 1] = 0.15 + 0.7 * ((np.arange(width)[None, :] + np.arange(height)[:, None]) % 2)      # texel-sized checker
+    img[..., 2] = 0.1 + 0.8 * t * np.ones_like(s)
+    img += (0.05 * rng.random(img.shape)).astype(np.float32)
+    return np.clip(img, 0.0, 1.0).astype(np.float32)
+
+
+def image_texture_scene(backend=None, resolution=(48, 48), wrap="repeat", material="matte", uscale=0.25, lens_radius=0.0):
+    """The 12x12 floor of textured_floor_scene seen at a grazing angle (the footprint, hence the mip level, varies
+    from the foreground to the horizon) plus a sphere carrying the same image through its own (phi, theta) uv;
+    a distant light and a uniform environment, so bounce hits look textures up too."""
+    tex = api.ImageTexture(api.MIPMap(procedural_image(), wrap), api.UVMapping(uscale, uscale * 1.5, 0.1, 0.2))
+    stex = api.ImageTexture(api.MIPMap(procedural_image(), wrap), api.UVMapping(2.0, 1.0, 0.0, 0.0))
+    make = (lambda t: api.MatteMaterial(t)) if material == "matte" else ((lambda t: api.MatteMaterial(t, sigma=30.0)) if material == "oren_nayar"
+                                                                         else (lambda t: api.PlasticMaterial(t, 0.2, 0.2)))
+    v = np.array([[-6, -6, 0], [6, -6, 0], [6, 6, 0], [-6, 6, 0]], np.float32)
+    mesh = api.TriangleMesh(Transform.identity(), np.array([0, 1, 2, 0, 2, 3], np.uint32), v, tex_coords=v[:, :2].copy())
+    sphere = api.Sphere(Transform.translate((1.5, 1.0, 1.2)), radius=1.2)
+    prims = [api.GeometricPrimitive(mesh, make(tex)), api.GeometricPrimitive(sphere, make(stex))]
+    lights = [api.DistantLight.from_params(L=2.5, from_=(0.3, -0.4, 1.0), to=(0.0, 0.0, 0.0)), api.InfiniteAreaLight.new_uniform(0.3)]
+    scene = api.Scene(prims, lights, backend=backend)
+    cam_to_world = Transform.look_at((0, -8.5, 1.6), (0, 1, 0.4), (0, 0, 1)).inverse()
+    camera = api.PerspectiveCamera(cam_to_world, resolution, fov=50.0, lens_radius=lens_radius, focal_dist=9.0)
     film = api.Film(resolution, backend=backend)
     return scene, camera, film

@@ -96,12 +96,26 @@ typedef enum FtnMaterialType {
 
 /* Texture of a spectrum parameter (src/texture): constant, the 2D checkerboard without anti-aliasing
  * (AAMethod::None, the only one implemented, checkerboard.rs:54-64) or the uv debug texture (uv.rs), both
- * through UVMapping (mapping.rs:36-53: st = scale * uv + delta).  Image textures are out of scope. */
+ * through UVMapping (mapping.rs:36-53: st = scale * uv + delta), or an image texture (image.rs:26-34): the
+ * host hands over the MIPMap pyramid it built (mipmap.rs:78-143) and the device does lookup_trilinear
+ * (mipmap.rs:245-279) with the camera ray's differentials (interaction.rs:124-176, camera/mod.rs:145-205,
+ * scaled by 1/sqrt(spp), integrator/mod.rs:249); rays spawned at a surface carry none, so every later
+ * hit filters level 0 bilinearly (width 0).  Deviation: the direct-lighting integrator's specular_reflect
+ * propagates differentials through a mirror (integrator/mod.rs:59-83); here they are dropped there too. */
 typedef enum FtnTextureType {
     FTN_TEXTURE_CONSTANT = 0,      /* texture/mod.rs:34-42: the value in the material's kd field */
     FTN_TEXTURE_CHECKERBOARD = 1,  /* tex1 where (floor(s) + floor(t)) % 2 == 0, else tex2 */
-    FTN_TEXTURE_UV = 2             /* (s - floor(s), t - floor(t), 0) */
+    FTN_TEXTURE_UV = 2,            /* (s - floor(s), t - floor(t), 0) */
+    FTN_TEXTURE_IMAGE = 3          /* ImageTexture<Spectrum, UVMapping>: MIPMap::lookup_trilinear */
 } FtnTextureType;
+
+/* mipmap.rs:15-17 `ImageWrap` (texel coordinates outside a level, mipmap.rs:297-311). */
+typedef enum FtnImageWrap {
+    FTN_WRAP_REPEAT = 0,           /* rem_euclid */
+    FTN_WRAP_BLACK = 1,            /* 0 outside */
+    FTN_WRAP_CLAMP = 2
+} FtnImageWrap;
+#define FTN_MAX_MIP_LEVELS 16
 
 /* Materials with constant parameters; Kd of matte / plastic may carry a texture (kd_texture). */
 typedef struct FtnMaterial {
@@ -119,6 +133,14 @@ typedef struct FtnMaterial {
     float uv_scale[2];       /* UVMapping uscale, vscale (constructors.rs:251-252, default 1) */
     float uv_delta[2];       /* UVMapping udelta, vdelta (default 0) */
     float sigma;             /* matte: Oren-Nayar roughness in DEGREES, clamped to [0, 90] (matte.rs:42); 0 = Lambert */
+    /* IMAGE: MIPMap::pyramid (mipmap.rs:19-23), levels concatenated from level 0; each level RGB f32, row-major
+     * with s fastest (texel (s, t) of a level of width w at 3 * (t * w + s)); level l is
+     * max(1, width >> l) x max(1, height >> l) and there are 1 + floor(log2(max(width, height))) levels
+     * (mipmap.rs:107-121).  Copied at scene creation. */
+    const float* image;
+    int32_t image_width, image_height;
+    int32_t image_levels;    /* checked against the rule above */
+    int32_t image_wrap;      /* FtnImageWrap */
 } FtnMaterial;
 
 /* shapes/sphere.rs:16-27 (+ the DiffuseAreaLight it may carry, light/diffuse.rs:24-41). */

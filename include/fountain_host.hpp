@@ -447,12 +447,59 @@ struct Material {
 struct UVMapping {                       // texture/mapping.rs:13-53; defaults (constructors.rs:251-254)
     float scale_u = 1.0f, scale_v = 1.0f, offset_u = 0.0f, offset_v = 0.0f;
 };
+// mipmap.rs:19-143 `MIPMap<Spectrum>`: the pyramid an ImageTexture filters.  Level l is max(1, w >> l) x max(1, h >> l)
+// and there are 1 + floor(log2(max(w, h))) levels (:107-121).  The reference halves each level with the `resize`
+// crate's Triangle filter (0.4.3, a third-party dependency that is not in its repository); from_image restates that
+// filter for a factor of two -- weights (1, 3, 3, 1) / 8 per axis, renormalised at the borders.  Host-side setup.
+struct MIPMap {
+    int width = 0, height = 0, wrap = FTN_WRAP_REPEAT;
+    int n_levels = 0;
+    std::vector<float> packed;            // the ABI's layout: levels concatenated, RGB, row-major with s fastest
+    static std::vector<float> halve(const std::vector<float>& src, int w, int h, int axis) {
+        const int n = axis == 0 ? w : h, m = std::max(1, n / 2);
+        const int ow = axis == 0 ? m : w, oh = axis == 0 ? h : m;
+        std::vector<float> out((size_t)3 * ow * oh);
+        static const double wt[4] = {1.0, 3.0, 3.0, 1.0};
+        for (int y = 0; y < oh; ++y) for (int x = 0; x < ow; ++x) for (int c = 0; c < 3; ++c) {
+            double acc = 0.0, ws = 0.0;
+            for (int k = 0; k < 4; ++k) {
+                const int j = 2 * (axis == 0 ? x : y) + k - 1;
+                if (j < 0 || j >= n) continue;
+                const int sx = axis == 0 ? j : x, sy = axis == 0 ? y : j;
+                acc += wt[k] * src[3 * ((size_t)sy * w + sx) + c]; ws += wt[k];
+            }
+            out[3 * ((size_t)y * ow + x) + c] = (float)(acc / ws);
+        }
+        return out;
+    }
+    // image: RGB f32, row-major (s fastest), width * height * 3
+    static std::shared_ptr<MIPMap> from_image(const std::vector<float>& image, int w, int h, int wrap_mode = FTN_WRAP_REPEAT) {
+        if (w < 1 || h < 1 || image.size() != (size_t)3 * w * h) throw Error(FTN_ERR_INVALID_ARGUMENT, "MIPMap: image must hold width * height * 3 floats");
+        auto mp = std::make_shared<MIPMap>();
+        mp->width = w; mp->height = h; mp->wrap = wrap_mode;
+        mp->n_levels = 1; for (int m = std::max(w, h); m > 1; m >>= 1) ++mp->n_levels;
+        std::vector<float> level = image;
+        int cw = w, ch = h;
+        mp->packed = level;
+        for (int l = 1; l < mp->n_levels; ++l) {
+            if (cw > 1) { level = halve(level, cw, ch, 0); cw = std::max(1, cw / 2); }
+            if (ch > 1) { level = halve(level, cw, ch, 1); ch = std::max(1, ch / 2); }
+            mp->packed.insert(mp->packed.end(), level.begin(), level.end());
+        }
+        return mp;
+    }
+};
+
 // A spectrum texture for Kd: ConstantTexture (texture/mod.rs:34-42), Checkerboard2DTexture over two constant
-// spectra with AAMethod::None (checkerboard.rs:10-64) or UVTexture (uv.rs:6-24)
+// spectra with AAMethod::None (checkerboard.rs:10-64), UVTexture (uv.rs:6-24) or ImageTexture (image.rs:8-34)
 struct SpectrumTexture {
     int type = FTN_TEXTURE_CONSTANT;
     Spectrum value, tex1, tex2;
     UVMapping mapping;
+    std::shared_ptr<MIPMap> mipmap;      // IMAGE
+    static SpectrumTexture image(std::shared_ptr<MIPMap> mp, UVMapping m = {}) {
+        SpectrumTexture t(Spectrum(0.0f)); t.type = FTN_TEXTURE_IMAGE; t.mipmap = std::move(mp); t.mapping = m; return t;
+    }
     SpectrumTexture(Spectrum constant) : value(constant) {}
     SpectrumTexture(float constant) : value(constant) {}
     static SpectrumTexture checkerboard(Spectrum tex1, Spectrum tex2, UVMapping m = {}) {
@@ -466,6 +513,11 @@ struct SpectrumTexture {
         m.tex2[0] = tex2.r; m.tex2[1] = tex2.g; m.tex2[2] = tex2.b;
         m.uv_scale[0] = mapping.scale_u; m.uv_scale[1] = mapping.scale_v;
         m.uv_delta[0] = mapping.offset_u; m.uv_delta[1] = mapping.offset_v;
+        if (type == FTN_TEXTURE_IMAGE) {
+            if (!mipmap) throw Error(FTN_ERR_INVALID_ARGUMENT, "image texture without a MIPMap");
+            m.image = mipmap->packed.data(); m.image_width = mipmap->width; m.image_height = mipmap->height;
+            m.image_levels = mipmap->n_levels; m.image_wrap = mipmap->wrap;
+        }
     }
 };
 struct MatteMaterial : Material {        // material/matte.rs; Kd default 0.5, sigma default 0 (constructors.rs:192-196)

@@ -42,6 +42,24 @@ ORC_API const char* orc_last_error(void) { return g_err.c_str(); }
 ORC_API int orc_set_threads(int n) { g_threads = n; return 0; }
 ORC_API int orc_hardware_threads(void) { return (int)std::max(1u, std::thread::hardware_concurrency()); }
 
+// MIPMap from the ABI's concatenated pyramid (level l: max(1, w >> l) x max(1, h >> l), mipmap.rs:107-121)
+static std::shared_ptr<MIPMap> make_mipmap(const float* data, int w, int h, int levels, int wrap) {
+    if (!data || w < 1 || h < 1 || wrap < 0 || wrap > 2) return nullptr;
+    int expect = 1; for (int m = std::max(w, h); m > 1; m >>= 1) ++expect;   // 1 + log2_usize(max(w, h))
+    if (levels != expect || levels > FTN_MAX_MIP_LEVELS) return nullptr;
+    auto mp = std::make_shared<MIPMap>();
+    mp->wrap = wrap;
+    size_t off = 0;
+    for (int l = 0; l < levels; ++l) {
+        int lw = std::max(1, w >> l), lh = std::max(1, h >> l);
+        std::vector<Spectrum> lv((size_t)lw * lh);
+        for (size_t k = 0; k < lv.size(); ++k) lv[k] = Spectrum(data[off + 3 * k], data[off + 3 * k + 1], data[off + 3 * k + 2]);
+        off += 3 * lv.size();
+        mp->w.push_back(lw); mp->h.push_back(lh); mp->pyramid.push_back(std::move(lv));
+    }
+    return mp;
+}
+
 ORC_API int orc_scene_create(const FtnSceneDesc* d, OrcScene** out) {
     if (!d || !out) return fail(FTN_ERR_INVALID_ARGUMENT, "null argument");
     if (d->abi_version != FTN_ABI_VERSION) return fail(FTN_ERR_INVALID_ARGUMENT, "abi version mismatch");
@@ -57,6 +75,10 @@ ORC_API int orc_scene_create(const FtnSceneDesc* d, OrcScene** out) {
         mm.kr = Spectrum(m.kr[0], m.kr[1], m.kr[2]); mm.sigma = m.sigma;
         mm.kd_texture = m.kd_texture; mm.tex1 = Spectrum(m.tex1[0], m.tex1[1], m.tex1[2]); mm.tex2 = Spectrum(m.tex2[0], m.tex2[1], m.tex2[2]);
         for (int c = 0; c < 2; ++c) { mm.uv_scale[c] = m.uv_scale[c]; mm.uv_delta[c] = m.uv_delta[c]; }
+        if (m.kd_texture == FTN_TEXTURE_IMAGE && (m.type == FTN_MATERIAL_MATTE || m.type == FTN_MATERIAL_PLASTIC)) {
+            mm.image = make_mipmap(m.image, m.image_width, m.image_height, m.image_levels, m.image_wrap);
+            if (!mm.image) { delete os; return fail(FTN_ERR_INVALID_ARGUMENT, "image texture: bad pyramid description"); }
+        }
         s.materials.push_back(mm);
     }
     // scene-wide arrays, one TriangleMesh view per FtnMeshDesc
@@ -383,6 +405,14 @@ ORC_API int orc_kat_env(const OrcScene* os, const float u[2], float out[11]) {
     Ray r; r.origin = Point3(0, 0, 0); r.dir = ls.wi; r.t_max = INF; r.time = 0;
     Spectrum le = l.environment_emitted_radiance(r);
     out[8] = le.c[0]; out[9] = le.c[1]; out[10] = le.c[2];
+    return FTN_OK;
+}
+// MIPMap::lookup_trilinear_width on a pyramid in the ABI's layout (mipmap.rs test_mipmap_lookup :364-382)
+ORC_API int orc_kat_mipmap_lookup(const float* pyramid, int w, int h, int levels, int wrap, float s, float t, float width, float out[3]) {
+    auto mp = make_mipmap(pyramid, w, h, levels, wrap);
+    if (!mp) return FTN_ERR_INVALID_ARGUMENT;
+    Spectrum v = mp->lookup_trilinear_width(s, t, width);
+    out[0] = v.c[0]; out[1] = v.c[1]; out[2] = v.c[2];
     return FTN_OK;
 }
 ORC_API float orc_kat_counter_uniform(uint64_t seed, uint64_t sample_index, uint32_t dim) { return counter_uniform(seed, sample_index, dim); }

@@ -62,6 +62,7 @@ def library():
             "orc_kat_camera_ray": (None, [P(A.FtnCamera), f32, f32, f32, f32, f32, P(A.FtnRay)]),
             "orc_kat_bsdf": (None, [P(A.FtnMaterial), P(f32), P(f32), P(f32), P(f32)]),
             "orc_kat_env": (C.c_int, [C.c_void_p, P(f32), P(f32)]),
+            "orc_kat_mipmap_lookup": (C.c_int, [P(f32), C.c_int, C.c_int, C.c_int, C.c_int, f32, f32, f32, P(f32)]),
             "orc_kat_counter_uniform": (f32, [u64, u64, u32]),
             "orc_kat_reference_stream": (None, [u64, C.c_int, P(f32)]),
         }

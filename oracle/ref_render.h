@@ -280,8 +280,46 @@ inline Spectrum uniform_sample_one_light(const SurfaceInteraction& isect, const 
     return (Float)n_lights * estimate_direct(bsdf, isect, us0, us1, cx.scene->lights[light_num], (int)light_num, ul0, ul1, cx);
 }
 
+// geometry/mod.rs:107-133 Differential (the `Option` is `has`)
+struct Differential {
+    bool has = false;
+    Point3 rx_origin, ry_origin; Vec3 rx_dir, ry_dir;
+};
+
+// math.rs:56-72
+inline bool solve_linear_system_2x2(const Float A[2][2] /* [col][row] */, Float b0, Float b1, Float* x0, Float* x1) {
+    Float det = A[0][0] * A[1][1] - A[1][0] * A[0][1];   // cgmath Matrix2::determinant
+    if (std::fabs(det) < 1.0e-10f) return false;
+    *x0 = (A[1][1] * b0 - A[1][0] * b1) / det;
+    *x1 = (A[0][0] * b1 - A[0][1] * b0) / det;
+    return !(std::isnan(*x0) || std::isnan(*x1));
+}
+
+// SurfaceInteraction::compute_tex_differentials, interaction.rs:124-176; None -> all zero (:117)
+inline void compute_tex_differentials(SurfaceInteraction* si, const Differential& diff) {
+    si->dudx = si->dvdx = si->dudy = si->dvdy = 0.0f;
+    if (!diff.has) return;
+    Vec3 n = si->hit.n;
+    Float d = dot(n, si->hit.p);
+    Float tx = -(dot(n, diff.rx_origin) - d) / dot(n, diff.rx_dir);
+    Point3 px = diff.rx_origin + tx * diff.rx_dir;
+    Float ty = -(dot(n, diff.ry_origin) - d) / dot(n, diff.ry_dir);
+    Point3 py = diff.ry_origin + ty * diff.ry_dir;
+    Vec3 dpdx = px - si->hit.p, dpdy = py - si->hit.p;
+    int d0, d1;
+    if (std::fabs(n.x) > std::fabs(n.y) && std::fabs(n.x) > std::fabs(n.z)) { d0 = 1; d1 = 2; }
+    else if (std::fabs(n.y) > std::fabs(n.z)) { d0 = 0; d1 = 2; }
+    else { d0 = 0; d1 = 1; }
+    Float A[2][2] = {{si->dpdu[d0], si->dpdu[d1]}, {si->dpdv[d0], si->dpdv[d1]}};   // from_cols(dpdu, dpdv)
+    Float dudx, dvdx, dudy, dvdy;
+    if (!solve_linear_system_2x2(A, dpdx[d0], dpdx[d1], &dudx, &dvdx)) return;
+    if (!solve_linear_system_2x2(A, dpdy[d0], dpdy[d1], &dudy, &dvdy)) return;
+    si->dudx = dudx; si->dvdx = dvdx; si->dudy = dudy; si->dvdy = dvdy;
+}
+
 // SurfaceInteraction::compute_scattering_functions, interaction.rs:111-121
-inline bool compute_bsdf(const Scene& scene, const SurfaceInteraction& si, Bsdf* bsdf) {
+inline bool compute_bsdf(const Scene& scene, SurfaceInteraction& si, const Differential& diff, Bsdf* bsdf) {
+    compute_tex_differentials(&si, diff);
     int m = scene.prims[si.prim].material;
     if (m < 0) return false;
     compute_scattering_functions(scene.materials[m], si, bsdf);
@@ -289,7 +327,9 @@ inline bool compute_bsdf(const Scene& scene, const SurfaceInteraction& si, Bsdf*
 }
 
 // integrator/path.rs:25-95
-inline Spectrum path_incident_radiance(Ray ray, int max_depth, Float rr_threshold, RenderCtx& cx) {
+// The spawned rays keep the CAMERA ray's differential unchanged (path.rs:73,79 pass `ray.diff` on), so every hit of
+// a path computes its texture differentials from the camera's two offset rays.
+inline Spectrum path_incident_radiance(Ray ray, const Differential& diff, int max_depth, Float rr_threshold, RenderCtx& cx) {
     const Scene& scene = *cx.scene;
     TraversalCounters* tc = cx.count_traversal ? &cx.ctr->trav : nullptr;
     Spectrum L(0.0f), beta(1.0f);
@@ -305,7 +345,7 @@ inline Spectrum path_incident_radiance(Ray ray, int max_depth, Float rr_threshol
         }
         if (!hit || bounces >= max_depth) break;
         Bsdf bsdf;
-        if (compute_bsdf(scene, si, &bsdf)) {
+        if (compute_bsdf(scene, si, diff, &bsdf)) {
             if (cx.sampler->mode == 0) cx.sampler->set_dim(DIM_CAMERA + DIM_PER_BOUNCE * (uint32_t)bounces);
             if (bsdf.num_components(BXDF_ALL & ~BXDF_SPECULAR) > 0) {
                 Spectrum direct = beta * uniform_sample_one_light(si, bsdf, cx);
@@ -337,9 +377,11 @@ inline Spectrum path_incident_radiance(Ray ray, int max_depth, Float rr_threshol
 // integrator/direct_lighting.rs:50-106 with LightStrategy::UniformSampleOne, and the specular
 // recursion of integrator/mod.rs:40-178: specular_reflect / specular_transmit sample the BSDF with
 // (REFLECTION | SPECULAR) / (TRANSMISSION | SPECULAR) and recurse with depth + 1.  sampler.get_2d()
-// is evaluated as an argument even when no such lobe exists (integrator/mod.rs:53,113).  Ray
-// differentials are not carried (they only feed texture filtering, out of scope).
-inline Spectrum direct_incident_radiance(Ray ray, int max_depth, int depth, RenderCtx& cx, bool* unsupported_null) {
+// is evaluated as an argument even when no such lobe exists (integrator/mod.rs:53,113).
+// DEVIATION (stated in include/fountain_gpu.h): specular_reflect derives new differentials for the mirrored ray
+// (integrator/mod.rs:59-83, needs dndu / dndv); this restatement and the device drop them there, so an image
+// texture seen through a mirror under this integrator is filtered at level 0.
+inline Spectrum direct_incident_radiance(Ray ray, const Differential& diff, int max_depth, int depth, RenderCtx& cx, bool* unsupported_null) {
     const Scene& scene = *cx.scene;
     TraversalCounters* tc = cx.count_traversal ? &cx.ctr->trav : nullptr;
     SurfaceInteraction si;
@@ -347,7 +389,7 @@ inline Spectrum direct_incident_radiance(Ray ray, int max_depth, int depth, Rend
     if (!scene.intersect(&ray, &si, tc)) return scene.environment_emitted_radiance(ray);
     Bsdf bsdf;
     Spectrum radiance(0.0f);
-    if (!compute_bsdf(scene, si, &bsdf)) { *unsupported_null = true; return radiance; }   // unimplemented!() :98
+    if (!compute_bsdf(scene, si, diff, &bsdf)) { *unsupported_null = true; return radiance; }   // unimplemented!() :98
     radiance = radiance + scene.emitted_radiance(si, si.wo);
     if (cx.sampler->mode == 0) cx.sampler->set_dim(DIM_CAMERA + DIM_PER_BOUNCE * (uint32_t)depth);
     radiance = radiance + uniform_sample_one_light(si, bsdf, cx);
@@ -357,7 +399,7 @@ inline Spectrum direct_incident_radiance(Ray ray, int max_depth, int depth, Rend
         cx.sampler->get_2d(&a, &b);   // specular_reflect, integrator/mod.rs:40-103
         ScatterSample s;
         if (bsdf.sample_f(si.wo, a, b, BXDF_REFLECTION | BXDF_SPECULAR, &s) && abs_dot(s.wi, si.shading_n) != 0.0f) {
-            Spectrum li = direct_incident_radiance(si.hit.spawn_ray(s.wi), max_depth, depth + 1, cx, unsupported_null);
+            Spectrum li = direct_incident_radiance(si.hit.spawn_ray(s.wi), Differential(), max_depth, depth + 1, cx, unsupported_null);
             radiance = radiance + s.f * li * std::fabs(dot(s.wi, si.shading_n)) / s.pdf;
         }
         if (cx.sampler->mode == 0) cx.sampler->set_dim(DIM_CAMERA + DIM_PER_BOUNCE * (uint32_t)depth + 7);
@@ -370,8 +412,7 @@ inline Spectrum direct_incident_radiance(Ray ray, int max_depth, int depth, Rend
 struct Camera {
     Mat4 camera_to_world, raster_to_camera;
     Float lens_radius, focal_distance, shutter_open, shutter_close;
-    // generate_ray_differential :145-205 restricted to the main ray (differentials feed only
-    // texture filtering, which constant textures ignore); identical to generate_ray :117-143.
+    // generate_ray :117-143 (= the main ray of generate_ray_differential :145-205)
     Ray generate_ray(Float fx, Float fy, Float lx, Float ly, Float time_u) const {
         Point3 p_camera = transform_point(raster_to_camera, Point3(fx, fy, 0.0f));
         Float time = (1.0f - time_u) * shutter_open + time_u * shutter_close;   // Float::lerp math.rs:21-23
@@ -385,6 +426,38 @@ struct Camera {
             ray.dir = normalize(p_focus - ray.origin);
         }
         return ray_transform(camera_to_world, ray);
+    }
+    // The two offset rays of generate_ray_differential :145-205, transformed (transform.rs:324-338: plain point /
+    // vector transforms) and scaled about the main ray (geometry/mod.rs:125-132, integrator/mod.rs:249-251).
+    // With a lens BOTH offsets use dx_camera (:178 repeats :172), as in the reference.
+    Differential generate_differential(const Ray& main_ray, Float fx, Float fy, Float lx, Float ly, Float scale) const {
+        Point3 p_camera = transform_point(raster_to_camera, Point3(fx, fy, 0.0f));
+        Point3 o0 = transform_point(raster_to_camera, Point3(0, 0, 0));
+        Vec3 dx_camera = transform_point(raster_to_camera, Point3(1, 0, 0)) - o0;   // :101-102
+        Vec3 dy_camera = transform_point(raster_to_camera, Point3(0, 1, 0)) - o0;
+        Differential df; df.has = true;
+        if (lens_radius > 0.0f) {
+            Float dx, dy; concentric_sample_disk(lx, ly, &dx, &dy);
+            Float plx = lens_radius * dx, ply = lens_radius * dy;
+            Vec3 ddx = normalize(p_camera + dx_camera);
+            Float ft = focal_distance / ddx.z;
+            Point3 p_focus = Point3(0, 0, 0) + (ft * ddx);
+            df.rx_origin = Point3(plx, ply, 0.0f); df.rx_dir = normalize(p_focus - df.rx_origin);
+            Vec3 ddy = normalize(p_camera + dx_camera);
+            ft = focal_distance / ddy.z;
+            p_focus = Point3(0, 0, 0) + (ft * ddy);
+            df.ry_origin = Point3(plx, ply, 0.0f); df.ry_dir = normalize(p_focus - df.ry_origin);
+        } else {
+            df.rx_origin = Point3(0, 0, 0); df.ry_origin = Point3(0, 0, 0);
+            df.rx_dir = normalize(p_camera + dx_camera); df.ry_dir = normalize(p_camera + dy_camera);
+        }
+        df.rx_origin = transform_point(camera_to_world, df.rx_origin); df.ry_origin = transform_point(camera_to_world, df.ry_origin);
+        df.rx_dir = transform_vector(camera_to_world, df.rx_dir); df.ry_dir = transform_vector(camera_to_world, df.ry_dir);
+        df.rx_origin = main_ray.origin + (df.rx_origin - main_ray.origin) * scale;
+        df.ry_origin = main_ray.origin + (df.ry_origin - main_ray.origin) * scale;
+        df.rx_dir = main_ray.dir + (df.rx_dir - main_ray.dir) * scale;
+        df.ry_dir = main_ray.dir + (df.ry_dir - main_ray.dir) * scale;
+        return df;
     }
 };
 
@@ -503,8 +576,10 @@ inline void render_tile(const Scene& scene, const Camera& cam, Film& film, const
             Spectrum L(0.0f);
             ctr->camera_samples++;
             if (ray_weight > 0.0f) {
-                if (rp.integrator == 0) L = path_incident_radiance(ray, rp.max_depth, rp.rr_threshold, cx);
-                else L = direct_incident_radiance(ray, rp.max_depth, 0, cx, &null_unsupported);
+                // scale_differentials(1 / sqrt(samples_per_pixel)), integrator/mod.rs:249-251
+                Differential diff = cam.generate_differential(ray, fx, fy, lx, ly, 1.0f / std::sqrt((Float)rp.spp));
+                if (rp.integrator == 0) L = path_incident_radiance(ray, diff, rp.max_depth, rp.rr_threshold, cx);
+                else L = direct_incident_radiance(ray, diff, rp.max_depth, 0, cx, &null_unsupported);
                 if (L.has_nans()) res->nan_radiance = true;   // check_radiance panics, :285-287
             }
             add_sample_to_tile(film, &tile, fx, fy, L, ray_weight);

@@ -34,6 +34,7 @@ struct SurfaceInteraction {
     Vec3 dpdu, dpdv;                 // geom
     Vec3 shading_n;
     Vec3 shading_dpdu, shading_dpdv; // shading_geom
+    Float dudx = 0.0f, dvdx = 0.0f, dudy = 0.0f, dvdy = 0.0f;   // tex_diffs (interaction.rs:193-215), default zero
     int prim;                        // index into Scene::prims (insertion order), -1 = none
     Float b[3];                      // triangle barycentrics (oracle-side extra, for the parity tests)
 };
@@ -313,7 +314,47 @@ struct Sphere {
     }
 };
 
-// ---- materials / lights tables (constant textures) ----------------------------------------
+// ---- mipmap.rs: the pyramid is built by the host (MIPMap::new, :78-143, through the `resize` crate 0.4.3, which is
+// not part of the hot path); the lookups below are the path's.
+struct MIPMap {
+    int wrap = 0;                     // ImageWrap :15-17: 0 Repeat, 1 Black, 2 Clamp
+    std::vector<int> w, h;            // per level
+    std::vector<std::vector<Spectrum>> pyramid;
+    int levels() const { return (int)pyramid.size(); }
+    // get_texel_from_level :297-311
+    Spectrum texel(int level, int s, int t) const {
+        int ss = w[level], ts = h[level];
+        if (wrap == 0) { s = ((s % ss) + ss) % ss; t = ((t % ts) + ts) % ts; }   // rem_euclid
+        else if (wrap == 2) { s = std::min(std::max(s, 0), ss - 1); t = std::min(std::max(t, 0), ts - 1); }
+        else if (s < 0 || s >= ss || t < 0 || t >= ts) return Spectrum(0.0f);
+        return pyramid[level][(size_t)t * ss + s];
+    }
+    // triangle :265-279
+    Spectrum triangle(int level, Float st0, Float st1) const {
+        level = std::min(std::max(level, 0), levels() - 1);
+        Float s = st0 * (Float)w[level] - 0.5f, t = st1 * (Float)h[level] - 0.5f;
+        int s0 = (int)std::floor(s), t0 = (int)std::floor(t);
+        Float ds = s - (Float)s0, dt = t - (Float)t0;
+        return texel(level, s0, t0) * (1.0f - ds) * (1.0f - dt) + texel(level, s0, t0 + 1) * (1.0f - ds) * dt
+             + texel(level, s0 + 1, t0) * ds * (1.0f - dt) + texel(level, s0 + 1, t0 + 1) * ds * dt;
+    }
+    // lookup_trilinear_width :245-257
+    Spectrum lookup_trilinear_width(Float st0, Float st1, Float width) const {
+        Float level = (Float)levels() - 1.0f + std::log2(fmax_(width, 1.0e-8f));
+        if (level < 0.0f) return triangle(0, st0, st1);
+        if (level >= (Float)(levels() - 1)) return texel(levels() - 1, 0, 0);
+        int lf = (int)std::floor(level);
+        Float delta = level - std::trunc(level);   // f32::fract
+        return triangle(lf, st0, st1) * (1.0f - delta) + triangle(lf + 1, st0, st1) * delta;   // Spectrum::lerp, spectrum/mod.rs:84-86
+    }
+    // lookup_trilinear :259-262 -- `dst0.y` enters without abs(), as in the reference
+    Spectrum lookup_trilinear(Float st0, Float st1, const Float dst0[2], const Float dst1[2]) const {
+        Float width = fmax_(fmax_(std::fabs(dst0[0]), dst0[1]), fmax_(std::fabs(dst1[0]), std::fabs(dst1[1])));
+        return lookup_trilinear_width(st0, st1, 2.0f * width);
+    }
+};
+
+// ---- materials / lights tables ------------------------------------------------------------
 struct Material {
     int type;          // FtnMaterialType
     Spectrum kd, ks, eta, k, kr;
@@ -321,6 +362,7 @@ struct Material {
     Spectrum tex1, tex2; Float uv_scale[2], uv_delta[2];
     Float u_rough, v_rough, sigma;
     bool remap;
+    std::shared_ptr<MIPMap> image;   // kd_texture == FTN_TEXTURE_IMAGE (texture/image.rs:8-15)
 };
 
 // primitive.rs:25-71 GeometricPrimitive<S>

@@ -344,12 +344,17 @@ struct Bsdf {
     }
 };
 
-// Kd through its texture: ConstantTexture (texture/mod.rs:34-42), Checkerboard2DTexture with
+// Kd through its texture: ConstantTexture (texture/mod.rs:34-42), ImageTexture (image.rs), Checkerboard2DTexture with
 // AAMethod::None (checkerboard.rs:50-64) or UVTexture (uv.rs:18-23), via UVMapping (mapping.rs:40-52).
 inline Spectrum evaluate_kd(const Material& m, const SurfaceInteraction& si) {
     if (m.kd_texture == 0) return m.kd;
     Float s = m.uv_scale[0] * si.uv[0] + m.uv_delta[0], t = m.uv_scale[1] * si.uv[1] + m.uv_delta[1];
     if (m.kd_texture == 1) return (((int)std::floor(s) + (int)std::floor(t)) % 2 == 0) ? m.tex1 : m.tex2;
+    if (m.kd_texture == 3) {   // ImageTexture::evaluate, image.rs:30-33, with UVMapping's dst_dx / dst_dy (mapping.rs:43-44)
+        Float dst_dx[2] = {m.uv_scale[0] * si.dudx, m.uv_scale[1] * si.dvdx};
+        Float dst_dy[2] = {m.uv_scale[0] * si.dudy, m.uv_scale[1] * si.dvdy};
+        return m.image->lookup_trilinear(s, t, dst_dx, dst_dy);
+    }
     return Spectrum(s - std::floor(s), t - std::floor(t), 0.0f);
 }
 

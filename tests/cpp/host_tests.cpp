@@ -188,6 +188,48 @@ static void textured_floor_and_mirror_closed_forms() {
         CHECK(std::fabs(s.r - 0.8f) < 1e-5f && std::fabs(s.g - 0.7f) < 1e-5f && std::fabs(s.b - 0.6f) < 1e-5f, "mirror %.7g %.7g %.7g", s.r, s.g, s.b);
 }
 
+// texture/image.rs through MIPMap::from_image; no reference test renders one -- closed forms as in tests/test_oracle_render.py:
+// (1) a ramp image is reproduced by the bilinear filter at level 0, (2) with a huge uscale the footprint exceeds the
+// image and the 1x1 top level (the mean of a two-valued checker) is returned
+static void image_texture_closed_forms() {
+    const float pi = 3.14159265358979f;
+    const int n = 16;
+    std::vector<float> ramp((size_t)3 * n * n), checker((size_t)3 * n * n);
+    for (int t = 0; t < n; ++t) for (int s = 0; s < n; ++s) {
+        float* px = &ramp[3 * ((size_t)t * n + s)];
+        px[0] = (s + 0.5f) / n; px[1] = (t + 0.5f) / n; px[2] = 0.25f;
+        float* cx = &checker[3 * ((size_t)t * n + s)];
+        cx[0] = cx[1] = cx[2] = ((s + t) % 2) ? 0.8f : 0.2f;
+    }
+    auto probe = [&](SpectrumTexture tex, double x, double y) {
+        std::vector<float> v = {-6, -6, 0, 6, -6, 0, 6, 6, 0, -6, 6, 0}, uv = {-6, -6, 6, -6, 6, 6, -6, 6};
+        auto mesh = std::make_shared<TriangleMesh>(Transform::identity(), std::vector<uint32_t>{0, 1, 2, 0, 2, 3}, v, std::vector<float>{}, uv);
+        std::vector<GeometricPrimitive> prims; prims.emplace_back(mesh, std::make_shared<MatteMaterial>(tex));
+        Scene scene(g_lib, prims, {Light(DistantLight::from_to(Point3f(0, 0, 1), Point3f(0, 0, 0), Spectrum(3.0f)))});
+        PerspectiveCamera camera(Transform::look_at({x, y, 30.0}, {x, y, 0.0}, {0, 1, 0}).inverse(), 5, 5, 0.5f);
+        Film film(g_lib, 5, 5);
+        SamplerIntegrator<DirectLightingIntegrator> integrator(camera, DirectLightingIntegrator(LightStrategy::UniformSampleOne, 1));
+        integrator.render_parallel(scene, film, RandomSampler::new_with_seed(2, 0));
+        Spectrum mean(0.0f);
+        const auto px = film.into_spectrum_buffer().first;
+        for (const Spectrum& s : px) { mean.r += s.r / px.size(); mean.g += s.g / px.size(); mean.b += s.b / px.size(); }
+        return mean;
+    };
+    auto mp = MIPMap::from_image(ramp, n, n, FTN_WRAP_CLAMP);
+    CHECK(mp->n_levels == 5 && mp->packed.size() == (size_t)3 * (256 + 64 + 16 + 4 + 1), "pyramid of a 16x16 image: %d levels", mp->n_levels);
+    const Spectrum a = probe(SpectrumTexture::image(mp, UVMapping{1.0f / 12.0f, 1.0f / 12.0f, 0.5f, 0.5f}), 2.2, -3.1);
+    CHECK(std::fabs(a.r - (2.2f / 12 + 0.5f) / pi * 3.0f) < 2e-3f && std::fabs(a.g - (-3.1f / 12 + 0.5f) / pi * 3.0f) < 2e-3f && std::fabs(a.b - 0.25f / pi * 3.0f) < 1e-5f,
+          "ramp %.7g %.7g %.7g", a.r, a.g, a.b);
+    const Spectrum b = probe(SpectrumTexture::image(MIPMap::from_image(checker, n, n, FTN_WRAP_REPEAT), UVMapping{500.0f, 500.0f, 0.0f, 0.0f}), 0.7, -0.4);
+    CHECK(std::fabs(b.r - 0.5f / pi * 3.0f) < 1e-4f, "top level of the checker pyramid %.7g", b.r);
+    bool threw = false;
+    try {
+        auto bad = MIPMap::from_image(ramp, n, n); bad->n_levels = 4;
+        probe(SpectrumTexture::image(bad), 0.0, 0.0);
+    } catch (const Error& e) { threw = e.code == FTN_ERR_INVALID_ARGUMENT; }
+    CHECK(threw, "a pyramid with the wrong level count must be FTN_ERR_INVALID_ARGUMENT");
+}
+
 static void invalid_arguments_are_errors() {
     bool threw = false;
     try {
@@ -226,6 +268,7 @@ int main(int argc, char** argv) {
         {"camera_raster_to_camera_fov", camera_raster_to_camera_fov},
         {"world_bound_and_morton_order", world_bound_and_morton_order},
         {"textured_floor_and_mirror_closed_forms", textured_floor_and_mirror_closed_forms},
+        {"image_texture_closed_forms", image_texture_closed_forms},
         {"invalid_arguments_are_errors", invalid_arguments_are_errors},
     };
     int ran = 0;

@@ -14,6 +14,7 @@
 #include <numeric>
 #include <string>
 #include <vector>
+#include <list>
 #include "../../fountain_b200/csrc/ftn_path.cuh"
 #include "../../fountain_b200/csrc/ftn_lbvh.cuh"
 #include "../../fountain_b200/csrc/ftn_ploc.cuh"
@@ -29,6 +30,7 @@ struct SimScene {
     std::vector<MeshData> meshes; std::vector<MaterialData> mats;
     std::vector<SphereData> spheres; std::vector<LightData> lights;
     std::vector<std::vector<F4>> env_tex; std::vector<std::vector<float>> env_f;   // storage behind EnvLightData pointers
+    std::list<std::vector<F4>> images;   // storage behind MaterialData::image
     std::vector<F4> nodes, tris; uint32_t n_nodes = 0;
     std::vector<uint32_t> codes, order;
     float bounds[6]; bool built = false; uint32_t n_tris = 0;
@@ -79,6 +81,12 @@ SIM_API int sim_scene_create(const FtnSceneDesc* d, SimScene** out) {
         }
         for (int c = 0; c < 3; ++c) { md.tex1[c] = fm.tex1[c]; md.tex2[c] = fm.tex2[c]; }
         for (int c = 0; c < 2; ++c) { md.uv_scale[c] = fm.uv_scale[c]; md.uv_delta[c] = fm.uv_delta[c]; }
+        md.image = nullptr; md.img_w = md.img_h = md.img_levels = md.img_wrap = 0;
+        if (md.kd_texture == FTN_TEXTURE_IMAGE) {   // as scene.cu
+            s->images.emplace_back();
+            if (!pack_image_pyramid(fm, &s->images.back())) { delete s; g_err = "image texture: bad pyramid description"; return FTN_ERR_INVALID_ARGUMENT; }
+            md.image = s->images.back().data(); md.img_w = fm.image_width; md.img_h = fm.image_height; md.img_levels = fm.image_levels; md.img_wrap = fm.image_wrap;
+        }
         if (fm.type == FTN_MATERIAL_PLASTIC) vr = ur;
         if (fm.remap_roughness) { ur = roughness_to_alpha_host(ur); vr = roughness_to_alpha_host(vr); }
         if (md.type != FTN_CLASS_OREN_NAYAR) { md.alpha_x = ur; md.alpha_y = vr; }   // Oren-Nayar keeps (a, b) there
@@ -423,7 +431,7 @@ SIM_API void sim_kat_bsdf(const FtnMaterial* m, const float wo[3], const float w
     Bsdf b; bsdf_init(&b, V3(0, 0, 1), V3(0, 0, 1), V3(1, 0, 0));
     const V3 o(wo[0], wo[1], wo[2]), i(wi[0], wi[1], wi[2]);
     V3 f; float pdf; ScatterSample sm; bool ok;
-#define SIM_BSDF(M) { material_bsdf<M>(s->mats[0], 0.0f, 0.0f, &b); f = bsdf_f<M>(b, o, i, BXDF_ALL); pdf = bsdf_pdf<M>(b, o, i, BXDF_ALL); ok = bsdf_sample_f<M>(b, o, u[0], u[1], BXDF_ALL, &sm); }
+#define SIM_BSDF(M) { material_bsdf<M>(s->mats[0], 0.0f, 0.0f, TexDiffs{0.0f, 0.0f, 0.0f, 0.0f}, &b); f = bsdf_f<M>(b, o, i, BXDF_ALL); pdf = bsdf_pdf<M>(b, o, i, BXDF_ALL); ok = bsdf_sample_f<M>(b, o, u[0], u[1], BXDF_ALL, &sm); }
     if (s->mats[0].type == FTN_CLASS_OREN_NAYAR) SIM_BSDF(FTN_CLASS_OREN_NAYAR)
     else if (m->type == FTN_MATERIAL_MATTE) SIM_BSDF(FTN_MATERIAL_MATTE)
     else if (m->type == FTN_MATERIAL_METAL) SIM_BSDF(FTN_MATERIAL_METAL)

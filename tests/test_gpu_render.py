@@ -243,3 +243,37 @@ def test_oren_nayar_closed_form(gpu_backend):
     from tests.test_oracle_render import _oren_nayar_probe, _oren_nayar_expected
     for case in ((20.0, 0.0, 0.0, 0.0), (20.0, 50.0, 30.0, 0.0), (35.0, 30.0, 55.0, 0.0), (20.0, 50.0, 30.0, 180.0)):
         assert np.allclose(_oren_nayar_probe(gpu_backend, *case), _oren_nayar_expected(*case)[None, :], rtol=3e-3), case
+
+
+# ---- image-textured Kd (texture/image.rs, mipmap.rs:245-311, interaction.rs:124-176) ----------------------------
+@pytest.mark.parametrize("wrap,material,integ,lens", [("repeat", "matte", "path", 0.0), ("clamp", "plastic", "path", 0.15),
+                                                      ("black", "oren_nayar", "direct", 0.0)])
+def test_image_texture_matches_oracle(gpu_backend, orc_backend, wrap, material, integ, lens):
+    kw = dict(resolution=(96, 96), wrap=wrap, material=material, lens_radius=lens)
+    integrator = api.PathIntegrator(3, 1.0) if integ == "path" else api.DirectLightingIntegrator(2)
+    a, apx, ast = parity.render(gpu_backend, scenes.image_texture_scene, integrator, 16, seed=13, **kw)
+    b, bpx, bst = parity.render(orc_backend, scenes.image_texture_scene, integrator, 16, seed=13, **kw)
+    mean_rel, frac_off = parity.image_diff(a, b)
+    assert mean_rel < 2e-3 and frac_off < 0.02, (mean_rel, frac_off)
+    assert np.array_equal(apx[..., 3], bpx[..., 3])
+
+
+def test_image_texture_level_selection_closed_form(gpu_backend):
+    """Level l of the pyramid is the constant .1 + .1 l: the pixel value reads the (fractional) level the device chose
+    from the camera differentials; closed form for a camera looking straight down (see tests/test_oracle_render.py)."""
+    from tests.test_oracle_render import constant_level_mipmap, expected_mip_level
+    mp = constant_level_mipmap()
+    for uscale in (0.02, 1.0, 3.0, 11.0, 500.0):
+        tex = api.ImageTexture(mp, api.UVMapping(uscale, uscale, 0.3, 0.1))
+        scene, camera, film = scenes.textured_floor_scene(backend=gpu_backend, resolution=(5, 5), texture=tex, look_at=(0.7, -0.4), fov=0.5)
+        api.SamplerIntegrator(camera, api.DirectLightingIntegrator(1)).render_parallel(scene, film, api.RandomSampler.new_with_seed(4, 0))
+        level = min(max(expected_mip_level(len(mp.levels), uscale, 0.5, 5, 30.0, 4), 0.0), len(mp.levels) - 1.0)
+        assert np.allclose(film.into_spectrum_buffer()[0], (0.1 + 0.1 * level) / np.pi * 3.0, rtol=2e-3), uscale
+
+
+def test_image_texture_bad_pyramid_is_rejected(gpu_backend):
+    mp = api.MIPMap(scenes.procedural_image(), "repeat")
+    mp.levels = mp.levels[:-1]          # one level short of 1 + floor(log2(max(w, h)))
+    tex = api.ImageTexture(mp)
+    with pytest.raises(api.FountainError):
+        scenes.textured_floor_scene(backend=gpu_backend, texture=tex)

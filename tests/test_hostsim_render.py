@@ -163,3 +163,28 @@ def test_oren_nayar_image_matches_oracle(sim_backend, orc_backend):
     lam, _, _ = parity.render(orc_backend, lambda backend, **k: scenes.rounded_cube_scene(backend=backend, material=api.MatteMaterial((0.6, 0.5, 0.4)), **k),
                               api.PathIntegrator(5, 1.0), 4, seed=3, resolution=(40, 40))
     assert parity.image_diff(b, lam)[0] > 1e-2            # and it is not the Lambert image
+
+
+# ---- image-textured Kd (ImageTexture + MIPMap::lookup_trilinear with the camera ray's differentials) --------
+@pytest.mark.parametrize("wrap,material,integ,lens", [("repeat", "matte", "path", 0.0), ("clamp", "plastic", "path", 0.15),
+                                                      ("black", "oren_nayar", "direct", 0.0)])
+def test_image_texture_matches_oracle(sim_backend, orc_backend, wrap, material, integ, lens):
+    kw = dict(resolution=(40, 40), wrap=wrap, material=material, lens_radius=lens)
+    integrator = api.PathIntegrator(3, 1.0) if integ == "path" else api.DirectLightingIntegrator(2)
+    a, apx, ast = parity.render(sim_backend, scenes.image_texture_scene, integrator, 4, seed=13, **kw)
+    b, bpx, bst = parity.render(orc_backend, scenes.image_texture_scene, integrator, 4, seed=13, **kw)
+    mean_rel, frac_off = parity.image_diff(a, b)
+    assert mean_rel < 2e-3 and frac_off < 0.02, (mean_rel, frac_off)
+    assert np.array_equal(apx[..., 3], bpx[..., 3])
+    assert len(np.unique(np.round(b.reshape(-1, 3), 2), axis=0)) > 50       # the texture is visible
+
+
+def test_image_texture_level_selection_closed_form_hostsim(sim_backend):
+    from tests.test_oracle_render import constant_level_mipmap, expected_mip_level
+    mp = constant_level_mipmap()
+    for uscale in (1.0, 3.0, 11.0):
+        tex = api.ImageTexture(mp, api.UVMapping(uscale, uscale, 0.3, 0.1))
+        scene, camera, film = scenes.textured_floor_scene(backend=sim_backend, resolution=(5, 5), texture=tex, look_at=(0.7, -0.4), fov=0.5)
+        api.SamplerIntegrator(camera, api.DirectLightingIntegrator(1)).render_parallel(scene, film, api.RandomSampler.new_with_seed(4, 0))
+        level = min(max(expected_mip_level(len(mp.levels), uscale, 0.5, 5, 30.0, 4), 0.0), len(mp.levels) - 1.0)
+        assert np.allclose(film.into_spectrum_buffer()[0], (0.1 + 0.1 * level) / np.pi * 3.0, rtol=2e-3), uscale

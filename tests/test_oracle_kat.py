@@ -289,3 +289,69 @@ def test_counter_stream_uniformity(oracle):
     # different dimensions / samples decorrelate
     a = v.reshape(-1, 4)
     assert abs(np.corrcoef(a[:, 0], a[:, 1])[0, 1]) < 0.05
+
+
+# ---- mipmap.rs: MIPMap lookups (the image texture's device half) ---------------------------------------------------
+def _mip_lookup(oracle, mp, s, t, width):
+    out = (C.c_float * 3)()
+    rc = oracle.library().orc_kat_mipmap_lookup(mp.packed.ctypes.data_as(C.POINTER(C.c_float)), mp.width, mp.height, len(mp.levels),
+                                               mp.wrap, float(s), float(t), float(width), out)
+    assert rc == 0
+    return np.array(list(out), np.float32)
+
+
+def test_mipmap_lookup_reference_kat(oracle):
+    """mipmap.rs:364-382 test_mipmap_lookup: a constant 16x15 image filters to the constant (6 ulps) at every
+    coordinate and width, including 0."""
+    from fountain_b200 import api
+    val = np.float32(0.5)
+    mp = api.MIPMap(np.full((15, 16, 3), val, np.float32), "repeat")
+    assert [l.shape[:2] for l in mp.levels] == [(15, 16), (7, 8), (3, 4), (1, 2), (1, 1)]     # :107-121
+    widths = list(np.logspace(-4.0, 0.0, 10)) + [0.0]
+    for s in np.linspace(0.0, 1.0, 25):
+        for t in np.linspace(0.0, 1.0, 25):
+            for w in widths:
+                got = _mip_lookup(oracle, mp, s, t, w)
+                assert np.all(np.abs(got.view(np.int32) - val.view(np.int32)) <= 6), (s, t, w, got)
+
+
+def _np_texel(mp, level, s, t):
+    lv = mp.levels[level]; h, w = lv.shape[:2]
+    if mp.wrap == 0: s, t = s % w, t % h
+    elif mp.wrap == 2: s, t = min(max(s, 0), w - 1), min(max(t, 0), h - 1)
+    elif s < 0 or s >= w or t < 0 or t >= h: return np.zeros(3)
+    return lv[t, s].astype(np.float64)
+
+
+def _np_triangle(mp, level, s, t):
+    lv = mp.levels[level]; h, w = lv.shape[:2]
+    x, y = s * w - 0.5, t * h - 0.5
+    s0, t0 = int(np.floor(x)), int(np.floor(y)); ds, dt = x - s0, y - t0
+    return ((1 - ds) * (1 - dt) * _np_texel(mp, level, s0, t0) + (1 - ds) * dt * _np_texel(mp, level, s0, t0 + 1)
+            + ds * (1 - dt) * _np_texel(mp, level, s0 + 1, t0) + ds * dt * _np_texel(mp, level, s0 + 1, t0 + 1))
+
+
+def _np_lookup(mp, s, t, width):
+    n = len(mp.levels)
+    level = n - 1 + np.log2(max(width, 1e-8))
+    if level < 0: return _np_triangle(mp, 0, s, t)
+    if level >= n - 1: return _np_texel(mp, n - 1, 0, 0)
+    lf = int(np.floor(level)); d = level - lf
+    return (1 - d) * _np_triangle(mp, lf, s, t) + d * _np_triangle(mp, lf + 1, s, t)
+
+
+@pytest.mark.parametrize("wrap", ["repeat", "black", "clamp"])
+def test_mipmap_lookup_closed_forms(oracle, wrap):
+    """No reference test reads distinct texels (the image one is #[ignore]d and needs a file): pinned against an
+    independent numpy statement of mipmap.rs:245-311."""
+    from fountain_b200 import api
+    rng = np.random.default_rng(11)
+    mp = api.MIPMap(rng.random((6, 8, 3)).astype(np.float32), wrap)
+    assert len(mp.levels) == 4
+    # texel centres at width 0 return the texel itself
+    for (si, ti) in ((0, 0), (7, 5), (3, 2)):
+        assert np.allclose(_mip_lookup(oracle, mp, (si + 0.5) / 8, (ti + 0.5) / 6, 0.0), mp.levels[0][ti, si], rtol=1e-6)
+    for _ in range(300):
+        s, t = rng.uniform(-0.3, 1.3, 2)
+        w = float(rng.choice([0.0, 1e-3, 0.13, 0.2, 0.26, 0.4, 0.51, 0.9, 1.0, 3.0]))
+        assert np.allclose(_mip_lookup(oracle, mp, s, t, w), _np_lookup(mp, np.float32(s), np.float32(t), w), rtol=2e-4, atol=2e-6), (s, t, w)

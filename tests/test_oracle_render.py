@@ -237,3 +237,62 @@ def test_oren_nayar_closed_form(orc_backend, sigma, theta_i, theta_o, dphi):
 def test_oren_nayar_sigma_zero_is_lambert(orc_backend):
     a = _oren_nayar_probe(orc_backend, 0.0, 40.0, 20.0, 30.0)
     assert np.allclose(a, (np.array([0.7, 0.5, 0.3]) / np.pi * 2.0 * np.cos(np.radians(40.0)))[None, :], rtol=1e-5)
+
+
+# ---- image texture (texture/image.rs, mipmap.rs:245-279, interaction.rs:124-176, camera/mod.rs:145-205) --------
+# No reference test renders one.  Pinned by closed forms: a pyramid whose level l is the constant c_l returns
+# lerp(level - floor(level), c_floor, c_floor+1) whatever st is, and for a camera looking straight down a plane
+# from height H the texture-space footprint is uscale * (pixel size on the plane) / sqrt(spp) (integrator/mod.rs:249).
+def constant_level_mipmap(n=64, wrap="repeat"):
+    levels, l = [], 0
+    while True:
+        m = max(1, n >> l)
+        levels.append(np.full((m, m, 3), 0.1 + 0.1 * l, np.float32))
+        if m == 1:
+            break
+        l += 1
+    return api.MIPMap(levels=levels, wrap=wrap)
+
+
+def expected_mip_level(n_levels, uscale, fov_deg, res, height, spp):
+    pix = 2.0 * height * np.tan(np.radians(fov_deg) / 2.0) / res
+    width = 2.0 * uscale * pix / np.sqrt(spp)
+    return n_levels - 1 + np.log2(max(width, 1e-8))
+
+
+@pytest.mark.parametrize("uscale", [0.02, 1.0, 3.0, 11.0, 500.0])
+def test_image_texture_level_selection_closed_form(orc_backend, uscale):
+    mp = constant_level_mipmap()
+    tex = api.ImageTexture(mp, api.UVMapping(uscale, uscale, 0.3, 0.1))
+    scene, camera, film = scenes.textured_floor_scene(backend=orc_backend, resolution=(5, 5), texture=tex, look_at=(0.7, -0.4), fov=0.5)
+    api.SamplerIntegrator(camera, api.DirectLightingIntegrator(1)).render_parallel(scene, film, api.RandomSampler.new_with_seed(4, 0))
+    rgb = film.into_spectrum_buffer()[0]
+    level = expected_mip_level(len(mp.levels), uscale, 0.5, 5, 30.0, 4)
+    n = len(mp.levels)
+    if level < 0: c = 0.1
+    elif level >= n - 1: c = 0.1 + 0.1 * (n - 1)
+    else: c = 0.1 + 0.1 * level          # the lerp of c_l = .1 + .1 l is linear in the level
+    assert np.allclose(rgb, c / np.pi * 3.0, rtol=2e-3), (level, rgb[:2])
+
+
+def test_image_texture_bilinear_closed_form(orc_backend):
+    """Level 0 of a ramp image is reproduced exactly by the bilinear `triangle` filter in the interior."""
+    n = 16
+    ramp = np.zeros((n, n, 3), np.float32)
+    ramp[..., 0] = (np.arange(n)[None, :] + 0.5) / n          # = s at texel centres
+    ramp[..., 1] = (np.arange(n)[:, None] + 0.5) / n          # = t
+    ramp[..., 2] = 0.25
+    tex = api.ImageTexture(api.MIPMap(ramp, "clamp"), api.UVMapping(1.0 / 12.0, 1.0 / 12.0, 0.5, 0.5))   # the 12x12 floor -> [0, 1]^2
+    for xy in ((0.0, 0.0), (2.2, -3.1), (-4.0, 1.5)):
+        scene, camera, film = scenes.textured_floor_scene(backend=orc_backend, resolution=(5, 5), texture=tex, look_at=xy, fov=0.5)
+        api.SamplerIntegrator(camera, api.DirectLightingIntegrator(1)).render_parallel(scene, film, api.RandomSampler.new_with_seed(2, 0))
+        rgb = film.into_spectrum_buffer()[0]
+        want = np.array([xy[0] / 12 + 0.5, xy[1] / 12 + 0.5, 0.25]) / np.pi * 3.0
+        assert np.allclose(rgb.mean(axis=0), want, rtol=3e-3), (xy, rgb.mean(axis=0), want)
+
+
+def test_image_texture_bad_pyramid_is_rejected(orc_backend):
+    mp = api.MIPMap(scenes.procedural_image(), "repeat")
+    mp.levels = mp.levels[:-1]          # one level short of 1 + floor(log2(max(w, h)))
+    with pytest.raises(api.FountainError):
+        scenes.textured_floor_scene(backend=orc_backend, texture=api.ImageTexture(mp))
