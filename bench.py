@@ -384,6 +384,10 @@ def run_ours_raybatch(args):
             gpu.call("intersect_device", scene.handle, n, C.c_void_p(d_rays.data_ptr()), C.c_void_p(d_hits.data_ptr()), C.c_void_p(stream.cuda_stream))
         times = []
         l0 = int(gpu.fn["kernel_launch_count"]())
+        sample_clocks = label == "incoherent_diffuse" and rank == 0
+        if sample_clocks:   # the timed steps are ~1.5 ms each: repeat them (untimed extras) until nvidia-smi has sampled the loaded GPU
+            clocks = ClockSampler(local_rank)
+            t_wall0 = time.perf_counter()
         for _ in range(args.steps):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -392,6 +396,11 @@ def run_ours_raybatch(args):
             e1.record(stream); e1.synchronize()
             times.append(e0.elapsed_time(e1))
         launches = int(gpu.fn["kernel_launch_count"]()) - l0
+        if sample_clocks:
+            while time.perf_counter() - t_wall0 < 0.3:
+                gpu.call("intersect_device", scene.handle, n, C.c_void_p(d_rays.data_ptr()), C.c_void_p(d_hits.data_ptr()), C.c_void_p(stream.cuda_stream))
+                torch.cuda.synchronize()
+            clock_info = clocks.stop(t_wall0, time.perf_counter())
         med = float(np.median(times))
         st = scene.stats()
         bytes_ = st["bvh_node_bytes"] * nodes + st["bvh_tri_bytes"] * tris + 48 * n
@@ -416,6 +425,22 @@ def run_ours_raybatch(args):
     assert np.array_equal(host_hits["t"], d_hits_inc_check["t"]) and np.array_equal(host_hits["prim"], d_hits_inc_check["prim"])   # same answers as the resident path
     gpu.call("host_free", p_rays); gpu.call("host_free", p_hits)
     inc_r = results["incoherent_diffuse"]
+    base = None
+    if rank == 0 and not args.no_cpu_baseline:
+        # the oracle's closest-hit query (reference BVH + traversal restated, all host threads) on the first rays of the same batch
+        from oracle import orc
+        cores = orc.hardware_threads(); orc.set_threads(cores)
+        o_scene, _ = scenes.synthetic_mesh_scene(side[0], side[1], backend=orc.backend(), resolution=(2048, 2048))
+        n_s = min(len(inc), 1 << 18)
+        o_scene.intersect(inc[:4096])
+        t0 = time.perf_counter(); o_hits = o_scene.intersect(inc[:n_s]); dt = time.perf_counter() - t0
+        n_s2 = int(min(len(inc), max(n_s, n_s * 10.0 / max(dt, 1e-3))))
+        if n_s2 > n_s:
+            t0 = time.perf_counter(); o_hits = o_scene.intersect(inc[:n_s2]); dt = time.perf_counter() - t0; n_s = n_s2
+        assert np.array_equal(o_hits["t"], d_hits_inc_check["t"][:n_s])   # and the device agrees with it bit for bit
+        base = {"value": n_s / dt / 1e6, "unit": UNIT, "cores": cores, "kind": "port", "seconds": dt,
+                "bvh_build_seconds": o_scene.stats()["bvh_build_seconds"],
+                "sample": "closest hit for the first %d of the %d incoherent diffuse-bounce rays, %d threads (C++ restatement of the reference; Rust toolchain absent)" % (n_s, len(inc), cores)}
     if rank == 0:
         st = scene.stats()
         print(json.dumps({"metric": METRIC, "value": inc_r["mrays_per_s"], "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
@@ -423,7 +448,7 @@ def run_ours_raybatch(args):
                           "data": "synthetic",
                           "config": {"workload": "C3 displaced sphere %d tris: closest-hit batches, 2048x2048 primary + %d incoherent diffuse-bounce rays"
                                                  % (scene.n_triangles, len(inc)), "l2": "flushed between timed steps (256 MiB write)"},
-                          "batches": results, "gpu_launches": results["incoherent_diffuse"]["launches"],
+                          "batches": results, "gpu_launches": results["incoherent_diffuse"]["launches"], "clocks": clock_info, "cpu_baseline": base,
                           "e2e": {"value": len(inc) / e2e_dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(inc.nbytes), "d2h_bytes_per_step": int(len(inc) * 16)},
                           "roofline": {"bound": "hbm", "kernel": "k_intersect_batch<closest>", "achieved": inc_r["achieved_gbs"], "peak": peak, "unit": "GB/s",
                                        "frac": inc_r["frac_of_peak"], "traffic": traffic_from_profiles("k_intersect_batch"), "peak_source": peak_src},
