@@ -323,6 +323,26 @@ int DeviceArena::pinned_counts(uint32_t** out, size_t need) {
     *out = (uint32_t*)h_pinned;
     return FTN_OK;
 }
+// Scene buffers come from the device's stream-ordered pool (cudaMallocAsync on the legacy stream), kept mapped between
+// scenes (release threshold = max): creating and destroying a scene per frame, as the end-to-end path does, costs no
+// page mapping after the first one.  ftn_release_cached_memory trims the pool.
+static bool g_pool_ready[FTN_MAX_DEVICES] = {};
+static cudaError_t scene_malloc(void** p, size_t bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < FTN_MAX_DEVICES && !g_pool_ready[dev]) {
+        cudaMemPool_t pool;
+        if ((e = cudaDeviceGetDefaultMemPool(&pool, dev)) != cudaSuccess) return e;
+        unsigned long long keep = ~0ull;
+        if ((e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep)) != cudaSuccess) return e;
+        g_pool_ready[dev] = true;
+    }
+    return cudaMallocAsync(p, bytes ? bytes : 1, 0);
+}
+template <class T> static cudaError_t scene_malloc(T** p, size_t bytes) { return scene_malloc((void**)p, bytes); }
+static void scene_free(void* p) { if (p) cudaFreeAsync(p, 0); }
+
 int release_cached_memory() {
     for (int d = 0; d < FTN_MAX_DEVICES; ++d) {
         DeviceArena& a = g_arena[d];
@@ -331,6 +351,12 @@ int release_cached_memory() {
         if (cudaSetDevice(d) != cudaSuccess) continue;
         for (int i = 0; i < 4; ++i) { cudaFree(a.p[i]); a.p[i] = nullptr; a.bytes[i] = 0; }
         if (a.h_pinned) { cudaFreeHost(a.h_pinned); a.h_pinned = nullptr; a.h_pinned_bytes = 0; }
+    }
+    for (int d = 0; d < FTN_MAX_DEVICES; ++d) {
+        if (!g_pool_ready[d]) continue;
+        cudaMemPool_t pool;
+        if (cudaSetDevice(d) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) continue;
+        if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
     }
     return FTN_OK;
 }
@@ -357,7 +383,7 @@ SceneView make_view(const FtnScene& s) {
 template <class T> static int upload(T** dst, const T* src, size_t count) {
     *dst = nullptr;
     if (count == 0) return FTN_OK;
-    FTN_CUDA(cudaMalloc((void**)dst, count * sizeof(T)));
+    FTN_CUDA(scene_malloc((void**)dst, count * sizeof(T)));
     FTN_CUDA(cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice));
     return FTN_OK;
 }
@@ -371,6 +397,11 @@ static float roughness_to_alpha_host(float roughness) {
     return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
 }
 
+__global__ void k_rgb_to_rgba(const float* __restrict__ rgb, size_t n, F4* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { F4 t; t.x = rgb[3 * i]; t.y = rgb[3 * i + 1]; t.z = rgb[3 * i + 2]; t.w = 0.0f; out[i] = t; }
+}
+
 static int build_env_light(FtnScene* s, const FtnLight& fl, LightData* out) {
     EnvLightData& e = out->env;
     e.w = fl.width; e.h = fl.height;
@@ -381,16 +412,20 @@ static int build_env_light(FtnScene* s, const FtnLight& fl, LightData* out) {
     e.l2w = to_m4(fl.light_to_world); e.w2l = to_m4(fl.world_to_light);
     e.world_radius = 0.0f; e.world_center[0] = e.world_center[1] = e.world_center[2] = 0.0f;
     const size_t n = (size_t)fl.width * fl.height;
-    std::vector<F4> tex(n);
-    for (size_t i = 0; i < n; ++i) { tex[i].x = fl.texels[3 * i]; tex[i].y = fl.texels[3 * i + 1]; tex[i].z = fl.texels[3 * i + 2]; tex[i].w = 0.0f; }
-    F4* d_tex; float *d_func, *d_cdf, *d_int, *d_mcdf;
-    FTN_TRY(upload(&d_tex, tex.data(), n));
+    // the caller's RGB floats go up as they are (25 MB for 2048x1024) and are widened to RGBA texels on the device
+    F4* d_tex; float *d_rgb, *d_func, *d_cdf, *d_int, *d_mcdf;
+    FTN_TRY(upload(&d_rgb, fl.texels, 3 * n));
+    cudaError_t me = scene_malloc(&d_tex, n * sizeof(F4));
+    if (me != cudaSuccess) { scene_free(d_rgb); return cuda_fail(me, "cudaMalloc env texels", __FILE__, __LINE__); }
     s->owned.push_back(d_tex);
+    k_rgb_to_rgba<<<(unsigned)((n + 255) / 256), 256>>>(d_rgb, n, d_tex);
+    FTN_LAUNCHED();
+    scene_free(d_rgb);   // ordered after the kernel on the same (legacy) stream
     e.texels = d_tex;
-    FTN_CUDA(cudaMalloc(&d_func, n * sizeof(float))); s->owned.push_back(d_func);
-    FTN_CUDA(cudaMalloc(&d_cdf, (size_t)e.nv * (e.nu + 1) * sizeof(float))); s->owned.push_back(d_cdf);
-    FTN_CUDA(cudaMalloc(&d_int, (size_t)e.nv * sizeof(float))); s->owned.push_back(d_int);
-    FTN_CUDA(cudaMalloc(&d_mcdf, (size_t)(e.nv + 1) * sizeof(float))); s->owned.push_back(d_mcdf);
+    FTN_CUDA(scene_malloc(&d_func, n * sizeof(float))); s->owned.push_back(d_func);
+    FTN_CUDA(scene_malloc(&d_cdf, (size_t)e.nv * (e.nu + 1) * sizeof(float))); s->owned.push_back(d_cdf);
+    FTN_CUDA(scene_malloc(&d_int, (size_t)e.nv * sizeof(float))); s->owned.push_back(d_int);
+    FTN_CUDA(scene_malloc(&d_mcdf, (size_t)(e.nv + 1) * sizeof(float))); s->owned.push_back(d_mcdf);
     e.cond_func = d_func; e.cond_cdf = d_cdf; e.cond_integral = d_int; e.marg_cdf = d_mcdf;
     k_env_func<<<(unsigned)((n + 255) / 256), 256>>>(e, d_func);
     FTN_LAUNCHED();
@@ -398,7 +433,7 @@ static int build_env_light(FtnScene* s, const FtnLight& fl, LightData* out) {
     FTN_LAUNCHED();
     // marginal = Distribution1D::new(row integrals): one more "row" of length nv
     float* d_mint;
-    FTN_CUDA(cudaMalloc(&d_mint, sizeof(float))); s->owned.push_back(d_mint);
+    FTN_CUDA(scene_malloc(&d_mint, sizeof(float))); s->owned.push_back(d_mint);
     k_env_row_cdf<<<1, 128>>>(d_int, e.nv, 1, d_mcdf, d_mint);
     FTN_LAUNCHED();
     FTN_CUDA(cudaMemcpy(&e.marg_integral, d_mint, sizeof(float), cudaMemcpyDeviceToHost));
@@ -523,7 +558,7 @@ int scene_create(const FtnSceneDesc* d, FtnScene** out) {
     }
     if ((rc = upload(&s->d_spheres, s->h_spheres.data(), s->h_spheres.size())) != FTN_OK) return bail(rc);
     if ((rc = upload(&s->d_lights, s->h_lights.data(), s->h_lights.size())) != FTN_OK) return bail(rc);
-    cudaError_t e = cudaMalloc(&s->d_work, sizeof(unsigned long long));
+    cudaError_t e = scene_malloc(&s->d_work, sizeof(unsigned long long));
     if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc work counter", __FILE__, __LINE__));
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return bail(cuda_fail(e, "scene_create sync", __FILE__, __LINE__));
@@ -533,10 +568,15 @@ int scene_create(const FtnSceneDesc* d, FtnScene** out) {
 
 int scene_destroy(FtnScene* s) {
     if (!s) return FTN_OK;
-    cudaFree(s->d_pos); cudaFree(s->d_nrm); cudaFree(s->d_uv); cudaFree(s->d_idx);
-    cudaFree(s->d_meshes); cudaFree(s->d_materials); cudaFree(s->d_spheres); cudaFree(s->d_lights);
-    cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_codes); cudaFree(s->d_order); cudaFree(s->d_work);
-    for (void* p : s->owned) cudaFree(p);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != s->device) cudaSetDevice(s->device);
+    cudaDeviceSynchronize();   // the frees below are ordered on the legacy stream only; nothing may still read the scene
+    scene_free(s->d_pos); scene_free(s->d_nrm); scene_free(s->d_uv); scene_free(s->d_idx);
+    scene_free(s->d_meshes); scene_free(s->d_materials); scene_free(s->d_spheres); scene_free(s->d_lights);
+    scene_free(s->d_nodes); scene_free(s->d_tris); scene_free(s->d_codes); scene_free(s->d_order); scene_free(s->d_work);
+    for (void* p : s->owned) scene_free(p);
+    if (cur != s->device) cudaSetDevice(cur);
     delete s;
     return FTN_OK;
 }
@@ -608,8 +648,8 @@ int bvh_build(FtnScene* s) {
             if ((rc = dalloc((void**)&tri_hi, (size_t)n * sizeof(F4))) != FTN_OK) break;
             if ((rc = dalloc((void**)&keys, (size_t)n * 4)) != FTN_OK) break;
             cudaError_t e;
-            if (!s->d_codes && (e = cudaMalloc(&s->d_codes, (size_t)n * 4)) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc codes", __FILE__, __LINE__); break; }
-            if (!s->d_order && (e = cudaMalloc(&s->d_order, (size_t)n * 4)) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc order", __FILE__, __LINE__); break; }
+            if (!s->d_codes && (e = scene_malloc(&s->d_codes, (size_t)n * 4)) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc codes", __FILE__, __LINE__); break; }
+            if (!s->d_order && (e = scene_malloc(&s->d_order, (size_t)n * 4)) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc order", __FILE__, __LINE__); break; }
             k_init_bounds<<<1, 32, 0, st>>>(d_gb); count_launch();
             k_tri_bounds<<<gb256, 256, 0, st>>>(s->d_pos, s->d_idx, n, tri_lo, tri_hi, d_gb); count_launch();
             k_morton<<<gb256, 256, 0, st>>>(tri_lo, tri_hi, n, d_gb, s->d_codes, keys, s->d_order); count_launch();
@@ -619,11 +659,11 @@ int bvh_build(FtnScene* s) {
             if ((rc = dalloc((void**)&leaf_lo, (size_t)n * sizeof(F4))) != FTN_OK) break;
             if ((rc = dalloc((void**)&leaf_hi, (size_t)n * sizeof(F4))) != FTN_OK) break;
             k_gather_leaf_boxes<<<gb256, 256, 0, st>>>(tri_lo, tri_hi, s->d_order, n, leaf_lo, leaf_hi); count_launch();
-            if (!s->d_tris && (e = cudaMalloc(&s->d_tris, (size_t)n * 3 * sizeof(F4))) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc tris", __FILE__, __LINE__); break; }
+            if (!s->d_tris && (e = scene_malloc(&s->d_tris, (size_t)n * 3 * sizeof(F4))) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc tris", __FILE__, __LINE__); break; }
             const uint32_t* final_order = s->d_order;   // leaf order of the emitted tree; PLOC: depth-first order of its tree
             if (n <= (uint32_t)FTN_LEAF_MAX) {
                 k_gather_tris<<<gb256, 256, 0, st>>>(s->d_pos, s->d_idx, final_order, n, s->d_meshes, s->n_meshes, s->d_tris); count_launch();
-                if (!s->d_nodes && (e = cudaMalloc(&s->d_nodes, FTN_NODE_F4 * sizeof(F4))) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc nodes", __FILE__, __LINE__); break; }
+                if (!s->d_nodes && (e = scene_malloc(&s->d_nodes, FTN_NODE_F4 * sizeof(F4))) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc nodes", __FILE__, __LINE__); break; }
                 k_lbvh_emit_single<<<1, 32, 0, st>>>(n, d_gb, s->d_nodes); count_launch();
                 s->n_nodes = 1;
             } else {
@@ -716,8 +756,8 @@ int bvh_build(FtnScene* s) {
                 if ((e = cudaMemcpyAsync(&last_idx, new_index + ni - 1, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { rc = cuda_fail(e, "read scan", __FILE__, __LINE__); break; }
                 if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { rc = cuda_fail(e, "lbvh sync", __FILE__, __LINE__); break; }
                 s->n_nodes = last_idx + last_flag;
-                if (s->d_nodes) { cudaFree(s->d_nodes); s->d_nodes = nullptr; }
-                if ((e = cudaMalloc(&s->d_nodes, (size_t)s->n_nodes * FTN_NODE_F4 * sizeof(F4))) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc nodes", __FILE__, __LINE__); break; }
+                if (s->d_nodes) { scene_free(s->d_nodes); s->d_nodes = nullptr; }
+                if ((e = scene_malloc(&s->d_nodes, (size_t)s->n_nodes * FTN_NODE_F4 * sizeof(F4))) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc nodes", __FILE__, __LINE__); break; }
                 k_lbvh_emit<<<gi, 256, 0, st>>>((int)n, a, leaf_lo, leaf_hi, survive, is_record, new_index, s->d_nodes); count_launch();
             }
             if ((e = cudaGetLastError()) != cudaSuccess) { rc = cuda_fail(e, "emit kernels", __FILE__, __LINE__); break; }
