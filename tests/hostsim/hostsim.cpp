@@ -453,6 +453,18 @@ SIM_API int sim_kat_env(const SimScene* s, const float u[2], float out[11]) {
     const V3 le = env_emitted(e, wi); out[8] = le.x; out[9] = le.y; out[10] = le.z;
     return FTN_OK;
 }
+// the device's mip_lookup_trilinear on a pyramid in the ABI's layout; (dsdx, 0, 0, 0) differentials give width = 2 |dsdx|
+SIM_API int sim_kat_mipmap_lookup(const float* pyramid, int w, int h, int levels, int wrap, float s, float t, float width, float out[3]) {
+    FtnMaterial fm; std::memset(&fm, 0, sizeof(fm));
+    fm.image = pyramid; fm.image_width = w; fm.image_height = h; fm.image_levels = levels; fm.image_wrap = wrap;
+    std::vector<F4> texels;
+    if (!pack_image_pyramid(fm, &texels)) return FTN_ERR_INVALID_ARGUMENT;
+    MaterialData md; std::memset(&md, 0, sizeof(md));
+    md.image = texels.data(); md.img_w = w; md.img_h = h; md.img_levels = levels; md.img_wrap = wrap;
+    const V3 v = mip_lookup_trilinear(md, s, t, 0.5f * width, 0.0f, 0.0f, 0.0f);
+    out[0] = v.x; out[1] = v.y; out[2] = v.z;
+    return FTN_OK;
+}
 SIM_API float sim_kat_counter_uniform(uint64_t seed, uint64_t sample_index, uint32_t dim) {
     return sampler_uniform(sampler_sample_key(sampler_seed_key(seed), sample_index), dim);
 }

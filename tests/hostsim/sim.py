@@ -36,6 +36,7 @@ def library():
             "sim_kat_camera_ray": (None, [P(A.FtnCamera), f32, f32, f32, f32, f32, P(A.FtnRay)]),
             "sim_kat_offset_ray_origin": (None, [P(f32), P(f32), P(f32), P(f32), P(f32)]),
             "sim_kat_bsdf": (None, [P(A.FtnMaterial), P(f32), P(f32), P(f32), P(f32)]),
+            "sim_kat_mipmap_lookup": (C.c_int, [P(f32), C.c_int, C.c_int, C.c_int, C.c_int, f32, f32, f32, P(f32)]),
             "sim_kat_env": (C.c_int, [C.c_void_p, P(f32), P(f32)]),
             "sim_kat_counter_uniform": (f32, [u64, u64, u32]),
             "sim_kat_gamma": (f32, [C.c_int]),

@@ -346,3 +346,19 @@ def test_ploc_depth_fallback_to_radix_tree(sim_backend, orc_backend, rounded_cub
     assert a.stats()["bvh_nodes"] == 1355          # the radix tree's node count for this mesh
     parity.check_morton(a, b)
     parity.check_ray_batch(a, b, parity.random_ray_batch(20000, 15), "fallback")
+
+
+# ---- the device's MIPMap lookup (ftn_shade.cuh mip_lookup_trilinear) against the oracle's (mipmap.rs:245-311) ------
+@pytest.mark.parametrize("wrap", ["repeat", "black", "clamp"])
+def test_mipmap_lookup_matches_oracle(sim, oracle, wrap):
+    rng = np.random.default_rng(17)
+    for shape in ((6, 8), (16, 16), (5, 33), (1, 1)):
+        mp = api.MIPMap(rng.random(shape + (3,)).astype(np.float32), wrap)
+        ptr = mp.packed.ctypes.data_as(C.POINTER(C.c_float))
+        for _ in range(400):
+            s, t = (float(x) for x in rng.uniform(-1.5, 2.5, 2))
+            w = float(rng.choice([0.0, 1e-9, 1e-3, 0.05, 0.13, 0.26, 0.51, 0.99, 1.0, 2.0, 7.0]))
+            a, b = (C.c_float * 3)(), (C.c_float * 3)()
+            assert sim.library().sim_kat_mipmap_lookup(ptr, mp.width, mp.height, len(mp.levels), mp.wrap, s, t, w, a) == 0
+            assert oracle.library().orc_kat_mipmap_lookup(ptr, mp.width, mp.height, len(mp.levels), mp.wrap, s, t, w, b) == 0
+            assert np.allclose(np.array(list(a)), np.array(list(b)), rtol=1e-5, atol=1e-7), (shape, s, t, w, list(a), list(b))
