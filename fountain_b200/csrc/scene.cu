@@ -301,6 +301,41 @@ k_env_row_cdf(const float* __restrict__ func, int nu, int nv, float* __restrict_
     if (v < nv) dist_row_build(func + (size_t)v * nu, nu, cdf + (size_t)v * (nu + 1), integral + v);
 }
 
+// The conditional rows of an environment map (2048 rows of 1024 for C4): the running sum of a row is sequential by
+// definition (dist_row_build), so one LANE owns one row, and the warp moves 32x32 tiles through shared memory so that
+// the global loads and stores are coalesced (one thread per row with strided accesses took 0.9 ms for 8 MB).  Same
+// operations in the same order as dist_row_build: the tables are bit-identical.
+__global__ void __launch_bounds__(128)
+k_env_rows_running_sum(const float* __restrict__ func, int nu, int nv, float* __restrict__ cdf, float* __restrict__ integral) {
+    __shared__ float tile[4][32][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = (blockIdx.x * 4 + warp) * 32;
+    if (row0 >= nv) return;   // warp-uniform
+    float (*t)[33] = tile[warp];
+    const float nf = (float)nu;
+    float run = 0.0f;
+    for (int k0 = 0; k0 < nu; k0 += 32) {
+        const int col = k0 + lane;
+        for (int r = 0; r < 32; ++r) t[r][lane] = (row0 + r < nv && col < nu) ? func[(size_t)(row0 + r) * nu + col] : 0.0f;
+        __syncwarp();
+        const int n_cols = min(32, nu - k0);
+        for (int j = 0; j < n_cols; ++j) { run = rn_add(run, rn_div(t[lane][j], nf)); t[lane][j] = run; }
+        __syncwarp();
+        for (int r = 0; r < 32; ++r) if (row0 + r < nv && col < nu) cdf[(size_t)(row0 + r) * (nu + 1) + col + 1] = t[r][lane];
+        __syncwarp();
+    }
+    if (row0 + lane < nv) { integral[row0 + lane] = run; cdf[(size_t)(row0 + lane) * (nu + 1)] = 0.0f; }
+}
+__global__ void __launch_bounds__(256)
+k_env_rows_normalise(int nu, int nv, const float* __restrict__ integral, float* __restrict__ cdf) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= (size_t)nv * (nu + 1)) return;
+    const int row = (int)(k / (size_t)(nu + 1)), i = (int)(k % (size_t)(nu + 1));
+    if (i == 0) return;
+    const float total = integral[row];
+    cdf[k] = (total == 0.0f) ? rn_div((float)i, (float)nu) : rn_div(cdf[k], total);
+}
+
 static DeviceArena g_arena[FTN_MAX_DEVICES];
 DeviceArena& device_arena(int device) { return g_arena[(device >= 0 && device < FTN_MAX_DEVICES) ? device : 0]; }
 int DeviceArena::reserve(int which, size_t need, const char* what, void** out) {
@@ -429,7 +464,9 @@ static int build_env_light(FtnScene* s, const FtnLight& fl, LightData* out) {
     e.cond_func = d_func; e.cond_cdf = d_cdf; e.cond_integral = d_int; e.marg_cdf = d_mcdf;
     k_env_func<<<(unsigned)((n + 255) / 256), 256>>>(e, d_func);
     FTN_LAUNCHED();
-    k_env_row_cdf<<<(e.nv + 127) / 128, 128>>>(d_func, e.nu, e.nv, d_cdf, d_int);
+    k_env_rows_running_sum<<<(e.nv + 127) / 128, 128>>>(d_func, e.nu, e.nv, d_cdf, d_int);
+    FTN_LAUNCHED();
+    k_env_rows_normalise<<<(unsigned)(((size_t)e.nv * (e.nu + 1) + 255) / 256), 256>>>(e.nu, e.nv, d_int, d_cdf);
     FTN_LAUNCHED();
     // marginal = Distribution1D::new(row integrals): one more "row" of length nv
     float* d_mint;

@@ -73,11 +73,12 @@ def test_c2_statistical_parity_with_reference_stream(gpu_backend, orc_backend):
     assert abs(g.mean() - r.mean()) / r.mean() < 0.005
 
 
-def test_envmap_thin_lens_metal_matches_oracle(gpu_backend, orc_backend):
+@pytest.mark.parametrize("env_size", [(128, 64), (50, 37), (33, 130)])
+def test_envmap_thin_lens_metal_matches_oracle(gpu_backend, orc_backend, env_size):
     """Config-C4-style content at test size: image env map importance sampling, TR conductor,
-    thin lens."""
+    thin lens.  The odd sizes exercise the partial 32x32 tiles of the distribution-table kernel."""
     def build(backend):
-        env = api.InfiniteAreaLight.new_envmap(scenes.sky_sun_envmap(128, 64, peak=50.0), Transform.rotate(20, (0, 0, 1)))
+        env = api.InfiniteAreaLight.new_envmap(scenes.sky_sun_envmap(env_size[0], env_size[1], peak=50.0), Transform.rotate(20, (0, 0, 1)))
         scene, camera, film = scenes.rounded_cube_scene(backend=backend, resolution=(72, 48), light=env,
                                                         material=api.MetalMaterial((0.2, 0.92, 1.1), (3.9, 2.45, 2.14), roughness=0.3))
         camera = api.PerspectiveCamera(camera.camera_to_world, (72, 48), fov=40.0, lens_radius=0.5, focal_dist=32.0)
