@@ -652,10 +652,23 @@ class Film:
         if nbytes and self.backend.has("host_alloc"):
             self._pinned = _PINNED.take(self.backend, nbytes)
             buf = (C.c_float * (self.height * self.width * 4)).from_address(self._pinned)
-            self.pixels = np.frombuffer(buf, dtype=np.float32).reshape(self.height, self.width, 4)
-            self.pixels[...] = 0.0
+            self._pixels = np.frombuffer(buf, dtype=np.float32).reshape(self.height, self.width, 4)
+            self._stale = True     # a recycled buffer: zeroed on first read unless a render overwrote it first
         else:
-            self.pixels = np.zeros((self.height, self.width, 4), dtype=np.float32)
+            self._pixels = np.zeros((self.height, self.width, 4), dtype=np.float32)
+            self._stale = False
+
+    @property
+    def pixels(self):
+        if self._stale:
+            self._pixels[...] = 0.0
+            self._stale = False
+        return self._pixels
+
+    @pixels.setter
+    def pixels(self, value):
+        self._pixels = value
+        self._stale = False
 
     def __del__(self):
         try:
@@ -743,10 +756,11 @@ class SamplerIntegrator:
         """Renders into film.pixels.  Raises FountainError(FTN_ERR_NAN_RADIANCE) where the
         reference panics in check_radiance (integrator/mod.rs:285)."""
         st = A.FtnStats()
-        out = film.pixels          # ftn_render overwrites every pixel of the cropped bounds
+        out = film._pixels         # ftn_render overwrites every pixel of the cropped bounds: no need to clear a recycled buffer first
         cam, f, s, it = self.camera.to_abi(), film.to_abi(), sampler.to_abi(sample_begin, sample_stride), self.radiance.to_abi()
         scene.backend.call("render", scene.handle, C.byref(cam), C.byref(f), C.byref(s), C.byref(it),
                            out.ctypes.data_as(C.POINTER(A.FtnPixel)), C.byref(st))
+        film._stale = False        # only after success: a failed render leaves the buffer to be cleared on first read
         self.last_stats = st.as_dict()
         return self.last_stats
 
