@@ -302,11 +302,14 @@ class MirrorMaterial:
     type = A.FTN_MATERIAL_MIRROR
 
     def __init__(self, kr=0.9):
-        self.kr = _spectrum(kr)
+        self.kr = kr if isinstance(kr, _TEXTURES) else _spectrum(kr)     # Kr may be textured (mirror.rs:23)
 
     def fill(self, m):
         m.type = self.type
-        m.kr[:] = self.kr.tolist()
+        if isinstance(self.kr, _TEXTURES):
+            _fill_kd(m, self.kr)             # the texture slot of the ABI serves Kd (matte, plastic) or Kr (mirror)
+        else:
+            m.kr[:] = self.kr.tolist()
 
 
 class DiffuseAreaLight:

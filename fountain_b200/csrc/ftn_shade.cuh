@@ -477,8 +477,9 @@ template <int MAT> FTN_HD void material_bsdf(const MaterialData& m, float u, flo
         const V3 kd0 = material_kd(m, u, v, td);
         const V3 r = V3(clampf(kd0.x, 0.0f, FTN_INF), clampf(kd0.y, 0.0f, FTN_INF), clampf(kd0.z, 0.0f, FTN_INF));
         if (!is_black(r)) { b->on0 = true; b->l0.r = r; b->l0.ax = m.alpha_x; b->l0.ay = m.alpha_y; }
-    } else if (MAT == FTN_MATERIAL_MIRROR) {   // mirror.rs:21-30; Kr is carried in MaterialData::kd
-        const V3 r = V3(clampf(m.kd[0], 0.0f, FTN_INF), clampf(m.kd[1], 0.0f, FTN_INF), clampf(m.kd[2], 0.0f, FTN_INF));
+    } else if (MAT == FTN_MATERIAL_MIRROR) {   // mirror.rs:21-30; Kr (constant or textured) is carried in MaterialData::kd and its texture fields
+        const V3 kr0 = material_kd(m, u, v, td);
+        const V3 r = V3(clampf(kr0.x, 0.0f, FTN_INF), clampf(kr0.y, 0.0f, FTN_INF), clampf(kr0.z, 0.0f, FTN_INF));
         if (!is_black(r)) { b->on0 = true; b->l0.r = r; }
     } else {
         const V3 kd = material_kd(m, u, v, td), ks = V3(m.ks[0], m.ks[1], m.ks[2]);

@@ -459,7 +459,11 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
                 else k_shade<Q_MAT2><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT2], q, counts, d_err);
                 FTN_LAUNCHED();
             }
-            if (s->material_present[3]) { k_shade<Q_MAT3><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT3], q, counts, d_err); FTN_LAUNCHED(); }
+            if (s->material_present[3]) {
+                if (s->has_image_texture) k_shade<Q_MAT3, true><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT3], q, counts, d_err);
+                else k_shade<Q_MAT3><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT3], q, counts, d_err);
+                FTN_LAUNCHED();
+            }
             if (s->material_present[4]) {
                 if (s->has_image_texture) k_shade<Q_MAT4, true><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT4], q, counts, d_err);
                 else k_shade<Q_MAT4><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT4], q, counts, d_err);

@@ -347,3 +347,15 @@ def image_texture_scene(backend=None, resolution=(48, 48), wrap="repeat", materi
     camera = api.PerspectiveCamera(cam_to_world, resolution, fov=50.0, lens_radius=lens_radius, focal_dist=9.0)
     film = api.Film(resolution, backend=backend)
     return scene, camera, film
+
+
+def textured_mirror_probe(backend=None, xz=(0.5, 0.5), texture=None, resolution=(5, 5)):
+    """A mirror quad in the plane y = 2 whose uv are its world (x, z), Kr through `texture`, under a uniform
+    environment of radiance 1; a narrow camera looks at (x, 2, z) head-on, so every pixel reads Kr(x, z)."""
+    v = np.array([[-6, 2, -6], [6, 2, -6], [6, 2, 6], [-6, 2, 6]], np.float32)
+    mesh = api.TriangleMesh(Transform.identity(), np.array([0, 1, 2, 0, 2, 3], np.uint32), v, tex_coords=v[:, [0, 2]].copy())
+    tex = texture if texture is not None else api.Checkerboard2DTexture((0.8, 0.7, 0.6), (0.3, 0.2, 0.1), api.UVMapping(1.0, 1.0, 0.0, 0.0))
+    scene = api.Scene([api.GeometricPrimitive(mesh, api.MirrorMaterial(tex))], [api.InfiniteAreaLight.new_uniform(1.0)], backend=backend)
+    camera = api.PerspectiveCamera(Transform.look_at((xz[0], -28.0, xz[1]), (xz[0], 2.0, xz[1]), (0, 0, 1)).inverse(), resolution, fov=0.5)
+    film = api.Film(resolution, backend=backend)
+    return scene, camera, film

@@ -117,7 +117,8 @@ typedef enum FtnImageWrap {
 } FtnImageWrap;
 #define FTN_MAX_MIP_LEVELS 16
 
-/* Materials with constant parameters; Kd of matte / plastic may carry a texture (kd_texture). */
+/* Materials with constant parameters, except that Kd of matte / plastic and Kr of mirror may carry a texture
+ * (kd_texture and the fields after it; mirror.rs:21-30 evaluates Kr like matte.rs:37 evaluates Kd). */
 typedef struct FtnMaterial {
     int32_t type;            /* FtnMaterialType */
     float kd[3];             /* matte Kd / plastic Kd */
@@ -128,7 +129,7 @@ typedef struct FtnMaterial {
     float v_roughness;
     int32_t remap_roughness; /* constructors.rs:227 default true */
     float kr[3];             /* mirror Kr (constructors.rs:207-210 default 0.9) */
-    int32_t kd_texture;      /* FtnTextureType of Kd (matte, plastic) */
+    int32_t kd_texture;      /* FtnTextureType of Kd (matte, plastic) or of Kr (mirror) */
     float tex1[3], tex2[3];  /* checkerboard: the two constant sub-textures (constructors.rs:276-287) */
     float uv_scale[2];       /* UVMapping uscale, vscale (constructors.rs:251-252, default 1) */
     float uv_delta[2];       /* UVMapping udelta, vdelta (default 0) */

@@ -561,11 +561,12 @@ struct PlasticMaterial : Material {      // material/plastic.rs; Kd = Ks = .25, 
 };
 
 struct MirrorMaterial : Material {       // material/mirror.rs; Kr default 0.9 (constructors.rs:207-210)
-    Spectrum kr;
-    explicit MirrorMaterial(Spectrum kr_ = Spectrum(0.9f)) : kr(kr_) {}
+    SpectrumTexture kr;                  // constant or textured (mirror.rs:23)
+    explicit MirrorMaterial(SpectrumTexture kr_ = SpectrumTexture(0.9f)) : kr(kr_) {}
     void fill(FtnMaterial& m) const override {
         m.type = FTN_MATERIAL_MIRROR;
-        m.kr[0] = kr.r; m.kr[1] = kr.g; m.kr[2] = kr.b;
+        kr.fill_kd(m);                   // the ABI's texture slot serves Kd (matte, plastic) or Kr (mirror)
+        m.kr[0] = kr.value.r; m.kr[1] = kr.value.g; m.kr[2] = kr.value.b;
     }
 };
 

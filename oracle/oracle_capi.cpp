@@ -75,7 +75,7 @@ ORC_API int orc_scene_create(const FtnSceneDesc* d, OrcScene** out) {
         mm.kr = Spectrum(m.kr[0], m.kr[1], m.kr[2]); mm.sigma = m.sigma;
         mm.kd_texture = m.kd_texture; mm.tex1 = Spectrum(m.tex1[0], m.tex1[1], m.tex1[2]); mm.tex2 = Spectrum(m.tex2[0], m.tex2[1], m.tex2[2]);
         for (int c = 0; c < 2; ++c) { mm.uv_scale[c] = m.uv_scale[c]; mm.uv_delta[c] = m.uv_delta[c]; }
-        if (m.kd_texture == FTN_TEXTURE_IMAGE && (m.type == FTN_MATERIAL_MATTE || m.type == FTN_MATERIAL_PLASTIC)) {
+        if (m.kd_texture == FTN_TEXTURE_IMAGE && (m.type == FTN_MATERIAL_MATTE || m.type == FTN_MATERIAL_PLASTIC || m.type == FTN_MATERIAL_MIRROR)) {
             mm.image = make_mipmap(m.image, m.image_width, m.image_height, m.image_levels, m.image_wrap);
             if (!mm.image) { delete os; return fail(FTN_ERR_INVALID_ARGUMENT, "image texture: bad pyramid description"); }
         }

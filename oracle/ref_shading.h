@@ -347,7 +347,7 @@ struct Bsdf {
 // Kd through its texture: ConstantTexture (texture/mod.rs:34-42), ImageTexture (image.rs), Checkerboard2DTexture with
 // AAMethod::None (checkerboard.rs:50-64) or UVTexture (uv.rs:18-23), via UVMapping (mapping.rs:40-52).
 inline Spectrum evaluate_kd(const Material& m, const SurfaceInteraction& si) {
-    if (m.kd_texture == 0) return m.kd;
+    if (m.kd_texture == 0) return m.type == 3 ? m.kr : m.kd;   // the mirror's textured parameter is Kr (mirror.rs:23)
     Float s = m.uv_scale[0] * si.uv[0] + m.uv_delta[0], t = m.uv_scale[1] * si.uv[1] + m.uv_delta[1];
     if (m.kd_texture == 1) return (((int)std::floor(s) + (int)std::floor(t)) % 2 == 0) ? m.tex1 : m.tex2;
     if (m.kd_texture == 3) {   // ImageTexture::evaluate, image.rs:30-33, with UVMapping's dst_dx / dst_dy (mapping.rs:43-44)
@@ -380,7 +380,7 @@ inline void compute_scattering_functions(const Material& m, const SurfaceInterac
         b.fresnel = 0; b.eta_i = Spectrum(1.0f); b.eta_t = m.eta; b.k = m.k;
         bsdf->add(b);
     } else if (m.type == 3) {   // mirror.rs:21-30
-        Spectrum r = m.kr.clamp_positive();
+        Spectrum r = evaluate_kd(m, si).clamp_positive();
         if (!r.is_black()) { BxDF b{}; b.kind = 2; b.r = r; bsdf->add(b); }
     } else {   // plastic.rs:24-48
         Spectrum kd = evaluate_kd(m, si);

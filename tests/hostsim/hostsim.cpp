@@ -69,7 +69,7 @@ SIM_API int sim_scene_create(const FtnSceneDesc* d, SimScene** out) {
         for (int c = 0; c < 3; ++c) { md.kd[c] = fm.kd[c]; md.ks[c] = fm.ks[c]; md.eta[c] = fm.eta[c]; md.k[c] = fm.k[c]; }
         float ur = fm.u_roughness, vr = fm.v_roughness;
         if (fm.type == FTN_MATERIAL_MIRROR) for (int c = 0; c < 3; ++c) md.kd[c] = fm.kr[c];   // Kr travels in the kd slot
-        md.kd_texture = (fm.type == FTN_MATERIAL_MATTE || fm.type == FTN_MATERIAL_PLASTIC) ? fm.kd_texture : 0;
+        md.kd_texture = (fm.type == FTN_MATERIAL_MATTE || fm.type == FTN_MATERIAL_PLASTIC || fm.type == FTN_MATERIAL_MIRROR) ? fm.kd_texture : 0;
         if (fm.type == FTN_MATERIAL_MATTE) {   // matte.rs:42-49: sigma clamped to [0, 90] degrees; != 0 -> OrenNayar::new (reflection/mod.rs:259-267)
             const float sigma = std::fmin(std::fmax(fm.sigma, 0.0f), 90.0f);
             if (sigma != 0.0f) {

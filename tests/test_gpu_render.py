@@ -278,3 +278,8 @@ def test_image_texture_bad_pyramid_is_rejected(gpu_backend):
     tex = api.ImageTexture(mp)
     with pytest.raises(api.FountainError):
         scenes.textured_floor_scene(backend=gpu_backend, texture=tex)
+
+
+def test_mirror_textured_kr_closed_form(gpu_backend):
+    from tests.test_oracle_render import mirror_kr_closed_form
+    mirror_kr_closed_form(gpu_backend)

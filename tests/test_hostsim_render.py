@@ -188,3 +188,8 @@ def test_image_texture_level_selection_closed_form_hostsim(sim_backend):
         api.SamplerIntegrator(camera, api.DirectLightingIntegrator(1)).render_parallel(scene, film, api.RandomSampler.new_with_seed(4, 0))
         level = min(max(expected_mip_level(len(mp.levels), uscale, 0.5, 5, 30.0, 4), 0.0), len(mp.levels) - 1.0)
         assert np.allclose(film.into_spectrum_buffer()[0], (0.1 + 0.1 * level) / np.pi * 3.0, rtol=2e-3), uscale
+
+
+def test_mirror_textured_kr_closed_form(sim_backend):
+    from tests.test_oracle_render import mirror_kr_closed_form
+    mirror_kr_closed_form(sim_backend)

@@ -296,3 +296,25 @@ def test_image_texture_bad_pyramid_is_rejected(orc_backend):
     mp.levels = mp.levels[:-1]          # one level short of 1 + floor(log2(max(w, h)))
     with pytest.raises(api.FountainError):
         scenes.textured_floor_scene(backend=orc_backend, texture=api.ImageTexture(mp))
+
+
+# ---- textured Kr (mirror.rs:23 evaluates its Kr texture like matte.rs:37 its Kd) -----------------------------------
+def mirror_kr_closed_form(backend):
+    t1, t2 = np.array([0.8, 0.7, 0.6]), np.array([0.3, 0.2, 0.1])
+    for xz, want in (((0.5, 0.5), t1), ((1.5, 0.5), t2), ((-0.5, 0.5), t2), ((-0.5, -0.5), t1)):
+        for integ in (api.PathIntegrator(3, 1.0), api.DirectLightingIntegrator(3)):
+            scene, camera, film = scenes.textured_mirror_probe(backend=backend, xz=xz)
+            api.SamplerIntegrator(camera, integ).render_parallel(scene, film, api.RandomSampler.new_with_seed(2, 0))
+            assert np.allclose(film.into_spectrum_buffer()[0], want[None, :], rtol=1e-5), (xz, type(integ).__name__)
+    # an image texture as Kr: level 0 of a ramp, bilinear (the footprint of the narrow camera is far below a texel)
+    n = 16
+    ramp = np.zeros((n, n, 3), np.float32)
+    ramp[..., 0] = (np.arange(n)[None, :] + 0.5) / n; ramp[..., 1] = (np.arange(n)[:, None] + 0.5) / n; ramp[..., 2] = 0.5
+    tex = api.ImageTexture(api.MIPMap(ramp, "clamp"), api.UVMapping(1.0 / 12.0, 1.0 / 12.0, 0.5, 0.5))
+    scene, camera, film = scenes.textured_mirror_probe(backend=backend, xz=(2.0, -3.0), texture=tex)
+    api.SamplerIntegrator(camera, api.PathIntegrator(3, 1.0)).render_parallel(scene, film, api.RandomSampler.new_with_seed(2, 0))
+    assert np.allclose(film.into_spectrum_buffer()[0].mean(axis=0), [2.0 / 12 + 0.5, -3.0 / 12 + 0.5, 0.5], rtol=3e-3)
+
+
+def test_mirror_textured_kr_closed_form(orc_backend):
+    mirror_kr_closed_form(orc_backend)
