@@ -283,3 +283,26 @@ def test_image_texture_bad_pyramid_is_rejected(gpu_backend):
 def test_mirror_textured_kr_closed_form(gpu_backend):
     from tests.test_oracle_render import mirror_kr_closed_form
     mirror_kr_closed_form(gpu_backend)
+
+
+def test_scene_pool_does_not_grow_and_is_released(gpu_backend):
+    """Scene buffers come from the device's stream-ordered pool: creating and destroying the same scene over and over
+    must reuse the pooled memory (no growth), results stay identical, and ftn_release_cached_memory gives it back."""
+    import torch
+    def cycle():
+        scene, camera = scenes.synthetic_mesh_scene(300, 150, backend=gpu_backend, resolution=(64, 64))    # 90 k triangles
+        hits = scene.intersect(scenes.primary_ray_batch(camera, (64, 64)))
+        scene.close()
+        return hits
+    first = cycle()
+    torch.cuda.synchronize()
+    free_after_first = torch.cuda.mem_get_info()[0]
+    for _ in range(20):
+        again = cycle()
+    torch.cuda.synchronize()
+    free_after_many = torch.cuda.mem_get_info()[0]
+    assert np.array_equal(first, again)
+    assert free_after_first - free_after_many < (32 << 20), (free_after_first, free_after_many)
+    gpu_backend.call("release_cached_memory")
+    assert torch.cuda.mem_get_info()[0] >= free_after_many
+    assert np.array_equal(first, cycle())
