@@ -18,7 +18,11 @@
 #if defined(__CUDACC__)
 #define FTN_HD __host__ __device__ __forceinline__
 #define FTN_D __device__ __forceinline__
-#define FTN_HD_COLD static __host__ __device__ __noinline__   // rare, register-hungry side paths kept out of the callers' budget
+#ifndef FTN_HD_COLD
+// side paths that only the kernel variants needing them instantiate (k_shade<.., IMG = true>); inlined there: a real
+// call cost 6-9 % on the textured scene (profiles/r01_ab_vote_ldg256.txt), and the plain variants never see the code
+#define FTN_HD_COLD static __host__ __device__ __forceinline__
+#endif
 #else
 #define FTN_HD inline
 #define FTN_D inline
