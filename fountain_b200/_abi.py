@@ -6,7 +6,9 @@ bound from ``oracle/orc.py`` -- never from this package.
 """
 import ctypes as C
 
-FTN_ABI_VERSION = 1
+FTN_ABI_VERSION = 2
+FTN_MAX_QUERIES_IN_FLIGHT = 64
+FTN_STATS_COUNT_TRAVERSAL, FTN_STATS_TIME_KERNELS = 1, 2
 FTN_NO_HIT = 0xFFFFFFFF
 
 FTN_OK = 0
@@ -43,7 +45,7 @@ class FtnHit(C.Structure):
 
 
 class FtnMeshDesc(C.Structure):
-    _fields_ = [("first_tri", u32), ("n_tris", u32), ("material_id", i32), ("flags", u32)]
+    _fields_ = [("first_tri", u32), ("n_tris", u32), ("material_id", i32), ("flags", u32), ("emissive", i32), ("emit", f32 * 3)]
 
 
 class FtnMaterial(C.Structure):
@@ -101,8 +103,9 @@ class FtnStats(C.Structure):
     _fields_ = [("camera_samples", u64), ("rays_closest", u64), ("rays_any", u64), ("node_visits", u64),
                 ("tri_tests", u64), ("kernel_launches", u64), ("device_seconds", C.c_double),
                 ("bvh_build_seconds", C.c_double), ("bvh_nodes", u32), ("bvh_node_bytes", u32),
-                ("bvh_tri_bytes", u32), ("reserved", u32), ("trace_seconds", C.c_double * 3),
-                ("trace_launches", u64 * 3), ("trace_rays", u64 * 3), ("trace_nodes", u64 * 3), ("trace_tris", u64 * 3)]
+                ("bvh_tri_bytes", u32), ("flags", u32), ("trace_seconds", C.c_double * 3),
+                ("trace_launches", u64 * 3), ("trace_rays", u64 * 3), ("trace_nodes", u64 * 3), ("trace_tris", u64 * 3),
+                ("shade_seconds", C.c_double), ("shade_launches", u64), ("morton_sort_seconds", C.c_double)]
 
     def as_dict(self):
         return {name: (list(getattr(self, name)) if hasattr(getattr(self, name), "__len__") else getattr(self, name))
@@ -132,6 +135,7 @@ PROTOTYPES = {
     "intersect_count_device": (C.c_int, [VOIDP, C.c_size_t, VOIDP, VOIDP, VOIDP, VOIDP]),
     "render": (C.c_int, [VOIDP, P(FtnCamera), P(FtnFilm), P(FtnSampler), P(FtnIntegrator), P(FtnPixel), P(FtnStats)]),
     "render_device": (C.c_int, [VOIDP, P(FtnCamera), P(FtnFilm), P(FtnSampler), P(FtnIntegrator), VOIDP, P(FtnStats), VOIDP]),
+    "render_multi": (C.c_int, [P(VOIDP), i32, P(FtnCamera), P(FtnFilm), P(FtnSampler), P(FtnIntegrator), P(FtnPixel), P(FtnStats)]),
     "film_to_rgb_device": (C.c_int, [C.c_size_t, VOIDP, VOIDP, VOIDP]),
     "film_pixel_count": (C.c_int, [P(FtnFilm), P(i32), P(i32)]),
     "release_cached_memory": (C.c_int, []),

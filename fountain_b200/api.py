@@ -22,6 +22,8 @@ Every compute call goes through a `Backend` (a bound shared library).  The defau
 the CUDA library; it raises if the extension or a GPU is missing -- there is no CPU path here.
 """
 import ctypes as C
+import weakref
+
 import numpy as np
 
 from . import _abi as A
@@ -404,8 +406,10 @@ class Scene:
     """scene/mod.rs:14-68.  `Scene(primitives, lights)` flattens everything into the SoA
     `FtnSceneDesc`, uploads it and builds the aggregate (BVH::build, bvh.rs:27)."""
 
-    def __init__(self, primitives, lights=(), backend=None, build=True):
+    def __init__(self, primitives, lights=(), backend=None, build=True, device=None):
         self.backend = backend or default_backend()
+        if device is not None:          # the scene lives on the CUDA device that is current when it is created
+            self.backend.call("set_device", int(device))
         self._handle = A.VOIDP()
         meshes = [p for p in primitives if isinstance(p.shape, TriangleMesh)]
         spheres = [p for p in primitives if isinstance(p.shape, Sphere)]
@@ -655,6 +659,9 @@ class Film:
         if nbytes and self.backend.has("host_alloc"):
             self._pinned = _PINNED.take(self.backend, nbytes)
             buf = (C.c_float * (self.height * self.width * 4)).from_address(self._pinned)
+            # the buffer goes back to the pool when the LAST array over it dies (every numpy view keeps `buf` alive
+            # through its base chain), not when the Film does: a caller may keep film.pixels beyond the Film
+            weakref.finalize(buf, _PINNED.give, self.backend, nbytes, self._pinned)
             self._pixels = np.frombuffer(buf, dtype=np.float32).reshape(self.height, self.width, 4)
             self._stale = True     # a recycled buffer: zeroed on first read unless a render overwrote it first
         else:
@@ -672,14 +679,6 @@ class Film:
     def pixels(self, value):
         self._pixels = value
         self._stale = False
-
-    def __del__(self):
-        try:
-            if self._pinned is not None:
-                _PINNED.give(self.backend, self.height * self.width * 16, self._pinned)
-                self._pinned = None
-        except Exception:
-            pass
 
     def to_abi(self):
         f = A.FtnFilm()
@@ -768,3 +767,17 @@ class SamplerIntegrator:
         return self.last_stats
 
     render = render_parallel   # integrator/mod.rs:206 (sequential variant: same result here)
+
+    def render_multi(self, scenes, film, sampler, sample_begin=0, sample_stride=1):
+        """One process, several GPUs (ftn_render_multi): `scenes` holds the same scene built on each device
+        (`Scene(..., device=i)`); the samples are sharded by index, the partial films are summed with one NCCL
+        reduce onto scenes[0]'s device and read back into film.pixels."""
+        st = A.FtnStats()
+        out = film._pixels
+        cam, f, s, it = self.camera.to_abi(), film.to_abi(), sampler.to_abi(sample_begin, sample_stride), self.radiance.to_abi()
+        handles = (A.VOIDP * len(scenes))(*[sc.handle.value for sc in scenes])
+        scenes[0].backend.call("render_multi", handles, len(scenes), C.byref(cam), C.byref(f), C.byref(s), C.byref(it),
+                               out.ctypes.data_as(C.POINTER(A.FtnPixel)), C.byref(st))
+        film._stale = False
+        self.last_stats = st.as_dict()
+        return self.last_stats

@@ -32,6 +32,8 @@ int film_pixel_count(const FtnFilm* f, int32_t* w, int32_t* h);
 int render_host(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, const FtnSampler* smp,
                 const FtnIntegrator* integ, FtnPixel* out_pixels, FtnStats* stats);
 int release_cached_memory();
+int render_multi(FtnScene* const* scenes, int32_t n, const FtnCamera* cam, const FtnFilm* film, const FtnSampler* smp,
+                 const FtnIntegrator* integ, FtnPixel* out_pixels, FtnStats* stats);
 }  // namespace ftn
 
 using namespace ftn;
@@ -75,7 +77,7 @@ FTN_API int ftn_scene_world_bound(const FtnScene* s, float out[6]) {
 FTN_API int ftn_scene_stats(const FtnScene* s, FtnStats* st) {
     if (!s || !st) return set_error(FTN_ERR_INVALID_ARGUMENT, "null argument");
     std::memset(st, 0, sizeof(*st));
-    st->bvh_build_seconds = s->build_seconds; st->bvh_nodes = s->n_nodes; st->bvh_node_bytes = FTN_NODE_BYTES; st->bvh_tri_bytes = 48;
+    st->bvh_build_seconds = s->build_seconds; st->morton_sort_seconds = s->sort_seconds; st->bvh_nodes = s->n_nodes; st->bvh_node_bytes = FTN_NODE_BYTES; st->bvh_tri_bytes = 48;
     st->kernel_launches = ftn_kernel_launch_count();
     return FTN_OK;
 }
@@ -103,7 +105,7 @@ static int intersect_host(const FtnScene* s, size_t n, const FtnRay* rays, FtnHi
     const size_t out_elem = any ? 1 : sizeof(FtnHit);
     const size_t in_bytes = (n * sizeof(FtnRay) + 255) & ~(size_t)255;
     DeviceArena& arena = device_arena(s->device);
-    std::lock_guard<std::mutex> lock(arena.m);
+    std::lock_guard<std::recursive_mutex> lock(arena.m);
     char* base = nullptr;
     FTN_TRY(arena.reserve(DeviceArena::BATCH, in_bytes + n * out_elem + 256, "cudaMalloc (ray batch staging)", (void**)&base));
     FtnRay* d_rays = (FtnRay*)base;
@@ -155,6 +157,13 @@ FTN_API int ftn_render_device(const FtnScene* s, const FtnCamera* cam, const Ftn
 FTN_API int ftn_render(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, const FtnSampler* smp,
                        const FtnIntegrator* integ, FtnPixel* out_pixels, FtnStats* stats) {
     return render_host(s, cam, film, smp, integ, out_pixels, stats);
+}
+FTN_API int ftn_render_multi(FtnScene* const* scenes, int32_t n_scenes, const FtnCamera* cam, const FtnFilm* film, const FtnSampler* smp,
+                             const FtnIntegrator* integ, FtnPixel* out_pixels, FtnStats* stats) {
+    const uint64_t l0 = ftn_kernel_launch_count();
+    const int rc = render_multi(scenes, n_scenes, cam, film, smp, integ, out_pixels, stats);
+    if (stats) stats->kernel_launches = ftn_kernel_launch_count() - l0;
+    return rc;
 }
 FTN_API int ftn_release_cached_memory(void) { return release_cached_memory(); }
 FTN_API int ftn_host_alloc(size_t bytes, void** out) {

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -145,7 +146,11 @@ struct FtnScene {
     uint32_t* d_order = nullptr;     // sorted primitive order
     float bounds[6] = {0, 0, 0, 0, 0, 0};
     double build_seconds = 0.0;
-    unsigned long long* d_work = nullptr;   // dynamic work-fetch counter of the batch queries
+    double sort_seconds = 0.0;       // Morton codes + radix sort, inside build_seconds
+    // dynamic work-fetch counters of the batch queries: a ring of FTN_MAX_QUERIES_IN_FLIGHT slots, one per call, so
+    // that queries enqueued on different streams never share a counter
+    unsigned long long* d_work = nullptr;
+    mutable std::atomic<uint32_t> work_slot{0};
     bool material_present[FTN_N_CLASSES] = {false, false, false, false, false};   // which shade kernels a render launches
     bool has_image_texture = false;         // any Kd image texture: selects the shade kernels that carry the mip lookup
     bool has_null_material = false;         // any primitive with a null BSDF (path.rs:76-80)
@@ -167,7 +172,8 @@ int radix_sort_pairs(uint32_t* d_keys, uint32_t* d_vals, size_t n, int bits, voi
 // Process-wide grow-only device arenas (one set per GPU): the wavefront path state, the film of
 // host-buffer renders, the temporaries of a BVH build.  Callers hold the arena's mutex while they use it.
 struct DeviceArena {
-    void* p[4] = {nullptr, nullptr, nullptr, nullptr}; size_t bytes[4] = {0, 0, 0, 0}; std::mutex m;
+    void* p[4] = {nullptr, nullptr, nullptr, nullptr}; size_t bytes[4] = {0, 0, 0, 0};
+    std::recursive_mutex m;   // recursive: ftn_render holds it from the film reservation to the read-back, around render_device's own lock
     enum { PATHS = 0, FILM = 1, BUILD = 2, BATCH = 3 };
     int reserve(int which, size_t need, const char* what, void** out);
     void* h_pinned = nullptr; size_t h_pinned_bytes = 0;   // small pinned host block (queue-counter read-back)

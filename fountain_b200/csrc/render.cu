@@ -334,21 +334,26 @@ struct Carver {
 // launches win; 16Mi paths cost 3.4 GB of the 180 GB.
 static size_t g_max_paths_per_pass = 16u << 20;
 
-// CUDA-event pairs around every traversal launch, per kernel class (extend / shadow / mis): the
-// live per-kernel durations bench.py's roofline uses.
-
+// CUDA-event pairs around every traversal / shading launch, per kernel class (0 extend, 1 shadow, 2 mis, 3 shade): the
+// live per-kernel durations bench.py's roofline uses.  Created only when the caller asks (FTN_STATS_TIME_KERNELS).
 struct TraceTimer {
     std::vector<cudaEvent_t> ev; std::vector<int> cls;
-    cudaStream_t st;
-    int begin(int c) { cudaEvent_t a, b; if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return -1; ev.push_back(a); ev.push_back(b); cls.push_back(c); cudaEventRecord(a, st); return 0; }
-    void end() { cudaEventRecord(ev.back(), st); }
-    void collect(double secs[3], uint64_t launches[3]) {
+    cudaStream_t st; bool on = false;
+    void begin(int c) { if (!on) return; cudaEvent_t a, b; if (cudaEventCreate(&a) != cudaSuccess) { on = false; return; } if (cudaEventCreate(&b) != cudaSuccess) { cudaEventDestroy(a); on = false; return; } ev.push_back(a); ev.push_back(b); cls.push_back(c); cudaEventRecord(a, st); }
+    void end() { if (on && !ev.empty()) cudaEventRecord(ev.back(), st); }
+    void collect(double secs[4], uint64_t launches[4]) {
         for (size_t i = 0; i < cls.size(); ++i) {
             float ms = 0.0f;
             if (cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]) == cudaSuccess) { secs[cls[i]] += ms * 1e-3; launches[cls[i]]++; }
         }
     }
     ~TraceTimer() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+};
+// owns an event for the duration of a scope: early error returns do not leak it
+struct EventGuard {
+    cudaEvent_t e = nullptr;
+    cudaError_t create(unsigned flags = cudaEventDefault) { return cudaEventCreateWithFlags(&e, flags); }
+    ~EventGuard() { if (e) cudaEventDestroy(e); }
 };
 
 int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, const FtnSampler* smp,
@@ -359,7 +364,8 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
     if (smp->samples_per_pixel < 1 || smp->sample_stride < 1 || smp->sample_begin < 0) return set_error(FTN_ERR_INVALID_ARGUMENT, "bad sampler");
     if (integ->type != FTN_INTEGRATOR_PATH && integ->type != FTN_INTEGRATOR_DIRECT_LIGHTING) return set_error(FTN_ERR_INVALID_ARGUMENT, "bad integrator");
     if (integ->max_depth < 0 || integ->max_depth > 60000) return set_error(FTN_ERR_INVALID_ARGUMENT, "bad max_depth");
-    const bool count_traversal = stats && stats->reserved == 1u;   // input flag: also count node visits / triangle tests
+    const uint32_t stat_flags = stats ? stats->flags : 0u;   // the one INPUT field of FtnStats
+    const bool count_traversal = (stat_flags & FTN_STATS_COUNT_TRAVERSAL) != 0u;
     FTN_CUDA(cudaSetDevice(s->device));
     FilmGeom fg;
     if (film_geometry(film, &fg) != FTN_OK) return set_error(FTN_ERR_INVALID_ARGUMENT, "bad film (resolution, filter radius or crop window)");
@@ -375,15 +381,16 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
     const size_t P = n_spix * (size_t)s_per_pass;
     if (P >= (1ull << 31)) return set_error(FTN_ERR_INVALID_ARGUMENT, "film too large for one pass");
 
-    cudaEvent_t ev0, ev1;
-    FTN_CUDA(cudaEventCreate(&ev0)); FTN_CUDA(cudaEventCreate(&ev1));
+    EventGuard g0, g1, gc;
+    FTN_CUDA(g0.create()); FTN_CUDA(g1.create()); FTN_CUDA(gc.create(cudaEventDisableTiming));
+    const cudaEvent_t ev0 = g0.e, ev1 = g1.e, ev_counts = gc.e;
     FTN_CUDA(cudaEventRecord(ev0, st));
 
     const size_t ws_bytes = 10 * (P * sizeof(float4) + 256) + 2 * (P * 4 + 256) + P * sizeof(float2) + 256 +
                             (size_t)fw * fh * sizeof(float4) + 256 + (size_t)(Q_COUNT + 1) * (P * 4 + 256) + n_spix + 4096;
     if (s->device < 0 || s->device >= FTN_MAX_DEVICES) return set_error(FTN_ERR_INVALID_ARGUMENT, "device index out of range");
     DeviceArena& arena = device_arena(s->device);
-    std::lock_guard<std::mutex> arena_lock(arena.m);
+    std::lock_guard<std::recursive_mutex> arena_lock(arena.m);
     Carver cv;
     FTN_TRY(arena.reserve(DeviceArena::PATHS, ws_bytes, "cudaMalloc (render workspace)", (void**)&cv.p));
     PathArrays pa;
@@ -411,11 +418,9 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
     uint64_t class_rays[3] = {0, 0, 0};
     const unsigned shade_grid = (unsigned)(sm_count() * 8);
     const int reach = (int)std::ceil(std::max(fg.radius[0], fg.radius[1]) + 0.5f);
-    TraceTimer timer; timer.st = st;
+    TraceTimer timer; timer.st = st; timer.on = (stat_flags & FTN_STATS_TIME_KERNELS) != 0u;
     uint32_t* h_counts = nullptr;           // pinned read-back slot of the queue counters, one per device
     FTN_TRY(arena.pinned_counts(&h_counts, CTR_COUNT * sizeof(uint32_t)));
-    cudaEvent_t ev_counts;
-    FTN_CUDA(cudaEventCreateWithFlags(&ev_counts, cudaEventDisableTiming));
 
     PassParams pp; std::memset(&pp, 0, sizeof(pp));
     pp.film = fg; pp.cam = *cam; pp.seed_key = sampler_seed_key(smp->seed);
@@ -445,6 +450,7 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
             timer.end();
             FTN_LAUNCHED();
             class_rays[0] += n_active;
+            timer.begin(3);
             k_shade_miss<<<shade_grid, 256, 0, st>>>(sc, pp, pa, q.q[Q_MISS], counts);
             FTN_LAUNCHED();
             if (s->has_null_material) { k_shade<Q_NULL><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_NULL], q, counts, d_err); FTN_LAUNCHED(); }
@@ -469,6 +475,7 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
                 else k_shade<Q_MAT4><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT4], q, counts, d_err);
                 FTN_LAUNCHED();
             }
+            timer.end();
             // The shadow and MIS queues cannot be longer than this iteration's input queue, and their kernels
             // read the exact lengths on the device: launch them sized by that bound BEFORE waiting for the
             // counts, so that the host round trip (needed to size the next iteration and to stop) is hidden
@@ -498,7 +505,6 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
         k_film_accumulate<<<(fw * fh + 127) / 128, 128, 0, st>>>(pp, pa, accum, reach, d_err);
         FTN_LAUNCHED();
     }
-    cudaEventDestroy(ev_counts);
     k_film_resolve<<<(fw * fh + 255) / 256, 256, 0, st>>>(accum, d_pixels, fw * fh);
     FTN_LAUNCHED();
     uint32_t h_err = 0;
@@ -509,14 +515,17 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
     FTN_CUDA(cudaEventSynchronize(ev1));
     float ms = 0.0f;
     FTN_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));
         stats->camera_samples = camera_samples;
         stats->rays_closest = class_rays[0] + class_rays[2]; stats->rays_any = class_rays[1];   // Scene::intersect / intersect_test calls
-        stats->device_seconds = ms * 1e-3; stats->bvh_build_seconds = s->build_seconds;
+        stats->device_seconds = ms * 1e-3; stats->bvh_build_seconds = s->build_seconds; stats->morton_sort_seconds = s->sort_seconds;
         stats->bvh_nodes = s->n_nodes; stats->bvh_node_bytes = FTN_NODE_BYTES; stats->bvh_tri_bytes = 48;
-        timer.collect(stats->trace_seconds, stats->trace_launches);
+        double tsec[4] = {0, 0, 0, 0}; uint64_t tl[4] = {0, 0, 0, 0};
+        timer.collect(tsec, tl);
+        for (int c = 0; c < 3; ++c) { stats->trace_seconds[c] = tsec[c]; stats->trace_launches[c] = tl[c]; }
+        stats->shade_seconds = tsec[3]; stats->shade_launches = tl[3];
+        stats->flags = stat_flags;
         for (int c = 0; c < 3; ++c) { stats->trace_rays[c] = class_rays[c]; stats->trace_nodes[c] = h_trav[2 * c]; stats->trace_tris[c] = h_trav[2 * c + 1]; }
         stats->node_visits = h_trav[0] + h_trav[2] + h_trav[4]; stats->tri_tests = h_trav[1] + h_trav[3] + h_trav[5];
     }
@@ -536,10 +545,10 @@ int render_host(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, co
     const size_t bytes = (size_t)w * h * sizeof(FtnPixel);
     DeviceArena& arena = device_arena(s->device);
     FtnPixel* d_px = nullptr;
-    {
-        std::lock_guard<std::mutex> lock(arena.m);
-        FTN_TRY(arena.reserve(DeviceArena::FILM, bytes, "cudaMalloc (film)", (void**)&d_px));
-    }
+    // held from the reservation of the film slot to the end of the read-back: a concurrent ftn_render with a larger
+    // film (or ftn_release_cached_memory) would otherwise re-allocate the slot under this render
+    std::lock_guard<std::recursive_mutex> lock(arena.m);
+    FTN_TRY(arena.reserve(DeviceArena::FILM, bytes, "cudaMalloc (film)", (void**)&d_px));
     FTN_CUDA(cudaMemsetAsync(d_px, 0, bytes, nullptr));
     const int render_rc = render_device(s, cam, film, smp, integ, d_px, stats, nullptr);
     // like the reference's panic, a NaN / unsupported render still leaves the film readable

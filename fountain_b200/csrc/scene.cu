@@ -381,7 +381,7 @@ static void scene_free(void* p) { if (p) cudaFreeAsync(p, 0); }
 int release_cached_memory() {
     for (int d = 0; d < FTN_MAX_DEVICES; ++d) {
         DeviceArena& a = g_arena[d];
-        std::lock_guard<std::mutex> lock(a.m);
+        std::lock_guard<std::recursive_mutex> lock(a.m);
         if (!a.p[0] && !a.p[1] && !a.p[2] && !a.p[3] && !a.h_pinned) continue;
         if (cudaSetDevice(d) != cudaSuccess) continue;
         for (int i = 0; i < 4; ++i) { cudaFree(a.p[i]); a.p[i] = nullptr; a.bytes[i] = 0; }
@@ -595,7 +595,7 @@ int scene_create(const FtnSceneDesc* d, FtnScene** out) {
     }
     if ((rc = upload(&s->d_spheres, s->h_spheres.data(), s->h_spheres.size())) != FTN_OK) return bail(rc);
     if ((rc = upload(&s->d_lights, s->h_lights.data(), s->h_lights.size())) != FTN_OK) return bail(rc);
-    cudaError_t e = scene_malloc(&s->d_work, sizeof(unsigned long long));
+    cudaError_t e = scene_malloc(&s->d_work, FTN_MAX_QUERIES_IN_FLIGHT * sizeof(unsigned long long));
     if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc work counter", __FILE__, __LINE__));
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return bail(cuda_fail(e, "scene_create sync", __FILE__, __LINE__));
@@ -638,8 +638,9 @@ int bvh_build(FtnScene* s) {
     if (s->built) return FTN_OK;
     FTN_CUDA(cudaSetDevice(s->device));
     cudaStream_t st = 0;
-    cudaEvent_t ev0, ev1;
-    FTN_CUDA(cudaEventCreate(&ev0)); FTN_CUDA(cudaEventCreate(&ev1));
+    cudaEvent_t ev0, ev1, ev_s0, ev_s1;
+    FTN_CUDA(cudaEventCreate(&ev0)); FTN_CUDA(cudaEventCreate(&ev1)); FTN_CUDA(cudaEventCreate(&ev_s0)); FTN_CUDA(cudaEventCreate(&ev_s1));
+    bool sort_timed = false;
     FTN_CUDA(cudaEventRecord(ev0, st));
     const uint32_t n = s->n_tris;
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
@@ -665,10 +666,10 @@ int bvh_build(FtnScene* s) {
                                + al(radix_sort_scratch_bytes(n)) + al(scan_scratch_elems(ni_max) * 4) + 4096
                                + (use_ploc ? 9 * al((size_t)n * 4) + 2 * al((size_t)n * sizeof(F4)) + al(scan_scratch_elems(n) * 4) + 4096 : 0);
         DeviceArena& arena = device_arena(s->device);
-        std::lock_guard<std::mutex> arena_lock(arena.m);
+        std::lock_guard<std::recursive_mutex> arena_lock(arena.m);
         char* tmp_base = nullptr; size_t tmp_off = 0;
         if ((rc = arena.reserve(DeviceArena::BUILD, tmp_bytes, "cudaMalloc (bvh build temporaries)", (void**)&tmp_base)) != FTN_OK) {
-            cudaEventDestroy(ev0); cudaEventDestroy(ev1); return rc;
+            cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev_s0); cudaEventDestroy(ev_s1); return rc;
         }
         auto dalloc = [&](void** p, size_t bytes) -> int {
             tmp_off = al(tmp_off);
@@ -689,10 +690,13 @@ int bvh_build(FtnScene* s) {
             if (!s->d_order && (e = scene_malloc(&s->d_order, (size_t)n * 4)) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc order", __FILE__, __LINE__); break; }
             k_init_bounds<<<1, 32, 0, st>>>(d_gb); count_launch();
             k_tri_bounds<<<gb256, 256, 0, st>>>(s->d_pos, s->d_idx, n, tri_lo, tri_hi, d_gb); count_launch();
+            if ((rc = dalloc(&sort_scratch, radix_sort_scratch_bytes(n))) != FTN_OK) break;
+            cudaEventRecord(ev_s0, st);
             k_morton<<<gb256, 256, 0, st>>>(tri_lo, tri_hi, n, d_gb, s->d_codes, keys, s->d_order); count_launch();
             if ((e = cudaGetLastError()) != cudaSuccess) { rc = cuda_fail(e, "bounds/morton kernels", __FILE__, __LINE__); break; }
-            if ((rc = dalloc(&sort_scratch, radix_sort_scratch_bytes(n))) != FTN_OK) break;
             if ((rc = radix_sort_pairs(keys, s->d_order, n, 30, sort_scratch, st)) != FTN_OK) break;
+            cudaEventRecord(ev_s1, st);
+            sort_timed = true;
             if ((rc = dalloc((void**)&leaf_lo, (size_t)n * sizeof(F4))) != FTN_OK) break;
             if ((rc = dalloc((void**)&leaf_hi, (size_t)n * sizeof(F4))) != FTN_OK) break;
             k_gather_leaf_boxes<<<gb256, 256, 0, st>>>(tri_lo, tri_hi, s->d_order, n, leaf_lo, leaf_hi); count_launch();
@@ -808,7 +812,7 @@ int bvh_build(FtnScene* s) {
             }
         } while (0);
         cleanup();
-        if (rc != FTN_OK) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); return rc; }
+        if (rc != FTN_OK) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev_s0); cudaEventDestroy(ev_s1); return rc; }
     }
     for (const SphereData& sd : s->h_spheres) {
         float slo[3], shi[3];
@@ -833,7 +837,8 @@ int bvh_build(FtnScene* s) {
     FTN_CUDA(cudaEventSynchronize(ev1));
     float ms = 0.0f;
     FTN_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    if (sort_timed) { float sms = 0.0f; if (cudaEventElapsedTime(&sms, ev_s0, ev_s1) == cudaSuccess) s->sort_seconds = sms * 1e-3; }
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev_s0); cudaEventDestroy(ev_s1);
     s->build_seconds = ms * 1e-3;
     s->built = true;
     return FTN_OK;

@@ -76,7 +76,8 @@ int intersect_device(const FtnScene* s, size_t n, const FtnRay* d_rays, FtnHit* 
     const size_t chunk = (size_t)1 << 30;   // the work counter is 32-bit
     for (size_t off = 0; off < n; off += chunk) {
         const uint32_t m = (uint32_t)std::min(chunk, n - off);
-        uint32_t* d_work = reinterpret_cast<uint32_t*>(s->d_work);   // one query at a time per scene
+        // this call's own work counter: the next slot of the scene's ring (calls on different streams may overlap)
+        uint32_t* d_work = reinterpret_cast<uint32_t*>(s->d_work + (s->work_slot.fetch_add(1u, std::memory_order_relaxed) % FTN_MAX_QUERIES_IN_FLIGHT));
         FTN_CUDA(cudaMemsetAsync(d_work, 0, sizeof(unsigned long long), st));
         const unsigned grid = trace_grid(m, FTN_TRACE_BLOCKS_PER_SM);
         const FtnRay* r = d_rays + off;

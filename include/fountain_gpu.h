@@ -13,10 +13,16 @@
  *     or aborts across the ABI.
  *   - The caller owns every input array and every output buffer.  The library
  *     copies inputs during ftn_scene_create and keeps nothing after return.
- *   - `*_device` variants take pointers into the CURRENT CUDA device's memory
- *     (e.g. a torch tensor's data_ptr) and enqueue work on `stream` (a
- *     cudaStream_t passed as void*; NULL = legacy default stream).  They do not
- *     synchronise.
+ *   - `*_device` variants take pointers into the scene's CUDA device's memory
+ *     (e.g. a torch tensor's data_ptr) and run on `stream` (a cudaStream_t passed
+ *     as void*; NULL = legacy default stream).  The ray queries
+ *     (ftn_intersect*_device) and ftn_film_to_rgb_device only ENQUEUE: they return
+ *     before the work has run and never block the host; up to FTN_MAX_QUERIES_IN_FLIGHT
+ *     queries on one scene may overlap on different streams.  ftn_render_device is
+ *     different: it runs on `stream` but RETURNS ONLY WHEN THE FILM IS COMPLETE (it
+ *     reads queue lengths back while the bounces run and the statistics at the end), so
+ *     the caller may use d_pixels on `stream` or after a stream sync straight away.
+ *     Renders on one device serialise on the library's per-device workspace.
  *   - Primitive ids crossing the ABI are insertion indices: triangles first, in
  *     index-buffer order (mesh order, tri_id), then spheres.  The reference's own
  *     post-build permutation (bvh.rs:52) is not stable and is not exposed.
@@ -39,7 +45,8 @@ extern "C" {
 #define FTN_API __attribute__((visibility("default")))
 #endif
 
-#define FTN_ABI_VERSION 1u
+#define FTN_ABI_VERSION 2u
+#define FTN_MAX_QUERIES_IN_FLIGHT 64
 #define FTN_NO_HIT 0xFFFFFFFFu
 
 typedef enum FtnStatus {
@@ -85,6 +92,11 @@ typedef struct FtnMeshDesc {
     uint32_t n_tris;
     int32_t  material_id;    /* index into materials[], -1 = no material (null BSDF, path.rs:76-80) */
     uint32_t flags;          /* FTN_MESH_* */
+    /* `AreaLightSource "diffuse"` in front of the shape: EVERY triangle of the mesh carries its own
+     * DiffuseAreaLight<Triangle> (loaders/pbrt.rs:275-316, light/diffuse.rs:24-93); the lights are
+     * appended to the scene's light list in primitive order (scene/mod.rs:40-44). */
+    int32_t  emissive;       /* 1 = every triangle is a diffuse area light */
+    float    emit[3];        /* L of those lights */
 } FtnMeshDesc;
 
 typedef enum FtnMaterialType {
@@ -251,7 +263,7 @@ typedef struct FtnStats {
     uint64_t camera_samples;
     uint64_t rays_closest;   /* Scene::intersect calls (primary + continuation + MIS) */
     uint64_t rays_any;       /* Scene::intersect_test calls (shadow) */
-    uint64_t node_visits;    /* 0 unless built with FTN_COUNT_TRAVERSAL / requested via env */
+    uint64_t node_visits;    /* 0 unless FTN_STATS_COUNT_TRAVERSAL was set in `flags` */
     uint64_t tri_tests;
     uint64_t kernel_launches;
     double   device_seconds; /* CUDA-event time of the whole call on its stream */
@@ -259,14 +271,20 @@ typedef struct FtnStats {
     uint32_t bvh_nodes;
     uint32_t bvh_node_bytes;
     uint32_t bvh_tri_bytes;
-    uint32_t reserved;       /* INPUT to ftn_render*: 1 = also count node visits / triangle tests (slower) */
+    uint32_t flags;          /* INPUT to ftn_render*: FTN_STATS_* bits; set before the call (0 = plain render) */
     /* per traversal-kernel class: 0 = extend (closest hit), 1 = shadow (any hit), 2 = MIS */
-    double   trace_seconds[3];   /* sum of CUDA-event durations of that class's launches */
+    double   trace_seconds[3];   /* FTN_STATS_TIME_KERNELS: sum of CUDA-event durations of that class's launches */
     uint64_t trace_launches[3];
     uint64_t trace_rays[3];
-    uint64_t trace_nodes[3];     /* only with reserved == 1 */
+    uint64_t trace_nodes[3];     /* FTN_STATS_COUNT_TRAVERSAL */
     uint64_t trace_tris[3];
+    double   shade_seconds;      /* FTN_STATS_TIME_KERNELS: all shading launches (miss, null, per material class) */
+    uint64_t shade_launches;
+    double   morton_sort_seconds; /* inside bvh_build_seconds: Morton codes (k_morton) + the stable radix sort of (code, primitive) */
 } FtnStats;
+/* FtnStats.flags (the only INPUT field of the struct; everything else is written by the call) */
+#define FTN_STATS_COUNT_TRAVERSAL 1u   /* also count node visits / triangle tests (slower kernels) */
+#define FTN_STATS_TIME_KERNELS    2u   /* CUDA-event pairs around every traversal / shading launch */
 
 typedef struct FtnScene FtnScene;
 
@@ -327,6 +345,18 @@ FTN_API int ftn_render(const FtnScene* scene, const FtnCamera* camera, const Ftn
 FTN_API int ftn_render_device(const FtnScene* scene, const FtnCamera* camera, const FtnFilm* film,
                               const FtnSampler* sampler, const FtnIntegrator* integrator,
                               FtnPixel* d_pixels, FtnStats* out_stats, void* stream);
+
+/* The render of one process driving SEVERAL GPUs (what render.rs:82-89 would call on a multi-GPU box):
+ * scenes[i] is the same scene created and built on device i (ftn_set_device(i); ftn_scene_create; ftn_bvh_build
+ * -- the scene is replicated, every GPU holds all of it).  The samples of `sampler` are sharded by index:
+ * device i renders s = sample_begin + (i + k * n_scenes) * sample_stride, on its own host thread and stream;
+ * the partial films are summed onto scenes[0]'s device with ONE ncclReduce over NVLink -- the analogue of
+ * merge_film_tile's mutex merge (film.rs:121-132) -- and copied to out_pixels (host).  NCCL (libnccl.so.2) is
+ * loaded on first use; without it the call fails with FTN_ERR_UNSUPPORTED.  out_stats sums the devices' ray
+ * counts; device_seconds is the slowest device's.  n_scenes == 1 is ftn_render. */
+FTN_API int ftn_render_multi(FtnScene* const* scenes, int32_t n_scenes, const FtnCamera* camera, const FtnFilm* film,
+                             const FtnSampler* sampler, const FtnIntegrator* integrator,
+                             FtnPixel* out_pixels, FtnStats* out_stats);
 
 /* Film::into_spectrum_buffer (film.rs:195-210): XYZ -> RGB, divide by weight, clamp >= 0.
  * n pixels; out_rgb is 3 floats per pixel.  Device buffers. */

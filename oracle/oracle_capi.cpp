@@ -297,7 +297,7 @@ ORC_API int orc_render(const OrcScene* os, const FtnCamera* cam, const FtnFilm* 
     rp.integrator = integ->type; rp.max_depth = integ->max_depth; rp.rr_threshold = integ->rr_threshold;
     rp.spp = smp->samples_per_pixel; rp.seed = smp->seed; rp.sampler_mode = smp->mode;
     rp.sample_begin = smp->sample_begin; rp.sample_stride = smp->sample_stride;
-    rp.threads = g_threads; rp.count_traversal = stats && stats->reserved == 1u;
+    rp.threads = g_threads; rp.count_traversal = stats && (stats->flags & FTN_STATS_COUNT_TRAVERSAL);
     Counters ctr;
     auto t0 = std::chrono::steady_clock::now();
     RenderResult rr = render(os->scene, c, film, rp, &ctr);

@@ -1,7 +1,8 @@
 import time, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-from fountain_b200 import api, scenes
+from fountain_b200 import api
+from workloads import scenes
 gpu = api.default_backend()
 def T(label, f):
     t=time.perf_counter(); r=f(); dt=(time.perf_counter()-t)*1e3; print("%-28s %8.2f ms"%(label,dt)); return r

@@ -1,7 +1,8 @@
 """Wall and device time of scene upload + BVH build, per iteration (builder from FTN_BVH_BUILDER)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from fountain_b200 import api, scenes
+from fountain_b200 import api
+from workloads import scenes
 gpu = api.default_backend()
 which = sys.argv[1] if len(sys.argv) > 1 else "c2"
 for it in range(8):

@@ -6,7 +6,8 @@ import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np  # noqa: E402
-from fountain_b200 import api, scenes  # noqa: E402
+from fountain_b200 import api
+from workloads import scenes  # noqa: E402
 
 gpu = api.default_backend()
 gpu.call("set_device", 0)
@@ -30,7 +31,7 @@ for label, material in (("image textures (matte)", "matte"), ("image textures (p
     scene.close()
 
 # the same geometry and lights with constant Kd
-import fountain_b200.scenes as S  # noqa: E402
+import workloads.scenes as S  # noqa: E402
 orig = api.ImageTexture
 try:
     api.ImageTexture = lambda mp, mapping=None: np.array([0.5, 0.4, 0.3], np.float32)

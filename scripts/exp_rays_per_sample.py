@@ -1,7 +1,8 @@
 """Sanity: rays per camera sample must not depend on spp / number of passes."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from fountain_b200 import api, scenes
+from fountain_b200 import api
+from workloads import scenes
 gpu = api.default_backend()
 scene, camera, film = scenes.logo_style_scene(backend=gpu, resolution=(1920, 1080))
 for spp in (8, 16, 24, 64, 128):

@@ -8,7 +8,8 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from fountain_b200 import _abi as A, api, scenes  # noqa: E402
+from fountain_b200 import _abi as A, api
+from workloads import scenes  # noqa: E402
 from tests.hostsim import sim  # noqa: E402
 
 be = sim.backend()

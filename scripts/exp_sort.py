@@ -10,7 +10,8 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
-from fountain_b200 import api, scenes  # noqa: E402
+from fountain_b200 import api
+from workloads import scenes  # noqa: E402
 
 
 def expand_bits(v):

@@ -9,6 +9,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+DATA = os.path.join(ROOT, "data")
 
 
 def pytest_configure(config):
@@ -35,7 +36,7 @@ def gpu_backend():
 
 @pytest.fixture(scope="session")
 def rounded_cube_path():
-    return os.path.join(GOLDEN, "rounded_cube.ply")
+    return os.path.join(DATA, "rounded_cube.ply")
 
 
 def unit_sphere_dirs(n, seed):

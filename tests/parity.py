@@ -5,7 +5,8 @@ import ctypes as C
 import numpy as np
 
 from fountain_b200 import _abi as A
-from fountain_b200 import api, scenes
+from fountain_b200 import api
+from workloads import scenes
 from tests.conftest import unit_sphere_dirs
 
 NO_HIT = A.FTN_NO_HIT

@@ -36,12 +36,12 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_the_header():
     # sizes implied by the header's field lists (LP64)
     assert C.sizeof(A.FtnRay) == 32 and C.sizeof(A.FtnHit) == 16 and C.sizeof(A.FtnPixel) == 16
-    assert C.sizeof(A.FtnMeshDesc) == 16
+    assert C.sizeof(A.FtnMeshDesc) == 16 + 4 + 12
     assert C.sizeof(A.FtnSphere) == 2 * 64 + 4 * 4 + 3 * 4 + 12
     assert C.sizeof(A.FtnCamera) == 2 * 64 + 16
     assert C.sizeof(A.FtnFilm) == 8 + 16 + 8
     assert C.sizeof(A.FtnIntegrator) == 12
-    assert C.sizeof(A.FtnStats) == 6 * 8 + 2 * 8 + 4 * 4 + 5 * 24
+    assert C.sizeof(A.FtnStats) == 6 * 8 + 2 * 8 + 4 * 4 + 5 * 24 + 16 + 8
 
 
 def test_no_cpu_fallback_without_a_device():

@@ -22,7 +22,8 @@ def _worker(rank, world, port, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from fountain_b200 import api, scenes
+    from fountain_b200 import api
+    from workloads import scenes
     from fountain_b200.distributed import render_sharded
     from oracle import orc
     orc.set_threads(2)
@@ -38,7 +39,8 @@ def _worker(rank, world, port, out_dir):
 
 
 def test_two_rank_sharded_render_equals_single(tmp_path):
-    from fountain_b200 import api, scenes
+    from fountain_b200 import api
+    from workloads import scenes
     from oracle import orc
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)

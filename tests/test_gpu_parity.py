@@ -7,7 +7,8 @@ import numpy as np
 import pytest
 
 from fountain_b200 import _abi as A
-from fountain_b200 import api, scenes
+from fountain_b200 import api
+from workloads import scenes
 from fountain_b200.transform import Transform
 from tests import parity
 
@@ -136,6 +137,59 @@ def test_million_triangle_properties(gpu_backend):
     outside = api.make_rays(dirs * 40.0, -dirs)
     h2 = scene.intersect(outside)
     assert (h2["prim"] != A.FTN_NO_HIT).all() and np.all(np.abs(h2["t"] - 30.0) < 0.6)
+
+
+def _interior_rays(n, seed, radius=9.0):
+    """Uniformly random origins inside the closed displaced sphere with uniformly random directions: every ray
+    hits, none is coherent (bench.py's `incoherent_interior` batch)."""
+    rng = np.random.default_rng(seed)
+    o = rng.normal(size=(n, 3)); o *= (rng.random((n, 1)) ** (1 / 3) * radius) / np.linalg.norm(o, axis=1, keepdims=True)
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return api.make_rays(o.astype(np.float32), d.astype(np.float32))
+
+
+def test_million_triangle_batches_bit_for_bit(gpu_backend, orc_backend):
+    """BASELINE config C3 at full size against the oracle (bvh.rs:160-215 restated): the incoherent diffuse-bounce
+    batch of bench.py (>= 1 M rays) and 256 Ki interior rays -- hit/miss identical, same primitive => t, b1, b2
+    bit-identical; any-hit == (closest hit exists)."""
+    a, camera = scenes.synthetic_mesh_scene(1000, 500, backend=gpu_backend, resolution=(1024, 1024))
+    b, _ = scenes.synthetic_mesh_scene(1000, 500, backend=orc_backend, resolution=(1024, 1024))
+    assert a.n_triangles == 1_000_000
+    prim = scenes.primary_ray_batch(camera, (1024, 1024))
+    hits = a.intersect(prim)
+    inc = scenes.diffuse_bounce_batch(prim, hits, a._positions, a._indices, seed=2)
+    inc = np.concatenate([inc] * int(np.ceil((1 << 20) / len(inc))))[: 1 << 20]
+    assert len(inc) >= 1 << 20
+    st = parity.compare_hits(a.intersect(inc), b.intersect(inc), "C3 incoherent diffuse")
+    assert st["hits"] > 10_000
+    sub = inc[: 1 << 18]
+    assert np.array_equal(a.intersect_test(sub), b.intersect_test(sub))
+    interior = _interior_rays(1 << 18, 4)
+    st2 = parity.compare_hits(a.intersect(interior), b.intersect(interior), "C3 interior")
+    assert st2["hits"] == len(interior)
+    st3 = parity.compare_hits(hits, b.intersect(prim), "C3 primary")
+    assert st3["hits"] > 100_000
+
+
+def test_eight_million_triangle_ploc_spot_check(gpu_backend, orc_backend):
+    """C5-class scene (8 M triangles, PLOC topology, the deepest trees of the suite): 400 k interior rays all hit,
+    any-hit == (closest hit exists), t within the displacement amplitude of the sphere, and a 50 k-ray subset equals
+    the oracle's BVH::intersect bit for bit."""
+    a, _ = scenes.synthetic_mesh_scene(2828, 1414, backend=gpu_backend, resolution=(64, 64))
+    assert a.n_triangles >= 7_900_000
+    rays = _interior_rays(400_000, 6)
+    hits = a.intersect(rays)
+    assert (hits["prim"] != A.FTN_NO_HIT).all()
+    assert a.intersect_test(rays).all()
+    p = rays["o"].astype(np.float64) + rays["d"].astype(np.float64) * hits["t"][:, None].astype(np.float64)
+    assert np.all(np.abs(np.linalg.norm(p, axis=1) - 10.0) < 0.6)
+    outside = api.make_rays(rays["d"] * np.float32(40.0), -rays["d"])          # from outside towards the centre
+    h2 = a.intersect(outside)
+    assert (h2["prim"] != A.FTN_NO_HIT).all() and np.all(np.abs(h2["t"] - 30.0) < 0.6)
+    b, _ = scenes.synthetic_mesh_scene(2828, 1414, backend=orc_backend, resolution=(64, 64))
+    sub = np.concatenate([rays[:40_000], outside[:10_000]])
+    parity.compare_hits(np.concatenate([hits[:40_000], h2[:10_000]]), b.intersect(sub), "C5 8M subset")
+    b.close(); a.close()
 
 
 # ---- both topology builders (FTN_BVH_BUILDER): results must not depend on the tree ----------------------

@@ -4,7 +4,8 @@ import numpy as np
 import pytest
 
 from fountain_b200 import _abi as A
-from fountain_b200 import api, scenes
+from fountain_b200 import api
+from workloads import scenes
 from fountain_b200.transform import Transform
 from tests import parity
 

@@ -9,7 +9,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CPP = os.path.join(ROOT, "tests", "cpp")
-PLY = os.path.join(ROOT, "tests", "golden", "rounded_cube.ply")
+PLY = os.path.join(ROOT, "data", "rounded_cube.ply")
 
 
 @pytest.fixture(scope="module")

@@ -6,7 +6,8 @@ import numpy as np
 import pytest
 
 from fountain_b200 import _abi as A
-from fountain_b200 import api, scenes
+from fountain_b200 import api
+from workloads import scenes
 
 
 def _render(backend, integrator, mode, spp=128, seed=0):
@@ -82,7 +83,7 @@ def test_rounded_cube_render_sane(orc_backend):
 # The reference holds no test for them, so the restatement is pinned against the closed form of
 # direct lighting on a Lambertian floor: L = Kd/pi * I cos(theta) / d^2 (point), Kd/pi * L cos(theta) (distant).
 def _floor_radiance(scene_kw, integrator, orc_backend, spp):
-    from fountain_b200 import scenes
+    from workloads import scenes
     scene, camera, film = scenes.delta_lights_scene(backend=orc_backend, resolution=(9, 9), fov=2.0, occluder=False, **scene_kw)
     # look straight down at the origin from (0, 0, 20): every pixel sees the floor within 0.4 units of the origin
     from fountain_b200.transform import Transform
@@ -118,7 +119,7 @@ def test_two_delta_lights_one_is_picked_per_sample(orc_backend):
 def test_delta_light_shadow(orc_backend):
     """The occluder at z = 1 over x in [1, 3] shadows the floor from the point light at (0, 0, 4):
     the shadow covers x in [4/3, 4] at y = 0; floor points there are exactly black."""
-    from fountain_b200 import scenes
+    from workloads import scenes
     from fountain_b200.transform import Transform
     scene, _, film = scenes.delta_lights_scene(backend=orc_backend, resolution=(5, 5), lights=("point",))
     camera = api.PerspectiveCamera(Transform.look_at((4.5, 0, 20), (4.5, 0, 0), (0, 1, 0)).inverse(), (5, 5), fov=1.0)   # x ~ 4.5: lit
@@ -134,7 +135,7 @@ def test_delta_light_shadow(orc_backend):
 # No reference test covers it: pinned against the closed form -- a mirror under a uniform environment
 # of radiance 1 returns exactly Kr (one specular bounce, pdf 1, f = Kr / |cos|, times |cos|).
 def test_mirror_closed_form_path(orc_backend):
-    from fountain_b200 import scenes
+    from workloads import scenes
     scene, camera, film = scenes.mirror_scene(backend=orc_backend, resolution=(9, 9), with_floor=False)
     from fountain_b200.transform import Transform
     camera = api.PerspectiveCamera(Transform.look_at((0, -7, 1.5), (0, 2, 1.0), (0, 0, 1)).inverse(), (9, 9), fov=5.0)
@@ -149,7 +150,7 @@ def test_mirror_closed_form_path(orc_backend):
 def test_mirror_closed_form_direct_lighting(orc_backend):
     """specular_reflect (integrator/mod.rs:40-103): with max_depth 2 the mirror shows Kr * environment,
     with max_depth 1 the recursion is cut (depth + 1 < max_depth fails) and the mirror is black."""
-    from fountain_b200 import scenes
+    from workloads import scenes
     from fountain_b200.transform import Transform
     scene, _, film = scenes.mirror_scene(backend=orc_backend, resolution=(9, 9), with_floor=False)
     camera = api.PerspectiveCamera(Transform.look_at((0, -7, 1.5), (0, 2, 1.0), (0, 0, 1)).inverse(), (9, 9), fov=5.0)
@@ -161,7 +162,7 @@ def test_mirror_closed_form_direct_lighting(orc_backend):
 
 @pytest.mark.parametrize("mode", [A.FTN_SAMPLER_COUNTER, A.FTN_SAMPLER_REFERENCE_TILE_STREAM])
 def test_mirror_scene_renders_in_both_sampler_modes(orc_backend, mode):
-    from fountain_b200 import scenes
+    from workloads import scenes
     scene, camera, film = scenes.mirror_scene(backend=orc_backend, resolution=(32, 32))
     api.SamplerIntegrator(camera, api.PathIntegrator(5, 1.0)).render_parallel(scene, film, api.RandomSampler.new_with_seed(16, 0, mode=mode))
     rgb = film.into_spectrum_buffer()[0]
@@ -172,7 +173,7 @@ def test_mirror_scene_renders_in_both_sampler_modes(orc_backend, mode):
 # No reference test: pinned by closed form -- under a distant light from straight above a Lambertian floor
 # shows Kd(texel) / pi * L exactly; the floor's uv are its world (x, y).
 def _probe(orc_backend, xy, texture):
-    from fountain_b200 import scenes
+    from workloads import scenes
     scene, camera, film = scenes.textured_floor_scene(backend=orc_backend, resolution=(5, 5), texture=texture, look_at=xy, fov=0.5)
     api.SamplerIntegrator(camera, api.DirectLightingIntegrator(1)).render_parallel(scene, film, api.RandomSampler.new_with_seed(2, 0))
     return film.into_spectrum_buffer()[0]

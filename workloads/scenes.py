@@ -7,11 +7,11 @@ import os
 
 import numpy as np
 
-from . import api
-from .transform import Transform
+from fountain_b200 import api
+from fountain_b200.transform import Transform
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-ROUNDED_CUBE_PLY = os.path.join(_ROOT, "tests", "golden", "rounded_cube.ply")
+ROUNDED_CUBE_PLY = os.path.join(_ROOT, "data", "rounded_cube.ply")
 
 
 # ---- C1: testscenes/furnace_empty.pbrt --------------------------------------------------------
