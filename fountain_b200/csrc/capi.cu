@@ -77,7 +77,7 @@ FTN_API int ftn_scene_world_bound(const FtnScene* s, float out[6]) {
 FTN_API int ftn_scene_stats(const FtnScene* s, FtnStats* st) {
     if (!s || !st) return set_error(FTN_ERR_INVALID_ARGUMENT, "null argument");
     std::memset(st, 0, sizeof(*st));
-    st->bvh_build_seconds = s->build_seconds; st->morton_sort_seconds = s->sort_seconds; st->bvh_nodes = s->n_nodes; st->bvh_node_bytes = FTN_NODE_BYTES; st->bvh_tri_bytes = 48;
+    st->bvh_build_seconds = s->build_seconds; st->morton_sort_seconds = s->sort_seconds; st->bvh_nodes = s->n_nodes; st->bvh_node_bytes = s->wide ? FTN_NODE8_BYTES : FTN_NODE_BYTES; st->bvh_tri_bytes = FTN_TRI_BYTES;
     st->kernel_launches = ftn_kernel_launch_count();
     return FTN_OK;
 }

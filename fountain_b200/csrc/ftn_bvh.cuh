@@ -1,9 +1,11 @@
 // Flattened BVH layouts and the single-ray traversal loop.
 //
-// Triangles are re-laid as 48-byte pre-gathered records in leaf order (3 x 128-bit loads, no
-// index indirection; replaces the reference's Box<dyn Primitive> -> Arc<TriangleMesh> ->
-// indices -> vertices chain, bvh.rs:181 / triangle.rs:96-111):
-//   tri:   (p0.xyz, prim id), (p1.xyz, mesh id), (p2.xyz, unused)
+// Triangles are re-laid as 64-byte pre-gathered records in leaf order (one 256-bit + one 128-bit
+// load: the traversal is bound by load INSTRUCTIONS per lane, not bytes, so the padded record costs
+// two L1 wavefronts per lane instead of the three of a packed 48-byte one; no index indirection --
+// replaces the reference's Box<dyn Primitive> -> Arc<TriangleMesh> -> indices -> vertices chain,
+// bvh.rs:181 / triangle.rs:96-111):
+//   tri:   (p0.xyz, prim id), (p1.xyz, mesh id), (p2.xyz, unused), (unused)
 //
 // Interior nodes, FTN_BVH_WIDTH = 2 (default) -- "BVH2x64": 64-byte record with both children's boxes:
 //   n0 = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)  n1 = (c1...)  nz = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)
@@ -34,6 +36,8 @@ namespace ftn {
 #define FTN_NODE_F4 4
 #endif
 #define FTN_NODE_BYTES (16 * FTN_NODE_F4)
+#define FTN_TRI_F4 4
+#define FTN_TRI_BYTES (16 * FTN_TRI_F4)
 
 #ifndef FTN_LEAF_MAX
 #define FTN_LEAF_MAX 4
@@ -47,9 +51,10 @@ struct F4 { float x, y, z, w; };
 
 struct BvhView {
     const F4* nodes;      // FTN_NODE_F4 x F4 per node
-    const F4* tris;       // 3 x F4 per triangle, leaf order
+    const F4* tris;       // FTN_TRI_F4 x F4 per triangle, leaf order
     uint32_t n_nodes;     // 0 => no triangles
     uint32_t n_tris;
+    uint32_t wide;        // 0: BVH2x64 records (this file); 1: BVH8q compressed 8-wide records (ftn_bvh8.cuh)
 };
 
 #ifndef FTN_PREFETCH_CHILDREN
@@ -129,6 +134,13 @@ FTN_HD bool slab_test(const RaySlab& r, float lox, float hix, float loy, float h
 
 struct TraceCounters { uint32_t nodes, tris; };
 
+// the three rows of triangle record `slot` (256-bit + 128-bit load)
+FTN_HD void load_tri(const BvhView& bvh, uint32_t slot, F4* a, F4* b, F4* c) {
+    const F4* t = bvh.tris + (size_t)FTN_TRI_F4 * (size_t)slot;
+    ld8(t, *a, *b);
+    *c = ld4(t + 2);
+}
+
 FTN_HD void cswap(float& ka, int& va, float& kb, int& vb) {   // compare-exchange on (key, value)
     const bool s = kb < ka;
     const float k0 = s ? kb : ka, k1 = s ? ka : kb;
@@ -173,10 +185,10 @@ FTN_HD int node_step_impl(const BvhView& bvh, int cur, const RaySlab& slab, floa
     // the next record this ray reads is one of the two children: start both L2 -> L1 fetches now,
     // under the ~60 instructions of the two slab tests, instead of after them
     prefetch_l1(c0 >= 0 ? (const void*)(bvh.nodes + (size_t)FTN_NODE_F4 * (size_t)c0)
-                        : (FTN_PREFETCH_CHILDREN > 1 ? (const void*)(bvh.tris + 3 * (size_t)((~(uint32_t)c0) >> 2)) : (const void*)nd));
+                        : (FTN_PREFETCH_CHILDREN > 1 ? (const void*)(bvh.tris + FTN_TRI_F4 * (size_t)((~(uint32_t)c0) >> 2)) : (const void*)nd));
     if (c1 != FTN_TRAVERSAL_DONE)
         prefetch_l1(c1 >= 0 ? (const void*)(bvh.nodes + (size_t)FTN_NODE_F4 * (size_t)c1)
-                            : (FTN_PREFETCH_CHILDREN > 1 ? (const void*)(bvh.tris + 3 * (size_t)((~(uint32_t)c1) >> 2)) : (const void*)nd));
+                            : (FTN_PREFETCH_CHILDREN > 1 ? (const void*)(bvh.tris + FTN_TRI_F4 * (size_t)((~(uint32_t)c1) >> 2)) : (const void*)nd));
 #endif
     const bool h0 = slab_test<NAN_FREE>(slab, n0.x, n0.y, n0.z, n0.w, nz.x, nz.y, t_max, &e0);
     const bool h1 = slab_test<NAN_FREE>(slab, n1.x, n1.y, n1.z, n1.w, nz.z, nz.w, t_max, &e1) && c1 != FTN_TRAVERSAL_DONE;
@@ -201,8 +213,9 @@ FTN_HD bool leaf_step(const BvhView& bvh, int leaf, V3 ro, const RayShear& shear
     const uint32_t ref = ~(uint32_t)leaf;
     const uint32_t first = ref >> 2, count = (ref & 3u) + 1u;
     for (uint32_t i = 0; i < count; ++i) {
-        const F4* t = bvh.tris + 3 * (size_t)(first + i);
-        const F4 a = ld4(t), b = ld4(t + 1), c = ld4(t + 2);
+        const F4* t = bvh.tris + (size_t)FTN_TRI_F4 * (size_t)(first + i);
+        F4 a, b; ld8(t, a, b);
+        const F4 c = ld4(t + 2);
         if (COUNT) ctr->tris++;
         TriHit h;
         if (triangle_intersect(V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), V3(c.x, c.y, c.z), ro, shear, *t_max, &h)) {

@@ -234,7 +234,7 @@ FTN_HD void lbvh_emit_single(uint32_t n, const float lo[3], const float hi[3], F
     nodes[0] = n0; nodes[1] = n1; nodes[2] = nz; nodes[3] = ci;
 #endif
 }
-// 48-byte pre-gathered triangle record for leaf-order slot i
+// 64-byte pre-gathered triangle record for leaf-order slot i
 FTN_HD void lbvh_gather_tri(const float* pos, const uint32_t* idx, const uint32_t* order, uint32_t i,
                             const MeshData* meshes, uint32_t n_meshes, F4* tris) {
     const uint32_t prim = order[i];
@@ -245,7 +245,9 @@ FTN_HD void lbvh_gather_tri(const float* pos, const uint32_t* idx, const uint32_
     a.x = pos[3 * v0]; a.y = pos[3 * v0 + 1]; a.z = pos[3 * v0 + 2]; a.w = u2f(prim);
     b.x = pos[3 * v1]; b.y = pos[3 * v1 + 1]; b.z = pos[3 * v1 + 2]; b.w = u2f(lo);
     c.x = pos[3 * v2]; c.y = pos[3 * v2 + 1]; c.z = pos[3 * v2 + 2]; c.w = 0.0f;
-    tris[3 * (size_t)i] = a; tris[3 * (size_t)i + 1] = b; tris[3 * (size_t)i + 2] = c;
+    F4 z; z.x = z.y = z.z = z.w = 0.0f;
+    F4* out = tris + (size_t)FTN_TRI_F4 * (size_t)i;
+    out[0] = a; out[1] = b; out[2] = c; out[3] = z;
 }
 
 }  // namespace ftn

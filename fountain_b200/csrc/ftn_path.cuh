@@ -88,7 +88,7 @@ FTN_HD bool surface_at_hit(const SceneView& sc, uint32_t slot, const RayF& ray, 
         sphere_surface(sd, sh, s);
         return true;
     }
-    const F4 a = ld4(sc.bvh.tris + 3 * (size_t)slot), b = ld4(sc.bvh.tris + 3 * (size_t)slot + 1), c = ld4(sc.bvh.tris + 3 * (size_t)slot + 2);
+    F4 a, b, c; load_tri(sc.bvh, slot, &a, &b, &c);
     TriHit th;
     const RayShear sh = make_ray_shear(ray.d);
     if (!triangle_intersect(V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), V3(c.x, c.y, c.z), ray.o, sh, ray.t_max, &th)) return false;
@@ -98,7 +98,7 @@ FTN_HD bool surface_at_hit(const SceneView& sc, uint32_t slot, const RayF& ray, 
 
 FTN_HD int hit_material(const SceneView& sc, uint32_t slot) {
     if (slot & FTN_SPHERE_SLOT_FLAG) return sc.spheres[slot & ~FTN_SPHERE_SLOT_FLAG].material;
-    return sc.meshes[f2u(ld4(sc.bvh.tris + 3 * (size_t)slot + 1).w)].material;
+    return sc.meshes[f2u(ld4(sc.bvh.tris + (size_t)FTN_TRI_F4 * (size_t)slot + 1).w)].material;
 }
 
 FTN_HD V3 area_emitted(const LightData& l, V3 n, V3 w) {   // DiffuseAreaLight::emitted_radiance, diffuse.rs:45-51

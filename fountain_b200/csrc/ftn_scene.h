@@ -8,12 +8,17 @@
 #include <vector>
 #include "../../include/fountain_gpu.h"
 #include "ftn_bvh.cuh"
+#include "ftn_bvh8.cuh"
 
 // runtime bools -> template arguments B0, B1
 #define FTN_BOOL2(f0, f1, CALL)                                                      \
     do {                                                                             \
         if (f0) { constexpr bool B0 = true;  if (f1) { constexpr bool B1 = true; CALL; } else { constexpr bool B1 = false; CALL; } } \
         else    { constexpr bool B0 = false; if (f1) { constexpr bool B1 = true; CALL; } else { constexpr bool B1 = false; CALL; } } \
+    } while (0)
+#define FTN_BOOL1(f0, CALL)                                                          \
+    do {                                                                             \
+        if (f0) { constexpr bool B0 = true; CALL; } else { constexpr bool B0 = false; CALL; } \
     } while (0)
 #define FTN_BOOL3(f0, f1, f2, CALL)                                                  \
     do {                                                                             \
@@ -121,7 +126,7 @@ struct SceneView {
     const LightData* lights; uint32_t n_lights;
     uint32_t n_tris;
     int refill_threshold;    // persistent traversal: leave the traverse loop when fewer lanes are active
-    bool vote;               // persistent traversal: per-step node/leaf vote (large scenes) or while-while (small)
+    bool vote;               // persistent traversal over BVH2x64: per-step node/leaf vote (large scenes) or while-while (small)
     int vote_bias;           // persistent traversal: node step when 16 * #node lanes >= vote_bias * #leaf lanes
 };
 
@@ -142,6 +147,8 @@ struct FtnScene {
     bool built = false;
     ftn::F4* d_nodes = nullptr; ftn::F4* d_tris = nullptr;
     uint32_t n_nodes = 0;
+    bool wide = false;               // d_nodes holds BVH8q records (ftn_bvh8.cuh) instead of BVH2x64
+    uint32_t bvh_levels = 0;         // wide layout: levels of the tree (bounds the traversal stack)
     uint32_t* d_codes = nullptr;     // Morton code per triangle, INPUT order
     uint32_t* d_order = nullptr;     // sorted primitive order
     float bounds[6] = {0, 0, 0, 0, 0, 0};

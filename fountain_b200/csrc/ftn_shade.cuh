@@ -502,7 +502,7 @@ struct Surface {
 // Triangle::intersect tail, triangle.rs:270-392, from the slot's vertices and the barycentrics
 // the traversal found (exact ops: p, p_err and n feed spawned ray origins).
 FTN_HD void triangle_surface(const SceneView& sc, uint32_t slot, const TriHit& h, V3 ray_d, Surface* s) {
-    const F4 a = ld4(sc.bvh.tris + 3 * (size_t)slot), b = ld4(sc.bvh.tris + 3 * (size_t)slot + 1), c = ld4(sc.bvh.tris + 3 * (size_t)slot + 2);
+    F4 a, b, c; load_tri(sc.bvh, slot, &a, &b, &c);
     const V3 p0 = V3(a.x, a.y, a.z), p1 = V3(b.x, b.y, b.z), p2 = V3(c.x, c.y, c.z);
     const uint32_t prim = f2u(a.w), mesh_id = f2u(b.w);
     const MeshData mesh = sc.meshes[mesh_id];
@@ -685,7 +685,7 @@ FTN_HD TexDiffs tex_differentials(V3 p, V3 n, V3 dpdu, V3 dpdv, const RayDiff& d
 
 // DiffGeom::dpdu / dpdv of a triangle (triangle.rs:258-295), for the texture differentials only
 FTN_HD void triangle_dpduv(const SceneView& sc, uint32_t slot, V3* dpdu, V3* dpdv) {
-    const F4 a = ld4(sc.bvh.tris + 3 * (size_t)slot), b = ld4(sc.bvh.tris + 3 * (size_t)slot + 1), c = ld4(sc.bvh.tris + 3 * (size_t)slot + 2);
+    F4 a, b, c; load_tri(sc.bvh, slot, &a, &b, &c);
     const V3 p0 = V3(a.x, a.y, a.z), p1 = V3(b.x, b.y, b.z), p2 = V3(c.x, c.y, c.z);
     const uint32_t prim = f2u(a.w);
     const uint32_t v0 = sc.idx[3 * (size_t)prim], v1 = sc.idx[3 * (size_t)prim + 1], v2 = sc.idx[3 * (size_t)prim + 2];

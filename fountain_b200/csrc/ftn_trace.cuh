@@ -4,6 +4,7 @@
 #include "ftn_scene.h"
 #include "ftn_geom.cuh"
 #include "ftn_bvh.cuh"
+#include "ftn_bvh8.cuh"
 
 namespace ftn {
 
@@ -40,7 +41,8 @@ FTN_HD void scene_intersect(const SceneView& sc, const RayF& ray, SceneHit* out,
         }
     }
     TriHit th;
-    const uint32_t slot = bvh_traverse<ANY, COUNT>(sc.bvh, ray.o, ray.d, &t_max, &th, ctr);
+    const uint32_t slot = sc.bvh.wide ? bvh8_traverse<ANY, COUNT>(sc.bvh, ray.o, ray.d, &t_max, &th, ctr)
+                                      : bvh_traverse<ANY, COUNT>(sc.bvh, ray.o, ray.d, &t_max, &th, ctr);
     if (slot != FTN_NO_HIT_SLOT) { out->slot = slot; out->tri = th; }
     out->t = t_max;
 }

@@ -25,10 +25,30 @@ namespace ftn {
 //          called by ALL 32 lanes together (valid = this lane has a finished ray), so it may use
 //          warp collectives (queue_push).
 // SPHERES = false compiles the EFloat sphere side list out of the kernel (scenes without spheres).
-// VOTE selects the form of the traverse loop (see below); SceneView::vote picks it per scene.
-template <bool ANY, bool COUNT, bool SPHERES, bool VOTE, class Source, class Sink>
+// MODE selects the layout and the form of the traverse loop (trace_mode(sc) picks it per scene):
+//   FTN_MODE_WHILE  BVH2x64, while-while      FTN_MODE_VOTE  BVH2x64, per-step vote      FTN_MODE_WIDE  BVH8q (below)
+#define FTN_MODE_WHILE 0
+#define FTN_MODE_VOTE 1
+#define FTN_MODE_WIDE 2
+inline int trace_mode(const SceneView& sc) { return sc.bvh.wide ? FTN_MODE_WIDE : (sc.vote ? FTN_MODE_VOTE : FTN_MODE_WHILE); }
+// runtime mode -> template argument M
+#define FTN_MODE3(mode, CALL)                                                   \
+    do {                                                                        \
+        if ((mode) == FTN_MODE_WIDE) { constexpr int M = FTN_MODE_WIDE; CALL; } \
+        else if ((mode) == FTN_MODE_VOTE) { constexpr int M = FTN_MODE_VOTE; CALL; } \
+        else { constexpr int M = FTN_MODE_WHILE; CALL; }                        \
+    } while (0)
+
+template <bool ANY, bool COUNT, bool SPHERES, class Source, class Sink>
+__device__ __forceinline__ void trace_persistent8(const SceneView& sc, uint32_t n_items, uint32_t* work_counter,
+                                                  Source& src, Sink& sink, TraceCounters& tc);
+
+template <bool ANY, bool COUNT, bool SPHERES, int MODE, class Source, class Sink>
 __device__ __forceinline__ void trace_persistent(const SceneView& sc, uint32_t n_items, uint32_t* work_counter,
                                                  Source& src, Sink& sink, TraceCounters& tc) {
+    if constexpr (MODE == FTN_MODE_WIDE) { trace_persistent8<ANY, COUNT, SPHERES>(sc, n_items, work_counter, src, sink, tc); return; }
+    else {
+    constexpr bool VOTE = MODE == FTN_MODE_VOTE;
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
     const BvhView bvh = sc.bvh;
@@ -135,6 +155,109 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sc, uint32_t n
             if (__popc(__ballot_sync(0xffffffffu, has_ray && !finished)) < thresh) break;
         }
         }
+    }
+    }
+}
+
+// ---- the same loop over the BVH8q layout (ftn_bvh8.cuh) -----------------------------------------------------------
+// Lane state: a NODE GROUP (child_base, permuted hit bits | imask) = the interior children of one node still to visit,
+// and a TRIANGLE GROUP (tri_base, permuted hit bits | counts) = its hit leaf children still to test.  A lane with a
+// triangle group waits for a leaf step, any other unfinished lane for a node step; the warp votes per step as above.
+// The stack holds node groups only: at most one entry per level of the tree (<= FTN_STACK8_SIZE, checked by the
+// build), the first FTN_STACK8_SHARED of them in shared memory ([entry][thread]: conflict-free for any mix of depths),
+// the rest in local memory.
+template <bool ANY, bool COUNT, bool SPHERES, class Source, class Sink>
+__device__ __forceinline__ void trace_persistent8(const SceneView& sc, uint32_t n_items, uint32_t* work_counter,
+                                                  Source& src, Sink& sink, TraceCounters& tc) {
+    __shared__ uint2 s_stack[FTN_STACK8_SHARED][FTN_TRACE_THREADS];
+    uint2 l_stack[FTN_STACK8_SIZE - FTN_STACK8_SHARED];
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    const BvhView bvh = sc.bvh;
+    bool has_ray = false, finished = false, exhausted = false;
+    uint32_t item = 0;
+    RayF ray; ray.o = v3s(0.0f); ray.d = v3s(0.0f); ray.t_max = 0.0f; ray.time = 0.0f;
+    Ray8 r8; r8.o = v3s(0.0f); r8.idir = v3s(1.0f); r8.octinv = 7u;
+    RayShear shear; shear.kx = 0; shear.ky = 1; shear.kz = 2; shear.sx = shear.sy = shear.sz = 0.0f;
+    SceneHit hit; hit.slot = FTN_NO_HIT_SLOT; hit.t = 0.0f; hit.tri.t = hit.tri.b0 = hit.tri.b1 = hit.tri.b2 = 0.0f;
+    float t_max = 0.0f;
+    uint32_t ng_base = 0u, ng_bits = 0u, tg_base = 0u, tg_bits = 0u;   // no hit bits in either group = nothing to do
+    int sp = 0;
+
+    for (;;) {
+        // ---- flush ----
+        hit.t = t_max;
+        sink.store(finished, item, ray, hit);
+        if (finished) { has_ray = false; finished = false; }
+        // ---- refill ----
+        const unsigned idle = __ballot_sync(0xffffffffu, !has_ray);
+        if (idle != 0u && !exhausted) {
+            const int n_idle = __popc(idle), leader = __ffs(idle) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(work_counter, (uint32_t)n_idle);
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (!has_ray) {
+                const uint32_t k = base + (uint32_t)__popc(idle & lt);
+                if (k < n_items) {
+                    item = k;
+                    has_ray = true;
+                    hit.slot = FTN_NO_HIT_SLOT;
+                    ng_bits = 0u; tg_bits = 0u; sp = 0;
+                    if (!src.load(k, &ray)) { finished = true; t_max = ray.t_max; }
+                    else {
+                        t_max = ray.t_max;
+                        if (SPHERES) {
+                            for (uint32_t i = 0; i < sc.n_spheres; ++i) {
+                                RayF r = ray; r.t_max = t_max;
+                                SphereHit sh;
+                                if (COUNT) tc.tris++;
+                                if (sphere_intersect(sc.spheres[i], r, &sh)) { t_max = sh.t; hit.slot = FTN_SPHERE_SLOT_FLAG | i; if (ANY) break; }
+                            }
+                        }
+                        if ((ANY && hit.slot != FTN_NO_HIT_SLOT) || bvh.n_nodes == 0u) finished = true;
+                        else {
+                            r8 = make_ray8(ray.o, ray.d); shear = make_ray_shear(ray.d);
+                            ng_base = 0u; ng_bits = (1u << r8.octinv) | (1u << 8);   // the root as the only child of a virtual group
+                        }
+                    }
+                }
+            }
+            if (base + (uint32_t)n_idle >= n_items) exhausted = true;   // warp-uniform
+        }
+        if (__ballot_sync(0xffffffffu, has_ray) == 0u) break;
+        // ---- traverse ----
+        const int thresh = exhausted ? 1 : sc.refill_threshold;
+        const int bias = sc.vote_bias;
+        for (;;) {
+            const bool want_leaf = (tg_bits & 0xFFu) != 0u;
+            const bool want_node = !want_leaf && (ng_bits & 0xFFu) != 0u;
+            const unsigned m_node = __ballot_sync(0xffffffffu, want_node), m_leaf = __ballot_sync(0xffffffffu, want_leaf);
+            if (__popc(m_node | m_leaf) < thresh) break;
+            if (16 * __popc(m_node) >= bias * __popc(m_leaf)) {
+                if (want_node) {
+                    const uint32_t node = node8_pop_child(ng_base, ng_bits, r8.octinv);
+                    if (ng_bits & 0xFFu) {                                        // siblings left: keep the group for later
+                        const uint2 e = make_uint2(ng_base, ng_bits);
+                        if (sp < FTN_STACK8_SHARED) s_stack[sp][threadIdx.x] = e; else l_stack[sp - FTN_STACK8_SHARED] = e;
+                        ++sp;
+                    }
+                    if (COUNT) tc.nodes++;
+                    const Node8Hits h = node8_test(bvh.nodes, node, r8, t_max);
+                    ng_base = h.child_base; ng_bits = h.ng_bits; tg_base = h.tri_base; tg_bits = h.tg_bits;
+                }
+            } else if (want_leaf) {
+                uint32_t first, count;
+                node8_pop_leaf(tg_base, tg_bits, r8.octinv, &first, &count);
+                if (tris8_test<ANY, COUNT>(bvh, first, count, ray.o, shear, &t_max, &hit.slot, &hit.tri, &tc)) { tg_bits = 0u; ng_bits = 0u; sp = 0; }
+            }
+            // a lane with nothing left in either group takes the next group from its stack
+            if (!((tg_bits | ng_bits) & 0xFFu) && sp > 0) {
+                --sp;
+                const uint2 e = (sp < FTN_STACK8_SHARED) ? s_stack[sp][threadIdx.x] : l_stack[sp - FTN_STACK8_SHARED];
+                ng_base = e.x; ng_bits = e.y;
+            }
+        }
+        if (has_ray && !((tg_bits | ng_bits) & 0xFFu) && sp == 0) finished = true;
     }
 }
 

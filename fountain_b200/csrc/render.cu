@@ -148,14 +148,14 @@ struct ExtendSink {
         queue_push(qs.q, counts, target, path);   // all 32 lanes arrive here together
     }
 };
-template <bool COUNT, bool SPH, bool VOTE>
+template <bool COUNT, bool SPH, int MODE>
 __global__ void FTN_TRACE_LAUNCH_BOUNDS
 k_extend(SceneView sc, PathArrays pa, const uint32_t* __restrict__ queue_in, uint32_t n_in, Queues qs, uint32_t* __restrict__ counts,
          unsigned long long* __restrict__ trav, bool miss_always) {
     PathRaySource src; src.pa = pa; src.queue = queue_in;
     ExtendSink sink; sink.sc = sc; sink.pa = pa; sink.queue = queue_in; sink.qs = qs; sink.counts = counts; sink.miss_always = miss_always;
     TraceCounters tc; tc.nodes = 0; tc.tris = 0;
-    trace_persistent<false, COUNT, SPH, VOTE>(sc, n_in, &counts[W_EXTEND], src, sink, tc);
+    trace_persistent<false, COUNT, SPH, MODE>(sc, n_in, &counts[W_EXTEND], src, sink, tc);
     if (COUNT) flush_trace_counters(tc, trav);
 }
 
@@ -233,13 +233,13 @@ struct ShadowSink {
         st3(pa.L, path, ld3(pa.L, path) + ld3(pa.sh_L, path));
     }
 };
-template <bool COUNT, bool SPH, bool VOTE>
+template <bool COUNT, bool SPH, int MODE>
 __global__ void FTN_TRACE_LAUNCH_BOUNDS
 k_shadow(SceneView sc, PathArrays pa, const uint32_t* __restrict__ queue, uint32_t* __restrict__ counts, unsigned long long* __restrict__ trav) {
     ShadowSource src; src.pa = pa; src.queue = queue;
     ShadowSink sink; sink.pa = pa; sink.queue = queue;
     TraceCounters tc; tc.nodes = 0; tc.tris = 0;
-    trace_persistent<true, COUNT, SPH, VOTE>(sc, counts[Q_SHADOW], &counts[W_SHADOW], src, sink, tc);
+    trace_persistent<true, COUNT, SPH, MODE>(sc, counts[Q_SHADOW], &counts[W_SHADOW], src, sink, tc);
     if (COUNT) flush_trace_counters(tc, trav);
 }
 
@@ -263,13 +263,13 @@ struct MisSink {
     }
 };
 // ENV_ONLY: with only infinite lights a hit contributes nothing whatever it is, so any-hit suffices
-template <bool ENV_ONLY, bool COUNT, bool SPH, bool VOTE>
+template <bool ENV_ONLY, bool COUNT, bool SPH, int MODE>
 __global__ void FTN_TRACE_LAUNCH_BOUNDS
 k_mis(SceneView sc, PathArrays pa, const uint32_t* __restrict__ queue, uint32_t* __restrict__ counts, unsigned long long* __restrict__ trav) {
     MisSource src; src.pa = pa; src.queue = queue;
     MisSink sink; sink.sc = sc; sink.pa = pa; sink.queue = queue;
     TraceCounters tc; tc.nodes = 0; tc.tris = 0;
-    trace_persistent<ENV_ONLY, COUNT, SPH, VOTE>(sc, counts[Q_MIS], &counts[W_MIS], src, sink, tc);
+    trace_persistent<ENV_ONLY, COUNT, SPH, MODE>(sc, counts[Q_MIS], &counts[W_MIS], src, sink, tc);
     if (COUNT) flush_trace_counters(tc, trav);
 }
 
@@ -427,6 +427,7 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
     pp.spp = smp->samples_per_pixel; pp.s_stride = smp->sample_stride;
     pp.integrator = integ->type; pp.max_depth = integ->max_depth; pp.rr_threshold = integ->rr_threshold;
 
+    const int tmode = trace_mode(sc);
     for (int done = 0; done < n_samples; done += s_per_pass) {
         const int sc_n = std::min(s_per_pass, n_samples - done);
         pp.s_first = smp->sample_begin + done * smp->sample_stride;
@@ -446,7 +447,7 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
             Queues q = qs; q.q[Q_ACTIVE_OUT] = q_out;
             const unsigned ge = trace_grid(n_active, FTN_TRACE_BLOCKS_PER_SM);
             timer.begin(0);
-            FTN_BOOL3(count_traversal, sph, sc.vote, (k_extend<B0, B1, B2><<<ge, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q_in, n_active, q, counts, d_trav, integ->type == FTN_INTEGRATOR_DIRECT_LIGHTING)));
+            FTN_MODE3(tmode, FTN_BOOL2(count_traversal, sph, (k_extend<B0, B1, M><<<ge, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q_in, n_active, q, counts, d_trav, integ->type == FTN_INTEGRATOR_DIRECT_LIGHTING))));
             timer.end();
             FTN_LAUNCHED();
             class_rays[0] += n_active;
@@ -486,12 +487,12 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
             FTN_CUDA(cudaEventRecord(ev_counts, st));
             const unsigned gq = trace_grid(n_active, FTN_TRACE_BLOCKS_PER_SM);
             timer.begin(1);
-            FTN_BOOL3(count_traversal, sph, sc.vote, (k_shadow<B0, B1, B2><<<gq, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_SHADOW], counts, d_trav + 2)));
+            FTN_MODE3(tmode, FTN_BOOL2(count_traversal, sph, (k_shadow<B0, B1, M><<<gq, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_SHADOW], counts, d_trav + 2))));
             timer.end();
             FTN_LAUNCHED();
             timer.begin(2);
-            if (has_area) { FTN_BOOL3(count_traversal, sph, sc.vote, (k_mis<false, B0, B1, B2><<<gq, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts, d_trav + 4))); }
-            else { FTN_BOOL3(count_traversal, sph, sc.vote, (k_mis<true, B0, B1, B2><<<gq, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts, d_trav + 4))); }
+            if (has_area) { FTN_MODE3(tmode, FTN_BOOL2(count_traversal, sph, (k_mis<false, B0, B1, M><<<gq, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts, d_trav + 4)))); }
+            else { FTN_MODE3(tmode, FTN_BOOL2(count_traversal, sph, (k_mis<true, B0, B1, M><<<gq, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts, d_trav + 4)))); }
             timer.end();
             FTN_LAUNCHED();
             FTN_CUDA(cudaEventSynchronize(ev_counts));
@@ -520,7 +521,7 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
         stats->camera_samples = camera_samples;
         stats->rays_closest = class_rays[0] + class_rays[2]; stats->rays_any = class_rays[1];   // Scene::intersect / intersect_test calls
         stats->device_seconds = ms * 1e-3; stats->bvh_build_seconds = s->build_seconds; stats->morton_sort_seconds = s->sort_seconds;
-        stats->bvh_nodes = s->n_nodes; stats->bvh_node_bytes = FTN_NODE_BYTES; stats->bvh_tri_bytes = 48;
+        stats->bvh_nodes = s->n_nodes; stats->bvh_node_bytes = s->wide ? FTN_NODE8_BYTES : FTN_NODE_BYTES; stats->bvh_tri_bytes = FTN_TRI_BYTES;
         double tsec[4] = {0, 0, 0, 0}; uint64_t tl[4] = {0, 0, 0, 0};
         timer.collect(tsec, tl);
         for (int c = 0; c < 3; ++c) { stats->trace_seconds[c] = tsec[c]; stats->trace_launches[c] = tl[c]; }

@@ -9,10 +9,12 @@
 //   k_lbvh_topology   Karras hierarchy over the sorted keys
 //   k_lbvh_refit      bottom-up boxes with per-node arrival counters
 //   k_lbvh_emit       leaf collapse (<= FTN_LEAF_MAX triangles) + BVH2x64 node records
-//   k_gather_tris     48-byte pre-gathered triangle records in leaf order
+//   k_bvh8_level      (default layout) level-synchronous collapse of the binary tree into BVH8q records (ftn_bvh8.cuh)
+//   k_gather_tris     64-byte pre-gathered triangle records in leaf order
 #include "ftn_scene.h"
 #include "ftn_lbvh.cuh"
 #include "ftn_ploc.cuh"
+#include "ftn_bvh8_build.cuh"
 #include <cstdio>
 #include <cstdlib>
 #define FTN_REFILL_THRESHOLD_DEFAULT 16
@@ -284,6 +286,46 @@ k_gather_tris(const float* __restrict__ pos, const uint32_t* __restrict__ idx, c
     if (i < n) lbvh_gather_tri(pos, idx, order, i, meshes, n_meshes, tris);
 }
 
+
+// ---- BVH8q collapse (body in ftn_bvh8_build.cuh) ------------------------------------------------------------------
+// One launch per level of the wide tree.  ctr[l] = number of wide nodes of level l (ctr[0] = 1, the root); the nodes of
+// level l are records [sum ctr[0..l), +ctr[l]) and brefs[] holds the binary subtree each of them covers.  A node reserves
+// the records of its interior children with one atomicAdd on ctr[l + 1] and its triangles with one on ctr[BVH8_CTR_TRIS]:
+// record and triangle ADDRESSES depend on the order of those atomics, the tree and every traversal result do not.
+#define BVH8_MAX_LEVELS 256
+#define BVH8_CTR_TRIS (BVH8_MAX_LEVELS + 1)
+#define BVH8_CTR_ERROR (BVH8_MAX_LEVELS + 2)
+#define BVH8_CTR_COUNT (BVH8_MAX_LEVELS + 3)
+struct Bvh8DeviceAlloc {
+    uint32_t next_begin, max_nodes; uint32_t* ctr; uint32_t level;
+    __device__ void operator()(uint32_t n_inner, uint32_t n_tris, uint32_t* child_base, uint32_t* tri_base) const {
+        uint32_t cb = next_begin + (n_inner ? atomicAdd(&ctr[level + 1], n_inner) : 0u);
+        if (cb + n_inner > max_nodes) { atomicExch(&ctr[BVH8_CTR_ERROR], 1u); cb = 0u; }   // cannot happen (bvh8_max_nodes); reported, not trusted
+        *child_base = cb;
+        *tri_base = n_tris ? atomicAdd(&ctr[BVH8_CTR_TRIS], n_tris) : 0u;
+    }
+};
+__global__ void __launch_bounds__(128)
+k_bvh8_level(LbvhArrays a, const F4* __restrict__ leaf_lo, const F4* __restrict__ leaf_hi, uint32_t level, uint32_t* __restrict__ ctr,
+             F4* __restrict__ nodes, uint32_t* __restrict__ brefs, const uint32_t* __restrict__ order_in, uint32_t* __restrict__ order_out,
+             uint32_t max_nodes, uint32_t single_count, const BuildBounds* __restrict__ gb) {
+    __shared__ uint32_t s_begin;
+    if (threadIdx.x == 0) { uint32_t b = 0; for (uint32_t l = 0; l < level; ++l) b += ctr[l]; s_begin = b; }
+    __syncthreads();
+    const uint32_t begin = s_begin, cnt = ctr[level];
+    if (level + 1u >= (uint32_t)BVH8_MAX_LEVELS) { if (cnt != 0u && threadIdx.x == 0 && blockIdx.x == 0) atomicExch(&ctr[BVH8_CTR_ERROR], 2u); return; }
+    Bvh8DeviceAlloc alloc; alloc.next_begin = begin + cnt; alloc.max_nodes = max_nodes; alloc.ctr = ctr; alloc.level = level;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+        const uint32_t w = begin + i, bref = brefs[w];
+        F4 lo, hi;
+        if (single_count != 0u) {
+            lo.x = float_unflip(gb->scene_lo[0]); lo.y = float_unflip(gb->scene_lo[1]); lo.z = float_unflip(gb->scene_lo[2]); lo.w = 0.0f;
+            hi.x = float_unflip(gb->scene_hi[0]); hi.y = float_unflip(gb->scene_hi[1]); hi.z = float_unflip(gb->scene_hi[2]); hi.w = 0.0f;
+        } else bvh8_ref_box(a, leaf_lo, leaf_hi, bref, &lo, &hi);
+        bvh8_collapse_node(a, leaf_lo, leaf_hi, bref, single_count, lo, hi, w, alloc, nodes, brefs, order_in, order_out);
+    }
+}
+
 // ---- env-map tables on the device -------------------------------------------------------------------------
 // MIPMap level-0 lookups (mipmap.rs:245-312); shared with the shading kernels via ftn_shade.cuh.
 }  // namespace ftn
@@ -398,7 +440,7 @@ int release_cached_memory() {
 
 SceneView make_view(const FtnScene& s) {
     SceneView v;
-    v.bvh.nodes = s.d_nodes; v.bvh.tris = s.d_tris; v.bvh.n_nodes = s.n_nodes; v.bvh.n_tris = s.n_tris;
+    v.bvh.nodes = s.d_nodes; v.bvh.tris = s.d_tris; v.bvh.n_nodes = s.n_nodes; v.bvh.n_tris = s.n_tris; v.bvh.wide = s.wide ? 1u : 0u;
     v.pos = s.d_pos; v.nrm = s.d_nrm; v.uv = s.d_uv; v.idx = s.d_idx;
     v.meshes = s.d_meshes; v.materials = s.d_materials;
     v.spheres = s.d_spheres; v.n_spheres = s.n_spheres;
@@ -657,6 +699,10 @@ int bvh_build(FtnScene* s) {
         // of build time against 0.15 ms saved per render, hence the size threshold.
         const char* builder_env = getenv("FTN_BVH_BUILDER");
         const bool use_ploc = builder_env ? std::string(builder_env) == "ploc" : n >= FTN_PLOC_MIN_TRIS;
+        // Node layout: BVH8q (compressed 8-wide, ftn_bvh8.cuh) unless FTN_BVH_LAYOUT=bvh2 asks for the BVH2x64 records
+        const char* layout_env = getenv("FTN_BVH_LAYOUT");
+        const bool wide = layout_env ? std::string(layout_env) != "bvh2" : true;
+        const size_t max_nodes8 = bvh8_max_nodes(n);
         // all temporaries come from the device's build arena: one (cached) allocation, no cudaFree
         // (each of which would synchronise the device) per build
         const size_t ni_max = n > 1 ? n - 1 : 1;
@@ -664,7 +710,8 @@ int bvh_build(FtnScene* s) {
         const size_t tmp_bytes = al(sizeof(BuildBounds)) + 4 * al((size_t)n * sizeof(F4)) + al((size_t)n * 4)
                                + 7 * al(ni_max * 4) + al((2 * (size_t)n - 1) * 4) + 2 * al(ni_max * sizeof(F4))
                                + al(radix_sort_scratch_bytes(n)) + al(scan_scratch_elems(ni_max) * 4) + 4096
-                               + (use_ploc ? 9 * al((size_t)n * 4) + 2 * al((size_t)n * sizeof(F4)) + al(scan_scratch_elems(n) * 4) + 4096 : 0);
+                               + (use_ploc ? 9 * al((size_t)n * 4) + 2 * al((size_t)n * sizeof(F4)) + al(scan_scratch_elems(n) * 4) + 4096 : 0)
+                               + (wide ? al(max_nodes8 * FTN_NODE8_BYTES) + al(max_nodes8 * 4) + al((size_t)n * 4) + al(BVH8_CTR_COUNT * 4) + 4096 : 0);
         DeviceArena& arena = device_arena(s->device);
         std::lock_guard<std::recursive_mutex> arena_lock(arena.m);
         char* tmp_base = nullptr; size_t tmp_off = 0;
@@ -700,9 +747,49 @@ int bvh_build(FtnScene* s) {
             if ((rc = dalloc((void**)&leaf_lo, (size_t)n * sizeof(F4))) != FTN_OK) break;
             if ((rc = dalloc((void**)&leaf_hi, (size_t)n * sizeof(F4))) != FTN_OK) break;
             k_gather_leaf_boxes<<<gb256, 256, 0, st>>>(tri_lo, tri_hi, s->d_order, n, leaf_lo, leaf_hi); count_launch();
-            if (!s->d_tris && (e = scene_malloc(&s->d_tris, (size_t)n * 3 * sizeof(F4))) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc tris", __FILE__, __LINE__); break; }
+            if (!s->d_tris && (e = scene_malloc(&s->d_tris, (size_t)n * FTN_TRI_F4 * sizeof(F4))) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc tris", __FILE__, __LINE__); break; }
             const uint32_t* final_order = s->d_order;   // leaf order of the emitted tree; PLOC: depth-first order of its tree
-            if (n <= (uint32_t)FTN_LEAF_MAX) {
+            // BVH8q: collapse the binary tree `a` (or, single_count != 0, wrap the whole scene into one leaf child) level by
+            // level, then move the records into an exact-size allocation; sets final_order to the wide tree's triangle order
+            auto collapse_wide = [&](const LbvhArrays& a8, const F4* llo, const F4* lhi, uint32_t single_count) -> int {
+                F4* nodes8 = nullptr; uint32_t *brefs = nullptr, *order8 = nullptr, *ctr = nullptr;
+                int r;
+                if ((r = dalloc((void**)&nodes8, max_nodes8 * FTN_NODE8_BYTES)) != FTN_OK || (r = dalloc((void**)&brefs, max_nodes8 * 4)) != FTN_OK ||
+                    (r = dalloc((void**)&order8, (size_t)n * 4)) != FTN_OK || (r = dalloc((void**)&ctr, BVH8_CTR_COUNT * 4)) != FTN_OK) return r;
+                cudaError_t ce;
+                const uint32_t one = 1u;
+                if ((ce = cudaMemsetAsync(ctr, 0, BVH8_CTR_COUNT * 4, st)) != cudaSuccess || (ce = cudaMemsetAsync(brefs, 0, 4, st)) != cudaSuccess ||
+                    (ce = cudaMemcpyAsync(ctr, &one, 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(ce, "bvh8 counters", __FILE__, __LINE__);
+                const unsigned g8 = (unsigned)std::min<size_t>((max_nodes8 + 127) / 128, (size_t)148 * 16);
+                std::vector<uint32_t> h_ctr(BVH8_CTR_COUNT, 0u);
+                uint32_t level = 0;
+                for (;;) {
+                    const uint32_t group = level == 0 ? 6u : 8u;    // levels launched per read-back of the counters
+                    for (uint32_t g = 0; g < group; ++g, ++level) {
+                        k_bvh8_level<<<g8, 128, 0, st>>>(a8, llo, lhi, level, ctr, nodes8, brefs, final_order, order8, (uint32_t)max_nodes8, single_count, d_gb); count_launch();
+                    }
+                    if ((ce = cudaMemcpyAsync(h_ctr.data(), ctr, BVH8_CTR_COUNT * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess || (ce = cudaStreamSynchronize(st)) != cudaSuccess)
+                        return cuda_fail(ce, "bvh8 collapse", __FILE__, __LINE__);
+                    if (h_ctr[BVH8_CTR_ERROR] != 0u) return set_error(FTN_ERR_CUDA, h_ctr[BVH8_CTR_ERROR] == 1u ? "bvh8 collapse: node bound exceeded" : "bvh8 collapse: tree deeper than the traversal stack");
+                    if (h_ctr[level] == 0u) break;                  // the last level launched produced no children
+                }
+                uint32_t total = 0, levels = 0;
+                for (uint32_t l = 0; l < (uint32_t)BVH8_MAX_LEVELS && h_ctr[l] != 0u; ++l) { total += h_ctr[l]; ++levels; }
+                if (h_ctr[BVH8_CTR_TRIS] != n) return set_error(FTN_ERR_CUDA, "bvh8 collapse: triangle count mismatch");
+                if (levels + 2u > (uint32_t)FTN_STACK8_SIZE) return set_error(FTN_ERR_CUDA, "bvh8 collapse: tree deeper than the traversal stack");
+                if (getenv("FTN_DEBUG_BUILD")) fprintf(stderr, "[ftn] BVH8q: %u triangles, %u records in %u levels\n", n, total, levels);
+                if (s->d_nodes) { scene_free(s->d_nodes); s->d_nodes = nullptr; }
+                if ((ce = scene_malloc(&s->d_nodes, (size_t)total * FTN_NODE8_BYTES)) != cudaSuccess) return cuda_fail(ce, "cudaMalloc nodes", __FILE__, __LINE__);
+                if ((ce = cudaMemcpyAsync(s->d_nodes, nodes8, (size_t)total * FTN_NODE8_BYTES, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return cuda_fail(ce, "copy nodes", __FILE__, __LINE__);
+                s->n_nodes = total; s->bvh_levels = levels; s->wide = true;
+                final_order = order8;
+                return FTN_OK;
+            };
+            if (wide && n <= (uint32_t)FTN_LEAF8_MAX) {
+                LbvhArrays none; std::memset(&none, 0, sizeof(none));
+                if ((rc = collapse_wide(none, leaf_lo, leaf_hi, n)) != FTN_OK) break;
+                k_gather_tris<<<gb256, 256, 0, st>>>(s->d_pos, s->d_idx, final_order, n, s->d_meshes, s->n_meshes, s->d_tris); count_launch();
+            } else if (!wide && n <= (uint32_t)FTN_LEAF_MAX) {
                 k_gather_tris<<<gb256, 256, 0, st>>>(s->d_pos, s->d_idx, final_order, n, s->d_meshes, s->n_meshes, s->d_tris); count_launch();
                 if (!s->d_nodes && (e = scene_malloc(&s->d_nodes, FTN_NODE_F4 * sizeof(F4))) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc nodes", __FILE__, __LINE__); break; }
                 k_lbvh_emit_single<<<1, 32, 0, st>>>(n, d_gb, s->d_nodes); count_launch();
@@ -780,7 +867,6 @@ int bvh_build(FtnScene* s) {
                         ploc_done = true;
                     }
                 }
-                k_gather_tris<<<gb256, 256, 0, st>>>(s->d_pos, s->d_idx, final_order, n, s->d_meshes, s->n_meshes, s->d_tris); count_launch();
                 if (!ploc_done) {
                     if ((e = cudaMemsetAsync(a.arrive, 0, ni * 4, st)) != cudaSuccess) { rc = cuda_fail(e, "memset arrive", __FILE__, __LINE__); break; }
                     k_lbvh_topology<<<gi, 256, 0, st>>>(keys, (int)n, a); count_launch();
@@ -788,6 +874,11 @@ int bvh_build(FtnScene* s) {
                     k_lbvh_survive<<<gi, 256, 0, st>>>((int)n, a, survive); count_launch();
                 }
                 if ((e = cudaGetLastError()) != cudaSuccess) { rc = cuda_fail(e, "lbvh kernels", __FILE__, __LINE__); break; }
+                if (wide) {
+                    if ((rc = collapse_wide(a, leaf_lo, leaf_hi, 0u)) != FTN_OK) break;
+                    k_gather_tris<<<gb256, 256, 0, st>>>(s->d_pos, s->d_idx, final_order, n, s->d_meshes, s->n_meshes, s->d_tris); count_launch();
+                } else {
+                k_gather_tris<<<gb256, 256, 0, st>>>(s->d_pos, s->d_idx, final_order, n, s->d_meshes, s->n_meshes, s->d_tris); count_launch();
                 uint32_t last_flag = 0, last_idx = 0;
                 k_lbvh_mark_records<<<gi, 256, 0, st>>>((int)n, a, survive, is_record); count_launch();
                 if ((e = cudaMemcpyAsync(&last_flag, is_record + ni - 1, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { rc = cuda_fail(e, "read record flags", __FILE__, __LINE__); break; }
@@ -800,6 +891,7 @@ int bvh_build(FtnScene* s) {
                 if (s->d_nodes) { scene_free(s->d_nodes); s->d_nodes = nullptr; }
                 if ((e = scene_malloc(&s->d_nodes, (size_t)s->n_nodes * FTN_NODE_F4 * sizeof(F4))) != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc nodes", __FILE__, __LINE__); break; }
                 k_lbvh_emit<<<gi, 256, 0, st>>>((int)n, a, leaf_lo, leaf_hi, survive, is_record, new_index, s->d_nodes); count_launch();
+                }
             }
             if ((e = cudaGetLastError()) != cudaSuccess) { rc = cuda_fail(e, "emit kernels", __FILE__, __LINE__); break; }
             BuildBounds hb;

@@ -29,19 +29,19 @@ struct BatchSink {
         uint32_t prim; float t = h.t, b1 = 0.0f, b2 = 0.0f;
         if (h.slot == FTN_NO_HIT_SLOT) { prim = FTN_NO_HIT; t = ray.t_max; }
         else if (h.slot & FTN_SPHERE_SLOT_FLAG) prim = sc.n_tris + (h.slot & ~FTN_SPHERE_SLOT_FLAG);
-        else { prim = f2u(ld4(sc.bvh.tris + 3 * (size_t)h.slot).w); b1 = h.tri.b1; b2 = h.tri.b2; }
+        else { prim = f2u(ld4(sc.bvh.tris + (size_t)FTN_TRI_F4 * (size_t)h.slot).w); b1 = h.tri.b1; b2 = h.tri.b2; }
         __stcs(reinterpret_cast<float4*>(hits) + i, make_float4(__uint_as_float(prim), t, b1, b2));
     }
 };
 
-template <bool ANY, bool COUNT, bool SPH, bool VOTE>
+template <bool ANY, bool COUNT, bool SPH, int MODE>
 __global__ void FTN_TRACE_LAUNCH_BOUNDS
 k_intersect_batch(SceneView sc, const FtnRay* __restrict__ rays, FtnHit* __restrict__ hits, uint8_t* __restrict__ any_out,
                   uint32_t n, uint32_t* __restrict__ work_counter, unsigned long long* __restrict__ counters) {
     BatchSource src; src.rays = rays;
     BatchSink<ANY> sink; sink.sc = sc; sink.hits = hits; sink.any_out = any_out;
     TraceCounters tc; tc.nodes = 0; tc.tris = 0;
-    trace_persistent<ANY, COUNT, SPH, VOTE>(sc, n, work_counter, src, sink, tc);
+    trace_persistent<ANY, COUNT, SPH, MODE>(sc, n, work_counter, src, sink, tc);
     if (COUNT) {
         unsigned long long nn = tc.nodes, tt = tc.tris;
 #pragma unroll
@@ -84,9 +84,10 @@ int intersect_device(const FtnScene* s, size_t n, const FtnRay* d_rays, FtnHit* 
         FtnHit* h = d_hits ? d_hits + off : nullptr;
         uint8_t* a = d_any ? d_any + off : nullptr;
         const bool sph = s->n_spheres != 0, count = d_counters != nullptr;
-        if (any) { FTN_BOOL2(sph, sc.vote, (k_intersect_batch<true, false, B0, B1><<<grid, FTN_TRACE_THREADS, 0, st>>>(sc, r, nullptr, a, m, d_work, nullptr))); }
-        else if (count) { FTN_BOOL2(sph, sc.vote, (k_intersect_batch<false, true, B0, B1><<<grid, FTN_TRACE_THREADS, 0, st>>>(sc, r, h, nullptr, m, d_work, d_counters))); }
-        else { FTN_BOOL2(sph, sc.vote, (k_intersect_batch<false, false, B0, B1><<<grid, FTN_TRACE_THREADS, 0, st>>>(sc, r, h, nullptr, m, d_work, nullptr))); }
+        const int mode = trace_mode(sc);
+        if (any) { FTN_MODE3(mode, FTN_BOOL1(sph, (k_intersect_batch<true, false, B0, M><<<grid, FTN_TRACE_THREADS, 0, st>>>(sc, r, nullptr, a, m, d_work, nullptr)))); }
+        else if (count) { FTN_MODE3(mode, FTN_BOOL1(sph, (k_intersect_batch<false, true, B0, M><<<grid, FTN_TRACE_THREADS, 0, st>>>(sc, r, h, nullptr, m, d_work, d_counters)))); }
+        else { FTN_MODE3(mode, FTN_BOOL1(sph, (k_intersect_batch<false, false, B0, M><<<grid, FTN_TRACE_THREADS, 0, st>>>(sc, r, h, nullptr, m, d_work, nullptr)))); }
         if (off + chunk < n) { FTN_LAUNCHED(); }
     }
     FTN_LAUNCHED();

@@ -18,6 +18,7 @@
 #include "../../fountain_b200/csrc/ftn_path.cuh"
 #include "../../fountain_b200/csrc/ftn_lbvh.cuh"
 #include "../../fountain_b200/csrc/ftn_ploc.cuh"
+#include "../../fountain_b200/csrc/ftn_bvh8_build.cuh"
 
 using namespace ftn;
 
@@ -31,12 +32,12 @@ struct SimScene {
     std::vector<SphereData> spheres; std::vector<LightData> lights;
     std::vector<std::vector<F4>> env_tex; std::vector<std::vector<float>> env_f;   // storage behind EnvLightData pointers
     std::list<std::vector<F4>> images;   // storage behind MaterialData::image
-    std::vector<F4> nodes, tris; uint32_t n_nodes = 0;
+    std::vector<F4> nodes, tris; uint32_t n_nodes = 0; bool wide = false; uint32_t bvh_levels = 0;
     std::vector<uint32_t> codes, order;
     float bounds[6]; bool built = false; uint32_t n_tris = 0;
     SceneView view() const {
         SceneView v;
-        v.bvh.nodes = nodes.data(); v.bvh.tris = tris.data(); v.bvh.n_nodes = n_nodes; v.bvh.n_tris = n_tris;
+        v.bvh.nodes = nodes.data(); v.bvh.tris = tris.data(); v.bvh.n_nodes = n_nodes; v.bvh.n_tris = n_tris; v.bvh.wide = wide ? 1u : 0u;
         v.pos = pos.data(); v.nrm = nrm.empty() ? nullptr : nrm.data(); v.uv = uv.empty() ? nullptr : uv.data(); v.idx = idx.data();
         v.meshes = meshes.data(); v.materials = mats.data(); v.spheres = spheres.data(); v.n_spheres = (uint32_t)spheres.size();
         v.lights = lights.data(); v.n_lights = (uint32_t)lights.size(); v.n_tris = n_tris; v.refill_threshold = 20; v.vote_bias = 14; v.vote = true;
@@ -165,11 +166,47 @@ SIM_API int sim_bvh_build(SimScene* s) {
         for (uint32_t i = 0; i < n; ++i) keys[i] = s->codes[s->order[i]];
         std::vector<F4> leaf_lo(n), leaf_hi(n);
         for (uint32_t i = 0; i < n; ++i) { leaf_lo[i] = tri_lo[s->order[i]]; leaf_hi[i] = tri_hi[s->order[i]]; }
-        s->tris.resize(3 * (size_t)n);
+        s->tris.resize((size_t)FTN_TRI_F4 * (size_t)n);
         std::vector<uint32_t> final_order = s->order;   // leaf order of the emitted tree (PLOC: depth-first order)
         const char* builder_env = getenv("FTN_BVH_BUILDER");
         const bool use_ploc = builder_env ? std::string(builder_env) == "ploc" : n >= 65536u;   // the policy of scene.cu
-        if (n <= (uint32_t)FTN_LEAF_MAX) {
+        const char* layout_env = getenv("FTN_BVH_LAYOUT");
+        const bool wide = layout_env ? std::string(layout_env) != "bvh2" : true;   // the policy of scene.cu
+        // k_bvh8_level of scene.cu, level by level, one node at a time
+        struct HostAlloc {
+            uint32_t next_nodes = 1, next_tris = 0;
+            void operator()(uint32_t ni, uint32_t nt, uint32_t* cb, uint32_t* tb) { *cb = next_nodes; next_nodes += ni; *tb = next_tris; next_tris += nt; }
+        };
+        auto collapse_wide = [&](const LbvhArrays& a8, const F4* llo, const F4* lhi, uint32_t single_count) -> int {
+            const size_t max_nodes = bvh8_max_nodes(n);
+            std::vector<F4> nodes8(max_nodes * FTN_NODE8_F4); std::vector<uint32_t> brefs(max_nodes, 0u), order8(n, 0xFFFFFFFFu);
+            HostAlloc alloc;
+            uint32_t begin = 0, end = 1, levels = 0;
+            while (begin < end) {
+                ++levels;
+                for (uint32_t w = begin; w < end; ++w) {
+                    F4 blo, bhi;
+                    if (single_count) { blo.x = lo[0]; blo.y = lo[1]; blo.z = lo[2]; blo.w = 0; bhi.x = hi[0]; bhi.y = hi[1]; bhi.z = hi[2]; bhi.w = 0; }
+                    else bvh8_ref_box(a8, llo, lhi, brefs[w], &blo, &bhi);
+                    bvh8_collapse_node(a8, llo, lhi, brefs[w], single_count, blo, bhi, w, alloc, nodes8.data(), brefs.data(), final_order.data(), order8.data());
+                    if (alloc.next_nodes > max_nodes) return fail(FTN_ERR_CUDA, "bvh8 collapse: node bound exceeded");
+                }
+                begin = end; end = alloc.next_nodes;
+            }
+            if (alloc.next_tris != n) return fail(FTN_ERR_CUDA, "bvh8 collapse: triangle count mismatch");
+            if (levels + 2u > (uint32_t)FTN_STACK8_SIZE) return fail(FTN_ERR_CUDA, "bvh8 collapse: too deep");
+            for (uint32_t i = 0; i < n; ++i) if (order8[i] == 0xFFFFFFFFu) return fail(FTN_ERR_CUDA, "bvh8 collapse: triangle order has holes");
+            nodes8.resize((size_t)alloc.next_nodes * FTN_NODE8_F4);
+            s->nodes = nodes8; s->n_nodes = alloc.next_nodes; s->wide = true; s->bvh_levels = levels;
+            final_order = order8;
+            if (getenv("FTN_DEBUG_BUILD")) fprintf(stderr, "[sim] BVH8q: %u triangles, %u records in %u levels\n", n, s->n_nodes, levels);
+            return FTN_OK;
+        };
+        if (wide && n <= (uint32_t)FTN_LEAF8_MAX) {
+            LbvhArrays none; std::memset(&none, 0, sizeof(none));
+            if (int rc = collapse_wide(none, leaf_lo.data(), leaf_hi.data(), n)) return rc;
+            for (uint32_t i = 0; i < n; ++i) lbvh_gather_tri(s->pos.data(), s->idx.data(), final_order.data(), i, s->meshes.data(), (uint32_t)s->meshes.size(), s->tris.data());
+        } else if (!wide && n <= (uint32_t)FTN_LEAF_MAX) {
             for (uint32_t i = 0; i < n; ++i) lbvh_gather_tri(s->pos.data(), s->idx.data(), final_order.data(), i, s->meshes.data(), (uint32_t)s->meshes.size(), s->tris.data());
             s->nodes.resize(FTN_NODE_F4); lbvh_emit_single(n, lo, hi, s->nodes.data()); s->n_nodes = 1;
         } else {
@@ -216,7 +253,6 @@ SIM_API int sim_bvh_build(SimScene* s) {
                     std::fill(parent.begin(), parent.end(), PLOC_NONE); std::fill(arrive.begin(), arrive.end(), 0u);
                 }
             }
-            for (uint32_t i = 0; i < n; ++i) lbvh_gather_tri(s->pos.data(), s->idx.data(), final_order.data(), i, s->meshes.data(), (uint32_t)s->meshes.size(), s->tris.data());
             if (!ploc_done) {
             for (size_t i = 0; i < ni; ++i) lbvh_topology_node(keys.data(), (int)n, (int)i, a);   // k_lbvh_topology
             for (uint32_t leaf = 0; leaf < n; ++leaf) {   // k_lbvh_refit: second arrival joins
@@ -229,12 +265,16 @@ SIM_API int sim_bvh_build(SimScene* s) {
             }
             for (size_t i = 0; i < ni; ++i) { if (arrive[i] != 2u) return fail(FTN_ERR_CUDA, "refit did not reach every node twice"); }
             }
+            if (wide) { if (int rc = collapse_wide(a, leaf_lo.data(), leaf_hi.data(), 0u)) return rc; }
+            for (uint32_t i = 0; i < n; ++i) lbvh_gather_tri(s->pos.data(), s->idx.data(), final_order.data(), i, s->meshes.data(), (uint32_t)s->meshes.size(), s->tris.data());
+            if (!wide) {
             uint32_t run = 0;
             for (size_t i = 0; i < ni; ++i) survive[i] = ploc_done ? ploc_survives(a, (int)i) : lbvh_survives(a, (int)i);   // k_lbvh_survive
             std::vector<uint32_t> is_record(ni);
             for (size_t i = 0; i < ni; ++i) { is_record[i] = lbvh_is_record(a, survive.data(), (int)i); new_index[i] = run; run += is_record[i]; }   // mark + scan
             s->n_nodes = run; s->nodes.resize((size_t)FTN_NODE_F4 * (size_t)run);
             for (size_t i = 0; i < ni; ++i) if (is_record[i]) lbvh_emit_node(a, leaf_lo.data(), leaf_hi.data(), survive.data(), new_index.data(), (int)i, s->nodes.data());
+            }
         }
     }
     // sphere bounds + light preprocessing exactly as bvh_build() in scene.cu
@@ -267,7 +307,7 @@ SIM_API int sim_bvh_debug_morton(const SimScene* s, uint32_t* codes, uint32_t* o
 }
 SIM_API int sim_scene_world_bound(const SimScene* s, float out[6]) { std::memcpy(out, s->bounds, 24); return FTN_OK; }
 SIM_API int sim_scene_stats(const SimScene* s, FtnStats* st) {
-    std::memset(st, 0, sizeof(*st)); st->bvh_nodes = s->n_nodes; st->bvh_node_bytes = FTN_NODE_BYTES; st->bvh_tri_bytes = 48; return FTN_OK;
+    std::memset(st, 0, sizeof(*st)); st->bvh_nodes = s->n_nodes; st->bvh_node_bytes = s->wide ? FTN_NODE8_BYTES : FTN_NODE_BYTES; st->bvh_tri_bytes = FTN_TRI_BYTES; return FTN_OK;
 }
 
 static RayF to_rayf(const FtnRay& r) { RayF q; q.o = V3(r.o[0], r.o[1], r.o[2]); q.d = V3(r.d[0], r.d[1], r.d[2]); q.t_max = r.t_max; q.time = r.time; return q; }
@@ -282,7 +322,7 @@ SIM_API int sim_intersect(const SimScene* s, size_t n, const FtnRay* rays, FtnHi
         FtnHit out;
         if (h.slot == FTN_NO_HIT_SLOT) { out.prim = FTN_NO_HIT; out.t = ray.t_max; out.b1 = 0; out.b2 = 0; }
         else if (h.slot & FTN_SPHERE_SLOT_FLAG) { out.prim = sc.n_tris + (h.slot & ~FTN_SPHERE_SLOT_FLAG); out.t = h.t; out.b1 = 0; out.b2 = 0; }
-        else { out.prim = f2u(sc.bvh.tris[3 * (size_t)h.slot].w); out.t = h.t; out.b1 = h.tri.b1; out.b2 = h.tri.b2; }
+        else { out.prim = f2u(sc.bvh.tris[(size_t)FTN_TRI_F4 * (size_t)h.slot].w); out.t = h.t; out.b1 = h.tri.b1; out.b2 = h.tri.b2; }
         hits[i] = out;
     }
     return FTN_OK;

@@ -15,8 +15,22 @@ from tests import parity
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(scope="module", params=["bvh8", "bvh2"], autouse=True)
+def bvh_layout(request):
+    """Every test of this module runs on both node layouts of the aggregate: BVH8q (compressed 8-wide, the default) and
+    BVH2x64 -- results must not depend on the layout (FTN_BVH_LAYOUT is read by ftn_bvh_build)."""
+    import os
+    old = os.environ.get("FTN_BVH_LAYOUT")
+    os.environ["FTN_BVH_LAYOUT"] = request.param
+    yield request.param
+    if old is None:
+        os.environ.pop("FTN_BVH_LAYOUT", None)
+    else:
+        os.environ["FTN_BVH_LAYOUT"] = old
+
+
 @pytest.fixture(scope="module")
-def cubes(gpu_backend, orc_backend, rounded_cube_path):
+def cubes(gpu_backend, orc_backend, rounded_cube_path, bvh_layout):
     return parity.cube_scenes(gpu_backend, orc_backend, rounded_cube_path)
 
 
@@ -249,7 +263,9 @@ def test_ploc_depth_fallback_to_radix_tree(gpu_backend, orc_backend, rounded_cub
     monkeypatch.setenv("FTN_BVH_BUILDER", "ploc")
     monkeypatch.setenv("FTN_PLOC_MAX_DEPTH", "3")
     a, b = parity.cube_scenes(gpu_backend, orc_backend, rounded_cube_path)
-    assert a.stats()["bvh_nodes"] == 1355
+    monkeypatch.setenv("FTN_BVH_BUILDER", "lbvh")
+    r, _ = parity.cube_scenes(gpu_backend, orc_backend, rounded_cube_path)
+    assert a.stats()["bvh_nodes"] == r.stats()["bvh_nodes"]
     parity.check_morton(a, b)
     parity.check_ray_batch(a, b, parity.random_ray_batch(100_000, 15), "fallback")
     parity.check_watertight(a, n=100_000)
