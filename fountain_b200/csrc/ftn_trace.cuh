@@ -12,6 +12,9 @@ namespace ftn {
 #ifndef FTN_TRACE_BLOCKS_PER_SM
 #define FTN_TRACE_BLOCKS_PER_SM 8     /* 64 registers/thread: 8 x 128 threads fill the register file */
 #endif
+#ifndef FTN_TRACE8_BLOCKS_PER_SM
+#define FTN_TRACE8_BLOCKS_PER_SM 7    /* BVH8q kernels: 72 registers/thread */
+#endif
 #ifdef FTN_TRACE_MIN_BLOCKS              /* A/B: force a register budget for more resident warps */
 #define FTN_TRACE_LAUNCH_BOUNDS __launch_bounds__(FTN_TRACE_THREADS, FTN_TRACE_MIN_BLOCKS)
 #else

@@ -445,7 +445,7 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
         for (int it = 0; it < iter_cap && n_active > 0; ++it) {
             FTN_CUDA(cudaMemsetAsync(counts, 0, CTR_COUNT * 4, st));
             Queues q = qs; q.q[Q_ACTIVE_OUT] = q_out;
-            const unsigned ge = trace_grid(n_active, FTN_TRACE_BLOCKS_PER_SM);
+            const unsigned ge = trace_grid(n_active, sc.bvh.wide ? FTN_TRACE8_BLOCKS_PER_SM : FTN_TRACE_BLOCKS_PER_SM);
             timer.begin(0);
             FTN_MODE3(tmode, FTN_BOOL2(count_traversal, sph, (k_extend<B0, B1, M><<<ge, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q_in, n_active, q, counts, d_trav, integ->type == FTN_INTEGRATOR_DIRECT_LIGHTING))));
             timer.end();
@@ -485,7 +485,7 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
             //  shadow / MIS kernels are already queued when the host wakes up)
             FTN_CUDA(cudaMemcpyAsync(h_counts, counts, CTR_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             FTN_CUDA(cudaEventRecord(ev_counts, st));
-            const unsigned gq = trace_grid(n_active, FTN_TRACE_BLOCKS_PER_SM);
+            const unsigned gq = trace_grid(n_active, sc.bvh.wide ? FTN_TRACE8_BLOCKS_PER_SM : FTN_TRACE_BLOCKS_PER_SM);
             timer.begin(1);
             FTN_MODE3(tmode, FTN_BOOL2(count_traversal, sph, (k_shadow<B0, B1, M><<<gq, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_SHADOW], counts, d_trav + 2))));
             timer.end();

@@ -21,6 +21,7 @@
 #define FTN_VOTE_BIAS_DEFAULT 14
 #define FTN_VOTE_MIN_TRIS 65536u
 #define FTN_PLOC_MIN_TRIS 65536u
+#define FTN_WIDE_MIN_TRIS 65536u
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -699,9 +700,12 @@ int bvh_build(FtnScene* s) {
         // of build time against 0.15 ms saved per render, hence the size threshold.
         const char* builder_env = getenv("FTN_BVH_BUILDER");
         const bool use_ploc = builder_env ? std::string(builder_env) == "ploc" : n >= FTN_PLOC_MIN_TRIS;
-        // Node layout: BVH8q (compressed 8-wide, ftn_bvh8.cuh) unless FTN_BVH_LAYOUT=bvh2 asks for the BVH2x64 records
+        // Node layout: BVH8q (compressed 8-wide, ftn_bvh8.cuh) for scenes of >= FTN_WIDE_MIN_TRIS triangles, BVH2x64 records
+        // below (FTN_BVH_LAYOUT=bvh8|bvh2 overrides).  Measured on B200 (profiles/r02_ab_bvh8.txt): 1M triangles, incoherent
+        // rays +4 % (diffuse bounce) / +23 % (interior); 147 k-triangle C4 render +2 %; 4332-triangle C2 render -5 %
+        // (three levels of wide nodes: the 230-instruction node test is not amortised).
         const char* layout_env = getenv("FTN_BVH_LAYOUT");
-        const bool wide = layout_env ? std::string(layout_env) != "bvh2" : true;
+        const bool wide = layout_env ? std::string(layout_env) != "bvh2" : n >= FTN_WIDE_MIN_TRIS;
         const size_t max_nodes8 = bvh8_max_nodes(n);
         // all temporaries come from the device's build arena: one (cached) allocation, no cudaFree
         // (each of which would synchronise the device) per build

@@ -79,7 +79,7 @@ int intersect_device(const FtnScene* s, size_t n, const FtnRay* d_rays, FtnHit* 
         // this call's own work counter: the next slot of the scene's ring (calls on different streams may overlap)
         uint32_t* d_work = reinterpret_cast<uint32_t*>(s->d_work + (s->work_slot.fetch_add(1u, std::memory_order_relaxed) % FTN_MAX_QUERIES_IN_FLIGHT));
         FTN_CUDA(cudaMemsetAsync(d_work, 0, sizeof(unsigned long long), st));
-        const unsigned grid = trace_grid(m, FTN_TRACE_BLOCKS_PER_SM);
+        const unsigned grid = trace_grid(m, sc.bvh.wide ? FTN_TRACE8_BLOCKS_PER_SM : FTN_TRACE_BLOCKS_PER_SM);
         const FtnRay* r = d_rays + off;
         FtnHit* h = d_hits ? d_hits + off : nullptr;
         uint8_t* a = d_any ? d_any + off : nullptr;

@@ -171,7 +171,7 @@ SIM_API int sim_bvh_build(SimScene* s) {
         const char* builder_env = getenv("FTN_BVH_BUILDER");
         const bool use_ploc = builder_env ? std::string(builder_env) == "ploc" : n >= 65536u;   // the policy of scene.cu
         const char* layout_env = getenv("FTN_BVH_LAYOUT");
-        const bool wide = layout_env ? std::string(layout_env) != "bvh2" : true;   // the policy of scene.cu
+        const bool wide = layout_env ? std::string(layout_env) != "bvh2" : n >= 65536u;   // the policy of scene.cu
         // k_bvh8_level of scene.cu, level by level, one node at a time
         struct HostAlloc {
             uint32_t next_nodes = 1, next_tris = 0;
@@ -653,6 +653,103 @@ SIM_API int sim_warp_model(const SimScene* s, size_t n, const FtnRay* rays, cons
     out[0] = node_slots; out[1] = node_work; out[2] = tri_slots; out[3] = tri_work; out[4] = leaf_slots; out[5] = leaf_work; out[6] = refills; out[7] = (double)n;
     return FTN_OK;
 }
+// ---- the same design tool for the BVH8q loop (trace_persistent8) ----------------------------------------------------
+//   ip[0] refill threshold   ip[1] vote bias (node step when 16 * #node lanes >= bias * #leaf lanes)   ip[2] warps
+//   ip[3] leaf granularity: 0 = one leaf child (<= 3 triangles) per leaf slot, 1 = one triangle per leaf slot
+//   ip[4] postponing: 0 = a lane holding a triangle group waits for a leaf step; 1 = when the warp runs a node step such a
+//         lane pushes its triangle group on its stack and walks on (groups popped later are tested then)
+//   ip[5] cooperative leaf step: 1 = the pending (lane, triangle) pairs of the warp are spread over all 32 lanes
+// out: [0] node slots [1] node lane-steps [2] triangle slots [3] triangle lane-tests [4] loop iterations [5] refill rounds
+//      [6] rays [7] max stack depth
+SIM_API int sim_warp_model8(const SimScene* s, size_t n, const FtnRay* rays, const int* ip, double* out) {
+    const SceneView sc = s->view();
+    const BvhView bvh = sc.bvh;
+    if (!bvh.wide) return FTN_ERR_INVALID_ARGUMENT;
+    const int refill_thresh = ip[0], bias = ip[1], n_warps = std::max(1, ip[2]), one_tri = ip[3], postpone = ip[4], coop = ip[5];
+    struct Entry { uint32_t base, bits; bool tri; };
+    struct Lane {
+        bool has_ray = false, finished = false;
+        RayF ray; Ray8 r8; RayShear shear; float t_max = 0; uint32_t slot = FTN_NO_HIT_SLOT; TriHit tri;
+        std::vector<Entry> stack;
+        uint32_t ng_base = 0, ng_bits = 0, tg_base = 0, tg_bits = 0;
+        uint32_t cur_first = 0, cur_count = 0;   // one_tri: the leaf child being tested
+    };
+    struct Warp { Lane l[32]; bool done = false; };
+    std::vector<Warp> warps(n_warps);
+    size_t next = 0;
+    double node_slots = 0, node_work = 0, tri_slots = 0, tri_work = 0, iters = 0, refills = 0, max_sp = 0;
+    TraceCounters tc; tc.nodes = tc.tris = 0;
+    int live = n_warps;
+    auto pending_tris = [&](const Lane& L) { return (L.tg_bits & 0xFFu) != 0u || L.cur_count != 0u; };
+    auto normalise = [&](Lane& L) {   // nothing left in either group: take the next group from the stack
+        while (!pending_tris(L) && !(L.ng_bits & 0xFFu) && !L.stack.empty()) {
+            const Entry e = L.stack.back(); L.stack.pop_back();
+            if (e.tri) { L.tg_base = e.base; L.tg_bits = e.bits; } else { L.ng_base = e.base; L.ng_bits = e.bits; }
+        }
+    };
+    while (live > 0) {
+        for (Warp& w : warps) {
+            if (w.done) continue;
+            int idle = 0;
+            for (Lane& L : w.l) { if (L.finished) { L.has_ray = false; L.finished = false; } if (!L.has_ray) ++idle; }
+            if (idle && next < n) {
+                refills += 1;
+                for (Lane& L : w.l) {
+                    if (L.has_ray || next >= n) continue;
+                    L.ray = to_rayf(rays[next++]); L.has_ray = true; L.slot = FTN_NO_HIT_SLOT; L.t_max = L.ray.t_max;
+                    L.r8 = make_ray8(L.ray.o, L.ray.d); L.shear = make_ray_shear(L.ray.d); L.stack.clear();
+                    L.ng_base = 0; L.ng_bits = (1u << L.r8.octinv) | (1u << 8); L.tg_bits = 0; L.cur_count = 0;
+                }
+            }
+            int with_ray = 0; for (Lane& L : w.l) with_ray += L.has_ray;
+            if (!with_ray) { w.done = true; --live; continue; }
+            const int thresh = (next >= n) ? 1 : refill_thresh;
+            for (;;) {
+                int nn = 0, nl = 0;
+                for (Lane& L : w.l) { if (!L.has_ray || L.finished) continue; if (pending_tris(L)) ++nl; else if (L.ng_bits & 0xFFu) ++nn; }
+                if (nn + nl < thresh || nn + nl == 0) break;
+                iters += 1;
+                const bool node_phase = nl == 0 || 16 * nn >= bias * nl;
+                if (node_phase) {
+                    node_slots += 1;
+                    for (Lane& L : w.l) {
+                        if (!L.has_ray || L.finished) continue;
+                        if (pending_tris(L)) {
+                            if (!postpone || L.cur_count != 0u || !(L.ng_bits & 0xFFu)) continue;
+                            Entry e; e.base = L.tg_base; e.bits = L.tg_bits; e.tri = true; L.stack.push_back(e); L.tg_bits = 0;
+                        }
+                        if (!(L.ng_bits & 0xFFu)) continue;
+                        node_work += 1;
+                        const uint32_t node = node8_pop_child(L.ng_base, L.ng_bits, L.r8.octinv);
+                        if (L.ng_bits & 0xFFu) { Entry e; e.base = L.ng_base; e.bits = L.ng_bits; e.tri = false; L.stack.push_back(e); }
+                        max_sp = std::max(max_sp, (double)L.stack.size());
+                        const Node8Hits h = node8_test(bvh.nodes, node, L.r8, L.t_max);
+                        L.ng_base = h.child_base; L.ng_bits = h.ng_bits; L.tg_base = h.tri_base; L.tg_bits = h.tg_bits;
+                    }
+                } else {
+                    uint32_t max_tests = 0, all_tests = 0;
+                    for (Lane& L : w.l) {
+                        if (!L.has_ray || L.finished || !pending_tris(L)) continue;
+                        if (L.cur_count == 0u) node8_pop_leaf(L.tg_base, L.tg_bits, L.r8.octinv, &L.cur_first, &L.cur_count);
+                        const uint32_t k = one_tri ? 1u : L.cur_count;
+                        tris8_test<false, false>(bvh, L.cur_first, k, L.ray.o, L.shear, &L.t_max, &L.slot, &L.tri, &tc);
+                        L.cur_first += k; L.cur_count -= k;
+                        tri_work += k; max_tests = std::max(max_tests, k); all_tests += k;
+                    }
+                    tri_slots += coop ? (all_tests + 31u) / 32u : max_tests;
+                }
+                for (Lane& L : w.l) {
+                    if (!L.has_ray || L.finished) continue;
+                    normalise(L);
+                    if (!pending_tris(L) && !(L.ng_bits & 0xFFu)) L.finished = true;
+                }
+            }
+        }
+    }
+    out[0] = node_slots; out[1] = node_work; out[2] = tri_slots; out[3] = tri_work; out[4] = iters; out[5] = refills; out[6] = (double)n; out[7] = max_sp;
+    return FTN_OK;
+}
+
 // slab test as the kernels run it: mode 0 = per-ray dispatch (nan_free fast form when allowed), 1 = exact form.
 // returns bit0 = accepted, bit1 = ray is nan_free; out[0] = entry distance
 SIM_API int sim_kat_slab_test(const float bmin[3], const float bmax[3], const FtnRay* ray, float out[1], int mode) {
