@@ -436,8 +436,6 @@ class Scene:
         first = 0
         for p in meshes:
             m = p.shape
-            if p.light is not None:
-                raise NotImplementedError("emissive triangle meshes are not in this path's scope (SURVEY 8a a18)")
             pos.append(m.vertices)
             if any_normals:
                 nrm.append(m.normals)
@@ -445,7 +443,9 @@ class Scene:
                 uvs.append(m.tex_coords)
             idx.append(m.vertex_indices + np.uint32(vbase))
             vbase += m.vertices.shape[0]
-            mdescs.append((first, m.n_triangles, mat_id(p.material), A.FTN_MESH_FLIP_NORMALS if m.flip_normals() else 0))
+            # `AreaLightSource "diffuse"` in front of the shape: every triangle carries its own DiffuseAreaLight (loaders/pbrt.rs:275-316)
+            mdescs.append((first, m.n_triangles, mat_id(p.material), A.FTN_MESH_FLIP_NORMALS if m.flip_normals() else 0,
+                           None if p.light is None else p.light.emit))
             first += m.n_triangles
         self.n_triangles = first
         self.n_spheres = len(spheres)
@@ -455,8 +455,11 @@ class Scene:
         self._indices = np.ascontiguousarray(np.concatenate(idx), dtype=np.uint32) if idx else np.zeros((0, 3), np.uint32)
 
         c_meshes = (A.FtnMeshDesc * max(1, len(mdescs)))()
-        for i, (f, n, mid, fl) in enumerate(mdescs):
+        for i, (f, n, mid, fl, emit) in enumerate(mdescs):
             c_meshes[i].first_tri, c_meshes[i].n_tris, c_meshes[i].material_id, c_meshes[i].flags = f, n, mid, fl
+            c_meshes[i].emissive = int(emit is not None)
+            if emit is not None:
+                c_meshes[i].emit[:] = emit.tolist()
         c_spheres = (A.FtnSphere * max(1, len(spheres)))()
         for i, p in enumerate(spheres):
             s, cs = p.shape, c_spheres[i]

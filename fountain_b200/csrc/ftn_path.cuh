@@ -153,6 +153,13 @@ FTN_HD void sample_direct(const SceneView& sc, const Surface& s, const Bsdf& bsd
         pdf = 1.0f;
         Li = V3(light.emit[0], light.emit[1], light.emit[2]);
         p1 = x_add(s.p, x_scale(wi, rn_mul(2.0f, light.env.world_radius)));
+    } else if (light.type == FTN_LIGHT_TYPE_TRIANGLE) {   // diffuse.rs:74-89 over a triangle of an emissive mesh
+        const TriLightGeom g = tri_light_geom(sc, light);
+        const ShapeSample ps = triangle_sample(sc, g, ul0, ul1);
+        wi = x_normalize(x_sub(ps.p, s.p));
+        pdf = triangle_pdf_from_ref(sc, g, s, wi);
+        Li = area_emitted(light, ps.n, x_neg(wi));
+        p1 = ps.p; p1_err = ps.p_err; p1_n = ps.n;
     } else {   // diffuse.rs:74-89
         const SphereData& sd = sc.spheres[light.sphere];
         const ShapeSample ps = sphere_sample(sd, ul0, ul1);
@@ -168,19 +175,20 @@ FTN_HD void sample_direct(const SceneView& sc, const Surface& s, const Bsdf& bsd
             // VisibilityTester -> SurfaceHit::spawn_ray_to_hit, interaction.rs:48-58
             const V3 origin = offset_ray_origin(s.p, s.p_err, s.n, x_sub(p1, s.p));
             const V3 target = offset_ray_origin(p1, p1_err, p1_n, x_sub(origin, p1));
-            const float w = (light.type >= 2) ? 1.0f : power_heuristic1(pdf, spdf);   // delta lights: f * Li / pdf (:331-332)
+            const float w = (light.type == 2 || light.type == 3) ? 1.0f : power_heuristic1(pdf, spdf);   // delta lights: f * Li / pdf (:331-332)
             out->has_shadow = true; out->sh_o = origin; out->sh_d = x_sub(target, origin);
             out->sh_L = scale * (nl * (f * Li * w / pdf));
         }
     }
     // --- BSDF sample ---
-    if (light.type >= 2) return;   // a delta light cannot be reached by sampling the BSDF (integrator/mod.rs:343)
+    if (light.type == 2 || light.type == 3) return;   // a delta light cannot be reached by sampling the BSDF (integrator/mod.rs:343)
     ScatterSample bs;
     if (bsdf_sample_f<MAT>(bsdf, s.wo, us0, us1, flags, &bs)) {
         const V3 f = bs.f * abs_dot(bs.wi, s.ns);
         if (is_black(f)) return;
         float lpdf;
         if (light.type == 0) lpdf = env_pdf(light.env, bs.wi);
+        else if (light.type == FTN_LIGHT_TYPE_TRIANGLE) lpdf = triangle_pdf_from_ref(sc, tri_light_geom(sc, light), s, bs.wi);
         else lpdf = sphere_pdf_from_ref(sc.spheres[light.sphere], s, bs.wi);
         if (lpdf == 0.0f) return;
         const float w = power_heuristic1(bs.pdf, lpdf);
@@ -291,6 +299,12 @@ FTN_HD V3 mis_incident(const SceneView& sc, const LightData& light, const RayF& 
         if (light.type == 1 && (uint32_t)light.sphere == si) {   // the SAME light only (:370-381)
             SphereHit sh;
             if (sphere_intersect(sc.spheres[si], ray, &sh)) return area_emitted(light, sh.n, x_neg(ray.d));
+        }
+    } else if (light.type == FTN_LIGHT_TYPE_TRIANGLE) {
+        const uint32_t prim = f2u(ld4(sc.bvh.tris + (size_t)FTN_TRI_F4 * (size_t)slot).w);
+        if (prim == (uint32_t)light.sphere) {                      // the triangle that carries this very light
+            Surface hs;
+            if (surface_at_hit(sc, slot, ray, &hs)) return area_emitted(light, hs.n, x_neg(ray.d));
         }
     }
     return v3s(0.0f);

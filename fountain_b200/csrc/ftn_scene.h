@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <atomic>
+#include <cstring>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -58,6 +59,9 @@ struct MeshData {
     uint32_t first_tri, n_tris;
     int32_t material;
     uint32_t flags;          // FTN_MESH_*
+    int32_t light_base;      // emissive mesh: index of the area light of its first triangle (one DiffuseAreaLight per triangle,
+                             // consecutive, loaders/pbrt.rs:275-316); -1 = not emissive
+    int32_t pad[3];
 };
 
 #define FTN_CLASS_OREN_NAYAR 4   /* matte.rs:45-49: its own class keeps the Lambert shade kernel free of the rough-diffuse code */
@@ -109,12 +113,37 @@ struct EnvLightData {
 };
 
 struct LightData {
-    int32_t type;            // 0 infinite, 1 diffuse area on a sphere, 2 point, 3 distant
-    int32_t sphere;          // area: sphere index
+    int32_t type;            // 0 infinite, 1 diffuse area on a sphere, 2 point, 3 distant, 4 diffuse area on a triangle
+    int32_t sphere;          // sphere area light: sphere index; triangle area light: primitive id (scene-wide triangle index)
     float emit[3];           // area: L; point: I; distant: L
     float vec[3];            // point: world position; distant: normalised direction towards the light
+    int32_t mesh;            // triangle area light: mesh of the triangle
     EnvLightData env;
 };
+
+#define FTN_LIGHT_TYPE_TRIANGLE 4
+// Fills MeshData (incl. light_base) and appends the per-triangle area lights of emissive meshes to `lights`, which must
+// hold exactly the explicit lights (scene/mod.rs:32-49: explicit lights, then the primitives' area lights -- here in
+// primitive order: triangles, then spheres).  Host side, shared by scene.cu and the host harness of the tests.
+template <class MeshVec, class LightVec>
+inline void build_mesh_table(const FtnSceneDesc* d, MeshVec* meshes, LightVec* lights) {
+    meshes->resize(d->n_meshes);
+    for (uint32_t m = 0; m < d->n_meshes; ++m) {
+        const FtnMeshDesc& fm = d->meshes[m];
+        MeshData md; std::memset(&md, 0, sizeof(md));
+        md.first_tri = fm.first_tri; md.n_tris = fm.n_tris; md.material = fm.material_id; md.flags = fm.flags; md.light_base = -1;
+        if (fm.emissive && fm.n_tris) {
+            md.light_base = (int32_t)lights->size();
+            for (uint32_t t = 0; t < fm.n_tris; ++t) {
+                LightData ld; std::memset(&ld, 0, sizeof(ld));
+                ld.type = FTN_LIGHT_TYPE_TRIANGLE; ld.sphere = (int32_t)(fm.first_tri + t); ld.mesh = (int32_t)m;
+                ld.emit[0] = fm.emit[0]; ld.emit[1] = fm.emit[1]; ld.emit[2] = fm.emit[2];
+                lights->push_back(ld);
+            }
+        }
+        (*meshes)[m] = md;
+    }
+}
 
 struct SceneView {
     BvhView bvh;

@@ -501,11 +501,7 @@ struct Surface {
 
 // Triangle::intersect tail, triangle.rs:270-392, from the slot's vertices and the barycentrics
 // the traversal found (exact ops: p, p_err and n feed spawned ray origins).
-FTN_HD void triangle_surface(const SceneView& sc, uint32_t slot, const TriHit& h, V3 ray_d, Surface* s) {
-    F4 a, b, c; load_tri(sc.bvh, slot, &a, &b, &c);
-    const V3 p0 = V3(a.x, a.y, a.z), p1 = V3(b.x, b.y, b.z), p2 = V3(c.x, c.y, c.z);
-    const uint32_t prim = f2u(a.w), mesh_id = f2u(b.w);
-    const MeshData mesh = sc.meshes[mesh_id];
+FTN_HD void triangle_surface_at(const SceneView& sc, V3 p0, V3 p1, V3 p2, uint32_t prim, const MeshData& mesh, const TriHit& h, V3 ray_d, Surface* s) {
     const uint32_t v0 = sc.idx[3 * (size_t)prim], v1 = sc.idx[3 * (size_t)prim + 1], v2 = sc.idx[3 * (size_t)prim + 2];
     float uv[3][2] = {{0.0f, 0.0f}, {1.0f, 0.0f}, {1.0f, 1.0f}};   // triangle.rs:131-143
     if (sc.uv) {
@@ -553,7 +549,11 @@ FTN_HD void triangle_surface(const SceneView& sc, uint32_t slot, const TriHit& h
     s->n = n; s->ns = ns; s->sdpdu = sdpdu;
     s->wo = x_neg(ray_d);
     s->material = mesh.material;
-    s->light = -1;
+    s->light = mesh.light_base >= 0 ? mesh.light_base + (int)(prim - mesh.first_tri) : -1;   // its own DiffuseAreaLight (primitive.rs:60-66)
+}
+FTN_HD void triangle_surface(const SceneView& sc, uint32_t slot, const TriHit& h, V3 ray_d, Surface* s) {
+    F4 a, b, c; load_tri(sc.bvh, slot, &a, &b, &c);
+    triangle_surface_at(sc, V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), V3(c.x, c.y, c.z), f2u(a.w), sc.meshes[f2u(b.w)], h, ray_d, s);
 }
 
 FTN_HD void sphere_surface(const SphereData& sd, const SphereHit& h, Surface* s) {
@@ -587,6 +587,49 @@ FTN_HD float sphere_pdf_from_ref(const SphereData& sd, const Surface& ref, V3 wi
     if (!sphere_intersect(sd, ray, &h)) return 0.0f;
     const V3 d = x_sub(ref.p, h.p);
     return rn_div(x_len2(d), rn_mul(x_abs_dot(h.n, x_neg(wi)), sd.area));
+}
+
+// ---- triangle area light (light/diffuse.rs over shapes/triangle.rs:171-174, 395-420 and the Shape defaults shapes/mod.rs:41-66) ----
+struct TriLightGeom { V3 p0, p1, p2; uint32_t prim, v0, v1, v2; MeshData mesh; };
+FTN_HD TriLightGeom tri_light_geom(const SceneView& sc, const LightData& light) {
+    const uint32_t prim = (uint32_t)light.sphere;
+    TriLightGeom g; g.prim = prim;
+    g.v0 = sc.idx[3 * (size_t)prim]; g.v1 = sc.idx[3 * (size_t)prim + 1]; g.v2 = sc.idx[3 * (size_t)prim + 2];
+    g.p0 = V3(sc.pos[3 * (size_t)g.v0], sc.pos[3 * (size_t)g.v0 + 1], sc.pos[3 * (size_t)g.v0 + 2]);
+    g.p1 = V3(sc.pos[3 * (size_t)g.v1], sc.pos[3 * (size_t)g.v1 + 1], sc.pos[3 * (size_t)g.v1 + 2]);
+    g.p2 = V3(sc.pos[3 * (size_t)g.v2], sc.pos[3 * (size_t)g.v2 + 1], sc.pos[3 * (size_t)g.v2 + 2]);
+    g.mesh = sc.meshes[light.mesh];
+    return g;
+}
+// Triangle::sample, triangle.rs:395-420 (uniform_sample_triangle, sampling.rs:48-51)
+FTN_HD ShapeSample triangle_sample(const SceneView& sc, const TriLightGeom& g, float u0, float u1) {
+    const float su0 = rn_sqrt(u0);
+    const float b0 = rn_sub(1.0f, su0), b1 = rn_mul(u1, su0), b2 = rn_sub(rn_sub(1.0f, b0), b1);
+    const V3 q0 = x_scale(g.p0, b0), q1 = x_scale(g.p1, b1), q2 = x_scale(g.p2, b2);
+    V3 n = x_normalize(x_cross(x_sub(g.p1, g.p0), x_sub(g.p2, g.p0)));
+    if (sc.nrm) {
+        const V3 n0 = V3(sc.nrm[3 * (size_t)g.v0], sc.nrm[3 * (size_t)g.v0 + 1], sc.nrm[3 * (size_t)g.v0 + 2]);
+        const V3 n1 = V3(sc.nrm[3 * (size_t)g.v1], sc.nrm[3 * (size_t)g.v1 + 1], sc.nrm[3 * (size_t)g.v1 + 2]);
+        const V3 n2 = V3(sc.nrm[3 * (size_t)g.v2], sc.nrm[3 * (size_t)g.v2 + 1], sc.nrm[3 * (size_t)g.v2 + 2]);
+        const V3 ns = x_normalize(x_add(x_add(x_scale(n0, b0), x_scale(n1, b1)), x_scale(n2, b2)));
+        n = faceforward(n, ns);
+    } else if (g.mesh.flags & FTN_MESH_FLIP_NORMALS) n = x_scale(n, -1.0f);
+    ShapeSample s;
+    s.p = x_add(x_add(q0, q1), q2);                                              // Point3(0,0,0) + sample_p
+    s.p_err = x_scale(x_add(x_add(x_abs(q0), x_abs(q1)), x_abs(q2)), gamma_n(6));
+    s.n = n;
+    return s;
+}
+// Shape::pdf_from_ref (shapes/mod.rs:55-66) over Triangle::intersect and Triangle::area
+FTN_HD float triangle_pdf_from_ref(const SceneView& sc, const TriLightGeom& g, const Surface& ref, V3 wi) {
+    const V3 o = spawn_origin(ref, wi);
+    TriHit th;
+    if (!triangle_intersect(g.p0, g.p1, g.p2, o, make_ray_shear(wi), FTN_INF, &th)) return 0.0f;
+    Surface hs;
+    triangle_surface_at(sc, g.p0, g.p1, g.p2, g.prim, g.mesh, th, wi, &hs);
+    const float area = rn_mul(0.5f, x_len(x_cross(x_sub(g.p1, g.p0), x_sub(g.p2, g.p0))));
+    const V3 d = x_sub(ref.p, hs.p);
+    return rn_div(x_len2(d), rn_mul(x_abs_dot(hs.n, x_neg(wi)), area));
 }
 
 // ---- thin-lens perspective camera, camera/mod.rs:117-143 (exact ops: primary rays match the oracle) -----

@@ -413,7 +413,7 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
     const SceneView sc = s->view();
     const bool sph = s->n_spheres > 0;
     bool has_area = false;
-    for (const LightData& l : s->h_lights) if (l.type == 1) has_area = true;
+    for (const LightData& l : s->h_lights) if (l.type == 1 || l.type == FTN_LIGHT_TYPE_TRIANGLE) has_area = true;
     uint64_t camera_samples = 0;
     uint64_t class_rays[3] = {0, 0, 0};
     const unsigned shade_grid = (unsigned)(sm_count() * 8);

@@ -547,12 +547,6 @@ int scene_create(const FtnSceneDesc* d, FtnScene** out) {
     if (d->normals && (rc = upload(&s->d_nrm, d->normals, 3 * (size_t)d->n_vertices)) != FTN_OK) return bail(rc);
     if (d->uvs && (rc = upload(&s->d_uv, d->uvs, 2 * (size_t)d->n_vertices)) != FTN_OK) return bail(rc);
     if ((rc = upload(&s->d_idx, d->indices, 3 * (size_t)d->n_triangles)) != FTN_OK) return bail(rc);
-    std::vector<MeshData> meshes(d->n_meshes);
-    for (uint32_t m = 0; m < d->n_meshes; ++m) {
-        meshes[m].first_tri = d->meshes[m].first_tri; meshes[m].n_tris = d->meshes[m].n_tris;
-        meshes[m].material = d->meshes[m].material_id; meshes[m].flags = d->meshes[m].flags;
-    }
-    if ((rc = upload(&s->d_meshes, meshes.data(), meshes.size())) != FTN_OK) return bail(rc);
     std::vector<MaterialData> mats(d->n_materials);
     for (uint32_t m = 0; m < d->n_materials; ++m) {
         const FtnMaterial& fm = d->materials[m];
@@ -593,7 +587,8 @@ int scene_create(const FtnSceneDesc* d, FtnScene** out) {
     for (uint32_t m = 0; m < d->n_meshes; ++m) if (d->meshes[m].material_id < 0 && d->meshes[m].n_tris) s->has_null_material = true;
     for (uint32_t i = 0; i < d->n_spheres; ++i) if (d->spheres[i].material_id < 0) s->has_null_material = true;
     if ((rc = upload(&s->d_materials, mats.data(), mats.size())) != FTN_OK) return bail(rc);
-    // explicit lights first, then area lights of emissive spheres in primitive order (scene/mod.rs:32-49)
+    // explicit lights first, then the primitives' area lights in primitive order (scene/mod.rs:32-49; the reference lists them
+    // in ITS BVH's order -- the same set, and uniform_sample_one_light picks uniformly, so the estimator is the same)
     for (uint32_t l = 0; l < d->n_lights; ++l) {
         const FtnLight& fl = d->lights[l];
         if (fl.type == FTN_LIGHT_POINT || fl.type == FTN_LIGHT_DISTANT) {   // light/point.rs, light/distant.rs
@@ -609,6 +604,11 @@ int scene_create(const FtnSceneDesc* d, FtnScene** out) {
         if ((rc = build_env_light(s, fl, &ld)) != FTN_OK) return bail(rc);
         s->h_lights.push_back(ld);
     }
+    // ... the area lights of emissive meshes (one per triangle) ...
+    std::vector<MeshData> meshes;
+    build_mesh_table(d, &meshes, &s->h_lights);
+    if ((rc = upload(&s->d_meshes, meshes.data(), meshes.size())) != FTN_OK) return bail(rc);
+    // ... then those of emissive spheres
     s->h_spheres.resize(d->n_spheres);
     for (uint32_t i = 0; i < d->n_spheres; ++i) {
         const FtnSphere& fs = d->spheres[i];

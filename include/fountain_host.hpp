@@ -627,8 +627,11 @@ struct GeometricPrimitive {
     std::shared_ptr<Sphere> sphere;
     std::shared_ptr<Material> material;
     std::shared_ptr<DiffuseAreaLight> light;
-    GeometricPrimitive(std::shared_ptr<TriangleMesh> m, std::shared_ptr<Material> mat = nullptr)
-        : mesh(std::move(m)), material(std::move(mat)) {}
+    // a light on a mesh = `AreaLightSource "diffuse"` in front of the shape: every triangle carries its own
+    // DiffuseAreaLight<Triangle> (loaders/pbrt.rs:275-316)
+    GeometricPrimitive(std::shared_ptr<TriangleMesh> m, std::shared_ptr<Material> mat = nullptr,
+                       std::shared_ptr<DiffuseAreaLight> l = nullptr)
+        : mesh(std::move(m)), material(std::move(mat)), light(std::move(l)) {}
     GeometricPrimitive(std::shared_ptr<Sphere> s, std::shared_ptr<Material> mat = nullptr,
                        std::shared_ptr<DiffuseAreaLight> l = nullptr)
         : sphere(std::move(s)), material(std::move(mat)), light(std::move(l)) {}
@@ -670,6 +673,8 @@ public:
             FtnMeshDesc d{};
             d.first_tri = first; d.n_tris = (uint32_t)m.n_triangles(); d.material_id = mat_id(p.material);
             d.flags = m.flip_normals() ? (uint32_t)FTN_MESH_FLIP_NORMALS : 0u;
+            d.emissive = p.light != nullptr;
+            if (p.light) { d.emit[0] = p.light->emit.r; d.emit[1] = p.light->emit.g; d.emit[2] = p.light->emit.b; }
             meshes.push_back(d);
             first += d.n_tris;
         }

@@ -106,14 +106,17 @@ ORC_API int orc_scene_create(const FtnSceneDesc* d, OrcScene** out) {
     }
     if (covered != d->n_triangles) { delete os; return fail(FTN_ERR_INVALID_ARGUMENT, "meshes do not cover all triangles"); }
     s.spheres.resize(d->n_spheres);
+    s.pending_emit.assign(d->n_triangles + d->n_spheres, Spectrum(0.0f));
     for (uint32_t mi = 0; mi < d->n_meshes; ++mi) {
-        for (uint32_t t = 0; t < d->meshes[mi].n_tris; ++t) {
+        const FtnMeshDesc& md = d->meshes[mi];
+        for (uint32_t t = 0; t < md.n_tris; ++t) {
             Primitive p{}; p.kind = 0; p.tri.mesh = &s.meshes[mi]; p.tri.tri_id = t; p.sphere = nullptr;
-            p.material = d->meshes[mi].material_id; p.light = -1;
+            // `AreaLightSource` in front of the shape: one DiffuseAreaLight per triangle (loaders/pbrt.rs:275-316)
+            p.material = md.material_id; p.light = md.emissive ? -2 : -1;
+            if (md.emissive) s.pending_emit[s.prims.size()] = Spectrum(md.emit[0], md.emit[1], md.emit[2]);
             s.prims.push_back(p);
         }
     }
-    s.pending_emit.assign(d->n_triangles + d->n_spheres, Spectrum(0.0f));
     for (uint32_t i = 0; i < d->n_spheres; ++i) {
         const FtnSphere& fs = d->spheres[i];
         Sphere& sp = s.spheres[i];
@@ -164,6 +167,17 @@ ORC_API int orc_bvh_build(OrcScene* os) {
     os->scene.finish();
     os->build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     os->built = true;
+    return FTN_OK;
+}
+
+// Test hook: the primitive (insertion index) behind every light of Scene::lights, -1 for lights that are not area
+// lights.  The reference lists area lights in ITS BVH's primitive order (scene/mod.rs:40-44); the parity tests use this
+// to lay the emissive triangles out so that the GPU's primitive-order light list enumerates them the same way.
+ORC_API int orc_debug_light_prims(const OrcScene* os, int32_t* out, uint32_t cap, uint32_t* n_lights) {
+    if (!os || !os->built) return fail(FTN_ERR_INVALID_ARGUMENT, "scene not built");
+    const std::vector<Light>& ls = os->scene.lights;
+    if (n_lights) *n_lights = (uint32_t)ls.size();
+    for (uint32_t i = 0; i < cap && i < ls.size(); ++i) out[i] = ls[i].type == 1 ? (int32_t)ls[i].prim : -1;
     return FTN_OK;
 }
 

@@ -44,6 +44,7 @@ def library():
             "orc_intersect_count": (C.c_int, [C.c_void_p, C.c_size_t, P(A.FtnRay), P(A.FtnHit), P(u64)]),
             "orc_intersect_brute": (C.c_int, [C.c_void_p, C.c_size_t, P(A.FtnRay), P(A.FtnHit)]),
             "orc_film_to_rgb": (C.c_int, [C.c_size_t, P(A.FtnPixel), P(f32)]),
+            "orc_debug_light_prims": (C.c_int, [C.c_void_p, P(i32), u32, P(u32)]),
             "orc_kat_morton3": (u32, [f32, f32, f32]),
             "orc_kat_expand_bits": (u32, [u32]),
             "orc_kat_to_fixed_point": (u32, [f32]),
@@ -87,3 +88,11 @@ def set_threads(n):
 
 def hardware_threads():
     return int(library().orc_hardware_threads())
+
+
+def light_prims(scene):
+    """Primitive id behind every light of the oracle scene's light list (-1: not an area light)."""
+    n = C.c_uint32(0)
+    out = (A.i32 * 65536)()
+    assert library().orc_debug_light_prims(scene.handle, out, 65536, C.byref(n)) == 0
+    return list(out[: n.value])

@@ -3,9 +3,9 @@ TAG=${1:-r2e}
 LAYOUTS=${2:-"bvh8"}
 mkdir -p gpurun_out
 for L in $LAYOUTS; do
-  FTN_BVH_LAYOUT=$L timeout 600 python bench.py --workload c3 --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ab_c3_${L}_$TAG.json 2> gpurun_out/ab_c3_${L}_$TAG.err
-  FTN_BVH_LAYOUT=$L timeout 600 python bench.py --workload c2 --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ab_c2_${L}_$TAG.json 2> gpurun_out/ab_c2_${L}_$TAG.err
-  FTN_BVH_LAYOUT=$L timeout 600 python bench.py --workload c4 --spp 64 --steps 3 --warmup 3 --no-cpu-baseline --no-extras --no-e2e > gpurun_out/ab_c4_${L}_$TAG.json 2> gpurun_out/ab_c4_${L}_$TAG.err
+  LAYOUT_ENV=$([ "$L" = default ] && echo "" || echo "FTN_BVH_LAYOUT=$L"); env $LAYOUT_ENV timeout 600 python bench.py --workload c3 --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ab_c3_${L}_$TAG.json 2> gpurun_out/ab_c3_${L}_$TAG.err
+  LAYOUT_ENV=$([ "$L" = default ] && echo "" || echo "FTN_BVH_LAYOUT=$L"); env $LAYOUT_ENV timeout 600 python bench.py --workload c2 --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ab_c2_${L}_$TAG.json 2> gpurun_out/ab_c2_${L}_$TAG.err
+  LAYOUT_ENV=$([ "$L" = default ] && echo "" || echo "FTN_BVH_LAYOUT=$L"); env $LAYOUT_ENV timeout 600 python bench.py --workload c4 --spp 64 --steps 3 --warmup 3 --no-cpu-baseline --no-extras --no-e2e > gpurun_out/ab_c4_${L}_$TAG.json 2> gpurun_out/ab_c4_${L}_$TAG.err
 done
 python - <<PY
 import json

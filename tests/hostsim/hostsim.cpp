@@ -64,7 +64,6 @@ SIM_API int sim_scene_create(const FtnSceneDesc* d, SimScene** out) {
     if (d->normals) s->nrm.assign(d->normals, d->normals + 3 * (size_t)d->n_vertices);
     if (d->uvs) s->uv.assign(d->uvs, d->uvs + 2 * (size_t)d->n_vertices);
     s->idx.assign(d->indices, d->indices + 3 * (size_t)d->n_triangles);
-    for (uint32_t m = 0; m < d->n_meshes; ++m) { MeshData md; md.first_tri = d->meshes[m].first_tri; md.n_tris = d->meshes[m].n_tris; md.material = d->meshes[m].material_id; md.flags = d->meshes[m].flags; s->meshes.push_back(md); }
     for (uint32_t m = 0; m < d->n_materials; ++m) {
         const FtnMaterial& fm = d->materials[m]; MaterialData md; md.type = fm.type;
         for (int c = 0; c < 3; ++c) { md.kd[c] = fm.kd[c]; md.ks[c] = fm.ks[c]; md.eta[c] = fm.eta[c]; md.k[c] = fm.k[c]; }
@@ -121,6 +120,7 @@ SIM_API int sim_scene_create(const FtnSceneDesc* d, SimScene** out) {
         e.cond_func = func.data(); e.cond_cdf = cdf.data(); e.cond_integral = integ.data(); e.marg_cdf = mcdf.data();
         s->lights.push_back(ld);
     }
+    build_mesh_table(d, &s->meshes, &s->lights);   // as scene.cu: the per-triangle area lights of emissive meshes
     for (uint32_t i = 0; i < d->n_spheres; ++i) {
         const FtnSphere& fs = d->spheres[i]; SphereData sd;
         sd.o2w = to_m4(fs.object_to_world); sd.w2o = to_m4(fs.world_to_object);
@@ -371,7 +371,7 @@ SIM_API int sim_render(const SimScene* s, const FtnCamera* cam, const FtnFilm* f
     const SceneView sc = s->view();
     uint32_t err = 0;
     uint64_t rays_closest = 0, rays_any = 0, camera_samples = 0;
-    bool has_area = false; for (const LightData& l : s->lights) if (l.type == 1) has_area = true;
+    bool has_area = false; for (const LightData& l : s->lights) if (l.type == 1 || l.type == FTN_LIGHT_TYPE_TRIANGLE) has_area = true;
     PassParams pp; std::memset(&pp, 0, sizeof(pp));
     pp.film = fg; pp.cam = *cam; pp.seed_key = sampler_seed_key(smp->seed);
     pp.spp = smp->samples_per_pixel; pp.s_stride = smp->sample_stride;

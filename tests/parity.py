@@ -102,3 +102,18 @@ def image_diff(test_rgb, ref_rgb):
 def rel_mse(a, b):
     a = a.astype(np.float64); b = b.astype(np.float64)
     return float(np.mean((a - b) ** 2 / (b ** 2 + 1e-2)))
+
+
+def quad_light_order(orc_backend, **kw):
+    """The triangle permutation of scenes.quad_light_scene's emissive quads for which the reference's light list
+    (area lights in ITS BVH's primitive order, scene/mod.rs:40-44 -- read back from the oracle) equals the ABI's
+    (primitive order): with it the oracle and the CUDA path pick the same light for the same random number."""
+    from oracle import orc
+    from workloads import scenes
+    for order in ((0, 1), (1, 0)):
+        sc, _, _ = scenes.quad_light_scene(backend=orc_backend, light_order=order, **kw)
+        prims = orc.light_prims(sc)
+        sc.close()
+        if prims == sorted(prims):
+            return order
+    return None    # (with several emissive meshes the reference's BVH leaves list them in an order no layout reproduces)

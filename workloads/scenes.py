@@ -359,3 +359,52 @@ def textured_mirror_probe(backend=None, xz=(0.5, 0.5), texture=None, resolution=
     camera = api.PerspectiveCamera(Transform.look_at((xz[0], -28.0, xz[1]), (xz[0], 2.0, xz[1]), (0, 0, 1)).inverse(), resolution, fov=0.5)
     film = api.Film(resolution, backend=backend)
     return scene, camera, film
+
+
+# ---- emissive triangle mesh: a quad light over a small Cornell-style set (light/diffuse.rs on triangles) ----
+def quad_light_scene(backend=None, resolution=(48, 48), light_order=(0, 1), emit=(17.0, 12.0, 4.0), two_lights=False, box=True):
+    """Floor, back wall and a small box of matte quads lit ONLY by a quad light (two emissive triangles, no material
+    hit from below: matte black) facing down at z = 3; `light_order` permutes the two triangles of the light inside
+    its mesh (the reference lists area lights in its BVH's order, the ABI in primitive order: the parity tests pick
+    the permutation that makes both enumerations agree).  `two_lights` adds a second, smaller emissive quad."""
+    def quad(p0, p1, p2, p3, order=(0, 1)):
+        v = np.array([p0, p1, p2, p3], np.float32)
+        tris = [[0, 1, 2], [0, 2, 3]]
+        return api.TriangleMesh(Transform.identity(), np.array([tris[order[0]], tris[order[1]]], np.uint32).reshape(-1), v)
+    white, red = api.MatteMaterial((0.7, 0.7, 0.7)), api.MatteMaterial((0.6, 0.1, 0.1))
+    prims = [api.GeometricPrimitive(quad((-3, -3, 0), (3, -3, 0), (3, 3, 0), (-3, 3, 0)), white),          # floor, normal +z
+             api.GeometricPrimitive(quad((-3, 3, 0), (3, 3, 0), (3, 3, 3.5), (-3, 3, 3.5)), red)]            # back wall
+    if box:
+        prims += [api.GeometricPrimitive(quad((-1, -1, 1), (0.5, -1, 1), (0.5, 0.5, 1), (-1, 0.5, 1)), white),   # box top
+                  api.GeometricPrimitive(quad((-1, -1, 0), (0.5, -1, 0), (0.5, -1, 1), (-1, -1, 1)), white)]     # box front
+    # the light: wound so that its geometric normal (p1 - p0) x (p2 - p0) points DOWN
+    prims.append(api.GeometricPrimitive(quad((-1, -1, 3), (-1, 1, 3), (1, 1, 3), (1, -1, 3), light_order),
+                                        api.MatteMaterial((0.0, 0.0, 0.0)), api.DiffuseAreaLight(emit)))
+    if two_lights:
+        prims.append(api.GeometricPrimitive(quad((2.0, -2, 1.0), (2.0, -1, 1.0), (2.0, -1, 2.0), (2.0, -2, 2.0), light_order),
+                                            api.MatteMaterial((0.0, 0.0, 0.0)), api.DiffuseAreaLight((2.0, 6.0, 9.0))))
+    scene = api.Scene(prims, [], backend=backend)
+    cam_to_world = Transform.look_at((0, -8, 2.2), (0, 0, 1.2), (0, 0, 1)).inverse()
+    camera = api.PerspectiveCamera(cam_to_world, resolution, fov=45.0)
+    film = api.Film(resolution, backend=backend)
+    return scene, camera, film
+
+
+def quad_light_probe(backend=None, side=1.0, height=2.0, emit=5.0, kd=0.5, resolution=(3, 3)):
+    """Closed-form check of a triangle-mesh area light: a square Lambertian emitter of side `side` facing down at
+    `height` over the origin of a large matte floor; a narrow camera off to the side looks at the origin.  Radiance
+    leaving the floor there = Kd / pi * E with E = 4 L (a/s) atan(a/s), a = side / 2, s = sqrt(a^2 + height^2)."""
+    def quad(p0, p1, p2, p3):
+        v = np.array([p0, p1, p2, p3], np.float32)
+        return api.TriangleMesh(Transform.identity(), np.array([0, 1, 2, 0, 2, 3], np.uint32), v)
+    a = 0.5 * side
+    prims = [api.GeometricPrimitive(quad((-50, -50, 0), (50, -50, 0), (50, 50, 0), (-50, 50, 0)), api.MatteMaterial(kd)),
+             api.GeometricPrimitive(quad((-a, -a, height), (-a, a, height), (a, a, height), (a, -a, height)),
+                                    api.MatteMaterial(0.0), api.DiffuseAreaLight(emit))]
+    scene = api.Scene(prims, [], backend=backend)
+    cam_to_world = Transform.look_at((4, 0, 1), (0, 0, 0), (0, 0, 1)).inverse()
+    camera = api.PerspectiveCamera(cam_to_world, resolution, fov=0.5)
+    film = api.Film(resolution, backend=backend)
+    s_ = float(np.sqrt(a * a + height * height))
+    expected = kd / np.pi * 4.0 * emit * (a / s_) * np.arctan(a / s_)
+    return scene, camera, film, expected
