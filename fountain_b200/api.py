@@ -775,6 +775,14 @@ class SamplerIntegrator:
         """One process, several GPUs (ftn_render_multi): `scenes` holds the same scene built on each device
         (`Scene(..., device=i)`); the samples are sharded by index, the partial films are summed with one NCCL
         reduce onto scenes[0]'s device and read back into film.pixels."""
+        if len(scenes) > 1:
+            # The library binds NCCL at run time by soname (libnccl.so.2).  A Python process that will also import torch
+            # must load torch's bundled (newer) copy FIRST, or torch's own import later fails on the system copy's
+            # missing symbols; a host without torch (the Rust binary) simply gets the system library.
+            try:
+                import torch  # noqa: F401
+            except ImportError:
+                pass
         st = A.FtnStats()
         out = film._pixels
         cam, f, s, it = self.camera.to_abi(), film.to_abi(), sampler.to_abi(sample_begin, sample_stride), self.radiance.to_abi()

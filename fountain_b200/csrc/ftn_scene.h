@@ -105,6 +105,11 @@ struct EnvLightData {
     const float* cond_cdf;   // nv * (nu+1)
     const float* cond_integral;  // nv  (== marginal func)
     const float* marg_cdf;   // nv + 1
+    // guide tables of the two cdf searches (ftn_shade.cuh env_guide_entry): entry g = number of cdf entries <= g / n of
+    // that row, so the search for u only looks between entries floor(u n) - 1 and floor(u n) + 2.  Same index as the
+    // full binary search (sampling.rs:66-81), ~3 dependent loads instead of ~11 per search.  nullptr = full search.
+    const uint32_t* cond_guide;  // nv * (nu + 1)
+    const uint32_t* marg_guide;  // nv + 1
     float marg_integral;
     int32_t levels;          // 1 + floor(log2(max(w,h)))  (mipmap.rs:103)
     M4 l2w, w2l;

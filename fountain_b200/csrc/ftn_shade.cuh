@@ -29,6 +29,16 @@ FTN_HD V3 cross(V3 a, V3 b) { return V3(a.y * b.z - a.z * b.y, a.z * b.x - a.x *
 FTN_HD V3 normalize(V3 a) { return a * (1.0f / sqrtf(dot(a, a))); }
 FTN_HD float abs_dot(V3 a, V3 b) { return fabsf(dot(a, b)); }
 
+// sin / cos of the SAMPLING code (directions drawn from random numbers; compared with the oracle under the image
+// tolerance, not bit for bit): the SFU forms on the device (abs error ~2^-21 on [0, 2 pi]), libm on the host harness
+#if defined(__CUDA_ARCH__) && !defined(FTN_SHADE_PRECISE)
+FTN_HD void f_sincos(float x, float* s, float* c) { __sincosf(x, s, c); }
+FTN_HD float f_sin(float x) { return __sinf(x); }
+#else
+FTN_HD void f_sincos(float x, float* s, float* c) { *s = sinf(x); *c = cosf(x); }
+FTN_HD float f_sin(float x) { return sinf(x); }
+#endif
+
 // ---- sampling.rs -------------------------------------------------------------------------------------
 FTN_HD void concentric_sample_disk(float u0, float u1, float* dx, float* dy) {   // :5-19
     const float ox = 2.0f * u0 - 1.0f, oy = 2.0f * u1 - 1.0f;
@@ -36,7 +46,8 @@ FTN_HD void concentric_sample_disk(float u0, float u1, float* dx, float* dy) {  
     float theta, r;
     if (fabsf(ox) > fabsf(oy)) { theta = FTN_PI_4 * (oy / ox); r = ox; }
     else { theta = FTN_PI_2 - FTN_PI_4 * (ox / oy); r = oy; }
-    *dx = r * cosf(theta); *dy = r * sinf(theta);
+    float st, ct; f_sincos(theta, &st, &ct);
+    *dx = r * ct; *dy = r * st;
 }
 FTN_HD V3 cosine_sample_hemisphere(float u0, float u1) {   // :21-25
     float dx, dy; concentric_sample_disk(u0, u1, &dx, &dy);
@@ -100,21 +111,38 @@ FTN_HD void dist_row_build(const float* f, int nu, float* c, float* integral) {
 }
 
 // sampling.rs:66-81 over a device array: index of the last cdf entry <= u, clamped to [0, size-2]
-FTN_HD int search_sorted_le(const float* cdf, int size, float u) {
-    int first = 0, len = size;
+// the partition point of the search: number of entries of cdf[first .. first + len) that are <= u, plus first
+FTN_HD int search_partition(const float* cdf, int first, int len, float u) {
     while (len > 0) {
         const int half = len >> 1, middle = first + half;
         if (cdf[middle] <= u) { first = middle + 1; len -= half + 1; }
         else len = half;
     }
-    int r = first - 1;
+    return first;
+}
+FTN_HD int search_sorted_le(const float* cdf, int size, float u) {
+    int r = search_partition(cdf, 0, size, u) - 1;
     if (r < 0) r = 0;
     if (r > size - 2) r = size - 2;
     return r;
 }
+// Guide table of one cdf row (n + 1 entries): entry g in [0, n] = partition point of the key g / n.
+FTN_HD uint32_t env_guide_entry(const float* cdf, int n, int g) { return (uint32_t)search_partition(cdf, 0, n + 1, (float)g / (float)n); }
+// search_sorted_le through the guide: floor(u n) is within one of the true bucket whatever the rounding of u * n, and the
+// partition point is monotone in u, so it lies between the guide entries of buckets g - 1 and g + 2.
+FTN_HD int search_sorted_le_guided(const float* cdf, const uint32_t* guide, int n, float u) {
+    const float gf = u * (float)n;
+    int g = (gf > 0.0f) ? (int)fminf(gf, 2.0e9f) : 0;
+    if (g > n - 1) g = n - 1;
+    const int lo = (int)guide[g > 0 ? g - 1 : 0], hi = (int)guide[g + 2 < n ? g + 2 : n];
+    int r = search_partition(cdf, lo, hi - lo, u) - 1;
+    if (r < 0) r = 0;
+    if (r > n - 1) r = n - 1;
+    return r;
+}
 // Distribution1D::sample_continuous, sampling.rs:121-134
-FTN_HD void dist1d_sample(const float* func, const float* cdf, int n, float integral, float u, float* x, float* pdf, int* idx) {
-    const int i = search_sorted_le(cdf, n + 1, u);
+FTN_HD void dist1d_sample(const float* func, const float* cdf, int n, float integral, float u, float* x, float* pdf, int* idx, const uint32_t* guide = nullptr) {
+    const int i = guide ? search_sorted_le_guided(cdf, guide, n, u) : search_sorted_le(cdf, n + 1, u);
     float du = u - cdf[i];
     const float w = cdf[i + 1] - cdf[i];
     if (w > 0.0f) du /= w;
@@ -125,8 +153,9 @@ FTN_HD void dist1d_sample(const float* func, const float* cdf, int n, float inte
 // Distribution2D::sample_continuous / pdf, sampling.rs:163-179
 FTN_HD void env_dist_sample(const EnvLightData& e, float u0, float u1, float* d0, float* d1, float* pdf) {
     float pdf1, pdf0; int v, dummy;
-    dist1d_sample(e.cond_integral, e.marg_cdf, e.nv, e.marg_integral, u1, d1, &pdf1, &v);
-    dist1d_sample(e.cond_func + (size_t)v * e.nu, e.cond_cdf + (size_t)v * (e.nu + 1), e.nu, e.cond_integral[v], u0, d0, &pdf0, &dummy);
+    dist1d_sample(e.cond_integral, e.marg_cdf, e.nv, e.marg_integral, u1, d1, &pdf1, &v, e.marg_guide);
+    dist1d_sample(e.cond_func + (size_t)v * e.nu, e.cond_cdf + (size_t)v * (e.nu + 1), e.nu, e.cond_integral[v], u0, d0, &pdf0, &dummy,
+                  e.cond_guide ? e.cond_guide + (size_t)v * (e.nu + 1) : nullptr);
     *pdf = pdf0 * pdf1;
 }
 FTN_HD float env_dist_pdf(const EnvLightData& e, float px, float py) {
@@ -159,8 +188,8 @@ FTN_HD bool env_sample(const EnvLightData& e, float u0, float u1, V3* wi, float*
     env_dist_sample(e, u0, u1, &uvx, &uvy, &map_pdf);
     if (map_pdf == 0.0f) return false;
     const float theta = uvy * FTN_PI, phi = uvx * 2.0f * FTN_PI;
-    const float st = sinf(theta), ct = cosf(theta);
-    *wi = transform_vector(e.l2w, V3(st * cosf(phi), st * sinf(phi), ct));
+    float st, ct, sp, cp; f_sincos(theta, &st, &ct); f_sincos(phi, &sp, &cp);
+    *wi = transform_vector(e.l2w, V3(st * cp, st * sp, ct));
     *pdf = (st == 0.0f) ? 0.0f : map_pdf / (2.0f * FTN_PI * FTN_PI * st);
     *radiance = env_lookup_width(e, uvx, uvy, 0.0f);
     return true;
@@ -272,7 +301,8 @@ FTN_HD V3 tr_sample_wh(const Lobe& l, V3 wo, float u0, float u1) {
         cos_t = 1.0f / sqrtf(1.0f + tan2);
     }
     const float sin_t = sqrtf(fmaxf(0.0f, 1.0f - cos_t * cos_t));
-    const V3 wh = V3(sin_t * cosf(phi), sin_t * sinf(phi), cos_t);   // spherical_direction, math.rs:74-80
+    float sphi, cphi; f_sincos(phi, &sphi, &cphi);
+    const V3 wh = V3(sin_t * cphi, sin_t * sphi, cos_t);   // spherical_direction, math.rs:74-80
     return same_hemisphere(wo, wh) ? wh : -wh;
 }
 template <int FRESNEL> FTN_HD V3 lobe_fresnel(const Lobe& l, float cos_i) {

@@ -480,6 +480,16 @@ __global__ void k_rgb_to_rgba(const float* __restrict__ rgb, size_t n, F4* __res
     if (i < n) { F4 t; t.x = rgb[3 * i]; t.y = rgb[3 * i + 1]; t.z = rgb[3 * i + 2]; t.w = 0.0f; out[i] = t; }
 }
 
+// one thread per guide entry: a full binary search of its key in its row (paid once per scene, saves ~8 dependent loads
+// per cdf search of every light sample)
+__global__ void __launch_bounds__(256)
+k_env_guide(const float* __restrict__ cdf, int n, int rows, uint32_t* __restrict__ guide) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= (size_t)rows * (size_t)(n + 1)) return;
+    const int row = (int)(k / (size_t)(n + 1)), g = (int)(k % (size_t)(n + 1));
+    guide[k] = env_guide_entry(cdf + (size_t)row * (size_t)(n + 1), n, g);
+}
+
 static int build_env_light(FtnScene* s, const FtnLight& fl, LightData* out) {
     EnvLightData& e = out->env;
     e.w = fl.width; e.h = fl.height;
@@ -516,6 +526,14 @@ static int build_env_light(FtnScene* s, const FtnLight& fl, LightData* out) {
     FTN_CUDA(scene_malloc(&d_mint, sizeof(float))); s->owned.push_back(d_mint);
     k_env_row_cdf<<<1, 128>>>(d_int, e.nv, 1, d_mcdf, d_mint);
     FTN_LAUNCHED();
+    uint32_t *d_cguide, *d_mguide;
+    FTN_CUDA(scene_malloc(&d_cguide, (size_t)e.nv * (e.nu + 1) * sizeof(uint32_t))); s->owned.push_back(d_cguide);
+    FTN_CUDA(scene_malloc(&d_mguide, (size_t)(e.nv + 1) * sizeof(uint32_t))); s->owned.push_back(d_mguide);
+    k_env_guide<<<(unsigned)(((size_t)e.nv * (e.nu + 1) + 255) / 256), 256>>>(d_cdf, e.nu, e.nv, d_cguide);
+    FTN_LAUNCHED();
+    k_env_guide<<<(unsigned)((e.nv + 1 + 255) / 256), 256>>>(d_mcdf, e.nv, 1, d_mguide);
+    FTN_LAUNCHED();
+    e.cond_guide = d_cguide; e.marg_guide = d_mguide;
     FTN_CUDA(cudaMemcpy(&e.marg_integral, d_mint, sizeof(float), cudaMemcpyDeviceToHost));
     return FTN_OK;
 }

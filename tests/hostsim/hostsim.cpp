@@ -31,6 +31,7 @@ struct SimScene {
     std::vector<MeshData> meshes; std::vector<MaterialData> mats;
     std::vector<SphereData> spheres; std::vector<LightData> lights;
     std::vector<std::vector<F4>> env_tex; std::vector<std::vector<float>> env_f;   // storage behind EnvLightData pointers
+    std::list<std::vector<uint32_t>> env_g;
     std::list<std::vector<F4>> images;   // storage behind MaterialData::image
     std::vector<F4> nodes, tris; uint32_t n_nodes = 0; bool wide = false; uint32_t bvh_levels = 0;
     std::vector<uint32_t> codes, order;
@@ -118,6 +119,11 @@ SIM_API int sim_scene_create(const FtnSceneDesc* d, SimScene** out) {
         s->env_f.emplace_back(e.nv + 1); std::vector<float>& mcdf = s->env_f.back();
         dist_row_build(integ.data(), e.nv, mcdf.data(), &e.marg_integral);
         e.cond_func = func.data(); e.cond_cdf = cdf.data(); e.cond_integral = integ.data(); e.marg_cdf = mcdf.data();
+        s->env_g.emplace_back((size_t)e.nv * (e.nu + 1)); std::vector<uint32_t>& cg = s->env_g.back();                    // k_env_guide
+        for (int v = 0; v < e.nv; ++v) for (int g = 0; g <= e.nu; ++g) cg[(size_t)v * (e.nu + 1) + g] = env_guide_entry(&cdf[(size_t)v * (e.nu + 1)], e.nu, g);
+        s->env_g.emplace_back((size_t)e.nv + 1); std::vector<uint32_t>& mg = s->env_g.back();
+        for (int g = 0; g <= e.nv; ++g) mg[g] = env_guide_entry(mcdf.data(), e.nv, g);
+        e.cond_guide = cg.data(); e.marg_guide = mg.data();
         s->lights.push_back(ld);
     }
     build_mesh_table(d, &s->meshes, &s->lights);   // as scene.cu: the per-triangle area lights of emissive meshes
@@ -492,6 +498,20 @@ SIM_API int sim_kat_env(const SimScene* s, const float u[2], float out[11]) {
     out[7] = env_pdf(e, wi);
     const V3 le = env_emitted(e, wi); out[8] = le.x; out[9] = le.y; out[10] = le.z;
     return FTN_OK;
+}
+// guided cdf search (search_sorted_le_guided over env_guide_entry) against the full binary search (sampling.rs:66-81):
+// builds the Distribution1D of func[0..n) the way the device does and returns the number of u's whose index differs
+SIM_API int sim_kat_guided_search(const float* func, int n, const float* u, int n_u, int* first_bad) {
+    std::vector<float> cdf((size_t)n + 1); float integral;
+    dist_row_build(func, n, cdf.data(), &integral);
+    std::vector<uint32_t> guide((size_t)n + 1);
+    for (int g = 0; g <= n; ++g) guide[g] = env_guide_entry(cdf.data(), n, g);
+    int bad = 0;
+    for (int k = 0; k < n_u; ++k) {
+        const int a = search_sorted_le(cdf.data(), n + 1, u[k]), b = search_sorted_le_guided(cdf.data(), guide.data(), n, u[k]);
+        if (a != b) { if (!bad && first_bad) *first_bad = k; ++bad; }
+    }
+    return bad;
 }
 // the device's mip_lookup_trilinear on a pyramid in the ABI's layout; (dsdx, 0, 0, 0) differentials give width = 2 |dsdx|
 SIM_API int sim_kat_mipmap_lookup(const float* pyramid, int w, int h, int levels, int wrap, float s, float t, float width, float out[3]) {

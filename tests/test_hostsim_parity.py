@@ -379,3 +379,24 @@ def test_mipmap_lookup_matches_oracle(sim, oracle, wrap):
             assert sim.library().sim_kat_mipmap_lookup(ptr, mp.width, mp.height, len(mp.levels), mp.wrap, s, t, w, a) == 0
             assert oracle.library().orc_kat_mipmap_lookup(ptr, mp.width, mp.height, len(mp.levels), mp.wrap, s, t, w, b) == 0
             assert np.allclose(np.array(list(a)), np.array(list(b)), rtol=1e-5, atol=1e-7), (shape, s, t, w, list(a), list(b))
+
+
+def test_guided_cdf_search_equals_binary_search(sim):
+    """The env light's two cdf searches go through guide tables on the device (ftn_shade.cuh search_sorted_le_guided):
+    same index as Distribution1D's binary search (sampling.rs:66-81) for flat, peaked, zero-run and tiny rows, at bucket
+    edges and for u just below 1."""
+    rng = np.random.default_rng(23)
+    lib = sim.library()
+    lib.sim_kat_guided_search.restype = C.c_int
+    lib.sim_kat_guided_search.argtypes = [C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]
+    for n in (1, 2, 3, 7, 64, 1000, 2048):
+        rows = [np.ones(n), rng.random(n), rng.random(n) ** 12, np.where(rng.random(n) < 0.7, 0.0, rng.random(n)), np.zeros(n)]
+        peak = np.full(n, 1e-6); peak[n // 3] = 1e4
+        rows.append(peak)
+        for f in rows:
+            f = np.ascontiguousarray(f, dtype=np.float32)
+            u = np.concatenate([rng.random(20000), np.arange(n + 1) / max(n, 1), np.nextafter(np.arange(1, n + 1) / n, 0), [0.0, np.nextafter(np.float32(1.0), np.float32(0.0))]]).astype(np.float32)
+            u = np.ascontiguousarray(np.clip(u, 0.0, np.nextafter(np.float32(1.0), np.float32(0.0))))
+            bad_at = C.c_int(-1)
+            bad = lib.sim_kat_guided_search(f.ctypes.data_as(C.POINTER(C.c_float)), n, u.ctypes.data_as(C.POINTER(C.c_float)), len(u), C.byref(bad_at))
+            assert bad == 0, (n, bad, float(u[bad_at.value]))
