@@ -6,7 +6,7 @@ bound from ``oracle/orc.py`` -- never from this package.
 """
 import ctypes as C
 
-FTN_ABI_VERSION = 2
+FTN_ABI_VERSION = 3
 FTN_MAX_QUERIES_IN_FLIGHT = 64
 FTN_STATS_COUNT_TRAVERSAL, FTN_STATS_TIME_KERNELS = 1, 2
 FTN_NO_HIT = 0xFFFFFFFF
@@ -20,7 +20,7 @@ FTN_ERR_UNSUPPORTED = -5
 FTN_ERR_OUT_OF_MEMORY = -6
 
 FTN_MESH_FLIP_NORMALS = 1
-FTN_MATERIAL_MATTE, FTN_MATERIAL_METAL, FTN_MATERIAL_PLASTIC, FTN_MATERIAL_MIRROR = 0, 1, 2, 3
+FTN_MATERIAL_MATTE, FTN_MATERIAL_METAL, FTN_MATERIAL_PLASTIC, FTN_MATERIAL_MIRROR, FTN_MATERIAL_GLASS = 0, 1, 2, 3, 4
 FTN_TEXTURE_CONSTANT, FTN_TEXTURE_CHECKERBOARD, FTN_TEXTURE_UV, FTN_TEXTURE_IMAGE = 0, 1, 2, 3
 FTN_WRAP_REPEAT, FTN_WRAP_BLACK, FTN_WRAP_CLAMP = 0, 1, 2
 FTN_MAX_MIP_LEVELS = 16
@@ -52,7 +52,8 @@ class FtnMaterial(C.Structure):
     _fields_ = [("type", i32), ("kd", f32 * 3), ("ks", f32 * 3), ("eta", f32 * 3), ("k", f32 * 3),
                 ("u_roughness", f32), ("v_roughness", f32), ("remap_roughness", i32), ("kr", f32 * 3),
                 ("kd_texture", i32), ("tex1", f32 * 3), ("tex2", f32 * 3), ("uv_scale", f32 * 2), ("uv_delta", f32 * 2), ("sigma", f32),
-                ("image", C.POINTER(f32)), ("image_width", i32), ("image_height", i32), ("image_levels", i32), ("image_wrap", i32)]
+                ("image", C.POINTER(f32)), ("image_width", i32), ("image_height", i32), ("image_levels", i32), ("image_wrap", i32),
+                ("kt", f32 * 3)]
 
 
 class FtnSphere(C.Structure):

@@ -314,6 +314,24 @@ class MirrorMaterial:
             m.kr[:] = self.kr.tolist()
 
 
+class GlassMaterial:
+    """material/glass.rs; defaults of constructors.rs:198-205 (Kr 1, Kt 1, index 1.5, roughness 0, remaproughness true --
+    which turns roughness 0 into a small alpha: rough glass).  Alphas of exactly 0 (FresnelSpecular, `todo!()` in the
+    reference) make scene creation fail with FTN_ERR_UNSUPPORTED."""
+    type = A.FTN_MATERIAL_GLASS
+
+    def __init__(self, kr=1.0, kt=1.0, eta=1.5, u_roughness=0.0, v_roughness=0.0, remap_roughness=True):
+        self.kr, self.kt, self.eta = _spectrum(kr), _spectrum(kt), float(eta)
+        self.u_roughness, self.v_roughness, self.remap_roughness = float(u_roughness), float(v_roughness), bool(remap_roughness)
+
+    def fill(self, m):
+        m.type = self.type
+        m.kr[:] = self.kr.tolist()
+        m.kt[:] = self.kt.tolist()
+        m.eta[:] = [self.eta] * 3
+        m.u_roughness, m.v_roughness, m.remap_roughness = self.u_roughness, self.v_roughness, int(self.remap_roughness)
+
+
 class DiffuseAreaLight:
     """light/diffuse.rs:24-41; attached to a shape through GeometricPrimitive.light."""
 

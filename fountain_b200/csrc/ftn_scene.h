@@ -64,11 +64,11 @@ struct MeshData {
     int32_t pad[3];
 };
 
-#define FTN_CLASS_OREN_NAYAR 4   /* matte.rs:45-49: its own class keeps the Lambert shade kernel free of the rough-diffuse code */
-#define FTN_N_CLASSES 5
+#define FTN_CLASS_OREN_NAYAR 5   /* matte.rs:45-49: its own class keeps the Lambert shade kernel free of the rough-diffuse code */
+#define FTN_N_CLASSES 6
 struct MaterialData {
     int32_t type;            // material CLASS = shade queue: FtnMaterialType, or FTN_CLASS_OREN_NAYAR for a matte with sigma != 0
-    float kd[3], ks[3], eta[3], k[3];
+    float kd[3], ks[3], eta[3], k[3];   // mirror: Kr in kd;  glass: Kr in kd, Kt in ks, index of refraction in eta[0]
     float alpha_x, alpha_y;  // after the roughness remap (microfacet.rs:40-45)
     int32_t kd_texture;      // FtnTextureType of Kd
     float tex1[3], tex2[3], uv_scale[2], uv_delta[2];
@@ -192,7 +192,7 @@ struct FtnScene {
     // that queries enqueued on different streams never share a counter
     unsigned long long* d_work = nullptr;
     mutable std::atomic<uint32_t> work_slot{0};
-    bool material_present[FTN_N_CLASSES] = {false, false, false, false, false};   // which shade kernels a render launches
+    bool material_present[FTN_N_CLASSES] = {false, false, false, false, false, false};   // which shade kernels a render launches
     bool has_image_texture = false;         // any Kd image texture: selects the shade kernels that carry the mip lookup
     bool has_null_material = false;         // any primitive with a null BSDF (path.rs:76-80)
     ftn::SceneView view() const;

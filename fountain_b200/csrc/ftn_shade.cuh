@@ -259,11 +259,15 @@ template <> struct LobeKind<FTN_MATERIAL_PLASTIC, 0> { static constexpr int valu
 template <> struct LobeKind<FTN_MATERIAL_PLASTIC, 1> { static constexpr int value = 1; };
 template <> struct LobeKind<FTN_MATERIAL_MIRROR, 0> { static constexpr int value = 2; };
 template <> struct LobeKind<FTN_CLASS_OREN_NAYAR, 0> { static constexpr int value = 3; };
-// Fresnel of the microfacet lobe: 0 FresnelConductor{1, eta, k} (metal.rs:52-56), 1 FresnelDielectric{1.5, 1.0} (plastic.rs:34)
-template <int MAT> struct LobeFresnel { static constexpr int value = (MAT == FTN_MATERIAL_PLASTIC) ? 1 : 0; };
+template <> struct LobeKind<FTN_MATERIAL_GLASS, 0> { static constexpr int value = 1; };   // MicrofacetReflection (Kr), glass.rs:76-79
+template <> struct LobeKind<FTN_MATERIAL_GLASS, 1> { static constexpr int value = 4; };   // MicrofacetTransmission (Kt), glass.rs:88-91
+// Fresnel of the microfacet lobe: 0 FresnelConductor{1, eta, k} (metal.rs:52-56), 1 FresnelDielectric{1.5, 1.0} (plastic.rs:34),
+// 2 FresnelDielectric{1, eta} with the material's index in Lobe::eta.x (glass.rs:70)
+template <int MAT> struct LobeFresnel { static constexpr int value = (MAT == FTN_MATERIAL_PLASTIC) ? 1 : (MAT == FTN_MATERIAL_GLASS) ? 2 : 0; };
 
 template <int KIND> FTN_HD constexpr int lobe_type() {
-    return (KIND == 0 || KIND == 3) ? (BXDF_REFLECTION | BXDF_DIFFUSE) : KIND == 1 ? (BXDF_REFLECTION | BXDF_GLOSSY) : (BXDF_REFLECTION | BXDF_SPECULAR);
+    return (KIND == 0 || KIND == 3) ? (BXDF_REFLECTION | BXDF_DIFFUSE) : KIND == 1 ? (BXDF_REFLECTION | BXDF_GLOSSY)
+         : KIND == 4 ? (BXDF_TRANSMISSION | BXDF_GLOSSY) : (BXDF_REFLECTION | BXDF_SPECULAR);
 }
 template <int KIND> FTN_HD constexpr bool lobe_matches(int flags) { return KIND >= 0 && (flags & lobe_type<KIND>()) == lobe_type<KIND>(); }
 
@@ -307,11 +311,39 @@ FTN_HD V3 tr_sample_wh(const Lobe& l, V3 wo, float u0, float u1) {
 }
 template <int FRESNEL> FTN_HD V3 lobe_fresnel(const Lobe& l, float cos_i) {
     if (FRESNEL == 0) return fresnel_conductor(fabsf(cos_i), l.eta, l.k);   // fresnel.rs:70-73
+    if (FRESNEL == 2) return v3s(fresnel_dielectric(cos_i, 1.0f, l.eta.x));
     return v3s(fresnel_dielectric(cos_i, 1.5f, 1.0f));
 }
+// refract, reflection/mod.rs:70-78
+FTN_HD bool refract(V3 wi, V3 n, float eta, V3* wt) {
+    const float cos_i = dot(n, wi);
+    const float sin2_i = fmaxf(0.0f, 1.0f - cos_i * cos_i);
+    const float sin2_t = eta * eta * sin2_i;
+    if (sin2_t >= 1.0f) return false;
+    const float cos_t = sqrtf(1.0f - sin2_t);
+    *wt = eta * -wi + (eta * cos_i - cos_t) * n;
+    return true;
+}
+// MicrofacetTransmission::get_eta with eta_a = 1, eta_b = the material's index (reflection/mod.rs:376-378)
+FTN_HD float mt_eta(const Lobe& l, V3 wo) { return (wo.z > 0.0f) ? l.eta.x / 1.0f : 1.0f / l.eta.x; }
+
 template <int KIND, int FRESNEL> FTN_HD V3 lobe_f(const Lobe& l, V3 wo, V3 wi) {
     if (KIND == 0) return l.r * FTN_INV_PI;   // reflection/mod.rs:159-161
     if (KIND == 2) return v3s(0.0f);           // reflection/mod.rs:181-183
+    if (KIND == 4) {                           // MicrofacetTransmission::f, reflection/mod.rs:386-404 (TransportMode::Radiance)
+        if (same_hemisphere(wo, wi)) return v3s(0.0f);
+        const float cos_o = wo.z, cos_i = wi.z;
+        if (cos_o == 0.0f || cos_i == 0.0f) return v3s(0.0f);
+        const float eta = mt_eta(l, wo);
+        V3 wh = normalize(wo + wi * eta);
+        if (wh.z < 0.0f) wh = -wh;
+        const float F = fresnel_dielectric(dot(wo, wh), 1.0f, l.eta.x);
+        const float sqrt_denom = dot(wo, wh) + eta * dot(wi, wh);
+        const float factor = 1.0f / eta;
+        const float G = 1.0f / (1.0f + tr_lambda(l, wo) + tr_lambda(l, wi));
+        return (v3s(1.0f) - v3s(F)) * l.r *
+               fabsf(tr_d(l, wh) * G * (eta * eta) * abs_dot(wi, wh) * abs_dot(wo, wh) * (factor * factor) / (cos_i * cos_o * (sqrt_denom * sqrt_denom)));
+    }
     if (KIND == 3) {                           // OrenNayar::f, reflection/mod.rs:274-296
         const float sin_i = sin_theta(wi), sin_o = sin_theta(wo);
         float max_cos = 0.0f;
@@ -336,6 +368,14 @@ template <int KIND, int FRESNEL> FTN_HD V3 lobe_f(const Lobe& l, V3 wo, V3 wi) {
 template <int KIND> FTN_HD float lobe_pdf(const Lobe& l, V3 wo, V3 wi) {
     if (KIND == 0 || KIND == 3) return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * FTN_INV_PI : 0.0f;   // DefaultSampleF :140-146
     if (KIND == 2) return 0.0f;                // :194-196
+    if (KIND == 4) {                           // MicrofacetTransmission::pdf, reflection/mod.rs:426-435
+        if (same_hemisphere(wo, wi)) return 0.0f;
+        const float eta = mt_eta(l, wo);
+        const V3 wh = normalize(wo + wi * eta);
+        const float sqrt_denom = dot(wo, wh) + eta * dot(wi, wh);
+        const float dwh_dwi = fabsf(((eta * eta) * dot(wi, wh)) / (sqrt_denom * sqrt_denom));
+        return tr_pdf(l, wh) * dwh_dwi;
+    }
     if (!same_hemisphere(wo, wi)) return 0.0f;   // :354-360
     const V3 wh = normalize(wo + wi);
     return tr_pdf(l, wh) / (4.0f * dot(wo, wh));
@@ -351,6 +391,16 @@ template <int KIND, int FRESNEL> FTN_HD bool lobe_sample_f(const Lobe& l, V3 wo,
     if (KIND == 2) {   // reflection/mod.rs:185-192; FresnelNoOp evaluates to 1
         const V3 wi = V3(-wo.x, -wo.y, wo.z);
         s->pdf = 1.0f; s->f = (v3s(1.0f) * l.r) / abs_cos_theta(wi); s->wi = wi; s->type = lobe_type<KIND>();
+        return true;
+    }
+    if (KIND == 4) {   // MicrofacetTransmission::sample_f, reflection/mod.rs:406-424
+        if (wo.z == 0.0f) return false;
+        const V3 wh = tr_sample_wh(l, wo, u0, u1);
+        if (dot(wo, wh) < 0.0f) return false;
+        const float eta = mt_eta(l, -wo);   // "NOTE: this inverts the eta fraction"
+        V3 wi;
+        if (!refract(wo, wh, eta, &wi)) return false;
+        s->f = lobe_f<KIND, FRESNEL>(l, wo, wi); s->wi = wi; s->pdf = lobe_pdf<KIND>(l, wo, wi); s->type = lobe_type<KIND>();
         return true;
     }
     const V3 wh = tr_sample_wh(l, wo, u0, u1);   // :338-352
@@ -381,13 +431,14 @@ FTN_HD V3 bsdf_to_local(const Bsdf& b, V3 v) { return V3(dot(v, b.ss), dot(v, b.
 FTN_HD V3 bsdf_to_world(const Bsdf& b, V3 v) {
     return V3(b.ss.x * v.x + b.ts.x * v.y + b.ns.x * v.z, b.ss.y * v.x + b.ts.y * v.y + b.ns.y * v.z, b.ss.z * v.x + b.ts.z * v.y + b.ns.z * v.z);
 }
-// Sum of f over the matching lobes that pass the reflect/transmit gate (all in-scope lobes are
-// REFLECTION lobes, so only `refl` opens the gate).
+// Sum of f over the matching lobes that pass the reflect/transmit gate (bsdf.rs:72-80): a REFLECTION lobe counts when wi
+// and wo lie on the same side of the geometric normal, a TRANSMISSION lobe (rough glass only) when they do not.
+template <int KIND> FTN_HD constexpr bool lobe_gate(bool refl) { return ((lobe_type<KIND < 0 ? 0 : KIND>() & BXDF_TRANSMISSION) != 0) ? !refl : refl; }
 template <int MAT> FTN_HD V3 bsdf_sum_f(const Bsdf& b, V3 wo, V3 wi, bool refl, int flags) {
     constexpr int K0 = LobeKind<MAT, 0>::value, K1 = LobeKind<MAT, 1>::value, FR = LobeFresnel<MAT>::value;
     V3 sum = v3s(0.0f);
-    if (K0 >= 0 && b.on0 && lobe_matches<K0>(flags) && refl) sum = sum + lobe_f<K0 < 0 ? 0 : K0, FR>(b.l0, wo, wi);
-    if (K1 >= 0 && b.on1 && lobe_matches<K1>(flags) && refl) sum = sum + lobe_f<K1 < 0 ? 0 : K1, FR>(b.l1, wo, wi);
+    if (K0 >= 0 && b.on0 && lobe_matches<K0>(flags) && lobe_gate<K0>(refl)) sum = sum + lobe_f<K0 < 0 ? 0 : K0, FR>(b.l0, wo, wi);
+    if (K1 >= 0 && b.on1 && lobe_matches<K1>(flags) && lobe_gate<K1>(refl)) sum = sum + lobe_f<K1 < 0 ? 0 : K1, FR>(b.l1, wo, wi);
     return sum;
 }
 template <int MAT> FTN_HD V3 bsdf_f(const Bsdf& b, V3 wo_w, V3 wi_w, int flags) {   // :67-82
@@ -507,6 +558,11 @@ template <int MAT> FTN_HD void material_bsdf(const MaterialData& m, float u, flo
         const V3 kd0 = material_kd(m, u, v, td);
         const V3 r = V3(clampf(kd0.x, 0.0f, FTN_INF), clampf(kd0.y, 0.0f, FTN_INF), clampf(kd0.z, 0.0f, FTN_INF));
         if (!is_black(r)) { b->on0 = true; b->l0.r = r; b->l0.ax = m.alpha_x; b->l0.ay = m.alpha_y; }
+    } else if (MAT == FTN_MATERIAL_GLASS) {   // glass.rs:52-96, the non-specular branch (rough glass); alphas remapped at scene creation
+        const V3 r = V3(clampf(m.kd[0], 0.0f, FTN_INF), clampf(m.kd[1], 0.0f, FTN_INF), clampf(m.kd[2], 0.0f, FTN_INF));
+        const V3 t = V3(clampf(m.ks[0], 0.0f, FTN_INF), clampf(m.ks[1], 0.0f, FTN_INF), clampf(m.ks[2], 0.0f, FTN_INF));
+        if (!is_black(r)) { b->on0 = true; b->l0.r = r; b->l0.ax = m.alpha_x; b->l0.ay = m.alpha_y; b->l0.eta = v3s(m.eta[0]); b->l0.k = v3s(0.0f); }
+        if (!is_black(t)) { b->on1 = true; b->l1.r = t; b->l1.ax = m.alpha_x; b->l1.ay = m.alpha_y; b->l1.eta = v3s(m.eta[0]); b->l1.k = v3s(0.0f); }
     } else if (MAT == FTN_MATERIAL_MIRROR) {   // mirror.rs:21-30; Kr (constant or textured) is carried in MaterialData::kd and its texture fields
         const V3 kr0 = material_kd(m, u, v, td);
         const V3 r = V3(clampf(kr0.x, 0.0f, FTN_INF), clampf(kr0.y, 0.0f, FTN_INF), clampf(kr0.z, 0.0f, FTN_INF));

@@ -28,8 +28,8 @@ namespace ftn {
 int sm_count();
 unsigned trace_grid(size_t n, int blocks_per_sm);
 
-enum { Q_ACTIVE_OUT = 0, Q_MISS, Q_NULL, Q_MAT0, Q_MAT1, Q_MAT2, Q_MAT3, Q_MAT4, Q_SHADOW, Q_MIS, Q_COUNT };
-static_assert(Q_MAT4 - Q_MAT0 + 1 == FTN_N_CLASSES, "one shade queue per material class");
+enum { Q_ACTIVE_OUT = 0, Q_MISS, Q_NULL, Q_MAT0, Q_MAT1, Q_MAT2, Q_MAT3, Q_MAT4, Q_MAT5, Q_SHADOW, Q_MIS, Q_COUNT };
+static_assert(Q_MAT5 - Q_MAT0 + 1 == FTN_N_CLASSES, "one shade queue per material class");
 enum { W_EXTEND = Q_COUNT, W_SHADOW, W_MIS, CTR_COUNT };
 
 struct PathArrays {
@@ -471,9 +471,10 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
                 else k_shade<Q_MAT3><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT3], q, counts, d_err);
                 FTN_LAUNCHED();
             }
-            if (s->material_present[4]) {
-                if (s->has_image_texture) k_shade<Q_MAT4, true><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT4], q, counts, d_err);
-                else k_shade<Q_MAT4><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT4], q, counts, d_err);
+            if (s->material_present[4]) { k_shade<Q_MAT4><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT4], q, counts, d_err); FTN_LAUNCHED(); }   // rough glass
+            if (s->material_present[5]) {
+                if (s->has_image_texture) k_shade<Q_MAT5, true><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT5], q, counts, d_err);
+                else k_shade<Q_MAT5><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT5], q, counts, d_err);
                 FTN_LAUNCHED();
             }
             timer.end();

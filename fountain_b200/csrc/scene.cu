@@ -570,10 +570,11 @@ int scene_create(const FtnSceneDesc* d, FtnScene** out) {
         const FtnMaterial& fm = d->materials[m];
         MaterialData& md = mats[m];
         md.type = fm.type;
-        if (fm.type < FTN_MATERIAL_MATTE || fm.type > FTN_MATERIAL_MIRROR) return bail(set_error(FTN_ERR_INVALID_ARGUMENT, "unknown material type"));
+        if (fm.type < FTN_MATERIAL_MATTE || fm.type > FTN_MATERIAL_GLASS) return bail(set_error(FTN_ERR_INVALID_ARGUMENT, "unknown material type"));
         for (int c = 0; c < 3; ++c) { md.kd[c] = fm.kd[c]; md.ks[c] = fm.ks[c]; md.eta[c] = fm.eta[c]; md.k[c] = fm.k[c]; }
         float ur = fm.u_roughness, vr = fm.v_roughness;
         if (fm.type == FTN_MATERIAL_MIRROR) for (int c = 0; c < 3; ++c) md.kd[c] = fm.kr[c];   // Kr travels in the kd slot
+        if (fm.type == FTN_MATERIAL_GLASS) for (int c = 0; c < 3; ++c) { md.kd[c] = fm.kr[c]; md.ks[c] = fm.kt[c]; }   // Kr, Kt; eta[0] = index
         md.kd_texture = (fm.type == FTN_MATERIAL_MATTE || fm.type == FTN_MATERIAL_PLASTIC || fm.type == FTN_MATERIAL_MIRROR) ? fm.kd_texture : 0;
         if (fm.type == FTN_MATERIAL_MATTE) {   // matte.rs:42-49: sigma clamped to [0, 90] degrees; != 0 -> OrenNayar::new (reflection/mod.rs:259-267)
             const float sigma = std::fmin(std::fmax(fm.sigma, 0.0f), 90.0f);
@@ -600,6 +601,8 @@ int scene_create(const FtnSceneDesc* d, FtnScene** out) {
         if (fm.type == FTN_MATERIAL_PLASTIC) vr = ur;
         if (fm.remap_roughness) { ur = roughness_to_alpha_host(ur); vr = roughness_to_alpha_host(vr); }
         if (md.type != FTN_CLASS_OREN_NAYAR) { md.alpha_x = ur; md.alpha_y = vr; }   // Oren-Nayar keeps (a, b) there
+        if (fm.type == FTN_MATERIAL_GLASS && ur == 0.0f && vr == 0.0f)   // glass.rs:64-67: FresnelSpecular is todo!() in the reference
+            return bail(set_error(FTN_ERR_UNSUPPORTED, "smooth glass (both alphas 0) is todo!() in the reference (glass.rs:66)"));
         s->material_present[md.type] = true;
     }
     for (uint32_t m = 0; m < d->n_meshes; ++m) if (d->meshes[m].material_id < 0 && d->meshes[m].n_tris) s->has_null_material = true;

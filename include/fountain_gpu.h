@@ -45,7 +45,7 @@ extern "C" {
 #define FTN_API __attribute__((visibility("default")))
 #endif
 
-#define FTN_ABI_VERSION 2u
+#define FTN_ABI_VERSION 3u
 #define FTN_MAX_QUERIES_IN_FLIGHT 64
 #define FTN_NO_HIT 0xFFFFFFFFu
 
@@ -103,7 +103,14 @@ typedef enum FtnMaterialType {
     FTN_MATERIAL_MATTE = 0,   /* material/matte.rs:36-52: Lambert for sigma == 0, Oren-Nayar otherwise */
     FTN_MATERIAL_METAL = 1,   /* material/metal.rs:38-65 */
     FTN_MATERIAL_PLASTIC = 2, /* material/plastic.rs:24-48 */
-    FTN_MATERIAL_MIRROR = 3   /* material/mirror.rs:21-30: SpecularReflection with FresnelNoOp */
+    FTN_MATERIAL_MIRROR = 3,  /* material/mirror.rs:21-30: SpecularReflection with FresnelNoOp */
+    /* material/glass.rs:52-96, ROUGH glass: MicrofacetReflection<TrowbridgeReitz, FresnelDielectric(1, eta)> (Kr) +
+     * MicrofacetTransmission<TrowbridgeReitz>(Kt, 1, eta, Radiance) (reflection/mod.rs:365-443).  With remap_roughness
+     * (the loader's default, constructors.rs:198-205) roughness 0 is remapped to a small non-zero alpha and is rough glass
+     * too; a glass whose alphas are exactly 0 is FresnelSpecular = `todo!()` under the reference's path integrator
+     * (glass.rs:66) and a two-branch recursion under its direct-lighting integrator: ftn_scene_create answers
+     * FTN_ERR_UNSUPPORTED for it. */
+    FTN_MATERIAL_GLASS = 4
 } FtnMaterialType;
 
 /* Texture of a spectrum parameter (src/texture): constant, the 2D checkerboard without anti-aliasing
@@ -135,12 +142,12 @@ typedef struct FtnMaterial {
     int32_t type;            /* FtnMaterialType */
     float kd[3];             /* matte Kd / plastic Kd */
     float ks[3];             /* plastic Ks */
-    float eta[3];            /* metal eta */
+    float eta[3];            /* metal eta; glass: eta[0] = index of refraction (constructors.rs:203, default 1.5) */
     float k[3];              /* metal k */
     float u_roughness;       /* metal uroughness / plastic+metal isotropic roughness */
     float v_roughness;
     int32_t remap_roughness; /* constructors.rs:227 default true */
-    float kr[3];             /* mirror Kr (constructors.rs:207-210 default 0.9) */
+    float kr[3];             /* mirror Kr (constructors.rs:207-210 default 0.9); glass Kr (default 1) */
     int32_t kd_texture;      /* FtnTextureType of Kd (matte, plastic) or of Kr (mirror) */
     float tex1[3], tex2[3];  /* checkerboard: the two constant sub-textures (constructors.rs:276-287) */
     float uv_scale[2];       /* UVMapping uscale, vscale (constructors.rs:251-252, default 1) */
@@ -154,6 +161,7 @@ typedef struct FtnMaterial {
     int32_t image_width, image_height;
     int32_t image_levels;    /* checked against the rule above */
     int32_t image_wrap;      /* FtnImageWrap */
+    float kt[3];             /* glass Kt (constructors.rs:200, default 1) */
 } FtnMaterial;
 
 /* shapes/sphere.rs:16-27 (+ the DiffuseAreaLight it may carry, light/diffuse.rs:24-41). */

@@ -570,6 +570,22 @@ struct MirrorMaterial : Material {       // material/mirror.rs; Kr default 0.9 (
     }
 };
 
+struct GlassMaterial : Material {        // material/glass.rs; defaults of constructors.rs:198-205
+    Spectrum kr{1.0f}, kt{1.0f};
+    float eta = 1.5f, u_roughness = 0.0f, v_roughness = 0.0f;
+    bool remap_roughness = true;         // roughness 0 then becomes a small alpha: rough glass (alphas of exactly 0 are todo!() in the reference)
+    GlassMaterial() {}
+    GlassMaterial(Spectrum kr_, Spectrum kt_, float eta_, float ur, float vr, bool remap = true)
+        : kr(kr_), kt(kt_), eta(eta_), u_roughness(ur), v_roughness(vr), remap_roughness(remap) {}
+    void fill(FtnMaterial& m) const override {
+        m.type = FTN_MATERIAL_GLASS;
+        m.kr[0] = kr.r; m.kr[1] = kr.g; m.kr[2] = kr.b;
+        m.kt[0] = kt.r; m.kt[1] = kt.g; m.kt[2] = kt.b;
+        m.eta[0] = m.eta[1] = m.eta[2] = eta;
+        m.u_roughness = u_roughness; m.v_roughness = v_roughness; m.remap_roughness = remap_roughness;
+    }
+};
+
 struct DiffuseAreaLight {                // light/diffuse.rs:24-41
     Spectrum emit;
     explicit DiffuseAreaLight(Spectrum l = Spectrum(1.0f)) : emit(l) {}

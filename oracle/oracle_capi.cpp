@@ -73,6 +73,12 @@ ORC_API int orc_scene_create(const FtnSceneDesc* d, OrcScene** out) {
         mm.eta = Spectrum(m.eta[0], m.eta[1], m.eta[2]); mm.k = Spectrum(m.k[0], m.k[1], m.k[2]);
         mm.u_rough = m.u_roughness; mm.v_rough = m.v_roughness; mm.remap = m.remap_roughness != 0;
         mm.kr = Spectrum(m.kr[0], m.kr[1], m.kr[2]); mm.sigma = m.sigma;
+        mm.kt = Spectrum(m.kt[0], m.kt[1], m.kt[2]);
+        if (m.type == FTN_MATERIAL_GLASS) {   // glass.rs:64-67: the specular branch is todo!() under the path integrator
+            Float ur = m.u_roughness, vr = m.v_roughness;
+            if (m.remap_roughness) { ur = roughness_to_alpha(ur); vr = roughness_to_alpha(vr); }
+            if (ur == 0.0f && vr == 0.0f) { delete os; return fail(FTN_ERR_UNSUPPORTED, "smooth glass is todo!() in the reference (glass.rs:66)"); }
+        }
         mm.kd_texture = m.kd_texture; mm.tex1 = Spectrum(m.tex1[0], m.tex1[1], m.tex1[2]); mm.tex2 = Spectrum(m.tex2[0], m.tex2[1], m.tex2[2]);
         for (int c = 0; c < 2; ++c) { mm.uv_scale[c] = m.uv_scale[c]; mm.uv_delta[c] = m.uv_delta[c]; }
         if (m.kd_texture == FTN_TEXTURE_IMAGE && (m.type == FTN_MATERIAL_MATTE || m.type == FTN_MATERIAL_PLASTIC || m.type == FTN_MATERIAL_MIRROR)) {
@@ -394,6 +400,7 @@ ORC_API void orc_kat_bsdf(const FtnMaterial* m, const float wo[3], const float w
     mm.eta = Spectrum(m->eta[0], m->eta[1], m->eta[2]); mm.k = Spectrum(m->k[0], m->k[1], m->k[2]);
     mm.u_rough = m->u_roughness; mm.v_rough = m->v_roughness; mm.remap = m->remap_roughness != 0;
     mm.kr = Spectrum(m->kr[0], m->kr[1], m->kr[2]); mm.kd_texture = 0; mm.sigma = m->sigma;
+    mm.kt = Spectrum(m->kt[0], m->kt[1], m->kt[2]);
     SurfaceInteraction si{};
     si.hit.n = Vec3(0, 0, 1); si.shading_n = Vec3(0, 0, 1); si.shading_dpdu = Vec3(1, 0, 0); si.dpdu = Vec3(1, 0, 0);
     Bsdf b; compute_scattering_functions(mm, si, &b);

@@ -357,7 +357,7 @@ struct MIPMap {
 // ---- materials / lights tables ------------------------------------------------------------
 struct Material {
     int type;          // FtnMaterialType
-    Spectrum kd, ks, eta, k, kr;
+    Spectrum kd, ks, eta, k, kr, kt;
     int kd_texture;    // FtnTextureType
     Spectrum tex1, tex2; Float uv_scale[2], uv_delta[2];
     Float u_rough, v_rough, sigma;

@@ -173,7 +173,8 @@ struct ScatterSample { Spectrum f; Vec3 wi; Float pdf; int sampled_type; };
 // One lobe: Lambert (reflection/mod.rs:116-162) or Torrance-Sparrow with Trowbridge-Reitz
 // (reflection/mod.rs:301-361, microfacet.rs:119-186) and a conductor or dielectric Fresnel.
 struct BxDF {
-    int kind;            // 0 lambert, 1 microfacet, 2 specular reflection with FresnelNoOp (reflection/mod.rs:165-197), 3 Oren-Nayar (:252-296)
+    int kind;            // 0 lambert, 1 microfacet, 2 specular reflection with FresnelNoOp (reflection/mod.rs:165-197), 3 Oren-Nayar (:252-296),
+                         // 4 MicrofacetTransmission (:365-436; t in `r`, eta_a / eta_b in d_eta_i / d_eta_t, TransportMode::Radiance)
     Float on_a, on_b;    // Oren-Nayar coefficients
     Spectrum r;
     Float alpha_x, alpha_y;
@@ -181,7 +182,11 @@ struct BxDF {
     Spectrum eta_i, eta_t, k;
     Float d_eta_i, d_eta_t;
 
-    int get_type() const { return (kind == 0 || kind == 3) ? (BXDF_REFLECTION | BXDF_DIFFUSE) : kind == 1 ? (BXDF_REFLECTION | BXDF_GLOSSY) : (BXDF_REFLECTION | BXDF_SPECULAR); }
+    int get_type() const {
+        return (kind == 0 || kind == 3) ? (BXDF_REFLECTION | BXDF_DIFFUSE) : kind == 1 ? (BXDF_REFLECTION | BXDF_GLOSSY)
+             : kind == 4 ? (BXDF_TRANSMISSION | BXDF_GLOSSY) : (BXDF_REFLECTION | BXDF_SPECULAR);
+    }
+    Float mt_get_eta(Vec3 wo) const { return (cos_theta(wo) > 0.0f) ? d_eta_t / d_eta_i : d_eta_i / d_eta_t; }   // :376-378
     bool matches(int flags) const { return (flags & get_type()) == get_type(); }
 
     Spectrum fresnel_eval(Float cos_i) const {
@@ -226,6 +231,20 @@ struct BxDF {
     Spectrum f(Vec3 wo, Vec3 wi) const {
         if (kind == 0) return r * FRAC_1_PI;   // reflection/mod.rs:159-161
         if (kind == 2) return Spectrum(0.0f);   // :181-183
+        if (kind == 4) {   // MicrofacetTransmission::f, :386-404
+            if (same_hemisphere(wo, wi)) return Spectrum(0.0f);
+            Float cos_theta_o = cos_theta(wo), cos_theta_i = cos_theta(wi);
+            if (cos_theta_o == 0.0f || cos_theta_i == 0.0f) return Spectrum(0.0f);
+            Float eta = mt_get_eta(wo);
+            Vec3 wh = normalize(wo + wi * eta);
+            if (wh.z < 0.0f) wh = -wh;
+            Float F = fresnel_dielectric(dot(wo, wh), d_eta_i, d_eta_t);
+            Float sqrt_denom = dot(wo, wh) + eta * dot(wi, wh);
+            Float factor = 1.0f / eta;   // TransportMode::Radiance
+            return (Spectrum(1.0f) - Spectrum(F)) * r *
+                   std::fabs(tr_d(wh) * tr_g(wo, wi) * (eta * eta) * abs_dot(wi, wh) * abs_dot(wo, wh) * (factor * factor)
+                             / (cos_theta_i * cos_theta_o * (sqrt_denom * sqrt_denom)));
+        }
         if (kind == 3) {   // OrenNayar::f, reflection/mod.rs:274-296
             Float sin_theta_i = sin_theta(wi), sin_theta_o = sin_theta(wo);
             Float max_cos = 0.0f;
@@ -250,6 +269,14 @@ struct BxDF {
     Float pdf(Vec3 wo, Vec3 wi) const {
         if (kind == 0 || kind == 3) return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * FRAC_1_PI : 0.0f;   // DefaultSampleF :140-146
         if (kind == 2) return 0.0f;   // :194-196
+        if (kind == 4) {   // :426-435
+            if (same_hemisphere(wo, wi)) return 0.0f;
+            Float eta = mt_get_eta(wo);
+            Vec3 wh = normalize(wo + wi * eta);
+            Float sqrt_denom = dot(wo, wh) + eta * dot(wi, wh);
+            Float dwh_dwi = std::fabs(((eta * eta) * dot(wi, wh)) / (sqrt_denom * sqrt_denom));
+            return tr_pdf(wo, wh) * dwh_dwi;
+        }
         if (!same_hemisphere(wo, wi)) return 0.0f;   // :354-360
         Vec3 wh = normalize(wo + wi);
         return tr_pdf(wo, wh) / (4.0f * dot(wo, wh));
@@ -264,6 +291,21 @@ struct BxDF {
         if (kind == 2) {   // :185-192; FresnelNoOp::evaluate is Spectrum::uniform(1.0) (fresnel.rs)
             Vec3 wi(-wo.x, -wo.y, wo.z);
             s->pdf = 1.0f; s->f = Spectrum(1.0f) * r / abs_cos_theta(wi); s->wi = wi; s->sampled_type = get_type();
+            return true;
+        }
+        if (kind == 4) {   // :406-424
+            if (wo.z == 0.0f) return false;
+            Vec3 wh = tr_sample_wh(wo, u0, u1);
+            if (dot(wo, wh) < 0.0f) return false;
+            Float eta = mt_get_eta(-wo);   // "NOTE: this inverts the eta fraction"
+            // refract, reflection/mod.rs:70-78
+            Float cos_theta_i = dot(wh, wo);
+            Float sin2_theta_i = fmax_(0.0f, 1.0f - cos_theta_i * cos_theta_i);
+            Float sin2_theta_t = eta * eta * sin2_theta_i;
+            if (sin2_theta_t >= 1.0f) return false;
+            Float cos_theta_t = std::sqrt(1.0f - sin2_theta_t);
+            Vec3 wi = eta * -wo + (eta * cos_theta_i - cos_theta_t) * wh;
+            s->f = f(wo, wi); s->wi = wi; s->pdf = pdf(wo, wi); s->sampled_type = get_type();
             return true;
         }
         Vec3 wh = tr_sample_wh(wo, u0, u1);   // :338-352
@@ -379,6 +421,18 @@ inline void compute_scattering_functions(const Material& m, const SurfaceInterac
         BxDF b{}; b.kind = 1; b.r = Spectrum(1.0f); b.alpha_x = ur; b.alpha_y = vr;
         b.fresnel = 0; b.eta_i = Spectrum(1.0f); b.eta_t = m.eta; b.k = m.k;
         bsdf->add(b);
+    } else if (m.type == 4) {   // glass.rs:52-96; the specular branch is todo!() (path) or a two-branch recursion (direct lighting): rejected at scene creation
+        Spectrum r = m.kr.clamp_positive(), t = m.kt.clamp_positive();
+        Float ur = m.u_rough, vr = m.v_rough;
+        if (m.remap) { ur = roughness_to_alpha(ur); vr = roughness_to_alpha(vr); }
+        if (!r.is_black()) {
+            BxDF b{}; b.kind = 1; b.r = r; b.alpha_x = ur; b.alpha_y = vr; b.fresnel = 1; b.d_eta_i = 1.0f; b.d_eta_t = m.eta.c[0];
+            bsdf->add(b);
+        }
+        if (!t.is_black()) {
+            BxDF b{}; b.kind = 4; b.r = t; b.alpha_x = ur; b.alpha_y = vr; b.d_eta_i = 1.0f; b.d_eta_t = m.eta.c[0];
+            bsdf->add(b);
+        }
     } else if (m.type == 3) {   // mirror.rs:21-30
         Spectrum r = evaluate_kd(m, si).clamp_positive();
         if (!r.is_black()) { BxDF b{}; b.kind = 2; b.r = r; bsdf->add(b); }

@@ -70,6 +70,7 @@ SIM_API int sim_scene_create(const FtnSceneDesc* d, SimScene** out) {
         for (int c = 0; c < 3; ++c) { md.kd[c] = fm.kd[c]; md.ks[c] = fm.ks[c]; md.eta[c] = fm.eta[c]; md.k[c] = fm.k[c]; }
         float ur = fm.u_roughness, vr = fm.v_roughness;
         if (fm.type == FTN_MATERIAL_MIRROR) for (int c = 0; c < 3; ++c) md.kd[c] = fm.kr[c];   // Kr travels in the kd slot
+        if (fm.type == FTN_MATERIAL_GLASS) for (int c = 0; c < 3; ++c) { md.kd[c] = fm.kr[c]; md.ks[c] = fm.kt[c]; }
         md.kd_texture = (fm.type == FTN_MATERIAL_MATTE || fm.type == FTN_MATERIAL_PLASTIC || fm.type == FTN_MATERIAL_MIRROR) ? fm.kd_texture : 0;
         if (fm.type == FTN_MATERIAL_MATTE) {   // matte.rs:42-49: sigma clamped to [0, 90] degrees; != 0 -> OrenNayar::new (reflection/mod.rs:259-267)
             const float sigma = std::fmin(std::fmax(fm.sigma, 0.0f), 90.0f);
@@ -91,6 +92,7 @@ SIM_API int sim_scene_create(const FtnSceneDesc* d, SimScene** out) {
         if (fm.type == FTN_MATERIAL_PLASTIC) vr = ur;
         if (fm.remap_roughness) { ur = roughness_to_alpha_host(ur); vr = roughness_to_alpha_host(vr); }
         if (md.type != FTN_CLASS_OREN_NAYAR) { md.alpha_x = ur; md.alpha_y = vr; }   // Oren-Nayar keeps (a, b) there
+        if (fm.type == FTN_MATERIAL_GLASS && ur == 0.0f && vr == 0.0f) { delete s; g_err = "smooth glass is todo!() in the reference (glass.rs:66)"; return FTN_ERR_UNSUPPORTED; }
         s->mats.push_back(md);
     }
     s->env_tex.reserve(d->n_lights); s->env_f.reserve(5 * d->n_lights);
@@ -411,6 +413,7 @@ SIM_API int sim_render(const SimScene* s, const FtnCamera* cam, const FtnFilm* f
                     case FTN_MATERIAL_METAL: shade_surface<FTN_MATERIAL_METAL>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err); break;
                     case FTN_MATERIAL_PLASTIC: shade_surface<FTN_MATERIAL_PLASTIC>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err); break;
                     case FTN_MATERIAL_MIRROR: shade_surface<FTN_MATERIAL_MIRROR>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err); break;
+                    case FTN_MATERIAL_GLASS: shade_surface<FTN_MATERIAL_GLASS>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err); break;
                     case FTN_CLASS_OREN_NAYAR: shade_surface<FTN_CLASS_OREN_NAYAR>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err); break;
                     default: shade_surface<-1>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err); break;
                 }
@@ -473,7 +476,7 @@ SIM_API void sim_kat_offset_ray_origin(const float p[3], const float e[3], const
 }
 SIM_API void sim_kat_bsdf(const FtnMaterial* m, const float wo[3], const float wi[3], const float u[2], float out[12]) {
     FtnSceneDesc d; std::memset(&d, 0, sizeof(d)); d.abi_version = FTN_ABI_VERSION; d.materials = m; d.n_materials = 1;
-    SimScene* s; sim_scene_create(&d, &s);
+    SimScene* s; if (sim_scene_create(&d, &s) != FTN_OK) { for (int k = 0; k < 12; ++k) out[k] = 0.0f; return; }
     Bsdf b; bsdf_init(&b, V3(0, 0, 1), V3(0, 0, 1), V3(1, 0, 0));
     const V3 o(wo[0], wo[1], wo[2]), i(wi[0], wi[1], wi[2]);
     V3 f; float pdf; ScatterSample sm; bool ok;
@@ -482,6 +485,7 @@ SIM_API void sim_kat_bsdf(const FtnMaterial* m, const float wo[3], const float w
     else if (m->type == FTN_MATERIAL_MATTE) SIM_BSDF(FTN_MATERIAL_MATTE)
     else if (m->type == FTN_MATERIAL_METAL) SIM_BSDF(FTN_MATERIAL_METAL)
     else if (m->type == FTN_MATERIAL_MIRROR) SIM_BSDF(FTN_MATERIAL_MIRROR)
+    else if (m->type == FTN_MATERIAL_GLASS) SIM_BSDF(FTN_MATERIAL_GLASS)
     else SIM_BSDF(FTN_MATERIAL_PLASTIC)
 #undef SIM_BSDF
     out[0] = f.x; out[1] = f.y; out[2] = f.z; out[3] = pdf;

@@ -347,3 +347,24 @@ def test_two_quad_lights_statistical_parity(gpu_backend, orc_backend):
     b2, _, _ = parity.render(orc_backend, scenes.quad_light_scene, integ, 256, seed=2, **kw)
     assert abs(a.mean() - b.mean()) < 0.02 * b.mean(), (a.mean(), b.mean())
     assert parity.rel_mse(a, b) <= 1.5 * parity.rel_mse(b2, b), (parity.rel_mse(a, b), parity.rel_mse(b2, b))
+
+
+# ---- rough glass: MicrofacetReflection<FresnelDielectric(1, eta)> + MicrofacetTransmission (glass.rs:52-96, reflection/mod.rs:365-436) ----
+@pytest.mark.parametrize("integrator,roughness,remap", [("path", 0.25, True), ("path", 0.0, True), ("direct", 0.1, False)])
+def test_rough_glass_image_matches_oracle(gpu_backend, orc_backend, integrator, roughness, remap):
+    integ = api.PathIntegrator(6, 1.0) if integrator == "path" else api.DirectLightingIntegrator(3)
+    kw = dict(resolution=(40, 40), roughness=roughness, remap=remap)
+    a, apx, ast = parity.render(gpu_backend, scenes.rough_glass_scene, integ, 4, seed=7, **kw)
+    b, bpx, bst = parity.render(orc_backend, scenes.rough_glass_scene, integ, 4, seed=7, **kw)
+    mean_rel, frac_off = parity.image_diff(a, b)
+    assert mean_rel < 3e-3 and frac_off < 0.03, (mean_rel, frac_off)
+    assert np.array_equal(apx[..., 3], bpx[..., 3])
+    assert abs(ast["rays_closest"] - bst["rays_closest"]) <= 0.002 * bst["rays_closest"]
+    assert b.max() > 0.1
+
+
+def test_smooth_glass_is_rejected(gpu_backend):
+    """Alphas of exactly 0 = FresnelSpecular, `todo!()` in the reference (glass.rs:66): refused at scene creation."""
+    with pytest.raises(api.FountainError) as e:
+        scenes.rough_glass_scene(backend=gpu_backend, roughness=0.0, remap=False)
+    assert e.value.code == A.FTN_ERR_UNSUPPORTED

@@ -227,12 +227,18 @@ def _material(kind):
     elif kind == "metal_aniso":
         m.type = A.FTN_MATERIAL_METAL; m.eta[:] = [0.2, 0.92, 1.1]; m.k[:] = [3.9, 2.45, 2.14]
         m.u_roughness, m.v_roughness, m.remap_roughness = 0.2, 0.05, 0
+    elif kind == "glass":          # rough glass: MicrofacetReflection(FresnelDielectric(1, eta)) + MicrofacetTransmission
+        m.type = A.FTN_MATERIAL_GLASS; m.kr[:] = [0.9, 0.8, 1.0]; m.kt[:] = [0.7, 1.0, 0.9]; m.eta[:] = [1.5] * 3
+        m.u_roughness = m.v_roughness = 0.3; m.remap_roughness = 1
+    elif kind == "glass_aniso":
+        m.type = A.FTN_MATERIAL_GLASS; m.kr[:] = [1.0] * 3; m.kt[:] = [1.0] * 3; m.eta[:] = [1.33] * 3
+        m.u_roughness, m.v_roughness, m.remap_roughness = 0.25, 0.1, 0
     else:
         m.type = A.FTN_MATERIAL_PLASTIC; m.kd[:] = [0.25] * 3; m.ks[:] = [0.25] * 3; m.u_roughness = m.v_roughness = 0.1; m.remap_roughness = 1
     return m
 
 
-@pytest.mark.parametrize("kind", ["matte", "metal", "metal_aniso", "plastic"])
+@pytest.mark.parametrize("kind", ["matte", "metal", "metal_aniso", "plastic", "glass", "glass_aniso"])
 def test_bsdf_matches_oracle(sim, oracle, kind):
     m = _material(kind)
     rng = np.random.default_rng(5)
@@ -243,6 +249,8 @@ def test_bsdf_matches_oracle(sim, oracle, kind):
         wi = rng.normal(0, 1, 3); wi /= np.linalg.norm(wi)
         if rng.random() < 0.5 and kind != "matte":      # near the specular direction, where the lobe is
             wi = np.array([-wo[0], -wo[1], wo[2]]) + rng.normal(0, 0.02, 3); wi /= np.linalg.norm(wi)
+        if kind.startswith("glass") and rng.random() < 0.5:      # through the surface, around the refracted direction
+            wi = -wo + rng.normal(0, 0.3, 3); wi /= np.linalg.norm(wi)
         u = rng.random(2)
         oa, ob = (A.f32 * 12)(), (A.f32 * 12)()
         sim.library().sim_kat_bsdf(C.byref(m), A3(*wo), A3(*wi), A2(*u), oa)

@@ -408,3 +408,26 @@ def quad_light_probe(backend=None, side=1.0, height=2.0, emit=5.0, kd=0.5, resol
     s_ = float(np.sqrt(a * a + height * height))
     expected = kd / np.pi * 4.0 * emit * (a / s_) * np.arctan(a / s_)
     return scene, camera, film, expected
+
+
+# ---- rough glass (material/glass.rs: MicrofacetReflection + MicrofacetTransmission) ----------------------
+def rough_glass_scene(backend=None, resolution=(48, 48), roughness=0.25, remap=True, eta=1.5):
+    """A rough-glass pane (two quads, front and back face, 0.3 apart) standing in front of a checkerboard floor and a red
+    wall, lit by a uniform environment and a point light behind the pane: paths refract in, scatter inside, refract out."""
+    def quad(p0, p1, p2, p3):
+        v = np.array([p0, p1, p2, p3], np.float32)
+        return api.TriangleMesh(Transform.identity(), np.array([0, 1, 2, 0, 2, 3], np.uint32), v, tex_coords=np.array([[0, 0], [1, 0], [1, 1], [0, 1]], np.float32))
+    glass = api.GlassMaterial(kr=(1.0, 0.95, 0.9), kt=(0.9, 1.0, 0.95), eta=eta, u_roughness=roughness, v_roughness=roughness, remap_roughness=remap)
+    floor = api.MatteMaterial(api.Checkerboard2DTexture((0.7, 0.7, 0.7), (0.15, 0.15, 0.4), api.UVMapping(1.0, 1.0, 0.0, 0.0)))
+    fv = np.array([(-6, -8, -1), (6, -8, -1), (6, 6, -1), (-6, 6, -1)], np.float32)
+    fmesh = api.TriangleMesh(Transform.identity(), np.array([0, 1, 2, 0, 2, 3], np.uint32), fv, tex_coords=fv[:, :2].copy())
+    prims = [api.GeometricPrimitive(quad((-2, 0.0, -1), (2, 0.0, -1), (2, 0.0, 2.5), (-2, 0.0, 2.5)), glass),       # front face (normal -y)
+             api.GeometricPrimitive(quad((2, 0.3, -1), (-2, 0.3, -1), (-2, 0.3, 2.5), (2, 0.3, 2.5)), glass),       # back face (normal +y)
+             api.GeometricPrimitive(fmesh, floor),
+             api.GeometricPrimitive(quad((-6, 6, -1), (6, 6, -1), (6, 6, 5), (-6, 6, 5)), api.MatteMaterial((0.6, 0.1, 0.1)))]
+    lights = [api.InfiniteAreaLight.new_uniform(0.4), api.PointLight.from_params(I=60.0, from_=(1.0, 3.0, 3.0))]
+    scene = api.Scene(prims, lights, backend=backend)
+    cam_to_world = Transform.look_at((0.5, -7, 1.5), (0, 0.5, 0.6), (0, 0, 1)).inverse()
+    camera = api.PerspectiveCamera(cam_to_world, resolution, fov=45.0)
+    film = api.Film(resolution, backend=backend)
+    return scene, camera, film
