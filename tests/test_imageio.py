@@ -134,3 +134,51 @@ def test_image_texture_from_file_is_cached_and_flipped(tmp_path):
     want = (imageio.inverse_gamma_correct(a.astype(np.float32) / np.float32(255.0)) * np.float32(1.5))[::-1]
     assert np.array_equal(t1.mipmap.levels[0], want)
     assert len(t1.mipmap.levels) == 4 and t1.mipmap.wrap == api.MIPMap.WRAP["clamp"]
+
+
+# ---- the C++ host's decoders (include/fountain_imageio.hpp) against the Python host's ---------------------------------
+def _cpp_dump(tmp_path, path, *texel_args):
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-s", "-C", os.path.join(root, "tests", "cpp"), "imageio_dump"], check=True)
+    out = str(tmp_path / "dump.bin")
+    p = subprocess.run([os.path.join(root, "tests", "cpp", "imageio_dump"), path, out, *[str(a) for a in texel_args]], capture_output=True, text=True)
+    if p.returncode != 0:
+        return p.returncode, p.stderr
+    raw = open(out, "rb").read()
+    w, h = struct.unpack_from("<ii", raw, 0)
+    return 0, np.frombuffer(raw, dtype="<f4", offset=8).reshape(h, w, 3)
+
+
+@pytest.mark.parametrize("compression,half", [("none", False), ("zips", True), ("zip", False), ("zip", True)])
+def test_cpp_host_reads_exr(tmp_path, compression, half):
+    img = _img(37, 21, 4)
+    p = str(tmp_path / "a.exr")
+    imageio.write_exr(p, img, compression, half)
+    rc, got = _cpp_dump(tmp_path, p)
+    assert rc == 0, got
+    assert np.array_equal(got, imageio.read_exr(p))
+
+
+def test_cpp_host_reads_png_pfm_and_applies_gamma_scale_flip(tmp_path):
+    from PIL import Image
+    a = np.random.default_rng(8).integers(0, 256, (11, 7, 4), dtype=np.uint8)
+    png = str(tmp_path / "t.png")
+    Image.fromarray(a, "RGBA").save(png)
+    rc, got = _cpp_dump(tmp_path, png)
+    assert rc == 0, got
+    assert np.array_equal(got, imageio.load_image(png))
+    rc, got = _cpp_dump(tmp_path, png, 2.0, -1, 1)
+    want = imageio.load_texels(imageio.ImageTexInfo(png, "repeat", 2.0, None, True))
+    assert rc == 0 and np.allclose(got, want, rtol=2e-6, atol=0)           # powf: libm vs numpy, an ulp apart at most
+    img = _img(5, 8, 9)
+    pfm = str(tmp_path / "a.pfm")
+    with open(pfm, "wb") as f:
+        f.write(b"PF\n8 5\n-1.0\n" + img[::-1].astype("<f4").tobytes())
+    rc, got = _cpp_dump(tmp_path, pfm)
+    assert rc == 0 and np.array_equal(got, img)
+    grey = str(tmp_path / "g.png")
+    Image.fromarray(a[..., 0], "L").save(grey)
+    rc, err = _cpp_dump(tmp_path, grey)
+    assert rc == 1 and "8-bit RGB / RGBA" in err
