@@ -34,7 +34,22 @@
 
 namespace ftn {
 
+// FTN_BVH8_PLANES16 = 1 (A/B build, measured SLOWER, kept like the BVH4 experiment of round 1): the child planes as 16-bit
+// bf16 INTEGERS (0..255, exact) instead of bytes, two children per word -- 128-byte records (4 x LDG.256).  Idea: ncu on the
+// byte layout shows the node test bound by the ALU pipe (69 % busy, FMA pipe 28 %): per child 6 PRMT byte->float conversions
+// + 4 min/max + compare + add on the ALU pipe against 6 FFMA.  A bf16 in the LOW half of a word becomes a float with one
+// shift (IMAD.SHL: FMA pipe); one in the HIGH half is used as it is -- the low half then adds < 1 quantisation step, which is
+// conservative for hi planes, and lo planes of odd children are stored one step lower at build time.  SASS: PRMT 57 -> 0,
+// IMAD 108 -> 114, registers 72 -> 80 (6 blocks / SM instead of 7).  B200 (profiles/r02_ab_bvh8.txt): coherent +3.5 %,
+// incoherent diffuse +0 %, interior -5 %, C4 k_extend -5.5 %: the larger records and the lost block cost what the ALU pipe gains.
+#ifndef FTN_BVH8_PLANES16
+#define FTN_BVH8_PLANES16 0
+#endif
+#if FTN_BVH8_PLANES16
+#define FTN_NODE8_F4 8
+#else
 #define FTN_NODE8_F4 6
+#endif
 #define FTN_NODE8_BYTES (16 * FTN_NODE8_F4)
 #define FTN_LEAF8_MAX 3            /* triangles per leaf child (2-bit count) */
 #define FTN_STACK8_SHARED 8        /* traversal stack entries per lane kept in shared memory */
@@ -98,6 +113,60 @@ struct Node8Hits {
         if (!(tn > tf)) hits |= 1u << (k);                                                                          \
     }
 
+#if FTN_BVH8_PLANES16
+#define FTN_BOX16_ERR_B (20.0f * FTN_MACHINE_EPS)
+#define FTN_BOX16_ERR_A (20.0f * 256.0f * FTN_MACHINE_EPS)
+#if defined(__CUDA_ARCH__)
+// word << 16 as a multiply: ptxas turns it into IMAD.SHL on the FMA pipe (a plain shift goes to the saturated ALU pipe)
+FTN_HD float bf16_lo(uint32_t w) { uint32_t r; asm("mul.lo.u32 %0, %1, 65536;" : "=r"(r) : "r"(w)); return __uint_as_float(r); }
+#else
+FTN_HD float bf16_lo(uint32_t w) { return u2f(w << 16); }
+#endif
+FTN_HD float bf16_hi(uint32_t w) { return u2f(w); }       // + the low half as mantissa garbage: < 1 unit above the stored integer
+// children 2j (low halves) and 2j + 1 (high halves) of word j of each selected plane vector
+#define FTN_BOX16_PAIR(j, NX, NY, NZ, FX, FY, FZ)                                                                   \
+    {                                                                                                               \
+        const float tnx0 = fmaf(bf16_lo(NX), ax, onx), tfx0 = fmaf(bf16_lo(FX), ax, ofx);                           \
+        const float tny0 = fmaf(bf16_lo(NY), ay, ony), tfy0 = fmaf(bf16_lo(FY), ay, ofy);                           \
+        const float tnz0 = fmaf(bf16_lo(NZ), az, onz), tfz0 = fmaf(bf16_lo(FZ), az, ofz);                           \
+        const float tnx1 = fmaf(bf16_hi(NX), ax, onx), tfx1 = fmaf(bf16_hi(FX), ax, ofx);                           \
+        const float tny1 = fmaf(bf16_hi(NY), ay, ony), tfy1 = fmaf(bf16_hi(FY), ay, ofy);                           \
+        const float tnz1 = fmaf(bf16_hi(NZ), az, onz), tfz1 = fmaf(bf16_hi(FZ), az, ofz);                           \
+        const float tn0 = fmaxf(fmaxf(tnx0, tny0), fmaxf(tnz0, 0.0f)), tf0 = fminf(fminf(tfx0, tfy0), fminf(tfz0, t_max)); \
+        const float tn1 = fmaxf(fmaxf(tnx1, tny1), fmaxf(tnz1, 0.0f)), tf1 = fminf(fminf(tfx1, tfy1), fminf(tfz1, t_max)); \
+        if (!(tn0 > tf0)) hits |= 1u << (2 * (j));                                                                  \
+        if (!(tn1 > tf1)) hits |= 1u << (2 * (j) + 1);                                                              \
+    }
+FTN_HD Node8Hits node8_test(const F4* nodes, uint32_t idx, const Ray8& r, float t_max) {
+    const F4* nd = nodes + (size_t)FTN_NODE8_F4 * (size_t)idx;
+    F4 w0, w1, lx, ly, lz, hx, hy, hz;
+    ld8(nd, w0, w1); ld8(nd + 2, lx, ly); ld8(nd + 4, lz, hx); ld8(nd + 6, hy, hz);
+    const uint32_t eb = f2u(w0.w);
+    // t = q * a + b with a = 2^e / d (exact: a power of two times 1/d), b = (p - o) / d, q the stored integer
+    const float ax = rn_mul(u2f((eb & 0xFFu) << 23), r.idir.x);
+    const float ay = rn_mul(u2f(((eb >> 8) & 0xFFu) << 23), r.idir.y);
+    const float az = rn_mul(u2f(((eb >> 16) & 0xFFu) << 23), r.idir.z);
+    const float bx = rn_mul(rn_sub(w0.x, r.o.x), r.idir.x), by = rn_mul(rn_sub(w0.y, r.o.y), r.idir.y), bz = rn_mul(rn_sub(w0.z, r.o.z), r.idir.z);
+    const float ex = fmaf(FTN_BOX16_ERR_B, fabsf(bx), FTN_BOX16_ERR_A * fabsf(ax));
+    const float ey = fmaf(FTN_BOX16_ERR_B, fabsf(by), FTN_BOX16_ERR_A * fabsf(ay));
+    const float ez = fmaf(FTN_BOX16_ERR_B, fabsf(bz), FTN_BOX16_ERR_A * fabsf(az));
+    const float onx = rn_sub(bx, ex), ofx = rn_add(bx, ex), ony = rn_sub(by, ey), ofy = rn_add(by, ey), onz = rn_sub(bz, ez), ofz = rn_add(bz, ez);
+    const bool px = !(r.idir.x < 0.0f), py = !(r.idir.y < 0.0f), pz = !(r.idir.z < 0.0f);
+    uint32_t hits = 0u;
+#define FTN_SEL(p, a, b) ((p) ? f2u(a) : f2u(b))
+    FTN_BOX16_PAIR(0, FTN_SEL(px, lx.x, hx.x), FTN_SEL(py, ly.x, hy.x), FTN_SEL(pz, lz.x, hz.x), FTN_SEL(px, hx.x, lx.x), FTN_SEL(py, hy.x, ly.x), FTN_SEL(pz, hz.x, lz.x))
+    FTN_BOX16_PAIR(1, FTN_SEL(px, lx.y, hx.y), FTN_SEL(py, ly.y, hy.y), FTN_SEL(pz, lz.y, hz.y), FTN_SEL(px, hx.y, lx.y), FTN_SEL(py, hy.y, ly.y), FTN_SEL(pz, hz.y, lz.y))
+    FTN_BOX16_PAIR(2, FTN_SEL(px, lx.z, hx.z), FTN_SEL(py, ly.z, hy.z), FTN_SEL(pz, lz.z, hz.z), FTN_SEL(px, hx.z, lx.z), FTN_SEL(py, hy.z, ly.z), FTN_SEL(pz, hz.z, lz.z))
+    FTN_BOX16_PAIR(3, FTN_SEL(px, lx.w, hx.w), FTN_SEL(py, ly.w, hy.w), FTN_SEL(pz, lz.w, hz.w), FTN_SEL(px, hx.w, lx.w), FTN_SEL(py, hy.w, ly.w), FTN_SEL(pz, hz.w, lz.w))
+#undef FTN_SEL
+    const uint32_t imask = eb >> 24, meta = f2u(w1.z), lmask = (meta >> 16) & 0xFFu;
+    const uint32_t m = bvh8_permute_hits((hits & imask) | ((hits & lmask) << 8), r.octinv);
+    Node8Hits h;
+    h.child_base = f2u(w1.x); h.ng_bits = (m & 0xFFu) | (imask << 8);
+    h.tri_base = f2u(w1.y);   h.tg_bits = (m >> 8) | (meta << 8);
+    return h;
+}
+#else
 // Tests the eight child boxes of node `idx`; returns the hit children as the two groups the traversal carries.
 FTN_HD Node8Hits node8_test(const F4* nodes, uint32_t idx, const Ray8& r, float t_max) {
     const F4* nd = nodes + (size_t)FTN_NODE8_F4 * (size_t)idx;
@@ -138,6 +207,7 @@ FTN_HD Node8Hits node8_test(const F4* nodes, uint32_t idx, const Ray8& r, float 
     h.tri_base = f2u(w1.y);   h.tg_bits = (m >> 8) | (meta << 8);            // counts16 = meta & 0xFFFF lands in bits 8..23; lmask above it (unused)
     return h;
 }
+#endif
 
 // Next interior child of a node group (its highest-priority hit bit), removed from the group.
 FTN_HD uint32_t node8_pop_child(uint32_t base, uint32_t& bits, uint32_t octinv) {

@@ -106,10 +106,25 @@ FTN_HD void bvh8_collapse_node(const LbvhArrays& a, const F4* leaf_lo, const F4*
     // quantisation frame
     const double px = box_lo.x, py = box_lo.y, pz = box_lo.z;
     const uint32_t Ex = bvh8_exponent((double)box_hi.x - px), Ey = bvh8_exponent((double)box_hi.y - py), Ez = bvh8_exponent((double)box_hi.z - pz);
+#if FTN_BVH8_PLANES16
+    uint32_t q[6][4] = {{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}};   // lo.x lo.y lo.z hi.x hi.y hi.z, four words of two bf16
+#else
     uint32_t q[6][2] = {{0u, 0u}, {0u, 0u}, {0u, 0u}, {0u, 0u}, {0u, 0u}, {0u, 0u}};   // lo.x lo.y lo.z hi.x hi.y hi.z, two words of four bytes
+#endif
     uint32_t ci = 0u, ti = 0u;
     for (int s = 0; s < 8; ++s) {
         const int i = child_in_slot[s];
+#if FTN_BVH8_PLANES16
+        const int wsel = s >> 1, sh = 16 * (s & 1);
+        // the integer as bf16 (exact up to 255); a lo plane in a HIGH half reads up to one unit too large, so it is stored one lower
+        #define FTN_Q16(v) (f2u((float)(v)) >> 16)
+        if (i < 0) { q[0][wsel] |= FTN_Q16(255u) << sh; q[1][wsel] |= FTN_Q16(255u) << sh; q[2][wsel] |= FTN_Q16(255u) << sh; continue; }
+        uint32_t qlx = bvh8_quant_lo(lo[i].x, px, Ex), qly = bvh8_quant_lo(lo[i].y, py, Ey), qlz = bvh8_quant_lo(lo[i].z, pz, Ez);
+        if (s & 1) { qlx = qlx ? qlx - 1u : 0u; qly = qly ? qly - 1u : 0u; qlz = qlz ? qlz - 1u : 0u; }
+        q[0][wsel] |= FTN_Q16(qlx) << sh; q[1][wsel] |= FTN_Q16(qly) << sh; q[2][wsel] |= FTN_Q16(qlz) << sh;
+        q[3][wsel] |= FTN_Q16(bvh8_quant_hi(hi[i].x, px, Ex)) << sh; q[4][wsel] |= FTN_Q16(bvh8_quant_hi(hi[i].y, py, Ey)) << sh; q[5][wsel] |= FTN_Q16(bvh8_quant_hi(hi[i].z, pz, Ez)) << sh;
+        #undef FTN_Q16
+#else
         const int wsel = s >> 2, sh = 8 * (s & 3);
         if (i < 0) {   // empty slot: inverted box (also masked out by imask | lmask)
             q[0][wsel] |= 255u << sh; q[1][wsel] |= 255u << sh; q[2][wsel] |= 255u << sh;
@@ -117,6 +132,7 @@ FTN_HD void bvh8_collapse_node(const LbvhArrays& a, const F4* leaf_lo, const F4*
         }
         q[0][wsel] |= bvh8_quant_lo(lo[i].x, px, Ex) << sh; q[1][wsel] |= bvh8_quant_lo(lo[i].y, py, Ey) << sh; q[2][wsel] |= bvh8_quant_lo(lo[i].z, pz, Ez) << sh;
         q[3][wsel] |= bvh8_quant_hi(hi[i].x, px, Ex) << sh; q[4][wsel] |= bvh8_quant_hi(hi[i].y, py, Ey) << sh; q[5][wsel] |= bvh8_quant_hi(hi[i].z, pz, Ez) << sh;
+#endif
         if (imask & (1u << s)) { brefs[child_base + ci] = ref[i]; ++ci; }
         else {
             const uint32_t f = single_count != 0u ? 0u : bvh8_ref_first(a, ref[i]);
@@ -128,10 +144,14 @@ FTN_HD void bvh8_collapse_node(const LbvhArrays& a, const F4* leaf_lo, const F4*
     F4 v;
     v.x = box_lo.x; v.y = box_lo.y; v.z = box_lo.z; v.w = u2f(Ex | (Ey << 8) | (Ez << 16) | (imask << 24)); out[0] = v;
     v.x = u2f(child_base); v.y = u2f(tri_base); v.z = u2f(counts16 | (lmask << 16)); v.w = 0.0f; out[1] = v;
+#if FTN_BVH8_PLANES16
+    for (int pl = 0; pl < 6; ++pl) { v.x = u2f(q[pl][0]); v.y = u2f(q[pl][1]); v.z = u2f(q[pl][2]); v.w = u2f(q[pl][3]); out[2 + pl] = v; }
+#else
     v.x = u2f(q[0][0]); v.y = u2f(q[0][1]); v.z = u2f(q[1][0]); v.w = u2f(q[1][1]); out[2] = v;
     v.x = u2f(q[2][0]); v.y = u2f(q[2][1]); v.z = u2f(q[3][0]); v.w = u2f(q[3][1]); out[3] = v;
     v.x = u2f(q[4][0]); v.y = u2f(q[4][1]); v.z = u2f(q[5][0]); v.w = u2f(q[5][1]); out[4] = v;
     v.x = v.y = v.z = v.w = 0.0f; out[5] = v;
+#endif
 }
 
 // upper bound of the number of wide nodes for n triangles (every all-leaf node holds >= 4 triangles, every other node
