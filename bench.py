@@ -133,26 +133,42 @@ def ncu_record(workload, kernel):
     return json.load(open(p)).get(workload, {}).get(kernel)
 
 
-def hierarchy_roofline(workload, kernel, bytes_per_launch, avg_launch_s, sm_mhz, extra):
-    """The memory-hierarchy roofline of a traversal kernel from ALGORITHMIC bytes (node + triangle + ray/hit bytes its
-    rays request) and the live CUDA-event launch time.  The bytes are requested from L1; what misses goes to L2, what
-    misses there to HBM -- so the same figure is an upper bound on the traffic of each level.  ncu says which level
-    binds (profiles/): every scene measured is bound by the SM's L1 data pipe + issue slots, DRAM <= 15 % of peak, so
-    the stated roof is the L1 data pipe; the L2 and HBM figures stand beside it."""
+def hierarchy_roofline(workload, kernel, bytes_per_launch, avg_launch_s, sm_mhz, extra, rays_per_launch=None):
+    """Roofline of a traversal kernel from the live CUDA-event launch time.
+
+    Which roof: ncu (profiles/, one record per workload and kernel in profiles/traffic.json, stamped with the commit it was
+    taken on) says the BVH8q kernels are bound by the SM's instruction issue -- the ALU pipe inside it -- and the BVH2x64
+    kernels by the L1 data pipe; no scene measured is HBM-bound (DRAM <= 15 % of peak).  So when a record with the
+    kernel's warp instructions per ray exists, `achieved` = those instructions x the rays one launch traces / the measured
+    launch time, against the issue peak (SMs x 4 schedulers x SM clock sampled under load).  Without a record the L1
+    data pipe stands in: ALGORITHMIC bytes (node + triangle + ray / hit bytes the rays request) per launch time against
+    SMs x 128 B/clk.  The L1, L2 and HBM figures of the same bytes always stand beside the stated roof; `traffic` is the DRAM
+    traffic ncu measured for this workload (None when there is no record -- never another workload's)."""
     peak_hbm, peak_src = measured_peak()
     clk = (sm_mhz or 1965.0) * 1e6
-    achieved = bytes_per_launch / max(avg_launch_s, 1e-12) / 1e9
+    achieved_b = bytes_per_launch / max(avg_launch_s, 1e-12) / 1e9
     l1_peak = SM_COUNT * L1_BYTES_PER_CLK * clk / 1e9
     l2_peak = L2_BYTES_PER_CLK * clk / 1e9
     rec = ncu_record(workload, kernel)
-    out = {"bound": "l1", "kernel": kernel, "achieved": achieved, "peak": l1_peak, "unit": "GB/s", "frac": achieved / l1_peak,
-           "peak_source": "L1 data pipe: %d SMs x %d B/clk x %.0f MHz (SM clock sampled under load)" % (SM_COUNT, L1_BYTES_PER_CLK, clk / 1e6),
-           "traffic": rec.get("dram_bytes_per_launch") if rec else None,
-           "l2": {"peak": l2_peak, "frac": achieved / l2_peak, "peak_source": "LTS cap %d B/clk x SM clock (B300_MICROARCH)" % L2_BYTES_PER_CLK},
-           "hbm": {"peak": peak_hbm, "frac_if_all_bytes_came_from_hbm": achieved / peak_hbm, "peak_source": peak_src,
-                   "note": "algorithmic bytes / HBM peak; > 1 only says the working set is cache-resident -- the measured DRAM traffic is `traffic`"},
-           "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_launch_s * 1e3,
-           "ncu": rec}
+    mem = {"l1": {"achieved": achieved_b, "peak": l1_peak, "frac": achieved_b / l1_peak, "unit": "GB/s",
+                  "peak_source": "L1 data pipe: %d SMs x %d B/clk x %.0f MHz" % (SM_COUNT, L1_BYTES_PER_CLK, clk / 1e6)},
+           "l2": {"peak": l2_peak, "frac": achieved_b / l2_peak, "peak_source": "LTS cap %d B/clk x SM clock (B300_MICROARCH)" % L2_BYTES_PER_CLK},
+           "hbm": {"peak": peak_hbm, "frac_if_all_bytes_came_from_hbm": achieved_b / peak_hbm, "peak_source": peak_src,
+                   "note": "algorithmic bytes / HBM peak; > 1 only says the working set is cache-resident -- the measured DRAM traffic is `traffic`"}}
+    if rec and rec.get("warp_inst_per_ray") and rays_per_launch:
+        issue_peak = SM_COUNT * 4 * clk / 1e9
+        achieved = rec["warp_inst_per_ray"] * rays_per_launch / max(avg_launch_s, 1e-12) / 1e9
+        out = {"bound": rec.get("bound", "sm-issue"), "kernel": kernel, "achieved": achieved, "peak": issue_peak, "unit": "Gwarp-inst/s",
+               "frac": achieved / issue_peak,
+               "peak_source": "instruction issue: %d SMs x 4 schedulers x %.0f MHz (SM clock sampled under load); warp instructions per ray from ncu (%s)"
+                              % (SM_COUNT, clk / 1e6, rec.get("source")),
+               "traffic": rec["dram_bytes_per_ray"] * rays_per_launch if rec.get("dram_bytes_per_ray") is not None else None}
+    else:
+        out = {"bound": "l1", "kernel": kernel, "achieved": achieved_b, "peak": l1_peak, "unit": "GB/s", "frac": achieved_b / l1_peak,
+               "peak_source": mem["l1"]["peak_source"] + " (SM clock sampled under load)",
+               "traffic": rec["dram_bytes_per_ray"] * rays_per_launch if (rec and rays_per_launch and rec.get("dram_bytes_per_ray") is not None) else None}
+    out.update(mem)
+    out.update({"algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_launch_s * 1e3, "rays_per_launch": rays_per_launch, "ncu": rec})
     out.update(extra)
     return out
 
@@ -375,7 +391,9 @@ def measure_render(D, name, args, steps, warmup, with_e2e=True, with_counts=True
             "kernel_mrays_per_s": trays[k] / max(tsec[k], 1e-12) / 1e6,
             "shadow_mrays_per_s": trays[1] / max(tsec[1], 1e-12) / 1e6, "mis_mrays_per_s": trays[2] / max(tsec[2], 1e-12) / 1e6,
             "shade_avg_launch_ms": shade_s / max(1, shade_l) * 1e3,
-            "working_set_mb": (cst.bvh_nodes * node_b + scene.n_triangles * tri_b) / 1e6})
+            "kernel_rays_per_step": [trays[0] // steps, trays[1] // steps, trays[2] // steps],
+            "working_set_mb": (cst.bvh_nodes * node_b + scene.n_triangles * tri_b) / 1e6},
+            rays_per_launch=trays[k] / max(1, tl[k]))
 
     # ---- e2e: host buffers in, host film out; scene upload + BVH build + render + read-back per step ----
     if with_e2e:
@@ -550,8 +568,10 @@ def measure_raybatch(D, args, steps, warmup, with_e2e=True, with_baseline=True, 
     out = {"scene": scene, "batches": results, "clocks": clock_info, "build": build, "n_inc": len(inc), "bvh_nodes": scene.stats()["bvh_nodes"]}
     sm_mhz = clock_info["sm_mhz"] if clock_info else None
     for label, r in results.items():
-        rl = hierarchy_roofline("c3", "k_intersect_batch:" + label, r["algorithmic_bytes"], r["ms_median"] * 1e-3, sm_mhz, {})
-        r["achieved_gbs"] = rl["achieved"]; r["frac_of_l1_peak"] = rl["frac"]; r["frac_of_l2_peak"] = rl["l2"]["frac"]
+        rl = hierarchy_roofline("c3", "k_intersect_batch:" + label, r["algorithmic_bytes"], r["ms_median"] * 1e-3, sm_mhz, {}, rays_per_launch=r["rays"])
+        r["achieved_gbs"] = rl["l1"]["achieved"]; r["frac_of_l1_peak"] = rl["l1"]["frac"]; r["frac_of_l2_peak"] = rl["l2"]["frac"]
+        if rl["unit"] != "GB/s":
+            r["issue_frac"] = rl["frac"]
         r["dram_traffic_bytes"] = rl["traffic"]
         if label == "incoherent_diffuse":
             out["roofline"] = rl
@@ -591,7 +611,8 @@ def measure_raybatch(D, args, steps, warmup, with_e2e=True, with_baseline=True, 
     return out
 
 
-BVH_NOTE = ("30-bit Morton codes + stable radix sort; topology: PLOC (>= 65536 tris) or Karras radix tree; see DESIGN.md section 3 for the node layout")
+BVH_NOTE = ("30-bit Morton codes + stable radix sort; topology: PLOC (>= 65536 tris) or Karras radix tree; records: BVH8q compressed 8-wide "
+            "(>= 65536 tris) or BVH2x64; see DESIGN.md section 3")
 
 
 def run_ours(args):

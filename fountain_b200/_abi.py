@@ -53,7 +53,16 @@ class FtnMaterial(C.Structure):
                 ("u_roughness", f32), ("v_roughness", f32), ("remap_roughness", i32), ("kr", f32 * 3),
                 ("kd_texture", i32), ("tex1", f32 * 3), ("tex2", f32 * 3), ("uv_scale", f32 * 2), ("uv_delta", f32 * 2), ("sigma", f32),
                 ("image", C.POINTER(f32)), ("image_width", i32), ("image_height", i32), ("image_levels", i32), ("image_wrap", i32),
-                ("kt", f32 * 3)]
+                ("kt", f32 * 3), ("param_texture", u32 * 10)]
+
+
+class FtnTexture(C.Structure):
+    _fields_ = [("type", i32), ("value", f32 * 3), ("tex1", f32 * 3), ("tex2", f32 * 3), ("uv_scale", f32 * 2), ("uv_delta", f32 * 2),
+                ("image", C.POINTER(f32)), ("image_width", i32), ("image_height", i32), ("image_levels", i32), ("image_wrap", i32)]
+
+
+(FTN_PARAM_KD, FTN_PARAM_KS, FTN_PARAM_ETA, FTN_PARAM_K, FTN_PARAM_KR, FTN_PARAM_KT, FTN_PARAM_UROUGHNESS, FTN_PARAM_VROUGHNESS,
+ FTN_PARAM_SIGMA, FTN_PARAM_INDEX, FTN_PARAM_COUNT) = range(11)
 
 
 class FtnSphere(C.Structure):
@@ -74,7 +83,8 @@ class FtnSceneDesc(C.Structure):
                 ("n_triangles", u32), ("meshes", C.POINTER(FtnMeshDesc)), ("n_meshes", u32),
                 ("spheres", C.POINTER(FtnSphere)), ("n_spheres", u32),
                 ("materials", C.POINTER(FtnMaterial)), ("n_materials", u32),
-                ("lights", C.POINTER(FtnLight)), ("n_lights", u32)]
+                ("lights", C.POINTER(FtnLight)), ("n_lights", u32),
+                ("textures", C.POINTER(FtnTexture)), ("n_textures", u32)]
 
 
 class FtnCamera(C.Structure):

@@ -231,8 +231,79 @@ class ImageTexture:
 _TEXTURES = (Checkerboard2DTexture, UVTexture, ImageTexture)
 
 
-def _fill_kd(m, kd):
-    """Kd is a constant spectrum or one of the textures above."""
+class ConstantTexture:
+    """texture/mod.rs:34-42 as an entry of the texture table."""
+    type = A.FTN_TEXTURE_CONSTANT
+
+    def __init__(self, value):
+        self.value = _spectrum(value)
+        self.tex1 = self.tex2 = _spectrum(0.0)
+        self.mapping = UVMapping()
+
+
+class InTable:
+    """Marks a Kd / Kr texture to travel through the scene's texture table (FtnMaterial::param_texture) instead of the
+    material's inline slot; every other parameter's texture always goes through the table."""
+
+    def __init__(self, texture):
+        self.texture = texture
+
+
+_TABLE_TEXTURES = (Checkerboard2DTexture, UVTexture, ImageTexture, ConstantTexture)
+
+
+class TextureTable:
+    """FtnSceneDesc::textures under construction: add() returns the 1-based id FtnMaterial::param_texture carries."""
+
+    def __init__(self):
+        self.entries, self._ids = [], {}
+
+    def add(self, tex):
+        if id(tex) in self._ids:
+            return self._ids[id(tex)]
+        t = A.FtnTexture()
+        t.type = tex.type
+        t.value[:] = getattr(tex, "value", _spectrum(0.0)).tolist()
+        t.tex1[:] = tex.tex1.tolist(); t.tex2[:] = tex.tex2.tolist()
+        t.uv_scale[:] = list(tex.mapping.scale); t.uv_delta[:] = list(tex.mapping.offset)
+        if isinstance(tex, ImageTexture):
+            mp = tex.mipmap
+            t.image = mp.packed.ctypes.data_as(C.POINTER(C.c_float))
+            t.image_width, t.image_height, t.image_levels, t.image_wrap = mp.width, mp.height, len(mp.levels), mp.wrap
+        self.entries.append((t, tex))        # the texture object (and its pyramid) stays alive with the table
+        self._ids[id(tex)] = len(self.entries)
+        return len(self.entries)
+
+    def c_array(self):
+        arr = (A.FtnTexture * max(1, len(self.entries)))()
+        for i, (t, _) in enumerate(self.entries):
+            arr[i] = t
+        return arr
+
+
+def _param(m, table, param, value, set_constant):
+    """One material parameter (loaders/constructors.rs get_texture_or_default): a texture goes into the table, anything
+    else into the constant field."""
+    if isinstance(value, InTable):
+        value = value.texture
+    if isinstance(value, _TABLE_TEXTURES):
+        if table is None:
+            raise ValueError("a textured material parameter needs the scene's texture table")
+        m.param_texture[param] = table.add(value)
+    else:
+        set_constant(value)
+
+
+def _tex_or(value, convert):
+    return value if isinstance(value, _TABLE_TEXTURES + (InTable,)) else convert(value)
+
+
+def _fill_kd(m, kd, table=None, param=A.FTN_PARAM_KD):
+    """Kd is a constant spectrum or one of the textures above (inline slot), or InTable(texture)."""
+    if isinstance(kd, InTable):
+        _param(m, table, param, kd, None)
+        m.uv_scale[:] = [1.0, 1.0]
+        return
     if isinstance(kd, _TEXTURES):
         m.kd_texture = kd.type
         m.tex1[:] = kd.tex1.tolist(); m.tex2[:] = kd.tex2.tolist()
@@ -252,13 +323,13 @@ class MatteMaterial:
     type = A.FTN_MATERIAL_MATTE
 
     def __init__(self, kd=0.5, sigma=0.0):
-        self.kd = kd if isinstance(kd, _TEXTURES) else _spectrum(kd)
-        self.sigma = float(sigma)            # degrees; != 0 selects Oren-Nayar (matte.rs:42-49)
+        self.kd = kd if isinstance(kd, _TEXTURES + (InTable,)) else _spectrum(kd)
+        self.sigma = _tex_or(sigma, float)   # degrees; != 0 selects Oren-Nayar (matte.rs:42-49); a float texture is allowed
 
-    def fill(self, m):
+    def fill(self, m, table=None):
         m.type = self.type
-        _fill_kd(m, self.kd)
-        m.sigma = self.sigma
+        _fill_kd(m, self.kd, table)
+        _param(m, table, A.FTN_PARAM_SIGMA, self.sigma, lambda v: setattr(m, "sigma", v))
 
 
 class MetalMaterial:
@@ -267,19 +338,21 @@ class MetalMaterial:
     type = A.FTN_MATERIAL_METAL
 
     def __init__(self, eta, k, roughness=0.01, u_roughness=None, v_roughness=None, remap_roughness=True):
-        self.eta = _spectrum(eta)
-        self.k = _spectrum(k)
-        if u_roughness is not None and v_roughness is not None:
-            self.u, self.v = float(u_roughness), float(v_roughness)
+        self.eta = _tex_or(eta, _spectrum)
+        self.k = _tex_or(k, _spectrum)
+        if u_roughness is not None and v_roughness is not None:     # RoughnessTex::Anisotropic, constructors.rs:221-226
+            self.u, self.v = _tex_or(u_roughness, float), _tex_or(v_roughness, float)
         else:
-            self.u = self.v = float(roughness)
+            self.u = self.v = _tex_or(roughness, float)
         self.remap = bool(remap_roughness)
 
-    def fill(self, m):
+    def fill(self, m, table=None):
         m.type = self.type
-        m.eta[:] = self.eta.tolist()
-        m.k[:] = self.k.tolist()
-        m.u_roughness, m.v_roughness, m.remap_roughness = self.u, self.v, int(self.remap)
+        _param(m, table, A.FTN_PARAM_ETA, self.eta, lambda v: m.eta.__setitem__(slice(None), v.tolist()))
+        _param(m, table, A.FTN_PARAM_K, self.k, lambda v: m.k.__setitem__(slice(None), v.tolist()))
+        _param(m, table, A.FTN_PARAM_UROUGHNESS, self.u, lambda v: setattr(m, "u_roughness", v))
+        _param(m, table, A.FTN_PARAM_VROUGHNESS, self.v, lambda v: setattr(m, "v_roughness", v))
+        m.remap_roughness = int(self.remap)
 
 
 class PlasticMaterial:
@@ -287,15 +360,18 @@ class PlasticMaterial:
     type = A.FTN_MATERIAL_PLASTIC
 
     def __init__(self, kd=0.25, ks=0.25, roughness=0.1, remap_roughness=True):
-        self.kd = kd if isinstance(kd, _TEXTURES) else _spectrum(kd)
-        self.ks = _spectrum(ks)
-        self.roughness, self.remap = float(roughness), bool(remap_roughness)
+        self.kd = kd if isinstance(kd, _TEXTURES + (InTable,)) else _spectrum(kd)
+        self.ks = _tex_or(ks, _spectrum)
+        self.roughness, self.remap = _tex_or(roughness, float), bool(remap_roughness)
 
-    def fill(self, m):
+    def fill(self, m, table=None):
         m.type = self.type
-        _fill_kd(m, self.kd)
-        m.ks[:] = self.ks.tolist()
-        m.u_roughness = m.v_roughness = self.roughness
+        _fill_kd(m, self.kd, table)
+        _param(m, table, A.FTN_PARAM_KS, self.ks, lambda v: m.ks.__setitem__(slice(None), v.tolist()))
+
+        def rough(v):
+            m.u_roughness = m.v_roughness = v
+        _param(m, table, A.FTN_PARAM_UROUGHNESS, self.roughness, rough)
         m.remap_roughness = int(self.remap)
 
 
@@ -304,12 +380,12 @@ class MirrorMaterial:
     type = A.FTN_MATERIAL_MIRROR
 
     def __init__(self, kr=0.9):
-        self.kr = kr if isinstance(kr, _TEXTURES) else _spectrum(kr)     # Kr may be textured (mirror.rs:23)
+        self.kr = kr if isinstance(kr, _TEXTURES + (InTable,)) else _spectrum(kr)     # Kr may be textured (mirror.rs:23)
 
-    def fill(self, m):
+    def fill(self, m, table=None):
         m.type = self.type
-        if isinstance(self.kr, _TEXTURES):
-            _fill_kd(m, self.kr)             # the texture slot of the ABI serves Kd (matte, plastic) or Kr (mirror)
+        if isinstance(self.kr, _TEXTURES + (InTable,)):
+            _fill_kd(m, self.kr, table, A.FTN_PARAM_KR)   # the inline slot of the ABI serves Kd (matte, plastic) or Kr (mirror)
         else:
             m.kr[:] = self.kr.tolist()
 
@@ -321,15 +397,17 @@ class GlassMaterial:
     type = A.FTN_MATERIAL_GLASS
 
     def __init__(self, kr=1.0, kt=1.0, eta=1.5, u_roughness=0.0, v_roughness=0.0, remap_roughness=True):
-        self.kr, self.kt, self.eta = _spectrum(kr), _spectrum(kt), float(eta)
-        self.u_roughness, self.v_roughness, self.remap_roughness = float(u_roughness), float(v_roughness), bool(remap_roughness)
+        self.kr, self.kt, self.eta = _tex_or(kr, _spectrum), _tex_or(kt, _spectrum), _tex_or(eta, float)
+        self.u_roughness, self.v_roughness, self.remap_roughness = _tex_or(u_roughness, float), _tex_or(v_roughness, float), bool(remap_roughness)
 
-    def fill(self, m):
+    def fill(self, m, table=None):
         m.type = self.type
-        m.kr[:] = self.kr.tolist()
-        m.kt[:] = self.kt.tolist()
-        m.eta[:] = [self.eta] * 3
-        m.u_roughness, m.v_roughness, m.remap_roughness = self.u_roughness, self.v_roughness, int(self.remap_roughness)
+        _param(m, table, A.FTN_PARAM_KR, self.kr, lambda v: m.kr.__setitem__(slice(None), v.tolist()))
+        _param(m, table, A.FTN_PARAM_KT, self.kt, lambda v: m.kt.__setitem__(slice(None), v.tolist()))
+        _param(m, table, A.FTN_PARAM_INDEX, self.eta, lambda v: m.eta.__setitem__(slice(None), [v] * 3))
+        _param(m, table, A.FTN_PARAM_UROUGHNESS, self.u_roughness, lambda v: setattr(m, "u_roughness", v))
+        _param(m, table, A.FTN_PARAM_VROUGHNESS, self.v_roughness, lambda v: setattr(m, "v_roughness", v))
+        m.remap_roughness = int(self.remap_roughness)
 
 
 class DiffuseAreaLight:
@@ -490,8 +568,10 @@ class Scene:
             if p.light is not None:
                 cs.emit[:] = p.light.emit.tolist()
         c_mats = (A.FtnMaterial * max(1, len(materials)))()
+        self._textures = TextureTable()
         for i, m in enumerate(materials):
-            m.fill(c_mats[i])
+            m.fill(c_mats[i], self._textures)
+        c_texs = self._textures.c_array()
         self._light_texels = []
         c_lights = (A.FtnLight * max(1, len(lights)))()
         for i, l in enumerate(lights):
@@ -530,6 +610,7 @@ class Scene:
         d.spheres, d.n_spheres = c_spheres, len(spheres)
         d.materials, d.n_materials = c_mats, len(materials)
         d.lights, d.n_lights = c_lights, len(lights)
+        d.textures, d.n_textures = c_texs, len(self._textures.entries)
         self.backend.call("scene_create", C.byref(d), C.byref(self._handle))
         self.upload_bytes = int(self._positions.nbytes + self._indices.nbytes
                                 + (self._normals.nbytes if self._normals is not None else 0)

@@ -254,10 +254,12 @@ FTN_HD void shade_surface(const SceneView& sc, const PassParams& pp, uint32_t pa
     Bsdf bsdf;
     bsdf_init(&bsdf, s.ns, s.n, s.sdpdu);
     TexDiffs td; td.dudx = td.dvdx = td.dudy = td.dvdy = 0.0f;
-    if (IMG && (M == FTN_MATERIAL_MATTE || M == FTN_MATERIAL_PLASTIC || M == FTN_CLASS_OREN_NAYAR || M == FTN_MATERIAL_MIRROR) && sc.materials[s.material].kd_texture == FTN_TEXTURE_IMAGE
+    if (IMG && sc.materials[s.material].uses_image
         && !(direct_only && bounces > 0))   // stated deviation: no differentials behind a mirror under direct lighting
         td = path_tex_differentials(sc, pp, path, slot, ray, s.p, s.n);
-    material_bsdf<M>(sc.materials[s.material], s.u, s.v, td, &bsdf);
+    bool unsupported = false;
+    material_bsdf<M, IMG>(sc, sc.materials[s.material], s.u, s.v, td, &bsdf, &unsupported);
+    if (unsupported) { flag_error(err, ERR_UNSUPPORTED); return; }
     const uint64_t key = path_sample_key(pp, path, nullptr, nullptr);
     // under the direct-lighting integrator `bounces` is the recursion depth of specular_reflect
     const uint32_t dim0 = DIM_CAMERA + (uint32_t)DIM_PER_BOUNCE * (uint32_t)bounces;

@@ -76,12 +76,25 @@ struct MaterialData {
     // level l is max(1, w >> l) x max(1, h >> l)
     const F4* image;
     int32_t img_w, img_h, img_levels, img_wrap;
+    // the texture table (FtnMaterial::param_texture): per FtnMaterialParam 0 = the constant above, k = SceneView::textures[k - 1];
+    // the raw roughnesses / sigma / remap flag are kept for parameters that are evaluated per hit
+    uint32_t ptex[FTN_PARAM_COUNT];
+    float u_rough, v_rough, sigma;
+    int32_t remap;
+    int32_t uses_image;      // any of its textures is an image: the hit needs texture differentials
+};
+// one entry of the texture table; the field names of the image part match MaterialData's inline slot (shared mip code)
+struct TextureData {
+    int32_t type;            // FtnTextureType
+    float v[3], tex1[3], tex2[3], uv_scale[2], uv_delta[2];
+    const F4* image;
+    int32_t img_w, img_h, img_levels, img_wrap;
 };
 
 // FtnMaterial's pyramid (RGB f32, include/fountain_gpu.h) -> RGBA texels; false when the description breaks the
 // level rule of mipmap.rs:107-121.  Host-side, shared by scene.cu and the host harness of the tests.
-template <class Vec>
-inline bool pack_image_pyramid(const FtnMaterial& fm, Vec* out) {
+template <class Vec, class Desc>
+inline bool pack_image_pyramid(const Desc& fm, Vec* out) {
     if (!fm.image || fm.image_width < 1 || fm.image_height < 1 || fm.image_wrap < FTN_WRAP_REPEAT || fm.image_wrap > FTN_WRAP_CLAMP) return false;
     int expect = 1;
     for (int m = fm.image_width > fm.image_height ? fm.image_width : fm.image_height; m > 1; m >>= 1) ++expect;
@@ -126,6 +139,37 @@ struct LightData {
     EnvLightData env;
 };
 
+// Host side, shared by scene.cu and the host harness of the tests: the per-parameter texture ids, raw roughnesses and the
+// class of a matte whose sigma is textured.  `tex_is_image(k)` tells whether table entry k (1-based) is an image texture.
+template <class IsImage>
+inline int material_params_from_abi(const FtnMaterial& fm, uint32_t n_textures, IsImage tex_is_image, MaterialData* md) {
+    md->uses_image = md->kd_texture == FTN_TEXTURE_IMAGE ? 1 : 0;
+    for (int p = 0; p < FTN_PARAM_COUNT; ++p) {
+        const uint32_t id = fm.param_texture[p];
+        if (id > n_textures) return FTN_ERR_INVALID_ARGUMENT;
+        md->ptex[p] = id;
+        if (id && tex_is_image(id)) md->uses_image = 1;
+    }
+    md->u_rough = fm.u_roughness; md->v_rough = fm.type == FTN_MATERIAL_PLASTIC ? fm.u_roughness : fm.v_roughness;
+    if (fm.type == FTN_MATERIAL_PLASTIC) md->ptex[FTN_PARAM_VROUGHNESS] = md->ptex[FTN_PARAM_UROUGHNESS];
+    md->sigma = fm.sigma; md->remap = fm.remap_roughness ? 1 : 0;
+    if (fm.type == FTN_MATERIAL_MATTE && md->ptex[FTN_PARAM_SIGMA]) md->type = FTN_CLASS_OREN_NAYAR;   // sigma decided per hit (0 => a = 1, b = 0 = Lambert)
+    return FTN_OK;
+}
+template <class Vec>
+inline int texture_from_abi(const FtnTexture& ft, TextureData* td, Vec* texels) {
+    if (ft.type < FTN_TEXTURE_CONSTANT || ft.type > FTN_TEXTURE_IMAGE) return FTN_ERR_INVALID_ARGUMENT;
+    std::memset(td, 0, sizeof(*td));
+    td->type = ft.type;
+    for (int c = 0; c < 3; ++c) { td->v[c] = ft.value[c]; td->tex1[c] = ft.tex1[c]; td->tex2[c] = ft.tex2[c]; }
+    for (int c = 0; c < 2; ++c) { td->uv_scale[c] = ft.uv_scale[c]; td->uv_delta[c] = ft.uv_delta[c]; }
+    if (ft.type == FTN_TEXTURE_IMAGE) {
+        if (!pack_image_pyramid(ft, texels)) return FTN_ERR_INVALID_ARGUMENT;
+        td->img_w = ft.image_width; td->img_h = ft.image_height; td->img_levels = ft.image_levels; td->img_wrap = ft.image_wrap;
+    }
+    return FTN_OK;
+}
+
 #define FTN_LIGHT_TYPE_TRIANGLE 4
 // Fills MeshData (incl. light_base) and appends the per-triangle area lights of emissive meshes to `lights`, which must
 // hold exactly the explicit lights (scene/mod.rs:32-49: explicit lights, then the primitives' area lights -- here in
@@ -156,6 +200,7 @@ struct SceneView {
     const uint32_t* idx;
     const MeshData* meshes;
     const MaterialData* materials;
+    const TextureData* textures;     // the scene's texture table (may be null)
     const SphereData* spheres; uint32_t n_spheres;
     const LightData* lights; uint32_t n_lights;
     uint32_t n_tris;
@@ -172,6 +217,7 @@ struct FtnScene {
     float* d_pos = nullptr; float* d_nrm = nullptr; float* d_uv = nullptr; uint32_t* d_idx = nullptr;
     ftn::MeshData* d_meshes = nullptr;
     ftn::MaterialData* d_materials = nullptr;
+    ftn::TextureData* d_textures = nullptr;
     ftn::SphereData* d_spheres = nullptr;
     ftn::LightData* d_lights = nullptr;
     std::vector<ftn::SphereData> h_spheres;

@@ -500,7 +500,7 @@ struct TexDiffs { float dudx, dvdx, dudy, dvdy; };
 FTN_HD int max_i(int a, int b) { return a > b ? a : b; }
 FTN_HD int min_i(int a, int b) { return a < b ? a : b; }
 struct MipLevel { const F4* texels; int w, h; };
-FTN_HD MipLevel mip_level(const MaterialData& m, int level) {
+template <class TEX> FTN_HD MipLevel mip_level(const TEX& m, int level) {
     size_t off = 0;
     for (int l = 0; l < level; ++l) off += (size_t)max_i(1, m.img_w >> l) * (size_t)max_i(1, m.img_h >> l);
     MipLevel lv; lv.texels = m.image + off; lv.w = max_i(1, m.img_w >> level); lv.h = max_i(1, m.img_h >> level);
@@ -515,7 +515,7 @@ FTN_HD V3 mip_texel(const MipLevel& lv, int wrap, int s, int t) {
     return V3(v.x, v.y, v.z);
 }
 // triangle, mipmap.rs:265-279: the four texels around the continuous coordinate
-FTN_HD V3 mip_triangle(const MaterialData& m, int level, float st0, float st1) {
+template <class TEX> FTN_HD V3 mip_triangle(const TEX& m, int level, float st0, float st1) {
     const MipLevel lv = mip_level(m, min_i(max_i(level, 0), m.img_levels - 1));
     const float s = st0 * (float)lv.w - 0.5f, t = st1 * (float)lv.h - 0.5f;
     const float fs = floorf(s), ft = floorf(t);
@@ -525,7 +525,7 @@ FTN_HD V3 mip_triangle(const MaterialData& m, int level, float st0, float st1) {
          + mip_texel(lv, m.img_wrap, s0 + 1, t0) * (ds * (1.0f - dt)) + mip_texel(lv, m.img_wrap, s0 + 1, t0 + 1) * (ds * dt);
 }
 // lookup_trilinear + lookup_trilinear_width, mipmap.rs:245-262 (`dst0.y` without abs(), as there)
-FTN_HD_COLD V3 mip_lookup_trilinear(const MaterialData& m, float st0, float st1, float dsdx, float dtdx, float dsdy, float dtdy) {
+template <class TEX> FTN_HD_COLD V3 mip_lookup_trilinear(const TEX& m, float st0, float st1, float dsdx, float dtdx, float dsdy, float dtdy) {
     const float width = 2.0f * fmaxf(fmaxf(fabsf(dsdx), dtdx), fmaxf(fabsf(dsdy), fabsf(dtdy)));
     const float level = (float)m.img_levels - 1.0f + log2f(fmaxf(width, 1.0e-8f));
     if (level < 0.0f) return mip_triangle(m, 0, st0, st1);
@@ -545,32 +545,86 @@ FTN_HD V3 material_kd(const MaterialData& m, float u, float v, const TexDiffs& t
         return mip_lookup_trilinear(m, s, t, m.uv_scale[0] * td.dudx, m.uv_scale[1] * td.dvdx, m.uv_scale[0] * td.dudy, m.uv_scale[1] * td.dvdy);
     return V3(rn_sub(s, floorf(s)), rn_sub(t, floorf(t)), 0.0f);
 }
-template <int MAT> FTN_HD void material_bsdf(const MaterialData& m, float u, float v, const TexDiffs& td, Bsdf* b) {
+// A texture-table entry: the same four textures as the inline slot (texture/{mod,checkerboard,uv,image}.rs)
+template <bool IMG> FTN_HD V3 texture_eval(const TextureData& t, float u, float v, const TexDiffs& td) {
+    if (t.type == FTN_TEXTURE_CONSTANT) return V3(t.v[0], t.v[1], t.v[2]);
+    const float s = rn_add(rn_mul(t.uv_scale[0], u), t.uv_delta[0]), tt = rn_add(rn_mul(t.uv_scale[1], v), t.uv_delta[1]);
+    if (t.type == FTN_TEXTURE_CHECKERBOARD) return (((int)floorf(s) + (int)floorf(tt)) % 2 == 0) ? V3(t.tex1[0], t.tex1[1], t.tex1[2]) : V3(t.tex2[0], t.tex2[1], t.tex2[2]);
+    if (IMG && t.type == FTN_TEXTURE_IMAGE)    // the mip lookup is compiled only into the shaders of scenes that hold an image texture
+        return mip_lookup_trilinear(t, s, tt, t.uv_scale[0] * td.dudx, t.uv_scale[1] * td.dvdx, t.uv_scale[0] * td.dudy, t.uv_scale[1] * td.dvdy);
+    return V3(rn_sub(s, floorf(s)), rn_sub(tt, floorf(tt)), 0.0f);
+}
+// a material parameter: its texture-table entry when it names one, its constant otherwise (loaders/constructors.rs:192-238)
+template <bool IMG> FTN_HD V3 mat_spectrum(const SceneView& sc, const MaterialData& m, int P, V3 constant, float u, float v, const TexDiffs& td) {
+    const uint32_t id = m.ptex[P];
+    return id ? texture_eval<IMG>(sc.textures[id - 1u], u, v, td) : constant;
+}
+template <bool IMG> FTN_HD float mat_float(const SceneView& sc, const MaterialData& m, int P, float constant, float u, float v, const TexDiffs& td) {
+    const uint32_t id = m.ptex[P];
+    return id ? texture_eval<IMG>(sc.textures[id - 1u], u, v, td).x : constant;
+}
+// Kd (matte, plastic) / Kr (mirror): table entry, else the inline slot, else the constant
+template <bool IMG> FTN_HD V3 mat_kd(const SceneView& sc, const MaterialData& m, int P, float u, float v, const TexDiffs& td) {
+    const uint32_t id = m.ptex[P];
+    return id ? texture_eval<IMG>(sc.textures[id - 1u], u, v, td) : material_kd(m, u, v, td);
+}
+// TrowbridgeReitzDistribution::roughness_to_alpha, microfacet.rs:40-45 (per hit only when the roughness is textured)
+FTN_HD float roughness_to_alpha_dev(float roughness) {
+    const float x = logf(fmaxf(roughness, 1.0e-3f));
+    return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
+}
+// the lobe's alphas: the values remapped at scene creation, or the textured roughnesses evaluated (and remapped) at this hit
+template <bool IMG> FTN_HD void mat_alphas(const SceneView& sc, const MaterialData& m, float u, float v, const TexDiffs& td, float* ax, float* ay) {
+    *ax = m.alpha_x; *ay = m.alpha_y;
+    if (m.ptex[FTN_PARAM_UROUGHNESS] | m.ptex[FTN_PARAM_VROUGHNESS]) {
+        float ur = mat_float<IMG>(sc, m, FTN_PARAM_UROUGHNESS, m.u_rough, u, v, td), vr = mat_float<IMG>(sc, m, FTN_PARAM_VROUGHNESS, m.v_rough, u, v, td);
+        if (m.remap) { ur = roughness_to_alpha_dev(ur); vr = roughness_to_alpha_dev(vr); }
+        *ax = ur; *ay = vr;
+    }
+}
+FTN_HD V3 clamp_positive(V3 c) { return V3(clampf(c.x, 0.0f, FTN_INF), clampf(c.y, 0.0f, FTN_INF), clampf(c.z, 0.0f, FTN_INF)); }
+
+// `unsupported` is set where the reference would hit todo!() (a glass whose textured alphas are both 0 at this hit, glass.rs:64-67)
+template <int MAT, bool IMG> FTN_HD void material_bsdf(const SceneView& sc, const MaterialData& m, float u, float v, const TexDiffs& td, Bsdf* b, bool* unsupported) {
     if (MAT == FTN_MATERIAL_MATTE) {
-        const V3 kd0 = material_kd(m, u, v, td);
-        const V3 r = V3(clampf(kd0.x, 0.0f, FTN_INF), clampf(kd0.y, 0.0f, FTN_INF), clampf(kd0.z, 0.0f, FTN_INF));
+        const V3 r = clamp_positive(mat_kd<IMG>(sc, m, FTN_PARAM_KD, u, v, td));
         if (!is_black(r)) { b->on0 = true; b->l0.r = r; }
     } else if (MAT == FTN_MATERIAL_METAL) {
         b->on0 = true;
-        b->l0.r = v3s(1.0f); b->l0.ax = m.alpha_x; b->l0.ay = m.alpha_y;
-        b->l0.eta = V3(m.eta[0], m.eta[1], m.eta[2]); b->l0.k = V3(m.k[0], m.k[1], m.k[2]);
-    } else if (MAT == FTN_CLASS_OREN_NAYAR) {   // matte.rs:45-49: OrenNayar::new(r, Deg(sigma)); (a, b) precomputed at scene creation
-        const V3 kd0 = material_kd(m, u, v, td);
-        const V3 r = V3(clampf(kd0.x, 0.0f, FTN_INF), clampf(kd0.y, 0.0f, FTN_INF), clampf(kd0.z, 0.0f, FTN_INF));
-        if (!is_black(r)) { b->on0 = true; b->l0.r = r; b->l0.ax = m.alpha_x; b->l0.ay = m.alpha_y; }
-    } else if (MAT == FTN_MATERIAL_GLASS) {   // glass.rs:52-96, the non-specular branch (rough glass); alphas remapped at scene creation
-        const V3 r = V3(clampf(m.kd[0], 0.0f, FTN_INF), clampf(m.kd[1], 0.0f, FTN_INF), clampf(m.kd[2], 0.0f, FTN_INF));
-        const V3 t = V3(clampf(m.ks[0], 0.0f, FTN_INF), clampf(m.ks[1], 0.0f, FTN_INF), clampf(m.ks[2], 0.0f, FTN_INF));
-        if (!is_black(r)) { b->on0 = true; b->l0.r = r; b->l0.ax = m.alpha_x; b->l0.ay = m.alpha_y; b->l0.eta = v3s(m.eta[0]); b->l0.k = v3s(0.0f); }
-        if (!is_black(t)) { b->on1 = true; b->l1.r = t; b->l1.ax = m.alpha_x; b->l1.ay = m.alpha_y; b->l1.eta = v3s(m.eta[0]); b->l1.k = v3s(0.0f); }
+        b->l0.r = v3s(1.0f);
+        mat_alphas<IMG>(sc, m, u, v, td, &b->l0.ax, &b->l0.ay);
+        b->l0.eta = mat_spectrum<IMG>(sc, m, FTN_PARAM_ETA, V3(m.eta[0], m.eta[1], m.eta[2]), u, v, td);
+        b->l0.k = mat_spectrum<IMG>(sc, m, FTN_PARAM_K, V3(m.k[0], m.k[1], m.k[2]), u, v, td);
+    } else if (MAT == FTN_CLASS_OREN_NAYAR) {   // matte.rs:45-49: OrenNayar::new(r, Deg(sigma)); (a, b) precomputed at scene creation unless sigma is textured
+        const V3 r = clamp_positive(mat_kd<IMG>(sc, m, FTN_PARAM_KD, u, v, td));
+        if (!is_black(r)) {
+            b->on0 = true; b->l0.r = r; b->l0.ax = m.alpha_x; b->l0.ay = m.alpha_y;
+            if (m.ptex[FTN_PARAM_SIGMA]) {      // reflection/mod.rs:259-267; sigma == 0 gives a = 1, b = 0: Lambert's r / pi exactly
+                const float sigma = clampf(mat_float<IMG>(sc, m, FTN_PARAM_SIGMA, m.sigma, u, v, td), 0.0f, 90.0f);
+                const float sr = sigma * (float)(3.14159265358979323846 / 180.0), s2 = sr * sr;
+                b->l0.ax = (sigma == 0.0f) ? 1.0f : 1.0f - (s2 / (2.0f * (s2 + 0.33f)));
+                b->l0.ay = (sigma == 0.0f) ? 0.0f : 0.45f * s2 / (s2 + 0.09f);
+            }
+        }
+    } else if (MAT == FTN_MATERIAL_GLASS) {   // glass.rs:52-96, the non-specular branch (rough glass)
+        const V3 r = clamp_positive(mat_spectrum<IMG>(sc, m, FTN_PARAM_KR, V3(m.kd[0], m.kd[1], m.kd[2]), u, v, td));
+        const V3 t = clamp_positive(mat_spectrum<IMG>(sc, m, FTN_PARAM_KT, V3(m.ks[0], m.ks[1], m.ks[2]), u, v, td));
+        const float eta = mat_float<IMG>(sc, m, FTN_PARAM_INDEX, m.eta[0], u, v, td);
+        float ax, ay; mat_alphas<IMG>(sc, m, u, v, td, &ax, &ay);
+        if (ax == 0.0f && ay == 0.0f) { *unsupported = true; return; }
+        if (!is_black(r)) { b->on0 = true; b->l0.r = r; b->l0.ax = ax; b->l0.ay = ay; b->l0.eta = v3s(eta); b->l0.k = v3s(0.0f); }
+        if (!is_black(t)) { b->on1 = true; b->l1.r = t; b->l1.ax = ax; b->l1.ay = ay; b->l1.eta = v3s(eta); b->l1.k = v3s(0.0f); }
     } else if (MAT == FTN_MATERIAL_MIRROR) {   // mirror.rs:21-30; Kr (constant or textured) is carried in MaterialData::kd and its texture fields
-        const V3 kr0 = material_kd(m, u, v, td);
-        const V3 r = V3(clampf(kr0.x, 0.0f, FTN_INF), clampf(kr0.y, 0.0f, FTN_INF), clampf(kr0.z, 0.0f, FTN_INF));
+        const V3 r = clamp_positive(mat_kd<IMG>(sc, m, FTN_PARAM_KR, u, v, td));
         if (!is_black(r)) { b->on0 = true; b->l0.r = r; }
-    } else {
-        const V3 kd = material_kd(m, u, v, td), ks = V3(m.ks[0], m.ks[1], m.ks[2]);
+    } else {                                    // plastic.rs:24-48
+        const V3 kd = mat_kd<IMG>(sc, m, FTN_PARAM_KD, u, v, td), ks = mat_spectrum<IMG>(sc, m, FTN_PARAM_KS, V3(m.ks[0], m.ks[1], m.ks[2]), u, v, td);
         if (!is_black(kd)) { b->on0 = true; b->l0.r = kd; }
-        if (!is_black(ks)) { b->on1 = true; b->l1.r = ks; b->l1.ax = m.alpha_x; b->l1.ay = m.alpha_x; b->l1.eta = v3s(0.0f); b->l1.k = v3s(0.0f); }
+        if (!is_black(ks)) {
+            b->on1 = true; b->l1.r = ks; b->l1.eta = v3s(0.0f); b->l1.k = v3s(0.0f);
+            float ax, ay; mat_alphas<IMG>(sc, m, u, v, td, &ax, &ay);
+            b->l1.ax = ax; b->l1.ay = ax;
+        }
     }
 }
 

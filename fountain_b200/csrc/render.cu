@@ -460,7 +460,11 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
                 else k_shade<Q_MAT0><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT0], q, counts, d_err);
                 FTN_LAUNCHED();
             }
-            if (s->material_present[1]) { k_shade<Q_MAT1><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT1], q, counts, d_err); FTN_LAUNCHED(); }
+            if (s->material_present[1]) {
+                if (s->has_image_texture) k_shade<Q_MAT1, true><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT1], q, counts, d_err);
+                else k_shade<Q_MAT1><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT1], q, counts, d_err);
+                FTN_LAUNCHED();
+            }
             if (s->material_present[2]) {
                 if (s->has_image_texture) k_shade<Q_MAT2, true><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT2], q, counts, d_err);
                 else k_shade<Q_MAT2><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT2], q, counts, d_err);
@@ -471,7 +475,11 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
                 else k_shade<Q_MAT3><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT3], q, counts, d_err);
                 FTN_LAUNCHED();
             }
-            if (s->material_present[4]) { k_shade<Q_MAT4><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT4], q, counts, d_err); FTN_LAUNCHED(); }   // rough glass
+            if (s->material_present[4]) {   // rough glass
+                if (s->has_image_texture) k_shade<Q_MAT4, true><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT4], q, counts, d_err);
+                else k_shade<Q_MAT4><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT4], q, counts, d_err);
+                FTN_LAUNCHED();
+            }
             if (s->material_present[5]) {
                 if (s->has_image_texture) k_shade<Q_MAT5, true><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT5], q, counts, d_err);
                 else k_shade<Q_MAT5><<<shade_grid, 128, 0, st>>>(sc, pp, pa, q.q[Q_MAT5], q, counts, d_err);

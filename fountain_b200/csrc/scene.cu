@@ -443,7 +443,7 @@ SceneView make_view(const FtnScene& s) {
     SceneView v;
     v.bvh.nodes = s.d_nodes; v.bvh.tris = s.d_tris; v.bvh.n_nodes = s.n_nodes; v.bvh.n_tris = s.n_tris; v.bvh.wide = s.wide ? 1u : 0u;
     v.pos = s.d_pos; v.nrm = s.d_nrm; v.uv = s.d_uv; v.idx = s.d_idx;
-    v.meshes = s.d_meshes; v.materials = s.d_materials;
+    v.meshes = s.d_meshes; v.materials = s.d_materials; v.textures = s.d_textures;
     v.spheres = s.d_spheres; v.n_spheres = s.n_spheres;
     v.lights = s.d_lights; v.n_lights = (uint32_t)s.h_lights.size();
     v.n_tris = s.n_tris;
@@ -565,10 +565,25 @@ int scene_create(const FtnSceneDesc* d, FtnScene** out) {
     if (d->normals && (rc = upload(&s->d_nrm, d->normals, 3 * (size_t)d->n_vertices)) != FTN_OK) return bail(rc);
     if (d->uvs && (rc = upload(&s->d_uv, d->uvs, 2 * (size_t)d->n_vertices)) != FTN_OK) return bail(rc);
     if ((rc = upload(&s->d_idx, d->indices, 3 * (size_t)d->n_triangles)) != FTN_OK) return bail(rc);
+    // the texture table (FtnSceneDesc::textures): image pyramids are copied as RGBA texels
+    std::vector<TextureData> texs(d->n_textures);
+    if (d->n_textures && !d->textures) return bail(set_error(FTN_ERR_INVALID_ARGUMENT, "n_textures != 0 but textures is null"));
+    for (uint32_t t = 0; t < d->n_textures; ++t) {
+        std::vector<F4> texels;
+        if (texture_from_abi(d->textures[t], &texs[t], &texels) != FTN_OK) return bail(set_error(FTN_ERR_INVALID_ARGUMENT, "texture table: bad texture type or image pyramid"));
+        if (texs[t].type == FTN_TEXTURE_IMAGE) {
+            F4* d_img = nullptr;
+            if ((rc = upload(&d_img, texels.data(), texels.size())) != FTN_OK) return bail(rc);
+            s->owned.push_back(d_img);
+            texs[t].image = d_img;
+        }
+    }
+    if ((rc = upload(&s->d_textures, texs.data(), texs.size())) != FTN_OK) return bail(rc);
     std::vector<MaterialData> mats(d->n_materials);
     for (uint32_t m = 0; m < d->n_materials; ++m) {
         const FtnMaterial& fm = d->materials[m];
         MaterialData& md = mats[m];
+        std::memset(&md, 0, sizeof(md));
         md.type = fm.type;
         if (fm.type < FTN_MATERIAL_MATTE || fm.type > FTN_MATERIAL_GLASS) return bail(set_error(FTN_ERR_INVALID_ARGUMENT, "unknown material type"));
         for (int c = 0; c < 3; ++c) { md.kd[c] = fm.kd[c]; md.ks[c] = fm.ks[c]; md.eta[c] = fm.eta[c]; md.k[c] = fm.k[c]; }
@@ -601,7 +616,11 @@ int scene_create(const FtnSceneDesc* d, FtnScene** out) {
         if (fm.type == FTN_MATERIAL_PLASTIC) vr = ur;
         if (fm.remap_roughness) { ur = roughness_to_alpha_host(ur); vr = roughness_to_alpha_host(vr); }
         if (md.type != FTN_CLASS_OREN_NAYAR) { md.alpha_x = ur; md.alpha_y = vr; }   // Oren-Nayar keeps (a, b) there
-        if (fm.type == FTN_MATERIAL_GLASS && ur == 0.0f && vr == 0.0f)   // glass.rs:64-67: FresnelSpecular is todo!() in the reference
+        if (material_params_from_abi(fm, d->n_textures, [&](uint32_t id) { return texs[id - 1].type == FTN_TEXTURE_IMAGE; }, &md) != FTN_OK)
+            return bail(set_error(FTN_ERR_INVALID_ARGUMENT, "material: param_texture id out of range"));
+        if (md.uses_image) s->has_image_texture = true;
+        const bool rough_textured = md.ptex[FTN_PARAM_UROUGHNESS] || md.ptex[FTN_PARAM_VROUGHNESS];
+        if (fm.type == FTN_MATERIAL_GLASS && !rough_textured && ur == 0.0f && vr == 0.0f)   // glass.rs:64-67: FresnelSpecular is todo!() in the reference
             return bail(set_error(FTN_ERR_UNSUPPORTED, "smooth glass (both alphas 0) is todo!() in the reference (glass.rs:66)"));
         s->material_present[md.type] = true;
     }
@@ -674,7 +693,7 @@ int scene_destroy(FtnScene* s) {
     if (cur != s->device) cudaSetDevice(s->device);
     cudaDeviceSynchronize();   // the frees below are ordered on the legacy stream only; nothing may still read the scene
     scene_free(s->d_pos); scene_free(s->d_nrm); scene_free(s->d_uv); scene_free(s->d_idx);
-    scene_free(s->d_meshes); scene_free(s->d_materials); scene_free(s->d_spheres); scene_free(s->d_lights);
+    scene_free(s->d_meshes); scene_free(s->d_materials); scene_free(s->d_textures); scene_free(s->d_spheres); scene_free(s->d_lights);
     scene_free(s->d_nodes); scene_free(s->d_tris); scene_free(s->d_codes); scene_free(s->d_order); scene_free(s->d_work);
     for (void* p : s->owned) scene_free(p);
     if (cur != s->device) cudaSetDevice(cur);

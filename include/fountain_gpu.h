@@ -136,8 +136,37 @@ typedef enum FtnImageWrap {
 } FtnImageWrap;
 #define FTN_MAX_MIP_LEVELS 16
 
-/* Materials with constant parameters, except that Kd of matte / plastic and Kr of mirror may carry a texture
- * (kd_texture and the fields after it; mirror.rs:21-30 evaluates Kr like matte.rs:37 evaluates Kd). */
+/* The textured parameters of the materials (loaders/constructors.rs:192-238: every one of them is read with
+ * get_texture_or_default / get_texture_or_const).  Spectrum parameters take any FtnTextureType; float parameters
+ * (roughnesses, sigma, the glass index) take the float textures the loader knows -- constant and checkerboard
+ * (pbrt.rs:372) -- and read component 0 of the texture's value. */
+typedef enum FtnMaterialParam {
+    FTN_PARAM_KD = 0,          /* matte, plastic */
+    FTN_PARAM_KS = 1,          /* plastic */
+    FTN_PARAM_ETA = 2,         /* metal (spectrum) */
+    FTN_PARAM_K = 3,           /* metal (spectrum) */
+    FTN_PARAM_KR = 4,          /* mirror, glass */
+    FTN_PARAM_KT = 5,          /* glass */
+    FTN_PARAM_UROUGHNESS = 6,  /* metal, glass; plastic / isotropic metal: `roughness` */
+    FTN_PARAM_VROUGHNESS = 7,  /* metal, glass */
+    FTN_PARAM_SIGMA = 8,       /* matte, degrees */
+    FTN_PARAM_INDEX = 9,       /* glass `eta` (a float texture in the loader) */
+    FTN_PARAM_COUNT = 10
+} FtnMaterialParam;
+
+/* One entry of the scene's texture table (FtnSceneDesc::textures). */
+typedef struct FtnTexture {
+    int32_t type;            /* FtnTextureType */
+    float value[3];          /* CONSTANT */
+    float tex1[3], tex2[3];  /* CHECKERBOARD */
+    float uv_scale[2];       /* UVMapping (constructors.rs:247-261) */
+    float uv_delta[2];
+    const float* image;      /* IMAGE: the MIPMap pyramid, laid out as FtnMaterial::image */
+    int32_t image_width, image_height, image_levels, image_wrap;
+} FtnTexture;
+
+/* Materials.  Every parameter is the constant below unless param_texture[] names an entry of the texture table; Kd of
+ * matte / plastic and Kr of mirror may also use the inline slot (kd_texture and the fields after it), kept from ABI v2. */
 typedef struct FtnMaterial {
     int32_t type;            /* FtnMaterialType */
     float kd[3];             /* matte Kd / plastic Kd */
@@ -162,6 +191,7 @@ typedef struct FtnMaterial {
     int32_t image_levels;    /* checked against the rule above */
     int32_t image_wrap;      /* FtnImageWrap */
     float kt[3];             /* glass Kt (constructors.rs:200, default 1) */
+    uint32_t param_texture[FTN_PARAM_COUNT];   /* per FtnMaterialParam: 0 = the constant above; k = FtnSceneDesc::textures[k - 1] */
 } FtnMaterial;
 
 /* shapes/sphere.rs:16-27 (+ the DiffuseAreaLight it may carry, light/diffuse.rs:24-41). */
@@ -212,6 +242,8 @@ typedef struct FtnSceneDesc {
     uint32_t n_materials;
     const FtnLight* lights;
     uint32_t n_lights;
+    const FtnTexture* textures;  /* the texture table FtnMaterial::param_texture indexes (may be NULL when n_textures == 0) */
+    uint32_t n_textures;
 } FtnSceneDesc;
 
 /* ---- sensor ----------------------------------------------------------------------- */

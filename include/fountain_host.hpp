@@ -440,12 +440,18 @@ struct Sphere {                         // shapes/sphere.rs:30-58
         : object_to_world(o2w), reverse_orientation(reverse), radius(r), z_min(zmin), z_max(zmax), phi_max(phimax) {}
 };
 
+struct UVMapping {                       // texture/mapping.rs:13-53; defaults (constructors.rs:251-254)
+    float scale_u = 1.0f, scale_v = 1.0f, offset_u = 0.0f, offset_v = 0.0f;
+};
+struct SpectrumTexture;
 struct Material {
     virtual ~Material() = default;
     virtual void fill(FtnMaterial& m) const = 0;
-};
-struct UVMapping {                       // texture/mapping.rs:13-53; defaults (constructors.rs:251-254)
-    float scale_u = 1.0f, scale_v = 1.0f, offset_u = 0.0f, offset_v = 0.0f;
+    // Textures of the parameters the loader reads with get_texture_or_default (constructors.rs:192-238): Ks, eta, k, Kr, Kt,
+    // roughnesses, sigma, the glass index.  They travel through the scene's texture table (FtnSceneDesc::textures); float
+    // parameters read component 0.  Kd (matte, plastic) / Kr (mirror) may also use the constructor's inline slot.
+    std::vector<std::pair<int, std::shared_ptr<SpectrumTexture>>> param_textures;
+    Material& with_texture(FtnMaterialParam p, const SpectrumTexture& t);
 };
 // mipmap.rs:19-143 `MIPMap<Spectrum>`: the pyramid an ImageTexture filters.  Level l is max(1, w >> l) x max(1, h >> l)
 // and there are 1 + floor(log2(max(w, h))) levels (:107-121).  The reference halves each level with the `resize`
@@ -520,6 +526,25 @@ struct SpectrumTexture {
         }
     }
 };
+inline Material& Material::with_texture(FtnMaterialParam p, const SpectrumTexture& t) {
+    param_textures.emplace_back((int)p, std::make_shared<SpectrumTexture>(t));
+    return *this;
+}
+inline FtnTexture to_abi_texture(const SpectrumTexture& t) {
+    FtnTexture o{};
+    o.type = t.type;
+    o.value[0] = t.value.r; o.value[1] = t.value.g; o.value[2] = t.value.b;
+    o.tex1[0] = t.tex1.r; o.tex1[1] = t.tex1.g; o.tex1[2] = t.tex1.b;
+    o.tex2[0] = t.tex2.r; o.tex2[1] = t.tex2.g; o.tex2[2] = t.tex2.b;
+    o.uv_scale[0] = t.mapping.scale_u; o.uv_scale[1] = t.mapping.scale_v;
+    o.uv_delta[0] = t.mapping.offset_u; o.uv_delta[1] = t.mapping.offset_v;
+    if (t.type == FTN_TEXTURE_IMAGE) {
+        if (!t.mipmap) throw Error(FTN_ERR_INVALID_ARGUMENT, "image texture without a MIPMap");
+        o.image = t.mipmap->packed.data(); o.image_width = t.mipmap->width; o.image_height = t.mipmap->height;
+        o.image_levels = t.mipmap->n_levels; o.image_wrap = t.mipmap->wrap;
+    }
+    return o;
+}
 struct MatteMaterial : Material {        // material/matte.rs; Kd default 0.5, sigma default 0 (constructors.rs:192-196)
     SpectrumTexture kd;
     float sigma;                         // degrees; != 0 selects Oren-Nayar (matte.rs:42-49)
@@ -708,7 +733,15 @@ public:
             spheres.push_back(c);
         }
         std::vector<FtnMaterial> cm(mats.size());
-        for (size_t i = 0; i < mats.size(); ++i) { cm[i] = FtnMaterial{}; mats[i]->fill(cm[i]); }
+        std::vector<FtnTexture> ct;          // the texture table
+        for (size_t i = 0; i < mats.size(); ++i) {
+            cm[i] = FtnMaterial{}; mats[i]->fill(cm[i]);
+            for (const auto& pt : mats[i]->param_textures) {
+                if (pt.first < 0 || pt.first >= FTN_PARAM_COUNT) throw Error(FTN_ERR_INVALID_ARGUMENT, "fountain: unknown material parameter");
+                ct.push_back(to_abi_texture(*pt.second));
+                cm[i].param_texture[pt.first] = (uint32_t)ct.size();
+            }
+        }
         std::vector<FtnLight> cl(lights.size());
         for (size_t i = 0; i < lights.size(); ++i) {
             cl[i] = FtnLight{};
@@ -736,6 +769,7 @@ public:
         d.spheres = spheres.data(); d.n_spheres = (uint32_t)spheres.size();
         d.materials = cm.data(); d.n_materials = (uint32_t)cm.size();
         d.lights = cl.data(); d.n_lights = (uint32_t)cl.size();
+        d.textures = ct.empty() ? nullptr : ct.data(); d.n_textures = (uint32_t)ct.size();
         n_triangles_ = first;
         lib_->check(lib_->scene_create(&d, &handle_), "ftn_scene_create");
         if (build) this->build();

@@ -65,10 +65,30 @@ ORC_API int orc_scene_create(const FtnSceneDesc* d, OrcScene** out) {
     if (d->abi_version != FTN_ABI_VERSION) return fail(FTN_ERR_INVALID_ARGUMENT, "abi version mismatch");
     OrcScene* os = new OrcScene();
     Scene& s = os->scene;
+    if (d->n_textures && !d->textures) { delete os; return fail(FTN_ERR_INVALID_ARGUMENT, "n_textures != 0 but textures is null"); }
+    s.textures.resize(d->n_textures);
+    for (uint32_t i = 0; i < d->n_textures; ++i) {
+        const FtnTexture& t = d->textures[i];
+        TextureDef& td = s.textures[i];
+        if (t.type < FTN_TEXTURE_CONSTANT || t.type > FTN_TEXTURE_IMAGE) { delete os; return fail(FTN_ERR_INVALID_ARGUMENT, "texture table: unknown texture type"); }
+        td.type = t.type; td.value = Spectrum(t.value[0], t.value[1], t.value[2]);
+        td.tex1 = Spectrum(t.tex1[0], t.tex1[1], t.tex1[2]); td.tex2 = Spectrum(t.tex2[0], t.tex2[1], t.tex2[2]);
+        for (int c = 0; c < 2; ++c) { td.uv_scale[c] = t.uv_scale[c]; td.uv_delta[c] = t.uv_delta[c]; }
+        if (t.type == FTN_TEXTURE_IMAGE) {
+            td.image = make_mipmap(t.image, t.image_width, t.image_height, t.image_levels, t.image_wrap);
+            if (!td.image) { delete os; return fail(FTN_ERR_INVALID_ARGUMENT, "texture table: bad pyramid description"); }
+        }
+    }
     for (uint32_t i = 0; i < d->n_materials; ++i) {
         const FtnMaterial& m = d->materials[i];
         Material mm{};
         mm.type = m.type;
+        mm.table = &s.textures;
+        for (int p = 0; p < FTN_PARAM_COUNT; ++p) {
+            if (m.param_texture[p] > d->n_textures) { delete os; return fail(FTN_ERR_INVALID_ARGUMENT, "material: param_texture id out of range"); }
+            mm.ptex[p] = m.param_texture[p];
+        }
+        if (m.type == FTN_MATERIAL_PLASTIC) mm.ptex[FTN_PARAM_VROUGHNESS] = mm.ptex[FTN_PARAM_UROUGHNESS];
         mm.kd = Spectrum(m.kd[0], m.kd[1], m.kd[2]); mm.ks = Spectrum(m.ks[0], m.ks[1], m.ks[2]);
         mm.eta = Spectrum(m.eta[0], m.eta[1], m.eta[2]); mm.k = Spectrum(m.k[0], m.k[1], m.k[2]);
         mm.u_rough = m.u_roughness; mm.v_rough = m.v_roughness; mm.remap = m.remap_roughness != 0;
@@ -77,7 +97,8 @@ ORC_API int orc_scene_create(const FtnSceneDesc* d, OrcScene** out) {
         if (m.type == FTN_MATERIAL_GLASS) {   // glass.rs:64-67: the specular branch is todo!() under the path integrator
             Float ur = m.u_roughness, vr = m.v_roughness;
             if (m.remap_roughness) { ur = roughness_to_alpha(ur); vr = roughness_to_alpha(vr); }
-            if (ur == 0.0f && vr == 0.0f) { delete os; return fail(FTN_ERR_UNSUPPORTED, "smooth glass is todo!() in the reference (glass.rs:66)"); }
+            const bool textured = m.param_texture[FTN_PARAM_UROUGHNESS] || m.param_texture[FTN_PARAM_VROUGHNESS];
+            if (!textured && ur == 0.0f && vr == 0.0f) { delete os; return fail(FTN_ERR_UNSUPPORTED, "smooth glass is todo!() in the reference (glass.rs:66)"); }
         }
         mm.kd_texture = m.kd_texture; mm.tex1 = Spectrum(m.tex1[0], m.tex1[1], m.tex1[2]); mm.tex2 = Spectrum(m.tex2[0], m.tex2[1], m.tex2[2]);
         for (int c = 0; c < 2; ++c) { mm.uv_scale[c] = m.uv_scale[c]; mm.uv_delta[c] = m.uv_delta[c]; }

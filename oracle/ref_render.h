@@ -175,6 +175,7 @@ struct Scene {
     std::vector<TriangleMesh> meshes;
     std::vector<Sphere> spheres;
     std::vector<Material> materials;
+    std::vector<TextureDef> textures;   // the table Material::ptex indexes
     std::vector<Primitive> prims;     // insertion order: triangles (mesh order, tri_id), then spheres
     std::vector<Light> lights;
     BVH bvh;
@@ -318,11 +319,11 @@ inline void compute_tex_differentials(SurfaceInteraction* si, const Differential
 }
 
 // SurfaceInteraction::compute_scattering_functions, interaction.rs:111-121
-inline bool compute_bsdf(const Scene& scene, SurfaceInteraction& si, const Differential& diff, Bsdf* bsdf) {
+inline bool compute_bsdf(const Scene& scene, SurfaceInteraction& si, const Differential& diff, Bsdf* bsdf, bool* unsupported = nullptr) {
     compute_tex_differentials(&si, diff);
     int m = scene.prims[si.prim].material;
     if (m < 0) return false;
-    compute_scattering_functions(scene.materials[m], si, bsdf);
+    if (!compute_scattering_functions(scene.materials[m], si, bsdf) && unsupported) *unsupported = true;   // todo!() in the reference (glass.rs:66)
     return true;
 }
 
@@ -345,7 +346,7 @@ inline Spectrum path_incident_radiance(Ray ray, const Differential& diff, int ma
         }
         if (!hit || bounces >= max_depth) break;
         Bsdf bsdf;
-        if (compute_bsdf(scene, si, diff, &bsdf)) {
+        if (compute_bsdf(scene, si, diff, &bsdf, cx.unsupported)) {
             if (cx.sampler->mode == 0) cx.sampler->set_dim(DIM_CAMERA + DIM_PER_BOUNCE * (uint32_t)bounces);
             if (bsdf.num_components(BXDF_ALL & ~BXDF_SPECULAR) > 0) {
                 Spectrum direct = beta * uniform_sample_one_light(si, bsdf, cx);
@@ -389,7 +390,7 @@ inline Spectrum direct_incident_radiance(Ray ray, const Differential& diff, int 
     if (!scene.intersect(&ray, &si, tc)) return scene.environment_emitted_radiance(ray);
     Bsdf bsdf;
     Spectrum radiance(0.0f);
-    if (!compute_bsdf(scene, si, diff, &bsdf)) { *unsupported_null = true; return radiance; }   // unimplemented!() :98
+    if (!compute_bsdf(scene, si, diff, &bsdf, cx.unsupported)) { *unsupported_null = true; return radiance; }   // unimplemented!() :98
     radiance = radiance + scene.emitted_radiance(si, si.wo);
     if (cx.sampler->mode == 0) cx.sampler->set_dim(DIM_CAMERA + DIM_PER_BOUNCE * (uint32_t)depth);
     radiance = radiance + uniform_sample_one_light(si, bsdf, cx);

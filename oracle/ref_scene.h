@@ -355,8 +355,16 @@ struct MIPMap {
 };
 
 // ---- materials / lights tables ------------------------------------------------------------
+// One entry of the scene's texture table: texture/{mod,checkerboard,uv,image}.rs behind UVMapping (mapping.rs:36-53)
+struct TextureDef {
+    int type;          // FtnTextureType
+    Spectrum value, tex1, tex2; Float uv_scale[2], uv_delta[2];
+    std::shared_ptr<MIPMap> image;
+};
 struct Material {
     int type;          // FtnMaterialType
+    uint32_t ptex[FTN_PARAM_COUNT];                 // per parameter: 0 = the constant, k = (*table)[k - 1]  (loaders/constructors.rs:192-238)
+    const std::vector<TextureDef>* table;
     Spectrum kd, ks, eta, k, kr, kt;
     int kd_texture;    // FtnTextureType
     Spectrum tex1, tex2; Float uv_scale[2], uv_delta[2];

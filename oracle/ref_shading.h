@@ -400,12 +400,36 @@ inline Spectrum evaluate_kd(const Material& m, const SurfaceInteraction& si) {
     return Spectrum(s - std::floor(s), t - std::floor(t), 0.0f);
 }
 
-// material/{matte,metal,plastic}.rs compute_scattering_functions
-inline void compute_scattering_functions(const Material& m, const SurfaceInteraction& si, Bsdf* bsdf) {
+// Texture::evaluate of a texture-table entry
+inline Spectrum evaluate_texture(const TextureDef& t, const SurfaceInteraction& si) {
+    if (t.type == 0) return t.value;
+    Float s = t.uv_scale[0] * si.uv[0] + t.uv_delta[0], tt = t.uv_scale[1] * si.uv[1] + t.uv_delta[1];
+    if (t.type == 1) return (((int)std::floor(s) + (int)std::floor(tt)) % 2 == 0) ? t.tex1 : t.tex2;
+    if (t.type == 3) {
+        Float dst_dx[2] = {t.uv_scale[0] * si.dudx, t.uv_scale[1] * si.dvdx};
+        Float dst_dy[2] = {t.uv_scale[0] * si.dudy, t.uv_scale[1] * si.dvdy};
+        return t.image->lookup_trilinear(s, tt, dst_dx, dst_dy);
+    }
+    return Spectrum(s - std::floor(s), tt - std::floor(tt), 0.0f);
+}
+inline bool param_textured(const Material& m, int p) { return m.table && m.ptex[p] != 0; }
+inline Spectrum param_spectrum(const Material& m, int p, Spectrum constant, const SurfaceInteraction& si) {
+    return param_textured(m, p) ? evaluate_texture((*m.table)[m.ptex[p] - 1], si) : constant;
+}
+inline Float param_float(const Material& m, int p, Float constant, const SurfaceInteraction& si) {
+    return param_textured(m, p) ? evaluate_texture((*m.table)[m.ptex[p] - 1], si).c[0] : constant;
+}
+// Kd (matte, plastic) / Kr (mirror): the texture table, else the inline slot of ABI v2, else the constant
+inline Spectrum param_kd(const Material& m, int p, const SurfaceInteraction& si) {
+    return param_textured(m, p) ? evaluate_texture((*m.table)[m.ptex[p] - 1], si) : evaluate_kd(m, si);
+}
+
+// material/{matte,metal,plastic,mirror,glass}.rs compute_scattering_functions; false where the reference hits todo!()
+inline bool compute_scattering_functions(const Material& m, const SurfaceInteraction& si, Bsdf* bsdf) {
     bsdf->init(si);
-    if (m.type == 0) {   // matte.rs:36-52 (sigma == 0 only)
-        Spectrum r = evaluate_kd(m, si).clamp_positive();
-        Float sigma = clampf(m.sigma, 0.0f, 90.0f);
+    if (m.type == 0) {   // matte.rs:36-52
+        Spectrum r = param_kd(m, FTN_PARAM_KD, si).clamp_positive();
+        Float sigma = clampf(param_float(m, FTN_PARAM_SIGMA, m.sigma, si), 0.0f, 90.0f);
         if (!r.is_black()) {
             BxDF b{}; b.r = r;
             if (sigma == 0.0f) b.kind = 0;
@@ -416,37 +440,40 @@ inline void compute_scattering_functions(const Material& m, const SurfaceInterac
             bsdf->add(b);
         }
     } else if (m.type == 1) {   // metal.rs:38-65
-        Float ur = m.u_rough, vr = m.v_rough;
+        Float ur = param_float(m, FTN_PARAM_UROUGHNESS, m.u_rough, si), vr = param_float(m, FTN_PARAM_VROUGHNESS, m.v_rough, si);
         if (m.remap) { ur = roughness_to_alpha(ur); vr = roughness_to_alpha(vr); }
         BxDF b{}; b.kind = 1; b.r = Spectrum(1.0f); b.alpha_x = ur; b.alpha_y = vr;
-        b.fresnel = 0; b.eta_i = Spectrum(1.0f); b.eta_t = m.eta; b.k = m.k;
+        b.fresnel = 0; b.eta_i = Spectrum(1.0f); b.eta_t = param_spectrum(m, FTN_PARAM_ETA, m.eta, si); b.k = param_spectrum(m, FTN_PARAM_K, m.k, si);
         bsdf->add(b);
     } else if (m.type == 4) {   // glass.rs:52-96; the specular branch is todo!() (path) or a two-branch recursion (direct lighting): rejected at scene creation
-        Spectrum r = m.kr.clamp_positive(), t = m.kt.clamp_positive();
-        Float ur = m.u_rough, vr = m.v_rough;
+        Float eta = param_float(m, FTN_PARAM_INDEX, m.eta.c[0], si);
+        Spectrum r = param_spectrum(m, FTN_PARAM_KR, m.kr, si).clamp_positive(), t = param_spectrum(m, FTN_PARAM_KT, m.kt, si).clamp_positive();
+        Float ur = param_float(m, FTN_PARAM_UROUGHNESS, m.u_rough, si), vr = param_float(m, FTN_PARAM_VROUGHNESS, m.v_rough, si);
         if (m.remap) { ur = roughness_to_alpha(ur); vr = roughness_to_alpha(vr); }
+        if (ur == 0.0f && vr == 0.0f) return false;   // glass.rs:64-67: todo!("FresnelSpecular")
         if (!r.is_black()) {
-            BxDF b{}; b.kind = 1; b.r = r; b.alpha_x = ur; b.alpha_y = vr; b.fresnel = 1; b.d_eta_i = 1.0f; b.d_eta_t = m.eta.c[0];
+            BxDF b{}; b.kind = 1; b.r = r; b.alpha_x = ur; b.alpha_y = vr; b.fresnel = 1; b.d_eta_i = 1.0f; b.d_eta_t = eta;
             bsdf->add(b);
         }
         if (!t.is_black()) {
-            BxDF b{}; b.kind = 4; b.r = t; b.alpha_x = ur; b.alpha_y = vr; b.d_eta_i = 1.0f; b.d_eta_t = m.eta.c[0];
+            BxDF b{}; b.kind = 4; b.r = t; b.alpha_x = ur; b.alpha_y = vr; b.d_eta_i = 1.0f; b.d_eta_t = eta;
             bsdf->add(b);
         }
     } else if (m.type == 3) {   // mirror.rs:21-30
-        Spectrum r = evaluate_kd(m, si).clamp_positive();
+        Spectrum r = param_kd(m, FTN_PARAM_KR, si).clamp_positive();
         if (!r.is_black()) { BxDF b{}; b.kind = 2; b.r = r; bsdf->add(b); }
     } else {   // plastic.rs:24-48
-        Spectrum kd = evaluate_kd(m, si);
+        Spectrum kd = param_kd(m, FTN_PARAM_KD, si), ks = param_spectrum(m, FTN_PARAM_KS, m.ks, si);
         if (!kd.is_black()) { BxDF b{}; b.kind = 0; b.r = kd; bsdf->add(b); }
-        if (!m.ks.is_black()) {
-            Float rough = m.u_rough;
+        if (!ks.is_black()) {
+            Float rough = param_float(m, FTN_PARAM_UROUGHNESS, m.u_rough, si);
             if (m.remap) rough = roughness_to_alpha(rough);
-            BxDF b{}; b.kind = 1; b.r = m.ks; b.alpha_x = rough; b.alpha_y = rough;
+            BxDF b{}; b.kind = 1; b.r = ks; b.alpha_x = rough; b.alpha_y = rough;
             b.fresnel = 1; b.d_eta_i = 1.5f; b.d_eta_t = 1.0f;
             bsdf->add(b);
         }
     }
+    return true;
 }
 
 }  // namespace ref

@@ -1,0 +1,55 @@
+"""Turns an ncu per-launch metrics CSV (scripts/gpu_r2_final.sh) + the bench line of the same command into the record
+bench.py's roofline uses: warp instructions, ALU / FMA-pipe instructions and DRAM bytes PER RAY of one kernel of one
+workload, stamped with the commit and the files they were read from.  usage:
+  ncu_traffic.py <workload> <kernel-key> <kernel-name-regex> <metrics.csv> <rays-per-render> <renders-captured> <source-note>"""
+import csv
+import json
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+workload, key, name_re, csv_path, rays, renders, note = sys.argv[1:8]
+rays, renders = float(rays), float(renders)
+rows = []
+with open(csv_path, newline="") as f:
+    lines = [l for l in f if not l.startswith("==")]
+r = list(csv.reader(lines))
+hdr = r[0]
+iname, imetric, ivalue, iunit = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+iid = hdr.index("ID")
+acc, launches = {}, set()
+pct = {}
+for row in r[1:]:
+    if len(row) <= ivalue or not re.search(name_re, row[iname]):
+        continue
+    launches.add(row[iid])
+    v = float(row[ivalue].replace(",", ""))
+    u = row[iunit]
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1.0}.get(u, 1.0)
+    m = row[imetric]
+    if "pct" in m or "ratio" in m:
+        pct.setdefault(m, []).append(v)
+    else:
+        acc[m] = acc.get(m, 0.0) + v * scale
+n = max(1, len(launches))
+total_rays = rays * renders
+rec = {
+    "bound": "sm-issue (ALU pipe)",
+    "warp_inst_per_ray": acc.get("smsp__inst_executed.sum", 0.0) / total_rays,
+    "alu_pipe_inst_per_ray": acc.get("sm__inst_executed_pipe_alu.sum", 0.0) / total_rays,
+    "fma_pipe_inst_per_ray": acc.get("sm__inst_executed_pipe_fma.sum", 0.0) / total_rays,
+    "lsu_wavefronts_per_ray": acc.get("l1tex__data_pipe_lsu_wavefronts.sum", 0.0) / total_rays,
+    "dram_bytes_per_ray": (acc.get("dram__bytes_read.sum", 0.0) + acc.get("dram__bytes_write.sum", 0.0)) / total_rays,
+    "launches_captured": n, "rays_captured": total_rays,
+    "gpu_time_under_ncu_ms": acc.get("gpu__time_duration.sum", 0.0) * 1e3,
+    "pct_mean": {m: sum(v) / len(v) for m, v in pct.items()},
+    "commit": subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip(),
+    "source": note,
+}
+p = os.path.join(ROOT, "profiles", "traffic.json")
+d = json.load(open(p))
+d.setdefault(workload, {})[key] = rec
+json.dump(d, open(p, "w"), indent=1)
+print(workload, key, json.dumps({k: rec[k] for k in ("warp_inst_per_ray", "alu_pipe_inst_per_ray", "fma_pipe_inst_per_ray", "dram_bytes_per_ray", "launches_captured")}))

@@ -188,6 +188,43 @@ static void textured_floor_and_mirror_closed_forms() {
         CHECK(std::fabs(s.r - 0.8f) < 1e-5f && std::fabs(s.g - 0.7f) < 1e-5f && std::fabs(s.b - 0.6f) < 1e-5f, "mirror %.7g %.7g %.7g", s.r, s.g, s.b);
 }
 
+// The texture table (FtnSceneDesc::textures): Kd of a matte floor through the table gives the closed forms of the inline
+// slot; constant textures for plastic's Ks / roughness and rough glass's Kt / index give the image of the plain constants.
+static void texture_table_parameters() {
+    const float pi = 3.14159265358979f;
+    auto probe = [&](std::shared_ptr<Material> mat, double x, double y) {
+        std::vector<float> v = {-6, -6, 0, 6, -6, 0, 6, 6, 0, -6, 6, 0}, uv = {-6, -6, 6, -6, 6, 6, -6, 6};
+        auto mesh = std::make_shared<TriangleMesh>(Transform::identity(), std::vector<uint32_t>{0, 1, 2, 0, 2, 3}, v, std::vector<float>{}, uv);
+        std::vector<GeometricPrimitive> prims; prims.emplace_back(mesh, mat);
+        Scene scene(g_lib, prims, {Light(DistantLight::from_to(Point3f(0.3, 0, 1), Point3f(0, 0, 0), Spectrum(3.0f))), Light(InfiniteAreaLight::new_uniform(Spectrum(0.3f)))});
+        PerspectiveCamera camera(Transform::look_at({x, y - 6.0, 20.0}, {x, y, 0.0}, {0, 1, 0}).inverse(), 6, 6, 1.0f);
+        Film film(g_lib, 6, 6);
+        SamplerIntegrator<PathIntegrator> integrator(camera, PathIntegrator(3, 1.0f));
+        integrator.render_parallel(scene, film, RandomSampler::new_with_seed(8, 3));
+        return film.into_spectrum_buffer().first;
+    };
+    auto same = [&](const std::vector<Spectrum>& a, const std::vector<Spectrum>& b, const char* what) {
+        bool eq = a.size() == b.size();
+        for (size_t i = 0; eq && i < a.size(); ++i) eq = a[i].r == b[i].r && a[i].g == b[i].g && a[i].b == b[i].b;
+        CHECK(eq, "%s: the table's constant textures differ from the constants", what);
+    };
+    auto plastic_c = std::make_shared<PlasticMaterial>(SpectrumTexture(0.3f), Spectrum(0.5f, 0.4f, 0.3f), 0.2f);
+    auto plastic_t = std::make_shared<PlasticMaterial>(SpectrumTexture(0.3f), Spectrum(0.0f), 0.9f);
+    plastic_t->with_texture(FTN_PARAM_KS, SpectrumTexture(Spectrum(0.5f, 0.4f, 0.3f))).with_texture(FTN_PARAM_UROUGHNESS, SpectrumTexture(0.2f));
+    same(probe(plastic_c, 0.5, 0.5), probe(plastic_t, 0.5, 0.5), "plastic");
+    auto glass_c = std::make_shared<GlassMaterial>(Spectrum(1.0f), Spectrum(0.8f, 0.9f, 1.0f), 1.4f, 0.3f, 0.3f);
+    auto glass_t = std::make_shared<GlassMaterial>(Spectrum(1.0f), Spectrum(0.0f), 2.0f, 0.3f, 0.3f);
+    glass_t->with_texture(FTN_PARAM_KT, SpectrumTexture(Spectrum(0.8f, 0.9f, 1.0f))).with_texture(FTN_PARAM_INDEX, SpectrumTexture(1.4f));
+    same(probe(glass_c, 0.5, 0.5), probe(glass_t, 0.5, 0.5), "glass");
+    // Kd checkerboard through the table: under the direct-lighting integrator the two cells give Kd / pi * (L cos + pi L_env)
+    auto matte_t = std::make_shared<MatteMaterial>(SpectrumTexture(0.0f));
+    matte_t->with_texture(FTN_PARAM_KD, SpectrumTexture::checkerboard(Spectrum(0.8f, 0.2f, 0.2f), Spectrum(0.1f, 0.1f, 0.9f)));
+    auto matte_i = std::make_shared<MatteMaterial>(SpectrumTexture::checkerboard(Spectrum(0.8f, 0.2f, 0.2f), Spectrum(0.1f, 0.1f, 0.9f)));
+    same(probe(matte_i, 0.5, 0.5), probe(matte_t, 0.5, 0.5), "matte Kd, tex1 cell");
+    same(probe(matte_i, -0.5, 0.5), probe(matte_t, -0.5, 0.5), "matte Kd, tex2 cell");
+    (void)pi;
+}
+
 // texture/image.rs through MIPMap::from_image; no reference test renders one -- closed forms as in tests/test_oracle_render.py:
 // (1) a ramp image is reproduced by the bilinear filter at level 0, (2) with a huge uscale the footprint exceeds the
 // image and the 1x1 top level (the mean of a two-valued checker) is returned
@@ -269,6 +306,7 @@ int main(int argc, char** argv) {
         {"world_bound_and_morton_order", world_bound_and_morton_order},
         {"textured_floor_and_mirror_closed_forms", textured_floor_and_mirror_closed_forms},
         {"image_texture_closed_forms", image_texture_closed_forms},
+        {"texture_table_parameters", texture_table_parameters},
         {"invalid_arguments_are_errors", invalid_arguments_are_errors},
     };
     int ran = 0;

@@ -32,7 +32,8 @@ struct SimScene {
     std::vector<SphereData> spheres; std::vector<LightData> lights;
     std::vector<std::vector<F4>> env_tex; std::vector<std::vector<float>> env_f;   // storage behind EnvLightData pointers
     std::list<std::vector<uint32_t>> env_g;
-    std::list<std::vector<F4>> images;   // storage behind MaterialData::image
+    std::list<std::vector<F4>> images;   // storage behind MaterialData::image / TextureData::image
+    std::vector<TextureData> texs;
     std::vector<F4> nodes, tris; uint32_t n_nodes = 0; bool wide = false; uint32_t bvh_levels = 0;
     std::vector<uint32_t> codes, order;
     float bounds[6]; bool built = false; uint32_t n_tris = 0;
@@ -40,7 +41,7 @@ struct SimScene {
         SceneView v;
         v.bvh.nodes = nodes.data(); v.bvh.tris = tris.data(); v.bvh.n_nodes = n_nodes; v.bvh.n_tris = n_tris; v.bvh.wide = wide ? 1u : 0u;
         v.pos = pos.data(); v.nrm = nrm.empty() ? nullptr : nrm.data(); v.uv = uv.empty() ? nullptr : uv.data(); v.idx = idx.data();
-        v.meshes = meshes.data(); v.materials = mats.data(); v.spheres = spheres.data(); v.n_spheres = (uint32_t)spheres.size();
+        v.meshes = meshes.data(); v.materials = mats.data(); v.textures = texs.data(); v.spheres = spheres.data(); v.n_spheres = (uint32_t)spheres.size();
         v.lights = lights.data(); v.n_lights = (uint32_t)lights.size(); v.n_tris = n_tris; v.refill_threshold = 20; v.vote_bias = 14; v.vote = true;
         return v;
     }
@@ -65,8 +66,14 @@ SIM_API int sim_scene_create(const FtnSceneDesc* d, SimScene** out) {
     if (d->normals) s->nrm.assign(d->normals, d->normals + 3 * (size_t)d->n_vertices);
     if (d->uvs) s->uv.assign(d->uvs, d->uvs + 2 * (size_t)d->n_vertices);
     s->idx.assign(d->indices, d->indices + 3 * (size_t)d->n_triangles);
+    s->texs.resize(d->n_textures);
+    for (uint32_t t = 0; t < d->n_textures; ++t) {   // as scene.cu
+        s->images.emplace_back();
+        if (texture_from_abi(d->textures[t], &s->texs[t], &s->images.back()) != FTN_OK) { delete s; g_err = "texture table: bad texture"; return FTN_ERR_INVALID_ARGUMENT; }
+        if (s->texs[t].type == FTN_TEXTURE_IMAGE) s->texs[t].image = s->images.back().data();
+    }
     for (uint32_t m = 0; m < d->n_materials; ++m) {
-        const FtnMaterial& fm = d->materials[m]; MaterialData md; md.type = fm.type;
+        const FtnMaterial& fm = d->materials[m]; MaterialData md; std::memset(&md, 0, sizeof(md)); md.type = fm.type;
         for (int c = 0; c < 3; ++c) { md.kd[c] = fm.kd[c]; md.ks[c] = fm.ks[c]; md.eta[c] = fm.eta[c]; md.k[c] = fm.k[c]; }
         float ur = fm.u_roughness, vr = fm.v_roughness;
         if (fm.type == FTN_MATERIAL_MIRROR) for (int c = 0; c < 3; ++c) md.kd[c] = fm.kr[c];   // Kr travels in the kd slot
@@ -92,7 +99,8 @@ SIM_API int sim_scene_create(const FtnSceneDesc* d, SimScene** out) {
         if (fm.type == FTN_MATERIAL_PLASTIC) vr = ur;
         if (fm.remap_roughness) { ur = roughness_to_alpha_host(ur); vr = roughness_to_alpha_host(vr); }
         if (md.type != FTN_CLASS_OREN_NAYAR) { md.alpha_x = ur; md.alpha_y = vr; }   // Oren-Nayar keeps (a, b) there
-        if (fm.type == FTN_MATERIAL_GLASS && ur == 0.0f && vr == 0.0f) { delete s; g_err = "smooth glass is todo!() in the reference (glass.rs:66)"; return FTN_ERR_UNSUPPORTED; }
+        if (material_params_from_abi(fm, d->n_textures, [&](uint32_t id) { return s->texs[id - 1].type == FTN_TEXTURE_IMAGE; }, &md) != FTN_OK) { delete s; g_err = "material: param_texture id out of range"; return FTN_ERR_INVALID_ARGUMENT; }
+        if (fm.type == FTN_MATERIAL_GLASS && !(md.ptex[FTN_PARAM_UROUGHNESS] || md.ptex[FTN_PARAM_VROUGHNESS]) && ur == 0.0f && vr == 0.0f) { delete s; g_err = "smooth glass is todo!() in the reference (glass.rs:66)"; return FTN_ERR_UNSUPPORTED; }
         s->mats.push_back(md);
     }
     s->env_tex.reserve(d->n_lights); s->env_f.reserve(5 * d->n_lights);
@@ -480,7 +488,8 @@ SIM_API void sim_kat_bsdf(const FtnMaterial* m, const float wo[3], const float w
     Bsdf b; bsdf_init(&b, V3(0, 0, 1), V3(0, 0, 1), V3(1, 0, 0));
     const V3 o(wo[0], wo[1], wo[2]), i(wi[0], wi[1], wi[2]);
     V3 f; float pdf; ScatterSample sm; bool ok;
-#define SIM_BSDF(M) { material_bsdf<M>(s->mats[0], 0.0f, 0.0f, TexDiffs{0.0f, 0.0f, 0.0f, 0.0f}, &b); f = bsdf_f<M>(b, o, i, BXDF_ALL); pdf = bsdf_pdf<M>(b, o, i, BXDF_ALL); ok = bsdf_sample_f<M>(b, o, u[0], u[1], BXDF_ALL, &sm); }
+    const SceneView scv = s->view(); bool unsupported = false;
+#define SIM_BSDF(M) { material_bsdf<M, true>(scv, s->mats[0], 0.0f, 0.0f, TexDiffs{0.0f, 0.0f, 0.0f, 0.0f}, &b, &unsupported); f = bsdf_f<M>(b, o, i, BXDF_ALL); pdf = bsdf_pdf<M>(b, o, i, BXDF_ALL); ok = bsdf_sample_f<M>(b, o, u[0], u[1], BXDF_ALL, &sm); }
     if (s->mats[0].type == FTN_CLASS_OREN_NAYAR) SIM_BSDF(FTN_CLASS_OREN_NAYAR)
     else if (m->type == FTN_MATERIAL_MATTE) SIM_BSDF(FTN_MATERIAL_MATTE)
     else if (m->type == FTN_MATERIAL_METAL) SIM_BSDF(FTN_MATERIAL_METAL)

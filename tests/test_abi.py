@@ -69,7 +69,7 @@ def test_ctypes_structs_match_the_compiled_header(tmp_path):
     """sizeof / offsetof of every ABI struct as gcc lays the header out == the ctypes mirror in
     fountain_b200/_abi.py (a stale mirror would silently shift array strides)."""
     import subprocess
-    structs = ["FtnRay", "FtnHit", "FtnMeshDesc", "FtnMaterial", "FtnSphere", "FtnLight", "FtnSceneDesc", "FtnCamera", "FtnFilm",
+    structs = ["FtnRay", "FtnHit", "FtnMeshDesc", "FtnMaterial", "FtnTexture", "FtnSphere", "FtnLight", "FtnSceneDesc", "FtnCamera", "FtnFilm",
                "FtnSampler", "FtnIntegrator", "FtnPixel", "FtnStats"]
     lines = []
     for s in structs:

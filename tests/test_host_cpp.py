@@ -26,15 +26,15 @@ def run(binary, lib, prefix, *names):
 
 def test_host_cpp_against_oracle(host_tests, oracle):
     out = run(host_tests, oracle.build(), "orc_")
-    assert "10 run, 0 failed" in out
+    assert "11 run, 0 failed" in out
 
 
 def test_host_cpp_against_hostsim(host_tests):
     from tests.hostsim import sim
     lib = sim.build()
     out = run(host_tests, lib, "sim_", "furnace_test_path_no_rr", "furnace_test_directlighting", "test_rounded_cube",
-              "world_bound_and_morton_order", "image_texture_closed_forms")
-    assert "5 run, 0 failed" in out
+              "world_bound_and_morton_order", "image_texture_closed_forms", "texture_table_parameters")
+    assert "6 run, 0 failed" in out
 
 
 def test_host_cpp_fails_loudly_without_a_library(host_tests):
@@ -46,4 +46,4 @@ def test_host_cpp_fails_loudly_without_a_library(host_tests):
 def test_host_cpp_on_gpu(host_tests, gpu_backend):
     from fountain_b200 import lib as gpulib
     out = run(host_tests, os.environ.get("FTN_GPU_LIB") or gpulib.GPU_LIB_PATH, "ftn_")
-    assert "10 run, 0 failed" in out
+    assert "11 run, 0 failed" in out

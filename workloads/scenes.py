@@ -431,3 +431,49 @@ def rough_glass_scene(backend=None, resolution=(48, 48), roughness=0.25, remap=T
     camera = api.PerspectiveCamera(cam_to_world, resolution, fov=45.0)
     film = api.Film(resolution, backend=backend)
     return scene, camera, film
+
+
+# ---- the texture table: every material parameter may be textured (loaders/constructors.rs:192-238; missing in round 1) ----
+def textured_params_scene(backend=None, resolution=(48, 48), variant="table"):
+    """Five quads in a row on a dark floor, each with a material whose NON-Kd parameters are textured through the scene's
+    texture table: plastic (Ks + roughness checkerboards, Kd image through the table), metal (eta / k checkerboards,
+    anisotropic roughness textures), matte (sigma checkerboard 0 / 35 degrees: Lambert and Oren-Nayar cells), rough glass
+    (Kt checkerboard, roughness checkerboard, index texture) and a mirror (Kr uv texture through the table).
+    variant = "constant" builds the same scene with ConstantTextures of each checkerboard's first value in the table
+    and plain constants -- what "table" must reduce to where only tex1 cells are seen; "inline" puts Kd / Kr textures in the
+    materials' inline slot instead of the table (must equal "table" bit for bit)."""
+    cb = lambda a, b, su=2.0, sv=2.0: api.Checkerboard2DTexture(a, b, api.UVMapping(su, sv, 0.0, 0.0))
+    img = api.ImageTexture(api.MIPMap(procedural_image(32, 16, 7), "repeat"), api.UVMapping(1.0, 1.0, 0.0, 0.0))
+    uvt = api.UVTexture(api.UVMapping(1.0, 1.0, 0.0, 0.0))
+    wrap = (lambda t: t) if variant == "inline" else api.InTable
+    if variant == "constant":
+        c = api.ConstantTexture
+        mats = [api.PlasticMaterial(0.3, c((0.5, 0.4, 0.3)), c(0.05)),
+                api.MetalMaterial(c((0.2, 0.92, 1.1)), c((3.9, 2.45, 2.14)), u_roughness=c(0.02), v_roughness=0.1),
+                api.MatteMaterial(0.6, c(35.0)),
+                api.GlassMaterial(1.0, c((0.9, 0.9, 1.0)), c(1.5), c(0.2), 0.2),
+                api.MirrorMaterial(0.8)]
+    else:
+        mats = [api.PlasticMaterial(wrap(img), cb((0.5, 0.4, 0.3), (0.05, 0.05, 0.05)), cb(0.05, 0.4, 3.0, 1.0)),
+                api.MetalMaterial(cb((0.2, 0.92, 1.1), (1.5, 0.9, 0.3)), cb((3.9, 2.45, 2.14), (2.0, 2.0, 2.0)),
+                                  u_roughness=cb(0.02, 0.3), v_roughness=cb(0.1, 0.05, 1.0, 4.0)),
+                api.MatteMaterial(0.6, cb(35.0, 0.0)),
+                api.GlassMaterial(1.0, cb((0.9, 0.9, 1.0), (0.2, 0.9, 0.3)), cb(1.5, 1.2, 1.0, 1.0), cb(0.2, 0.05), 0.2),
+                api.MirrorMaterial(wrap(uvt))]
+    uv = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], np.float32)
+
+    def quad(p0, p1, p2, p3):
+        return api.TriangleMesh(Transform.identity(), np.array([0, 1, 2, 0, 2, 3], np.uint32), np.array([p0, p1, p2, p3], np.float32), tex_coords=uv)
+    prims = [api.GeometricPrimitive(quad((-8, -6, -0.01), (8, -6, -0.01), (8, 8, -0.01), (-8, 8, -0.01)), api.MatteMaterial(0.05))]
+    for i, m in enumerate(mats):
+        x0 = -5.0 + 2.05 * i
+        if isinstance(m, api.GlassMaterial):      # a standing pane so that light passes through it
+            prims.append(api.GeometricPrimitive(quad((x0, 0.5, 0.0), (x0 + 2, 0.5, 0.0), (x0 + 2, 0.5, 2.0), (x0, 0.5, 2.0)), m))
+        else:
+            prims.append(api.GeometricPrimitive(quad((x0, -1, 0.0), (x0 + 2, -1, 0.0), (x0 + 2, 1, 0.6), (x0, 1, 0.6)), m))
+    lights = [api.InfiniteAreaLight.new_uniform(0.5), api.PointLight.from_params(I=80.0, from_=(0.0, -3.0, 4.0))]
+    scene = api.Scene(prims, lights, backend=backend)
+    cam_to_world = Transform.look_at((0, -9, 4.5), (0, 0, 0.3), (0, 0, 1)).inverse()
+    camera = api.PerspectiveCamera(cam_to_world, resolution, fov=50.0)
+    film = api.Film(resolution, backend=backend)
+    return scene, camera, film
