@@ -139,6 +139,33 @@ struct LightData {
     EnvLightData env;
 };
 
+// Host side: a parameter whose table entry is a CONSTANT texture is that constant (texture/mod.rs:34-42) -- fold it into
+// the material at scene creation, so the per-hit table lookup (and the per-hit roughness remap, whose device logf need not
+// round like the host's) is kept for the textures that vary.  Ids out of range are left for material_params_from_abi to refuse.
+inline FtnMaterial fold_constant_param_textures(const FtnMaterial& in, const FtnTexture* textures, uint32_t n_textures) {
+    FtnMaterial fm = in;
+    for (int p = 0; p < FTN_PARAM_COUNT; ++p) {
+        const uint32_t id = fm.param_texture[p];
+        if (!id || id > n_textures || !textures || textures[id - 1].type != FTN_TEXTURE_CONSTANT) continue;
+        const float* v = textures[id - 1].value;
+        const int t = fm.type;
+        bool folded = true;
+        if (p == FTN_PARAM_KD && (t == FTN_MATERIAL_MATTE || t == FTN_MATERIAL_PLASTIC)) { for (int c = 0; c < 3; ++c) fm.kd[c] = v[c]; fm.kd_texture = FTN_TEXTURE_CONSTANT; }
+        else if (p == FTN_PARAM_KS && t == FTN_MATERIAL_PLASTIC) { for (int c = 0; c < 3; ++c) fm.ks[c] = v[c]; }
+        else if (p == FTN_PARAM_ETA && t == FTN_MATERIAL_METAL) { for (int c = 0; c < 3; ++c) fm.eta[c] = v[c]; }
+        else if (p == FTN_PARAM_K && t == FTN_MATERIAL_METAL) { for (int c = 0; c < 3; ++c) fm.k[c] = v[c]; }
+        else if (p == FTN_PARAM_KR && (t == FTN_MATERIAL_MIRROR || t == FTN_MATERIAL_GLASS)) { for (int c = 0; c < 3; ++c) fm.kr[c] = v[c]; if (t == FTN_MATERIAL_MIRROR) fm.kd_texture = FTN_TEXTURE_CONSTANT; }
+        else if (p == FTN_PARAM_KT && t == FTN_MATERIAL_GLASS) { for (int c = 0; c < 3; ++c) fm.kt[c] = v[c]; }
+        else if (p == FTN_PARAM_UROUGHNESS && (t == FTN_MATERIAL_METAL || t == FTN_MATERIAL_GLASS || t == FTN_MATERIAL_PLASTIC)) fm.u_roughness = v[0];
+        else if (p == FTN_PARAM_VROUGHNESS && (t == FTN_MATERIAL_METAL || t == FTN_MATERIAL_GLASS)) fm.v_roughness = v[0];
+        else if (p == FTN_PARAM_SIGMA && t == FTN_MATERIAL_MATTE) fm.sigma = v[0];
+        else if (p == FTN_PARAM_INDEX && t == FTN_MATERIAL_GLASS) fm.eta[0] = v[0];
+        else folded = false;
+        if (folded) fm.param_texture[p] = 0;
+    }
+    return fm;
+}
+
 // Host side, shared by scene.cu and the host harness of the tests: the per-parameter texture ids, raw roughnesses and the
 // class of a matte whose sigma is textured.  `tex_is_image(k)` tells whether table entry k (1-based) is an image texture.
 template <class IsImage>

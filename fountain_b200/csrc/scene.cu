@@ -581,7 +581,7 @@ int scene_create(const FtnSceneDesc* d, FtnScene** out) {
     if ((rc = upload(&s->d_textures, texs.data(), texs.size())) != FTN_OK) return bail(rc);
     std::vector<MaterialData> mats(d->n_materials);
     for (uint32_t m = 0; m < d->n_materials; ++m) {
-        const FtnMaterial& fm = d->materials[m];
+        const FtnMaterial fm = fold_constant_param_textures(d->materials[m], d->textures, d->n_textures);
         MaterialData& md = mats[m];
         std::memset(&md, 0, sizeof(md));
         md.type = fm.type;

@@ -73,7 +73,7 @@ SIM_API int sim_scene_create(const FtnSceneDesc* d, SimScene** out) {
         if (s->texs[t].type == FTN_TEXTURE_IMAGE) s->texs[t].image = s->images.back().data();
     }
     for (uint32_t m = 0; m < d->n_materials; ++m) {
-        const FtnMaterial& fm = d->materials[m]; MaterialData md; std::memset(&md, 0, sizeof(md)); md.type = fm.type;
+        const FtnMaterial fm = fold_constant_param_textures(d->materials[m], d->textures, d->n_textures); MaterialData md; std::memset(&md, 0, sizeof(md)); md.type = fm.type;
         for (int c = 0; c < 3; ++c) { md.kd[c] = fm.kd[c]; md.ks[c] = fm.ks[c]; md.eta[c] = fm.eta[c]; md.k[c] = fm.k[c]; }
         float ur = fm.u_roughness, vr = fm.v_roughness;
         if (fm.type == FTN_MATERIAL_MIRROR) for (int c = 0; c < 3; ++c) md.kd[c] = fm.kr[c];   // Kr travels in the kd slot
