@@ -183,16 +183,69 @@ k_shade_miss(SceneView sc, PassParams pp, PathArrays pa, const uint32_t* __restr
 #define FTN_SHADE_LAUNCH_BOUNDS __launch_bounds__(128, FTN_SHADE_MIN_BLOCKS)
 // IMG: the scene holds an image texture -- only then is the mip lookup (and its call frame) compiled into the
 // matte / plastic / Oren-Nayar shaders, so scenes without one run the kernels they always ran
+// Software pipeline over the queue (FTN_SHADE_PREFETCH) -- an A/B experiment, measured and left OFF.  The shaders are
+// latency-bound at 4 blocks per SM: ncu's source page (profiles/r02_ncu_c4_shade_source.txt) puts 35-40 % of k_shade<metal>'s
+// stall samples on the head and the tail of the loop body -- queue[k] -> path -> six scattered state arrays -> the triangle
+// record, and the late uses of beta / L -- long-scoreboard waits on a chain that does not depend on the shading itself.
+// Levels: 1 = queue entries loaded three iterations ahead; 2 = + prefetch of the path state two iterations ahead; 3 = + the
+// triangle record of the next path.  B200 (profiles/r02_ab_shade_prefetch.txt): level 1 changes nothing (3.94 ms per launch on
+// C4), levels 2 / 3 cost 8 % on C4 (4.26 ms, L1 or L2 alike -- a prefetch moves whole lines where the loads move 32-byte
+// sectors, and the kernel already draws 24 % of the DRAM peak) and gain 5 % on the cache-resident C2.
+#ifndef FTN_SHADE_PREFETCH
+#define FTN_SHADE_PREFETCH 0
+#endif
+#ifndef FTN_SHADE_PREFETCH_L2
+#define FTN_SHADE_PREFETCH_L2 0
+#endif
+#if FTN_SHADE_PREFETCH_L2
+__device__ __forceinline__ void prefetch_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#else
+__device__ __forceinline__ void prefetch_line(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#endif
+__device__ __forceinline__ void prefetch_path_state(const PathArrays& pa, uint32_t path) {
+    prefetch_line(pa.ray_o + path); prefetch_line(pa.ray_d + path); prefetch_line(pa.beta + path); prefetch_line(pa.L + path);
+    prefetch_line(pa.hit + path); prefetch_line(pa.state + path);
+}
+__device__ __forceinline__ void prefetch_hit_record(const SceneView& sc, uint32_t slot) {
+    if (slot == FTN_NO_HIT_SLOT || (slot & FTN_SPHERE_SLOT_FLAG)) return;
+    const F4* t = sc.bvh.tris + (size_t)FTN_TRI_F4 * (size_t)slot;
+    prefetch_line(t); prefetch_line(t + 2);
+}
 template <int QUEUE, bool IMG = false>
 __global__ void FTN_SHADE_LAUNCH_BOUNDS
 k_shade(SceneView sc, PassParams pp, PathArrays pa, const uint32_t* __restrict__ queue, Queues qs, uint32_t* __restrict__ counts, uint32_t* __restrict__ err) {
     const uint32_t n = counts[QUEUE];
     const uint32_t n32 = (n + 31u) & ~31u;
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n32; k += gridDim.x * blockDim.x) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+#if FTN_SHADE_PREFETCH
+    uint32_t p0 = k < n ? queue[k] : 0u;                               // this iteration's path
+    uint32_t p1 = k + stride < n ? queue[k + stride] : 0u;            // n < 2^31 and stride < 2^23: no wrap below 2^32
+    uint32_t p2 = k + 2u * stride < n ? queue[k + 2u * stride] : 0u;
+#if FTN_SHADE_PREFETCH >= 2
+    if (k + stride < n) prefetch_path_state(pa, p1);
+#endif
+#endif
+    for (; k < n32; k += stride) {
         int t_active = -1, t_shadow = -1, t_mis = -1;
         uint32_t path = 0;
+#if FTN_SHADE_PREFETCH
+        const uint32_t k1 = k + stride, k2 = k + 2u * stride, k3 = k + 3u * stride;
+        const uint32_t p3 = k3 < n ? queue[k3] : 0u;                     // lands while this path is shaded
+#if FTN_SHADE_PREFETCH >= 2
+        if (k2 < n) prefetch_path_state(pa, p2);
+#endif
+#if FTN_SHADE_PREFETCH >= 3
+        if (k1 < n) prefetch_hit_record(sc, pa.hit[p1]);                 // p1's state was prefetched one iteration ago
+#endif
+        (void)k1; (void)k2;
+#endif
         if (k < n) {
+#if FTN_SHADE_PREFETCH
+            path = p0;
+#else
             path = queue[k];
+#endif
             const RayF ray = load_ray(pa, path);
             ShadeOut o;
             shade_surface<QUEUE == Q_NULL ? -1 : QUEUE - Q_MAT0, IMG>(sc, pp, path, ray, pa.hit[path], pa.state[path], ld3(pa.beta, path), ld3(pa.L, path), &o, err);
@@ -211,6 +264,9 @@ k_shade(SceneView sc, PassParams pp, PathArrays pa, const uint32_t* __restrict__
             }
         }
         queue_push3(qs, counts, t_active >= 0, t_shadow >= 0, t_mis >= 0, path);
+#if FTN_SHADE_PREFETCH
+        p0 = p1; p1 = p2; p2 = p3;
+#endif
     }
 }
 
@@ -329,10 +385,17 @@ struct Carver {
     template <class T> T* take(size_t count) { off = (off + 255) & ~(size_t)255; T* r = reinterpret_cast<T*>(p + off); off += count * sizeof(T); return r; }
 };
 
-// Paths per wavefront pass.  Measured on C2 (profiles/r01_ab_pass_size.txt): 4Mi -> 7.6 ms, 8Mi -> 6.7 ms,
-// 16Mi -> 6.0 ms per 16.8M-path step: every launch has a tail in which SMs idle, so fewer, larger
-// launches win; 16Mi paths cost 3.4 GB of the 180 GB.
-static size_t g_max_paths_per_pass = 16u << 20;
+// Paths per wavefront pass.  Every launch ends in a tail with idle SMs and every bounce in one host read-back, so
+// fewer, larger passes win: C2 (profiles/r01_ab_pass_size.txt) 4Mi -> 7.6 ms, 8Mi -> 6.7 ms, 16Mi -> 6.0 ms per
+// 16.8M-path step; C4 at 64 spp (profiles/r02_ab_pass_size.txt) 16Mi -> 4076, 32Mi -> 4252, 64Mi -> 4331 Mrays/s.
+// 64Mi paths take 14.8 GB of the 180 GB (220 B per path); a pass is halved until its workspace fits in what the
+// device has free (render_device), so a GPU that is shared or holds a 50M-triangle scene still renders.
+static size_t g_max_paths_per_pass = 64u << 20;
+// bytes of wavefront state for P paths over a film of fw x fh pixels and n_spix sample pixels
+static size_t pass_workspace_bytes(size_t P, size_t film_px, size_t n_spix) {
+    return 10 * (P * sizeof(float4) + 256) + 2 * (P * 4 + 256) + P * sizeof(float2) + 256 +
+           film_px * sizeof(float4) + 256 + (size_t)(Q_COUNT + 1) * (P * 4 + 256) + n_spix + 4096;
+}
 
 // CUDA-event pairs around every traversal / shading launch, per kernel class (0 extend, 1 shadow, 2 mis, 3 shade): the
 // live per-kernel durations bench.py's roofline uses.  Created only when the caller asks (FTN_STATS_TIME_KERNELS).
@@ -378,6 +441,19 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
     size_t max_paths = env_pp ? (size_t)strtoull(env_pp, nullptr, 10) : g_max_paths_per_pass;
     int s_per_pass = (int)std::max<size_t>(1, max_paths / std::max<size_t>(1, n_spix));
     s_per_pass = std::min(s_per_pass, std::max(1, n_samples));
+    if (s->device < 0 || s->device >= FTN_MAX_DEVICES) return set_error(FTN_ERR_INVALID_ARGUMENT, "device index out of range");
+    DeviceArena& arena = device_arena(s->device);
+    std::lock_guard<std::recursive_mutex> arena_lock(arena.m);
+    while (s_per_pass > 1 && n_spix * (size_t)s_per_pass >= (1ull << 31)) s_per_pass = (s_per_pass + 1) / 2;
+    if (pass_workspace_bytes(n_spix * (size_t)s_per_pass, (size_t)fw * fh, n_spix) > arena.bytes[DeviceArena::PATHS]) {
+        // the arena has to grow: shrink the pass until its workspace fits in what the arena already holds + 3/4 of the free
+        // memory (cudaMemGetInfo costs 0.7-6 ms on a process that holds GBs, so it is asked only here, not per render)
+        size_t free_b = 0, total_b = 0;
+        FTN_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const size_t budget = arena.bytes[DeviceArena::PATHS] + free_b / 4 * 3;
+        while (s_per_pass > 1 && pass_workspace_bytes(n_spix * (size_t)s_per_pass, (size_t)fw * fh, n_spix) > budget)
+            s_per_pass = (s_per_pass + 1) / 2;
+    }
     const size_t P = n_spix * (size_t)s_per_pass;
     if (P >= (1ull << 31)) return set_error(FTN_ERR_INVALID_ARGUMENT, "film too large for one pass");
 
@@ -386,11 +462,7 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
     const cudaEvent_t ev0 = g0.e, ev1 = g1.e, ev_counts = gc.e;
     FTN_CUDA(cudaEventRecord(ev0, st));
 
-    const size_t ws_bytes = 10 * (P * sizeof(float4) + 256) + 2 * (P * 4 + 256) + P * sizeof(float2) + 256 +
-                            (size_t)fw * fh * sizeof(float4) + 256 + (size_t)(Q_COUNT + 1) * (P * 4 + 256) + n_spix + 4096;
-    if (s->device < 0 || s->device >= FTN_MAX_DEVICES) return set_error(FTN_ERR_INVALID_ARGUMENT, "device index out of range");
-    DeviceArena& arena = device_arena(s->device);
-    std::lock_guard<std::recursive_mutex> arena_lock(arena.m);
+    const size_t ws_bytes = pass_workspace_bytes(P, (size_t)fw * fh, n_spix);
     Carver cv;
     FTN_TRY(arena.reserve(DeviceArena::PATHS, ws_bytes, "cudaMalloc (render workspace)", (void**)&cv.p));
     PathArrays pa;
@@ -416,7 +488,10 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
     for (const LightData& l : s->h_lights) if (l.type == 1 || l.type == FTN_LIGHT_TYPE_TRIANGLE) has_area = true;
     uint64_t camera_samples = 0;
     uint64_t class_rays[3] = {0, 0, 0};
-    const unsigned shade_grid = (unsigned)(sm_count() * 8);
+    // shade kernels: grid-stride loops over the class queues; FTN_SHADE_BLOCKS_PER_SM (A/B knob, default 8 = two waves of
+    // the 4 resident blocks)
+    const char* env_sb = getenv("FTN_SHADE_BLOCKS_PER_SM");
+    const unsigned shade_grid = (unsigned)(sm_count() * std::max(1, std::min(32, env_sb ? atoi(env_sb) : 8)));
     const int reach = (int)std::ceil(std::max(fg.radius[0], fg.radius[1]) + 0.5f);
     TraceTimer timer; timer.st = st; timer.on = (stat_flags & FTN_STATS_TIME_KERNELS) != 0u;
     uint32_t* h_counts = nullptr;           // pinned read-back slot of the queue counters, one per device
