@@ -42,6 +42,7 @@ struct PassParams {
 
 #define FTN_STATE_BOUNCES 0xFFFFu
 #define FTN_STATE_SPECULAR 0x10000u
+#define FTN_STATE_HAS_DIFF 0x20000u   /* direct-lighting integrator: the path carries the ray differential specular_reflect derived */
 
 // path id -> counter-sampler key.  path = sample_pixel * s_count + local sample; the global
 // pixel-sample index is ((y * xres) + x) * spp + s in RASTER coordinates (same in the oracle).
@@ -203,37 +204,66 @@ struct ShadeOut {
     uint32_t state;
     bool alive; V3 next_o, next_d;
     DirectOut direct;
+    bool has_diff; RayDiff diff;   // the differential of the mirrored ray (specular_reflect, integrator/mod.rs:59-83)
 };
 
-// Texture differentials of the hit (interaction.rs:117).  The path integrator hands the CAMERA ray's differential on
-// to every spawned ray unchanged (path.rs:73,79), so each hit of a path intersects the camera's two offset rays with
-// its own tangent plane; they are re-derived here from the path's camera sample instead of being carried.
-FTN_HD_COLD TexDiffs path_tex_differentials(const SceneView& sc, const PassParams& pp, uint32_t path, uint32_t slot, const RayF& ray, V3 p, V3 n) {
+// The camera ray's differential of this path (camera/mod.rs:145-205 scaled by 1/sqrt(spp), integrator/mod.rs:249-251),
+// re-derived from the path's camera sample instead of being carried.
+FTN_HD_COLD RayDiff path_camera_differential(const PassParams& pp, uint32_t path) {
     int x, y;
     const uint64_t key = path_sample_key(pp, path, &x, &y);
     const float fx = rn_add((float)x, sampler_uniform(key, 0)), fy = rn_add((float)y, sampler_uniform(key, 1));
     const float lx = sampler_uniform(key, 2), ly = sampler_uniform(key, 3), tu = sampler_uniform(key, 4);
     const RayF main_ray = camera_ray(pp.cam, fx, fy, lx, ly, tu);
-    const RayDiff df = camera_differential(pp.cam, main_ray, fx, fy, lx, ly, 1.0f / sqrtf((float)pp.spp));
+    return camera_differential(pp.cam, main_ray, fx, fy, lx, ly, 1.0f / sqrtf((float)pp.spp));
+}
+// Texture differentials of the hit (interaction.rs:117) from the ray's differential `df`.  The path integrator hands the
+// CAMERA ray's differential on to every spawned ray unchanged (path.rs:73,79), so each hit of a path intersects the camera's
+// two offset rays with its own tangent plane; the direct-lighting integrator uses the camera's at depth 0 and the mirrored
+// one behind a specular reflection.
+FTN_HD_COLD TexDiffs hit_tex_differentials(const SceneView& sc, uint32_t slot, const RayF& ray, V3 p, V3 n, const RayDiff& df,
+                                           V3* dpdx = nullptr, V3* dpdy = nullptr) {
     V3 dpdu, dpdv;
     if (slot & FTN_SPHERE_SLOT_FLAG) {
         SphereHit sh;
-        if (!sphere_intersect(sc.spheres[slot & ~FTN_SPHERE_SLOT_FLAG], ray, &sh)) { TexDiffs z; z.dudx = z.dvdx = z.dudy = z.dvdy = 0.0f; return z; }
+        if (!sphere_intersect(sc.spheres[slot & ~FTN_SPHERE_SLOT_FLAG], ray, &sh)) {
+            TexDiffs z; z.dudx = z.dvdx = z.dudy = z.dvdy = 0.0f;
+            if (dpdx) { *dpdx = v3s(0.0f); *dpdy = v3s(0.0f); }
+            return z;
+        }
         dpdu = sh.dpdu; dpdv = sh.dpdv;
     } else {
         triangle_dpduv(sc, slot, &dpdu, &dpdv);
     }
-    return tex_differentials(p, n, dpdu, dpdv, df);
+    return tex_differentials(p, n, dpdu, dpdv, df, dpdx, dpdy);
+}
+// specular_reflect's `ray.diff.map(...)`, integrator/mod.rs:59-83
+FTN_HD_COLD RayDiff reflect_differential(const SceneView& sc, uint32_t slot, const Surface& s, const RayDiff& df, const TexDiffs& td,
+                                         V3 dpdx, V3 dpdy, V3 wi) {
+    V3 dndu, dndv;
+    if (slot & FTN_SPHERE_SLOT_FLAG) sphere_dnduv(sc.spheres[slot & ~FTN_SPHERE_SLOT_FLAG], s.p, &dndu, &dndv);
+    else triangle_dnduv(sc, slot, &dndu, &dndv);
+    const V3 dndx = dndu * td.dudx + dndv * td.dvdx, dndy = dndu * td.dudy + dndv * td.dvdy;
+    const V3 dwo_dx = -df.rx_d - s.wo, dwo_dy = -df.ry_d - s.wo;
+    const float ddn_dx = dot(dwo_dx, s.ns) + dot(s.wo, dndx), ddn_dy = dot(dwo_dy, s.ns) + dot(s.wo, dndy);
+    const float two_won = 2.0f * dot(s.wo, s.ns);
+    RayDiff o;
+    o.rx_o = s.p + dpdx; o.ry_o = s.p + dpdy;
+    o.rx_d = (wi - dwo_dx) + dndx * two_won + s.ns * ddn_dx;
+    o.ry_d = (wi - dwo_dy) + dndy * two_won + s.ns * ddn_dy;
+    return o;
 }
 
 // `ray` is the ray that produced `slot`; state/beta/L are the path's values on entry.
 // MAT = the material class of the queue this path sits in (FtnMaterialType), or -1 for the
 // null-BSDF queue.
+// `carried`: the differential a specular reflection left on the path (direct-lighting integrator, FTN_STATE_HAS_DIFF), or null.
 template <int MAT, bool IMG = true>
 FTN_HD void shade_surface(const SceneView& sc, const PassParams& pp, uint32_t path, const RayF& ray, uint32_t slot,
-                          uint32_t state, V3 beta, V3 L, ShadeOut* out, uint32_t* err) {
+                          uint32_t state, V3 beta, V3 L, ShadeOut* out, uint32_t* err, const RayDiff* carried = nullptr) {
     out->L = L; out->beta = beta; out->state = state; out->alive = false;
     out->direct.has_shadow = false; out->direct.has_mis = false;
+    out->has_diff = false;
     Surface s;
     if (!surface_at_hit(sc, slot, ray, &s)) return;
     const int bounces = (int)(state & FTN_STATE_BOUNCES);
@@ -254,9 +284,22 @@ FTN_HD void shade_surface(const SceneView& sc, const PassParams& pp, uint32_t pa
     Bsdf bsdf;
     bsdf_init(&bsdf, s.ns, s.n, s.sdpdu);
     TexDiffs td; td.dudx = td.dvdx = td.dudy = td.dvdy = 0.0f;
-    if (IMG && sc.materials[s.material].uses_image
-        && !(direct_only && bounces > 0))   // stated deviation: no differentials behind a mirror under direct lighting
-        td = path_tex_differentials(sc, pp, path, slot, ray, s.p, s.n);
+    // the ray's differential at this hit: the camera's for every hit of the path integrator (path.rs:73,79) and at depth 0 of
+    // the direct-lighting integrator, the mirrored one behind its specular reflections (integrator/mod.rs:59-83)
+    RayDiff df; df.rx_o = df.rx_d = df.ry_o = df.ry_d = v3s(0.0f);
+    V3 dpdx = v3s(0.0f), dpdy = v3s(0.0f);
+    bool have_df = false;
+    if (IMG) {
+        const bool uses_image = sc.materials[s.material].uses_image != 0;
+        if (!direct_only) {
+            if (uses_image) td = hit_tex_differentials(sc, slot, ray, s.p, s.n, path_camera_differential(pp, path));
+        } else {
+            const bool chain_goes_on = bounces + 1 < pp.max_depth && LobeKind<M, 0>::value == 2;   // only the mirror has a specular lobe
+            if (bounces == 0) { if (uses_image || chain_goes_on) { df = path_camera_differential(pp, path); have_df = true; } }
+            else if (carried) { df = *carried; have_df = true; }
+            if (have_df && (uses_image || chain_goes_on)) td = hit_tex_differentials(sc, slot, ray, s.p, s.n, df, &dpdx, &dpdy);
+        }
+    }
     bool unsupported = false;
     material_bsdf<M, IMG>(sc, sc.materials[s.material], s.u, s.v, td, &bsdf, &unsupported);
     if (unsupported) { flag_error(err, ERR_UNSUPPORTED); return; }
@@ -275,6 +318,10 @@ FTN_HD void shade_surface(const SceneView& sc, const PassParams& pp, uint32_t pa
         out->alive = true; out->next_o = spawn_origin(s, rs.wi); out->next_d = rs.wi;
         out->beta = beta * (rs.f * fabsf(dot(rs.wi, s.ns)) / rs.pdf);
         out->state = (uint32_t)(bounces + 1);
+        if (IMG && have_df) {
+            out->has_diff = true; out->diff = reflect_differential(sc, slot, s, df, td, dpdx, dpdy, rs.wi);
+            out->state |= FTN_STATE_HAS_DIFF;
+        }
         return;
     }
     // continuation: Bsdf::sample_f(wo, get_2d(), ALL), path.rs:68-76

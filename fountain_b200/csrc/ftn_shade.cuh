@@ -849,9 +849,11 @@ FTN_HD bool solve_2x2(float a00, float a01, float a10, float a11, float b0, floa
 }
 FTN_HD float v3_at(V3 v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
 
-// SurfaceInteraction::compute_tex_differentials, interaction.rs:124-176 (None -> zeros, :117)
-FTN_HD TexDiffs tex_differentials(V3 p, V3 n, V3 dpdu, V3 dpdv, const RayDiff& df) {
+// SurfaceInteraction::compute_tex_differentials, interaction.rs:124-176 (None -> zeros, :117).  dpdx / dpdy (optional) are
+// TextureDifferentials::dpdx / dpdy, which specular_reflect needs (integrator/mod.rs:61-62); zero like the rest when a solve fails.
+FTN_HD TexDiffs tex_differentials(V3 p, V3 n, V3 dpdu, V3 dpdv, const RayDiff& df, V3* dpdx_out = nullptr, V3* dpdy_out = nullptr) {
     TexDiffs td; td.dudx = td.dvdx = td.dudy = td.dvdy = 0.0f;
+    if (dpdx_out) { *dpdx_out = v3s(0.0f); *dpdy_out = v3s(0.0f); }
     const float d = dot(n, p);
     const float tx = -(dot(n, df.rx_o) - d) / dot(n, df.rx_d), ty = -(dot(n, df.ry_o) - d) / dot(n, df.ry_d);
     const V3 dpdx = (df.rx_o + df.rx_d * tx) - p, dpdy = (df.ry_o + df.ry_d * ty) - p;
@@ -863,6 +865,7 @@ FTN_HD TexDiffs tex_differentials(V3 p, V3 n, V3 dpdu, V3 dpdv, const RayDiff& d
     if (!solve_2x2(v3_at(dpdu, d0), v3_at(dpdu, d1), v3_at(dpdv, d0), v3_at(dpdv, d1), v3_at(dpdx, d0), v3_at(dpdx, d1), &dudx, &dvdx)) return td;
     if (!solve_2x2(v3_at(dpdu, d0), v3_at(dpdu, d1), v3_at(dpdv, d0), v3_at(dpdv, d1), v3_at(dpdy, d0), v3_at(dpdy, d1), &dudy, &dvdy)) return td;
     td.dudx = dudx; td.dvdx = dvdx; td.dudy = dudy; td.dvdy = dvdy;
+    if (dpdx_out) { *dpdx_out = dpdx; *dpdy_out = dpdy; }
     return td;
 }
 
@@ -884,6 +887,58 @@ FTN_HD void triangle_dpduv(const SceneView& sc, uint32_t slot, V3* dpdu, V3* dpd
     const float inv = 1.0f / determinant;
     *dpdu = (dp02 * duv12y - dp12 * duv02y) * inv;
     *dpdv = (dp12 * duv02x - dp02 * duv12x) * inv;
+}
+
+// shading_geom.dndu / dndv of a triangle (triangle.rs:357-375): zero without vertex normals (:308-313); only specular_reflect's
+// ray differentials read them (integrator/mod.rs:65-66)
+FTN_HD void triangle_dnduv(const SceneView& sc, uint32_t slot, V3* dndu, V3* dndv) {
+    *dndu = v3s(0.0f); *dndv = v3s(0.0f);
+    if (!sc.nrm) return;
+    const uint32_t prim = f2u(ld4(sc.bvh.tris + (size_t)FTN_TRI_F4 * (size_t)slot).w);
+    const uint32_t v0 = sc.idx[3 * (size_t)prim], v1 = sc.idx[3 * (size_t)prim + 1], v2 = sc.idx[3 * (size_t)prim + 2];
+    float uv[3][2] = {{0.0f, 0.0f}, {1.0f, 0.0f}, {1.0f, 1.0f}};
+    if (sc.uv) {
+        uv[0][0] = sc.uv[2 * v0]; uv[0][1] = sc.uv[2 * v0 + 1]; uv[1][0] = sc.uv[2 * v1]; uv[1][1] = sc.uv[2 * v1 + 1];
+        uv[2][0] = sc.uv[2 * v2]; uv[2][1] = sc.uv[2 * v2 + 1];
+    }
+    const V3 n0 = V3(sc.nrm[3 * v0], sc.nrm[3 * v0 + 1], sc.nrm[3 * v0 + 2]);
+    const V3 n1 = V3(sc.nrm[3 * v1], sc.nrm[3 * v1 + 1], sc.nrm[3 * v1 + 2]);
+    const V3 n2 = V3(sc.nrm[3 * v2], sc.nrm[3 * v2 + 1], sc.nrm[3 * v2 + 2]);
+    const float duv02x = uv[0][0] - uv[2][0], duv02y = uv[0][1] - uv[2][1], duv12x = uv[1][0] - uv[2][0], duv12y = uv[1][1] - uv[2][1];
+    const float determinant = rn_sub(rn_mul(duv02x, duv12y), rn_mul(duv02y, duv12x));
+    if (fabsf(determinant) < 1.0e-8f) {
+        const V3 dn = cross(n2 - n0, n1 - n0);
+        if (dot(dn, dn) != 0.0f) coordinate_system(dn, dndu, dndv);   // `coordinate_system(dn)`: dn is NOT normalised there (:364)
+        return;
+    }
+    const float inv = 1.0f / determinant;
+    const V3 dn1 = n0 - n2, dn2 = n1 - n2;
+    *dndu = (dn1 * duv12y - dn2 * duv02y) * inv;
+    *dndv = (dn2 * duv02x - dn1 * duv12x) * inv;
+}
+// dndu / dndv of a sphere hit: the Weingarten equations of sphere.rs:160-178 on the object-space hit point, carried to world
+// space like normals (DiffGeom::transform, transform.rs:353-354).  The object-space point is recovered from the world-space
+// hit (tolerance-tested code, like everything that only feeds texture filtering).
+FTN_HD void sphere_dnduv(const SphereData& s, V3 p_world, V3* dndu, V3* dndv) {
+    V3 p = transform_point(s.w2o, p_world);
+    p = p * (s.radius / sqrtf(dot(p, p)));
+    if (p.x == 0.0f && p.y == 0.0f) p.x = 1.0e-5f * s.radius;
+    const float theta = acosf(clampf(p.z / s.radius, -1.0f, 1.0f));
+    const float inv_zr = 1.0f / sqrtf(p.x * p.x + p.y * p.y);
+    const float cos_phi = p.x * inv_zr, sin_phi = p.y * inv_zr;
+    const float dth = s.theta_max - s.theta_min;
+    const V3 dpdu = V3(-s.phi_max * p.y, s.phi_max * p.x, 0.0f);
+    const V3 dpdv = V3(p.z * cos_phi, p.z * sin_phi, -s.radius * sinf(theta)) * dth;
+    const V3 d2pduu = V3(p.x, p.y, 0.0f) * (-s.phi_max * s.phi_max);
+    const V3 d2pduv = V3(-sin_phi, cos_phi, 0.0f) * (dth * p.z * s.phi_max);
+    const V3 d2pdvv = p * (-dth * dth);
+    const float E = dot(dpdu, dpdu), F = dot(dpdu, dpdv), G = dot(dpdv, dpdv);
+    const V3 N = normalize(cross(dpdu, dpdv));
+    const float e = dot(N, d2pduu), f = dot(N, d2pduv), g = dot(N, d2pdvv);
+    const float inv_egf2 = 1.0f / (E * G - F * F);
+    const V3 du = dpdu * ((f * F - e * G) * inv_egf2) + dpdv * ((e * F - f * E) * inv_egf2);
+    const V3 dv = dpdu * ((g * F - f * G) * inv_egf2) + dpdv * ((f * F - g * E) * inv_egf2);
+    *dndu = transform_normal_inv(s.w2o, du); *dndv = transform_normal_inv(s.w2o, dv);
 }
 
 }  // namespace ftn

@@ -46,6 +46,8 @@ struct PathArrays {
     float4* mis_d;      // MIS ray dir
     float4* mis_w;      // weight rgb, light index (bits)
     float2* p_film;     // CameraSample.p_film
+    float4* diff[4];    // rx_origin, rx_dir, ry_origin, ry_dir of the ray differential a specular reflection left on the path
+                        // (FTN_STATE_HAS_DIFF); allocated only for the direct-lighting integrator on scenes with image textures
     uint8_t* spill;     // per sample pixel: some sample's footprint is not exactly its own pixel
 };
 
@@ -248,7 +250,17 @@ k_shade(SceneView sc, PassParams pp, PathArrays pa, const uint32_t* __restrict__
 #endif
             const RayF ray = load_ray(pa, path);
             ShadeOut o;
-            shade_surface<QUEUE == Q_NULL ? -1 : QUEUE - Q_MAT0, IMG>(sc, pp, path, ray, pa.hit[path], pa.state[path], ld3(pa.beta, path), ld3(pa.L, path), &o, err);
+            const uint32_t state = pa.state[path];
+            RayDiff cd; const RayDiff* carried = nullptr;
+            if (IMG && pa.diff[0] && (state & FTN_STATE_HAS_DIFF)) {
+                cd.rx_o = ld3(pa.diff[0], path); cd.rx_d = ld3(pa.diff[1], path); cd.ry_o = ld3(pa.diff[2], path); cd.ry_d = ld3(pa.diff[3], path);
+                carried = &cd;
+            }
+            shade_surface<QUEUE == Q_NULL ? -1 : QUEUE - Q_MAT0, IMG>(sc, pp, path, ray, pa.hit[path], state, ld3(pa.beta, path), ld3(pa.L, path), &o, err, carried);
+            if (IMG && o.has_diff) {
+                if (pa.diff[0]) { st3(pa.diff[0], path, o.diff.rx_o); st3(pa.diff[1], path, o.diff.rx_d); st3(pa.diff[2], path, o.diff.ry_o); st3(pa.diff[3], path, o.diff.ry_d); }
+                else o.state &= ~FTN_STATE_HAS_DIFF;
+            }
             st3(pa.L, path, o.L);
             if (o.direct.has_shadow) { st3(pa.sh_o, path, o.direct.sh_o); st3(pa.sh_d, path, o.direct.sh_d); st3(pa.sh_L, path, o.direct.sh_L); t_shadow = Q_SHADOW; }
             if (o.direct.has_mis) {
@@ -392,8 +404,8 @@ struct Carver {
 // device has free (render_device), so a GPU that is shared or holds a 50M-triangle scene still renders.
 static size_t g_max_paths_per_pass = 64u << 20;
 // bytes of wavefront state for P paths over a film of fw x fh pixels and n_spix sample pixels
-static size_t pass_workspace_bytes(size_t P, size_t film_px, size_t n_spix) {
-    return 10 * (P * sizeof(float4) + 256) + 2 * (P * 4 + 256) + P * sizeof(float2) + 256 +
+static size_t pass_workspace_bytes(size_t P, size_t film_px, size_t n_spix, bool with_diff) {
+    return (with_diff ? 14 : 10) * (P * sizeof(float4) + 256) + 2 * (P * 4 + 256) + P * sizeof(float2) + 256 +
            film_px * sizeof(float4) + 256 + (size_t)(Q_COUNT + 1) * (P * 4 + 256) + n_spix + 4096;
 }
 
@@ -444,14 +456,16 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
     if (s->device < 0 || s->device >= FTN_MAX_DEVICES) return set_error(FTN_ERR_INVALID_ARGUMENT, "device index out of range");
     DeviceArena& arena = device_arena(s->device);
     std::lock_guard<std::recursive_mutex> arena_lock(arena.m);
+    // ray differentials behind mirrors (integrator/mod.rs:59-83) only matter where a texture is filtered with them
+    const bool with_diff = integ->type == FTN_INTEGRATOR_DIRECT_LIGHTING && s->has_image_texture;
     while (s_per_pass > 1 && n_spix * (size_t)s_per_pass >= (1ull << 31)) s_per_pass = (s_per_pass + 1) / 2;
-    if (pass_workspace_bytes(n_spix * (size_t)s_per_pass, (size_t)fw * fh, n_spix) > arena.bytes[DeviceArena::PATHS]) {
+    if (pass_workspace_bytes(n_spix * (size_t)s_per_pass, (size_t)fw * fh, n_spix, with_diff) > arena.bytes[DeviceArena::PATHS]) {
         // the arena has to grow: shrink the pass until its workspace fits in what the arena already holds + 3/4 of the free
         // memory (cudaMemGetInfo costs 0.7-6 ms on a process that holds GBs, so it is asked only here, not per render)
         size_t free_b = 0, total_b = 0;
         FTN_CUDA(cudaMemGetInfo(&free_b, &total_b));
         const size_t budget = arena.bytes[DeviceArena::PATHS] + free_b / 4 * 3;
-        while (s_per_pass > 1 && pass_workspace_bytes(n_spix * (size_t)s_per_pass, (size_t)fw * fh, n_spix) > budget)
+        while (s_per_pass > 1 && pass_workspace_bytes(n_spix * (size_t)s_per_pass, (size_t)fw * fh, n_spix, with_diff) > budget)
             s_per_pass = (s_per_pass + 1) / 2;
     }
     const size_t P = n_spix * (size_t)s_per_pass;
@@ -462,7 +476,7 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
     const cudaEvent_t ev0 = g0.e, ev1 = g1.e, ev_counts = gc.e;
     FTN_CUDA(cudaEventRecord(ev0, st));
 
-    const size_t ws_bytes = pass_workspace_bytes(P, (size_t)fw * fh, n_spix);
+    const size_t ws_bytes = pass_workspace_bytes(P, (size_t)fw * fh, n_spix, with_diff);
     Carver cv;
     FTN_TRY(arena.reserve(DeviceArena::PATHS, ws_bytes, "cudaMalloc (render workspace)", (void**)&cv.p));
     PathArrays pa;
@@ -470,6 +484,7 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
     pa.sh_o = cv.take<float4>(P); pa.sh_d = cv.take<float4>(P); pa.sh_L = cv.take<float4>(P);
     pa.mis_o = cv.take<float4>(P); pa.mis_d = cv.take<float4>(P); pa.mis_w = cv.take<float4>(P);
     pa.hit = cv.take<uint32_t>(P); pa.state = cv.take<uint32_t>(P); pa.p_film = cv.take<float2>(P);
+    for (int i = 0; i < 4; ++i) pa.diff[i] = with_diff ? cv.take<float4>(P) : nullptr;
     pa.spill = cv.take<uint8_t>(n_spix);
     float4* accum = cv.take<float4>((size_t)fw * fh);
     Queues qs;

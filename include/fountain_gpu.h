@@ -117,10 +117,10 @@ typedef enum FtnMaterialType {
  * (AAMethod::None, the only one implemented, checkerboard.rs:54-64) or the uv debug texture (uv.rs), both
  * through UVMapping (mapping.rs:36-53: st = scale * uv + delta), or an image texture (image.rs:26-34): the
  * host hands over the MIPMap pyramid it built (mipmap.rs:78-143) and the device does lookup_trilinear
- * (mipmap.rs:245-279) with the camera ray's differentials (interaction.rs:124-176, camera/mod.rs:145-205,
- * scaled by 1/sqrt(spp), integrator/mod.rs:249); rays spawned at a surface carry none, so every later
- * hit filters level 0 bilinearly (width 0).  Deviation: the direct-lighting integrator's specular_reflect
- * propagates differentials through a mirror (integrator/mod.rs:59-83); here they are dropped there too. */
+ * (mipmap.rs:245-279) with the ray's differentials (interaction.rs:124-176): the camera ray's (camera/mod.rs:145-205,
+ * scaled by 1/sqrt(spp), integrator/mod.rs:249), which the path integrator hands on unchanged to every ray it
+ * spawns (path.rs:73,79), and under the direct-lighting integrator the differentials specular_reflect derives for
+ * the mirrored ray from the hit's dndu / dndv (integrator/mod.rs:59-83). */
 typedef enum FtnTextureType {
     FTN_TEXTURE_CONSTANT = 0,      /* texture/mod.rs:34-42: the value in the material's kd field */
     FTN_TEXTURE_CHECKERBOARD = 1,  /* tex1 where (floor(s) + floor(t)) % 2 == 0, else tex2 */

@@ -307,6 +307,7 @@ inline void compute_tex_differentials(SurfaceInteraction* si, const Differential
     Float ty = -(dot(n, diff.ry_origin) - d) / dot(n, diff.ry_dir);
     Point3 py = diff.ry_origin + ty * diff.ry_dir;
     Vec3 dpdx = px - si->hit.p, dpdy = py - si->hit.p;
+    si->dpdx = Vec3(0.0f, 0.0f, 0.0f); si->dpdy = Vec3(0.0f, 0.0f, 0.0f);   // unwrap_or_default (:117) when a solve below fails
     int d0, d1;
     if (std::fabs(n.x) > std::fabs(n.y) && std::fabs(n.x) > std::fabs(n.z)) { d0 = 1; d1 = 2; }
     else if (std::fabs(n.y) > std::fabs(n.z)) { d0 = 0; d1 = 2; }
@@ -316,6 +317,7 @@ inline void compute_tex_differentials(SurfaceInteraction* si, const Differential
     if (!solve_linear_system_2x2(A, dpdx[d0], dpdx[d1], &dudx, &dvdx)) return;
     if (!solve_linear_system_2x2(A, dpdy[d0], dpdy[d1], &dudy, &dvdy)) return;
     si->dudx = dudx; si->dvdx = dvdx; si->dudy = dudy; si->dvdy = dvdy;
+    si->dpdx = dpdx; si->dpdy = dpdy;
 }
 
 // SurfaceInteraction::compute_scattering_functions, interaction.rs:111-121
@@ -379,9 +381,9 @@ inline Spectrum path_incident_radiance(Ray ray, const Differential& diff, int ma
 // recursion of integrator/mod.rs:40-178: specular_reflect / specular_transmit sample the BSDF with
 // (REFLECTION | SPECULAR) / (TRANSMISSION | SPECULAR) and recurse with depth + 1.  sampler.get_2d()
 // is evaluated as an argument even when no such lobe exists (integrator/mod.rs:53,113).
-// DEVIATION (stated in include/fountain_gpu.h): specular_reflect derives new differentials for the mirrored ray
-// (integrator/mod.rs:59-83, needs dndu / dndv); this restatement and the device drop them there, so an image
-// texture seen through a mirror under this integrator is filtered at level 0.
+// specular_reflect derives the differentials of the mirrored ray from the incoming ones, the hit's texture differentials and
+// the shading geometry's dndu / dndv (integrator/mod.rs:59-83), so an image texture seen through a mirror is filtered with
+// the reflected footprint.
 inline Spectrum direct_incident_radiance(Ray ray, const Differential& diff, int max_depth, int depth, RenderCtx& cx, bool* unsupported_null) {
     const Scene& scene = *cx.scene;
     TraversalCounters* tc = cx.count_traversal ? &cx.ctr->trav : nullptr;
@@ -400,7 +402,19 @@ inline Spectrum direct_incident_radiance(Ray ray, const Differential& diff, int 
         cx.sampler->get_2d(&a, &b);   // specular_reflect, integrator/mod.rs:40-103
         ScatterSample s;
         if (bsdf.sample_f(si.wo, a, b, BXDF_REFLECTION | BXDF_SPECULAR, &s) && abs_dot(s.wi, si.shading_n) != 0.0f) {
-            Spectrum li = direct_incident_radiance(si.hit.spawn_ray(s.wi), Differential(), max_depth, depth + 1, cx, unsupported_null);
+            Differential nd;   // `ray.diff.map(...)`, integrator/mod.rs:59-83
+            if (diff.has) {
+                nd.has = true;
+                nd.rx_origin = si.hit.p + si.dpdx; nd.ry_origin = si.hit.p + si.dpdy;
+                Vec3 ns = si.shading_n, wo = si.wo;
+                Vec3 dndx = si.shading_dndu * si.dudx + si.shading_dndv * si.dvdx;
+                Vec3 dndy = si.shading_dndu * si.dudy + si.shading_dndv * si.dvdy;
+                Vec3 dwo_dx = -diff.rx_dir - wo, dwo_dy = -diff.ry_dir - wo;
+                Float dDN_dx = dot(dwo_dx, ns) + dot(wo, dndx), dDN_dy = dot(dwo_dy, ns) + dot(wo, dndy);
+                nd.rx_dir = (s.wi - dwo_dx) + 2.0f * dot(wo, ns) * dndx + dDN_dx * ns;
+                nd.ry_dir = (s.wi - dwo_dy) + 2.0f * dot(wo, ns) * dndy + dDN_dy * ns;
+            }
+            Spectrum li = direct_incident_radiance(si.hit.spawn_ray(s.wi), nd, max_depth, depth + 1, cx, unsupported_null);
             radiance = radiance + s.f * li * std::fabs(dot(s.wi, si.shading_n)) / s.pdf;
         }
         if (cx.sampler->mode == 0) cx.sampler->set_dim(DIM_CAMERA + DIM_PER_BOUNCE * (uint32_t)depth + 7);

@@ -34,7 +34,9 @@ struct SurfaceInteraction {
     Vec3 dpdu, dpdv;                 // geom
     Vec3 shading_n;
     Vec3 shading_dpdu, shading_dpdv; // shading_geom
+    Vec3 shading_dndu = Vec3(0.0f, 0.0f, 0.0f), shading_dndv = Vec3(0.0f, 0.0f, 0.0f);   // shading_geom.dndu / dndv (specular_reflect's differentials)
     Float dudx = 0.0f, dvdx = 0.0f, dudy = 0.0f, dvdy = 0.0f;   // tex_diffs (interaction.rs:193-215), default zero
+    Vec3 dpdx = Vec3(0.0f, 0.0f, 0.0f), dpdy = Vec3(0.0f, 0.0f, 0.0f);                     // tex_diffs.dpdx / dpdy
     int prim;                        // index into Scene::prims (insertion order), -1 = none
     Float b[3];                      // triangle barycentrics (oracle-side extra, for the parity tests)
 };
@@ -170,6 +172,17 @@ struct Triangle {
                 coordinate_system(ns, &ts, &ss);   // `let (ts, ss) = coordinate_system(ns.0)`
             }
             si->shading_dpdu = ss; si->shading_dpdv = ts;
+            {   // :357-375 dndu / dndv of the shading geometry
+                Vec3 dn1 = mesh->normals[v[0]] - mesh->normals[v[2]], dn2 = mesh->normals[v[1]] - mesh->normals[v[2]];
+                if (degenerate_uv) {
+                    Vec3 dn = cross(mesh->normals[v[2]] - mesh->normals[v[0]], mesh->normals[v[1]] - mesh->normals[v[0]]);
+                    if (magnitude2(dn) == 0.0f) { si->shading_dndu = Vec3(0.0f, 0.0f, 0.0f); si->shading_dndv = Vec3(0.0f, 0.0f, 0.0f); }
+                    else coordinate_system(dn, &si->shading_dndu, &si->shading_dndv);
+                } else {
+                    si->shading_dndu = (duv12[1] * dn1 - duv02[1] * dn2) * inv_det_uv;
+                    si->shading_dndv = (-duv12[0] * dn1 + duv02[0] * dn2) * inv_det_uv;
+                }
+            }
             si->shading_n = ns;
             si->hit.n = faceforward(si->hit.n, si->shading_n);   // :390
         }
@@ -280,9 +293,18 @@ struct Sphere {
         Vec3 dpdu(-phi_max * p_hit.y, phi_max * p_hit.x, 0.0f);
         Vec3 dpdv = (theta_max - theta_min) * Vec3(p_hit.z * cos_phi, p_hit.z * sin_phi, -radius * std::sin(theta));
         Vec3 N = normalize(cross(dpdu, dpdv));
+        // :160-178 Weingarten equations (N before the orientation flip)
+        Vec3 d2pduu = (-phi_max * phi_max) * Vec3(p_hit.x, p_hit.y, 0.0f);
+        Vec3 d2pduv = (theta_max - theta_min) * p_hit.z * phi_max * Vec3(-sin_phi, cos_phi, 0.0f);
+        Vec3 d2pdvv = -(theta_max - theta_min) * (theta_max - theta_min) * Vec3(p_hit.x, p_hit.y, p_hit.z);
+        Float E = dot(dpdu, dpdu), F = dot(dpdu, dpdv), G = dot(dpdv, dpdv);
+        Float e = dot(N, d2pduu), f = dot(N, d2pduv), g = dot(N, d2pdvv);
+        Float inv_egf2 = 1.0f / (E * G - F * F);
+        Vec3 dndu = (f * F - e * G) * inv_egf2 * dpdu + (e * F - f * E) * inv_egf2 * dpdv;
+        Vec3 dndv = (g * F - f * G) * inv_egf2 * dpdu + (f * F - g * E) * inv_egf2 * dpdv;
         Vec3 p_err = gamma(5) * vabs(p_hit);
         if (reverse_orientation) N = N * -1.0f;   // :183-185 (FIXME in the reference: ignores handedness)
-        // SurfaceInteraction::transform, transform.rs:374-389 (dndu/dndv unused downstream)
+        // SurfaceInteraction::transform, transform.rs:374-389
         const Transform& T = object_to_world;
         si->hit.p = point_tf_err_to_err(T.t, p_hit, p_err, &si->hit.p_err);
         si->hit.n = normalize(transform_normal(T, N));
@@ -292,6 +314,7 @@ struct Sphere {
         si->dpdu = transform_vector(T.t, dpdu); si->dpdv = transform_vector(T.t, dpdv);
         si->shading_n = normalize(transform_normal(T, N));
         si->shading_dpdu = si->dpdu; si->shading_dpdv = si->dpdv;
+        si->shading_dndu = transform_normal(T, dndu); si->shading_dndv = transform_normal(T, dndv);   // transform.rs:353-354
         si->b[0] = si->b[1] = si->b[2] = 0.0f;
         *t_out = t_shape_hit.v;
         return true;

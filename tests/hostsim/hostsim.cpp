@@ -403,6 +403,7 @@ SIM_API int sim_render(const SimScene* s, const FtnCamera* cam, const FtnFilm* f
             if (spills) spill[path / (uint32_t)pp.s_count] = 1;
             pfilm[path] = make_float2(fx, fy);
             V3 Lp = v3s(0.0f), beta = v3s(1.0f); uint32_t state = 0;
+            RayDiff cd; cd.rx_o = cd.rx_d = cd.ry_o = cd.ry_d = v3s(0.0f);   // PathArrays::diff of the kernels
             ++camera_samples;
             for (int it = 0; it < integ->max_depth + 2 + 4096; ++it) {
                 SceneHit h; TraceCounters tc; tc.nodes = tc.tris = 0;
@@ -416,14 +417,15 @@ SIM_API int sim_render(const SimScene* s, const FtnCamera* cam, const FtnFilm* f
                 ShadeOut o;
                 const int material = hit_material(sc, h.slot);   // the queue k_extend would bin this path into
                 const int mclass = material < 0 ? -1 : sc.materials[material].type;
+                const RayDiff* carried = (state & FTN_STATE_HAS_DIFF) ? &cd : nullptr;
                 switch (mclass) {   // k_shade<QUEUE>
-                    case FTN_MATERIAL_MATTE: shade_surface<FTN_MATERIAL_MATTE>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err); break;
-                    case FTN_MATERIAL_METAL: shade_surface<FTN_MATERIAL_METAL>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err); break;
-                    case FTN_MATERIAL_PLASTIC: shade_surface<FTN_MATERIAL_PLASTIC>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err); break;
-                    case FTN_MATERIAL_MIRROR: shade_surface<FTN_MATERIAL_MIRROR>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err); break;
-                    case FTN_MATERIAL_GLASS: shade_surface<FTN_MATERIAL_GLASS>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err); break;
-                    case FTN_CLASS_OREN_NAYAR: shade_surface<FTN_CLASS_OREN_NAYAR>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err); break;
-                    default: shade_surface<-1>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err); break;
+                    case FTN_MATERIAL_MATTE: shade_surface<FTN_MATERIAL_MATTE>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err, carried); break;
+                    case FTN_MATERIAL_METAL: shade_surface<FTN_MATERIAL_METAL>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err, carried); break;
+                    case FTN_MATERIAL_PLASTIC: shade_surface<FTN_MATERIAL_PLASTIC>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err, carried); break;
+                    case FTN_MATERIAL_MIRROR: shade_surface<FTN_MATERIAL_MIRROR>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err, carried); break;
+                    case FTN_MATERIAL_GLASS: shade_surface<FTN_MATERIAL_GLASS>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err, carried); break;
+                    case FTN_CLASS_OREN_NAYAR: shade_surface<FTN_CLASS_OREN_NAYAR>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err, carried); break;
+                    default: shade_surface<-1>(sc, pp, path, ray, h.slot, state, beta, Lp, &o, &err, carried); break;
                 }
                 Lp = o.L;
                 if (o.direct.has_shadow) {   // k_shadow
@@ -440,6 +442,7 @@ SIM_API int sim_render(const SimScene* s, const FtnCamera* cam, const FtnFilm* f
                     if (!is_black(inc)) Lp = Lp + o.direct.mis_w * inc;
                 }
                 if (!o.alive) break;
+                if (o.has_diff) cd = o.diff;
                 ray.o = o.next_o; ray.d = o.next_d; ray.t_max = FTN_INF; beta = o.beta; state = o.state;
             }
             L[path] = make_float4(Lp.x, Lp.y, Lp.z, 0.0f);

@@ -286,6 +286,25 @@ def test_mirror_textured_kr_closed_form(gpu_backend):
     mirror_kr_closed_form(gpu_backend)
 
 
+# ---- ray differentials behind a mirror under the direct-lighting integrator (integrator/mod.rs:59-83) -------------------
+def test_mirror_differentials_closed_form(gpu_backend):
+    """A flat mirror unfolds the path: the ceiling seen in it is filtered at the level of a camera h_cam + h_ceiling away."""
+    from tests.test_oracle_render import mirror_differentials_closed_form
+    mirror_differentials_closed_form(gpu_backend, uscales=(1.0, 3.0, 11.0, 40.0))
+
+
+@pytest.mark.parametrize("depth", [2, 4])
+def test_mirrored_image_texture_matches_oracle(gpu_backend, orc_backend, depth):
+    """A splayed-normal mirror quad (triangle dndu / dndv) and a mirror sphere (Weingarten dndu / dndv) over the image-textured
+    floor: the differentials specular_reflect derives select the same mip levels as the oracle's."""
+    integrator = api.DirectLightingIntegrator(depth)
+    a, apx, _ = parity.render(gpu_backend, scenes.mirrored_image_texture_scene, integrator, 16, seed=21, resolution=(96, 96))
+    b, bpx, _ = parity.render(orc_backend, scenes.mirrored_image_texture_scene, integrator, 16, seed=21, resolution=(96, 96))
+    mean_rel, frac_off = parity.image_diff(a, b)
+    assert mean_rel < 2e-3 and frac_off < 0.02, (mean_rel, frac_off)
+    assert np.array_equal(apx[..., 3], bpx[..., 3])
+
+
 def test_scene_pool_does_not_grow_and_is_released(gpu_backend):
     """Scene buffers come from the device's stream-ordered pool: creating and destroying the same scene over and over
     must reuse the pooled memory (no growth), results stay identical, and ftn_release_cached_memory gives it back."""

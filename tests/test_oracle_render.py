@@ -319,3 +319,32 @@ def mirror_kr_closed_form(backend):
 
 def test_mirror_textured_kr_closed_form(orc_backend):
     mirror_kr_closed_form(orc_backend)
+
+
+# ---- ray differentials behind a mirror under the direct-lighting integrator (integrator/mod.rs:59-83) -------------------
+# No reference test renders one.  Closed form: a flat mirror unfolds the path, so the ceiling seen in a mirror on the floor
+# is filtered with the footprint of a camera h_cam + h_ceiling away (the level formula of the floor test above); the radiance
+# is Kr * c(level) / pi * L * cos(60 deg).  Without the mirrored differentials the lookup would be bilinear at level 0 (c = .1).
+def mirror_differentials_closed_form(backend, uscales=(1.0, 3.0, 11.0)):
+    mp = constant_level_mipmap()
+    n = len(mp.levels)
+    for uscale in uscales:
+        tex = api.ImageTexture(mp, api.UVMapping(uscale, uscale, 0.3, 0.1))
+        scene, camera, film = scenes.mirror_ceiling_probe(backend=backend, texture=tex)
+        api.SamplerIntegrator(camera, api.DirectLightingIntegrator(3)).render_parallel(scene, film, api.RandomSampler.new_with_seed(4, 0))
+        rgb = film.into_spectrum_buffer()[0]
+        level = min(max(expected_mip_level(n, uscale, 0.5, 5, 30.0, 4), 0.0), n - 1.0)
+        assert level > 0.5                                     # the case tells the mirrored footprint from a point lookup
+        assert np.allclose(rgb, (0.1 + 0.1 * level) / np.pi * 3.0 * 0.5, rtol=3e-3), (uscale, level, rgb[:2])
+
+
+def test_mirror_differentials_closed_form(orc_backend):
+    mirror_differentials_closed_form(orc_backend)
+
+
+def test_mirror_differentials_stop_with_the_recursion(orc_backend):
+    """max_depth 1: specular_reflect is not called (direct_lighting.rs:93), the mirror is black."""
+    mp = constant_level_mipmap()
+    scene, camera, film = scenes.mirror_ceiling_probe(backend=orc_backend, texture=api.ImageTexture(mp, api.UVMapping(3.0, 3.0, 0.0, 0.0)))
+    api.SamplerIntegrator(camera, api.DirectLightingIntegrator(1)).render_parallel(scene, film, api.RandomSampler.new_with_seed(2, 0))
+    assert np.all(film.into_spectrum_buffer()[0] == 0.0)

@@ -477,3 +477,47 @@ def textured_params_scene(backend=None, resolution=(48, 48), variant="table"):
     camera = api.PerspectiveCamera(cam_to_world, resolution, fov=50.0)
     film = api.Film(resolution, backend=backend)
     return scene, camera, film
+
+
+# ---- ray differentials behind a mirror (specular_reflect, integrator/mod.rs:59-83) -------------------------------
+def mirror_ceiling_probe(backend=None, texture=None, xy=(0.3, -0.2), h_cam=10.0, h_ceiling=20.0, resolution=(5, 5), fov=0.5):
+    """A narrow camera looks straight down at a small flat mirror (Kr 1) in the plane z = 0; the mirror shows a textured
+    matte ceiling at z = h_ceiling > h_cam (uv = world (x, y)) lit by a distant light from below at 60 degrees (its shadow rays pass
+    beside the mirror).  Unfolded, the camera sees the ceiling from h_cam + h_ceiling away: with the mirrored differentials
+    the texture footprint is that of the unfolded path; without them it would be a point."""
+    def quad(z, half, flip):
+        v = np.array([[-half, -half, z], [half, -half, z], [half, half, z], [-half, half, z]], np.float32)
+        idx = np.array([0, 2, 1, 0, 3, 2] if flip else [0, 1, 2, 0, 2, 3], np.uint32)
+        return api.TriangleMesh(Transform.identity(), idx, v, tex_coords=v[:, :2].copy())
+    prims = [api.GeometricPrimitive(quad(0.0, 1.0, False), api.MirrorMaterial((1.0, 1.0, 1.0))),
+             api.GeometricPrimitive(quad(h_ceiling, 30.0, True), api.MatteMaterial(texture))]
+    lights = [api.DistantLight.from_params(L=3.0, from_=(np.sqrt(3.0), 0.0, -1.0), to=(0.0, 0.0, 0.0))]
+    scene = api.Scene(prims, lights, backend=backend)
+    cam_to_world = Transform.look_at((xy[0], xy[1], h_cam), (xy[0], xy[1], 0.0), (0, 1, 0)).inverse()
+    camera = api.PerspectiveCamera(cam_to_world, resolution, fov=fov)
+    film = api.Film(resolution, backend=backend)
+    return scene, camera, film
+
+
+def mirrored_image_texture_scene(backend=None, resolution=(48, 48), wrap="repeat"):
+    """The image-textured floor of image_texture_scene seen directly and in two mirrors: a quad whose vertex normals are
+    splayed (a convex mirror: dndu / dndv of triangle.rs:357-375 are not zero) and a sphere (sphere.rs:160-178), so the
+    texture is filtered with footprints that the reflections widened."""
+    tex = api.ImageTexture(api.MIPMap(procedural_image(), wrap), api.UVMapping(0.25, 0.375, 0.1, 0.2))
+    v = np.array([[-6, -6, 0], [6, -6, 0], [6, 6, 0], [-6, 6, 0]], np.float32)
+    up = np.tile(np.array([[0, 0, 1]], np.float32), (4, 1))
+    floor = api.TriangleMesh(Transform.identity(), np.array([0, 1, 2, 0, 2, 3], np.uint32), v, normals=up, tex_coords=v[:, :2].copy())
+    mv = np.array([[-3.5, 3, 0.05], [0.5, 3, 0.05], [0.5, 3, 3.5], [-3.5, 3, 3.5]], np.float32)
+    mn = np.array([[-0.35, -1, -0.3], [0.35, -1, -0.3], [0.35, -1, 0.3], [-0.35, -1, 0.3]], np.float32)
+    mn /= np.linalg.norm(mn, axis=1, keepdims=True)
+    mirror = api.TriangleMesh(Transform.identity(), np.array([0, 1, 2, 0, 2, 3], np.uint32), mv, normals=mn, tex_coords=mv[:, [0, 2]].copy())
+    ball = api.Sphere(Transform.translate((2.6, 0.5, 1.1)), radius=1.1)
+    prims = [api.GeometricPrimitive(floor, api.MatteMaterial(tex)),
+             api.GeometricPrimitive(mirror, api.MirrorMaterial((0.9, 0.9, 0.9))),
+             api.GeometricPrimitive(ball, api.MirrorMaterial((0.8, 0.85, 0.9)))]
+    lights = [api.DistantLight.from_params(L=2.5, from_=(0.3, -0.4, 1.0), to=(0.0, 0.0, 0.0)), api.InfiniteAreaLight.new_uniform(0.3)]
+    scene = api.Scene(prims, lights, backend=backend)
+    cam_to_world = Transform.look_at((0, -8.5, 2.2), (0, 1, 0.9), (0, 0, 1)).inverse()
+    camera = api.PerspectiveCamera(cam_to_world, resolution, fov=50.0)
+    film = api.Film(resolution, backend=backend)
+    return scene, camera, film
