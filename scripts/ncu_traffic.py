@@ -1,7 +1,9 @@
 """Turns an ncu per-launch metrics CSV (scripts/gpu_r2_final.sh) + the bench line of the same command into the record
 bench.py's roofline uses: warp instructions, ALU / FMA-pipe instructions and DRAM bytes PER RAY of one kernel of one
 workload, stamped with the commit and the files they were read from.  usage:
-  ncu_traffic.py <workload> <kernel-key> <kernel-name-regex> <metrics.csv> <rays-per-render> <renders-captured> <source-note>"""
+  ncu_traffic.py <workload> <kernel-key> <kernel-name-regex> <metrics.csv> <rays-per-render> <renders-captured> <source-note> [<separator-regex> <segment> [<max-launches>]]
+With a separator regex the launch list is cut into segments at every launch whose name matches it (bench.py --workload c3 runs one
+COUNTING launch before the timed launches of each ray batch) and only the launches of segment <segment> (0-based) are used."""
 import csv
 import json
 import os
@@ -11,6 +13,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 workload, key, name_re, csv_path, rays, renders, note = sys.argv[1:8]
+sep_re, segment = (sys.argv[8], int(sys.argv[9])) if len(sys.argv) > 9 else (None, 0)
+max_launches = int(sys.argv[10]) if len(sys.argv) > 10 else 0   # only the first launches of the segment (what follows is another input)
 rays, renders = float(rays), float(renders)
 rows = []
 with open(csv_path, newline="") as f:
@@ -21,8 +25,17 @@ iname, imetric, ivalue, iunit = hdr.index("Kernel Name"), hdr.index("Metric Name
 iid = hdr.index("ID")
 acc, launches = {}, set()
 pct = {}
+seg, last_sep_id = -1 if sep_re else 0, None
 for row in r[1:]:
-    if len(row) <= ivalue or not re.search(name_re, row[iname]):
+    if len(row) <= ivalue:
+        continue
+    if sep_re and re.search(sep_re, row[iname]):
+        if row[iid] != last_sep_id:
+            seg += 1; last_sep_id = row[iid]
+        continue
+    if seg != segment or not re.search(name_re, row[iname]):
+        continue
+    if max_launches and row[iid] not in launches and len(launches) >= max_launches:
         continue
     launches.add(row[iid])
     v = float(row[ivalue].replace(",", ""))
@@ -34,9 +47,17 @@ for row in r[1:]:
     else:
         acc[m] = acc.get(m, 0.0) + v * scale
 n = max(1, len(launches))
+mean = {m: sum(v) / len(v) for m, v in pct.items()}
+lsu = mean.get("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", 0.0)
+issue = mean.get("sm__inst_issued.avg.pct_of_peak_sustained_active", 0.0)
+alu = mean.get("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", 0.0)
+# the limiter ncu names: the busier of instruction issue and the L1 data pipe (DRAM stays below 25 % everywhere)
+bound = "l1-lsu" if lsu > issue else ("sm-issue (ALU pipe)" if alu > 0.8 * issue else "sm-issue")
+if renders == 0:            # one launch = one pass over the batch (bench.py --workload c3)
+    renders = float(n)
 total_rays = rays * renders
 rec = {
-    "bound": "sm-issue (ALU pipe)",
+    "bound": bound,
     "warp_inst_per_ray": acc.get("smsp__inst_executed.sum", 0.0) / total_rays,
     "alu_pipe_inst_per_ray": acc.get("sm__inst_executed_pipe_alu.sum", 0.0) / total_rays,
     "fma_pipe_inst_per_ray": acc.get("sm__inst_executed_pipe_fma.sum", 0.0) / total_rays,
