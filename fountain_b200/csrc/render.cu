@@ -320,25 +320,55 @@ struct MisSource {
         return true;
     }
 };
+// FTN_MIS_RESOLVE = 1 (default): the traversal kernel only records the slot the MIS ray found (in PathArrays::hit, which the
+// shade stage of this bounce has already consumed) and k_mis_resolve looks the radiance up afterwards with full warps.
+// Inlined into the sink (= 0, round 1) the environment lookup (acos / atan2 / four texel fetches) ran on the few lanes that
+// had just finished, inside an issue-bound kernel, and its registers cost the persistent loop two resident blocks per SM
+// (94-96 registers -> 5 blocks instead of 7; profiles/r02_ab_mis_resolve.txt).
+#ifndef FTN_MIS_RESOLVE
+#define FTN_MIS_RESOLVE 1
+#endif
+// FTN_MIS_MIN_BLOCKS (A/B, with FTN_MIS_RESOLVE = 0): cap k_mis's registers for that many resident blocks instead
 struct MisSink {
     SceneView sc; PathArrays pa; const uint32_t* queue;
     __device__ __forceinline__ void store(bool valid, uint32_t k, const RayF& ray, const SceneHit& h) const {
         if (!valid) return;
         const uint32_t path = queue[k];
+#if FTN_MIS_RESOLVE
+        pa.hit[path] = h.slot;
+#else
         const float4 w4 = pa.mis_w[path];
         const V3 incident = mis_incident(sc, sc.lights[f2u(w4.w)], ray, h.slot);
         if (!is_black(incident)) st3(pa.L, path, ld3(pa.L, path) + V3(w4.x, w4.y, w4.z) * incident);
+#endif
     }
 };
+#if defined(FTN_MIS_MIN_BLOCKS)
+#define FTN_MIS_LAUNCH_BOUNDS __launch_bounds__(FTN_TRACE_THREADS, FTN_MIS_MIN_BLOCKS)
+#else
+#define FTN_MIS_LAUNCH_BOUNDS FTN_TRACE_LAUNCH_BOUNDS
+#endif
 // ENV_ONLY: with only infinite lights a hit contributes nothing whatever it is, so any-hit suffices
 template <bool ENV_ONLY, bool COUNT, bool SPH, int MODE>
-__global__ void FTN_TRACE_LAUNCH_BOUNDS
+__global__ void FTN_MIS_LAUNCH_BOUNDS
 k_mis(SceneView sc, PathArrays pa, const uint32_t* __restrict__ queue, uint32_t* __restrict__ counts, unsigned long long* __restrict__ trav) {
     MisSource src; src.pa = pa; src.queue = queue;
     MisSink sink; sink.sc = sc; sink.pa = pa; sink.queue = queue;
     TraceCounters tc; tc.nodes = 0; tc.tris = 0;
     trace_persistent<ENV_ONLY, COUNT, SPH, MODE>(sc, counts[Q_MIS], &counts[W_MIS], src, sink, tc);
     if (COUNT) flush_trace_counters(tc, trav);
+}
+// Radiance arriving along the MIS rays of this bounce (integrator/mod.rs:364-389), one thread per ray of the MIS queue
+__global__ void __launch_bounds__(256)
+k_mis_resolve(SceneView sc, PathArrays pa, const uint32_t* __restrict__ queue, const uint32_t* __restrict__ counts) {
+    const uint32_t n = counts[Q_MIS];
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint32_t path = queue[k];
+        const float4 w4 = pa.mis_w[path];
+        RayF ray; ray.o = ld3(pa.mis_o, path); ray.d = ld3(pa.mis_d, path); ray.t_max = FTN_INF; ray.time = pa.ray_o[path].w;
+        const V3 incident = mis_incident(sc, sc.lights[f2u(w4.w)], ray, pa.hit[path]);
+        if (!is_black(incident)) st3(pa.L, path, ld3(pa.L, path) + V3(w4.x, w4.y, w4.z) * incident);
+    }
 }
 
 // ---- film ---------------------------------------------------------------------------------------------------------------
@@ -592,8 +622,12 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
             timer.begin(2);
             if (has_area) { FTN_MODE3(tmode, FTN_BOOL2(count_traversal, sph, (k_mis<false, B0, B1, M><<<gq, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts, d_trav + 4)))); }
             else { FTN_MODE3(tmode, FTN_BOOL2(count_traversal, sph, (k_mis<true, B0, B1, M><<<gq, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts, d_trav + 4)))); }
-            timer.end();
             FTN_LAUNCHED();
+#if FTN_MIS_RESOLVE
+            k_mis_resolve<<<shade_grid, 256, 0, st>>>(sc, pa, q.q[Q_MIS], counts);
+            FTN_LAUNCHED();
+#endif
+            timer.end();
             FTN_CUDA(cudaEventSynchronize(ev_counts));
             const uint32_t* hc = h_counts;
             class_rays[1] += hc[Q_SHADOW];
