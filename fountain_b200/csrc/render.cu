@@ -21,12 +21,36 @@
 #include <algorithm>
 #include <cstring>
 #include <cmath>
+#include <map>
 #include <mutex>
 
 namespace ftn {
 
 int sm_count();
 unsigned trace_grid(size_t n, int blocks_per_sm);
+// Persistent grid of one traversal-kernel instantiation: as many blocks per SM as the kernel's registers / shared memory
+// really allow (64 registers -> 8 blocks of 128 threads, 72 -> 7; asked from the runtime once per instantiation), capped by
+// the work.  A fixed 7 left the 64-register BVH8q kernels one block per SM short (profiles/r02_ab_trace_grid.txt).
+template <class Kernel>
+static unsigned persistent_grid(Kernel kernel, size_t n) {
+    // keyed by the kernel's ADDRESS (instantiations of one template share a function type); every device of a box is the same GPU
+    static std::mutex m;
+    static std::map<const void*, int> cache;
+    int blocks;
+    {
+        std::lock_guard<std::mutex> lock(m);
+        auto it = cache.find((const void*)kernel);
+        if (it == cache.end()) {
+            int b = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, FTN_TRACE_THREADS, 0) != cudaSuccess || b < 1) { cudaGetLastError(); b = FTN_TRACE8_BLOCKS_PER_SM; }
+            const char* cap = getenv("FTN_TRACE_MAX_BLOCKS_PER_SM");   // A/B knob
+            if (cap && atoi(cap) > 0 && b > atoi(cap)) b = atoi(cap);
+            it = cache.emplace((const void*)kernel, b).first;
+        }
+        blocks = it->second;
+    }
+    return trace_grid(n, blocks);
+}
 
 enum { Q_ACTIVE_OUT = 0, Q_MISS, Q_NULL, Q_MAT0, Q_MAT1, Q_MAT2, Q_MAT3, Q_MAT4, Q_MAT5, Q_SHADOW, Q_MIS, Q_COUNT };
 static_assert(Q_MAT5 - Q_MAT0 + 1 == FTN_N_CLASSES, "one shade queue per material class");
@@ -256,12 +280,14 @@ k_shade(SceneView sc, PassParams pp, PathArrays pa, const uint32_t* __restrict__
                 cd.rx_o = ld3(pa.diff[0], path); cd.rx_d = ld3(pa.diff[1], path); cd.ry_o = ld3(pa.diff[2], path); cd.ry_d = ld3(pa.diff[3], path);
                 carried = &cd;
             }
-            shade_surface<QUEUE == Q_NULL ? -1 : QUEUE - Q_MAT0, IMG>(sc, pp, path, ray, pa.hit[path], state, ld3(pa.beta, path), ld3(pa.L, path), &o, err, carried);
+            // L enters as 0: the stage only ADDS the hit's own emission (beta * Le), so the path's radiance is read and
+            // written back only where that is not black -- L_old + (0 + beta Le) is the sum the reference forms
+            shade_surface<QUEUE == Q_NULL ? -1 : QUEUE - Q_MAT0, IMG>(sc, pp, path, ray, pa.hit[path], state, ld3(pa.beta, path), v3s(0.0f), &o, err, carried);
             if (IMG && o.has_diff) {
                 if (pa.diff[0]) { st3(pa.diff[0], path, o.diff.rx_o); st3(pa.diff[1], path, o.diff.rx_d); st3(pa.diff[2], path, o.diff.ry_o); st3(pa.diff[3], path, o.diff.ry_d); }
                 else o.state &= ~FTN_STATE_HAS_DIFF;
             }
-            st3(pa.L, path, o.L);
+            if (!is_black(o.L)) st3(pa.L, path, ld3(pa.L, path) + o.L);
             if (o.direct.has_shadow) { st3(pa.sh_o, path, o.direct.sh_o); st3(pa.sh_d, path, o.direct.sh_d); st3(pa.sh_L, path, o.direct.sh_L); t_shadow = Q_SHADOW; }
             if (o.direct.has_mis) {
                 st3(pa.mis_o, path, o.direct.mis_o); st3(pa.mis_d, path, o.direct.mis_d);
@@ -565,9 +591,8 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
         for (int it = 0; it < iter_cap && n_active > 0; ++it) {
             FTN_CUDA(cudaMemsetAsync(counts, 0, CTR_COUNT * 4, st));
             Queues q = qs; q.q[Q_ACTIVE_OUT] = q_out;
-            const unsigned ge = trace_grid(n_active, sc.bvh.wide ? FTN_TRACE8_BLOCKS_PER_SM : FTN_TRACE_BLOCKS_PER_SM);
             timer.begin(0);
-            FTN_MODE3(tmode, FTN_BOOL2(count_traversal, sph, (k_extend<B0, B1, M><<<ge, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q_in, n_active, q, counts, d_trav, integ->type == FTN_INTEGRATOR_DIRECT_LIGHTING))));
+            FTN_MODE3(tmode, FTN_BOOL2(count_traversal, sph, (k_extend<B0, B1, M><<<persistent_grid(k_extend<B0, B1, M>, n_active), FTN_TRACE_THREADS, 0, st>>>(sc, pa, q_in, n_active, q, counts, d_trav, integ->type == FTN_INTEGRATOR_DIRECT_LIGHTING))));
             timer.end();
             FTN_LAUNCHED();
             class_rays[0] += n_active;
@@ -614,14 +639,13 @@ int render_device(const FtnScene* s, const FtnCamera* cam, const FtnFilm* film, 
             //  shadow / MIS kernels are already queued when the host wakes up)
             FTN_CUDA(cudaMemcpyAsync(h_counts, counts, CTR_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             FTN_CUDA(cudaEventRecord(ev_counts, st));
-            const unsigned gq = trace_grid(n_active, sc.bvh.wide ? FTN_TRACE8_BLOCKS_PER_SM : FTN_TRACE_BLOCKS_PER_SM);
             timer.begin(1);
-            FTN_MODE3(tmode, FTN_BOOL2(count_traversal, sph, (k_shadow<B0, B1, M><<<gq, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_SHADOW], counts, d_trav + 2))));
+            FTN_MODE3(tmode, FTN_BOOL2(count_traversal, sph, (k_shadow<B0, B1, M><<<persistent_grid(k_shadow<B0, B1, M>, n_active), FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_SHADOW], counts, d_trav + 2))));
             timer.end();
             FTN_LAUNCHED();
             timer.begin(2);
-            if (has_area) { FTN_MODE3(tmode, FTN_BOOL2(count_traversal, sph, (k_mis<false, B0, B1, M><<<gq, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts, d_trav + 4)))); }
-            else { FTN_MODE3(tmode, FTN_BOOL2(count_traversal, sph, (k_mis<true, B0, B1, M><<<gq, FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts, d_trav + 4)))); }
+            if (has_area) { FTN_MODE3(tmode, FTN_BOOL2(count_traversal, sph, (k_mis<false, B0, B1, M><<<persistent_grid(k_mis<false, B0, B1, M>, n_active), FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts, d_trav + 4)))); }
+            else { FTN_MODE3(tmode, FTN_BOOL2(count_traversal, sph, (k_mis<true, B0, B1, M><<<persistent_grid(k_mis<true, B0, B1, M>, n_active), FTN_TRACE_THREADS, 0, st>>>(sc, pa, q.q[Q_MIS], counts, d_trav + 4)))); }
             FTN_LAUNCHED();
 #if FTN_MIS_RESOLVE
             k_mis_resolve<<<shade_grid, 256, 0, st>>>(sc, pa, q.q[Q_MIS], counts);
