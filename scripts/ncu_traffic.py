@@ -24,7 +24,7 @@ hdr = r[0]
 iname, imetric, ivalue, iunit = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
 iid = hdr.index("ID")
 acc, launches = {}, set()
-pct = {}
+pct, dur = {}, {}
 seg, last_sep_id = -1 if sep_re else 0, None
 for row in r[1:]:
     if len(row) <= ivalue:
@@ -43,11 +43,15 @@ for row in r[1:]:
     scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1.0}.get(u, 1.0)
     m = row[imetric]
     if "pct" in m or "ratio" in m:
-        pct.setdefault(m, []).append(v)
+        pct.setdefault(m, []).append((row[iid], v))
     else:
         acc[m] = acc.get(m, 0.0) + v * scale
+        if m == "gpu__time_duration.sum":
+            dur[row[iid]] = v * scale
 n = max(1, len(launches))
-mean = {m: sum(v) / len(v) for m, v in pct.items()}
+# utilisations as DURATION-weighted means over the launches (the short late-bounce launches of a render would otherwise count
+# like the long first ones)
+mean = {m: sum(dur.get(i, 0.0) * v for i, v in vs) / max(sum(dur.get(i, 0.0) for i, _ in vs), 1e-30) for m, vs in pct.items()}
 lsu = mean.get("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", 0.0)
 issue = mean.get("sm__inst_issued.avg.pct_of_peak_sustained_active", 0.0)
 alu = mean.get("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", 0.0)
@@ -65,7 +69,7 @@ rec = {
     "dram_bytes_per_ray": (acc.get("dram__bytes_read.sum", 0.0) + acc.get("dram__bytes_write.sum", 0.0)) / total_rays,
     "launches_captured": n, "rays_captured": total_rays,
     "gpu_time_under_ncu_ms": acc.get("gpu__time_duration.sum", 0.0) * 1e3,
-    "pct_mean": {m: sum(v) / len(v) for m, v in pct.items()},
+    "pct_mean": mean,
     "commit": subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip(),
     "source": note,
 }
