@@ -315,7 +315,7 @@ struct ShadowSource {
         const uint32_t path = queue[k];
         ray->o = ld3(pa.sh_o, path); ray->d = ld3(pa.sh_d, path);
         ray->t_max = rn_sub(1.0f, 0.0001f);   // 1 - SHADOW_EPSILON, interaction.rs:10,55
-        ray->time = pa.ray_o[path].w;
+        ray->time = 0.0f;                     // carried by the reference's Ray, read by nothing on this path (no motion blur): not worth a sector
         return true;
     }
 };
@@ -342,7 +342,7 @@ struct MisSource {
     PathArrays pa; const uint32_t* queue;
     __device__ __forceinline__ bool load(uint32_t k, RayF* ray) const {
         const uint32_t path = queue[k];
-        ray->o = ld3(pa.mis_o, path); ray->d = ld3(pa.mis_d, path); ray->t_max = FTN_INF; ray->time = pa.ray_o[path].w;
+        ray->o = ld3(pa.mis_o, path); ray->d = ld3(pa.mis_d, path); ray->t_max = FTN_INF; ray->time = 0.0f;
         return true;
     }
 };
@@ -355,13 +355,16 @@ struct MisSource {
 #define FTN_MIS_RESOLVE 1
 #endif
 // FTN_MIS_MIN_BLOCKS (A/B, with FTN_MIS_RESOLVE = 0): cap k_mis's registers for that many resident blocks instead
+template <bool ENV_ONLY>
 struct MisSink {
     SceneView sc; PathArrays pa; const uint32_t* queue;
     __device__ __forceinline__ void store(bool valid, uint32_t k, const RayF& ray, const SceneHit& h) const {
         if (!valid) return;
         const uint32_t path = queue[k];
 #if FTN_MIS_RESOLVE
-        pa.hit[path] = h.slot;
+        // env lights only: a hit contributes nothing, and hit[path] still holds the (non-miss) slot this bounce was shaded at --
+        // only the misses are recorded
+        if (!ENV_ONLY || h.slot == FTN_NO_HIT_SLOT) pa.hit[path] = h.slot;
 #else
         const float4 w4 = pa.mis_w[path];
         const V3 incident = mis_incident(sc, sc.lights[f2u(w4.w)], ray, h.slot);
@@ -379,7 +382,7 @@ template <bool ENV_ONLY, bool COUNT, bool SPH, int MODE>
 __global__ void FTN_MIS_LAUNCH_BOUNDS
 k_mis(SceneView sc, PathArrays pa, const uint32_t* __restrict__ queue, uint32_t* __restrict__ counts, unsigned long long* __restrict__ trav) {
     MisSource src; src.pa = pa; src.queue = queue;
-    MisSink sink; sink.sc = sc; sink.pa = pa; sink.queue = queue;
+    MisSink<ENV_ONLY> sink; sink.sc = sc; sink.pa = pa; sink.queue = queue;
     TraceCounters tc; tc.nodes = 0; tc.tris = 0;
     trace_persistent<ENV_ONLY, COUNT, SPH, MODE>(sc, counts[Q_MIS], &counts[W_MIS], src, sink, tc);
     if (COUNT) flush_trace_counters(tc, trav);
@@ -390,9 +393,17 @@ k_mis_resolve(SceneView sc, PathArrays pa, const uint32_t* __restrict__ queue, c
     const uint32_t n = counts[Q_MIS];
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const uint32_t path = queue[k];
+        const uint32_t slot = pa.hit[path];
         const float4 w4 = pa.mis_w[path];
-        RayF ray; ray.o = ld3(pa.mis_o, path); ray.d = ld3(pa.mis_d, path); ray.t_max = FTN_INF; ray.time = pa.ray_o[path].w;
-        const V3 incident = mis_incident(sc, sc.lights[f2u(w4.w)], ray, pa.hit[path]);
+        const LightData& light = sc.lights[f2u(w4.w)];
+        V3 incident;
+        if (light.type == 0) {                         // infinite light: only a miss sees it, and only the direction matters
+            if (slot != FTN_NO_HIT_SLOT) continue;
+            incident = env_emitted(light.env, ld3(pa.mis_d, path));
+        } else {
+            RayF ray; ray.o = ld3(pa.mis_o, path); ray.d = ld3(pa.mis_d, path); ray.t_max = FTN_INF; ray.time = 0.0f;
+            incident = mis_incident(sc, light, ray, slot);
+        }
         if (!is_black(incident)) st3(pa.L, path, ld3(pa.L, path) + V3(w4.x, w4.y, w4.z) * incident);
     }
 }
