@@ -42,12 +42,13 @@ for row in r[1:]:
     u = row[iunit]
     scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1.0}.get(u, 1.0)
     m = row[imetric]
-    if "pct" in m or "ratio" in m:
+    if m == "gpu__time_duration.sum":          # ("du-ratio-n" is not a ratio)
+        dur[row[iid]] = v * scale
+        acc[m] = acc.get(m, 0.0) + v * scale
+    elif "pct" in m or m.endswith(".ratio"):
         pct.setdefault(m, []).append((row[iid], v))
     else:
         acc[m] = acc.get(m, 0.0) + v * scale
-        if m == "gpu__time_duration.sum":
-            dur[row[iid]] = v * scale
 n = max(1, len(launches))
 # utilisations as DURATION-weighted means over the launches (the short late-bounce launches of a render would otherwise count
 # like the long first ones)
