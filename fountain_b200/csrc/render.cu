@@ -209,72 +209,76 @@ k_shade_miss(SceneView sc, PassParams pp, PathArrays pa, const uint32_t* __restr
 #define FTN_SHADE_LAUNCH_BOUNDS __launch_bounds__(128, FTN_SHADE_MIN_BLOCKS)
 // IMG: the scene holds an image texture -- only then is the mip lookup (and its call frame) compiled into the
 // matte / plastic / Oren-Nayar shaders, so scenes without one run the kernels they always ran
-// Software pipeline over the queue (FTN_SHADE_PREFETCH) -- an A/B experiment, measured and left OFF.  The shaders are
-// latency-bound at 4 blocks per SM: ncu's source page (profiles/r02_ncu_c4_shade_source.txt) puts 35-40 % of k_shade<metal>'s
-// stall samples on the head and the tail of the loop body -- queue[k] -> path -> six scattered state arrays -> the triangle
-// record, and the late uses of beta / L -- long-scoreboard waits on a chain that does not depend on the shading itself.
-// Levels: 1 = queue entries loaded three iterations ahead; 2 = + prefetch of the path state two iterations ahead; 3 = + the
-// triangle record of the next path.  B200 (profiles/r02_ab_shade_prefetch.txt): level 1 changes nothing (3.94 ms per launch on
-// C4), levels 2 / 3 cost 8 % on C4 (4.26 ms, L1 or L2 alike -- a prefetch moves whole lines where the loads move 32-byte
-// sectors, and the kernel already draws 24 % of the DRAM peak) and gain 5 % on the cache-resident C2.
-#ifndef FTN_SHADE_PREFETCH
-#define FTN_SHADE_PREFETCH 0
+// The head of the shader's dependent-load chain.  The shaders are latency-bound at 4 blocks per SM: ncu's source page
+// (profiles/r02_ncu_c4_shade_source.txt) puts 35-40 % of k_shade<metal>'s stall samples on queue[k] -> path -> the scattered
+// state arrays -> the triangle record, long-scoreboard waits on a chain that does not depend on the shading itself.
+//   * prefetch.global.L1 / .L2 of the next paths' state (round-2 experiment, removed): -8 % on C4 -- a prefetch moves whole
+//     lines where the loads move 32-byte sectors and the kernel already draws 24 % of the DRAM peak
+//     (profiles/r02_ab_shade_prefetch.txt);
+//   * FTN_SHADE_STAGE = 1 (A/B, measured, left OFF): the queue entry is loaded two iterations ahead (one register) and the
+//     NEXT path's state (ray origin / direction, beta, hit slot, state word: 56 B) is copied global -> shared with cp.async
+//     while the current path is shaded -- sector-granular like a load, no registers held across the shading body, no warp
+//     stalled on it; two 7-KB buffers per block of 128 threads (each thread reads and refills only its own slots: no
+//     barrier).  B200 (profiles/r02_ab_shade_prefetch.txt): +7 % on C2's Lambert shader (0.251 -> 0.234 ms per launch), -4.5 %
+//     on C4 (3.75 -> 3.92 ms): with the image light the shader's time goes to scattered L2 / DRAM sectors of the 48 MB of
+//     environment tables, and the 56 KB of shared memory per SM come out of the L1 that caches them.
+#ifndef FTN_SHADE_STAGE
+#define FTN_SHADE_STAGE 0
 #endif
-#ifndef FTN_SHADE_PREFETCH_L2
-#define FTN_SHADE_PREFETCH_L2 0
-#endif
-#if FTN_SHADE_PREFETCH_L2
-__device__ __forceinline__ void prefetch_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-#else
-__device__ __forceinline__ void prefetch_line(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-#endif
-__device__ __forceinline__ void prefetch_path_state(const PathArrays& pa, uint32_t path) {
-    prefetch_line(pa.ray_o + path); prefetch_line(pa.ray_d + path); prefetch_line(pa.beta + path); prefetch_line(pa.L + path);
-    prefetch_line(pa.hit + path); prefetch_line(pa.state + path);
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
 }
-__device__ __forceinline__ void prefetch_hit_record(const SceneView& sc, uint32_t slot) {
-    if (slot == FTN_NO_HIT_SLOT || (slot & FTN_SPHERE_SLOT_FLAG)) return;
-    const F4* t = sc.bvh.tris + (size_t)FTN_TRI_F4 * (size_t)slot;
-    prefetch_line(t); prefetch_line(t + 2);
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+struct ShadeStage { float4 ray_o[128], ray_d[128], beta[128]; uint32_t hit[128], state[128]; };
+__device__ __forceinline__ void stage_path_state(ShadeStage& st, const PathArrays& pa, uint32_t path) {
+    const int t = threadIdx.x;
+    cp_async16(&st.ray_o[t], pa.ray_o + path); cp_async16(&st.ray_d[t], pa.ray_d + path); cp_async16(&st.beta[t], pa.beta + path);
+    cp_async4(&st.hit[t], pa.hit + path); cp_async4(&st.state[t], pa.state + path);
 }
 template <int QUEUE, bool IMG = false>
 __global__ void FTN_SHADE_LAUNCH_BOUNDS
 k_shade(SceneView sc, PassParams pp, PathArrays pa, const uint32_t* __restrict__ queue, Queues qs, uint32_t* __restrict__ counts, uint32_t* __restrict__ err) {
     const uint32_t n = counts[QUEUE];
     const uint32_t n32 = (n + 31u) & ~31u;
-    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t stride = gridDim.x * blockDim.x;   // n < 2^31 and stride < 2^23: k + 2 stride does not wrap
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-#if FTN_SHADE_PREFETCH
+#if FTN_SHADE_STAGE
+    __shared__ ShadeStage stage[2];
     uint32_t p0 = k < n ? queue[k] : 0u;                               // this iteration's path
-    uint32_t p1 = k + stride < n ? queue[k + stride] : 0u;            // n < 2^31 and stride < 2^23: no wrap below 2^32
-    uint32_t p2 = k + 2u * stride < n ? queue[k + 2u * stride] : 0u;
-#if FTN_SHADE_PREFETCH >= 2
-    if (k + stride < n) prefetch_path_state(pa, p1);
-#endif
+    uint32_t p1 = k + stride < n ? queue[k + stride] : 0u;            // the next one
+    int buf = 0;
+    if (k < n) stage_path_state(stage[0], pa, p0);
+    cp_async_commit();
 #endif
     for (; k < n32; k += stride) {
         int t_active = -1, t_shadow = -1, t_mis = -1;
         uint32_t path = 0;
-#if FTN_SHADE_PREFETCH
-        const uint32_t k1 = k + stride, k2 = k + 2u * stride, k3 = k + 3u * stride;
-        const uint32_t p3 = k3 < n ? queue[k3] : 0u;                     // lands while this path is shaded
-#if FTN_SHADE_PREFETCH >= 2
-        if (k2 < n) prefetch_path_state(pa, p2);
-#endif
-#if FTN_SHADE_PREFETCH >= 3
-        if (k1 < n) prefetch_hit_record(sc, pa.hit[p1]);                 // p1's state was prefetched one iteration ago
-#endif
-        (void)k1; (void)k2;
+#if FTN_SHADE_STAGE
+        const uint32_t k1 = k + stride, k2 = k + 2u * stride;
+        const uint32_t p2 = k2 < n ? queue[k2] : 0u;                     // lands while this path is shaded
+        cp_async_wait_all();                                             // this path's state (issued one iteration ago)
+        const float4 s_o = stage[buf].ray_o[threadIdx.x], s_d = stage[buf].ray_d[threadIdx.x], s_b = stage[buf].beta[threadIdx.x];
+        const uint32_t s_hit = stage[buf].hit[threadIdx.x], s_state = stage[buf].state[threadIdx.x];
+        if (k1 < n) stage_path_state(stage[buf ^ 1], pa, p1);           // the next path's, into the other buffer
+        cp_async_commit();
 #endif
         if (k < n) {
-#if FTN_SHADE_PREFETCH
+#if FTN_SHADE_STAGE
             path = p0;
+            RayF ray; ray.o = V3(s_o.x, s_o.y, s_o.z); ray.d = V3(s_d.x, s_d.y, s_d.z); ray.t_max = s_d.w; ray.time = s_o.w;
+            const uint32_t slot = s_hit, state = s_state;
+            const V3 beta = V3(s_b.x, s_b.y, s_b.z);
 #else
             path = queue[k];
-#endif
             const RayF ray = load_ray(pa, path);
+            const uint32_t slot = pa.hit[path], state = pa.state[path];
+            const V3 beta = ld3(pa.beta, path);
+#endif
             ShadeOut o;
-            const uint32_t state = pa.state[path];
             RayDiff cd; const RayDiff* carried = nullptr;
             if (IMG && pa.diff[0] && (state & FTN_STATE_HAS_DIFF)) {
                 cd.rx_o = ld3(pa.diff[0], path); cd.rx_d = ld3(pa.diff[1], path); cd.ry_o = ld3(pa.diff[2], path); cd.ry_d = ld3(pa.diff[3], path);
@@ -282,7 +286,7 @@ k_shade(SceneView sc, PassParams pp, PathArrays pa, const uint32_t* __restrict__
             }
             // L enters as 0: the stage only ADDS the hit's own emission (beta * Le), so the path's radiance is read and
             // written back only where that is not black -- L_old + (0 + beta Le) is the sum the reference forms
-            shade_surface<QUEUE == Q_NULL ? -1 : QUEUE - Q_MAT0, IMG>(sc, pp, path, ray, pa.hit[path], state, ld3(pa.beta, path), v3s(0.0f), &o, err, carried);
+            shade_surface<QUEUE == Q_NULL ? -1 : QUEUE - Q_MAT0, IMG>(sc, pp, path, ray, slot, state, beta, v3s(0.0f), &o, err, carried);
             if (IMG && o.has_diff) {
                 if (pa.diff[0]) { st3(pa.diff[0], path, o.diff.rx_o); st3(pa.diff[1], path, o.diff.rx_d); st3(pa.diff[2], path, o.diff.ry_o); st3(pa.diff[3], path, o.diff.ry_d); }
                 else o.state &= ~FTN_STATE_HAS_DIFF;
@@ -302,8 +306,8 @@ k_shade(SceneView sc, PassParams pp, PathArrays pa, const uint32_t* __restrict__
             }
         }
         queue_push3(qs, counts, t_active >= 0, t_shadow >= 0, t_mis >= 0, path);
-#if FTN_SHADE_PREFETCH
-        p0 = p1; p1 = p2; p2 = p3;
+#if FTN_SHADE_STAGE
+        p0 = p1; p1 = p2; buf ^= 1;
 #endif
     }
 }
