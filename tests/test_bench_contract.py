@@ -24,8 +24,12 @@ def test_committed_bench_line_has_the_contract_keys():
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0
     assert d["e2e"]["value"] != d["value"] and d["gpu_launches"] > 0
     r = d["roofline"]
-    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] == "l1" and r["unit"] == "GB/s"
-    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["frac"] <= 1.2
+    # the stated roof is the limiter ncu measured for this workload's kernel (profiles/traffic.json): instruction issue for the
+    # BVH8q traversal; the L1 / L2 / HBM figures of the same algorithmic bytes stand beside it, traffic = ncu's DRAM bytes
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "l1", "l2", "hbm", "ncu"} <= set(r)
+    assert r["bound"].startswith("sm-issue") and r["unit"] == "Gwarp-inst/s" and r["traffic"] is not None and r["ncu"]["commit"]
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["frac"] <= 1.0
+    assert r["hbm"]["peak"] > 0 and r["l1"]["frac"] <= 1.0
     c = d["cpu_baseline"]
     assert {"value", "unit", "cores", "kind", "sample"} <= set(c) and c["kind"] == "port" and c["cores"] >= 1
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
