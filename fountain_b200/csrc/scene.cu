@@ -19,6 +19,7 @@
 #include <cstdlib>
 #define FTN_REFILL_THRESHOLD_DEFAULT 16
 #define FTN_VOTE_BIAS_DEFAULT 14
+#define FTN_VOTE_BIAS_WIDE_DEFAULT 28
 #define FTN_VOTE_MIN_TRIS 65536u
 #define FTN_PLOC_MIN_TRIS 65536u
 #define FTN_WIDE_MIN_TRIS 65536u
@@ -449,8 +450,10 @@ SceneView make_view(const FtnScene& s) {
     v.n_tris = s.n_tris;
     static const int thr = [] { const char* e = getenv("FTN_REFILL_THRESHOLD"); int t = e ? atoi(e) : FTN_REFILL_THRESHOLD_DEFAULT; return t < 1 ? 1 : (t > 32 ? 32 : t); }();
     v.refill_threshold = thr;
-    static const int bias = [] { const char* e = getenv("FTN_VOTE_BIAS"); int t = e ? atoi(e) : FTN_VOTE_BIAS_DEFAULT; return t < 1 ? 1 : (t > 256 ? 256 : t); }();
-    v.vote_bias = bias;
+    // node step wins the per-step vote when 16 * #node lanes >= bias * #leaf lanes.  BVH8q (final code, 8 blocks per SM,
+    // profiles/r02_ab_vote_bias.txt): 28 against 14 gives C4 +1.3 %, C3 coherent +4.4 %, incoherent diffuse +3.6 %
+    static const int bias_env = [] { const char* e = getenv("FTN_VOTE_BIAS"); int t = e ? atoi(e) : 0; return t < 0 ? 0 : (t > 256 ? 256 : t); }();
+    v.vote_bias = bias_env ? bias_env : (s.wide ? FTN_VOTE_BIAS_WIDE_DEFAULT : FTN_VOTE_BIAS_DEFAULT);
     // measured (profiles/r01_ab_vote_ldg256.txt): the vote pays on deep trees (1M triangles: +6..9 %) and costs
     // on shallow ones (4332 triangles: -9 %), where its per-step bookkeeping is not amortised
     static const int vote_env = [] { const char* e = getenv("FTN_TRAVERSE_VOTE"); return e ? atoi(e) : -1; }();
