@@ -404,6 +404,9 @@ FTN_API int ftn_film_to_rgb_device(size_t n, const FtnPixel* d_pixels, float* d_
 
 /* The library keeps one grow-only device arena per GPU for the wavefront path state (sized by the
  * largest render so far) so that renders -- also of newly created scenes -- allocate nothing.
+ * A render works in passes of up to 64 Mi paths (220 B per path: 14.8 GB of a B200's 180 GB); when
+ * the arena has to grow, the pass is halved until it fits in 3/4 of the device's free memory, so
+ * a GPU that is shared or holds a very large scene still renders (FTN_PATHS_PER_PASS overrides).
  * This returns that memory to the driver; the next render allocates again. */
 FTN_API int ftn_release_cached_memory(void);
 
