@@ -114,15 +114,21 @@ FTN_HD V3 scene_env_radiance(const SceneView& sc, V3 dir) {
 }
 
 // ---- uniform_sample_one_light + estimate_direct (integrator/mod.rs:289-395) ------------------------------
+// The two rays estimate_direct spawns.  A SINK receives each of them as soon as it is known: the default one (DirectOut, used by
+// the host harness of the tests) just keeps them; the kernels' sink writes them straight into the path's shadow / MIS slots, so
+// their 18 floats are not live across the continuation sampling that follows (the shaders run at a 128-register cap).
 struct DirectOut {
     bool has_shadow; V3 sh_o, sh_d, sh_L;
     bool has_mis; V3 mis_o, mis_d, mis_w; int mis_light;
+    FTN_HD void reset() { has_shadow = false; has_mis = false; }
+    FTN_HD void shadow(V3 o, V3 d, V3 L) { has_shadow = true; sh_o = o; sh_d = d; sh_L = L; }
+    FTN_HD void mis(V3 o, V3 d, V3 w, int light) { has_mis = true; mis_o = o; mis_d = d; mis_w = w; mis_light = light; }
 };
 
-template <int MAT>
+template <int MAT, class Sink>
 FTN_HD void sample_direct(const SceneView& sc, const Surface& s, const Bsdf& bsdf, V3 scale,
-                          uint64_t key, uint32_t dim0, DirectOut* out, uint32_t* err) {
-    out->has_shadow = false; out->has_mis = false;
+                          uint64_t key, uint32_t dim0, Sink* out, uint32_t* err) {
+    out->reset();
     const uint32_t n_lights = sc.n_lights;
     if (n_lights == 0u) return;
     const float pick = sampler_uniform(key, dim0) * (float)n_lights;
@@ -177,8 +183,7 @@ FTN_HD void sample_direct(const SceneView& sc, const Surface& s, const Bsdf& bsd
             const V3 origin = offset_ray_origin(s.p, s.p_err, s.n, x_sub(p1, s.p));
             const V3 target = offset_ray_origin(p1, p1_err, p1_n, x_sub(origin, p1));
             const float w = (light.type == 2 || light.type == 3) ? 1.0f : power_heuristic1(pdf, spdf);   // delta lights: f * Li / pdf (:331-332)
-            out->has_shadow = true; out->sh_o = origin; out->sh_d = x_sub(target, origin);
-            out->sh_L = scale * (nl * (f * Li * w / pdf));
+            out->shadow(origin, x_sub(target, origin), scale * (nl * (f * Li * w / pdf)));
         }
     }
     // --- BSDF sample ---
@@ -193,8 +198,7 @@ FTN_HD void sample_direct(const SceneView& sc, const Surface& s, const Bsdf& bsd
         else lpdf = sphere_pdf_from_ref(sc.spheres[light.sphere], s, bs.wi);
         if (lpdf == 0.0f) return;
         const float w = power_heuristic1(bs.pdf, lpdf);
-        out->has_mis = true; out->mis_o = spawn_origin(s, bs.wi); out->mis_d = bs.wi;
-        out->mis_w = scale * (nl * (f * w / bs.pdf)); out->mis_light = (int)li;
+        out->mis(spawn_origin(s, bs.wi), bs.wi, scale * (nl * (f * w / bs.pdf)), (int)li);
     }
 }
 
@@ -258,11 +262,12 @@ FTN_HD_COLD RayDiff reflect_differential(const SceneView& sc, uint32_t slot, con
 // MAT = the material class of the queue this path sits in (FtnMaterialType), or -1 for the
 // null-BSDF queue.
 // `carried`: the differential a specular reflection left on the path (direct-lighting integrator, FTN_STATE_HAS_DIFF), or null.
-template <int MAT, bool IMG = true>
-FTN_HD void shade_surface(const SceneView& sc, const PassParams& pp, uint32_t path, const RayF& ray, uint32_t slot,
-                          uint32_t state, V3 beta, V3 L, ShadeOut* out, uint32_t* err, const RayDiff* carried = nullptr) {
+// `direct`: the sink of the two rays of estimate_direct (see DirectOut); the convenience overload below keeps them in out->direct.
+template <int MAT, bool IMG, class Sink>
+FTN_HD void shade_surface_to(const SceneView& sc, const PassParams& pp, uint32_t path, const RayF& ray, uint32_t slot,
+                             uint32_t state, V3 beta, V3 L, ShadeOut* out, Sink* direct, uint32_t* err, const RayDiff* carried = nullptr) {
     out->L = L; out->beta = beta; out->state = state; out->alive = false;
-    out->direct.has_shadow = false; out->direct.has_mis = false;
+    direct->reset();
     out->has_diff = false;
     Surface s;
     if (!surface_at_hit(sc, slot, ray, &s)) return;
@@ -307,7 +312,7 @@ FTN_HD void shade_surface(const SceneView& sc, const PassParams& pp, uint32_t pa
     // under the direct-lighting integrator `bounces` is the recursion depth of specular_reflect
     const uint32_t dim0 = DIM_CAMERA + (uint32_t)DIM_PER_BOUNCE * (uint32_t)bounces;
     if (direct_only || bsdf_num_components<M>(bsdf, BXDF_ALL & ~BXDF_SPECULAR) > 0)   // path.rs:60 guards; direct_lighting.rs:79 does not
-        sample_direct<M>(sc, s, bsdf, beta, key, dim0, &out->direct, err);
+        sample_direct<M>(sc, s, bsdf, beta, key, dim0, direct, err);
     if (direct_only) {
         // specular_reflect (integrator/mod.rs:40-103): follow the mirror direction with depth + 1;
         // the recursion is a chain, so it continues this path with beta *= f |wi.n| / pdf
@@ -338,6 +343,12 @@ FTN_HD void shade_surface(const SceneView& sc, const PassParams& pp, uint32_t pa
     }
     out->alive = true; out->next_o = spawn_origin(s, cs.wi); out->next_d = cs.wi;
     out->beta = beta; out->state = spec | (uint32_t)(bounces + 1);
+}
+
+template <int MAT, bool IMG = true>
+FTN_HD void shade_surface(const SceneView& sc, const PassParams& pp, uint32_t path, const RayF& ray, uint32_t slot,
+                          uint32_t state, V3 beta, V3 L, ShadeOut* out, uint32_t* err, const RayDiff* carried = nullptr) {
+    shade_surface_to<MAT, IMG>(sc, pp, path, ray, slot, state, beta, L, out, &out->direct, err, carried);
 }
 
 // Radiance arriving along an MIS (BSDF-sampled) ray, integrator/mod.rs:364-389.

@@ -239,6 +239,15 @@ __device__ __forceinline__ void stage_path_state(ShadeStage& st, const PathArray
     cp_async16(&st.ray_o[t], pa.ray_o + path); cp_async16(&st.ray_d[t], pa.ray_d + path); cp_async16(&st.beta[t], pa.beta + path);
     cp_async4(&st.hit[t], pa.hit + path); cp_async4(&st.state[t], pa.state + path);
 }
+// The kernels' sink of estimate_direct's two rays (ftn_path.cuh DirectOut): straight into the path's shadow / MIS slots
+struct PathDirectSink {
+    PathArrays pa; uint32_t path; bool has_shadow, has_mis;
+    __device__ __forceinline__ void reset() { has_shadow = false; has_mis = false; }
+    __device__ __forceinline__ void shadow(V3 o, V3 d, V3 L) { has_shadow = true; st3(pa.sh_o, path, o); st3(pa.sh_d, path, d); st3(pa.sh_L, path, L); }
+    __device__ __forceinline__ void mis(V3 o, V3 d, V3 w, int light) {
+        has_mis = true; st3(pa.mis_o, path, o); st3(pa.mis_d, path, d); st3(pa.mis_w, path, w, u2f((uint32_t)light));
+    }
+};
 template <int QUEUE, bool IMG = false>
 __global__ void FTN_SHADE_LAUNCH_BOUNDS
 k_shade(SceneView sc, PassParams pp, PathArrays pa, const uint32_t* __restrict__ queue, Queues qs, uint32_t* __restrict__ counts, uint32_t* __restrict__ err) {
@@ -286,17 +295,15 @@ k_shade(SceneView sc, PassParams pp, PathArrays pa, const uint32_t* __restrict__
             }
             // L enters as 0: the stage only ADDS the hit's own emission (beta * Le), so the path's radiance is read and
             // written back only where that is not black -- L_old + (0 + beta Le) is the sum the reference forms
-            shade_surface<QUEUE == Q_NULL ? -1 : QUEUE - Q_MAT0, IMG>(sc, pp, path, ray, slot, state, beta, v3s(0.0f), &o, err, carried);
+            PathDirectSink ds; ds.pa = pa; ds.path = path;
+            shade_surface_to<QUEUE == Q_NULL ? -1 : QUEUE - Q_MAT0, IMG>(sc, pp, path, ray, slot, state, beta, v3s(0.0f), &o, &ds, err, carried);
             if (IMG && o.has_diff) {
                 if (pa.diff[0]) { st3(pa.diff[0], path, o.diff.rx_o); st3(pa.diff[1], path, o.diff.rx_d); st3(pa.diff[2], path, o.diff.ry_o); st3(pa.diff[3], path, o.diff.ry_d); }
                 else o.state &= ~FTN_STATE_HAS_DIFF;
             }
             if (!is_black(o.L)) st3(pa.L, path, ld3(pa.L, path) + o.L);
-            if (o.direct.has_shadow) { st3(pa.sh_o, path, o.direct.sh_o); st3(pa.sh_d, path, o.direct.sh_d); st3(pa.sh_L, path, o.direct.sh_L); t_shadow = Q_SHADOW; }
-            if (o.direct.has_mis) {
-                st3(pa.mis_o, path, o.direct.mis_o); st3(pa.mis_d, path, o.direct.mis_d);
-                st3(pa.mis_w, path, o.direct.mis_w, u2f((uint32_t)o.direct.mis_light)); t_mis = Q_MIS;
-            }
+            if (ds.has_shadow) t_shadow = Q_SHADOW;
+            if (ds.has_mis) t_mis = Q_MIS;
             if (o.alive) {
                 st3(pa.ray_o, path, o.next_o, ray.time);
                 st3(pa.ray_d, path, o.next_d, FTN_INF);
