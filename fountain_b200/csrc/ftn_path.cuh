@@ -121,6 +121,7 @@ struct DirectOut {
     bool has_shadow; V3 sh_o, sh_d, sh_L;
     bool has_mis; V3 mis_o, mis_d, mis_w; int mis_light;
     FTN_HD void reset() { has_shadow = false; has_mis = false; }
+    FTN_HD void emitted(V3) {}                                            // the caller reads ShadeOut::L
     FTN_HD void shadow(V3 o, V3 d, V3 L) { has_shadow = true; sh_o = o; sh_d = d; sh_L = L; }
     FTN_HD void mis(V3 o, V3 d, V3 w, int light) { has_mis = true; mis_o = o; mis_d = d; mis_w = w; mis_light = light; }
 };
@@ -274,8 +275,11 @@ FTN_HD void shade_surface_to(const SceneView& sc, const PassParams& pp, uint32_t
     const int bounces = (int)(state & FTN_STATE_BOUNCES);
     const bool direct_only = pp.integrator == FTN_INTEGRATOR_DIRECT_LIGHTING;
     // emitted light at the intersection: path.rs:45-51 / direct_lighting.rs:71
-    if (s.light >= 0 && (direct_only || bounces == 0 || (state & FTN_STATE_SPECULAR)))
-        L = L + beta * area_emitted(sc.lights[s.light], s.n, direct_only ? s.wo : x_neg(ray.d));
+    if (s.light >= 0 && (direct_only || bounces == 0 || (state & FTN_STATE_SPECULAR))) {
+        const V3 e = beta * area_emitted(sc.lights[s.light], s.n, direct_only ? s.wo : x_neg(ray.d));
+        L = L + e;
+        direct->emitted(e);   // a sink that accumulates radiance itself takes it now (out->L is then dead weight it does not read)
+    }
     out->L = L;
     if (!direct_only && bounces >= pp.max_depth) return;   // path.rs:54
     if (MAT < 0) {

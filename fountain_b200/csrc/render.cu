@@ -243,6 +243,8 @@ __device__ __forceinline__ void stage_path_state(ShadeStage& st, const PathArray
 struct PathDirectSink {
     PathArrays pa; uint32_t path; bool has_shadow, has_mis;
     __device__ __forceinline__ void reset() { has_shadow = false; has_mis = false; }
+    // the hit's own emission (beta * Le): the path's radiance is read and written back only here, i.e. only where a hit emits
+    __device__ __forceinline__ void emitted(V3 e) { if (!is_black(e)) st3(pa.L, path, ld3(pa.L, path) + e); }
     __device__ __forceinline__ void shadow(V3 o, V3 d, V3 L) { has_shadow = true; st3(pa.sh_o, path, o); st3(pa.sh_d, path, d); st3(pa.sh_L, path, L); }
     __device__ __forceinline__ void mis(V3 o, V3 d, V3 w, int light) {
         has_mis = true; st3(pa.mis_o, path, o); st3(pa.mis_d, path, d); st3(pa.mis_w, path, w, u2f((uint32_t)light));
@@ -293,15 +295,13 @@ k_shade(SceneView sc, PassParams pp, PathArrays pa, const uint32_t* __restrict__
                 cd.rx_o = ld3(pa.diff[0], path); cd.rx_d = ld3(pa.diff[1], path); cd.ry_o = ld3(pa.diff[2], path); cd.ry_d = ld3(pa.diff[3], path);
                 carried = &cd;
             }
-            // L enters as 0: the stage only ADDS the hit's own emission (beta * Le), so the path's radiance is read and
-            // written back only where that is not black -- L_old + (0 + beta Le) is the sum the reference forms
+            // L enters as 0: the stage only ADDS the hit's own emission (beta * Le), which the sink adds to the path's radiance
             PathDirectSink ds; ds.pa = pa; ds.path = path;
             shade_surface_to<QUEUE == Q_NULL ? -1 : QUEUE - Q_MAT0, IMG>(sc, pp, path, ray, slot, state, beta, v3s(0.0f), &o, &ds, err, carried);
             if (IMG && o.has_diff) {
                 if (pa.diff[0]) { st3(pa.diff[0], path, o.diff.rx_o); st3(pa.diff[1], path, o.diff.rx_d); st3(pa.diff[2], path, o.diff.ry_o); st3(pa.diff[3], path, o.diff.ry_d); }
                 else o.state &= ~FTN_STATE_HAS_DIFF;
             }
-            if (!is_black(o.L)) st3(pa.L, path, ld3(pa.L, path) + o.L);
             if (ds.has_shadow) t_shadow = Q_SHADOW;
             if (ds.has_mis) t_mis = Q_MIS;
             if (o.alive) {
